@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""bench.py — scan-to-map GICP aligns/s (VLP-16 sweep vs 500k-point submap), BASELINE.json config C2.
+
+A "step" is what the odometry node does per LiDAR frame (rgc_slam/src/RGC_odometer.cpp:998-1011):
+a fresh FastGICP object, the call-site parameters (25 iterations, corr 2 m, trans eps 1e-6),
+setInputTarget(NEW 500k-point submap) + setInputSource(new sweep) + align(guess).  The target
+changes every frame at the reference call site, so every step is COLD: target voxel-hash build,
+k=20 kNN and covariances are inside the timed region (`warm` = target cached is reported beside it).
+
+  value : aligns/s, inputs already resident in HBM, device time (CUDA events on the library's
+          stream, summed over the K steps; L2 flushed between steps outside the events)
+  e2e   : aligns/s through the same public call with pinned HOST clouds: H2D of both clouds and
+          the D2H of the result are inside the timed (wall-clock) region
+  --impl reference : the CPU restatement of the reference's OpenMP FastGICP path (oracle/, the
+          reference itself cannot be built here) on the same workload, all host threads
+
+N > 1 (torchrun): independent registrations sharded across ranks, no collective in the data path
+(weak scaling); value = total aligns / max-over-ranks time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from rgc_slam_b200 import synth  # noqa: E402
+
+N_SUBMAP = 500_000
+CALL_SITE = dict(max_iterations=25, corr_dist=2.0, transformation_epsilon=1e-6)  # RGC_odometer.cpp:1000-1006
+N_PAIRS = 2  # distinct (sweep, submap) pairs cycled through
+
+
+def build_workload(rank: int, n_submap: int, n_pairs: int = N_PAIRS):
+    """Seeded synthetic stream: sweeps along a trajectory, submap = accumulation of the preceding
+    sweeps in the previous frame's coordinates, subsampled to exactly n_submap points."""
+    scene = synth.Scene.make(synth.BASE_SEED + 2000)
+    need = int(np.ceil(n_submap * 1.03 / 20000.0)) + 2
+    traj = synth.trajectory(need + n_pairs + 8 + rank, seed=2)
+    scans = {}
+
+    def scan(f):
+        if f not in scans:
+            scans[f] = synth.lidar_scan(scene, traj[f], seed=synth.BASE_SEED + 2000 + f)
+        return scans[f]
+
+    pairs = []
+    for p in range(n_pairs):
+        frame = need + p * 3 + rank
+        ref = traj[frame - 1]
+        chunks, total, f = [], 0, frame - 1
+        while total < n_submap * 1.02 and f >= 0:
+            sc = scan(f)
+            Tr = synth.relative_pose(traj[f], ref)
+            chunks.append((sc[:, :3].astype(np.float64) @ Tr[:3, :3].T + Tr[:3, 3]).astype(np.float32))
+            total += len(sc)
+            f -= 1
+        pts = np.concatenate(chunks, 0)
+        if len(pts) < n_submap:
+            raise RuntimeError("not enough points for the submap")
+        rng = np.random.Generator(np.random.PCG64(1234 + p + 100 * rank))
+        sel = np.sort(rng.permutation(len(pts))[:n_submap])
+        tgt = np.ones((n_submap, 4), np.float32)
+        tgt[:, :3] = pts[sel]
+        src = synth.to_xyz1(scan(frame))
+        # guess = previous frame-to-frame motion
+        guess = synth.relative_pose(traj[frame - 1], traj[frame - 2]).astype(np.float32)
+        truth = synth.relative_pose(traj[frame], traj[frame - 1])
+        pairs.append(dict(src=src, tgt=tgt, guess=guess, truth=truth))
+    return pairs
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu_index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def new_reg(rgc, ctx):
+    g = rgc.FastGICP(ctx)
+    g.setMaximumIterations(CALL_SITE["max_iterations"])
+    g.setMaxCorrespondenceDistance(CALL_SITE["corr_dist"])
+    g.setTransformationEpsilon(CALL_SITE["transformation_epsilon"])
+    g.setEuclideanFitnessEpsilon(1e-6)
+    g.setRANSACIterations(0)
+    g.setNumThreads(14)
+    return g
+
+
+def run_ours(args, rank, world):
+    import torch
+    import torch.distributed as dist
+    import rgc_slam_b200 as rgc
+
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pairs = build_workload(rank, args.submap_points)
+    ctx = rgc.Context(local)
+    ext = torch.cuda.ExternalStream(ctx.stream, device=local)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")  # > 126 MB L2
+
+    dev = [dict(src=torch.from_numpy(p["src"]).cuda(local), tgt=torch.from_numpy(p["tgt"]).cuda(local)) for p in pairs]
+    pin = [dict(src=torch.from_numpy(p["src"]).pin_memory(), tgt=torch.from_numpy(p["tgt"]).pin_memory()) for p in pairs]
+    torch.cuda.synchronize()
+
+    def step(i, clouds, fresh=True):
+        p = pairs[i % len(pairs)]
+        c = clouds[i % len(pairs)]
+        g = new_reg(rgc, ctx)
+        # a new tensor view per step = a new cloud identity, as at the reference call site
+        g.setInputTarget(c["tgt"][:] if fresh else c["tgt"])
+        g.setInputSource(c["src"][:] if fresh else c["src"])
+        T = g.align(p["guess"])
+        return g, T
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- value: device-resident inputs, CUDA events on the library's stream
+    for i in range(args.warmup):
+        step(i, dev)
+    stage_acc = {}
+    iters = []
+    sampler = ClockSampler(local)
+    launches0 = ctx.launch_count
+    barrier()
+    sampler.start()
+    dev_ms = 0.0
+    wall0 = time.perf_counter()
+    n_launch_timed = 0
+    for i in range(args.steps):
+        with torch.cuda.stream(ext):
+            flush.zero_()  # L2 flush between timed iterations (outside the event pair)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launch_count
+        e0.record(ext)
+        g, T = step(i, dev)
+        e1.record(ext)
+        e1.synchronize()
+        n_launch_timed += ctx.launch_count - l0
+        dev_ms += e0.elapsed_time(e1)
+        for k, v in g.stage_ms().items():
+            stage_acc[k] = stage_acc.get(k, 0.0) + v
+        iters.append(g.last_result["iterations"])
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max = float(t.item())
+    value = world * args.steps / (dev_ms_max / 1e3)
+
+    # ---------------- warm: target cached (same object), source changes
+    gw = new_reg(rgc, ctx)
+    gw.setInputTarget(dev[0]["tgt"])
+    gw.setInputSource(dev[0]["src"])
+    gw.align(pairs[0]["guess"])
+    warm_ms = 0.0
+    nwarm = max(3, min(args.steps, 10))
+    for i in range(nwarm):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        gw.setInputSource(dev[0]["src"][:])
+        gw.align(pairs[0]["guess"])
+        e1.record(ext)
+        e1.synchronize()
+        warm_ms += e0.elapsed_time(e1)
+    warm_ms /= nwarm
+
+    # ---------------- e2e: pinned host clouds through the public call, wall clock
+    for i in range(max(1, args.warmup // 2)):
+        step(i, pin)
+    barrier()
+    e2e_s = 0.0
+    for i in range(args.steps):
+        with torch.cuda.stream(ext):
+            flush.zero_()
+        ctx.synchronize()
+        t0 = time.perf_counter()
+        g, T = step(i, pin)
+        ctx.synchronize()
+        e2e_s += time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * args.steps / float(t.item())
+    n_src, n_tgt = len(pairs[0]["src"]), len(pairs[0]["tgt"])
+    h2d = 16 * (n_src + n_tgt)
+    res = g.last_result
+    d2h = 64 + (res["n_linearize"] * 29 + res["n_compute_error"]) * 8 + 296 * 24 * 2 + 22 * 4 * 2
+
+    # ---------------- per-kernel roofline (live CUDA-event stage times from the library)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    k = 20
+    st = {kk: v / args.steps for kk, v in stage_acc.items()}
+    knn_bytes = n_tgt * (16 + 4 * k)          # read own float4, write k int32 positions
+    cov_bytes = n_tgt * (16 + 4 * k + 48)     # + 6 fp64 out (fp64 covariances)
+    # one linearize / compute_error launch timed alone
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    Tg = pairs[0]["guess"].astype(np.float64)
+    gw.linearize(Tg)
+    lin_ms = ce_ms = 0.0
+    for _ in range(5):
+        e0.record(ext); gw.linearize(Tg); e1.record(ext); e1.synchronize(); lin_ms += e0.elapsed_time(e1) / 5
+        e0.record(ext); gw.compute_error(Tg); e1.record(ext); e1.synchronize(); ce_ms += e0.elapsed_time(e1) / 5
+    lin_bytes = n_src * (16 + 48 + 4 + 4 + 16 + 48 + 48)   # p, C_A, corr+d2 out, q, C_B gathers, M out
+    ce_bytes = n_src * (16 + 4 + 16 + 48)
+
+    def gbs(b, ms):
+        return b / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+
+    kernels = {
+        "k_knn<20,self> (target)": {"ms": st["tgt_knn"], "alg_bytes": knn_bytes, "GBps": gbs(knn_bytes, st["tgt_knn"]), "bound": "sm (see profiles/)"},
+        "k_covariance (target)": {"ms": st["tgt_cov"], "alg_bytes": cov_bytes, "GBps": gbs(cov_bytes, st["tgt_cov"]), "bound": "hbm"},
+        "k_linearize (1 launch + sync)": {"ms": lin_ms, "alg_bytes": lin_bytes, "GBps": gbs(lin_bytes, lin_ms), "bound": "latency at 1 scan"},
+        "k_compute_error (1 launch + sync)": {"ms": ce_ms, "alg_bytes": ce_bytes, "GBps": gbs(ce_bytes, ce_ms), "bound": "latency at 1 scan"},
+    }
+    dom = "k_knn<20,self> (target)"
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
+                "frac": kernels[dom]["GBps"] / peak, "traffic": None, "peak_source": peak_src,
+                "note": "dominant kernel is the k=20 kNN, which is SM/latency-bound (north_star: report SM throughput); "
+                        "HBM-bound kernels are listed under `kernels`; ncu summaries in profiles/",
+                "kernels": kernels}
+
+    # ---------------- CPU baseline (oracle port), rank 0, N=1 only, bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline(pairs, n_aligns=2)
+
+    if rank == 0:
+        Tt = pairs[(args.steps - 1) % len(pairs)]["truth"]
+        out = {
+            "metric": "scan-to-map GICP aligns/sec (VLP-16 vs 500k-pt map)", "value": value, "unit": "aligns/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64 (H/b, covariances) + f32 (points, kNN distances)", "data": "synthetic",
+            "config": {"workload": "C2: VLP-16 sweep vs 500k-point submap, cold target every step (new submap per frame as at "
+                                   "RGC_odometer.cpp:985-1009), call-site params 25 it / corr 2 m / trans_eps 1e-6, k=20 PLANE LM",
+                       "n_source": n_src, "n_target": n_tgt, "pairs_cycled": len(pairs), "l2": "flushed between steps (256 MB memset)",
+                       "sharding": "independent registrations per rank, no collective" if world > 1 else "single GPU"},
+            "e2e": {"value": e2e_value, "unit": "aligns/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "timing": "wall clock around setInputTarget+setInputSource+align with pinned host clouds"},
+            "gpu_launches": int(n_launch_timed),
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "warm_ms_per_align": warm_ms,
+            "stage_ms": st,
+            "lm_iterations_mean": float(np.mean(iters)),
+            "wall_s_timed_region": wall,
+            "pose_err_vs_truth_m": float(np.abs(T[:3, 3] - Tt[:3, 3]).max()),
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(pairs, n_aligns=2):
+    from oracle import oracle as orc
+    threads = orc.max_threads()
+    secs = []
+    for i in range(n_aligns):
+        p = pairs[i % len(pairs)]
+        o = orc.FastGICP(max_iterations=CALL_SITE["max_iterations"], corr_dist=CALL_SITE["corr_dist"],
+                         transformation_epsilon=CALL_SITE["transformation_epsilon"])
+        t0 = time.perf_counter()
+        o.setInputTarget(p["tgt"])   # kd-tree build (fast_gicp_impl.hpp:88)
+        o.setInputSource(p["src"])
+        o.align(p["guess"])          # lazy covariances + LM (fast_gicp_impl.hpp:103-112)
+        secs.append(time.perf_counter() - t0)
+    return {"value": 1.0 / float(np.mean(secs)), "unit": "aligns/s", "cores": threads, "kind": "port",
+            "sample": f"{n_aligns} cold aligns of the same C2 pairs (sweep vs {len(pairs[0]['tgt'])}-pt submap), OpenMP guided,8 on all "
+                      f"{threads} host threads; the reference call site asks for 14 threads (RGC_odometer.cpp:1006)",
+            "seconds_per_align": [float(s) for s in secs]}
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path: the OpenMP FastGICP restatement in oracle/
+    (the reference cannot be compiled in this image: no PCL/Eigen/FLANN)."""
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    pairs = build_workload(0, args.submap_points)
+    threads = orc.max_threads()
+
+    def step(i):
+        p = pairs[i % len(pairs)]
+        o = orc.FastGICP(max_iterations=CALL_SITE["max_iterations"], corr_dist=CALL_SITE["corr_dist"],
+                         transformation_epsilon=CALL_SITE["transformation_epsilon"])
+        o.setInputTarget(p["tgt"])
+        o.setInputSource(p["src"])
+        o.align(p["guess"])
+
+    for i in range(args.warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(i)
+    dt = time.perf_counter() - t0
+    v = args.steps / dt
+    n_src, n_tgt = len(pairs[0]["src"]), len(pairs[0]["tgt"])
+    out = {
+        "impl": "reference", "metric": "scan-to-map GICP aligns/sec (VLP-16 vs 500k-pt map)", "value": v, "unit": "aligns/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64 (H/b, covariances) + f32 (points, kNN distances)", "data": "synthetic",
+        "config": {"workload": "C2: VLP-16 sweep vs 500k-point submap, cold target every step, call-site params 25 it / corr 2 m / "
+                               "trans_eps 1e-6, k=20 PLANE LM", "n_source": n_src, "n_target": n_tgt, "pairs_cycled": len(pairs)},
+        "cpu_baseline": {"value": v, "unit": "aligns/s", "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} cold aligns, CPU restatement of the reference OpenMP FastGICP path, {threads} threads"},
+        "e2e": {"value": v, "unit": "aligns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--submap-points", type=int, default=N_SUBMAP)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        args.warmup = max(args.warmup, 3)
+        run_ours(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

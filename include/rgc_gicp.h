@@ -1,0 +1,146 @@
+/* rgc_gicp.h — C-ABI of the B200-native scan-matching path (librgc_gicp.so).
+ *
+ * Drop-in boundary for the reference's CPU FastGICP path.  Each entry point names the
+ * reference interface it replaces (paths under /root/reference/rgc_slam/):
+ *   FG  = include/fast_gicp/gicp/          FGI = include/fast_gicp/gicp/impl/
+ *   SRC = src/
+ * The C++ facade include/rgc/fast_gicp.hpp wraps these 1:1 behind the pcl::Registration-style
+ * names the odometry node calls (SRC/RGC_odometer.cpp:998-1011).
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 (rgc_status) on failure; rgc_last_error(ctx)
+ *     gives the message.  No exceptions, no torch types, caller-owned host memory in and out.
+ *   - 4x4 / 6x6 matrices are COLUMN-major (Eigen's default, so Eigen::Matrix4f::data() passes
+ *     straight through).  Covariances are arrays of column-major 4x4 doubles (Eigen::Matrix4d),
+ *     row/column 3 zero, exactly the reference's std::vector<Eigen::Matrix4d>.
+ *   - point clouds: pointer to the first point, count, byte stride; xyz are the first three
+ *     floats of every point (pcl::PointXYZ 16 B, PointXYZI 32 B, PointNormal 48 B —
+ *     SRC/fast_gicp/gicp/fast_gicp.cpp:4-6).  The homogeneous coordinate is taken as 1.
+ *   - there is NO CPU fallback: with no usable CUDA device rgc_ctx_create fails.
+ *   - one rgc_reg per host thread; a ctx may serve several regs sequentially.
+ */
+#ifndef RGC_GICP_H
+#define RGC_GICP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rgc_ctx rgc_ctx;
+typedef struct rgc_reg rgc_reg;
+
+typedef enum {
+  RGC_OK = 0,
+  RGC_ERR_CUDA = -1,        /* a CUDA call failed (message has the CUDA error string) */
+  RGC_ERR_INVALID = -2,     /* bad argument */
+  RGC_ERR_STATE = -3,       /* e.g. align() before both clouds are set */
+  RGC_ERR_UNSUPPORTED = -4, /* e.g. k_correspondences > 32 */
+  RGC_ERR_NOMEM = -5
+} rgc_status;
+
+/* FG/gicp_settings.hpp:6 */
+typedef enum { RGC_REG_NONE = 0, RGC_REG_MIN_EIG = 1, RGC_REG_NORMALIZED_MIN_EIG = 2, RGC_REG_PLANE = 3, RGC_REG_FROBENIUS = 4 } rgc_regularization;
+/* FG/lsq_registration.hpp:13 */
+typedef enum { RGC_OPT_GAUSS_NEWTON = 0, RGC_OPT_LEVENBERG_MARQUARDT = 1 } rgc_optimizer;
+
+/* Defaults = FGI/lsq_registration_impl.hpp:9-22 and FGI/fast_gicp_impl.hpp:8-23. */
+typedef struct {
+  int max_iterations;                /* pcl setMaximumIterations            (64)      */
+  double rotation_epsilon;           /* setRotationEpsilon                  (2e-3)    */
+  double transformation_epsilon;     /* pcl setTransformationEpsilon        (5e-4)    */
+  float max_correspondence_distance; /* pcl setMaxCorrespondenceDistance    (FLT_MAX) */
+  int k_correspondences;             /* setCorrespondenceRandomness         (20), <= 32 */
+  int regularization;                /* setRegularizationMethod             (PLANE)   */
+  int optimizer;                     /* lsq_optimizer_type_                 (LM)      */
+  int lm_max_iterations;             /* lm_max_iterations_                  (10)      */
+  double lm_init_lambda_factor;      /* setInitialLambdaFactor              (1e-9)    */
+  int lm_debug_print;                /* setDebugPrint                       (0)       */
+  float grid_cell;                   /* finest voxel edge of the kNN grid in metres; 0 = default (0.2) */
+} rgc_params;
+
+typedef struct {
+  int converged;            /* pcl hasConverged()                                   */
+  int iterations;           /* nr_iterations_ (FGI/lsq_registration_impl.hpp:66)    */
+  int n_linearize;          /* device linearize launches                            */
+  int n_compute_error;      /* device compute_error launches                        */
+  int n_inliers;            /* correspondences within max distance at the last linearize */
+  double final_error;       /* sum e^T M e at the last accepted linearize           */
+  double final_hessian[36]; /* getFinalHessian(), column-major                      */
+  float device_ms;          /* CUDA-event time of the whole align on the ctx stream */
+} rgc_result;
+
+/* ---- context: device, stream, pooled device memory, pinned result buffers ------------------ */
+int rgc_ctx_create(int device, rgc_ctx** out);
+int rgc_ctx_destroy(rgc_ctx* ctx);
+const char* rgc_last_error(const rgc_ctx* ctx);
+int rgc_ctx_synchronize(rgc_ctx* ctx);
+/* raw cudaStream_t of the context (so callers can record CUDA events on the launching stream) */
+void* rgc_ctx_stream(rgc_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t rgc_ctx_launch_count(const rgc_ctx* ctx);
+
+/* ---- registration object: fast_gicp::FastGICP<PointSource, PointTarget> (FG/fast_gicp.hpp:20) -- */
+int rgc_reg_create(rgc_ctx* ctx, rgc_reg** out); /* FastGICP() — cheap, tolerates per-frame create/destroy */
+int rgc_reg_destroy(rgc_reg* reg);
+void rgc_params_default(rgc_params* p);
+int rgc_reg_set_params(rgc_reg* reg, const rgc_params* p);
+int rgc_reg_get_params(const rgc_reg* reg, rgc_params* p);
+
+/* setInputSource / setInputTarget (FGI/fast_gicp_impl.hpp:72-91).  `identity_key` plays the role
+ * of the shared_ptr identity: non-zero and equal to the current key => early return, nothing is
+ * copied or recomputed; otherwise the cloud is uploaded, its search structure rebuilt and its
+ * covariances cleared (recomputed lazily inside align, FGI/fast_gicp_impl.hpp:104-109).  */
+int rgc_reg_set_source(rgc_reg* reg, const void* points, size_t n, size_t stride_bytes, uint64_t identity_key);
+int rgc_reg_set_target(rgc_reg* reg, const void* points, size_t n, size_t stride_bytes, uint64_t identity_key);
+/* same, but `points` is a DEVICE pointer (cloud already resident in HBM) */
+int rgc_reg_set_source_device(rgc_reg* reg, const void* d_points, size_t n, size_t stride_bytes, uint64_t identity_key);
+int rgc_reg_set_target_device(rgc_reg* reg, const void* d_points, size_t n, size_t stride_bytes, uint64_t identity_key);
+
+int rgc_reg_swap_source_and_target(rgc_reg* reg); /* FGI/fast_gicp_impl.hpp:49-57 */
+int rgc_reg_clear_source(rgc_reg* reg);           /* :59-63 */
+int rgc_reg_clear_target(rgc_reg* reg);           /* :65-69 */
+
+/* set/get{Source,Target}Covariances (FG/fast_gicp.hpp:62-72): n column-major 4x4 doubles */
+int rgc_reg_set_source_covs(rgc_reg* reg, const double* m4x4, size_t n);
+int rgc_reg_set_target_covs(rgc_reg* reg, const double* m4x4, size_t n);
+int rgc_reg_get_source_covs(rgc_reg* reg, double* m4x4, size_t n); /* computes them if missing */
+int rgc_reg_get_target_covs(rgc_reg* reg, double* m4x4, size_t n);
+
+/* pcl::Registration::align(output, guess) -> FastGICP::computeTransformation
+ * (FGI/fast_gicp_impl.hpp:103-112) -> LsqRegistration::computeTransformation
+ * (FGI/lsq_registration_impl.hpp:53-79).  guess may be NULL (identity).  out_points (nullable):
+ * n_source x 4 floats, the source transformed by the result (the `output` cloud).        */
+int rgc_reg_align(rgc_reg* reg, const float* guess16, float* final_T16, rgc_result* result, float* out_points);
+
+/* LsqRegistration::evaluateCost / linearize (FGI/lsq_registration_impl.hpp:48-51,
+ * FGI/fast_gicp_impl.hpp:155-211).  H (36, column-major) and b (6) may both be NULL.        */
+int rgc_reg_linearize(rgc_reg* reg, const double* T16, double* err, double* H36, double* b6);
+/* FastGICP::compute_error (FGI/fast_gicp_impl.hpp:214-237): correspondences and Mahalanobis
+ * matrices stay frozen from the last linearize.                                            */
+int rgc_reg_compute_error(rgc_reg* reg, const double* T16, double* err);
+/* correspondences_ / sq_distances_ of the last linearize, caller's index space (-1 = none;
+ * sq_dist is +inf where no target lies within max_correspondence_distance)                  */
+int rgc_reg_get_correspondences(rgc_reg* reg, int32_t* corr, float* sq_dist);
+
+/* pcl::Registration::getFitnessScore(max_range) with the final transformation of the last
+ * align (callers: SRC/RGC_odometer.cpp:1010, SRC/RGC_mapping.cpp:2070)                        */
+int rgc_reg_fitness(rgc_reg* reg, double max_range, double* score);
+int rgc_reg_get_final_transformation(const rgc_reg* reg, float* T16);
+
+/* pcl::search::KdTree::nearestKSearch for a batch of queries (exact; ascending by (d2, index)).
+ * idx/d2: m x k row-major; rows are padded with -1 / +inf when k > n.  Test hook + public op. */
+int rgc_knn(rgc_ctx* ctx, const void* points, size_t n, size_t stride_bytes, const void* queries, size_t m, size_t qstride_bytes, int k,
+            int32_t* idx, float* d2, float grid_cell);
+
+/* per-stage device times (ms, CUDA events) of the last set_source / set_target / align on this reg:
+ * [0] source build (ingest+sort+tables) [1] source kNN [2] source cov [3] target build
+ * [4] target kNN [5] target cov [6] LM loop (all linearize/compute_error incl. host turnarounds) */
+int rgc_reg_stage_ms(const rgc_reg* reg, float* ms7);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RGC_GICP_H */

@@ -1,0 +1,112 @@
+// rgc_common.cuh — shared definitions for the B200 scan-matching kernels.
+//
+// Everything marked RGC_HD is plain arithmetic that compiles both for sm_100a (nvcc) and for
+// the host (g++).  The host build exists ONLY for tests/hostsim (a CPU simulation of the
+// kernels' per-thread logic, so the search / algebra can be checked against the oracle in a
+// container without a GPU).  The product library never runs these functions on the CPU.
+#pragma once
+#include <cstdint>
+#include <cmath>
+#include <cstring>
+
+#if defined(__CUDACC__)
+#define RGC_HD __host__ __device__ __forceinline__
+#define RGC_D __device__ __forceinline__
+#else
+#define RGC_HD inline
+#define RGC_D inline
+#endif
+
+namespace rgc {
+
+// ---- float arithmetic with pinned rounding (no FMA contraction) -------------------------------
+// The reference's float expressions (flann::L2_Simple distance, Isometry3f * Vector4f,
+// scanRegistration.cpp curvature sums) are evaluated on x86-64 without FMA; kNN indices and
+// feature labels must be bit-exact, so every float product/sum on those paths goes through
+// these helpers (round-to-nearest, never fused).
+RGC_HD float fmul(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fmul_rn(a, b);
+#else
+  return a * b;
+#endif
+}
+RGC_HD float fadd(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fadd_rn(a, b);
+#else
+  return a + b;
+#endif
+}
+RGC_HD float fsub(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fsub_rn(a, b);
+#else
+  return a - b;
+#endif
+}
+RGC_HD double dmul(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __dmul_rn(a, b);
+#else
+  return a * b;
+#endif
+}
+RGC_HD double dadd(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __dadd_rn(a, b);
+#else
+  return a + b;
+#endif
+}
+RGC_HD double dsub(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __dsub_rn(a, b);
+#else
+  return a - b;
+#endif
+}
+
+RGC_HD int f2i_bits(float f) {
+#if defined(__CUDA_ARCH__)
+  return __float_as_int(f);
+#else
+  int i;
+  std::memcpy(&i, &f, 4);
+  return i;
+#endif
+}
+RGC_HD float i2f_bits(int i) {
+#if defined(__CUDA_ARCH__)
+  return __int_as_float(i);
+#else
+  float f;
+  std::memcpy(&f, &i, 4);
+  return f;
+#endif
+}
+
+struct F4 {  // layout-compatible with float4
+  float x, y, z, w;
+};
+
+// squared distance exactly as flann::L2_Simple<float> accumulates it: ((dx*dx)+dy*dy)+dz*dz
+RGC_HD float dist2_ref(float qx, float qy, float qz, float px, float py, float pz) {
+  float dx = fsub(qx, px), dy = fsub(qy, py), dz = fsub(qz, pz);
+  float d = fmul(dx, dx);
+  d = fadd(d, fmul(dy, dy));
+  d = fadd(d, fmul(dz, dz));
+  return d;
+}
+
+// float Isometry3f * Vector4f with w = 1 (fast_gicp_impl.hpp:131): ((r0*x + r1*y) + r2*z) + t
+// T: row-major 3x4 floats.
+RGC_HD void transform_f(const float* T, float x, float y, float z, float& ox, float& oy, float& oz) {
+  ox = fadd(fadd(fadd(fmul(T[0], x), fmul(T[1], y)), fmul(T[2], z)), T[3]);
+  oy = fadd(fadd(fadd(fmul(T[4], x), fmul(T[5], y)), fmul(T[6], z)), T[7]);
+  oz = fadd(fadd(fadd(fmul(T[8], x), fmul(T[9], y)), fmul(T[10], z)), T[11]);
+}
+
+enum RegMethod { REG_NONE = 0, REG_MIN_EIG = 1, REG_NORMALIZED_MIN_EIG = 2, REG_PLANE = 3, REG_FROBENIUS = 4 };
+
+}  // namespace rgc

@@ -1,0 +1,777 @@
+// rgc_gicp.cu — host side of librgc_gicp.so: context / memory pool, cloud build pipeline,
+// the registration object and its LM driver, and the C-ABI declared in include/rgc_gicp.h.
+//
+// Reference behaviour mirrored here (paths under /root/reference/rgc_slam/include/fast_gicp/gicp/):
+//   impl/fast_gicp_impl.hpp:72-112   setInputSource/Target caching, lazy covariances, align
+//   impl/lsq_registration_impl.hpp:53-172  GN / LM outer loop, lambda schedule, convergence
+// There is no CPU fallback anywhere in this file: every numeric step is a kernel launch.
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/rgc_gicp.h"
+#include "rgc_kernels.cuh"
+#include "rgc_lm.hpp"
+
+using namespace rgc;
+
+// ------------------------------------------------------------------------------------------------
+struct rgc_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+  // pooled device memory: power-of-two size classes, never returned to the driver before destroy
+  std::multimap<size_t, void*> free_blocks;
+  std::unordered_map<void*, size_t> block_size;
+  // pinned, device-mapped result area the reduction kernels write straight into
+  double* h_result = nullptr;
+  double* d_result = nullptr;  // device alias of h_result
+  float* h_bbox = nullptr;     // pinned: kBboxBlocks x 6
+  uint32_t* h_counts = nullptr;  // pinned: kMaxLevels
+  unsigned int* d_ticket = nullptr;
+  cudaEvent_t ev[8];
+
+  void* get(size_t bytes) {
+    size_t cls = 4096;
+    while (cls < bytes) cls <<= 1;
+    auto it = free_blocks.find(cls);
+    if (it != free_blocks.end()) {
+      void* p = it->second;
+      free_blocks.erase(it);
+      return p;
+    }
+    void* p = nullptr;
+    if (cudaMalloc(&p, cls) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    block_size[p] = cls;
+    return p;
+  }
+  void put(void* p) {
+    if (!p) return;
+    free_blocks.insert({block_size[p], p});
+  }
+};
+
+#define CK(ctx, call)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess) {                                                                            \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                  \
+      return RGC_ERR_CUDA;                                                                              \
+    }                                                                                                   \
+  } while (0)
+#define CKL(ctx)                                                                                        \
+  do {                                                                                                  \
+    (ctx)->launches++;                                                                                  \
+    cudaError_t e_ = cudaGetLastError();                                                                \
+    if (e_ != cudaSuccess) {                                                                            \
+      (ctx)->err = std::string("kernel launch: ") + cudaGetErrorString(e_);                             \
+      return RGC_ERR_CUDA;                                                                              \
+    }                                                                                                   \
+  } while (0)
+#define FAIL(ctx, code, msg) \
+  do {                       \
+    (ctx)->err = (msg);      \
+    return (code);           \
+  } while (0)
+#define TRY(expr)          \
+  do {                     \
+    int rc_ = (expr);      \
+    if (rc_ != 0) return rc_; \
+  } while (0)
+
+static inline int div_up(int a, int b) { return (a + b - 1) / b; }
+
+// ------------------------------------------------------------------------------------------------
+struct Cloud {
+  int n = 0;
+  uint64_t key = 0;
+  bool valid = false;
+  float4* sorted = nullptr;
+  GridSlot* tables = nullptr;
+  GridView view{};
+  double* cov = nullptr;  // 6 doubles per sorted point
+  bool has_cov = false;
+  float build_ms = 0, knn_ms = 0, cov_ms = 0;
+};
+
+static void cloud_release(rgc_ctx* c, Cloud& cl) {
+  c->put(cl.sorted);
+  c->put(cl.tables);
+  c->put(cl.cov);
+  cl = Cloud();
+}
+
+// upload (or adopt a device pointer), Morton-sort, build the level tables
+static int cloud_build(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, size_t stride, bool on_device, uint64_t key, float cell) {
+  cloud_release(c, cl);
+  if (n_sz == 0 || points == nullptr) FAIL(c, RGC_ERR_INVALID, "empty point cloud");
+  if (n_sz > 0x7fffffff / 32) FAIL(c, RGC_ERR_UNSUPPORTED, "point cloud too large for 32-bit indexing");
+  if (stride < 12 || stride % 4) FAIL(c, RGC_ERR_INVALID, "point stride must be a multiple of 4 and >= 12 bytes");
+  const int n = (int)n_sz;
+  cudaStream_t st = c->stream;
+  CK(c, cudaEventRecord(c->ev[0], st));
+
+  const unsigned char* d_raw = (const unsigned char*)points;
+  void* staging = nullptr;
+  if (!on_device) {
+    staging = c->get(n_sz * stride);
+    if (!staging) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (staging)");
+    CK(c, cudaMemcpyAsync(staging, points, n_sz * stride, cudaMemcpyHostToDevice, st));
+    d_raw = (const unsigned char*)staging;
+  }
+  float4* orig = (float4*)c->get(sizeof(float4) * n_sz);
+  float* d_bbox = (float*)c->get(sizeof(float) * 6 * kBboxBlocks);
+  uint64_t* keys_a = (uint64_t*)c->get(8 * n_sz);
+  uint64_t* keys_b = (uint64_t*)c->get(8 * n_sz);
+  uint32_t* vals_a = (uint32_t*)c->get(4 * n_sz);
+  uint32_t* vals_b = (uint32_t*)c->get(4 * n_sz);
+  const int nblk = div_up(n, RS_TILE);
+  uint32_t* hist = (uint32_t*)c->get(4 * 256 * (size_t)nblk);
+  uint32_t* d_counts = (uint32_t*)c->get(4 * kMaxLevels);
+  cl.sorted = (float4*)c->get(sizeof(float4) * n_sz);
+  if (!orig || !d_bbox || !keys_a || !keys_b || !vals_a || !vals_b || !hist || !d_counts || !cl.sorted) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (build)");
+
+  k_ingest<<<kBboxBlocks, 256, 0, st>>>(d_raw, stride, n, orig, d_bbox);
+  CKL(c);
+  CK(c, cudaMemcpyAsync(c->h_bbox, d_bbox, sizeof(float) * 6 * kBboxBlocks, cudaMemcpyDeviceToHost, st));
+  CK(c, cudaStreamSynchronize(st));
+  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int b = 0; b < kBboxBlocks; b++)
+    for (int a = 0; a < 3; a++) {
+      mn[a] = std::min(mn[a], c->h_bbox[b * 6 + a]);
+      mx[a] = std::max(mx[a], c->h_bbox[b * 6 + 3 + a]);
+    }
+  for (int a = 0; a < 3; a++)
+    if (!std::isfinite(mn[a]) || !std::isfinite(mx[a])) FAIL(c, RGC_ERR_INVALID, "point cloud contains non-finite coordinates");
+
+  // ---- grid geometry ----
+  GridView& v = cl.view;
+  v.n = n;
+  grid_geometry(mn, mx, cell, v);
+  const int nbits = v.nbits;
+  GridGeom geom{v.ox, v.oy, v.oz, v.inv_s0, nbits};
+
+  // ---- Morton keys + LSD radix sort ----
+  k_morton<<<div_up(n, 256), 256, 0, st>>>(orig, n, geom, keys_a, vals_a);
+  CKL(c);
+  const int passes = div_up(3 * nbits, 8);
+  uint64_t *kin = keys_a, *kout = keys_b;
+  uint32_t *vin = vals_a, *vout = vals_b;
+  for (int p = 0; p < passes; p++) {
+    k_rs_hist<<<nblk, 256, 0, st>>>(kin, n, 8 * p, hist, nblk);
+    CKL(c);
+    k_rs_scan<<<1, 1024, 0, st>>>(hist, 256 * nblk);
+    CKL(c);
+    k_rs_scatter<<<nblk, 256, 0, st>>>(kin, vin, kout, vout, hist, n, 8 * p, nblk);
+    CKL(c);
+    std::swap(kin, kout);
+    std::swap(vin, vout);
+  }
+  k_gather_sorted<<<div_up(n, 256), 256, 0, st>>>(orig, vin, n, cl.sorted);
+  CKL(c);
+
+  // ---- level tables ----
+  CK(c, cudaMemsetAsync(d_counts, 0, 4 * kMaxLevels, st));
+  k_count_cells<<<div_up(n, 256), 256, 0, st>>>(kin, n, v.nlevels, d_counts);
+  CKL(c);
+  CK(c, cudaMemcpyAsync(c->h_counts, d_counts, 4 * kMaxLevels, cudaMemcpyDeviceToHost, st));
+  CK(c, cudaStreamSynchronize(st));
+  size_t total_slots = 0;
+  size_t slots[kMaxLevels];
+  for (int l = 0; l < v.nlevels; l++) {
+    size_t s = 8;
+    while (s < 2 * (size_t)c->h_counts[l]) s <<= 1;
+    slots[l] = s;
+    total_slots += s;
+  }
+  cl.tables = (GridSlot*)c->get(total_slots * sizeof(GridSlot));
+  if (!cl.tables) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (tables)");
+  CK(c, cudaMemsetAsync(cl.tables, 0xff, total_slots * sizeof(GridSlot), st));
+  TableSet ts;
+  ts.nlevels = v.nlevels;
+  size_t off = 0;
+  for (int l = 0; l < kMaxLevels; l++) {
+    if (l < v.nlevels) {
+      ts.table[l] = cl.tables + off;
+      ts.mask[l] = (uint32_t)(slots[l] - 1);
+      off += slots[l];
+    } else {
+      ts.table[l] = nullptr;
+      ts.mask[l] = 0;
+    }
+    v.table[l] = ts.table[l];
+    v.mask[l] = ts.mask[l];
+  }
+  k_build_tables<<<div_up(n, 256), 256, 0, st>>>(kin, n, ts);
+  CKL(c);
+  v.pts = reinterpret_cast<const F4*>(cl.sorted);
+
+  c->put(staging);
+  c->put(orig);
+  c->put(d_bbox);
+  c->put(keys_a);
+  c->put(keys_b);
+  c->put(vals_a);
+  c->put(vals_b);
+  c->put(hist);
+  c->put(d_counts);
+  cl.n = n;
+  cl.key = key;
+  cl.valid = true;
+  CK(c, cudaEventRecord(c->ev[1], st));
+  CK(c, cudaEventSynchronize(c->ev[1]));
+  CK(c, cudaEventElapsedTime(&cl.build_ms, c->ev[0], c->ev[1]));
+  return RGC_OK;
+}
+
+template <bool SELF>
+static int launch_knn(rgc_ctx* c, const GridView& v, const float4* queries, int m, int k, int* idx, float* d2) {
+  const int grid = div_up(m, kThreads);
+  if (k == 1)
+    k_knn<1, SELF><<<grid, kThreads, 0, c->stream>>>(v, queries, m, k, idx, d2);
+  else if (k <= 8)
+    k_knn<8, SELF><<<grid, kThreads, 0, c->stream>>>(v, queries, m, k, idx, d2);
+  else if (k <= 20)
+    k_knn<20, SELF><<<grid, kThreads, 0, c->stream>>>(v, queries, m, k, idx, d2);
+  else if (k <= 32)
+    k_knn<32, SELF><<<grid, kThreads, 0, c->stream>>>(v, queries, m, k, idx, d2);
+  else
+    FAIL(c, RGC_ERR_UNSUPPORTED, "k_correspondences > 32 is not supported");
+  CKL(c);
+  return RGC_OK;
+}
+
+// FastGICP::calculate_covariances (fast_gicp_impl.hpp:241-299)
+static int cloud_covariances(rgc_ctx* c, Cloud& cl, int k, int method) {
+  if (cl.has_cov) return RGC_OK;
+  if (k < 1) FAIL(c, RGC_ERR_INVALID, "k_correspondences must be >= 1");
+  cudaStream_t st = c->stream;
+  int* nbr = (int*)c->get(sizeof(int) * (size_t)k * cl.n);
+  if (!cl.cov) cl.cov = (double*)c->get(sizeof(double) * 6 * (size_t)cl.n);
+  if (!nbr || !cl.cov) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (covariances)");
+  CK(c, cudaEventRecord(c->ev[2], st));
+  TRY(launch_knn<true>(c, cl.view, nullptr, cl.n, k, nbr, nullptr));
+  CK(c, cudaEventRecord(c->ev[3], st));
+  k_covariance<<<div_up(cl.n, kThreads), kThreads, 0, st>>>(cl.sorted, nbr, cl.n, k, method, cl.cov);
+  CKL(c);
+  CK(c, cudaEventRecord(c->ev[4], st));
+  c->put(nbr);
+  cl.has_cov = true;
+  CK(c, cudaEventSynchronize(c->ev[4]));
+  CK(c, cudaEventElapsedTime(&cl.knn_ms, c->ev[2], c->ev[3]));
+  CK(c, cudaEventElapsedTime(&cl.cov_ms, c->ev[3], c->ev[4]));
+  return RGC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct rgc_reg {
+  rgc_ctx* ctx = nullptr;
+  rgc_params prm{};
+  Cloud src, tgt;
+  // per-source-point state of the last linearize
+  int* corr = nullptr;
+  float* sqd = nullptr;
+  double* maha = nullptr;
+  double* partials = nullptr;
+  int cap_src = 0;
+  bool have_corr = false;
+  // LsqRegistration state
+  double lm_lambda = -1.0;
+  double final_hessian[36];  // row-major (symmetric)
+  float final_T[16];         // row-major
+  bool converged = false;
+  int n_linearize = 0, n_compute_error = 0, last_inliers = 0;
+  float lm_ms = 0;
+};
+
+static int reg_ensure_work(rgc_reg* r) {
+  rgc_ctx* c = r->ctx;
+  if (r->cap_src >= r->src.n && r->corr) return RGC_OK;
+  c->put(r->corr);
+  c->put(r->sqd);
+  c->put(r->maha);
+  c->put(r->partials);
+  const size_t n = (size_t)r->src.n;
+  r->corr = (int*)c->get(4 * n);
+  r->sqd = (float*)c->get(4 * n);
+  r->maha = (double*)c->get(48 * n);
+  r->partials = (double*)c->get(sizeof(double) * kLinN * (size_t)div_up(r->src.n, kThreads));
+  if (!r->corr || !r->sqd || !r->maha || !r->partials) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (work buffers)");
+  r->cap_src = r->src.n;
+  return RGC_OK;
+}
+
+static void to_rt(const double* T /*row-major 4x4*/, Rt& d, RtF& f) {
+  for (int i = 0; i < 12; i++) {
+    d.m[i] = T[i];
+    f.m[i] = (float)T[i];  // Eigen::Isometry3d::cast<float>() (fast_gicp_impl.hpp:119)
+  }
+}
+
+// FastGICP::linearize (fast_gicp_impl.hpp:155-211); H row-major 6x6
+static int reg_linearize(rgc_reg* r, const double* T, double* err, double* H, double* b) {
+  rgc_ctx* c = r->ctx;
+  TRY(reg_ensure_work(r));
+  Rt Td;
+  RtF Tf;
+  to_rt(T, Td, Tf);
+  const float thr = r->prm.max_correspondence_distance;
+  const float thr2 = thr * thr;  // float product, +inf for the FLT_MAX default (fast_gicp_impl.hpp:136)
+  const int want = (H && b) ? 1 : 0;
+  k_linearize<<<div_up(r->src.n, kThreads), kThreads, 0, c->stream>>>(r->tgt.view, r->src.sorted, r->src.cov, r->tgt.cov, r->src.n, Tf, Td, thr2, want,
+                                                                     r->corr, r->sqd, r->maha, r->partials, c->d_ticket, c->d_result);
+  CKL(c);
+  CK(c, cudaStreamSynchronize(c->stream));
+  r->n_linearize++;
+  r->have_corr = true;
+  const double* res = c->h_result;
+  *err = res[0];
+  r->last_inliers = (int)res[kAccN];
+  if (want) {
+    int o = 1;
+    for (int i = 0; i < 6; i++)
+      for (int j = i; j < 6; j++) {
+        H[i * 6 + j] = H[j * 6 + i] = res[o];
+        o++;
+      }
+    for (int i = 0; i < 6; i++) b[i] = res[22 + i];
+  }
+  return RGC_OK;
+}
+
+// FastGICP::compute_error (fast_gicp_impl.hpp:214-237)
+static int reg_compute_error(rgc_reg* r, const double* T, double* err) {
+  rgc_ctx* c = r->ctx;
+  if (!r->have_corr) FAIL(c, RGC_ERR_STATE, "compute_error before any linearize");
+  Rt Td;
+  RtF Tf;
+  to_rt(T, Td, Tf);
+  k_compute_error<<<div_up(r->src.n, kThreads), kThreads, 0, c->stream>>>(r->tgt.sorted, r->src.sorted, r->src.n, Td, r->corr, r->maha, r->partials,
+                                                                         c->d_ticket, c->d_result);
+  CKL(c);
+  CK(c, cudaStreamSynchronize(c->stream));
+  r->n_compute_error++;
+  *err = c->h_result[0];
+  return RGC_OK;
+}
+
+static int reg_ready(rgc_reg* r) {
+  rgc_ctx* c = r->ctx;
+  if (!r->src.valid || !r->tgt.valid) FAIL(c, RGC_ERR_STATE, "source and target clouds must both be set");
+  // fast_gicp_impl.hpp:104-109 — covariances are computed lazily, source first
+  TRY(cloud_covariances(c, r->src, r->prm.k_correspondences, r->prm.regularization));
+  TRY(cloud_covariances(c, r->tgt, r->prm.k_correspondences, r->prm.regularization));
+  return RGC_OK;
+}
+
+// lsq_registration_impl.hpp:106-122
+static int step_gn(rgc_reg* r, double* x0, double* delta) {
+  double H[36], b[6], nb[6], d[6], y0;
+  TRY(reg_linearize(r, x0, &y0, H, b));
+  for (int i = 0; i < 6; i++) nb[i] = -b[i];
+  lm::solve_ldlt6(H, nb, d);
+  lm::se3_delta(d, delta);
+  lm::mul4(delta, x0, x0);
+  std::memcpy(r->final_hessian, H, sizeof(H));
+  return 1;
+}
+
+// lsq_registration_impl.hpp:125-172 ; returns 1 = step taken, 0 = "lm not converged", <0 = error
+static int step_lm(rgc_reg* r, double* x0, double* delta, double* y0_out) {
+  double H[36], b[6], y0;
+  TRY(reg_linearize(r, x0, &y0, H, b));
+  *y0_out = y0;
+  if (r->lm_lambda < 0.0) {
+    double mx = 0.0;
+    for (int i = 0; i < 6; i++) mx = std::max(mx, std::fabs(H[i * 7]));
+    r->lm_lambda = r->prm.lm_init_lambda_factor * mx;
+  }
+  double nu = 2.0;
+  for (int i = 0; i < r->prm.lm_max_iterations; i++) {
+    double A[36], nb[6], d[6], xi[16], yi;
+    for (int j = 0; j < 36; j++) A[j] = H[j];
+    for (int j = 0; j < 6; j++) {
+      A[j * 7] += r->lm_lambda;
+      nb[j] = -b[j];
+    }
+    lm::solve_ldlt6(A, nb, d);
+    lm::se3_delta(d, delta);
+    lm::mul4(delta, x0, xi);
+    TRY(reg_compute_error(r, xi, &yi));
+    double denom = 0.0;
+    for (int j = 0; j < 6; j++) denom += d[j] * (r->lm_lambda * d[j] - b[j]);
+    const double rho = (y0 - yi) / denom;
+    if (r->prm.lm_debug_print) {
+      if (i == 0) std::printf("--- LM optimization ---\n%5s %15s %15s %15s %15s %15s %5s\n", "i", "y0", "yi", "rho", "lambda", "|delta|", "dec");
+      double dn = 0.0;
+      for (int j = 0; j < 6; j++) dn += d[j] * d[j];
+      std::printf("%5d %15g %15g %15g %15g %15g %5c\n", i, y0, yi, rho, r->lm_lambda, std::sqrt(dn), rho > 0.0 ? 'x' : ' ');
+    }
+    if (rho < 0) {
+      if (lm::is_converged(delta, r->prm.rotation_epsilon, r->prm.transformation_epsilon)) return 1;
+      r->lm_lambda = nu * r->lm_lambda;
+      nu = 2 * nu;
+      continue;
+    }
+    std::memcpy(x0, xi, sizeof(xi));
+    r->lm_lambda = r->lm_lambda * std::max(1.0 / 3.0, 1 - std::pow(2 * rho - 1, 3));
+    std::memcpy(r->final_hessian, H, sizeof(H));
+    return 1;
+  }
+  return 0;
+}
+
+// ================================================================================================
+extern "C" {
+
+int rgc_ctx_create(int device, rgc_ctx** out) {
+  if (!out) return RGC_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+    cudaGetLastError();
+    std::fprintf(stderr, "rgc_ctx_create: no usable CUDA device %d (found %d); this library has no CPU fallback\n", device, count);
+    return RGC_ERR_CUDA;
+  }
+  rgc_ctx* c = new rgc_ctx();
+  c->device = device;
+  bool ok = cudaSetDevice(device) == cudaSuccess && cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaHostAlloc((void**)&c->h_result, sizeof(double) * 64, cudaHostAllocMapped) == cudaSuccess &&
+            cudaHostGetDevicePointer((void**)&c->d_result, c->h_result, 0) == cudaSuccess &&
+            cudaHostAlloc((void**)&c->h_bbox, sizeof(float) * 6 * kBboxBlocks, cudaHostAllocDefault) == cudaSuccess &&
+            cudaHostAlloc((void**)&c->h_counts, sizeof(uint32_t) * kMaxLevels, cudaHostAllocDefault) == cudaSuccess &&
+            cudaMalloc((void**)&c->d_ticket, 64) == cudaSuccess && cudaMemset(c->d_ticket, 0, 64) == cudaSuccess;
+  for (int i = 0; ok && i < 8; i++) ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
+  if (!ok) {
+    std::fprintf(stderr, "rgc_ctx_create: %s\n", cudaGetErrorString(cudaGetLastError()));
+    delete c;
+    return RGC_ERR_CUDA;
+  }
+  *out = c;
+  return RGC_OK;
+}
+
+int rgc_ctx_destroy(rgc_ctx* c) {
+  if (!c) return RGC_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto& kv : c->block_size) cudaFree(kv.first);
+  cudaFreeHost(c->h_result);
+  cudaFreeHost(c->h_bbox);
+  cudaFreeHost(c->h_counts);
+  cudaFree(c->d_ticket);
+  for (int i = 0; i < 8; i++) cudaEventDestroy(c->ev[i]);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return RGC_OK;
+}
+
+const char* rgc_last_error(const rgc_ctx* c) { return c ? c->err.c_str() : "null context"; }
+int rgc_ctx_synchronize(rgc_ctx* c) {
+  CK(c, cudaStreamSynchronize(c->stream));
+  return RGC_OK;
+}
+void* rgc_ctx_stream(rgc_ctx* c) { return (void*)c->stream; }
+uint64_t rgc_ctx_launch_count(const rgc_ctx* c) { return c->launches; }
+
+void rgc_params_default(rgc_params* p) {
+  p->max_iterations = 64;
+  p->rotation_epsilon = 2e-3;
+  p->transformation_epsilon = 5e-4;
+  p->max_correspondence_distance = FLT_MAX;
+  p->k_correspondences = 20;
+  p->regularization = RGC_REG_PLANE;
+  p->optimizer = RGC_OPT_LEVENBERG_MARQUARDT;
+  p->lm_max_iterations = 10;
+  p->lm_init_lambda_factor = 1e-9;
+  p->lm_debug_print = 0;
+  p->grid_cell = 0.f;
+}
+
+int rgc_reg_create(rgc_ctx* c, rgc_reg** out) {
+  if (!c || !out) return RGC_ERR_INVALID;
+  rgc_reg* r = new rgc_reg();
+  r->ctx = c;
+  rgc_params_default(&r->prm);
+  for (int i = 0; i < 36; i++) r->final_hessian[i] = (i % 7 == 0) ? 1.0 : 0.0;  // final_hessian_.setIdentity()
+  for (int i = 0; i < 16; i++) r->final_T[i] = (i % 5 == 0) ? 1.f : 0.f;
+  *out = r;
+  return RGC_OK;
+}
+
+int rgc_reg_destroy(rgc_reg* r) {
+  if (!r) return RGC_OK;
+  rgc_ctx* c = r->ctx;
+  cudaSetDevice(c->device);
+  cloud_release(c, r->src);
+  cloud_release(c, r->tgt);
+  c->put(r->corr);
+  c->put(r->sqd);
+  c->put(r->maha);
+  c->put(r->partials);
+  delete r;
+  return RGC_OK;
+}
+
+int rgc_reg_set_params(rgc_reg* r, const rgc_params* p) {
+  if (!r || !p) return RGC_ERR_INVALID;
+  if (p->k_correspondences < 1 || p->k_correspondences > 32) FAIL(r->ctx, RGC_ERR_UNSUPPORTED, "k_correspondences must be in [1, 32]");
+  if (p->regularization < 0 || p->regularization > 4) FAIL(r->ctx, RGC_ERR_INVALID, "unknown regularization method");
+  r->prm = *p;
+  return RGC_OK;
+}
+int rgc_reg_get_params(const rgc_reg* r, rgc_params* p) {
+  if (!r || !p) return RGC_ERR_INVALID;
+  *p = r->prm;
+  return RGC_OK;
+}
+
+static int set_cloud(rgc_reg* r, Cloud& cl, const void* pts, size_t n, size_t stride, uint64_t key, bool on_device) {
+  rgc_ctx* c = r->ctx;
+  CK(c, cudaSetDevice(c->device));
+  if (key != 0 && cl.valid && cl.key == key) return RGC_OK;  // fast_gicp_impl.hpp:73-75 / :84-86
+  r->have_corr = false;
+  return cloud_build(c, cl, pts, n, stride, on_device, key, r->prm.grid_cell);
+}
+int rgc_reg_set_source(rgc_reg* r, const void* p, size_t n, size_t s, uint64_t key) { return r ? set_cloud(r, r->src, p, n, s, key, false) : RGC_ERR_INVALID; }
+int rgc_reg_set_target(rgc_reg* r, const void* p, size_t n, size_t s, uint64_t key) { return r ? set_cloud(r, r->tgt, p, n, s, key, false) : RGC_ERR_INVALID; }
+int rgc_reg_set_source_device(rgc_reg* r, const void* p, size_t n, size_t s, uint64_t key) { return r ? set_cloud(r, r->src, p, n, s, key, true) : RGC_ERR_INVALID; }
+int rgc_reg_set_target_device(rgc_reg* r, const void* p, size_t n, size_t s, uint64_t key) { return r ? set_cloud(r, r->tgt, p, n, s, key, true) : RGC_ERR_INVALID; }
+
+int rgc_reg_swap_source_and_target(rgc_reg* r) {
+  if (!r) return RGC_ERR_INVALID;
+  std::swap(r->src, r->tgt);
+  r->have_corr = false;  // correspondences_.clear(); sq_distances_.clear();
+  return RGC_OK;
+}
+int rgc_reg_clear_source(rgc_reg* r) {
+  if (!r) return RGC_ERR_INVALID;
+  cloud_release(r->ctx, r->src);
+  r->have_corr = false;
+  return RGC_OK;
+}
+int rgc_reg_clear_target(rgc_reg* r) {
+  if (!r) return RGC_ERR_INVALID;
+  cloud_release(r->ctx, r->tgt);
+  r->have_corr = false;
+  return RGC_OK;
+}
+
+static int set_covs(rgc_reg* r, Cloud& cl, const double* m, size_t n) {
+  rgc_ctx* c = r->ctx;
+  CK(c, cudaSetDevice(c->device));
+  if (!cl.valid) FAIL(c, RGC_ERR_STATE, "set the point cloud before its covariances");
+  if ((int)n != cl.n) FAIL(c, RGC_ERR_INVALID, "covariance count does not match the cloud size");
+  double* stage = (double*)c->get(128 * n);
+  if (!cl.cov) cl.cov = (double*)c->get(48 * n);
+  if (!stage || !cl.cov) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (covariance import)");
+  CK(c, cudaMemcpyAsync(stage, m, 128 * n, cudaMemcpyHostToDevice, c->stream));
+  k_cov_import<<<div_up(cl.n, 256), 256, 0, c->stream>>>(cl.sorted, cl.n, stage, cl.cov);
+  CKL(c);
+  CK(c, cudaStreamSynchronize(c->stream));
+  c->put(stage);
+  cl.has_cov = true;
+  return RGC_OK;
+}
+static int get_covs(rgc_reg* r, Cloud& cl, double* m, size_t n) {
+  rgc_ctx* c = r->ctx;
+  CK(c, cudaSetDevice(c->device));
+  if (!cl.valid) FAIL(c, RGC_ERR_STATE, "no point cloud set");
+  if ((int)n != cl.n) FAIL(c, RGC_ERR_INVALID, "covariance count does not match the cloud size");
+  TRY(cloud_covariances(c, cl, r->prm.k_correspondences, r->prm.regularization));
+  double* stage = (double*)c->get(128 * n);
+  if (!stage) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (covariance export)");
+  k_cov_export<<<div_up(cl.n, 256), 256, 0, c->stream>>>(cl.sorted, cl.n, cl.cov, stage);
+  CKL(c);
+  CK(c, cudaMemcpyAsync(m, stage, 128 * n, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  c->put(stage);
+  return RGC_OK;
+}
+int rgc_reg_set_source_covs(rgc_reg* r, const double* m, size_t n) { return (r && m) ? set_covs(r, r->src, m, n) : RGC_ERR_INVALID; }
+int rgc_reg_set_target_covs(rgc_reg* r, const double* m, size_t n) { return (r && m) ? set_covs(r, r->tgt, m, n) : RGC_ERR_INVALID; }
+int rgc_reg_get_source_covs(rgc_reg* r, double* m, size_t n) { return (r && m) ? get_covs(r, r->src, m, n) : RGC_ERR_INVALID; }
+int rgc_reg_get_target_covs(rgc_reg* r, double* m, size_t n) { return (r && m) ? get_covs(r, r->tgt, m, n) : RGC_ERR_INVALID; }
+
+static void colmajor_to_row(const double* in, double* out) {
+  for (int r = 0; r < 4; r++)
+    for (int c = 0; c < 4; c++) out[r * 4 + c] = in[c * 4 + r];
+}
+
+int rgc_reg_align(rgc_reg* r, const float* guess, float* final_T16, rgc_result* result, float* out_points) {
+  if (!r) return RGC_ERR_INVALID;
+  rgc_ctx* c = r->ctx;
+  CK(c, cudaSetDevice(c->device));
+  CK(c, cudaEventRecord(c->ev[5], c->stream));
+  TRY(reg_ready(r));
+  // lsq_registration_impl.hpp:53-57
+  double x0[16];
+  for (int rr = 0; rr < 4; rr++)
+    for (int cc = 0; cc < 4; cc++) x0[rr * 4 + cc] = guess ? (double)guess[cc * 4 + rr] : (rr == cc ? 1.0 : 0.0);
+  r->lm_lambda = -1.0;
+  r->converged = false;
+  r->n_linearize = r->n_compute_error = 0;
+  int iterations = 0;
+  double last_y0 = 0.0;
+  CK(c, cudaEventRecord(c->ev[6], c->stream));
+  for (int i = 0; i < r->prm.max_iterations && !r->converged; i++) {
+    iterations = i;
+    double delta[16];
+    int rc = (r->prm.optimizer == RGC_OPT_GAUSS_NEWTON) ? step_gn(r, x0, delta) : step_lm(r, x0, delta, &last_y0);
+    if (rc < 0) return rc;
+    if (rc == 0) {
+      std::fprintf(stderr, "lm not converged!!\n");  // lsq_registration_impl.hpp:69-72
+      break;
+    }
+    r->converged = lm::is_converged(delta, r->prm.rotation_epsilon, r->prm.transformation_epsilon);
+  }
+  for (int i = 0; i < 16; i++) r->final_T[i] = (float)x0[i];  // final_transformation_ = x0.cast<float>()
+  if (out_points) {
+    RtF Tf;
+    for (int i = 0; i < 12; i++) Tf.m[i] = r->final_T[i];
+    float4* d_out = (float4*)c->get(sizeof(float4) * (size_t)r->src.n);
+    if (!d_out) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (output cloud)");
+    k_transform_out<<<div_up(r->src.n, 256), 256, 0, c->stream>>>(r->src.sorted, r->src.n, Tf, d_out);
+    CKL(c);
+    CK(c, cudaMemcpyAsync(out_points, d_out, sizeof(float4) * (size_t)r->src.n, cudaMemcpyDeviceToHost, c->stream));
+    c->put(d_out);
+  }
+  CK(c, cudaEventRecord(c->ev[7], c->stream));
+  CK(c, cudaEventSynchronize(c->ev[7]));
+  float total_ms = 0.f;
+  CK(c, cudaEventElapsedTime(&total_ms, c->ev[5], c->ev[7]));
+  CK(c, cudaEventElapsedTime(&r->lm_ms, c->ev[6], c->ev[7]));
+  if (final_T16)
+    for (int rr = 0; rr < 4; rr++)
+      for (int cc = 0; cc < 4; cc++) final_T16[cc * 4 + rr] = r->final_T[rr * 4 + cc];
+  if (result) {
+    result->converged = r->converged ? 1 : 0;
+    result->iterations = iterations;
+    result->n_linearize = r->n_linearize;
+    result->n_compute_error = r->n_compute_error;
+    result->n_inliers = r->last_inliers;
+    result->final_error = last_y0;
+    for (int i = 0; i < 6; i++)
+      for (int j = 0; j < 6; j++) result->final_hessian[j * 6 + i] = r->final_hessian[i * 6 + j];
+    result->device_ms = total_ms;
+  }
+  return RGC_OK;
+}
+
+int rgc_reg_linearize(rgc_reg* r, const double* T16, double* err, double* H36, double* b6) {
+  if (!r || !T16 || !err) return RGC_ERR_INVALID;
+  rgc_ctx* c = r->ctx;
+  CK(c, cudaSetDevice(c->device));
+  TRY(reg_ready(r));
+  double T[16], H[36];
+  colmajor_to_row(T16, T);
+  TRY(reg_linearize(r, T, err, (H36 && b6) ? H : nullptr, b6));
+  if (H36 && b6)
+    for (int i = 0; i < 6; i++)
+      for (int j = 0; j < 6; j++) H36[j * 6 + i] = H[i * 6 + j];
+  return RGC_OK;
+}
+
+int rgc_reg_compute_error(rgc_reg* r, const double* T16, double* err) {
+  if (!r || !T16 || !err) return RGC_ERR_INVALID;
+  rgc_ctx* c = r->ctx;
+  CK(c, cudaSetDevice(c->device));
+  double T[16];
+  colmajor_to_row(T16, T);
+  return reg_compute_error(r, T, err);
+}
+
+int rgc_reg_get_correspondences(rgc_reg* r, int32_t* corr, float* sq_dist) {
+  if (!r || !corr) return RGC_ERR_INVALID;
+  rgc_ctx* c = r->ctx;
+  CK(c, cudaSetDevice(c->device));
+  if (!r->have_corr) FAIL(c, RGC_ERR_STATE, "no correspondences yet (call linearize or align first)");
+  const size_t n = (size_t)r->src.n;
+  int* d_c = (int*)c->get(4 * n);
+  float* d_s = (float*)c->get(4 * n);
+  if (!d_c || !d_s) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (correspondence export)");
+  k_corr_to_orig<<<div_up(r->src.n, 256), 256, 0, c->stream>>>(r->src.sorted, r->tgt.sorted, r->corr, r->sqd, r->src.n, d_c, d_s);
+  CKL(c);
+  CK(c, cudaMemcpyAsync(corr, d_c, 4 * n, cudaMemcpyDeviceToHost, c->stream));
+  if (sq_dist) CK(c, cudaMemcpyAsync(sq_dist, d_s, 4 * n, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  c->put(d_c);
+  c->put(d_s);
+  return RGC_OK;
+}
+
+int rgc_reg_fitness(rgc_reg* r, double max_range, double* score) {
+  if (!r || !score) return RGC_ERR_INVALID;
+  rgc_ctx* c = r->ctx;
+  CK(c, cudaSetDevice(c->device));
+  if (!r->src.valid || !r->tgt.valid) FAIL(c, RGC_ERR_STATE, "source and target clouds must both be set");
+  TRY(reg_ensure_work(r));
+  RtF Tf;
+  for (int i = 0; i < 12; i++) Tf.m[i] = r->final_T[i];
+  k_fitness<<<div_up(r->src.n, kThreads), kThreads, 0, c->stream>>>(r->tgt.view, r->src.sorted, r->src.n, Tf, max_range, r->partials, c->d_ticket, c->d_result);
+  CKL(c);
+  CK(c, cudaStreamSynchronize(c->stream));
+  const double sum = c->h_result[0], nr = c->h_result[1];
+  *score = nr > 0 ? sum / nr : DBL_MAX;
+  return RGC_OK;
+}
+
+int rgc_reg_get_final_transformation(const rgc_reg* r, float* T16) {
+  if (!r || !T16) return RGC_ERR_INVALID;
+  for (int rr = 0; rr < 4; rr++)
+    for (int cc = 0; cc < 4; cc++) T16[cc * 4 + rr] = r->final_T[rr * 4 + cc];
+  return RGC_OK;
+}
+
+int rgc_knn(rgc_ctx* c, const void* points, size_t n, size_t stride, const void* queries, size_t m, size_t qstride, int k, int32_t* idx, float* d2,
+            float grid_cell) {
+  if (!c || !points || !queries || !idx || k < 1) return RGC_ERR_INVALID;
+  CK(c, cudaSetDevice(c->device));
+  if (k > 32) FAIL(c, RGC_ERR_UNSUPPORTED, "k > 32 is not supported");
+  if (qstride < 12 || qstride % 4) FAIL(c, RGC_ERR_INVALID, "query stride must be a multiple of 4 and >= 12 bytes");
+  Cloud cl;
+  TRY(cloud_build(c, cl, points, n, stride, false, 0, grid_cell));
+  void* qraw = c->get(m * qstride);
+  float4* q4 = (float4*)c->get(sizeof(float4) * m);
+  float* bb = (float*)c->get(sizeof(float) * 6 * kBboxBlocks);
+  int* d_idx = (int*)c->get(4 * m * (size_t)k);
+  float* d_d2 = (float*)c->get(4 * m * (size_t)k);
+  if (!qraw || !q4 || !bb || !d_idx || !d_d2) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (knn)");
+  CK(c, cudaMemcpyAsync(qraw, queries, m * qstride, cudaMemcpyHostToDevice, c->stream));
+  k_ingest<<<kBboxBlocks, 256, 0, c->stream>>>((const unsigned char*)qraw, qstride, (int)m, q4, bb);
+  CKL(c);
+  TRY(launch_knn<false>(c, cl.view, q4, (int)m, k, d_idx, d_d2));
+  CK(c, cudaMemcpyAsync(idx, d_idx, 4 * m * (size_t)k, cudaMemcpyDeviceToHost, c->stream));
+  if (d2) CK(c, cudaMemcpyAsync(d2, d_d2, 4 * m * (size_t)k, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  c->put(qraw);
+  c->put(q4);
+  c->put(bb);
+  c->put(d_idx);
+  c->put(d_d2);
+  cloud_release(c, cl);
+  return RGC_OK;
+}
+
+int rgc_reg_stage_ms(const rgc_reg* r, float* ms7) {
+  if (!r || !ms7) return RGC_ERR_INVALID;
+  ms7[0] = r->src.build_ms;
+  ms7[1] = r->src.knn_ms;
+  ms7[2] = r->src.cov_ms;
+  ms7[3] = r->tgt.build_ms;
+  ms7[4] = r->tgt.knn_ms;
+  ms7[5] = r->tgt.cov_ms;
+  ms7[6] = r->lm_ms;
+  return RGC_OK;
+}
+
+}  // extern "C"

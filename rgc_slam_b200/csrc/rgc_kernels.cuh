@@ -1,0 +1,466 @@
+// rgc_kernels.cuh — sm_100a kernels of the scan-matching path (included by rgc_gicp.cu only).
+//
+// Kernel inventory (each cites the reference code it replaces):
+//   k_ingest          AoS point cloud (any PCL stride) -> float4 SoA + per-block bbox partials
+//   k_morton          Morton key of the finest voxel of every point
+//   k_rs_hist / k_rs_scan / k_rs_scatter   LSD radix sort (8-bit digits, stable)
+//   k_gather_sorted   points in Morton order, original index packed in .w
+//   k_count_cells / k_build_tables         per-level voxel hash tables over the sorted array
+//   k_knn             exact kNN (pcl::search::KdTree::nearestKSearch; fast_gicp_impl.hpp:133,254)
+//   k_covariance      k-neighbour covariance + regularisation (fast_gicp_impl.hpp:256-293)
+//   k_linearize       1-NN + Mahalanobis + H/b/err reduction (fast_gicp_impl.hpp:115-211)
+//   k_compute_error   err reduction with frozen correspondences (fast_gicp_impl.hpp:214-237)
+//   k_fitness         pcl::Registration::getFitnessScore
+//   k_transform_out   pcl::transformPointCloud (lsq_registration_impl.hpp:78)
+#pragma once
+#include <cuda_runtime.h>
+
+#include "rgc_grid.cuh"
+#include "rgc_math.cuh"
+
+namespace rgc {
+
+constexpr int kBboxBlocks = 296;  // 2 x 148 SMs
+constexpr int kThreads = 128;
+
+// ------------------------------------------------------------------------------------------------
+// ingest: raw[n] with byte stride (xyz at offset 0, as every PCL point type) -> float4(x,y,z,1)
+// plus per-block min/max partials (reduced on the host: 296 x 6 floats).
+__global__ void __launch_bounds__(256) k_ingest(const unsigned char* __restrict__ raw, size_t stride, int n, float4* __restrict__ out,
+                                                float* __restrict__ bbox_partials) {
+  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float* p = reinterpret_cast<const float*>(raw + (size_t)i * stride);
+    float x = p[0], y = p[1], z = p[2];
+    if (out) out[i] = make_float4(x, y, z, 1.0f);
+    mn[0] = fminf(mn[0], x); mx[0] = fmaxf(mx[0], x);
+    mn[1] = fminf(mn[1], y); mx[1] = fmaxf(mx[1], y);
+    mn[2] = fminf(mn[2], z); mx[2] = fmaxf(mx[2], z);
+  }
+  __shared__ float sm[8][6];
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+    }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0)
+    for (int a = 0; a < 3; a++) {
+      sm[warp][a] = mn[a];
+      sm[warp][3 + a] = mx[a];
+    }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    float v = sm[0][threadIdx.x];
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++) v = threadIdx.x < 3 ? fminf(v, sm[w][threadIdx.x]) : fmaxf(v, sm[w][threadIdx.x]);
+    bbox_partials[blockIdx.x * 6 + threadIdx.x] = v;
+  }
+}
+
+struct GridGeom {
+  float ox, oy, oz, inv_s0;
+  int nbits;
+};
+
+__global__ void __launch_bounds__(256) k_morton(const float4* __restrict__ pts, int n, GridGeom g, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = pts[i];
+  const int hi = (1 << g.nbits) - 1;
+  int cx = min(max(cell_coord(p.x, g.ox, g.inv_s0), 0), hi);
+  int cy = min(max(cell_coord(p.y, g.oy, g.inv_s0), 0), hi);
+  int cz = min(max(cell_coord(p.z, g.oz, g.inv_s0), 0), hi);
+  keys[i] = morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
+  vals[i] = (uint32_t)i;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LSD radix sort, 8-bit digits.  Tile = 256 threads x RS_ITEMS keys; inside a tile the key order
+// is (warp, round, lane) == ascending index, so ranks computed per (warp, round) with match_any
+// are stable.  hist is digit-major [256][nblk] so one exclusive scan yields every block's base.
+constexpr int RS_ITEMS = 8;
+constexpr int RS_TILE = 256 * RS_ITEMS;
+
+__global__ void __launch_bounds__(256) k_rs_hist(const uint64_t* __restrict__ keys, int n, int shift, uint32_t* __restrict__ hist, int nblk) {
+  __shared__ uint32_t h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const int base = blockIdx.x * RS_TILE;
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; r++) {
+    int i = base + r * 256 + threadIdx.x;
+    if (i < n) atomicAdd(&h[(uint32_t)(keys[i] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  hist[threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];
+}
+
+// single-block exclusive scan over m = 256*nblk counters
+__global__ void __launch_bounds__(1024) k_rs_scan(uint32_t* __restrict__ hist, int m) {
+  __shared__ uint32_t warp_sums[32];
+  const int per = (m + 1023) / 1024;
+  const int lo = threadIdx.x * per, hi = min(lo + per, m);
+  uint32_t s = 0;
+  for (int i = lo; i < hi; i++) s += hist[i];
+  // block exclusive scan of s
+  uint32_t v = s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  if (lane == 31) warp_sums[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = warp_sums[lane];
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += t;
+    }
+    warp_sums[lane] = w;
+  }
+  __syncthreads();
+  uint32_t excl = v - s + (warp > 0 ? warp_sums[warp - 1] : 0u);
+  for (int i = lo; i < hi; i++) {
+    uint32_t c = hist[i];
+    hist[i] = excl;
+    excl += c;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_rs_scatter(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                                                    uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+                                                    const uint32_t* __restrict__ offsets, int n, int shift, int nblk) {
+  __shared__ uint32_t cnt[8][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp_base = blockIdx.x * RS_TILE + warp * (32 * RS_ITEMS);
+  for (int i = threadIdx.x; i < 8 * 256; i += 256) (&cnt[0][0])[i] = 0;
+  __syncthreads();
+  uint64_t k[RS_ITEMS];
+  uint32_t d[RS_ITEMS];
+  const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; r++) {
+    int i = warp_base + r * 32 + lane;
+    bool valid = i < n;
+    k[r] = valid ? keys_in[i] : 0ull;
+    d[r] = valid ? ((uint32_t)(k[r] >> shift) & 255u) : (256u + lane);  // invalid lanes never match
+    uint32_t peers = __match_any_sync(0xffffffffu, d[r]);
+    if (valid && (peers & lt_mask) == 0) cnt[warp][d[r]] += __popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
+  {  // per digit: running base over the 8 warps
+    uint32_t base = offsets[threadIdx.x * nblk + blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+      uint32_t c = cnt[w][threadIdx.x];
+      cnt[w][threadIdx.x] = base;
+      base += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; r++) {
+    int i = warp_base + r * 32 + lane;
+    bool valid = i < n;
+    uint32_t peers = __match_any_sync(0xffffffffu, d[r]);
+    uint32_t rank = __popc(peers & lt_mask);
+    uint32_t off = valid ? cnt[warp][d[r]] : 0u;
+    __syncwarp();
+    if (valid && rank == 0) cnt[warp][d[r]] = off + __popc(peers);
+    __syncwarp();
+    if (valid) {
+      keys_out[off + rank] = k[r];
+      vals_out[off + rank] = vals_in[i];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_gather_sorted(const float4* __restrict__ pts, const uint32_t* __restrict__ vals, int n, float4* __restrict__ sorted) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t o = vals[i];
+  float4 p = pts[o];
+  p.w = __int_as_float((int)o);
+  sorted[i] = p;
+}
+
+// cells per level: point i opens a new cell at every level l with 3l <= highest differing bit
+__global__ void __launch_bounds__(256) k_count_cells(const uint64_t* __restrict__ keys, int n, int nlevels, uint32_t* __restrict__ counts) {
+  __shared__ uint32_t c[kMaxLevels];
+  if (threadIdx.x < kMaxLevels) c[threadIdx.x] = 0;
+  __syncthreads();
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    int top;  // highest level at which i starts a new cell
+    if (i == 0)
+      top = nlevels - 1;
+    else {
+      uint64_t x = keys[i] ^ keys[i - 1];
+      top = x ? min((63 - __clzll((long long)x)) / 3, nlevels - 1) : -1;
+    }
+    for (int l = 0; l <= top; l++) atomicAdd(&c[l], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < nlevels && c[threadIdx.x]) atomicAdd(&counts[threadIdx.x], c[threadIdx.x]);
+}
+
+struct TableSet {
+  GridSlot* table[kMaxLevels];
+  uint32_t mask[kMaxLevels];
+  int nlevels;
+};
+
+__device__ __forceinline__ GridSlot* slot_insert_or_find(GridSlot* tab, uint32_t mask, uint64_t key) {
+  uint32_t h = (uint32_t)mix64(key) & mask;
+  for (;;) {
+    unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long*>(&tab[h].key), (unsigned long long)kEmptyKey, (unsigned long long)key);
+    if (prev == kEmptyKey || prev == key) return &tab[h];
+    h = (h + 1) & mask;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_build_tables(const uint64_t* __restrict__ keys, int n, TableSet ts) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t key = keys[i];
+  int top;
+  uint64_t prev = 0;
+  if (i == 0)
+    top = ts.nlevels - 1;
+  else {
+    prev = keys[i - 1];
+    uint64_t x = key ^ prev;
+    top = x ? min((63 - __clzll((long long)x)) / 3, ts.nlevels - 1) : -1;
+  }
+  for (int l = 0; l <= top; l++) {
+    slot_insert_or_find(ts.table[l], ts.mask[l], key >> (3 * l))->start = (uint32_t)i;
+    if (i > 0) slot_insert_or_find(ts.table[l], ts.mask[l], prev >> (3 * l))->end = (uint32_t)i;
+  }
+  if (i == n - 1)
+    for (int l = 0; l < ts.nlevels; l++) slot_insert_or_find(ts.table[l], ts.mask[l], key >> (3 * l))->end = (uint32_t)n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kNN.  SELF: queries are the grid's own sorted points (thread t <-> sorted point t) and the
+// result is stored k-major as sorted positions for k_covariance.  Otherwise queries are float4
+// and results go out row-major [m][k] as ORIGINAL indices + d2 (test hook / public rgc_knn).
+template <int KCAP, bool SELF>
+__global__ void __launch_bounds__(kThreads, (KCAP >= 32 ? 2 : (KCAP >= 20 ? 4 : 8))) k_knn(GridView g, const float4* __restrict__ queries, int m, int k, int* __restrict__ out_idx,
+                                                  float* __restrict__ out_d2) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= m) return;
+  float4 q = SELF ? reinterpret_cast<const float4*>(g.pts)[t] : queries[t];
+  TopK<KCAP> top;
+  knn_search<KCAP>(g, q.x, q.y, q.z, k, INFINITY, -1, top);
+  const int first = KCAP - k;  // slot of the best entry (TopK keeps the k live entries last)
+  if (SELF) {
+#pragma unroll
+    for (int j = 0; j < KCAP; j++)
+      if (j >= first) out_idx[(size_t)(j - first) * m + t] = top.id[j];
+  } else {
+#pragma unroll
+    for (int j = 0; j < KCAP; j++)
+      if (j >= first) {
+        int id = top.id[j];
+        out_idx[(size_t)t * k + (j - first)] = id >= 0 ? __float_as_int(g.pts[id].w) : -1;
+        if (out_d2) out_d2[(size_t)t * k + (j - first)] = top.d[j];
+      }
+  }
+}
+
+// covariance of sorted point t from its k neighbour positions (k-major), regularised; 6 doubles out
+__global__ void __launch_bounds__(kThreads, 4) k_covariance(const float4* __restrict__ pts, const int* __restrict__ nbr, int n, int k, int method,
+                                                         double* __restrict__ cov) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  int found = 0;
+  while (found < k && nbr[(size_t)found * n + t] >= 0) found++;
+  Sym3 c = covariance_from_points(found, k, [&](int j) {
+    float4 p = __ldg(&pts[nbr[(size_t)j * n + t]]);
+    return F4{p.x, p.y, p.z, p.w};
+  });
+  Sym3 r = regularize_cov(c, method);
+  double2* o = reinterpret_cast<double2*>(cov + (size_t)t * 6);
+  o[0] = make_double2(r.xx, r.xy);
+  o[1] = make_double2(r.xz, r.yy);
+  o[2] = make_double2(r.yz, r.zz);
+}
+
+__device__ __forceinline__ Sym3 load_sym3(const double* __restrict__ base, size_t i) {
+  const double2* p = reinterpret_cast<const double2*>(base + i * 6);
+  double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+  return Sym3{a.x, a.y, b.x, b.y, c.x, c.y};
+}
+__device__ __forceinline__ void store_sym3(double* __restrict__ base, size_t i, const Sym3& s) {
+  double2* p = reinterpret_cast<double2*>(base + i * 6);
+  p[0] = make_double2(s.xx, s.xy);
+  p[1] = make_double2(s.xz, s.yy);
+  p[2] = make_double2(s.yz, s.zz);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Deterministic grid reduction of NV doubles per thread: warp shuffle -> smem -> per-block partial
+// -> the last block to finish sums the partials in block order and writes `result` (which may be
+// mapped pinned host memory).  The order is fixed by the launch shape, so results are
+// bit-reproducible run to run (the reference's OpenMP sums are not).
+template <int NV>
+__device__ __forceinline__ void grid_reduce(double* v, double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ result) {
+  __shared__ double sm[kThreads / 32][NV];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < NV; j++) {
+    double x = v[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    if (lane == 0) sm[warp][j] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double s = sm[0][threadIdx.x];
+#pragma unroll
+    for (int w = 1; w < kThreads / 32; w++) s += sm[w][threadIdx.x];
+    partials[(size_t)blockIdx.x * NV + threadIdx.x] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    if (threadIdx.x < NV) {
+      double s = 0.0;
+      for (unsigned b = 0; b < gridDim.x; b++) s += __ldcg(&partials[(size_t)b * NV + threadIdx.x]);
+      result[threadIdx.x] = s;
+    }
+    if (threadIdx.x == 0) *ticket = 0;
+    __threadfence_system();
+  }
+}
+
+struct RtF {
+  float m[12];
+};
+
+constexpr int kLinN = kAccN + 1;  // + inlier count
+
+// fused update_correspondences + linearize (fast_gicp_impl.hpp:115-211).  One thread per source
+// point (Morton order).  Stores the correspondence (sorted target position), its d2 and M for
+// the compute_error calls that follow.
+__global__ void __launch_bounds__(kThreads, 4) k_linearize(GridView tgt, const float4* __restrict__ src, const double* __restrict__ src_cov,
+                                                        const double* __restrict__ tgt_cov, int n_src, RtF Tf, Rt Td, float thr2, int want_hb,
+                                                        int* __restrict__ corr, float* __restrict__ sqd, double* __restrict__ maha,
+                                                        double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ result) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int pos = -1;
+  float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < n_src) {
+    p = __ldg(&src[i]);
+    float qx, qy, qz;
+    transform_f(Tf.m, p.x, p.y, p.z, qx, qy, qz);
+    TopK<1> top;
+    knn_search<1>(tgt, qx, qy, qz, 1, thr2, -1, top);
+    pos = (top.id[0] >= 0 && top.d[0] < thr2) ? top.id[0] : -1;
+    corr[i] = pos;
+    sqd[i] = top.d[0];
+  }
+  // accumulators are declared only after the search so they are not live across it
+  double acc[kLinN];
+#pragma unroll
+  for (int j = 0; j < kLinN; j++) acc[j] = 0.0;
+  if (pos >= 0) {
+    const F4 q = load_pt(tgt.pts + pos);
+    const Sym3 CA = load_sym3(src_cov, i);
+    const Sym3 CB = load_sym3(tgt_cov, pos);
+    const Sym3 M = gicp_mahalanobis(Td, CA, CB);
+    store_sym3(maha, i, M);
+    if (want_hb)
+      gicp_point_terms(Td, M, p.x, p.y, p.z, q.x, q.y, q.z, acc);
+    else
+      acc[0] = gicp_error_term(Td, M, p.x, p.y, p.z, q.x, q.y, q.z);
+    acc[kAccN] = 1.0;
+  }
+  grid_reduce<kLinN>(acc, partials, ticket, result);
+}
+
+// fast_gicp_impl.hpp:214-237 — correspondences and M frozen from the last k_linearize
+__global__ void __launch_bounds__(kThreads) k_compute_error(const float4* __restrict__ tgt_pts, const float4* __restrict__ src, int n_src, Rt Td,
+                                                            const int* __restrict__ corr, const double* __restrict__ maha,
+                                                            double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ result) {
+  double acc[1] = {0.0};
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_src) {
+    const int pos = corr[i];
+    if (pos >= 0) {
+      const float4 p = __ldg(&src[i]);
+      const float4 q = __ldg(&tgt_pts[pos]);
+      const Sym3 M = load_sym3(maha, i);
+      acc[0] = gicp_error_term(Td, M, p.x, p.y, p.z, q.x, q.y, q.z);
+    }
+  }
+  grid_reduce<1>(acc, partials, ticket, result);
+}
+
+// pcl::Registration::getFitnessScore: [sum d2, count] over 1-NN d2 <= max_range
+__global__ void __launch_bounds__(kThreads, 8) k_fitness(GridView tgt, const float4* __restrict__ src, int n_src, RtF Tf, double max_range,
+                                                      double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ result) {
+  double acc[2] = {0.0, 0.0};
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_src) {
+    const float4 p = __ldg(&src[i]);
+    float qx, qy, qz;
+    transform_f(Tf.m, p.x, p.y, p.z, qx, qy, qz);
+    TopK<1> top;
+    knn_search<1>(tgt, qx, qy, qz, 1, INFINITY, -1, top);
+    if (top.id[0] >= 0 && (double)top.d[0] <= max_range) {
+      acc[0] = (double)top.d[0];
+      acc[1] = 1.0;
+    }
+  }
+  grid_reduce<2>(acc, partials, ticket, result);
+}
+
+__global__ void __launch_bounds__(256) k_transform_out(const float4* __restrict__ src_sorted, int n, RtF Tf, float4* __restrict__ out_orig_order) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = src_sorted[i];
+  float x, y, z;
+  transform_f(Tf.m, p.x, p.y, p.z, x, y, z);
+  out_orig_order[__float_as_int(p.w)] = make_float4(x, y, z, 1.0f);
+}
+
+// correspondences in the caller's index space
+__global__ void __launch_bounds__(256) k_corr_to_orig(const float4* __restrict__ src_sorted, const float4* __restrict__ tgt_sorted, const int* __restrict__ corr,
+                                                      const float* __restrict__ sqd, int n, int* __restrict__ corr_out, float* __restrict__ sqd_out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int o = __float_as_int(src_sorted[i].w);
+  int c = corr[i];
+  corr_out[o] = c >= 0 ? __float_as_int(tgt_sorted[c].w) : -1;
+  sqd_out[o] = sqd[i];
+}
+
+// covariances between the caller's layout (4x4 doubles, original order) and ours (6 doubles, sorted)
+__global__ void __launch_bounds__(256) k_cov_import(const float4* __restrict__ sorted, int n, const double* __restrict__ m4x4, double* __restrict__ cov6) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* m = m4x4 + (size_t)__float_as_int(sorted[i].w) * 16;
+  // column-major or row-major is irrelevant for the symmetric 3x3 block; take the upper triangle
+  double* o = cov6 + (size_t)i * 6;
+  o[0] = m[0]; o[1] = m[4]; o[2] = m[8]; o[3] = m[5]; o[4] = m[9]; o[5] = m[10];
+}
+__global__ void __launch_bounds__(256) k_cov_export(const float4* __restrict__ sorted, int n, const double* __restrict__ cov6, double* __restrict__ m4x4) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double* m = m4x4 + (size_t)__float_as_int(sorted[i].w) * 16;
+  const double* c = cov6 + (size_t)i * 6;
+  m[0] = c[0]; m[1] = c[1]; m[2] = c[2]; m[3] = 0.0;
+  m[4] = c[1]; m[5] = c[3]; m[6] = c[4]; m[7] = 0.0;
+  m[8] = c[2]; m[9] = c[4]; m[10] = c[5]; m[11] = 0.0;
+  m[12] = 0.0; m[13] = 0.0; m[14] = 0.0; m[15] = 0.0;
+}
+
+}  // namespace rgc

@@ -1,0 +1,263 @@
+// rgc_math.cuh — per-point fp64 algebra of the GICP path (host/device, see rgc_common.cuh).
+//
+//  * covariance_from_points  : centred 3x3 covariance / k and its regularisation
+//                              (fast_gicp_impl.hpp:256-293)
+//  * gicp_mahalanobis        : M = (C_B + R C_A R^T)^-1          (fast_gicp_impl.hpp:146-150)
+//  * gicp_point_terms        : e^T M e, H = J^T M J, b = J^T M e  (fast_gicp_impl.hpp:173-198)
+//
+// Symmetric 3x3 matrices are stored as 6 doubles {xx, xy, xz, yy, yz, zz}.
+#pragma once
+#include "rgc_common.cuh"
+
+namespace rgc {
+
+struct Sym3 {
+  double xx, xy, xz, yy, yz, zz;
+};
+
+// Cyclic Jacobi eigen-decomposition of a symmetric 3x3 (fp64).  On return A ~ V diag(w) V^T,
+// V column-major-by-index: V[r][c] = component r of eigenvector c.  Unsorted.
+// The reference uses Eigen::JacobiSVD on the same PSD matrix (fast_gicp_impl.hpp:273); for a
+// symmetric PSD input its U and V equal the eigenvectors (up to the sign pairing handled by the
+// caller), so an eigen-solver gives the same U diag(values) V^T.
+RGC_HD void eig_sym3(const Sym3& A, double w[3], double V[3][3]) {
+  double a[3][3] = {{A.xx, A.xy, A.xz}, {A.xy, A.yy, A.yz}, {A.xz, A.yz, A.zz}};
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) V[i][j] = (i == j) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 12; sweep++) {
+    double off = fabs(a[0][1]) + fabs(a[0][2]) + fabs(a[1][2]);
+    double diag = fabs(a[0][0]) + fabs(a[1][1]) + fabs(a[2][2]);
+    if (off <= 1e-18 * diag || off < 1e-300) break;
+#pragma unroll
+    for (int pq = 0; pq < 3; pq++) {
+      const int p = (pq == 2) ? 1 : 0;
+      const int q = (pq == 0) ? 1 : 2;
+      double apq = a[p][q];
+      if (fabs(apq) < 1e-300) continue;
+      double tau = (a[q][q] - a[p][p]) / (2.0 * apq);
+      double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+      double c = 1.0 / sqrt(1.0 + t * t), s = t * c;
+      // A <- J^T A J with J = [[c, s], [-s, c]] on (p,q)
+      a[p][p] -= t * apq;
+      a[q][q] += t * apq;
+      a[p][q] = a[q][p] = 0.0;
+      const int r = 3 - p - q;
+      double arp = a[r][p], arq = a[r][q];
+      a[r][p] = a[p][r] = c * arp - s * arq;
+      a[r][q] = a[q][r] = s * arp + c * arq;
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        double vip = V[i][p], viq = V[i][q];
+        V[i][p] = c * vip - s * viq;
+        V[i][q] = s * vip + c * viq;
+      }
+    }
+  }
+  w[0] = a[0][0];
+  w[1] = a[1][1];
+  w[2] = a[2][2];
+}
+
+RGC_HD Sym3 inv_sym3(const Sym3& m) {
+  double c00 = m.yy * m.zz - m.yz * m.yz;
+  double c01 = m.xz * m.yz - m.xy * m.zz;
+  double c02 = m.xy * m.yz - m.xz * m.yy;
+  double det = m.xx * c00 + m.xy * c01 + m.xz * c02;
+  double id = 1.0 / det;
+  Sym3 r;
+  r.xx = c00 * id;
+  r.xy = c01 * id;
+  r.xz = c02 * id;
+  r.yy = (m.xx * m.zz - m.xz * m.xz) * id;
+  r.yz = (m.xy * m.xz - m.xx * m.yz) * id;
+  r.zz = (m.xx * m.yy - m.xy * m.xy) * id;
+  return r;
+}
+
+// sum_i val[i] * sign_i * v_i v_i^T  — the reference's U diag(values) V^T where JacobiSVD sets
+// U.col(i) = sign(lambda_i) * V.col(i) (a negative eigenvalue of the PSD input can only come
+// from round-off; we reproduce the resulting sign instead of "fixing" it).
+RGC_HD Sym3 recompose(const double V[3][3], const double val[3], const double sgn[3]) {
+  Sym3 r = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    double f = val[c] * sgn[c];
+    r.xx += f * V[0][c] * V[0][c];
+    r.xy += f * V[0][c] * V[1][c];
+    r.xz += f * V[0][c] * V[2][c];
+    r.yy += f * V[1][c] * V[1][c];
+    r.yz += f * V[1][c] * V[2][c];
+    r.zz += f * V[2][c] * V[2][c];
+  }
+  return r;
+}
+
+// fast_gicp_impl.hpp:264-293
+RGC_HD Sym3 regularize_cov(const Sym3& cov, int method) {
+  if (method == REG_NONE) return cov;
+  if (method == REG_FROBENIUS) {
+    const double lambda = 1e-3;
+    Sym3 C = cov;
+    C.xx += lambda;
+    C.yy += lambda;
+    C.zz += lambda;
+    Sym3 Ci = inv_sym3(C);
+    double nrm = sqrt(Ci.xx * Ci.xx + Ci.yy * Ci.yy + Ci.zz * Ci.zz + 2.0 * (Ci.xy * Ci.xy + Ci.xz * Ci.xz + Ci.yz * Ci.yz));
+    double s = 1.0 / nrm;
+    Sym3 Cn = {Ci.xx * s, Ci.xy * s, Ci.xz * s, Ci.yy * s, Ci.yz * s, Ci.zz * s};
+    return inv_sym3(Cn);
+  }
+  double w[3], V[3][3];
+  eig_sym3(cov, w, V);
+  // singular values = |eigenvalues|; rank them descending like JacobiSVD's final sort
+  double sv[3] = {fabs(w[0]), fabs(w[1]), fabs(w[2])};
+  double sgn[3] = {w[0] < 0 ? -1.0 : 1.0, w[1] < 0 ? -1.0 : 1.0, w[2] < 0 ? -1.0 : 1.0};
+  int rank[3];  // rank[c] = position of column c in descending order
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    int r = 0;
+#pragma unroll
+    for (int o = 0; o < 3; o++)
+      if (o != c && (sv[o] > sv[c] || (sv[o] == sv[c] && o < c))) r++;
+    rank[c] = r;
+  }
+  double val[3];
+  if (method == REG_PLANE) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) val[c] = (rank[c] == 2) ? 1e-3 : 1.0;
+  } else if (method == REG_MIN_EIG) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) val[c] = sv[c] > 1e-3 ? sv[c] : 1e-3;
+  } else {  // REG_NORMALIZED_MIN_EIG
+    double mx = sv[0] > sv[1] ? (sv[0] > sv[2] ? sv[0] : sv[2]) : (sv[1] > sv[2] ? sv[1] : sv[2]);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      double v = sv[c] / mx;
+      val[c] = v > 1e-3 ? v : 1e-3;
+    }
+  }
+  return recompose(V, val, sgn);
+}
+
+// Row-major 3x4 rigid transform in double.
+struct Rt {
+  double m[12];
+};
+
+RGC_HD void transform_d(const Rt& T, double x, double y, double z, double& ox, double& oy, double& oz) {
+  ox = ((T.m[0] * x + T.m[1] * y) + T.m[2] * z) + T.m[3];
+  oy = ((T.m[4] * x + T.m[5] * y) + T.m[6] * z) + T.m[7];
+  oz = ((T.m[8] * x + T.m[9] * y) + T.m[10] * z) + T.m[11];
+}
+
+// M = (C_B + R C_A R^T)^-1 (the 4x4 of the reference is block diagonal with a pinned 1, so its
+// inverse is this 3x3 inverse; fast_gicp_impl.hpp:146-150)
+RGC_HD Sym3 gicp_mahalanobis(const Rt& T, const Sym3& CA, const Sym3& CB) {
+  const double* R = T.m;
+  double RC[3][3];
+  const double A[3][3] = {{CA.xx, CA.xy, CA.xz}, {CA.xy, CA.yy, CA.yz}, {CA.xz, CA.yz, CA.zz}};
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) RC[i][j] = R[i * 4 + 0] * A[0][j] + R[i * 4 + 1] * A[1][j] + R[i * 4 + 2] * A[2][j];
+  Sym3 S;
+  S.xx = CB.xx + (RC[0][0] * R[0] + RC[0][1] * R[1] + RC[0][2] * R[2]);
+  S.xy = CB.xy + (RC[0][0] * R[4] + RC[0][1] * R[5] + RC[0][2] * R[6]);
+  S.xz = CB.xz + (RC[0][0] * R[8] + RC[0][1] * R[9] + RC[0][2] * R[10]);
+  S.yy = CB.yy + (RC[1][0] * R[4] + RC[1][1] * R[5] + RC[1][2] * R[6]);
+  S.yz = CB.yz + (RC[1][0] * R[8] + RC[1][1] * R[9] + RC[1][2] * R[10]);
+  S.zz = CB.zz + (RC[2][0] * R[8] + RC[2][1] * R[9] + RC[2][2] * R[10]);
+  return inv_sym3(S);
+}
+
+// Accumulator layout of one linearize() reduction: 28 doubles + 1 inlier count
+//   [0]      sum e^T M e
+//   [1..21]  upper triangle of H (6x6), row-major: (0,0)(0,1)..(0,5)(1,1)..(5,5)
+//   [22..27] b
+constexpr int kAccN = 28;
+
+RGC_HD double gicp_error_term(const Rt& T, const Sym3& M, float px, float py, float pz, float qx, float qy, float qz) {
+  double ax, ay, az;
+  transform_d(T, (double)px, (double)py, (double)pz, ax, ay, az);
+  const double ex = (double)qx - ax, ey = (double)qy - ay, ez = (double)qz - az;
+  const double mx = M.xx * ex + M.xy * ey + M.xz * ez;
+  const double my = M.xy * ex + M.yy * ey + M.yz * ez;
+  const double mz = M.xz * ex + M.yz * ey + M.zz * ez;
+  return ex * mx + ey * my + ez * mz;
+}
+
+// acc += terms of one correspondence.  J = [skew(a) | -I], a = T p.
+RGC_HD void gicp_point_terms(const Rt& T, const Sym3& M, float px, float py, float pz, float qx, float qy, float qz, double* acc) {
+  double a[3];
+  transform_d(T, (double)px, (double)py, (double)pz, a[0], a[1], a[2]);
+  const double e[3] = {(double)qx - a[0], (double)qy - a[1], (double)qz - a[2]};
+  const double Mm[3][3] = {{M.xx, M.xy, M.xz}, {M.xy, M.yy, M.yz}, {M.xz, M.yz, M.zz}};
+  double Me[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) Me[i] = Mm[i][0] * e[0] + Mm[i][1] * e[1] + Mm[i][2] * e[2];
+  acc[0] += e[0] * Me[0] + e[1] * Me[1] + e[2] * Me[2];
+  // J (3x6): columns 0..2 = skew(a), columns 3..5 = -I
+  const double J[3][6] = {{0.0, -a[2], a[1], -1.0, 0.0, 0.0}, {a[2], 0.0, -a[0], 0.0, -1.0, 0.0}, {-a[1], a[0], 0.0, 0.0, 0.0, -1.0}};
+  double MJ[3][6];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int c = 0; c < 6; c++) MJ[i][c] = Mm[i][0] * J[0][c] + Mm[i][1] * J[1][c] + Mm[i][2] * J[2][c];
+  int o = 1;
+#pragma unroll
+  for (int r = 0; r < 6; r++)
+#pragma unroll
+    for (int c = r; c < 6; c++) {
+      acc[o] += J[0][r] * MJ[0][c] + J[1][r] * MJ[1][c] + J[2][r] * MJ[2][c];
+      o++;
+    }
+#pragma unroll
+  for (int r = 0; r < 6; r++) acc[22 + r] += J[0][r] * Me[0] + J[1][r] * Me[1] + J[2][r] * Me[2];
+}
+
+// Centred covariance of `found` gathered points (k columns; missing columns are zero, matching
+// the oracle's handling of k > N), divided by k.  fast_gicp_impl.hpp:256-262.
+template <class GetPt>
+RGC_HD Sym3 covariance_from_points(int found, int k, GetPt get) {
+  double mx = 0.0, my = 0.0, mz = 0.0;
+  for (int j = 0; j < found; j++) {
+    F4 p = get(j);
+    mx += (double)p.x;
+    my += (double)p.y;
+    mz += (double)p.z;
+  }
+  const double ik = 1.0 / (double)k;
+  mx *= ik;
+  my *= ik;
+  mz *= ik;
+  Sym3 c = {0, 0, 0, 0, 0, 0};
+  for (int j = 0; j < found; j++) {
+    F4 p = get(j);
+    double dx = (double)p.x - mx, dy = (double)p.y - my, dz = (double)p.z - mz;
+    c.xx += dx * dx;
+    c.xy += dx * dy;
+    c.xz += dx * dz;
+    c.yy += dy * dy;
+    c.yz += dy * dz;
+    c.zz += dz * dz;
+  }
+  const int missing = k - found;  // zero columns still get centred: each contributes mean*mean^T
+  if (missing > 0) {
+    double m = (double)missing;
+    c.xx += m * mx * mx;
+    c.xy += m * mx * my;
+    c.xz += m * mx * mz;
+    c.yy += m * my * my;
+    c.yz += m * my * mz;
+    c.zz += m * mz * mz;
+  }
+  c.xx *= ik;
+  c.xy *= ik;
+  c.xz *= ik;
+  c.yy *= ik;
+  c.yz *= ik;
+  c.zz *= ik;
+  return c;
+}
+
+}  // namespace rgc

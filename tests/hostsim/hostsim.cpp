@@ -1,0 +1,175 @@
+// tests/hostsim/hostsim.cpp — TEST-ONLY CPU simulation of the kernels' per-thread logic.
+//
+// Compiles the host/device headers of the product (rgc_grid.cuh, rgc_math.cuh) with g++ and
+// runs one "thread" per point in plain loops, building the Morton order and level tables the way
+// the CUDA build pipeline does.  Lets the CPU test-suite check the grid search, covariance and
+// linearize arithmetic against the oracle in a container that has no GPU.  It is never linked
+// into librgc_gicp.so and is not a fallback: the product library has no CPU path.
+#include <algorithm>
+#include <cstdio>
+#include <numeric>
+#include <vector>
+
+#include "../../rgc_slam_b200/csrc/rgc_grid.cuh"
+#include "../../rgc_slam_b200/csrc/rgc_math.cuh"
+
+using namespace rgc;
+
+struct SimCloud {
+  std::vector<F4> sorted;
+  std::vector<std::vector<GridSlot>> tables;
+  GridView v{};
+};
+
+static void sim_build(const float* xyzw, int n, float cell, SimCloud& c) {
+  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int i = 0; i < n; i++)
+    for (int a = 0; a < 3; a++) {
+      mn[a] = std::min(mn[a], xyzw[4 * (size_t)i + a]);
+      mx[a] = std::max(mx[a], xyzw[4 * (size_t)i + a]);
+    }
+  GridView& v = c.v;
+  v.n = n;
+  grid_geometry(mn, mx, cell, v);
+  const int hi = (1 << v.nbits) - 1;
+  std::vector<uint64_t> keys(n);
+  std::vector<int> order(n);
+  for (int i = 0; i < n; i++) {
+    int cx = std::min(std::max(cell_coord(xyzw[4 * (size_t)i], v.ox, v.inv_s0), 0), hi);
+    int cy = std::min(std::max(cell_coord(xyzw[4 * (size_t)i + 1], v.oy, v.inv_s0), 0), hi);
+    int cz = std::min(std::max(cell_coord(xyzw[4 * (size_t)i + 2], v.oz, v.inv_s0), 0), hi);
+    keys[i] = morton3(cx, cy, cz);
+    order[i] = i;
+  }
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return keys[a] < keys[b]; });
+  c.sorted.resize(n);
+  std::vector<uint64_t> ks(n);
+  for (int i = 0; i < n; i++) {
+    int o = order[i];
+    c.sorted[i] = F4{xyzw[4 * (size_t)o], xyzw[4 * (size_t)o + 1], xyzw[4 * (size_t)o + 2], i2f_bits(o)};
+    ks[i] = keys[o];
+  }
+  c.tables.assign(v.nlevels, {});
+  for (int l = 0; l < v.nlevels; l++) {
+    size_t cells = 0;
+    for (int i = 0; i < n; i++)
+      if (i == 0 || (ks[i] >> (3 * l)) != (ks[i - 1] >> (3 * l))) cells++;
+    size_t s = 8;
+    while (s < 2 * cells) s <<= 1;
+    auto& t = c.tables[l];
+    t.assign(s, GridSlot{kEmptyKey, 0, 0});
+    uint32_t mask = (uint32_t)(s - 1);
+    int start = 0;
+    for (int i = 1; i <= n; i++) {
+      if (i == n || (ks[i] >> (3 * l)) != (ks[i - 1] >> (3 * l))) {
+        uint64_t key = ks[i - 1] >> (3 * l);
+        uint32_t h = (uint32_t)mix64(key) & mask;
+        while (t[h].key != kEmptyKey) h = (h + 1) & mask;
+        t[h] = GridSlot{key, (uint32_t)start, (uint32_t)i};
+        start = i;
+      }
+    }
+    v.table[l] = t.data();
+    v.mask[l] = mask;
+  }
+  v.pts = c.sorted.data();
+}
+
+template <int KCAP>
+static void sim_knn_t(const SimCloud& c, const float* q, int m, int k, int* idx, float* d2, long long* stats) {
+#pragma omp parallel for schedule(dynamic, 64)
+  for (int t = 0; t < m; t++) {
+    TopK<KCAP> top;
+    SearchStats st{0, 0, 0};
+    knn_search<KCAP>(c.v, q[4 * (size_t)t], q[4 * (size_t)t + 1], q[4 * (size_t)t + 2], k, INFINITY, -1, top, &st);
+    const int first = KCAP - k;
+    for (int j = first; j < KCAP; j++) {
+      int id = top.id[j];
+      idx[(size_t)t * k + (j - first)] = id >= 0 ? f2i_bits(c.sorted[id].w) : -1;
+      d2[(size_t)t * k + (j - first)] = top.d[j];
+    }
+    if (stats) {
+#pragma omp atomic
+      stats[0] += st.levels;
+#pragma omp atomic
+      stats[1] += st.lookups;
+#pragma omp atomic
+      stats[2] += st.candidates;
+    }
+  }
+}
+
+extern "C" {
+
+int sim_knn(const float* pts, int n, const float* queries, int m, int k, int* idx, float* d2, float cell, long long* stats) {
+  SimCloud c;
+  sim_build(pts, n, cell, c);
+  if (stats) stats[0] = stats[1] = stats[2] = 0;
+  if (k == 1) sim_knn_t<1>(c, queries, m, k, idx, d2, stats);
+  else if (k <= 8) sim_knn_t<8>(c, queries, m, k, idx, d2, stats);
+  else if (k <= 20) sim_knn_t<20>(c, queries, m, k, idx, d2, stats);
+  else if (k <= 32) sim_knn_t<32>(c, queries, m, k, idx, d2, stats);
+  else return -1;
+  return c.v.nlevels;
+}
+
+// covariances (column-major == row-major 4x4, symmetric) in ORIGINAL order, from given kNN lists
+void sim_covs(const float* pts, int n, const int* knn_idx, int k, int method, double* covs16) {
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n; i++) {
+    int found = 0;
+    while (found < k && knn_idx[(size_t)i * k + found] >= 0) found++;
+    Sym3 c = covariance_from_points(found, k, [&](int j) {
+      const float* p = &pts[4 * (size_t)knn_idx[(size_t)i * k + j]];
+      return F4{p[0], p[1], p[2], p[3]};
+    });
+    Sym3 r = regularize_cov(c, method);
+    double* o = &covs16[16 * (size_t)i];
+    for (int j = 0; j < 16; j++) o[j] = 0.0;
+    o[0] = r.xx; o[1] = r.xy; o[2] = r.xz;
+    o[4] = r.xy; o[5] = r.yy; o[6] = r.yz;
+    o[8] = r.xz; o[9] = r.yz; o[10] = r.zz;
+  }
+}
+
+// one linearize: T row-major 4x4 double; covs as 16-double matrices in original order.
+// out: err, H (row-major 36), b (6), corr (original target index or -1)
+void sim_linearize(const float* src, int ns, const float* tgt, int nt, const double* covA16, const double* covB16, const double* T, float thr,
+                   float cell, double* err, double* H, double* b, int* corr) {
+  SimCloud c;
+  sim_build(tgt, nt, cell, c);
+  Rt Td;
+  float Tf[12];
+  for (int i = 0; i < 12; i++) {
+    Td.m[i] = T[i];
+    Tf[i] = (float)T[i];
+  }
+  const float thr2 = thr * thr;
+  double acc[kAccN] = {0};
+  for (int i = 0; i < ns; i++) {
+    const float* p = &src[4 * (size_t)i];
+    float qx, qy, qz;
+    transform_f(Tf, p[0], p[1], p[2], qx, qy, qz);
+    TopK<1> top;
+    knn_search<1>(c.v, qx, qy, qz, 1, thr2, -1, top);
+    int pos = (top.id[0] >= 0 && top.d[0] < thr2) ? top.id[0] : -1;
+    corr[i] = pos >= 0 ? f2i_bits(c.sorted[pos].w) : -1;
+    if (pos < 0) continue;
+    const double* a = &covA16[16 * (size_t)i];
+    const double* bb = &covB16[16 * (size_t)corr[i]];
+    Sym3 CA{a[0], a[1], a[2], a[5], a[6], a[10]}, CB{bb[0], bb[1], bb[2], bb[5], bb[6], bb[10]};
+    Sym3 M = gicp_mahalanobis(Td, CA, CB);
+    F4 q = c.sorted[pos];
+    gicp_point_terms(Td, M, p[0], p[1], p[2], q.x, q.y, q.z, acc);
+  }
+  *err = acc[0];
+  int o = 1;
+  for (int i = 0; i < 6; i++)
+    for (int j = i; j < 6; j++) {
+      H[i * 6 + j] = H[j * 6 + i] = acc[o];
+      o++;
+    }
+  for (int i = 0; i < 6; i++) b[i] = acc[22 + i];
+}
+
+}  // extern "C"
