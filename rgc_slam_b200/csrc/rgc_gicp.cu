@@ -213,6 +213,8 @@ static int cloud_build(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, s
   }
   k_build_tables<<<div_up(n, 256), 256, 0, st>>>(kin, n, ts);
   CKL(c);
+  k_child_masks<<<div_up(n, 256), 256, 0, st>>>(kin, n, ts);
+  CKL(c);
   v.pts = reinterpret_cast<const F4*>(cl.sorted);
 
   c->put(staging);

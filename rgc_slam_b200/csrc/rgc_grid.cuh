@@ -12,22 +12,33 @@
 //                 because Morton order nests (an octree laid out in an array).
 // Cell size at level l is s0 * 2^l; level nbits is a single root cell.
 //
-// Search = for the query's cell c at level l, scan the 3x3x3 block around c, keep the best k by
-// (d2, original index), and stop as soon as the k-th distance is provably smaller than the
-// distance to the nearest block face that still has cells behind it; otherwise go one level
-// coarser (8x volume).  The start level is found by climbing own-cell counts (1 lookup/level).
-// Result is the exact kNN under the total order (d2, index) — independent of scan order, so
-// no sort stability or atomics ordering can change it.
+// Each slot also carries an 8-bit mask of its occupied children (top byte of the key word).
+//
+// Search (exact, density-adaptive):
+//   1. bound  = largest d2 to k points that are adjacent in Morton order to the query (k loads) —
+//               a valid upper bound on the k-th nearest distance;
+//   2. roots  = the <= 3x3x3 cells, at the finest level whose cell edge >= sqrt(bound), that
+//               intersect the ball(q, sqrt(bound));
+//   3. descend each root depth-first, nearest child first, pruning every cell whose box is
+//               farther than the current k-th best, scanning the contiguous point range of a cell
+//               once it holds <= kLeafPoints points (or is at level 0).
+// Work is proportional to the points near the ball, whatever the local density (a sparse query
+// next to a dense region never scans the dense region).  The result is the exact kNN under the
+// total order (d2, original index) — independent of scan order, sort stability or atomics.
 #pragma once
 #include "rgc_common.cuh"
 
 namespace rgc {
 
-constexpr int kMaxLevels = 22;          // nbits <= 21  (3*21 = 63-bit Morton keys)
+constexpr int kMaxBits = 18;            // cells per axis <= 2^18 (54-bit Morton keys + 8-bit child mask)
+constexpr int kMaxLevels = kMaxBits + 1;
+constexpr uint64_t kKeyMask = (1ull << 56) - 1;
+constexpr int kLeafPoints = 12;         // scan a cell directly once it holds this few points
+constexpr int kStackCap = 40;           // DFS stack entries per thread (overflow => scan the cell)
 constexpr uint64_t kEmptyKey = ~0ull;
 
 struct GridSlot {  // 16 bytes, loaded as one uint4
-  uint64_t key;
+  uint64_t key;  // [55:0] Morton key at this level, [63:56] occupied-children mask
   uint32_t start, end;
 };
 
@@ -46,16 +57,16 @@ struct GridView {
 // Grid geometry from a bounding box (host side; shared by the library and tests/hostsim so both
 // place every point in the same cell).  Sets origin, cell size, nbits/nlevels and the margin.
 inline void grid_geometry(const float mn[3], const float mx[3], float cell, GridView& v) {
-  float s0 = cell > 0.f ? cell : 0.2f;
+  float s0 = cell > 0.f ? cell : 0.05f;
   float extent = 0.f, maxabs = 0.f;
   for (int a = 0; a < 3; a++) {
     extent = fmaxf(extent, mx[a] - mn[a]);
     maxabs = fmaxf(maxabs, fmaxf(fabsf(mn[a]), fabsf(mx[a])));
   }
   extent += 2.f * s0;
-  if (extent / s0 > (float)(1 << 21)) s0 = extent / (float)(1 << 21) * 1.001f;
+  if (extent / s0 > (float)(1 << kMaxBits)) s0 = extent / (float)(1 << kMaxBits) * 1.001f;
   int nbits = 1;
-  while ((float)(1 << nbits) * s0 < extent && nbits < 21) nbits++;
+  while ((float)(1 << nbits) * s0 < extent && nbits < kMaxBits) nbits++;
   v.ox = mn[0] - s0;
   v.oy = mn[1] - s0;
   v.oz = mn[2] - s0;
@@ -117,8 +128,8 @@ RGC_HD F4 load_pt(const F4* p) {
 #endif
 }
 
-// cell (cx,cy,cz) at level l -> [start,end) ; false if the cell is empty / out of range
-RGC_HD bool grid_lookup(const GridView& g, int l, int cx, int cy, int cz, uint32_t& start, uint32_t& end) {
+// cell (cx,cy,cz) at level l -> [start,end) + child mask ; false if the cell is empty / out of range
+RGC_HD bool grid_lookup(const GridView& g, int l, int cx, int cy, int cz, uint32_t& start, uint32_t& end, uint32_t& cmask) {
   const int ncell = 1 << (g.nbits - l);
   if ((unsigned)cx >= (unsigned)ncell || (unsigned)cy >= (unsigned)ncell || (unsigned)cz >= (unsigned)ncell) return false;
   const uint64_t key = morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
@@ -127,14 +138,26 @@ RGC_HD bool grid_lookup(const GridView& g, int l, int cx, int cy, int cz, uint32
   uint32_t h = (uint32_t)mix64(key) & mask;
   for (;;) {
     GridSlot s = load_slot(tab + h);
-    if (s.key == key) {
+    if (s.key == kEmptyKey) return false;
+    if ((s.key & kKeyMask) == key) {
       start = s.start;
       end = s.end;
+      cmask = (uint32_t)(s.key >> 56);
       return true;
     }
-    if (s.key == kEmptyKey) return false;
     h = (h + 1) & mask;
   }
+}
+
+// conservative squared distance from q to the box of cell (cx,cy,cz) at level l: never larger
+// than the reference-arithmetic d2 of any point stored in that cell
+RGC_HD float box_dist2(const GridView& g, int l, int cx, int cy, int cz, float qx, float qy, float qz) {
+  const float cs = g.s0 * (float)(1 << l);
+  const float lox = g.ox + (float)cx * cs, loy = g.oy + (float)cy * cs, loz = g.oz + (float)cz * cs;
+  float gx = fmaxf(fmaxf(lox - qx, qx - (lox + cs)) - g.margin, 0.f);
+  float gy = fmaxf(fmaxf(loy - qy, qy - (loy + cs)) - g.margin, 0.f);
+  float gz = fmaxf(fmaxf(loz - qz, qz - (loz + cs)) - g.margin, 0.f);
+  return (gx * gx + gy * gy + gz * gz) * 0.999999f;
 }
 
 // ---- bounded sorted list of the k best candidates, kept in registers ---------------------------
@@ -198,86 +221,126 @@ struct TopK {
 };
 
 struct SearchStats {
-  int levels, lookups, candidates;
+  int nodes, lookups, candidates;
 };
 
-// Exact kNN of (qx,qy,qz) in grid g.  `max_d2`: candidates with d2 > max_d2 are never needed
-// (pass +inf for an unbounded search).  `level_hint` (>=0) starts the climb at that level.
-// Returns the level the search finished at (useful as the next hint).
+struct StackEntry {  // 24 bytes
+  uint32_t cx_lvl;   // cx | level << 24
+  uint32_t cy_mask;  // cy | child mask << 24
+  uint32_t cz;
+  uint32_t start, end;
+  uint32_t pad;
+};
+
 template <int KCAP>
-RGC_HD int knn_search(const GridView& g, float qx, float qy, float qz, int k, float max_d2, int level_hint, TopK<KCAP>& top,
-                      SearchStats* st = nullptr) {
-  const int fx = cell_coord(qx, g.ox, g.inv_s0);
-  const int fy = cell_coord(qy, g.oy, g.inv_s0);
-  const int fz = cell_coord(qz, g.oz, g.inv_s0);
-  const int top_level = g.nlevels - 1;
-
-  // ---- pick the start level: the parent cell at level l+1 lies inside the 3x3x3 block of
-  // level l, so the first level whose own-cell count reaches k gives a block that fills the list.
-  int l = level_hint < 0 ? 0 : (level_hint > top_level ? top_level : level_hint);
-  if (level_hint < 0) {
-    int lv = 1;
-    for (; lv <= top_level; lv++) {
-      uint32_t s, e;
-      if (st) st->lookups++;
-      if (grid_lookup(g, lv, fx >> lv, fy >> lv, fz >> lv, s, e) && (int)(e - s) >= k) break;
-    }
-    l = lv - 1;
-    if (l > top_level) l = top_level;
+RGC_HD void scan_range(const GridView& g, uint32_t s, uint32_t e, float qx, float qy, float qz, TopK<KCAP>& top, SearchStats* st) {
+  for (uint32_t p = s; p < e; p++) {
+    const F4 c = load_pt(g.pts + p);
+    const float d2 = dist2_ref(qx, qy, qz, c.x, c.y, c.z);
+    if (st) st->candidates++;
+    top.insert(d2, (int)p, f2i_bits(c.w), g.pts);
   }
+}
 
-  float prune = max_d2;
-  for (;; l++) {
-    if (l > top_level) l = top_level;
-    const int cx = fx >> l, cy = fy >> l, cz = fz >> l;
-    top.reset(k, prune);  // prune carries the best known k-th distance (or the caller's radius)
-    for (int dz = -1; dz <= 1; dz++)
-      for (int dy = -1; dy <= 1; dy++)
-        for (int dx = -1; dx <= 1; dx++) {
-          uint32_t s, e;
-          if (st) st->lookups++;
-          if (!grid_lookup(g, l, cx + dx, cy + dy, cz + dz, s, e)) continue;
-          for (uint32_t p = s; p < e; p++) {
-            F4 c = load_pt(g.pts + p);
-            float d2 = dist2_ref(qx, qy, qz, c.x, c.y, c.z);
-            if (st) st->candidates++;
-            top.insert(d2, (int)p, f2i_bits(c.w), g.pts);
-          }
-        }
-    if (st) st->levels++;
-    // ---- termination: distance to the nearest face of the block that still has cells behind it
-    const int ncell = 1 << (g.nbits - l);
-    const float cs = g.s0 * (float)(1 << l);
-    float gap = INFINITY;
-    {
-      const int c3[3] = {cx, cy, cz};
-      const float q3[3] = {qx, qy, qz};
-      const float o3[3] = {g.ox, g.oy, g.oz};
-#pragma unroll
-      for (int a = 0; a < 3; a++) {
-        if (c3[a] - 1 > 0) {  // cells exist below the low face
-          float lo = o3[a] + (float)(c3[a] - 1) * cs;
-          float ga = q3[a] - lo - g.margin;
-          gap = ga < gap ? ga : gap;
-        }
-        if (c3[a] + 2 < ncell) {  // cells exist above the high face
-          float hi = o3[a] + (float)(c3[a] + 2) * cs;
-          float ga = hi - q3[a] - g.margin;
-          gap = ga < gap ? ga : gap;
+// Exact kNN of (qx,qy,qz) in grid g, ascending by (d2, original index), into `top`.
+// `max_d2`: candidates with d2 > max_d2 are never needed (+inf = unbounded).  `near_pos`: a sorted
+// position known to be spatially close to q (the query's own position for self-kNN), or -1.
+template <int KCAP>
+RGC_HD void knn_search(const GridView& g, float qx, float qy, float qz, int k, float max_d2, int near_pos, TopK<KCAP>& top,
+                       SearchStats* st = nullptr) {
+  const int top_level = g.nlevels - 1;
+  // ---- 1. initial bound from k Morton-adjacent points
+  float bound = max_d2;
+  if (g.n >= k) {
+    int p0;
+    if (near_pos >= 0) {
+      p0 = near_pos - (k >> 1);
+    } else {
+      const int fx = cell_coord(qx, g.ox, g.inv_s0), fy = cell_coord(qy, g.oy, g.inv_s0), fz = cell_coord(qz, g.oz, g.inv_s0);
+      p0 = 0;
+      for (int l = 0; l <= top_level; l++) {
+        uint32_t s, e, m;
+        if (st) st->lookups++;
+        if (grid_lookup(g, l, fx >> l, fy >> l, fz >> l, s, e, m)) {
+          p0 = (int)s - (k >> 1) + (int)((e - s) >> 1);
+          break;
         }
       }
     }
-    if (gap == INFINITY) break;  // block covers the whole grid
-    if (gap > 0.f) {
-      const float gap2 = gap * gap * 0.999999f;
-      const bool full = top.full();
-      if (full && top.worst() < gap2) break;  // k-th best is closer than anything outside
-      if (gap2 > max_d2) break;               // everything the caller can accept has been seen
-      if (full) prune = top.worst();
+    p0 = p0 < 0 ? 0 : (p0 > g.n - k ? g.n - k : p0);
+    float far = 0.f;
+    for (int j = 0; j < k; j++) {
+      const F4 c = load_pt(g.pts + p0 + j);
+      far = fmaxf(far, dist2_ref(qx, qy, qz, c.x, c.y, c.z));
     }
-    if (l == top_level) break;  // unreachable: the top block always covers the grid
+    bound = fminf(bound, far);
   }
-  return l;
+  top.reset(k, bound);
+
+  // ---- 2. root level: finest level whose cell edge >= ball radius
+  const float r = sqrtf(bound) * 1.00001f + 2.f * g.margin;  // +inf when bound is +inf
+  int lb = 0;
+  while (lb < top_level && !(g.s0 * (float)(1 << lb) >= r)) lb++;
+  const float inv_cs = g.inv_s0 / (float)(1 << lb);
+  const int ncell = 1 << (g.nbits - lb);
+  int lo[3], hi[3];
+  {
+    const float q3[3] = {qx, qy, qz};
+    const float o3[3] = {g.ox, g.oy, g.oz};
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      float tl = (q3[a] - r - o3[a]) * inv_cs, th = (q3[a] + r - o3[a]) * inv_cs;
+      // NaN (inf - inf) cannot occur: r = +inf gives tl = -inf, th = +inf
+      int il = tl < 0.f ? 0 : (tl >= (float)ncell ? ncell : (int)tl);
+      int ih = th < 0.f ? -1 : (th >= (float)ncell ? ncell - 1 : (int)th);
+      lo[a] = il > 0 ? il - 1 : 0;                  // one cell of slack against float rounding
+      hi[a] = ih < ncell - 1 ? ih + 1 : ncell - 1;
+      if (ih < 0 || il >= ncell) hi[a] = lo[a] - 1;  // ball misses the grid on this axis
+    }
+  }
+
+  StackEntry stack[kStackCap];
+  for (int rz = lo[2]; rz <= hi[2]; rz++)
+    for (int ry = lo[1]; ry <= hi[1]; ry++)
+      for (int rx = lo[0]; rx <= hi[0]; rx++) {
+        {
+          const float cur = top.full() ? fminf(top.lim, top.worst()) : top.lim;
+          if (box_dist2(g, lb, rx, ry, rz, qx, qy, qz) > cur) continue;
+        }
+        uint32_t s, e, m;
+        if (st) st->lookups++;
+        if (!grid_lookup(g, lb, rx, ry, rz, s, e, m)) continue;
+        int sp = 0;
+        stack[sp++] = StackEntry{(uint32_t)rx | ((uint32_t)lb << 24), (uint32_t)ry | (m << 24), (uint32_t)rz, s, e, 0u};
+        // ---- 3. depth-first descent
+        while (sp > 0) {
+          const StackEntry n = stack[--sp];
+          const int l = (int)(n.cx_lvl >> 24);
+          const int cx = (int)(n.cx_lvl & 0xffffffu), cy = (int)(n.cy_mask & 0xffffffu), cz = (int)n.cz;
+          const uint32_t cm = n.cy_mask >> 24;
+          const float cur = top.full() ? fminf(top.lim, top.worst()) : top.lim;
+          if (box_dist2(g, l, cx, cy, cz, qx, qy, qz) > cur) continue;
+          if (st) st->nodes++;
+          if (l == 0 || n.end - n.start <= (uint32_t)kLeafPoints || sp + 8 > kStackCap) {
+            scan_range(g, n.start, n.end, qx, qy, qz, top, st);
+            continue;
+          }
+          // children, nearest octant first (pushed in reverse so it is popped first)
+          const float half = g.s0 * (float)(1 << (l - 1));
+          const float mx = g.ox + (float)(2 * cx + 1) * half, my = g.oy + (float)(2 * cy + 1) * half, mz = g.oz + (float)(2 * cz + 1) * half;
+          const int first = (qx >= mx ? 1 : 0) | (qy >= my ? 2 : 0) | (qz >= mz ? 4 : 0);
+          for (int j = 7; j >= 0; j--) {
+            const int ci = first ^ j;
+            if (!((cm >> ci) & 1u)) continue;
+            const int ccx = 2 * cx + (ci & 1), ccy = 2 * cy + ((ci >> 1) & 1), ccz = 2 * cz + ((ci >> 2) & 1);
+            if (box_dist2(g, l - 1, ccx, ccy, ccz, qx, qy, qz) > cur) continue;
+            uint32_t cs2, ce2, cm2;
+            if (st) st->lookups++;
+            if (!grid_lookup(g, l - 1, ccx, ccy, ccz, cs2, ce2, cm2)) continue;  // cannot happen: mask says occupied
+            stack[sp++] = StackEntry{(uint32_t)ccx | ((uint32_t)(l - 1) << 24), (uint32_t)ccy | (cm2 << 24), (uint32_t)ccz, cs2, ce2, 0u};
+          }
+        }
+      }
 }
 
 }  // namespace rgc

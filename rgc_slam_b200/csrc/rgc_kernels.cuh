@@ -243,6 +243,29 @@ __global__ void __launch_bounds__(256) k_build_tables(const uint64_t* __restrict
     for (int l = 0; l < ts.nlevels; l++) slot_insert_or_find(ts.table[l], ts.mask[l], key >> (3 * l))->end = (uint32_t)n;
 }
 
+// second pass (tables complete): every cell sets its bit in its parent's occupied-children mask
+__global__ void __launch_bounds__(256) k_child_masks(const uint64_t* __restrict__ keys, int n, TableSet ts) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t key = keys[i];
+  int top;
+  if (i == 0)
+    top = ts.nlevels - 1;
+  else {
+    uint64_t x = key ^ keys[i - 1];
+    top = x ? min((63 - __clzll((long long)x)) / 3, ts.nlevels - 1) : -1;
+  }
+  for (int l = 0; l <= top && l + 1 < ts.nlevels; l++) {
+    const uint64_t ck = key >> (3 * l), pk = ck >> 3;
+    GridSlot* tab = ts.table[l + 1];
+    const uint32_t mask = ts.mask[l + 1];
+    uint32_t h = (uint32_t)mix64(pk) & mask;
+    while ((tab[h].key & kKeyMask) != pk) h = (h + 1) & mask;  // parent exists by construction
+    // the mask lives in the top byte of the 64-bit key word = top byte of its high 32-bit half
+    atomicOr(reinterpret_cast<unsigned int*>(&tab[h].key) + 1, 1u << (24 + (int)(ck & 7)));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // kNN.  SELF: queries are the grid's own sorted points (thread t <-> sorted point t) and the
 // result is stored k-major as sorted positions for k_covariance.  Otherwise queries are float4
@@ -254,7 +277,7 @@ __global__ void __launch_bounds__(kThreads, (KCAP >= 32 ? 2 : (KCAP >= 20 ? 4 : 
   if (t >= m) return;
   float4 q = SELF ? reinterpret_cast<const float4*>(g.pts)[t] : queries[t];
   TopK<KCAP> top;
-  knn_search<KCAP>(g, q.x, q.y, q.z, k, INFINITY, -1, top);
+  knn_search<KCAP>(g, q.x, q.y, q.z, k, INFINITY, SELF ? t : -1, top);
   const int first = KCAP - k;  // slot of the best entry (TopK keeps the k live entries last)
   if (SELF) {
 #pragma unroll

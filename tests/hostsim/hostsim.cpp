@@ -72,6 +72,17 @@ static void sim_build(const float* xyzw, int n, float cell, SimCloud& c) {
     v.table[l] = t.data();
     v.mask[l] = mask;
   }
+  // occupied-children masks (k_child_masks)
+  for (int l = 0; l + 1 < v.nlevels; l++)
+    for (int i = 0; i < n; i++)
+      if (i == 0 || (ks[i] >> (3 * l)) != (ks[i - 1] >> (3 * l))) {
+        uint64_t ck = ks[i] >> (3 * l), pk = ck >> 3;
+        auto& t = c.tables[l + 1];
+        uint32_t mask = (uint32_t)(t.size() - 1);
+        uint32_t hh = (uint32_t)mix64(pk) & mask;
+        while ((t[hh].key & kKeyMask) != pk) hh = (hh + 1) & mask;
+        t[hh].key |= (uint64_t)1 << (56 + (int)(ck & 7));
+      }
   v.pts = c.sorted.data();
 }
 
@@ -90,7 +101,7 @@ static void sim_knn_t(const SimCloud& c, const float* q, int m, int k, int* idx,
     }
     if (stats) {
 #pragma omp atomic
-      stats[0] += st.levels;
+      stats[0] += st.nodes;
 #pragma omp atomic
       stats[1] += st.lookups;
 #pragma omp atomic
