@@ -188,6 +188,7 @@ def run_ours(args, rank, world):
     for i in range(args.steps):
         with torch.cuda.stream(ext):
             flush.zero_()  # L2 flush between timed iterations (outside the event pair)
+        ctx.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = ctx.launch_count
         e0.record(ext)

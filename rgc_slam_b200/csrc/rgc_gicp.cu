@@ -8,6 +8,8 @@
 #include <cuda_runtime.h>
 
 #include <cfloat>
+#include <chrono>
+#include <cstdlib>
 #include <cstdio>
 #include <map>
 #include <string>
@@ -90,6 +92,22 @@ struct rgc_ctx {
 
 static inline int div_up(int a, int b) { return (a + b - 1) / b; }
 
+// RGC_TRACE=1: wall-clock trace of the host side of the build pipeline (debug aid)
+static bool trace_on() {
+  static int v = -1;
+  if (v < 0) v = std::getenv("RGC_TRACE") ? 1 : 0;
+  return v == 1;
+}
+struct Tracer {
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  void lap(const char* what) {
+    if (!trace_on()) return;
+    auto t1 = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[rgc trace] %-28s %9.1f us\n", what, std::chrono::duration<double, std::micro>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+
 // ------------------------------------------------------------------------------------------------
 struct Cloud {
   int n = 0;
@@ -118,6 +136,7 @@ static int cloud_build(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, s
   if (stride < 12 || stride % 4) FAIL(c, RGC_ERR_INVALID, "point stride must be a multiple of 4 and >= 12 bytes");
   const int n = (int)n_sz;
   cudaStream_t st = c->stream;
+  Tracer tr;
   CK(c, cudaEventRecord(c->ev[0], st));
 
   const unsigned char* d_raw = (const unsigned char*)points;
@@ -140,10 +159,12 @@ static int cloud_build(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, s
   cl.sorted = (float4*)c->get(sizeof(float4) * n_sz);
   if (!orig || !d_bbox || !keys_a || !keys_b || !vals_a || !vals_b || !hist || !d_counts || !cl.sorted) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (build)");
 
+  tr.lap("alloc");
   k_ingest<<<kBboxBlocks, 256, 0, st>>>(d_raw, stride, n, orig, d_bbox);
   CKL(c);
   CK(c, cudaMemcpyAsync(c->h_bbox, d_bbox, sizeof(float) * 6 * kBboxBlocks, cudaMemcpyDeviceToHost, st));
   CK(c, cudaStreamSynchronize(st));
+  tr.lap("ingest+bbox sync");
   float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
   for (int b = 0; b < kBboxBlocks; b++)
     for (int a = 0; a < 3; a++) {
@@ -184,7 +205,9 @@ static int cloud_build(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, s
   k_count_cells<<<div_up(n, 256), 256, 0, st>>>(kin, n, v.nlevels, d_counts);
   CKL(c);
   CK(c, cudaMemcpyAsync(c->h_counts, d_counts, 4 * kMaxLevels, cudaMemcpyDeviceToHost, st));
+  tr.lap("sort launches");
   CK(c, cudaStreamSynchronize(st));
+  tr.lap("sort+count sync");
   size_t total_slots = 0;
   size_t slots[kMaxLevels];
   for (int l = 0; l < v.nlevels; l++) {
@@ -229,25 +252,20 @@ static int cloud_build(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, s
   cl.n = n;
   cl.key = key;
   cl.valid = true;
+  tr.lap("tables launches");
   CK(c, cudaEventRecord(c->ev[1], st));
   CK(c, cudaEventSynchronize(c->ev[1]));
+  tr.lap("tables sync");
   CK(c, cudaEventElapsedTime(&cl.build_ms, c->ev[0], c->ev[1]));
   return RGC_OK;
 }
 
 template <bool SELF>
 static int launch_knn(rgc_ctx* c, const GridView& v, const float4* queries, int m, int k, int* idx, float* d2) {
+  if (k > 32) FAIL(c, RGC_ERR_UNSUPPORTED, "k_correspondences > 32 is not supported");
   const int grid = div_up(m, kThreads);
-  if (k == 1)
-    k_knn<1, SELF><<<grid, kThreads, 0, c->stream>>>(v, queries, m, k, idx, d2);
-  else if (k <= 8)
-    k_knn<8, SELF><<<grid, kThreads, 0, c->stream>>>(v, queries, m, k, idx, d2);
-  else if (k <= 20)
-    k_knn<20, SELF><<<grid, kThreads, 0, c->stream>>>(v, queries, m, k, idx, d2);
-  else if (k <= 32)
-    k_knn<32, SELF><<<grid, kThreads, 0, c->stream>>>(v, queries, m, k, idx, d2);
-  else
-    FAIL(c, RGC_ERR_UNSUPPORTED, "k_correspondences > 32 is not supported");
+  const size_t smem = (size_t)k * kThreads * 8;  // per-thread max-heap of k (d2, position) pairs
+  k_knn<SELF><<<grid, kThreads, smem, c->stream>>>(v, queries, m, k, idx, d2);
   CKL(c);
   return RGC_OK;
 }

@@ -149,6 +149,24 @@ RGC_HD bool grid_lookup(const GridView& g, int l, int cx, int cy, int cz, uint32
   }
 }
 
+// same, for a cell known by its Morton key (children of a visited cell: key = parent << 3 | octant)
+RGC_HD bool grid_lookup_key(const GridView& g, int l, uint64_t key, uint32_t& start, uint32_t& end, uint32_t& cmask) {
+  const GridSlot* tab = g.table[l];
+  const uint32_t mask = g.mask[l];
+  uint32_t h = (uint32_t)mix64(key) & mask;
+  for (;;) {
+    GridSlot s = load_slot(tab + h);
+    if (s.key == kEmptyKey) return false;
+    if ((s.key & kKeyMask) == key) {
+      start = s.start;
+      end = s.end;
+      cmask = (uint32_t)(s.key >> 56);
+      return true;
+    }
+    h = (h + 1) & mask;
+  }
+}
+
 // conservative squared distance from q to the box of cell (cx,cy,cz) at level l: never larger
 // than the reference-arithmetic d2 of any point stored in that cell
 RGC_HD float box_dist2(const GridView& g, int l, int cx, int cy, int cz, float qx, float qy, float qz) {
@@ -160,64 +178,125 @@ RGC_HD float box_dist2(const GridView& g, int l, int cx, int cy, int cz, float q
   return (gx * gx + gy * gy + gz * gz) * 0.999999f;
 }
 
-// ---- bounded sorted list of the k best candidates, kept in registers ---------------------------
-// KCAP slots, ascending by (d2, original index).  The k live entries occupy the LAST k slots, so
-// the current k-th best always sits in the static slot KCAP-1 (a run-time position would make
-// the compiler index the arrays dynamically and demote them to local memory); the leading
-// KCAP-k slots are -inf sentinels that no candidate can precede.  id[] = sorted position in
-// g.pts (-1 = empty, -2 = sentinel).  Exact distance ties are ordered by the ORIGINAL index,
-// fetched lazily from pts[].w only when two distances compare equal.
-template <int KCAP>
-struct TopK {
-  float d[KCAP];
-  int id[KCAP];
+// ---- the k best candidates so far --------------------------------------------------------------
+// Binary max-heap ordered by (d2, original index): the root is the current k-th best, so the
+// pruning bound is O(1) and an insertion is one sift (<= log2 k steps) instead of a k-slot shift.
+// Storage is caller-provided and strided (device: one column of a shared-memory array per thread,
+// dynamic indexing is free there; an ncu profile of the register-resident sorted-list version
+// showed 62 % of all instructions in its 20-slot insertion at 4-5 active lanes).
+// id[] = sorted position in g.pts.  Exact distance ties are ordered by the ORIGINAL index, fetched
+// lazily from pts[].w only when two distances compare equal.
+struct HeapK {
+  float* d;
+  int* id;
+  int stride;
+  int k, cnt;
   float lim;  // external pruning radius (inclusive): candidates with d2 > lim are never needed
-  int k;
 
+  RGC_HD void init(float* d_, int* id_, int stride_) {
+    d = d_;
+    id = id_;
+    stride = stride_;
+  }
   RGC_HD void reset(int k_, float lim_) {
     k = k_;
+    cnt = 0;
     lim = lim_;
-#pragma unroll
-    for (int j = 0; j < KCAP; j++) {
-      const bool live = j >= KCAP - k_;
-      d[j] = live ? INFINITY : -INFINITY;
-      id[j] = live ? -1 : -2;
-    }
   }
-  RGC_HD bool full() const { return id[KCAP - 1] >= 0; }
-  RGC_HD float worst() const { return d[KCAP - 1]; }
-  // (dn, orig_n) strictly before (dj, orig(idj)) ?
-  RGC_HD bool before(float dn, int orig_n, float dj, int idj, const F4* pts) const {
-    if (dn < dj) return true;
-    if (dn > dj) return false;
-    if (idj < 0) return idj == -1;  // unreachable for finite dn: empty slots hold +inf, sentinels -inf
-    return orig_n < f2i_bits(load_pt(pts + idj).w);
+  RGC_HD bool full() const { return cnt == k; }
+  RGC_HD float worst() const { return d[0]; }  // valid when full()
+  RGC_HD float bound() const { return cnt == k ? fminf(lim, d[0]) : lim; }
+  // (da, a) ordered after (db, b)?   a/b are sorted positions; orig_a may be supplied (>= 0)
+  RGC_HD static bool after(float da, int orig_a, float db, int pb, const F4* pts) {
+    if (da > db) return true;
+    if (da < db) return false;
+    return orig_a > f2i_bits(load_pt(pts + pb).w);
   }
   RGC_HD void insert(float dn, int pos, int orig, const F4* pts) {
     if (dn > lim) return;
-    // new entry must precede the current k-th best (static slot KCAP-1)
-    bool b_j = before(dn, orig, d[KCAP - 1], id[KCAP - 1], pts);
-    if (!b_j) return;
-    // walk from the tail: slot j takes slot j-1 if the new entry precedes j-1, else takes the
-    // new entry if it precedes j.
-#pragma unroll
-    for (int j = KCAP - 1; j >= 1; j--) {
-      const bool b_jm1 = before(dn, orig, d[j - 1], id[j - 1], pts);
-      if (b_jm1) {
-        d[j] = d[j - 1];
-        id[j] = id[j - 1];
-      } else if (b_j) {
-        d[j] = dn;
-        id[j] = pos;
+    if (cnt < k) {  // sift up
+      int j = cnt++;
+      while (j > 0) {
+        const int p = (j - 1) >> 1;
+        const float dp = d[p * stride];
+        const int ip = id[p * stride];
+        if (!after(dn, orig, dp, ip, pts)) break;
+        d[j * stride] = dp;
+        id[j * stride] = ip;
+        j = p;
       }
-      b_j = b_jm1;
+      d[j * stride] = dn;
+      id[j * stride] = pos;
+      return;
     }
-    if (b_j) {
-      d[0] = dn;
-      id[0] = pos;
+    // full: the new entry must precede the current worst (the root), then sifts down from it
+    {
+      const float dr = d[0];
+      if (dn > dr) return;
+      if (dn == dr && !(orig < f2i_bits(load_pt(pts + id[0]).w))) return;
+    }
+    sift_down_from_root(dn, pos, orig, k, pts);
+  }
+  RGC_HD void sift_down_from_root(float dn, int pos, int orig, int size, const F4* pts) {
+    int j = 0;
+    for (;;) {
+      int c = 2 * j + 1;
+      if (c >= size) break;
+      float dc = d[c * stride];
+      int ic = id[c * stride];
+      if (c + 1 < size) {
+        const float d2 = d[(c + 1) * stride];
+        const int i2 = id[(c + 1) * stride];
+        bool right_larger = d2 > dc;
+        if (d2 == dc) right_larger = f2i_bits(load_pt(pts + i2).w) > f2i_bits(load_pt(pts + ic).w);
+        if (right_larger) {
+          c++;
+          dc = d2;
+          ic = i2;
+        }
+      }
+      // stop when the larger child is not after the new entry
+      bool child_after = dc > dn;
+      if (dc == dn) child_after = f2i_bits(load_pt(pts + ic).w) > orig;
+      if (!child_after) break;
+      d[j * stride] = dc;
+      id[j * stride] = ic;
+      j = c;
+    }
+    d[j * stride] = dn;
+    id[j * stride] = pos;
+  }
+  // heap-sort in place: afterwards slots 0..cnt-1 are ascending by (d2, original index)
+  RGC_HD void sort_ascending(const F4* pts) {
+    for (int size = cnt; size > 1; size--) {
+      const float dl = d[(size - 1) * stride];
+      const int il = id[(size - 1) * stride];
+      d[(size - 1) * stride] = d[0];
+      id[(size - 1) * stride] = id[0];
+      sift_down_from_root(dl, il, f2i_bits(load_pt(pts + il).w), size - 1, pts);
     }
   }
-  // j-th best (0-based) lives in slot KCAP-k+j; callers read it with a static unrolled loop
+};
+
+// k = 1 container (registers): same interface as HeapK
+struct Best1 {
+  float d0;
+  int id0;
+  float lim;
+  RGC_HD void reset(int, float lim_) {
+    d0 = INFINITY;
+    id0 = -1;
+    lim = lim_;
+  }
+  RGC_HD bool full() const { return id0 >= 0; }
+  RGC_HD float worst() const { return d0; }
+  RGC_HD float bound() const { return id0 >= 0 ? fminf(lim, d0) : lim; }
+  RGC_HD void insert(float dn, int pos, int orig, const F4* pts) {
+    if (dn > lim || dn > d0) return;
+    if (dn == d0 && id0 >= 0 && !(orig < f2i_bits(load_pt(pts + id0).w))) return;
+    d0 = dn;
+    id0 = pos;
+  }
 };
 
 struct SearchStats {
@@ -232,8 +311,8 @@ struct StackEntry {  // 24 bytes
   uint32_t pad;
 };
 
-template <int KCAP>
-RGC_HD void scan_range(const GridView& g, uint32_t s, uint32_t e, float qx, float qy, float qz, TopK<KCAP>& top, SearchStats* st) {
+template <class Top>
+RGC_HD void scan_range(const GridView& g, uint32_t s, uint32_t e, float qx, float qy, float qz, Top& top, SearchStats* st) {
   for (uint32_t p = s; p < e; p++) {
     const F4 c = load_pt(g.pts + p);
     const float d2 = dist2_ref(qx, qy, qz, c.x, c.y, c.z);
@@ -242,11 +321,11 @@ RGC_HD void scan_range(const GridView& g, uint32_t s, uint32_t e, float qx, floa
   }
 }
 
-// Exact kNN of (qx,qy,qz) in grid g, ascending by (d2, original index), into `top`.
+// Exact kNN of (qx,qy,qz) in grid g into the heap `top` (call top.sort_ascending() for ordered output).
 // `max_d2`: candidates with d2 > max_d2 are never needed (+inf = unbounded).  `near_pos`: a sorted
 // position known to be spatially close to q (the query's own position for self-kNN), or -1.
-template <int KCAP>
-RGC_HD void knn_search(const GridView& g, float qx, float qy, float qz, int k, float max_d2, int near_pos, TopK<KCAP>& top,
+template <class Top>
+RGC_HD void knn_search(const GridView& g, float qx, float qy, float qz, int k, float max_d2, int near_pos, Top& top,
                        SearchStats* st = nullptr) {
   const int top_level = g.nlevels - 1;
   // ---- 1. initial bound from k Morton-adjacent points
@@ -304,8 +383,7 @@ RGC_HD void knn_search(const GridView& g, float qx, float qy, float qz, int k, f
     for (int ry = lo[1]; ry <= hi[1]; ry++)
       for (int rx = lo[0]; rx <= hi[0]; rx++) {
         {
-          const float cur = top.full() ? fminf(top.lim, top.worst()) : top.lim;
-          if (box_dist2(g, lb, rx, ry, rz, qx, qy, qz) > cur) continue;
+          if (box_dist2(g, lb, rx, ry, rz, qx, qy, qz) > top.bound()) continue;
         }
         uint32_t s, e, m;
         if (st) st->lookups++;
@@ -318,7 +396,7 @@ RGC_HD void knn_search(const GridView& g, float qx, float qy, float qz, int k, f
           const int l = (int)(n.cx_lvl >> 24);
           const int cx = (int)(n.cx_lvl & 0xffffffu), cy = (int)(n.cy_mask & 0xffffffu), cz = (int)n.cz;
           const uint32_t cm = n.cy_mask >> 24;
-          const float cur = top.full() ? fminf(top.lim, top.worst()) : top.lim;
+          const float cur = top.bound();
           if (box_dist2(g, l, cx, cy, cz, qx, qy, qz) > cur) continue;
           if (st) st->nodes++;
           if (l == 0 || n.end - n.start <= (uint32_t)kLeafPoints || sp + 8 > kStackCap) {
@@ -329,6 +407,7 @@ RGC_HD void knn_search(const GridView& g, float qx, float qy, float qz, int k, f
           const float half = g.s0 * (float)(1 << (l - 1));
           const float mx = g.ox + (float)(2 * cx + 1) * half, my = g.oy + (float)(2 * cy + 1) * half, mz = g.oz + (float)(2 * cz + 1) * half;
           const int first = (qx >= mx ? 1 : 0) | (qy >= my ? 2 : 0) | (qz >= mz ? 4 : 0);
+          const uint64_t pkey = morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz) << 3;
           for (int j = 7; j >= 0; j--) {
             const int ci = first ^ j;
             if (!((cm >> ci) & 1u)) continue;
@@ -336,7 +415,7 @@ RGC_HD void knn_search(const GridView& g, float qx, float qy, float qz, int k, f
             if (box_dist2(g, l - 1, ccx, ccy, ccz, qx, qy, qz) > cur) continue;
             uint32_t cs2, ce2, cm2;
             if (st) st->lookups++;
-            if (!grid_lookup(g, l - 1, ccx, ccy, ccz, cs2, ce2, cm2)) continue;  // cannot happen: mask says occupied
+            if (!grid_lookup_key(g, l - 1, pkey | (uint64_t)ci, cs2, ce2, cm2)) continue;  // cannot happen: mask says occupied
             stack[sp++] = StackEntry{(uint32_t)ccx | ((uint32_t)(l - 1) << 24), (uint32_t)ccy | (cm2 << 24), (uint32_t)ccz, cs2, ce2, 0u};
           }
         }

@@ -270,27 +270,25 @@ __global__ void __launch_bounds__(256) k_child_masks(const uint64_t* __restrict_
 // kNN.  SELF: queries are the grid's own sorted points (thread t <-> sorted point t) and the
 // result is stored k-major as sorted positions for k_covariance.  Otherwise queries are float4
 // and results go out row-major [m][k] as ORIGINAL indices + d2 (test hook / public rgc_knn).
-template <int KCAP, bool SELF>
-__global__ void __launch_bounds__(kThreads, (KCAP >= 32 ? 2 : (KCAP >= 20 ? 4 : 8))) k_knn(GridView g, const float4* __restrict__ queries, int m, int k, int* __restrict__ out_idx,
-                                                  float* __restrict__ out_d2) {
+template <bool SELF>
+__global__ void __launch_bounds__(kThreads, 8) k_knn(GridView g, const float4* __restrict__ queries, int m, int k, int* __restrict__ out_idx,
+                                                     float* __restrict__ out_d2) {
+  extern __shared__ float heap_smem[];  // [k][kThreads] distances, then [k][kThreads] positions
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= m) return;
   float4 q = SELF ? reinterpret_cast<const float4*>(g.pts)[t] : queries[t];
-  TopK<KCAP> top;
-  knn_search<KCAP>(g, q.x, q.y, q.z, k, INFINITY, SELF ? t : -1, top);
-  const int first = KCAP - k;  // slot of the best entry (TopK keeps the k live entries last)
+  HeapK top;
+  top.init(heap_smem + threadIdx.x, reinterpret_cast<int*>(heap_smem + (size_t)k * kThreads) + threadIdx.x, kThreads);
+  knn_search(g, q.x, q.y, q.z, k, INFINITY, SELF ? t : -1, top);
+  top.sort_ascending(g.pts);
   if (SELF) {
-#pragma unroll
-    for (int j = 0; j < KCAP; j++)
-      if (j >= first) out_idx[(size_t)(j - first) * m + t] = top.id[j];
+    for (int j = 0; j < k; j++) out_idx[(size_t)j * m + t] = j < top.cnt ? top.id[j * kThreads] : -1;
   } else {
-#pragma unroll
-    for (int j = 0; j < KCAP; j++)
-      if (j >= first) {
-        int id = top.id[j];
-        out_idx[(size_t)t * k + (j - first)] = id >= 0 ? __float_as_int(g.pts[id].w) : -1;
-        if (out_d2) out_d2[(size_t)t * k + (j - first)] = top.d[j];
-      }
+    for (int j = 0; j < k; j++) {
+      const bool have = j < top.cnt;
+      out_idx[(size_t)t * k + j] = have ? __float_as_int(g.pts[top.id[j * kThreads]].w) : -1;
+      if (out_d2) out_d2[(size_t)t * k + j] = have ? top.d[j * kThreads] : INFINITY;
+    }
   }
 }
 
@@ -384,11 +382,11 @@ __global__ void __launch_bounds__(kThreads, 4) k_linearize(GridView tgt, const f
     p = __ldg(&src[i]);
     float qx, qy, qz;
     transform_f(Tf.m, p.x, p.y, p.z, qx, qy, qz);
-    TopK<1> top;
-    knn_search<1>(tgt, qx, qy, qz, 1, thr2, -1, top);
-    pos = (top.id[0] >= 0 && top.d[0] < thr2) ? top.id[0] : -1;
+    Best1 top;
+    knn_search(tgt, qx, qy, qz, 1, thr2, -1, top);
+    pos = (top.id0 >= 0 && top.d0 < thr2) ? top.id0 : -1;
     corr[i] = pos;
-    sqd[i] = top.d[0];
+    sqd[i] = top.d0;
   }
   // accumulators are declared only after the search so they are not live across it
   double acc[kLinN];
@@ -436,10 +434,10 @@ __global__ void __launch_bounds__(kThreads, 8) k_fitness(GridView tgt, const flo
     const float4 p = __ldg(&src[i]);
     float qx, qy, qz;
     transform_f(Tf.m, p.x, p.y, p.z, qx, qy, qz);
-    TopK<1> top;
-    knn_search<1>(tgt, qx, qy, qz, 1, INFINITY, -1, top);
-    if (top.id[0] >= 0 && (double)top.d[0] <= max_range) {
-      acc[0] = (double)top.d[0];
+    Best1 top;
+    knn_search(tgt, qx, qy, qz, 1, INFINITY, -1, top);
+    if (top.id0 >= 0 && (double)top.d0 <= max_range) {
+      acc[0] = (double)top.d0;
       acc[1] = 1.0;
     }
   }

@@ -44,5 +44,7 @@ def small_pair(scene, traj):
 
 
 def rot_angle(Ra, Rb):
+    """Angle of Ra^T Rb, from the skew part (well conditioned near zero, unlike acos(trace))."""
     R = Ra.astype(np.float64).T @ Rb.astype(np.float64)
-    return float(np.arccos(np.clip((np.trace(R) - 1) / 2, -1, 1)))
+    v = np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]]) / 2
+    return float(np.arctan2(np.linalg.norm(v), (np.trace(R) - 1) / 2))

@@ -86,18 +86,20 @@ static void sim_build(const float* xyzw, int n, float cell, SimCloud& c) {
   v.pts = c.sorted.data();
 }
 
-template <int KCAP>
 static void sim_knn_t(const SimCloud& c, const float* q, int m, int k, int* idx, float* d2, long long* stats) {
 #pragma omp parallel for schedule(dynamic, 64)
   for (int t = 0; t < m; t++) {
-    TopK<KCAP> top;
+    float hd[64];
+    int hi[64];
+    HeapK top;
+    top.init(hd, hi, 1);
     SearchStats st{0, 0, 0};
-    knn_search<KCAP>(c.v, q[4 * (size_t)t], q[4 * (size_t)t + 1], q[4 * (size_t)t + 2], k, INFINITY, -1, top, &st);
-    const int first = KCAP - k;
-    for (int j = first; j < KCAP; j++) {
-      int id = top.id[j];
-      idx[(size_t)t * k + (j - first)] = id >= 0 ? f2i_bits(c.sorted[id].w) : -1;
-      d2[(size_t)t * k + (j - first)] = top.d[j];
+    knn_search(c.v, q[4 * (size_t)t], q[4 * (size_t)t + 1], q[4 * (size_t)t + 2], k, INFINITY, -1, top, &st);
+    top.sort_ascending(c.v.pts);
+    for (int j = 0; j < k; j++) {
+      const bool have = j < top.cnt;
+      idx[(size_t)t * k + j] = have ? f2i_bits(c.sorted[hi[j]].w) : -1;
+      d2[(size_t)t * k + j] = have ? hd[j] : INFINITY;
     }
     if (stats) {
 #pragma omp atomic
@@ -116,11 +118,8 @@ int sim_knn(const float* pts, int n, const float* queries, int m, int k, int* id
   SimCloud c;
   sim_build(pts, n, cell, c);
   if (stats) stats[0] = stats[1] = stats[2] = 0;
-  if (k == 1) sim_knn_t<1>(c, queries, m, k, idx, d2, stats);
-  else if (k <= 8) sim_knn_t<8>(c, queries, m, k, idx, d2, stats);
-  else if (k <= 20) sim_knn_t<20>(c, queries, m, k, idx, d2, stats);
-  else if (k <= 32) sim_knn_t<32>(c, queries, m, k, idx, d2, stats);
-  else return -1;
+  if (k > 64) return -1;
+  sim_knn_t(c, queries, m, k, idx, d2, stats);
   return c.v.nlevels;
 }
 
@@ -161,9 +160,9 @@ void sim_linearize(const float* src, int ns, const float* tgt, int nt, const dou
     const float* p = &src[4 * (size_t)i];
     float qx, qy, qz;
     transform_f(Tf, p[0], p[1], p[2], qx, qy, qz);
-    TopK<1> top;
-    knn_search<1>(c.v, qx, qy, qz, 1, thr2, -1, top);
-    int pos = (top.id[0] >= 0 && top.d[0] < thr2) ? top.id[0] : -1;
+    Best1 top;
+    knn_search(c.v, qx, qy, qz, 1, thr2, -1, top);
+    int pos = (top.id0 >= 0 && top.d0 < thr2) ? top.id0 : -1;
     corr[i] = pos >= 0 ? f2i_bits(c.sorted[pos].w) : -1;
     if (pos < 0) continue;
     const double* a = &covA16[16 * (size_t)i];
