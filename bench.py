@@ -79,53 +79,57 @@ def build_workload(rank: int, n_submap: int, n_pairs: int = N_PAIRS):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed region.  In-process NVML at 5 Hz (an
+    `nvidia-smi -lms` subprocess was measurably perturbing the latency-bound LM loop: its queries
+    take driver locks); falls back to nvidia-smi if pynvml is unavailable."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index: int):
-        self.rows = []
-        self.proc = None
         self.gpu_index = gpu_index
+        self.sm, self.mx, self.reasons = [], [], set()
+        self._stop = threading.Event()
+        self.thr = None
+        self.how = "nvml"
+
+    def _loop(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu_index]) if vis and vis.split(",")[0].isdigit() else self.gpu_index
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            while not self._stop.is_set():
+                self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                self.mx.append(float(mx))
+                try:
+                    r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for bit, name in self.REASONS.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+                self._stop.wait(0.2)
+        except Exception as e:  # noqa: BLE001
+            self.how = f"nvml failed ({type(e).__name__}); nvidia-smi single query"
+            try:
+                out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits", "-i", str(self.gpu_index)],
+                                     capture_output=True, text=True, timeout=10).stdout.strip().split(",")
+                self.sm.append(float(out[0]))
+                self.mx.append(float(out[1]))
+            except Exception:
+                pass
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu_index)],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thr = threading.Thread(target=self._read, daemon=True)
-            self.thr.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+        self.thr = threading.Thread(target=self._loop, daemon=True)
+        self.thr.start()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        self._stop.set()
+        if self.thr:
+            self.thr.join(timeout=3)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "how": self.how}
 
 
 def new_reg(rgc, ctx):

@@ -263,9 +263,10 @@ static int cloud_build(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, s
 template <bool SELF>
 static int launch_knn(rgc_ctx* c, const GridView& v, const float4* queries, int m, int k, int* idx, float* d2) {
   if (k > 32) FAIL(c, RGC_ERR_UNSUPPORTED, "k_correspondences > 32 is not supported");
-  const int grid = div_up(m, kThreads);
+  const int spread = query_spread(m);
+  const int grid = div_up(m * spread, kThreads);
   const size_t smem = (size_t)k * kThreads * 8;  // per-thread max-heap of k (d2, position) pairs
-  k_knn<SELF><<<grid, kThreads, smem, c->stream>>>(v, queries, m, k, idx, d2);
+  k_knn<SELF><<<grid, kThreads, smem, c->stream>>>(v, queries, m, k, spread, idx, d2);
   CKL(c);
   return RGC_OK;
 }
@@ -324,7 +325,7 @@ static int reg_ensure_work(rgc_reg* r) {
   r->corr = (int*)c->get(4 * n);
   r->sqd = (float*)c->get(4 * n);
   r->maha = (double*)c->get(48 * n);
-  r->partials = (double*)c->get(sizeof(double) * kLinN * (size_t)div_up(r->src.n, kThreads));
+  r->partials = (double*)c->get(sizeof(double) * kLinN * (size_t)div_up(r->src.n * query_spread(r->src.n), kThreads));
   if (!r->corr || !r->sqd || !r->maha || !r->partials) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (work buffers)");
   r->cap_src = r->src.n;
   return RGC_OK;
@@ -347,7 +348,8 @@ static int reg_linearize(rgc_reg* r, const double* T, double* err, double* H, do
   const float thr = r->prm.max_correspondence_distance;
   const float thr2 = thr * thr;  // float product, +inf for the FLT_MAX default (fast_gicp_impl.hpp:136)
   const int want = (H && b) ? 1 : 0;
-  k_linearize<<<div_up(r->src.n, kThreads), kThreads, 0, c->stream>>>(r->tgt.view, r->src.sorted, r->src.cov, r->tgt.cov, r->src.n, Tf, Td, thr2, want,
+  const int spread = query_spread(r->src.n);
+  k_linearize<<<div_up(r->src.n * spread, kThreads), kThreads, 0, c->stream>>>(r->tgt.view, r->src.sorted, r->src.cov, r->tgt.cov, r->src.n, spread, Tf, Td, thr2, want,
                                                                      r->corr, r->sqd, r->maha, r->partials, c->d_ticket, c->d_result);
   CKL(c);
   CK(c, cudaStreamSynchronize(c->stream));
@@ -737,7 +739,9 @@ int rgc_reg_fitness(rgc_reg* r, double max_range, double* score) {
   TRY(reg_ensure_work(r));
   RtF Tf;
   for (int i = 0; i < 12; i++) Tf.m[i] = r->final_T[i];
-  k_fitness<<<div_up(r->src.n, kThreads), kThreads, 0, c->stream>>>(r->tgt.view, r->src.sorted, r->src.n, Tf, max_range, r->partials, c->d_ticket, c->d_result);
+  const int spread = query_spread(r->src.n);
+  k_fitness<<<div_up(r->src.n * spread, kThreads), kThreads, 0, c->stream>>>(r->tgt.view, r->src.sorted, r->src.n, spread, Tf, max_range, r->partials, c->d_ticket,
+                                                                            c->d_result);
   CKL(c);
   CK(c, cudaStreamSynchronize(c->stream));
   const double sum = c->h_result[0], nr = c->h_result[1];

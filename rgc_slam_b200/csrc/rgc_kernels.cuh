@@ -23,6 +23,12 @@ namespace rgc {
 constexpr int kBboxBlocks = 296;  // 2 x 148 SMs
 constexpr int kThreads = 128;
 
+// Small clouds (one LiDAR sweep) cannot fill 148 SMs with one query per thread: the search kernels
+// are then bound by the latency of a few divergent warps.  `spread` (power of two) leaves only
+// every spread-th lane active, so the same queries occupy spread x more warps, each with fewer
+// divergent paths to serialise.  Large clouds use spread = 1 (throughput-bound).
+__host__ __device__ inline int query_spread(int n) { return n <= 12000 ? 8 : (n <= 48000 ? 4 : (n <= 96000 ? 2 : 1)); }
+
 // ------------------------------------------------------------------------------------------------
 // ingest: raw[n] with byte stride (xyz at offset 0, as every PCL point type) -> float4(x,y,z,1)
 // plus per-block min/max partials (reduced on the host: 296 x 6 floats).
@@ -271,10 +277,12 @@ __global__ void __launch_bounds__(256) k_child_masks(const uint64_t* __restrict_
 // result is stored k-major as sorted positions for k_covariance.  Otherwise queries are float4
 // and results go out row-major [m][k] as ORIGINAL indices + d2 (test hook / public rgc_knn).
 template <bool SELF>
-__global__ void __launch_bounds__(kThreads, 8) k_knn(GridView g, const float4* __restrict__ queries, int m, int k, int* __restrict__ out_idx,
+__global__ void __launch_bounds__(kThreads, 8) k_knn(GridView g, const float4* __restrict__ queries, int m, int k, int spread, int* __restrict__ out_idx,
                                                      float* __restrict__ out_d2) {
   extern __shared__ float heap_smem[];  // [k][kThreads] distances, then [k][kThreads] positions
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gt & (spread - 1)) return;
+  const int t = gt / spread;
   if (t >= m) return;
   float4 q = SELF ? reinterpret_cast<const float4*>(g.pts)[t] : queries[t];
   HeapK top;
@@ -372,13 +380,14 @@ constexpr int kLinN = kAccN + 1;  // + inlier count
 // point (Morton order).  Stores the correspondence (sorted target position), its d2 and M for
 // the compute_error calls that follow.
 __global__ void __launch_bounds__(kThreads, 4) k_linearize(GridView tgt, const float4* __restrict__ src, const double* __restrict__ src_cov,
-                                                        const double* __restrict__ tgt_cov, int n_src, RtF Tf, Rt Td, float thr2, int want_hb,
+                                                        const double* __restrict__ tgt_cov, int n_src, int spread, RtF Tf, Rt Td, float thr2, int want_hb,
                                                         int* __restrict__ corr, float* __restrict__ sqd, double* __restrict__ maha,
                                                         double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ result) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = gt / spread;
   int pos = -1;
   float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (i < n_src) {
+  if ((gt & (spread - 1)) == 0 && i < n_src) {
     p = __ldg(&src[i]);
     float qx, qy, qz;
     transform_f(Tf.m, p.x, p.y, p.z, qx, qy, qz);
@@ -426,11 +435,12 @@ __global__ void __launch_bounds__(kThreads) k_compute_error(const float4* __rest
 }
 
 // pcl::Registration::getFitnessScore: [sum d2, count] over 1-NN d2 <= max_range
-__global__ void __launch_bounds__(kThreads, 8) k_fitness(GridView tgt, const float4* __restrict__ src, int n_src, RtF Tf, double max_range,
+__global__ void __launch_bounds__(kThreads, 8) k_fitness(GridView tgt, const float4* __restrict__ src, int n_src, int spread, RtF Tf, double max_range,
                                                       double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ result) {
   double acc[2] = {0.0, 0.0};
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_src) {
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = gt / spread;
+  if ((gt & (spread - 1)) == 0 && i < n_src) {
     const float4 p = __ldg(&src[i]);
     float qx, qy, qz;
     transform_f(Tf.m, p.x, p.y, p.z, qx, qy, qz);

@@ -183,3 +183,11 @@ void sim_linearize(const float* src, int ns, const float* tgt, int nt, const dou
 }
 
 }  // extern "C"
+
+// host-side LM helpers of the product (rgc_lm.hpp) exposed for the CPU tests
+#include "../../rgc_slam_b200/csrc/rgc_lm.hpp"
+extern "C" {
+void sim_solve_ldlt6(const double* A, const double* rhs, double* x) { rgc::lm::solve_ldlt6(A, rhs, x); }
+void sim_se3_delta(const double* d, double* delta16) { rgc::lm::se3_delta(d, delta16); }
+int sim_is_converged(const double* delta16, double rot_eps, double trans_eps) { return rgc::lm::is_converged(delta16, rot_eps, trans_eps) ? 1 : 0; }
+}

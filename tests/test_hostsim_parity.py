@@ -1,0 +1,119 @@
+"""CPU: the PRODUCT's host/device headers (rgc_grid.cuh, rgc_math.cuh, rgc_lm.hpp), compiled by g++
+in tests/hostsim and run one simulated thread per point, against the oracle.  This is the no-GPU
+check of the search / algebra logic; the real parity tests (-m gpu) call the CUDA path."""
+import numpy as np
+import pytest
+
+import hostsim
+from oracle import oracle as orc
+
+FLT_MAX = float(np.finfo(np.float32).max)
+
+
+@pytest.mark.parametrize("k", [1, 5, 20, 32])
+def test_grid_knn_is_exact_on_a_lidar_sweep(small_pair, k):
+    src, tgt, _ = small_pair
+    idx, d2 = hostsim.knn(tgt, tgt, k)
+    oi, od = orc.knn(tgt, tgt, k)
+    assert np.array_equal(idx, oi) and np.array_equal(d2, od)
+    idx, d2 = hostsim.knn(tgt, src, k)
+    oi, od = orc.knn(tgt, src, k)
+    assert np.array_equal(idx, oi) and np.array_equal(d2, od)
+
+
+@pytest.mark.parametrize("cell", [0.0, 0.2, 1.5])
+def test_grid_knn_edge_cases(cell):
+    rng = np.random.default_rng(0)
+    P = np.ones((5000, 4), np.float32)
+    P[:, :3] = rng.normal(0, 10, (5000, 3))
+    Q = np.ones((2000, 4), np.float32)
+    Q[:, :3] = rng.normal(0, 60, (2000, 3))  # mostly far outside the grid
+    for k in (1, 20):
+        idx, d2 = hostsim.knn(P, Q, k, cell)
+        oi, od = orc.knn(P, Q, k, brute=True)
+        assert np.array_equal(idx, oi) and np.array_equal(d2, od)
+    # n < k with exact duplicates
+    T = np.ones((7, 4), np.float32)
+    T[:, :3] = rng.normal(0, 1, (7, 3))
+    T[3] = T[2]
+    T[5] = T[2]
+    idx, d2 = hostsim.knn(T, T, 20, cell)
+    oi, od = orc.knn(T, T, 20, brute=True)
+    assert np.array_equal(idx, oi) and np.array_equal(d2, od)
+    # integer lattice: every distance tied many times
+    g = np.stack(np.meshgrid(*[np.arange(10)] * 3, indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    L = np.ones((len(g), 4), np.float32)
+    L[:, :3] = g[rng.permutation(len(g))]
+    idx, d2 = hostsim.knn(L, L, 20, cell)
+    oi, od = orc.knn(L, L, 20, brute=True)
+    assert np.array_equal(idx, oi) and np.array_equal(d2, od)
+    # huge coordinates / tiny extent / single point
+    B = (P * np.float32(1.0)).copy()
+    B[:, :3] += np.float32(5000.0)
+    idx, d2 = hostsim.knn(B, B[:500], 5, cell)
+    oi, od = orc.knn(B, B[:500], 5, brute=True)
+    assert np.array_equal(idx, oi) and np.array_equal(d2, od)
+    one = np.ones((1, 4), np.float32)
+    idx, d2 = hostsim.knn(one, Q[:10], 1, cell)
+    assert (idx == 0).all()
+
+
+def test_search_work_is_density_independent(scan_pair):
+    """the octree descent must not degrade on a sweep whose density varies by orders of magnitude"""
+    src, tgt, _ = scan_pair
+    _, _, st = hostsim.knn(tgt, tgt, 20, want_stats=True)
+    nodes, lookups, cands = st
+    assert cands < 150 and lookups < 60, st
+
+
+@pytest.mark.parametrize("method", [0, 1, 2, 3, 4])
+def test_covariance_math(small_pair, method):
+    src, tgt, _ = small_pair
+    idx, _ = orc.knn(tgt, tgt, 20)
+    oc = orc.covariances_from_knn(tgt, idx, method)
+    sc = hostsim.covs(tgt, idx, method)
+    scale = np.abs(oc).max(axis=(1, 2), keepdims=True)
+    assert (np.abs(sc - oc) / scale).max() < 1e-8
+
+
+@pytest.mark.parametrize("thr", [FLT_MAX, 2.0, 0.3])
+def test_linearize_math(small_pair, thr):
+    src, tgt, _ = small_pair
+    o = orc.FastGICP(corr_dist=thr)
+    o.setInputTarget(tgt)
+    o.setInputSource(src)
+    T = np.eye(4)
+    T[:3, 3] = [0.1, -0.05, 0.02]
+    oe, oH, ob = o.linearize(T)
+    ocorr, _ = o.correspondences()
+    e, H, b, corr = hostsim.linearize(src, tgt, o.getSourceCovariances(), o.getTargetCovariances(), T, thr)
+    assert np.array_equal(corr, ocorr)
+    assert abs(e - oe) <= 1e-10 * abs(oe)
+    assert np.abs(H - oH).max() <= 1e-10 * np.abs(oH).max()
+    assert np.abs(b - ob).max() <= 1e-10 * np.abs(ob).max()
+
+
+def test_host_lm_helpers():
+    L = hostsim.lib()
+    rng = np.random.default_rng(0)
+    for _ in range(100):
+        B = rng.normal(size=(6, 9))
+        H = np.ascontiguousarray(B @ B.T + 1e-6 * np.eye(6))
+        b = rng.normal(size=6)
+        x = np.empty(6)
+        L.sim_solve_ldlt6(H.reshape(-1), b, x)
+        assert np.allclose(x, orc.ldlt6_solve(H, b), rtol=1e-9, atol=1e-12)
+        assert np.allclose(x, np.linalg.solve(H, b), rtol=1e-7, atol=1e-10)
+        d = rng.normal(size=6) * 10 ** rng.uniform(-7, 0)
+        D = np.empty(16)
+        L.sim_se3_delta(d, D)
+        D = D.reshape(4, 4)
+        assert np.allclose(D[:3, :3], orc.so3_exp(d[:3]), atol=1e-15) and np.allclose(D[:3, 3], d[3:]) and D[3, 3] == 1
+    D = np.eye(4)
+    D[0, 3] = 4e-4
+    assert L.sim_is_converged(D.reshape(-1), 2e-3, 5e-4) == 1
+    D[0, 3] = 6e-4
+    assert L.sim_is_converged(D.reshape(-1), 2e-3, 5e-4) == 0
+    D[0, 3] = 0
+    D[0, 1] = 3e-3
+    assert L.sim_is_converged(D.reshape(-1), 2e-3, 5e-4) == 0
