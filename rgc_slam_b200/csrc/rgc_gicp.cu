@@ -16,81 +16,11 @@
 #include <unordered_map>
 #include <vector>
 
-#include "../../include/rgc_gicp.h"
+#include "rgc_ctx.hpp"
 #include "rgc_kernels.cuh"
 #include "rgc_lm.hpp"
 
 using namespace rgc;
-
-// ------------------------------------------------------------------------------------------------
-struct rgc_ctx {
-  int device = 0;
-  cudaStream_t stream = nullptr;
-  std::string err;
-  uint64_t launches = 0;
-  // pooled device memory: power-of-two size classes, never returned to the driver before destroy
-  std::multimap<size_t, void*> free_blocks;
-  std::unordered_map<void*, size_t> block_size;
-  // pinned, device-mapped result area the reduction kernels write straight into
-  double* h_result = nullptr;
-  double* d_result = nullptr;  // device alias of h_result
-  float* h_bbox = nullptr;     // pinned: kBboxBlocks x 6
-  uint32_t* h_counts = nullptr;  // pinned: kMaxLevels
-  unsigned int* d_ticket = nullptr;
-  cudaEvent_t ev[8];
-
-  void* get(size_t bytes) {
-    size_t cls = 4096;
-    while (cls < bytes) cls <<= 1;
-    auto it = free_blocks.find(cls);
-    if (it != free_blocks.end()) {
-      void* p = it->second;
-      free_blocks.erase(it);
-      return p;
-    }
-    void* p = nullptr;
-    if (cudaMalloc(&p, cls) != cudaSuccess) {
-      cudaGetLastError();
-      return nullptr;
-    }
-    block_size[p] = cls;
-    return p;
-  }
-  void put(void* p) {
-    if (!p) return;
-    free_blocks.insert({block_size[p], p});
-  }
-};
-
-#define CK(ctx, call)                                                                                   \
-  do {                                                                                                  \
-    cudaError_t e_ = (call);                                                                            \
-    if (e_ != cudaSuccess) {                                                                            \
-      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                  \
-      return RGC_ERR_CUDA;                                                                              \
-    }                                                                                                   \
-  } while (0)
-#define CKL(ctx)                                                                                        \
-  do {                                                                                                  \
-    (ctx)->launches++;                                                                                  \
-    cudaError_t e_ = cudaGetLastError();                                                                \
-    if (e_ != cudaSuccess) {                                                                            \
-      (ctx)->err = std::string("kernel launch: ") + cudaGetErrorString(e_);                             \
-      return RGC_ERR_CUDA;                                                                              \
-    }                                                                                                   \
-  } while (0)
-#define FAIL(ctx, code, msg) \
-  do {                       \
-    (ctx)->err = (msg);      \
-    return (code);           \
-  } while (0)
-#define TRY(expr)          \
-  do {                     \
-    int rc_ = (expr);      \
-    if (rc_ != 0) return rc_; \
-  } while (0)
-
-static inline int div_up(int a, int b) { return (a + b - 1) / b; }
 
 // RGC_TRACE=1: wall-clock trace of the host side of the build pipeline (debug aid)
 static bool trace_on() {
