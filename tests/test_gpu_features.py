@@ -34,8 +34,9 @@ def test_features_match_oracle_on_a_batch(scene, traj, beams, az):
     scans = [synth.lidar_scan(scene, traj[f], n_beams=beams, n_azimuth=az, seed=700 + f) for f in (3, 9, 17, 25)]
     # a near obstacle so the r < 2 m incidence-angle / intensity-smoothing branch runs
     near = scans[0].copy()
-    sel = (near[:, 0] > 0) & (np.abs(near[:, 1]) < 1.0) & (near[:, 2] > -0.4)
-    near[sel, :3] *= (1.5 / np.maximum(np.linalg.norm(near[sel, :3], axis=1), 1e-3))[:, None]
+    sel = (near[:, 0] > 0) & (np.abs(near[:, 1]) < 0.17 * near[:, 0])
+    rng = np.random.default_rng(5)
+    near[sel, :3] *= ((1.2 + 0.5 * rng.random(sel.sum())) / np.maximum(np.linalg.norm(near[sel, :3], axis=1), 1e-3))[:, None]
     scans.append(near)
     scans.append(scans[1][:137])  # ragged: a scan with almost nothing in it
     res, ms = extract_features(scans, n_rings=beams)
