@@ -1,0 +1,35 @@
+"""GPU: the header-only C++ facade (include/rgc/fast_gicp.hpp) driven exactly like the reference
+call site (RGC_odometer.cpp:998-1015), compared with the oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import rot_angle
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cpp_facade_matches_oracle(small_pair, tmp_path):
+    from oracle import oracle as orc
+    src, tgt, _ = small_pair
+    exe = str(tmp_path / "facade_smoke")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    libdir = os.path.join(ROOT, "rgc_slam_b200")
+    subprocess.check_call([cxx, "-std=c++17", "-O2", "-o", exe, os.path.join(ROOT, "tests", "cpp", "facade_smoke.cpp"),
+                           "-L", libdir, "-lrgc_gicp", f"-Wl,-rpath,{libdir}"])
+    tgt.tofile(tmp_path / "tgt.bin")
+    src.tofile(tmp_path / "src.bin")
+    out = subprocess.run([exe, str(tmp_path / "tgt.bin"), str(tmp_path / "src.bin")], capture_output=True, text=True, check=True).stdout.split("\n")
+    head = out[0].split()
+    T = np.array([[float(v) for v in out[1 + r].split()] for r in range(4)])
+    o = orc.FastGICP(max_iterations=25, corr_dist=2.0, transformation_epsilon=1e-6)
+    o.setInputTarget(tgt)
+    o.setInputSource(src)
+    To = o.align()
+    assert int(head[1]) == int(o.last["converged"]) and int(head[3]) == o.last["iterations"]
+    assert np.abs(T[:3, 3] - To[:3, 3]).max() < 1e-4 and rot_angle(T[:3, :3], To[:3, :3]) < 1e-5
+    assert abs(float(head[5]) - o.getFitnessScore()) < 1e-6 * o.getFitnessScore()
+    assert int(head[7]) == len(src) and int(head[9]) == 1
