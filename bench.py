@@ -90,35 +90,41 @@ class ClockSampler:
         self._stop = threading.Event()
         self.thr = None
         self.how = "nvml"
+        self.interval = float(os.environ.get("RGC_CLOCK_INTERVAL", "0.05"))
+        self._nv = None
 
-    def _loop(self):
+    def prepare(self):
+        """nvmlInit + handle lookup are slow and take driver locks: do them BEFORE the timed region."""
         try:
             import pynvml
             pynvml.nvmlInit()
             vis = os.environ.get("CUDA_VISIBLE_DEVICES")
             idx = int(vis.split(",")[self.gpu_index]) if vis and vis.split(",")[0].isdigit() else self.gpu_index
-            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
-            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
-            while not self._stop.is_set():
-                self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
-                self.mx.append(float(mx))
-                try:
-                    r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                    for bit, name in self.REASONS.items():
-                        if r & bit:
-                            self.reasons.add(name)
-                except Exception:
-                    pass
-                self._stop.wait(0.2)
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self._max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
         except Exception as e:  # noqa: BLE001
-            self.how = f"nvml failed ({type(e).__name__}); nvidia-smi single query"
-            try:
-                out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits", "-i", str(self.gpu_index)],
-                                     capture_output=True, text=True, timeout=10).stdout.strip().split(",")
-                self.sm.append(float(out[0]))
-                self.mx.append(float(out[1]))
-            except Exception:
-                pass
+            self._nv = None
+            self.how = f"nvml unavailable ({type(e).__name__}); one nvidia-smi query after the timed region"
+
+    def _sample(self):
+        nv, h = self._nv, self._h
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+        self.mx.append(self._max)
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            for bit, name in self.REASONS.items():
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _loop(self):
+        if self._nv is None:
+            return
+        while not self._stop.is_set():
+            self._sample()
+            self._stop.wait(self.interval)
 
     def start(self):
         self.thr = threading.Thread(target=self._loop, daemon=True)
@@ -128,6 +134,14 @@ class ClockSampler:
         self._stop.set()
         if self.thr:
             self.thr.join(timeout=3)
+        if self._nv is None:
+            try:
+                out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits", "-i", str(self.gpu_index)],
+                                     capture_output=True, text=True, timeout=10).stdout.strip().split(",")
+                self.sm.append(float(out[0]))
+                self.mx.append(float(out[1]))
+            except Exception:
+                pass
         return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
                 "reasons": sorted(self.reasons), "samples": len(self.sm), "how": self.how}
 
@@ -183,7 +197,7 @@ def run_ours(args, rank, world):
     stage_acc = {}
     iters = []
     sampler = ClockSampler(local)
-    launches0 = ctx.launch_count
+    sampler.prepare()
     barrier()
     sampler.start()
     dev_ms = 0.0

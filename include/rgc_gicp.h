@@ -58,7 +58,7 @@ typedef struct {
   int lm_max_iterations;             /* lm_max_iterations_                  (10)      */
   double lm_init_lambda_factor;      /* setInitialLambdaFactor              (1e-9)    */
   int lm_debug_print;                /* setDebugPrint                       (0)       */
-  float grid_cell;                   /* finest voxel edge of the kNN grid in metres; 0 = default (0.2) */
+  float grid_cell;                   /* finest voxel edge of the kNN grid in metres; 0 = default (0.05) */
 } rgc_params;
 
 typedef struct {
@@ -134,6 +134,19 @@ int rgc_reg_get_final_transformation(const rgc_reg* reg, float* T16);
  * idx/d2: m x k row-major; rows are padded with -1 / +inf when k > n.  Test hook + public op. */
 int rgc_knn(rgc_ctx* ctx, const void* points, size_t n, size_t stride_bytes, const void* queries, size_t m, size_t qstride_bytes, int k,
             int32_t* idx, float* d2, float grid_cell);
+
+/* ---- sharded target: this rank holds only a spatial slab of the target
+ * (plus a halo >= max_correspondence_distance).  A source point is handled by exactly one rank: the
+ * one whose slab [lo, hi) along `axis` (0/1/2) contains its TRANSFORMED position (computed in float,
+ * identically on every rank).  axis < 0 switches sharding off.                                      */
+int rgc_reg_set_owner_slab(rgc_reg* reg, int axis, float lo, float hi);
+/* After every linearize / compute_error / fitness kernel the partial sums (n doubles: 29 / 1 / 2)
+ * sit in `d_buf` (device memory, caller-owned, >= 29 doubles); `fn` must sum them across ranks IN
+ * PLACE on the context's stream (one NCCL all-reduce; the caller owns the communicator, e.g.
+ * torch.distributed) before returning 0.  The host LM loop then proceeds on the reduced values, so
+ * every rank takes identical steps.  fn == NULL switches the hook off.                              */
+typedef int (*rgc_reduce_fn)(void* user, void* d_buf, int n_doubles);
+int rgc_reg_set_allreduce(rgc_reg* reg, rgc_reduce_fn fn, void* user, void* d_buf);
 
 /* per-stage device times (ms, CUDA events) of the last set_source / set_target / align on this reg:
  * [0] source build (ingest+sort+tables) [1] source kNN [2] source cov [3] target build

@@ -242,7 +242,24 @@ struct rgc_reg {
   bool converged = false;
   int n_linearize = 0, n_compute_error = 0, last_inliers = 0;
   float lm_ms = 0;
+  // sharded target (config C5)
+  Slab slab{-1, 0.f, 0.f};
+  rgc_reduce_fn reduce_fn = nullptr;
+  void* reduce_user = nullptr;
+  double* reduce_buf = nullptr;  // device, caller-owned
 };
+
+// where the reduction kernels write, and (sharded) the cross-rank sum before the host reads it
+static double* reg_result_ptr(rgc_reg* r) { return r->reduce_fn ? r->reduce_buf : r->ctx->d_result; }
+static int reg_finish_reduce(rgc_reg* r, int n_doubles) {
+  rgc_ctx* c = r->ctx;
+  if (r->reduce_fn) {
+    if (r->reduce_fn(r->reduce_user, r->reduce_buf, n_doubles) != 0) FAIL(c, RGC_ERR_STATE, "all-reduce hook failed");
+    CK(c, cudaMemcpyAsync(c->h_result, r->reduce_buf, sizeof(double) * n_doubles, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CK(c, cudaStreamSynchronize(c->stream));
+  return RGC_OK;
+}
 
 static int reg_ensure_work(rgc_reg* r) {
   rgc_ctx* c = r->ctx;
@@ -279,10 +296,10 @@ static int reg_linearize(rgc_reg* r, const double* T, double* err, double* H, do
   const float thr2 = thr * thr;  // float product, +inf for the FLT_MAX default (fast_gicp_impl.hpp:136)
   const int want = (H && b) ? 1 : 0;
   const int spread = query_spread(r->src.n);
-  k_linearize<<<div_up(r->src.n * spread, kThreads), kThreads, 0, c->stream>>>(r->tgt.view, r->src.sorted, r->src.cov, r->tgt.cov, r->src.n, spread, Tf, Td, thr2, want,
-                                                                     r->corr, r->sqd, r->maha, r->partials, c->d_ticket, c->d_result);
+  k_linearize<<<div_up(r->src.n * spread, kThreads), kThreads, 0, c->stream>>>(r->tgt.view, r->src.sorted, r->src.cov, r->tgt.cov, r->src.n, spread, Tf, Td, thr2, want, r->slab,
+                                                                     r->corr, r->sqd, r->maha, r->partials, c->d_ticket, reg_result_ptr(r));
   CKL(c);
-  CK(c, cudaStreamSynchronize(c->stream));
+  TRY(reg_finish_reduce(r, kLinN));
   r->n_linearize++;
   r->have_corr = true;
   const double* res = c->h_result;
@@ -308,9 +325,9 @@ static int reg_compute_error(rgc_reg* r, const double* T, double* err) {
   RtF Tf;
   to_rt(T, Td, Tf);
   k_compute_error<<<div_up(r->src.n, kThreads), kThreads, 0, c->stream>>>(r->tgt.sorted, r->src.sorted, r->src.n, Td, r->corr, r->maha, r->partials,
-                                                                         c->d_ticket, c->d_result);
+                                                                         c->d_ticket, reg_result_ptr(r));
   CKL(c);
-  CK(c, cudaStreamSynchronize(c->stream));
+  TRY(reg_finish_reduce(r, 1));
   r->n_compute_error++;
   *err = c->h_result[0];
   return RGC_OK;
@@ -670,10 +687,10 @@ int rgc_reg_fitness(rgc_reg* r, double max_range, double* score) {
   RtF Tf;
   for (int i = 0; i < 12; i++) Tf.m[i] = r->final_T[i];
   const int spread = query_spread(r->src.n);
-  k_fitness<<<div_up(r->src.n * spread, kThreads), kThreads, 0, c->stream>>>(r->tgt.view, r->src.sorted, r->src.n, spread, Tf, max_range, r->partials, c->d_ticket,
-                                                                            c->d_result);
+  k_fitness<<<div_up(r->src.n * spread, kThreads), kThreads, 0, c->stream>>>(r->tgt.view, r->src.sorted, r->src.n, spread, Tf, max_range, r->slab, r->partials, c->d_ticket,
+                                                                            reg_result_ptr(r));
   CKL(c);
-  CK(c, cudaStreamSynchronize(c->stream));
+  TRY(reg_finish_reduce(r, 2));
   const double sum = c->h_result[0], nr = c->h_result[1];
   *score = nr > 0 ? sum / nr : DBL_MAX;
   return RGC_OK;
@@ -713,6 +730,20 @@ int rgc_knn(rgc_ctx* c, const void* points, size_t n, size_t stride, const void*
   c->put(d_idx);
   c->put(d_d2);
   cloud_release(c, cl);
+  return RGC_OK;
+}
+
+int rgc_reg_set_owner_slab(rgc_reg* r, int axis, float lo, float hi) {
+  if (!r || axis > 2) return RGC_ERR_INVALID;
+  r->slab = Slab{axis, lo, hi};
+  r->have_corr = false;
+  return RGC_OK;
+}
+int rgc_reg_set_allreduce(rgc_reg* r, rgc_reduce_fn fn, void* user, void* d_buf) {
+  if (!r || (fn && !d_buf)) return RGC_ERR_INVALID;
+  r->reduce_fn = fn;
+  r->reduce_user = user;
+  r->reduce_buf = (double*)d_buf;
   return RGC_OK;
 }
 

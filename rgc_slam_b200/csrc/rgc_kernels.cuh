@@ -374,13 +374,24 @@ struct RtF {
   float m[12];
 };
 
+// ownership slab of a sharded target: a query is this rank's iff lo <= q[axis] < hi (axis < 0: all)
+struct Slab {
+  int axis;
+  float lo, hi;
+};
+__device__ __forceinline__ bool slab_owns(const Slab& s, float qx, float qy, float qz) {
+  if (s.axis < 0) return true;
+  const float v = s.axis == 0 ? qx : (s.axis == 1 ? qy : qz);
+  return v >= s.lo && v < s.hi;
+}
+
 constexpr int kLinN = kAccN + 1;  // + inlier count
 
 // fused update_correspondences + linearize (fast_gicp_impl.hpp:115-211).  One thread per source
 // point (Morton order).  Stores the correspondence (sorted target position), its d2 and M for
 // the compute_error calls that follow.
 __global__ void __launch_bounds__(kThreads, 4) k_linearize(GridView tgt, const float4* __restrict__ src, const double* __restrict__ src_cov,
-                                                        const double* __restrict__ tgt_cov, int n_src, int spread, RtF Tf, Rt Td, float thr2, int want_hb,
+                                                        const double* __restrict__ tgt_cov, int n_src, int spread, RtF Tf, Rt Td, float thr2, int want_hb, Slab slab,
                                                         int* __restrict__ corr, float* __restrict__ sqd, double* __restrict__ maha,
                                                         double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ result) {
   const int gt = blockIdx.x * blockDim.x + threadIdx.x;
@@ -392,7 +403,8 @@ __global__ void __launch_bounds__(kThreads, 4) k_linearize(GridView tgt, const f
     float qx, qy, qz;
     transform_f(Tf.m, p.x, p.y, p.z, qx, qy, qz);
     Best1 top;
-    knn_search(tgt, qx, qy, qz, 1, thr2, -1, top);
+    top.reset(1, thr2);
+    if (slab_owns(slab, qx, qy, qz)) knn_search(tgt, qx, qy, qz, 1, thr2, -1, top);
     pos = (top.id0 >= 0 && top.d0 < thr2) ? top.id0 : -1;
     corr[i] = pos;
     sqd[i] = top.d0;
@@ -435,7 +447,7 @@ __global__ void __launch_bounds__(kThreads) k_compute_error(const float4* __rest
 }
 
 // pcl::Registration::getFitnessScore: [sum d2, count] over 1-NN d2 <= max_range
-__global__ void __launch_bounds__(kThreads, 8) k_fitness(GridView tgt, const float4* __restrict__ src, int n_src, int spread, RtF Tf, double max_range,
+__global__ void __launch_bounds__(kThreads, 8) k_fitness(GridView tgt, const float4* __restrict__ src, int n_src, int spread, RtF Tf, double max_range, Slab slab,
                                                       double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ result) {
   double acc[2] = {0.0, 0.0};
   const int gt = blockIdx.x * blockDim.x + threadIdx.x;
@@ -445,7 +457,8 @@ __global__ void __launch_bounds__(kThreads, 8) k_fitness(GridView tgt, const flo
     float qx, qy, qz;
     transform_f(Tf.m, p.x, p.y, p.z, qx, qy, qz);
     Best1 top;
-    knn_search(tgt, qx, qy, qz, 1, INFINITY, -1, top);
+    top.reset(1, INFINITY);
+    if (slab_owns(slab, qx, qy, qz)) knn_search(tgt, qx, qy, qz, 1, INFINITY, -1, top);
     if (top.id0 >= 0 && (double)top.d0 <= max_range) {
       acc[0] = (double)top.d0;
       acc[1] = 1.0;

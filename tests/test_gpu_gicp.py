@@ -230,3 +230,40 @@ def test_errors_are_loud(rgc):
         g.setCorrespondenceRandomness(64)  # k > 32 unsupported
     with pytest.raises(rgc.RgcError):
         g.setInputSource(np.zeros((0, 4), np.float32))
+
+
+def test_fake_sharded_target_matches_unsharded(rgc, scan_pair):
+    """Config C5 logic on ONE GPU: two slabs of the target held by two registration objects, every
+    source point handled by exactly one of them, partial (err, H, b) summed on the host ==
+    the unsharded linearize (SURVEY §4 'fake shard' mode; fp64 summation order is the only difference)."""
+    import ctypes as C
+    from rgc_slam_b200 import sharded
+    src, tgt, _ = scan_pair
+    corr, cov_halo = 2.0, 4.0
+    T = np.eye(4)
+    T[:3, 3] = [0.1, -0.05, 0.02]
+    full = rgc.FastGICP()
+    full.setMaxCorrespondenceDistance(corr)
+    full.setInputTarget(tgt)
+    full.setInputSource(src)
+    e, H, b = full.linearize(T)
+    n_in = (full.correspondences()[0] >= 0).sum()
+    L = rgc.lib()
+    L.rgc_reg_set_owner_slab.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float]
+    for world in (2, 3):
+        edges = sharded.slab_boundaries(tgt[:, 0], world)
+        es, Hs, bs, ins = 0.0, np.zeros((6, 6)), np.zeros(6), 0
+        for r in range(world):
+            g = rgc.FastGICP()
+            g.setMaxCorrespondenceDistance(corr)
+            keep = sharded.slab_select(tgt, 0, edges[r], edges[r + 1], corr + cov_halo)
+            g.setInputTarget(np.ascontiguousarray(tgt[keep]))
+            g.setInputSource(src)
+            big = float(np.finfo(np.float32).max)
+            g.ctx.check(L.rgc_reg_set_owner_slab(g._h, 0, max(float(edges[r]), -big), min(float(edges[r + 1]), big)))
+            er, Hr, br = g.linearize(T)
+            es, Hs, bs = es + er, Hs + Hr, bs + br
+            ins += (g.correspondences()[0] >= 0).sum()
+        assert ins == n_in
+        assert abs(es - e) <= 1e-11 * abs(e)
+        assert np.abs(Hs - H).max() <= 1e-11 * np.abs(H).max() and np.abs(bs - b).max() <= 1e-11 * np.abs(b).max()
