@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -102,6 +103,7 @@ class Context:
         if rc != 0:
             raise RgcError(f"rgc_ctx_create(device={device}) failed with {rc}: no usable CUDA device (there is no CPU fallback)")
         self.device = device
+        self._regs = weakref.WeakSet()  # registration objects that must be destroyed before the context
 
     def check(self, rc: int):
         if rc != 0:
@@ -120,6 +122,8 @@ class Context:
 
     def close(self):
         if self._h:
+            for r in list(self._regs):
+                r._destroy()
             lib().rgc_ctx_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -165,6 +169,7 @@ class FastGICP:
         self.ctx = ctx or default_context(device)
         self._h = C.c_void_p()
         self.ctx.check(lib().rgc_reg_create(self.ctx._h, C.byref(self._h)))
+        self.ctx._regs.add(self)
         self._p = _Params()
         lib().rgc_params_default(C.byref(self._p))
         self._src = self._tgt = None
@@ -174,11 +179,14 @@ class FastGICP:
         self._result = None
         self.output = None
 
+    def _destroy(self):
+        if self._h and self.ctx._h:
+            lib().rgc_reg_destroy(self._h)
+        self._h = C.c_void_p()
+
     def __del__(self):
         try:
-            if self._h:
-                lib().rgc_reg_destroy(self._h)
-                self._h = C.c_void_p()
+            self._destroy()
         except Exception:
             pass
 
