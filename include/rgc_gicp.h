@@ -135,6 +135,11 @@ int rgc_reg_get_final_transformation(const rgc_reg* reg, float* T16);
 int rgc_knn(rgc_ctx* ctx, const void* points, size_t n, size_t stride_bytes, const void* queries, size_t m, size_t qstride_bytes, int k,
             int32_t* idx, float* d2, float grid_cell);
 
+/* k nearest neighbours of every point of a cloud within the cloud itself (self included, rank 0),
+ * through the same warp-cooperative kernel calculate_covariances uses (FGI/fast_gicp_impl.hpp:254).
+ * idx: n x k row-major, original indices, ascending by (d2, index); -1 padding when k > n.      */
+int rgc_knn_self(rgc_ctx* ctx, const void* points, size_t n, size_t stride_bytes, int k, int32_t* idx, float grid_cell);
+
 /* ---- sharded target: this rank holds only a spatial slab of the target
  * (plus a halo >= max_correspondence_distance).  A source point is handled by exactly one rank: the
  * one whose slab [lo, hi) along `axis` (0/1/2) contains its TRANSFORMED position (computed in float,

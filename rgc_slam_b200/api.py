@@ -79,6 +79,7 @@ def lib():
         L.rgc_reg_get_final_transformation.argtypes = [vp, vp]
         L.rgc_knn.argtypes = [vp, vp, sz, sz, vp, sz, sz, C.c_int, vp, vp, C.c_float]
         L.rgc_reg_stage_ms.argtypes = [vp, vp]
+        L.rgc_knn_self.argtypes = [vp, vp, sz, sz, C.c_int, vp, C.c_float]
         _LIB = L
     return _LIB
 
@@ -90,7 +91,7 @@ EXPORTED_SYMBOLS = [
     "rgc_reg_swap_source_and_target", "rgc_reg_clear_source", "rgc_reg_clear_target",
     "rgc_reg_set_source_covs", "rgc_reg_set_target_covs", "rgc_reg_get_source_covs", "rgc_reg_get_target_covs",
     "rgc_reg_align", "rgc_reg_linearize", "rgc_reg_compute_error", "rgc_reg_get_correspondences", "rgc_reg_fitness",
-    "rgc_reg_get_final_transformation", "rgc_knn", "rgc_reg_stage_ms",
+    "rgc_reg_get_final_transformation", "rgc_knn", "rgc_reg_stage_ms", "rgc_knn_self", "rgc_reg_set_owner_slab", "rgc_reg_set_allreduce",
 ]
 
 
@@ -364,3 +365,12 @@ def knn(points, queries, k, ctx: Context | None = None, grid_cell: float = 0.0):
     d2 = np.empty((m, k), np.float32)
     ctx.check(lib().rgc_knn(ctx._h, pp, n, ps, qp, m, qs, k, idx.ctypes.data, d2.ctypes.data, grid_cell))
     return idx, d2
+
+
+def knn_self(points, k, ctx: Context | None = None, grid_cell: float = 0.0):
+    """kNN of every point within its own cloud through the production (tile) kernel -> idx (n, k)."""
+    ctx = ctx or default_context(0)
+    pp, n, ps, pd, keep = _as_cloud(points)
+    idx = np.empty((n, k), np.int32)
+    ctx.check(lib().rgc_knn_self(ctx._h, pp, n, ps, k, idx.ctypes.data, grid_cell))
+    return idx

@@ -201,6 +201,20 @@ static int launch_knn(rgc_ctx* c, const GridView& v, const float4* queries, int 
   return RGC_OK;
 }
 
+// self-kNN of a whole cloud: the warp-cooperative tile kernel (RGC_KNN_THREAD=1 selects the
+// thread-per-query kernel instead, for A/B profiling)
+static int launch_knn_self(rgc_ctx* c, const GridView& v, int n, int k, int* nbr) {
+  static const bool per_thread = std::getenv("RGC_KNN_THREAD") != nullptr;
+  if (per_thread) return launch_knn<true>(c, v, nullptr, n, k, nbr, nullptr);
+  if (k > 32) FAIL(c, RGC_ERR_UNSUPPORTED, "k_correspondences > 32 is not supported");
+  const size_t per_warp = sizeof(float4) * KT_CAND + sizeof(TileNode) * KT_STACK + (size_t)(k + KT_PEND) * 32 * 8;
+  const size_t smem = per_warp * KT_WARPS;
+  CK(c, cudaFuncSetAttribute(k_knn_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_knn_tile<<<div_up(n, KT_WARPS * 32), KT_WARPS * 32, smem, c->stream>>>(v, n, k, nbr);
+  CKL(c);
+  return RGC_OK;
+}
+
 // FastGICP::calculate_covariances (fast_gicp_impl.hpp:241-299)
 static int cloud_covariances(rgc_ctx* c, Cloud& cl, int k, int method) {
   if (cl.has_cov) return RGC_OK;
@@ -210,7 +224,7 @@ static int cloud_covariances(rgc_ctx* c, Cloud& cl, int k, int method) {
   if (!cl.cov) cl.cov = (double*)c->get(sizeof(double) * 6 * (size_t)cl.n);
   if (!nbr || !cl.cov) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (covariances)");
   CK(c, cudaEventRecord(c->ev[2], st));
-  TRY(launch_knn<true>(c, cl.view, nullptr, cl.n, k, nbr, nullptr));
+  TRY(launch_knn_self(c, cl.view, cl.n, k, nbr));
   CK(c, cudaEventRecord(c->ev[3], st));
   k_covariance<<<div_up(cl.n, kThreads), kThreads, 0, st>>>(cl.sorted, nbr, cl.n, k, method, cl.cov);
   CKL(c);
@@ -729,6 +743,27 @@ int rgc_knn(rgc_ctx* c, const void* points, size_t n, size_t stride, const void*
   c->put(bb);
   c->put(d_idx);
   c->put(d_d2);
+  cloud_release(c, cl);
+  return RGC_OK;
+}
+
+// kNN of every point of a cloud within the cloud itself, through the SAME kernel calculate_covariances
+// uses (test hook for fast_gicp_impl.hpp:254); idx: n x k original indices, ascending by (d2, index)
+int rgc_knn_self(rgc_ctx* c, const void* points, size_t n, size_t stride, int k, int32_t* idx, float grid_cell) {
+  if (!c || !points || !idx || k < 1) return RGC_ERR_INVALID;
+  CK(c, cudaSetDevice(c->device));
+  Cloud cl;
+  TRY(cloud_build(c, cl, points, n, stride, false, 0, grid_cell));
+  int* nbr = (int*)c->get(sizeof(int) * (size_t)k * n);
+  int* d_idx = (int*)c->get(sizeof(int) * (size_t)k * n);
+  if (!nbr || !d_idx) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (knn_self)");
+  TRY(launch_knn_self(c, cl.view, cl.n, k, nbr));
+  k_nbr_to_orig<<<div_up(cl.n, 256), 256, 0, c->stream>>>(cl.sorted, nbr, cl.n, k, d_idx);
+  CKL(c);
+  CK(c, cudaMemcpyAsync(idx, d_idx, sizeof(int) * (size_t)k * n, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  c->put(nbr);
+  c->put(d_idx);
   cloud_release(c, cl);
   return RGC_OK;
 }

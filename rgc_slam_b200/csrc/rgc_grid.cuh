@@ -237,7 +237,36 @@ struct HeapK {
     }
     sift_down_from_root(dn, pos, orig, k, pts);
   }
-  RGC_HD void sift_down_from_root(float dn, int pos, int orig, int size, const F4* pts) {
+  // same as insert(), but the original index of the new entry is fetched only if a tie needs it
+  RGC_HD void insert_lazy(float dn, int pos, const F4* pts) {
+    if (dn > lim) return;
+    if (cnt < k) {
+      int j = cnt++;
+      while (j > 0) {
+        const int p = (j - 1) >> 1;
+        const float dp = d[p * stride];
+        const int ip = id[p * stride];
+        bool up = dn > dp;
+        if (dn == dp) up = f2i_bits(load_pt(pts + pos).w) > f2i_bits(load_pt(pts + ip).w);
+        if (!up) break;
+        d[j * stride] = dp;
+        id[j * stride] = ip;
+        j = p;
+      }
+      d[j * stride] = dn;
+      id[j * stride] = pos;
+      return;
+    }
+    const float dr = d[0];
+    if (dn > dr) return;
+    int orig = -1;
+    if (dn == dr) {
+      orig = f2i_bits(load_pt(pts + pos).w);
+      if (!(orig < f2i_bits(load_pt(pts + id[0]).w))) return;
+    }
+    sift_down_from_root(dn, pos, orig, k, pts, pos);
+  }
+  RGC_HD void sift_down_from_root(float dn, int pos, int orig, int size, const F4* pts, int lazy_pos = -1) {
     int j = 0;
     for (;;) {
       int c = 2 * j + 1;
@@ -257,7 +286,10 @@ struct HeapK {
       }
       // stop when the larger child is not after the new entry
       bool child_after = dc > dn;
-      if (dc == dn) child_after = f2i_bits(load_pt(pts + ic).w) > orig;
+      if (dc == dn) {
+        if (orig < 0 && lazy_pos >= 0) orig = f2i_bits(load_pt(pts + lazy_pos).w);
+        child_after = f2i_bits(load_pt(pts + ic).w) > orig;
+      }
       if (!child_after) break;
       d[j * stride] = dc;
       id[j * stride] = ic;

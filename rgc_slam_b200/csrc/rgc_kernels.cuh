@@ -300,6 +300,189 @@ __global__ void __launch_bounds__(kThreads, 8) k_knn(GridView g, const float4* _
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Warp-cooperative self-kNN ("tile" kernel): one warp owns 32 Morton-adjacent queries.
+//
+// An ncu profile of the thread-per-query walk (profiles/) showed ~5 of 32 lanes active: every lane
+// walks its own tree and inserts into its own heap at different times.  Here the warp does the
+// walk ONCE for its 32 queries and all divergent work is turned into lockstep phases:
+//   seeds    the 64 Morton-adjacent points are folded into every lane's heap (lockstep inserts):
+//            a tight per-lane bound on the k-th distance before any tree node is touched;
+//   gather   warp-uniform depth-first walk; a cell is visited iff ANY lane's ball (its query,
+//            radius = its current k-th distance) touches the cell's box (per-lane test + vote);
+//            the points of small cells are copied, coalesced, into a shared candidate buffer;
+//   consume  every lane scans the buffer (shared-memory broadcast reads, no divergence) and APPENDS
+//            the candidates inside its ball to a pending list (no heap work here);
+//   fold     when a pending list fills up (and at the end) all lanes fold their pending entries
+//            into their heaps together, tightening the balls.
+// Exactness is unchanged: a point is dropped only if its cell is outside every ball or its d2
+// exceeds the lane's current k-th distance; ties are resolved by (d2, original index) in the heap.
+constexpr int KT_WARPS = 4;
+constexpr int KT_CAND = 224;    // candidate buffer entries per warp
+constexpr int KT_STACK = 64;    // DFS stack entries per warp
+constexpr int KT_SEEDS = 64;    // Morton-adjacent seed points per warp
+constexpr int KT_PEND = 28;     // pending slots per lane
+constexpr int KT_LEAF = 32;     // cells with <= this many points are gathered whole
+
+struct TileNode {
+  uint32_t cx_lvl, cy_mask, cz, start, end;
+};
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__global__ void __launch_bounds__(KT_WARPS * 32) k_knn_tile(GridView g, int n, int k, int* __restrict__ out_idx) {
+  extern __shared__ __align__(16) unsigned char tile_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cap = k + KT_PEND;
+  // per-warp carve-up
+  const size_t per_warp = sizeof(float4) * KT_CAND + sizeof(TileNode) * KT_STACK + (size_t)cap * 32 * 8;
+  unsigned char* base = tile_smem + (size_t)warp * per_warp;
+  float4* cand = reinterpret_cast<float4*>(base);
+  TileNode* stack = reinterpret_cast<TileNode*>(base + sizeof(float4) * KT_CAND);
+  float* hd = reinterpret_cast<float*>(base + sizeof(float4) * KT_CAND + sizeof(TileNode) * KT_STACK);
+  int* hi = reinterpret_cast<int*>(hd + (size_t)cap * 32);
+
+  const int first = (blockIdx.x * KT_WARPS + warp) * 32;
+  if (first >= n) return;
+  const int t = min(first + lane, n - 1);  // tail lanes shadow the last query (no output)
+  const float4 q = reinterpret_cast<const float4*>(g.pts)[t];
+  const F4* pts = g.pts;
+
+  HeapK heap;
+  heap.init(hd + lane, hi + lane, 32);
+  heap.reset(k, INFINITY);
+  int npend = 0;
+
+  // ---- seeds: Morton neighbours of the tile, folded in lockstep
+  const int ns = min(KT_SEEDS, n);
+  const int s0 = max(0, min(first - (KT_SEEDS - 32) / 2, n - ns));
+  for (int j = lane; j < ns; j += 32) {
+    float4 c = reinterpret_cast<const float4*>(pts)[s0 + j];
+    c.w = __int_as_float(s0 + j);
+    cand[j] = c;
+  }
+  __syncwarp();
+  for (int j = 0; j < ns; j++) {
+    const float4 c = cand[j];
+    heap.insert_lazy(dist2_ref(q.x, q.y, q.z, c.x, c.y, c.z), __float_as_int(c.w), pts);
+  }
+  __syncwarp();
+
+  auto fold = [&]() {
+    const int mx = __reduce_max_sync(0xffffffffu, npend);
+    for (int e = 0; e < mx; e++)
+      if (e < npend) heap.insert_lazy(hd[(k + e) * 32 + lane], hi[(k + e) * 32 + lane], pts);
+    npend = 0;
+  };
+  auto bound = [&]() { return heap.cnt == k ? heap.d[0] : INFINITY; };
+  int ncand = 0;
+  auto consume = [&]() {
+    __syncwarp();
+    for (int j = 0; j < ncand; j++) {
+      const float4 c = cand[j];
+      const float d2 = dist2_ref(q.x, q.y, q.z, c.x, c.y, c.z);
+      if (d2 <= bound()) {
+        hd[(k + npend) * 32 + lane] = d2;
+        hi[(k + npend) * 32 + lane] = __float_as_int(c.w);
+        npend++;
+      }
+      if (__any_sync(0xffffffffu, npend == KT_PEND)) fold();
+    }
+    ncand = 0;
+    __syncwarp();
+  };
+
+  if (n > ns) {
+    // ---- roots: cells covering the union of the balls, at a level where that is <= 4 cells per axis
+    const float b0 = bound();
+    const float r = b0 < INFINITY ? sqrtf(b0) * 1.00001f + 2.f * g.margin : INFINITY;
+    const float lox = warp_min(q.x - r), loy = warp_min(q.y - r), loz = warp_min(q.z - r);
+    const float hix = warp_max(q.x + r), hiy = warp_max(q.y + r), hiz = warp_max(q.z + r);
+    const float ext = fmaxf(fmaxf(hix - lox, hiy - loy), hiz - loz);
+    const int top_level = g.nlevels - 1;
+    int lb = 0;
+    while (lb < top_level && !(g.s0 * (float)(1 << lb) >= 0.5f * ext)) lb++;
+    const float inv_cs = g.inv_s0 / (float)(1 << lb);
+    const int ncell = 1 << (g.nbits - lb);
+    int rlo[3], rhi[3];
+    {
+      const float l3[3] = {lox, loy, loz}, h3[3] = {hix, hiy, hiz}, o3[3] = {g.ox, g.oy, g.oz};
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        const float tl = (l3[a] - o3[a]) * inv_cs, th = (h3[a] - o3[a]) * inv_cs;
+        const int il = tl < 0.f ? 0 : (tl >= (float)ncell ? ncell : (int)tl);
+        const int ih = th < 0.f ? -1 : (th >= (float)ncell ? ncell - 1 : (int)th);
+        rlo[a] = il > 0 ? il - 1 : 0;
+        rhi[a] = ih < ncell - 1 ? ih + 1 : ncell - 1;
+        if (ih < 0 || il >= ncell) rhi[a] = rlo[a] - 1;
+      }
+    }
+    for (int rz = rlo[2]; rz <= rhi[2]; rz++)
+      for (int ry = rlo[1]; ry <= rhi[1]; ry++)
+        for (int rx = rlo[0]; rx <= rhi[0]; rx++) {
+          if (!__any_sync(0xffffffffu, box_dist2(g, lb, rx, ry, rz, q.x, q.y, q.z) <= bound())) continue;
+          uint32_t s, e, m;
+          if (!grid_lookup(g, lb, rx, ry, rz, s, e, m)) continue;  // uniform across the warp
+          int sp = 0;
+          if (lane == 0) stack[0] = TileNode{(uint32_t)rx | ((uint32_t)lb << 24), (uint32_t)ry | (m << 24), (uint32_t)rz, s, e};
+          sp = 1;
+          __syncwarp();
+          while (sp > 0) {
+            const TileNode nd = stack[--sp];
+            __syncwarp();
+            const int l = (int)(nd.cx_lvl >> 24);
+            const int cx = (int)(nd.cx_lvl & 0xffffffu), cy = (int)(nd.cy_mask & 0xffffffu), cz = (int)nd.cz;
+            const uint32_t cm = nd.cy_mask >> 24;
+            if (!__any_sync(0xffffffffu, box_dist2(g, l, cx, cy, cz, q.x, q.y, q.z) <= bound())) continue;
+            if (l == 0 || nd.end - nd.start <= (uint32_t)KT_LEAF || sp + 8 > KT_STACK) {
+              // gather the cell's points (minus the seeds, already folded)
+              for (uint32_t p0 = nd.start; p0 < nd.end; p0 += 32) {
+                const uint32_t p = p0 + lane;
+                const bool take = p < nd.end && (uint32_t)((int)p - s0) >= (uint32_t)ns;
+                const uint32_t bal = __ballot_sync(0xffffffffu, take);
+                if (take) {
+                  float4 c = reinterpret_cast<const float4*>(pts)[p];
+                  c.w = __int_as_float((int)p);
+                  cand[ncand + __popc(bal & ((1u << lane) - 1u))] = c;
+                }
+                ncand += __popc(bal);
+                if (ncand > KT_CAND - 32) consume();
+              }
+              continue;
+            }
+            // expand: lane c < 8 resolves child c (mask bit -> hash lookup); the others wait
+            const uint64_t pkey = morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz) << 3;
+            uint32_t cs = 0, ce = 0, cmk = 0;
+            bool have = false;
+            if (lane < 8 && ((cm >> lane) & 1u)) have = grid_lookup_key(g, l - 1, pkey | (uint64_t)lane, cs, ce, cmk);
+            const uint32_t hv = __ballot_sync(0xffffffffu, have);
+            for (int c = 0; c < 8; c++) {
+              if (!((hv >> c) & 1u)) continue;
+              const int ccx = 2 * cx + (c & 1), ccy = 2 * cy + ((c >> 1) & 1), ccz = 2 * cz + ((c >> 2) & 1);
+              if (!__any_sync(0xffffffffu, box_dist2(g, l - 1, ccx, ccy, ccz, q.x, q.y, q.z) <= bound())) continue;
+              if (lane == c) stack[sp] = TileNode{(uint32_t)ccx | ((uint32_t)(l - 1) << 24), (uint32_t)ccy | (cmk << 24), (uint32_t)ccz, cs, ce};
+              sp++;
+            }
+            __syncwarp();
+          }
+        }
+    consume();
+  }
+  fold();
+  heap.sort_ascending(pts);
+  if (first + lane < n)
+    for (int j = 0; j < k; j++) out_idx[(size_t)j * n + t] = j < heap.cnt ? hi[j * 32 + lane] : -1;
+}
+
 // covariance of sorted point t from its k neighbour positions (k-major), regularised; 6 doubles out
 __global__ void __launch_bounds__(kThreads, 4) k_covariance(const float4* __restrict__ pts, const int* __restrict__ nbr, int n, int k, int method,
                                                          double* __restrict__ cov) {
@@ -485,6 +668,17 @@ __global__ void __launch_bounds__(256) k_corr_to_orig(const float4* __restrict__
   int c = corr[i];
   corr_out[o] = c >= 0 ? __float_as_int(tgt_sorted[c].w) : -1;
   sqd_out[o] = sqd[i];
+}
+
+// k-major neighbour positions (sorted order) -> row-major original indices in the caller's order
+__global__ void __launch_bounds__(256) k_nbr_to_orig(const float4* __restrict__ sorted, const int* __restrict__ nbr, int n, int k, int* __restrict__ out) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int o = __float_as_int(sorted[t].w);
+  for (int j = 0; j < k; j++) {
+    const int p = nbr[(size_t)j * n + t];
+    out[(size_t)o * k + j] = p >= 0 ? __float_as_int(sorted[p].w) : -1;
+  }
 }
 
 // covariances between the caller's layout (4x4 doubles, original order) and ours (6 doubles, sorted)

@@ -41,6 +41,26 @@ def test_knn_bitexact_self(rgc, orc, scan_pair, k):
     assert np.array_equal(d2, od)
 
 
+@pytest.mark.parametrize("k", [1, 7, 20, 32])
+def test_knn_self_tile_kernel_bitexact(rgc, orc, scan_pair, k):
+    """the production self-kNN (warp-cooperative tile kernel used by calculate_covariances)"""
+    src, tgt, _ = scan_pair
+    for cloud in (tgt, src[:1000], src[:33], src[:5]):
+        idx = rgc.knn_self(cloud, k)
+        oi, _ = orc.knn(cloud, cloud, k)
+        assert np.array_equal(idx, oi)
+    rng = np.random.default_rng(3)
+    g = np.stack(np.meshgrid(*[np.arange(11)] * 3, indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    L = np.ones((len(g), 4), np.float32)
+    L[:, :3] = g[rng.permutation(len(g))]          # integer lattice: every distance tied many times
+    oi, _ = orc.knn(L, L, k, brute=True)
+    assert np.array_equal(rgc.knn_self(L, k), oi)
+    C = np.ones((4000, 4), np.float32)
+    C[:, :3] = np.concatenate([rng.normal(0, 0.05, (2000, 3)), rng.normal(0, 30, (2000, 3))]).astype(np.float32)  # dense blob + sparse halo
+    oi, _ = orc.knn(C, C, k, brute=True)
+    assert np.array_equal(rgc.knn_self(C, k), oi)
+
+
 def test_knn_bitexact_cross_and_far(rgc, orc, scan_pair):
     src, tgt, _ = scan_pair
     idx, d2 = rgc.knn(tgt, src, 1)
