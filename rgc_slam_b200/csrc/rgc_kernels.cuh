@@ -318,10 +318,10 @@ __global__ void __launch_bounds__(kThreads, 8) k_knn(GridView g, const float4* _
 // Exactness is unchanged: a point is dropped only if its cell is outside every ball or its d2
 // exceeds the lane's current k-th distance; ties are resolved by (d2, original index) in the heap.
 constexpr int KT_WARPS = 4;
-constexpr int KT_CAND = 224;    // candidate buffer entries per warp
+constexpr int KT_CAND = 160;    // candidate buffer entries per warp
 constexpr int KT_STACK = 64;    // DFS stack entries per warp
 constexpr int KT_SEEDS = 64;    // Morton-adjacent seed points per warp
-constexpr int KT_PEND = 28;     // pending slots per lane
+constexpr int KT_PEND = 12;     // pending slots per lane
 constexpr int KT_LEAF = 32;     // cells with <= this many points are gathered whole
 
 struct TileNode {
