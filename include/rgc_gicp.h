@@ -79,6 +79,11 @@ const char* rgc_last_error(const rgc_ctx* ctx);
 int rgc_ctx_synchronize(rgc_ctx* ctx);
 /* raw cudaStream_t of the context (so callers can record CUDA events on the launching stream) */
 void* rgc_ctx_stream(rgc_ctx* ctx);
+/* profiling: when on, CUDA events bracket the kernels of every linearize / compute_error and
+ * rgc_ctx_last_kernel_ms returns the device time of the last [k_correspond, k_linearize,
+ * k_compute_error] launch in ms (live roofline numbers for bench.py).  Off by default. */
+int rgc_ctx_set_profiling(rgc_ctx* ctx, int on);
+int rgc_ctx_last_kernel_ms(const rgc_ctx* ctx, float* ms3);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t rgc_ctx_launch_count(const rgc_ctx* ctx);
 

@@ -58,6 +58,8 @@ def lib():
         L.rgc_ctx_synchronize.argtypes = [vp]
         L.rgc_ctx_stream.argtypes = [vp]
         L.rgc_ctx_stream.restype = vp
+        L.rgc_ctx_set_profiling.argtypes = [vp, C.c_int]
+        L.rgc_ctx_last_kernel_ms.argtypes = [vp, vp]
         L.rgc_ctx_launch_count.argtypes = [vp]
         L.rgc_ctx_launch_count.restype = u64
         L.rgc_reg_create.argtypes = [vp, C.POINTER(vp)]
@@ -92,6 +94,7 @@ EXPORTED_SYMBOLS = [
     "rgc_reg_set_source_covs", "rgc_reg_set_target_covs", "rgc_reg_get_source_covs", "rgc_reg_get_target_covs",
     "rgc_reg_align", "rgc_reg_linearize", "rgc_reg_compute_error", "rgc_reg_get_correspondences", "rgc_reg_fitness",
     "rgc_reg_get_final_transformation", "rgc_knn", "rgc_reg_stage_ms", "rgc_knn_self", "rgc_reg_set_owner_slab", "rgc_reg_set_allreduce",
+    "rgc_ctx_set_profiling", "rgc_ctx_last_kernel_ms",
 ]
 
 
@@ -120,6 +123,14 @@ class Context:
 
     def synchronize(self):
         self.check(lib().rgc_ctx_synchronize(self._h))
+
+    def set_profiling(self, on: bool):
+        self.check(lib().rgc_ctx_set_profiling(self._h, int(on)))
+
+    def last_kernel_ms(self):
+        ms = np.zeros(3, np.float32)
+        lib().rgc_ctx_last_kernel_ms(self._h, ms.ctypes.data)
+        return dict(zip(("k_correspond", "k_linearize", "k_compute_error"), ms.tolist()))
 
     def close(self):
         if self._h:

@@ -26,6 +26,9 @@ struct rgc_ctx {
   uint32_t* h_counts = nullptr;  // pinned: kMaxLevels
   unsigned int* d_ticket = nullptr;
   cudaEvent_t ev[8];
+  cudaEvent_t evk[4];       // per-kernel timing of the last linearize / compute_error (profiling only)
+  bool profile = false;     // rgc_ctx_set_profiling
+  float last_kernel_ms[3] = {0, 0, 0};  // k_correspond, k_linearize, k_compute_error
 
   void* get(size_t bytes) {
     size_t cls = 4096;

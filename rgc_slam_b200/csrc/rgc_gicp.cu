@@ -310,10 +310,19 @@ static int reg_linearize(rgc_reg* r, const double* T, double* err, double* H, do
   const float thr2 = thr * thr;  // float product, +inf for the FLT_MAX default (fast_gicp_impl.hpp:136)
   const int want = (H && b) ? 1 : 0;
   const int spread = query_spread(r->src.n);
-  k_linearize<<<div_up(r->src.n * spread, kThreads), kThreads, 0, c->stream>>>(r->tgt.view, r->src.sorted, r->src.cov, r->tgt.cov, r->src.n, spread, Tf, Td, thr2, want, r->slab,
-                                                                     r->corr, r->sqd, r->maha, r->partials, c->d_ticket, reg_result_ptr(r));
+  if (c->profile) CK(c, cudaEventRecord(c->evk[0], c->stream));
+  k_correspond<<<div_up(r->src.n * spread, kThreads), kThreads, 0, c->stream>>>(r->tgt.view, r->src.sorted, r->src.n, spread, Tf, thr2, r->slab, r->corr, r->sqd);
   CKL(c);
+  if (c->profile) CK(c, cudaEventRecord(c->evk[1], c->stream));
+  k_linearize<<<div_up(r->src.n, kThreads), kThreads, 0, c->stream>>>(r->tgt.sorted, r->src.sorted, r->src.cov, r->tgt.cov, r->src.n, Td, want, r->corr, r->maha,
+                                                                     r->partials, c->d_ticket, reg_result_ptr(r));
+  CKL(c);
+  if (c->profile) CK(c, cudaEventRecord(c->evk[2], c->stream));
   TRY(reg_finish_reduce(r, kLinN));
+  if (c->profile) {
+    cudaEventElapsedTime(&c->last_kernel_ms[0], c->evk[0], c->evk[1]);
+    cudaEventElapsedTime(&c->last_kernel_ms[1], c->evk[1], c->evk[2]);
+  }
   r->n_linearize++;
   r->have_corr = true;
   const double* res = c->h_result;
@@ -338,10 +347,13 @@ static int reg_compute_error(rgc_reg* r, const double* T, double* err) {
   Rt Td;
   RtF Tf;
   to_rt(T, Td, Tf);
+  if (c->profile) CK(c, cudaEventRecord(c->evk[0], c->stream));
   k_compute_error<<<div_up(r->src.n, kThreads), kThreads, 0, c->stream>>>(r->tgt.sorted, r->src.sorted, r->src.n, Td, r->corr, r->maha, r->partials,
                                                                          c->d_ticket, reg_result_ptr(r));
   CKL(c);
+  if (c->profile) CK(c, cudaEventRecord(c->evk[1], c->stream));
   TRY(reg_finish_reduce(r, 1));
+  if (c->profile) cudaEventElapsedTime(&c->last_kernel_ms[2], c->evk[0], c->evk[1]);
   r->n_compute_error++;
   *err = c->h_result[0];
   return RGC_OK;
@@ -434,6 +446,8 @@ int rgc_ctx_create(int device, rgc_ctx** out) {
             cudaHostAlloc((void**)&c->h_counts, sizeof(uint32_t) * kMaxLevels, cudaHostAllocDefault) == cudaSuccess &&
             cudaMalloc((void**)&c->d_ticket, 64) == cudaSuccess && cudaMemset(c->d_ticket, 0, 64) == cudaSuccess;
   for (int i = 0; ok && i < 8; i++) ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
+  for (int i = 0; ok && i < 4; i++) ok = cudaEventCreate(&c->evk[i]) == cudaSuccess;
+  c->profile = std::getenv("RGC_PROFILE") != nullptr;
   if (!ok) {
     std::fprintf(stderr, "rgc_ctx_create: %s\n", cudaGetErrorString(cudaGetLastError()));
     delete c;
@@ -453,6 +467,7 @@ int rgc_ctx_destroy(rgc_ctx* c) {
   cudaFreeHost(c->h_counts);
   cudaFree(c->d_ticket);
   for (int i = 0; i < 8; i++) cudaEventDestroy(c->ev[i]);
+  for (int i = 0; i < 4; i++) cudaEventDestroy(c->evk[i]);
   cudaStreamDestroy(c->stream);
   delete c;
   return RGC_OK;
@@ -464,6 +479,16 @@ int rgc_ctx_synchronize(rgc_ctx* c) {
   return RGC_OK;
 }
 void* rgc_ctx_stream(rgc_ctx* c) { return (void*)c->stream; }
+int rgc_ctx_set_profiling(rgc_ctx* c, int on) {
+  if (!c) return RGC_ERR_INVALID;
+  c->profile = on != 0;
+  return RGC_OK;
+}
+int rgc_ctx_last_kernel_ms(const rgc_ctx* c, float* ms3) {
+  if (!c || !ms3) return RGC_ERR_INVALID;
+  for (int i = 0; i < 3; i++) ms3[i] = c->last_kernel_ms[i];
+  return RGC_OK;
+}
 uint64_t rgc_ctx_launch_count(const rgc_ctx* c) { return c->launches; }
 
 void rgc_params_default(rgc_params* p) {

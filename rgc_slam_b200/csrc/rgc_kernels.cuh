@@ -570,43 +570,51 @@ __device__ __forceinline__ bool slab_owns(const Slab& s, float qx, float qy, flo
 
 constexpr int kLinN = kAccN + 1;  // + inlier count
 
-// fused update_correspondences + linearize (fast_gicp_impl.hpp:115-211).  One thread per source
-// point (Morton order).  Stores the correspondence (sorted target position), its d2 and M for
-// the compute_error calls that follow.
-__global__ void __launch_bounds__(kThreads, 4) k_linearize(GridView tgt, const float4* __restrict__ src, const double* __restrict__ src_cov,
-                                                        const double* __restrict__ tgt_cov, int n_src, int spread, RtF Tf, Rt Td, float thr2, int want_hb, Slab slab,
-                                                        int* __restrict__ corr, float* __restrict__ sqd, double* __restrict__ maha,
-                                                        double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ result) {
+// update_correspondences, search part (fast_gicp_impl.hpp:115-137): float transform of every source
+// point, exact 1-NN in the target (pruned at thr2), thresholded.  SM/latency-bound tree walk; small
+// clouds use sparse warps.  Stores the sorted target position (or -1) and d2.
+__global__ void __launch_bounds__(kThreads, 8) k_correspond(GridView tgt, const float4* __restrict__ src, int n_src, int spread, RtF Tf, float thr2, Slab slab,
+                                                            int* __restrict__ corr, float* __restrict__ sqd) {
   const int gt = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = gt / spread;
-  int pos = -1;
-  float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-  if ((gt & (spread - 1)) == 0 && i < n_src) {
-    p = __ldg(&src[i]);
-    float qx, qy, qz;
-    transform_f(Tf.m, p.x, p.y, p.z, qx, qy, qz);
-    Best1 top;
-    top.reset(1, thr2);
-    if (slab_owns(slab, qx, qy, qz)) knn_search(tgt, qx, qy, qz, 1, thr2, -1, top);
-    pos = (top.id0 >= 0 && top.d0 < thr2) ? top.id0 : -1;
-    corr[i] = pos;
-    sqd[i] = top.d0;
-  }
-  // accumulators are declared only after the search so they are not live across it
+  if ((gt & (spread - 1)) != 0 || i >= n_src) return;
+  const float4 p = __ldg(&src[i]);
+  float qx, qy, qz;
+  transform_f(Tf.m, p.x, p.y, p.z, qx, qy, qz);
+  Best1 top;
+  top.reset(1, thr2);
+  if (slab_owns(slab, qx, qy, qz)) knn_search(tgt, qx, qy, qz, 1, thr2, -1, top);
+  corr[i] = (top.id0 >= 0 && top.d0 < thr2) ? top.id0 : -1;
+  sqd[i] = top.d0;
+}
+
+// Mahalanobis part of update_correspondences + linearize (fast_gicp_impl.hpp:139-211), fused:
+// per correspondence M = (C_B + R C_A R^T)^-1 (stored for compute_error), e^T M e, the 21 unique
+// entries of H = J^T M J and b = J^T M e, reduced deterministically.  Streams p, C_A, corr; gathers
+// q, C_B; writes M: 184 algorithmic bytes per source point -> HBM-bound once the batch exceeds L2.
+__global__ void __launch_bounds__(kThreads, 4) k_linearize(const float4* __restrict__ tgt_pts, const float4* __restrict__ src, const double* __restrict__ src_cov,
+                                                           const double* __restrict__ tgt_cov, int n_src, Rt Td, int want_hb, const int* __restrict__ corr,
+                                                           double* __restrict__ maha, double* __restrict__ partials, unsigned int* __restrict__ ticket,
+                                                           double* __restrict__ result) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double acc[kLinN];
 #pragma unroll
   for (int j = 0; j < kLinN; j++) acc[j] = 0.0;
-  if (pos >= 0) {
-    const F4 q = load_pt(tgt.pts + pos);
-    const Sym3 CA = load_sym3(src_cov, i);
-    const Sym3 CB = load_sym3(tgt_cov, pos);
-    const Sym3 M = gicp_mahalanobis(Td, CA, CB);
-    store_sym3(maha, i, M);
-    if (want_hb)
-      gicp_point_terms(Td, M, p.x, p.y, p.z, q.x, q.y, q.z, acc);
-    else
-      acc[0] = gicp_error_term(Td, M, p.x, p.y, p.z, q.x, q.y, q.z);
-    acc[kAccN] = 1.0;
+  if (i < n_src) {
+    const int pos = __ldg(&corr[i]);
+    if (pos >= 0) {
+      const float4 p = __ldg(&src[i]);
+      const float4 q = __ldg(&tgt_pts[pos]);
+      const Sym3 CA = load_sym3(src_cov, i);
+      const Sym3 CB = load_sym3(tgt_cov, pos);
+      const Sym3 M = gicp_mahalanobis(Td, CA, CB);
+      store_sym3(maha, i, M);
+      if (want_hb)
+        gicp_point_terms(Td, M, p.x, p.y, p.z, q.x, q.y, q.z, acc);
+      else
+        acc[0] = gicp_error_term(Td, M, p.x, p.y, p.z, q.x, q.y, q.z);
+      acc[kAccN] = 1.0;
+    }
   }
   grid_reduce<kLinN>(acc, partials, ticket, result);
 }

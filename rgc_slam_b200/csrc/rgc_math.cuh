@@ -15,6 +15,33 @@ struct Sym3 {
   double xx, xy, xz, yy, yz, zz;
 };
 
+// 1/x and 1/sqrt(x) to ~1 ulp: hardware approximation (MUFU) + two Newton steps.  The IEEE-rounded
+// double division / sqrt sequences cost ~30 instructions each and dominated the covariance kernel
+// (9+ Jacobi rotations per point); results differ from IEEE by <= 1 ulp, far inside every tolerance.
+RGC_HD double fast_rcp(double a) {
+#if defined(__CUDA_ARCH__)
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  y = fma(y, fma(-a, y, 1.0), y);
+  y = fma(y, fma(-a, y, 1.0), y);
+  return y;
+#else
+  return 1.0 / a;
+#endif
+}
+RGC_HD double fast_rsqrt(double a) {
+#if defined(__CUDA_ARCH__)
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  const double h = 0.5 * a;
+  y = y * fma(-h * y, y, 1.5);
+  y = y * fma(-h * y, y, 1.5);
+  return y;
+#else
+  return 1.0 / sqrt(a);
+#endif
+}
+
 // Cyclic Jacobi eigen-decomposition of a symmetric 3x3 (fp64).  On return A ~ V diag(w) V^T,
 // V column-major-by-index: V[r][c] = component r of eigenvector c.  Unsorted.
 // The reference uses Eigen::JacobiSVD on the same PSD matrix (fast_gicp_impl.hpp:273); for a
@@ -27,16 +54,18 @@ RGC_HD void eig_sym3(const Sym3& A, double w[3], double V[3][3]) {
   for (int sweep = 0; sweep < 12; sweep++) {
     double off = fabs(a[0][1]) + fabs(a[0][2]) + fabs(a[1][2]);
     double diag = fabs(a[0][0]) + fabs(a[1][1]) + fabs(a[2][2]);
-    if (off <= 1e-18 * diag || off < 1e-300) break;
+    if (off <= 1e-17 * diag || off < 1e-300) break;
 #pragma unroll
     for (int pq = 0; pq < 3; pq++) {
       const int p = (pq == 2) ? 1 : 0;
       const int q = (pq == 0) ? 1 : 2;
       double apq = a[p][q];
       if (fabs(apq) < 1e-300) continue;
-      double tau = (a[q][q] - a[p][p]) / (2.0 * apq);
-      double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-      double c = 1.0 / sqrt(1.0 + t * t), s = t * c;
+      // rotation angle: tau = cot(2 theta), t = tan(theta) (smaller root), c = cos, s = sin
+      const double tau = (a[q][q] - a[p][p]) * fast_rcp(2.0 * apq);
+      const double w2 = 1.0 + tau * tau;
+      const double t = (tau >= 0.0 ? 1.0 : -1.0) * fast_rcp(fabs(tau) + w2 * fast_rsqrt(w2));
+      const double c = fast_rsqrt(1.0 + t * t), s = t * c;
       // A <- J^T A J with J = [[c, s], [-s, c]] on (p,q)
       a[p][p] -= t * apq;
       a[q][q] += t * apq;
@@ -219,21 +248,19 @@ RGC_HD void gicp_point_terms(const Rt& T, const Sym3& M, float px, float py, flo
 // the oracle's handling of k > N), divided by k.  fast_gicp_impl.hpp:256-262.
 template <class GetPt>
 RGC_HD Sym3 covariance_from_points(int found, int k, GetPt get) {
-  double mx = 0.0, my = 0.0, mz = 0.0;
-  for (int j = 0; j < found; j++) {
-    F4 p = get(j);
-    mx += (double)p.x;
-    my += (double)p.y;
-    mz += (double)p.z;
-  }
-  const double ik = 1.0 / (double)k;
-  mx *= ik;
-  my *= ik;
-  mz *= ik;
+  // one pass: moments of (p_j - p_0) in fp64 (p_0 = the query itself, so the shifted data is as
+  // small as the neighbourhood and E[dd^T] - E[d]E[d]^T loses nothing), then re-centre.
+  if (found <= 0) return Sym3{0, 0, 0, 0, 0, 0};
+  const F4 p0 = get(0);
+  const double ox = (double)p0.x, oy = (double)p0.y, oz = (double)p0.z;
+  double sx = 0.0, sy = 0.0, sz = 0.0;
   Sym3 c = {0, 0, 0, 0, 0, 0};
-  for (int j = 0; j < found; j++) {
-    F4 p = get(j);
-    double dx = (double)p.x - mx, dy = (double)p.y - my, dz = (double)p.z - mz;
+  for (int j = 1; j < found; j++) {
+    const F4 p = get(j);
+    const double dx = (double)p.x - ox, dy = (double)p.y - oy, dz = (double)p.z - oz;
+    sx += dx;
+    sy += dy;
+    sz += dz;
     c.xx += dx * dx;
     c.xy += dx * dy;
     c.xz += dx * dz;
@@ -241,22 +268,29 @@ RGC_HD Sym3 covariance_from_points(int found, int k, GetPt get) {
     c.yz += dy * dz;
     c.zz += dz * dz;
   }
-  const int missing = k - found;  // zero columns still get centred: each contributes mean*mean^T
+  // missing columns (k > N) are zero vectors in the reference's matrix, i.e. the point -p_0 in
+  // shifted coordinates; they are rare (tiny clouds) and handled exactly
+  const int missing = k - found;
   if (missing > 0) {
-    double m = (double)missing;
-    c.xx += m * mx * mx;
-    c.xy += m * mx * my;
-    c.xz += m * mx * mz;
-    c.yy += m * my * my;
-    c.yz += m * my * mz;
-    c.zz += m * mz * mz;
+    const double m = (double)missing;
+    sx -= m * ox;
+    sy -= m * oy;
+    sz -= m * oz;
+    c.xx += m * ox * ox;
+    c.xy += m * ox * oy;
+    c.xz += m * ox * oz;
+    c.yy += m * oy * oy;
+    c.yz += m * oy * oz;
+    c.zz += m * oz * oz;
   }
-  c.xx *= ik;
-  c.xy *= ik;
-  c.xz *= ik;
-  c.yy *= ik;
-  c.yz *= ik;
-  c.zz *= ik;
+  const double ik = 1.0 / (double)k;
+  const double mx = sx * ik, my = sy * ik, mz = sz * ik;
+  c.xx = c.xx * ik - mx * mx;
+  c.xy = c.xy * ik - mx * my;
+  c.xz = c.xz * ik - mx * mz;
+  c.yy = c.yy * ik - my * my;
+  c.yz = c.yz * ik - my * mz;
+  c.zz = c.zz * ik - mz * mz;
   return c;
 }
 
