@@ -314,7 +314,7 @@ static int reg_linearize(rgc_reg* r, const double* T, double* err, double* H, do
   k_correspond<<<div_up(r->src.n * spread, kThreads), kThreads, 0, c->stream>>>(r->tgt.view, r->src.sorted, r->src.n, spread, Tf, thr2, r->slab, r->corr, r->sqd);
   CKL(c);
   if (c->profile) CK(c, cudaEventRecord(c->evk[1], c->stream));
-  k_linearize<<<div_up(r->src.n, kThreads), kThreads, 0, c->stream>>>(r->tgt.sorted, r->src.sorted, r->src.cov, r->tgt.cov, r->src.n, Td, want, r->corr, r->maha,
+  k_linearize<<<reduce_grid(r->src.n), kThreads, 0, c->stream>>>(r->tgt.sorted, r->src.sorted, r->src.cov, r->tgt.cov, r->src.n, Td, want, r->corr, r->maha,
                                                                      r->partials, c->d_ticket, reg_result_ptr(r));
   CKL(c);
   if (c->profile) CK(c, cudaEventRecord(c->evk[2], c->stream));
@@ -348,7 +348,7 @@ static int reg_compute_error(rgc_reg* r, const double* T, double* err) {
   RtF Tf;
   to_rt(T, Td, Tf);
   if (c->profile) CK(c, cudaEventRecord(c->evk[0], c->stream));
-  k_compute_error<<<div_up(r->src.n, kThreads), kThreads, 0, c->stream>>>(r->tgt.sorted, r->src.sorted, r->src.n, Td, r->corr, r->maha, r->partials,
+  k_compute_error<<<reduce_grid(r->src.n), kThreads, 0, c->stream>>>(r->tgt.sorted, r->src.sorted, r->src.n, Td, r->corr, r->maha, r->partials,
                                                                          c->d_ticket, reg_result_ptr(r));
   CKL(c);
   if (c->profile) CK(c, cudaEventRecord(c->evk[1], c->stream));

@@ -543,14 +543,32 @@ __device__ __forceinline__ void grid_reduce(double* v, double* __restrict__ part
   __syncthreads();
   if (is_last) {
     __threadfence();
+    // final pass: value j is summed by the kThreads/32 lanes (j, group g) over blocks b = g, g+G, ...
+    // in ascending order, then the G group sums are added in group order: a fixed order for a
+    // given grid size, whichever block happens to run last.
+    constexpr int G = kThreads / 32;
+    const int j = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    double s = 0.0;
+    if (j < NV)
+      for (unsigned b = grp; b < gridDim.x; b += G) s += __ldcg(&partials[(size_t)b * NV + j]);
+    if (j < NV) sm[grp][j] = s;
+    __syncthreads();
     if (threadIdx.x < NV) {
-      double s = 0.0;
-      for (unsigned b = 0; b < gridDim.x; b++) s += __ldcg(&partials[(size_t)b * NV + threadIdx.x]);
-      result[threadIdx.x] = s;
+      double tot = sm[0][threadIdx.x];
+#pragma unroll
+      for (int w = 1; w < G; w++) tot += sm[w][threadIdx.x];
+      result[threadIdx.x] = tot;
     }
     if (threadIdx.x == 0) *ticket = 0;
     __threadfence_system();
   }
+}
+
+// grid size of the reduction kernels: enough blocks to fill the machine, few enough that the
+// final pass over the per-block partials stays short (persistent grid-stride threads)
+__host__ __device__ inline int reduce_grid(int n) {
+  const int blocks = (n + kThreads - 1) / kThreads;
+  return blocks < 148 * 8 ? blocks : 148 * 8;
 }
 
 struct RtF {
@@ -596,11 +614,10 @@ __global__ void __launch_bounds__(kThreads, 4) k_linearize(const float4* __restr
                                                            const double* __restrict__ tgt_cov, int n_src, Rt Td, int want_hb, const int* __restrict__ corr,
                                                            double* __restrict__ maha, double* __restrict__ partials, unsigned int* __restrict__ ticket,
                                                            double* __restrict__ result) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double acc[kLinN];
 #pragma unroll
   for (int j = 0; j < kLinN; j++) acc[j] = 0.0;
-  if (i < n_src) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_src; i += gridDim.x * blockDim.x) {
     const int pos = __ldg(&corr[i]);
     if (pos >= 0) {
       const float4 p = __ldg(&src[i]);
@@ -612,8 +629,8 @@ __global__ void __launch_bounds__(kThreads, 4) k_linearize(const float4* __restr
       if (want_hb)
         gicp_point_terms(Td, M, p.x, p.y, p.z, q.x, q.y, q.z, acc);
       else
-        acc[0] = gicp_error_term(Td, M, p.x, p.y, p.z, q.x, q.y, q.z);
-      acc[kAccN] = 1.0;
+        acc[0] += gicp_error_term(Td, M, p.x, p.y, p.z, q.x, q.y, q.z);
+      acc[kAccN] += 1.0;
     }
   }
   grid_reduce<kLinN>(acc, partials, ticket, result);
@@ -624,14 +641,13 @@ __global__ void __launch_bounds__(kThreads) k_compute_error(const float4* __rest
                                                             const int* __restrict__ corr, const double* __restrict__ maha,
                                                             double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ result) {
   double acc[1] = {0.0};
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_src) {
-    const int pos = corr[i];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_src; i += gridDim.x * blockDim.x) {
+    const int pos = __ldg(&corr[i]);
     if (pos >= 0) {
       const float4 p = __ldg(&src[i]);
       const float4 q = __ldg(&tgt_pts[pos]);
       const Sym3 M = load_sym3(maha, i);
-      acc[0] = gicp_error_term(Td, M, p.x, p.y, p.z, q.x, q.y, q.z);
+      acc[0] += gicp_error_term(Td, M, p.x, p.y, p.z, q.x, q.y, q.z);
     }
   }
   grid_reduce<1>(acc, partials, ticket, result);
