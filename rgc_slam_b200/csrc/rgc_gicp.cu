@@ -44,6 +44,7 @@ struct Cloud {
   uint64_t key = 0;
   bool valid = false;
   float4* sorted = nullptr;
+  int* inv = nullptr;  // original index -> sorted position
   GridSlot* tables = nullptr;
   GridView view{};
   double* cov = nullptr;  // 6 doubles per sorted point
@@ -53,6 +54,7 @@ struct Cloud {
 
 static void cloud_release(rgc_ctx* c, Cloud& cl) {
   c->put(cl.sorted);
+  c->put(cl.inv);
   c->put(cl.tables);
   c->put(cl.cov);
   cl = Cloud();
@@ -87,7 +89,8 @@ static int cloud_build(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, s
   uint32_t* hist = (uint32_t*)c->get(4 * 256 * (size_t)nblk);
   uint32_t* d_counts = (uint32_t*)c->get(4 * kMaxLevels);
   cl.sorted = (float4*)c->get(sizeof(float4) * n_sz);
-  if (!orig || !d_bbox || !keys_a || !keys_b || !vals_a || !vals_b || !hist || !d_counts || !cl.sorted) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (build)");
+  cl.inv = (int*)c->get(sizeof(int) * n_sz);
+  if (!cl.inv || !orig || !d_bbox || !keys_a || !keys_b || !vals_a || !vals_b || !hist || !d_counts || !cl.sorted) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (build)");
 
   tr.lap("alloc");
   k_ingest<<<kBboxBlocks, 256, 0, st>>>(d_raw, stride, n, orig, d_bbox);
@@ -127,7 +130,7 @@ static int cloud_build(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, s
     std::swap(kin, kout);
     std::swap(vin, vout);
   }
-  k_gather_sorted<<<div_up(n, 256), 256, 0, st>>>(orig, vin, n, cl.sorted);
+  k_gather_sorted<<<div_up(n, 256), 256, 0, st>>>(orig, vin, n, cl.sorted, cl.inv);
   CKL(c);
 
   // ---- level tables ----
@@ -169,6 +172,7 @@ static int cloud_build(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, s
   k_child_masks<<<div_up(n, 256), 256, 0, st>>>(kin, n, ts);
   CKL(c);
   v.pts = reinterpret_cast<const F4*>(cl.sorted);
+  v.inv = cl.inv;
 
   c->put(staging);
   c->put(orig);

@@ -43,6 +43,7 @@ struct GridSlot {  // 16 bytes, loaded as one uint4
 };
 
 struct GridView {
+  const int* inv;  // original index -> sorted position
   const F4* pts;   // sorted points, w = original index bits
   int n;
   float ox, oy, oz;   // origin
@@ -306,6 +307,65 @@ struct HeapK {
       d[(size - 1) * stride] = d[0];
       id[(size - 1) * stride] = id[0];
       sift_down_from_root(dl, il, f2i_bits(load_pt(pts + il).w), size - 1, pts);
+    }
+  }
+};
+
+// Max-heap of packed 64-bit keys  (float bits of d2) << 32 | original index.  d2 >= +0, so the
+// unsigned integer order of the key IS the lexicographic (d2, original index) order: one integer
+// compare per step, no tie branches, one shared-memory word per entry.  Used by the tile kernel.
+RGC_HD unsigned long long pack_key(float d2, int orig) { return ((unsigned long long)(unsigned)f2i_bits(d2) << 32) | (unsigned)orig; }
+RGC_HD float key_d2(unsigned long long key) { return i2f_bits((int)(unsigned)(key >> 32)); }
+struct HeapK64 {
+  unsigned long long* h;
+  int stride, k, cnt;
+  RGC_HD void init(unsigned long long* h_, int stride_, int k_) {
+    h = h_;
+    stride = stride_;
+    k = k_;
+    cnt = 0;
+  }
+  RGC_HD bool full() const { return cnt == k; }
+  RGC_HD void sift_down(unsigned long long key, int size) {
+    int j = 0;
+    for (;;) {
+      int c = 2 * j + 1;
+      if (c >= size) break;
+      unsigned long long kc = h[c * stride];
+      if (c + 1 < size) {
+        const unsigned long long k2 = h[(c + 1) * stride];
+        if (k2 > kc) {
+          kc = k2;
+          c++;
+        }
+      }
+      if (kc <= key) break;
+      h[j * stride] = kc;
+      j = c;
+    }
+    h[j * stride] = key;
+  }
+  RGC_HD void insert(unsigned long long key) {
+    if (cnt < k) {
+      int j = cnt++;
+      while (j > 0) {
+        const int p = (j - 1) >> 1;
+        const unsigned long long kp = h[p * stride];
+        if (kp >= key) break;
+        h[j * stride] = kp;
+        j = p;
+      }
+      h[j * stride] = key;
+      return;
+    }
+    if (key >= h[0]) return;
+    sift_down(key, k);
+  }
+  RGC_HD void sort_ascending() {
+    for (int size = cnt; size > 1; size--) {
+      const unsigned long long last = h[(size - 1) * stride];
+      h[(size - 1) * stride] = h[0];
+      sift_down(last, size - 1);
     }
   }
 };

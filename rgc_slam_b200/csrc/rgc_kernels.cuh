@@ -184,13 +184,15 @@ __global__ void __launch_bounds__(256) k_rs_scatter(const uint64_t* __restrict__
   }
 }
 
-__global__ void __launch_bounds__(256) k_gather_sorted(const float4* __restrict__ pts, const uint32_t* __restrict__ vals, int n, float4* __restrict__ sorted) {
+__global__ void __launch_bounds__(256) k_gather_sorted(const float4* __restrict__ pts, const uint32_t* __restrict__ vals, int n, float4* __restrict__ sorted,
+                                                       int* __restrict__ inv) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t o = vals[i];
   float4 p = pts[o];
   p.w = __int_as_float((int)o);
   sorted[i] = p;
+  inv[o] = i;
 }
 
 // cells per level: point i opens a new cell at every level l with 3l <= highest differing bit
@@ -343,59 +345,58 @@ __global__ void __launch_bounds__(KT_WARPS * 32) k_knn_tile(GridView g, int n, i
   extern __shared__ __align__(16) unsigned char tile_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cap = k + KT_PEND;
-  // per-warp carve-up
+  // per-warp carve-up: candidate buffer | DFS stack | [cap][32] packed heap / pending keys
   const size_t per_warp = sizeof(float4) * KT_CAND + sizeof(TileNode) * KT_STACK + (size_t)cap * 32 * 8;
   unsigned char* base = tile_smem + (size_t)warp * per_warp;
   float4* cand = reinterpret_cast<float4*>(base);
   TileNode* stack = reinterpret_cast<TileNode*>(base + sizeof(float4) * KT_CAND);
-  float* hd = reinterpret_cast<float*>(base + sizeof(float4) * KT_CAND + sizeof(TileNode) * KT_STACK);
-  int* hi = reinterpret_cast<int*>(hd + (size_t)cap * 32);
+  unsigned long long* hk = reinterpret_cast<unsigned long long*>(base + sizeof(float4) * KT_CAND + sizeof(TileNode) * KT_STACK);
 
   const int first = (blockIdx.x * KT_WARPS + warp) * 32;
   if (first >= n) return;
   const int t = min(first + lane, n - 1);  // tail lanes shadow the last query (no output)
   const float4 q = reinterpret_cast<const float4*>(g.pts)[t];
-  const F4* pts = g.pts;
+  const float4* pts4 = reinterpret_cast<const float4*>(g.pts);
 
-  HeapK heap;
-  heap.init(hd + lane, hi + lane, 32);
-  heap.reset(k, INFINITY);
+  HeapK64 heap;
+  heap.init(hk + lane, 32, k);
   int npend = 0;
 
   // ---- seeds: Morton neighbours of the tile, folded in lockstep
   const int ns = min(KT_SEEDS, n);
   const int s0 = max(0, min(first - (KT_SEEDS - 32) / 2, n - ns));
-  for (int j = lane; j < ns; j += 32) {
-    float4 c = reinterpret_cast<const float4*>(pts)[s0 + j];
-    c.w = __int_as_float(s0 + j);
-    cand[j] = c;
-  }
+  for (int j = lane; j < ns; j += 32) cand[j] = pts4[s0 + j];
   __syncwarp();
   for (int j = 0; j < ns; j++) {
     const float4 c = cand[j];
-    heap.insert_lazy(dist2_ref(q.x, q.y, q.z, c.x, c.y, c.z), __float_as_int(c.w), pts);
+    heap.insert(pack_key(dist2_ref(q.x, q.y, q.z, c.x, c.y, c.z), __float_as_int(c.w)));
   }
   __syncwarp();
 
   auto fold = [&]() {
     const int mx = __reduce_max_sync(0xffffffffu, npend);
     for (int e = 0; e < mx; e++)
-      if (e < npend) heap.insert_lazy(hd[(k + e) * 32 + lane], hi[(k + e) * 32 + lane], pts);
+      if (e < npend) heap.insert(hk[(k + e) * 32 + lane]);
     npend = 0;
   };
-  auto bound = [&]() { return heap.cnt == k ? heap.d[0] : INFINITY; };
+  // current k-th best as a key (inclusive bound for appends) and as a distance (for box tests)
+  auto bound_key = [&]() { return heap.cnt == k ? hk[lane] : ~0ull; };
+  auto bound = [&]() { return heap.cnt == k ? key_d2(hk[lane]) : INFINITY; };
   int ncand = 0;
   auto consume = [&]() {
     __syncwarp();
+    unsigned long long bk = bound_key();
     for (int j = 0; j < ncand; j++) {
       const float4 c = cand[j];
-      const float d2 = dist2_ref(q.x, q.y, q.z, c.x, c.y, c.z);
-      if (d2 <= bound()) {
-        hd[(k + npend) * 32 + lane] = d2;
-        hi[(k + npend) * 32 + lane] = __float_as_int(c.w);
+      const unsigned long long key = pack_key(dist2_ref(q.x, q.y, q.z, c.x, c.y, c.z), __float_as_int(c.w));
+      if (key < bk) {
+        hk[(k + npend) * 32 + lane] = key;
         npend++;
       }
-      if (__any_sync(0xffffffffu, npend == KT_PEND)) fold();
+      if (__any_sync(0xffffffffu, npend == KT_PEND)) {
+        fold();
+        bk = bound_key();
+      }
     }
     ncand = 0;
     __syncwarp();
@@ -426,61 +427,76 @@ __global__ void __launch_bounds__(KT_WARPS * 32) k_knn_tile(GridView g, int n, i
         if (ih < 0 || il >= ncell) rhi[a] = rlo[a] - 1;
       }
     }
-    for (int rz = rlo[2]; rz <= rhi[2]; rz++)
-      for (int ry = rlo[1]; ry <= rhi[1]; ry++)
-        for (int rx = rlo[0]; rx <= rhi[0]; rx++) {
-          if (!__any_sync(0xffffffffu, box_dist2(g, lb, rx, ry, rz, q.x, q.y, q.z) <= bound())) continue;
-          uint32_t s, e, m;
-          if (!grid_lookup(g, lb, rx, ry, rz, s, e, m)) continue;  // uniform across the warp
-          int sp = 0;
-          if (lane == 0) stack[0] = TileNode{(uint32_t)rx | ((uint32_t)lb << 24), (uint32_t)ry | (m << 24), (uint32_t)rz, s, e};
-          sp = 1;
-          __syncwarp();
-          while (sp > 0) {
-            const TileNode nd = stack[--sp];
-            __syncwarp();
-            const int l = (int)(nd.cx_lvl >> 24);
-            const int cx = (int)(nd.cx_lvl & 0xffffffu), cy = (int)(nd.cy_mask & 0xffffffu), cz = (int)nd.cz;
-            const uint32_t cm = nd.cy_mask >> 24;
-            if (!__any_sync(0xffffffffu, box_dist2(g, l, cx, cy, cz, q.x, q.y, q.z) <= bound())) continue;
-            if (l == 0 || nd.end - nd.start <= (uint32_t)KT_LEAF || sp + 8 > KT_STACK) {
-              // gather the cell's points (minus the seeds, already folded)
-              for (uint32_t p0 = nd.start; p0 < nd.end; p0 += 32) {
-                const uint32_t p = p0 + lane;
-                const bool take = p < nd.end && (uint32_t)((int)p - s0) >= (uint32_t)ns;
-                const uint32_t bal = __ballot_sync(0xffffffffu, take);
-                if (take) {
-                  float4 c = reinterpret_cast<const float4*>(pts)[p];
-                  c.w = __int_as_float((int)p);
-                  cand[ncand + __popc(bal & ((1u << lane) - 1u))] = c;
-                }
-                ncand += __popc(bal);
-                if (ncand > KT_CAND - 32) consume();
-              }
-              continue;
-            }
-            // expand: lane c < 8 resolves child c (mask bit -> hash lookup); the others wait
-            const uint64_t pkey = morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz) << 3;
-            uint32_t cs = 0, ce = 0, cmk = 0;
-            bool have = false;
-            if (lane < 8 && ((cm >> lane) & 1u)) have = grid_lookup_key(g, l - 1, pkey | (uint64_t)lane, cs, ce, cmk);
-            const uint32_t hv = __ballot_sync(0xffffffffu, have);
-            for (int c = 0; c < 8; c++) {
-              if (!((hv >> c) & 1u)) continue;
-              const int ccx = 2 * cx + (c & 1), ccy = 2 * cy + ((c >> 1) & 1), ccz = 2 * cz + ((c >> 2) & 1);
-              if (!__any_sync(0xffffffffu, box_dist2(g, l - 1, ccx, ccy, ccz, q.x, q.y, q.z) <= bound())) continue;
-              if (lane == c) stack[sp] = TileNode{(uint32_t)ccx | ((uint32_t)(l - 1) << 24), (uint32_t)ccy | (cmk << 24), (uint32_t)ccz, cs, ce};
-              sp++;
-            }
-            __syncwarp();
-          }
+    // root cells are resolved 32 at a time: lane r tests / looks up root r, hits are pushed
+    const int nx = rhi[0] - rlo[0] + 1, ny = rhi[1] - rlo[1] + 1, nz = rhi[2] - rlo[2] + 1;
+    const int nroots = (nx > 0 && ny > 0 && nz > 0) ? nx * ny * nz : 0;
+    int sp = 0;
+    for (int r0 = 0; r0 < nroots; r0 += 32) {
+      const int ri = r0 + lane;
+      uint32_t s = 0, e = 0, m = 0;
+      int rx = 0, ry = 0, rz = 0;
+      bool have = false;
+      if (ri < nroots) {
+        rx = rlo[0] + ri % nx;
+        ry = rlo[1] + (ri / nx) % ny;
+        rz = rlo[2] + ri / (nx * ny);
+        have = grid_lookup(g, lb, rx, ry, rz, s, e, m);
+      }
+      uint32_t hv = __ballot_sync(0xffffffffu, have);
+      while (hv) {
+        const int src_lane = __ffs(hv) - 1;
+        hv &= hv - 1;
+        // does any lane's ball touch this root?  (every lane tests its own query)
+        const int bx = __shfl_sync(0xffffffffu, rx, src_lane), by = __shfl_sync(0xffffffffu, ry, src_lane), bz = __shfl_sync(0xffffffffu, rz, src_lane);
+        if (!__any_sync(0xffffffffu, box_dist2(g, lb, bx, by, bz, q.x, q.y, q.z) <= bound())) continue;
+        if (sp < KT_STACK) {
+          if (lane == src_lane) stack[sp] = TileNode{(uint32_t)rx | ((uint32_t)lb << 24), (uint32_t)ry | (m << 24), (uint32_t)rz, s, e};
+          sp++;
         }
+      }
+      __syncwarp();
+      // ---- depth-first walk of everything pushed so far
+      while (sp > 0) {
+        const TileNode nd = stack[--sp];
+        __syncwarp();
+        const int l = (int)(nd.cx_lvl >> 24);
+        const int cx = (int)(nd.cx_lvl & 0xffffffu), cy = (int)(nd.cy_mask & 0xffffffu), cz = (int)nd.cz;
+        const uint32_t cm = nd.cy_mask >> 24;
+        if (!__any_sync(0xffffffffu, box_dist2(g, l, cx, cy, cz, q.x, q.y, q.z) <= bound())) continue;
+        if (l == 0 || nd.end - nd.start <= (uint32_t)KT_LEAF || sp + 8 > KT_STACK) {
+          // gather the cell's points (minus the seeds, already folded)
+          for (uint32_t p0 = nd.start; p0 < nd.end; p0 += 32) {
+            const uint32_t p = p0 + lane;
+            const bool take = p < nd.end && (uint32_t)((int)p - s0) >= (uint32_t)ns;
+            const uint32_t bal = __ballot_sync(0xffffffffu, take);
+            if (take) cand[ncand + __popc(bal & ((1u << lane) - 1u))] = pts4[p];
+            ncand += __popc(bal);
+            if (ncand > KT_CAND - 32) consume();
+          }
+          continue;
+        }
+        // expand: lane c < 8 resolves child c (mask bit -> hash lookup); the others wait
+        const uint64_t pkey = morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz) << 3;
+        uint32_t cs = 0, ce = 0, cmk = 0;
+        bool hc = false;
+        if (lane < 8 && ((cm >> lane) & 1u)) hc = grid_lookup_key(g, l - 1, pkey | (uint64_t)lane, cs, ce, cmk);
+        const uint32_t hvc = __ballot_sync(0xffffffffu, hc);
+        for (int c = 0; c < 8; c++) {
+          if (!((hvc >> c) & 1u)) continue;
+          const int ccx = 2 * cx + (c & 1), ccy = 2 * cy + ((c >> 1) & 1), ccz = 2 * cz + ((c >> 2) & 1);
+          if (!__any_sync(0xffffffffu, box_dist2(g, l - 1, ccx, ccy, ccz, q.x, q.y, q.z) <= bound())) continue;
+          if (lane == c) stack[sp] = TileNode{(uint32_t)ccx | ((uint32_t)(l - 1) << 24), (uint32_t)ccy | (cmk << 24), (uint32_t)ccz, cs, ce};
+          sp++;
+        }
+        __syncwarp();
+      }
+    }
     consume();
   }
   fold();
-  heap.sort_ascending(pts);
+  heap.sort_ascending();
   if (first + lane < n)
-    for (int j = 0; j < k; j++) out_idx[(size_t)j * n + t] = j < heap.cnt ? hi[j * 32 + lane] : -1;
+    for (int j = 0; j < k; j++) out_idx[(size_t)j * n + t] = j < heap.cnt ? __ldg(&g.inv[(unsigned)(hk[j * 32 + lane] & 0xffffffffull)]) : -1;
 }
 
 // covariance of sorted point t from its k neighbour positions (k-major), regularised; 6 doubles out

@@ -84,6 +84,7 @@ static void sim_build(const float* xyzw, int n, float cell, SimCloud& c) {
         t[hh].key |= (uint64_t)1 << (56 + (int)(ck & 7));
       }
   v.pts = c.sorted.data();
+  v.inv = nullptr;
 }
 
 static void sim_knn_t(const SimCloud& c, const float* q, int m, int k, int* idx, float* d2, long long* stats) {
