@@ -797,6 +797,30 @@ int rgc_knn_self(rgc_ctx* c, const void* points, size_t n, size_t stride, int k,
   return RGC_OK;
 }
 
+// debug aid (not part of the documented ABI): per-warp statistics of the tile kNN kernel on a cloud;
+// stats: ceil(n/32) x 4 int64 {cycles, nodes, candidates, fold steps}
+int rgc_debug_tile_stats(rgc_ctx* c, const void* points, size_t n, size_t stride, int k, long long* stats, float grid_cell) {
+  if (!c || !points || !stats) return RGC_ERR_INVALID;
+  CK(c, cudaSetDevice(c->device));
+  Cloud cl;
+  TRY(cloud_build(c, cl, points, n, stride, false, 0, grid_cell));
+  const size_t nw = (n + 31) / 32;
+  int* nbr = (int*)c->get(sizeof(int) * (size_t)k * n);
+  long long* d_stats = (long long*)c->get(sizeof(long long) * 4 * nw);
+  if (!nbr || !d_stats) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (debug)");
+  CK(c, cudaMemsetAsync(d_stats, 0, sizeof(long long) * 4 * nw, c->stream));
+  CK(c, cudaMemcpyToSymbolAsync(g_tile_dbg, &d_stats, sizeof(d_stats), 0, cudaMemcpyHostToDevice, c->stream));
+  TRY(launch_knn_self(c, cl.view, cl.n, k, nbr));
+  long long* null_ptr = nullptr;
+  CK(c, cudaMemcpyToSymbolAsync(g_tile_dbg, &null_ptr, sizeof(null_ptr), 0, cudaMemcpyHostToDevice, c->stream));
+  CK(c, cudaMemcpyAsync(stats, d_stats, sizeof(long long) * 4 * nw, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  c->put(nbr);
+  c->put(d_stats);
+  cloud_release(c, cl);
+  return RGC_OK;
+}
+
 int rgc_reg_set_owner_slab(rgc_reg* r, int axis, float lo, float hi) {
   if (!r || axis > 2) return RGC_ERR_INVALID;
   r->slab = Slab{axis, lo, hi};

@@ -341,9 +341,14 @@ __device__ __forceinline__ float warp_min(float v) {
   return v;
 }
 
+// debug: per-warp {cycles, nodes visited, candidates gathered, heap inserts} (rgc_debug_tile_stats)
+__device__ long long* g_tile_dbg = nullptr;
+
 __global__ void __launch_bounds__(KT_WARPS * 32) k_knn_tile(GridView g, int n, int k, int* __restrict__ out_idx) {
   extern __shared__ __align__(16) unsigned char tile_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long dbg_t0 = clock64();
+  int dbg_nodes = 0, dbg_cands = 0, dbg_ins = 0;
   const int cap = k + KT_PEND;
   // per-warp carve-up: candidate buffer | DFS stack | [cap][32] packed heap / pending keys
   const size_t per_warp = sizeof(float4) * KT_CAND + sizeof(TileNode) * KT_STACK + (size_t)cap * 32 * 8;
@@ -377,11 +382,32 @@ __global__ void __launch_bounds__(KT_WARPS * 32) k_knn_tile(GridView g, int n, i
     const int mx = __reduce_max_sync(0xffffffffu, npend);
     for (int e = 0; e < mx; e++)
       if (e < npend) heap.insert(hk[(k + e) * 32 + lane]);
+    dbg_ins += mx;
     npend = 0;
   };
+  // ---- geometric cap: the smallest cell around q that holds >= k points bounds the k-th distance
+  // by its diagonal.  Lanes whose Morton neighbours lie across a Z-curve jump get a loose bound from
+  // the seeds (per-warp stats showed 1 % of the tiles gathering 10-40x the usual candidates because
+  // of one such lane); this cap costs a handful of probes and removes that tail.
+  float cap2 = INFINITY;
+  {
+    const int fx = cell_coord(q.x, g.ox, g.inv_s0), fy = cell_coord(q.y, g.oy, g.inv_s0), fz = cell_coord(q.z, g.oz, g.inv_s0);
+    const float seed_b = heap.cnt == k ? key_d2(hk[lane]) : INFINITY;
+    for (int l = 0; l < g.nlevels; l++) {
+      const float edge = g.s0 * (float)(1 << l) + 2.f * g.margin;
+      const float diag2 = 3.f * edge * edge * 1.0001f;
+      if (diag2 >= seed_b) break;  // cannot improve on the seed bound any more
+      uint32_t s, e, m;
+      if (grid_lookup(g, l, fx >> l, fy >> l, fz >> l, s, e, m) && (int)(e - s) >= k) {
+        cap2 = diag2;
+        break;
+      }
+    }
+  }
+  const unsigned long long capk = pack_key(cap2, 0x7fffffff);
   // current k-th best as a key (inclusive bound for appends) and as a distance (for box tests)
   auto bound_key = [&]() { return heap.cnt == k ? hk[lane] : ~0ull; };
-  auto bound = [&]() { return heap.cnt == k ? key_d2(hk[lane]) : INFINITY; };
+  auto bound = [&]() { return fminf(heap.cnt == k ? key_d2(hk[lane]) : INFINITY, cap2); };
   int ncand = 0;
   auto consume = [&]() {
     __syncwarp();
@@ -389,7 +415,7 @@ __global__ void __launch_bounds__(KT_WARPS * 32) k_knn_tile(GridView g, int n, i
     for (int j = 0; j < ncand; j++) {
       const float4 c = cand[j];
       const unsigned long long key = pack_key(dist2_ref(q.x, q.y, q.z, c.x, c.y, c.z), __float_as_int(c.w));
-      if (key < bk) {
+      if (key < bk && key <= capk) {
         hk[(k + npend) * 32 + lane] = key;
         npend++;
       }
@@ -459,6 +485,7 @@ __global__ void __launch_bounds__(KT_WARPS * 32) k_knn_tile(GridView g, int n, i
       while (sp > 0) {
         const TileNode nd = stack[--sp];
         __syncwarp();
+        dbg_nodes++;
         const int l = (int)(nd.cx_lvl >> 24);
         const int cx = (int)(nd.cx_lvl & 0xffffffu), cy = (int)(nd.cy_mask & 0xffffffu), cz = (int)nd.cz;
         const uint32_t cm = nd.cy_mask >> 24;
@@ -471,6 +498,7 @@ __global__ void __launch_bounds__(KT_WARPS * 32) k_knn_tile(GridView g, int n, i
             const uint32_t bal = __ballot_sync(0xffffffffu, take);
             if (take) cand[ncand + __popc(bal & ((1u << lane) - 1u))] = pts4[p];
             ncand += __popc(bal);
+            dbg_cands += __popc(bal);
             if (ncand > KT_CAND - 32) consume();
           }
           continue;
@@ -497,6 +525,13 @@ __global__ void __launch_bounds__(KT_WARPS * 32) k_knn_tile(GridView g, int n, i
   heap.sort_ascending();
   if (first + lane < n)
     for (int j = 0; j < k; j++) out_idx[(size_t)j * n + t] = j < heap.cnt ? __ldg(&g.inv[(unsigned)(hk[j * 32 + lane] & 0xffffffffull)]) : -1;
+  if (g_tile_dbg && lane == 0) {
+    long long* o = g_tile_dbg + (size_t)(first / 32) * 4;
+    o[0] = clock64() - dbg_t0;
+    o[1] = dbg_nodes;
+    o[2] = dbg_cands;
+    o[3] = dbg_ins;
+  }
 }
 
 // covariance of sorted point t from its k neighbour positions (k-major), regularised; 6 doubles out
