@@ -86,7 +86,8 @@ static int cloud_build(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, s
   uint32_t* vals_a = (uint32_t*)c->get(4 * n_sz);
   uint32_t* vals_b = (uint32_t*)c->get(4 * n_sz);
   const int nblk = div_up(n, RS_TILE);
-  uint32_t* hist = (uint32_t*)c->get(4 * 256 * (size_t)nblk);
+  uint32_t* hist = (uint32_t*)c->get(4 * 256 * ((size_t)nblk + 1));
+  uint32_t* digit_total = hist ? hist + 256 * (size_t)nblk : nullptr;
   uint32_t* d_counts = (uint32_t*)c->get(4 * kMaxLevels);
   cl.sorted = (float4*)c->get(sizeof(float4) * n_sz);
   cl.inv = (int*)c->get(sizeof(int) * n_sz);
@@ -123,9 +124,9 @@ static int cloud_build(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, s
   for (int p = 0; p < passes; p++) {
     k_rs_hist<<<nblk, 256, 0, st>>>(kin, n, 8 * p, hist, nblk);
     CKL(c);
-    k_rs_scan<<<1, 1024, 0, st>>>(hist, 256 * nblk);
+    k_rs_scan<<<256, 256, 0, st>>>(hist, nblk, digit_total);
     CKL(c);
-    k_rs_scatter<<<nblk, 256, 0, st>>>(kin, vin, kout, vout, hist, n, 8 * p, nblk);
+    k_rs_scatter<<<nblk, 256, 0, st>>>(kin, vin, kout, vout, hist, digit_total, n, 8 * p, nblk);
     CKL(c);
     std::swap(kin, kout);
     std::swap(vin, vout);
@@ -167,7 +168,7 @@ static int cloud_build(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, s
     v.table[l] = ts.table[l];
     v.mask[l] = ts.mask[l];
   }
-  k_build_tables<<<div_up(n, 256), 256, 0, st>>>(kin, n, ts);
+  k_build_tables<<<dim3(div_up(n, 256), v.nlevels), 256, 0, st>>>(kin, n, ts);
   CKL(c);
   k_child_masks<<<div_up(n, 256), 256, 0, st>>>(kin, n, ts);
   CKL(c);

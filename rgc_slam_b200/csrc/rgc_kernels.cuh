@@ -102,43 +102,56 @@ __global__ void __launch_bounds__(256) k_rs_hist(const uint64_t* __restrict__ ke
   hist[threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];
 }
 
-// single-block exclusive scan over m = 256*nblk counters
-__global__ void __launch_bounds__(1024) k_rs_scan(uint32_t* __restrict__ hist, int m) {
-  __shared__ uint32_t warp_sums[32];
-  const int per = (m + 1023) / 1024;
-  const int lo = threadIdx.x * per, hi = min(lo + per, m);
-  uint32_t s = 0;
-  for (int i = lo; i < hi; i++) s += hist[i];
-  // block exclusive scan of s
-  uint32_t v = s;
+// one block per digit: exclusive scan of that digit's per-tile counts in place + the digit total.
+// (The first version scanned all 256*nblk counters in ONE block: 27 us per pass on a 500k cloud.)
+__global__ void __launch_bounds__(256) k_rs_scan(uint32_t* __restrict__ hist, int nblk, uint32_t* __restrict__ digit_total) {
+  __shared__ uint32_t warp_sums[8];
+  uint32_t* row = hist + (size_t)blockIdx.x * nblk;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int o = 1; o < 32; o <<= 1) {
-    uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
-    if (lane >= o) v += t;
-  }
-  if (lane == 31) warp_sums[warp] = v;
-  __syncthreads();
-  if (warp == 0) {
-    uint32_t w = warp_sums[lane];
+  uint32_t carry = 0;
+  for (int base = 0; base < nblk; base += 256) {
+    const int i = base + threadIdx.x;
+    const uint32_t c = i < nblk ? row[i] : 0u;
+    uint32_t v = c;
     for (int o = 1; o < 32; o <<= 1) {
-      uint32_t t = __shfl_up_sync(0xffffffffu, w, o);
-      if (lane >= o) w += t;
+      const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
     }
-    warp_sums[lane] = w;
+    if (lane == 31) warp_sums[warp] = v;
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+    for (int w = 0; w < 8; w++) {
+      const uint32_t s = warp_sums[w];
+      if (w < warp) before += s;
+      total += s;
+    }
+    if (i < nblk) row[i] = carry + before + v - c;
+    carry += total;
+    __syncthreads();
   }
-  __syncthreads();
-  uint32_t excl = v - s + (warp > 0 ? warp_sums[warp - 1] : 0u);
-  for (int i = lo; i < hi; i++) {
-    uint32_t c = hist[i];
-    hist[i] = excl;
-    excl += c;
-  }
+  if (threadIdx.x == 0) digit_total[blockIdx.x] = carry;
 }
 
 __global__ void __launch_bounds__(256) k_rs_scatter(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                                                     uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
-                                                    const uint32_t* __restrict__ offsets, int n, int shift, int nblk) {
+                                                    const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ digit_total, int n, int shift,
+                                                    int nblk) {
   __shared__ uint32_t cnt[8][256];
+  __shared__ uint32_t digit_base[256];
+  {  // exclusive prefix of the 256 digit totals (every block recomputes it: 256 values)
+    __shared__ uint32_t ws[8];
+    const uint32_t c = digit_total[threadIdx.x];
+    uint32_t v = c;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+      if ((threadIdx.x & 31) >= o) v += t;
+    }
+    if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = v;
+    __syncthreads();
+    uint32_t before = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); w++) before += ws[w];
+    digit_base[threadIdx.x] = before + v - c;
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int warp_base = blockIdx.x * RS_TILE + warp * (32 * RS_ITEMS);
   for (int i = threadIdx.x; i < 8 * 256; i += 256) (&cnt[0][0])[i] = 0;
@@ -158,7 +171,7 @@ __global__ void __launch_bounds__(256) k_rs_scatter(const uint64_t* __restrict__
   }
   __syncthreads();
   {  // per digit: running base over the 8 warps
-    uint32_t base = offsets[threadIdx.x * nblk + blockIdx.x];
+    uint32_t base = digit_base[threadIdx.x] + offsets[threadIdx.x * nblk + blockIdx.x];
 #pragma unroll
     for (int w = 0; w < 8; w++) {
       uint32_t c = cnt[w][threadIdx.x];
@@ -230,25 +243,25 @@ __device__ __forceinline__ GridSlot* slot_insert_or_find(GridSlot* tab, uint32_t
   }
 }
 
+// blockIdx.y = level: one (point, level) pair per thread, so no thread walks all the levels
+// serially (the 1-D version was bound by the CAS chain of the few threads that open a cell at
+// every level: 62 us whatever the cloud size).
 __global__ void __launch_bounds__(256) k_build_tables(const uint64_t* __restrict__ keys, int n, TableSet ts) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int l = blockIdx.y;
   if (i >= n) return;
   const uint64_t key = keys[i];
-  int top;
+  bool opens = true;  // does point i open a new cell at level l?
   uint64_t prev = 0;
-  if (i == 0)
-    top = ts.nlevels - 1;
-  else {
+  if (i > 0) {
     prev = keys[i - 1];
-    uint64_t x = key ^ prev;
-    top = x ? min((63 - __clzll((long long)x)) / 3, ts.nlevels - 1) : -1;
+    opens = (key >> (3 * l)) != (prev >> (3 * l));
   }
-  for (int l = 0; l <= top; l++) {
+  if (opens) {
     slot_insert_or_find(ts.table[l], ts.mask[l], key >> (3 * l))->start = (uint32_t)i;
     if (i > 0) slot_insert_or_find(ts.table[l], ts.mask[l], prev >> (3 * l))->end = (uint32_t)i;
   }
-  if (i == n - 1)
-    for (int l = 0; l < ts.nlevels; l++) slot_insert_or_find(ts.table[l], ts.mask[l], key >> (3 * l))->end = (uint32_t)n;
+  if (i == n - 1) slot_insert_or_find(ts.table[l], ts.mask[l], key >> (3 * l))->end = (uint32_t)n;
 }
 
 // second pass (tables complete): every cell sets its bit in its parent's occupied-children mask
