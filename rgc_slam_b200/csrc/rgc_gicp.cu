@@ -316,7 +316,11 @@ static int reg_linearize(rgc_reg* r, const double* T, double* err, double* H, do
   const int want = (H && b) ? 1 : 0;
   const int spread = query_spread(r->src.n);
   if (c->profile) CK(c, cudaEventRecord(c->evk[0], c->stream));
-  k_correspond<<<div_up(r->src.n * spread, kThreads), kThreads, 0, c->stream>>>(r->tgt.view, r->src.sorted, r->src.n, spread, Tf, thr2, r->slab, r->corr, r->sqd);
+  static const bool corr_per_thread = std::getenv("RGC_CORR_THREAD") != nullptr;
+  if (corr_per_thread)
+    k_correspond<<<div_up(r->src.n * spread, kThreads), kThreads, 0, c->stream>>>(r->tgt.view, r->src.sorted, r->src.n, spread, Tf, thr2, r->slab, r->corr, r->sqd);
+  else
+    k_correspond_tile<<<div_up(r->src.n, KT_WARPS * 32), KT_WARPS * 32, 0, c->stream>>>(r->tgt.view, r->src.sorted, r->src.n, Tf, thr2, r->slab, r->corr, r->sqd);
   CKL(c);
   if (c->profile) CK(c, cudaEventRecord(c->evk[1], c->stream));
   k_linearize<<<reduce_grid(r->src.n), kThreads, 0, c->stream>>>(r->tgt.sorted, r->src.sorted, r->src.cov, r->tgt.cov, r->src.n, Td, want, r->corr, r->maha,
