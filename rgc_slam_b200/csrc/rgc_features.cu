@@ -57,7 +57,7 @@ __device__ __forceinline__ float absf(float v) { return v < 0 ? -v : v; }
 // ------------------------------------------------------------------------------------------------
 // One block per scan.  Stable partition of the kept points by ring id (scanRegistration.cpp:135-230).
 __global__ void __launch_bounds__(256) k_feat_rings(const float4* __restrict__ raw, const int* __restrict__ scan_offsets, int n_rings, float th1, float th2,
-                                                    int* __restrict__ tmp_ring, float* __restrict__ tmp_inten, FeatArrays A) {
+                                                    int* __restrict__ tmp_ring, float* __restrict__ tmp_inten, int* __restrict__ max_seg, FeatArrays A) {
   const int b = blockIdx.x;
   const int in0 = scan_offsets[b], n = scan_offsets[b + 1] - in0;
   const int out0 = in0 + 8 * b;
@@ -186,6 +186,10 @@ __global__ void __launch_bounds__(256) k_feat_rings(const float4* __restrict__ r
     const bool in = tid < n_rings;
     A.scan_start[b * kMaxRings + tid] = in ? s_ring_off[tid] + 5 : 0;
     A.scan_end[b * kMaxRings + tid] = in ? s_ring_off[tid + 1] - 5 : 0;
+    if (in) {  // longest sextant of the batch: sizes the selection kernel's shared-memory sort
+      const int span = s_ring_off[tid + 1] - s_ring_off[tid] - 10;
+      if (span >= 10) atomicMax(max_seg, span / 6 + 2);
+    }
   }
   // ---- stable scatter, chunk by chunk in firing order
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -513,27 +517,47 @@ __device__ void bitonic_sort(float* key, int* idx, int npad) {
 }
 
 // One block per (scan, ring); the six sextants run in order because a pick suppresses up to five
-// neighbours that may lie in the next sextant (:517-534).  Each sextant: two shared-memory bitonic
-// sorts (by cloudCurvature and by intensityCurvature, ties by index), then thread 0 replays the
-// greedy loops (:485-641) on shared-memory copies of the segment window.
-__global__ void __launch_bounds__(128) k_feat_select(const int* __restrict__ scan_offsets, int n_rings, FeatArrays A, int* __restrict__ err_flag) {
+// neighbours that may lie in the next sextant (:517-534).  Each sextant: its window [sp-5, ep+5] of
+// points, curvatures, intensities and flags is staged in shared memory, two bitonic sorts (by
+// cloudCurvature and by intensityCurvature, ties by index) run on all threads, then thread 0
+// replays the greedy loops (:485-641) entirely out of shared memory and the flags are written back.
+// (The first version ran the greedy loops against global memory: 87 % of the feature path's time.)
+constexpr int kSelThreads = 64;
+struct SelSmem {  // carve-up of the dynamic shared memory for a given sort capacity `cap`
+  float* k1; int* i1; float* k2; int* i2;          // [cap] sort keys / indices
+  float4* pt;                                      // [cap + 10] window points
+  float *cv, *c2, *ci; int* in;                    // [cap + 10]
+  signed char *np, *inp, *lb, *ilb, *gm;           // [cap + 10]
+  __device__ SelSmem(unsigned char* base, int cap) {
+    const int w = cap + 10;
+    pt = reinterpret_cast<float4*>(base);
+    k1 = reinterpret_cast<float*>(pt + w);
+    i1 = reinterpret_cast<int*>(k1 + cap);
+    k2 = reinterpret_cast<float*>(i1 + cap);
+    i2 = reinterpret_cast<int*>(k2 + cap);
+    cv = reinterpret_cast<float*>(i2 + cap);
+    c2 = cv + w;
+    ci = c2 + w;
+    in = reinterpret_cast<int*>(ci + w);
+    np = reinterpret_cast<signed char*>(in + w);
+    inp = np + w;
+    lb = inp + w;
+    ilb = lb + w;
+    gm = ilb + w;
+  }
+};
+static size_t sel_smem_bytes(int cap) { return (size_t)(cap + 10) * (16 + 16 + 5) + (size_t)cap * 16 + 16; }
+
+__global__ void __launch_bounds__(kSelThreads) k_feat_select(const int* __restrict__ scan_offsets, int n_rings, int cap, FeatArrays A) {
   const int b = blockIdx.x / n_rings, ring = blockIdx.x % n_rings;
   const int out0 = scan_offsets[b] + 8 * b;
   const int ss = A.scan_start[b * kMaxRings + ring], se = A.scan_end[b * kMaxRings + ring];
   const int seg0 = (b * n_rings + ring) * 6;
   if (threadIdx.x < 6 * 5) A.seg_counts[seg0 * 5 + threadIdx.x] = 0;
   if (se - ss < 10) return;  // :471
-  extern __shared__ unsigned char smem_raw[];
-  float* k1 = reinterpret_cast<float*>(smem_raw);  // [kSegCap] curvature keys
-  int* i1 = reinterpret_cast<int*>(k1 + kSegCap);
-  float* k2 = reinterpret_cast<float*>(i1 + kSegCap);  // intensity-curvature keys
-  int* i2 = reinterpret_cast<int*>(k2 + kSegCap);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SelSmem S(smem_raw, cap);
   const float4* C = A.cloud + out0;
-  const float* CV = A.curvature + out0;
-  const float* CI = A.inten_curvature + out0;
-  const float* C2 = A.curvature2 + out0;
-  const int* IN = A.intensity_num + out0;
-  const int* GM = A.ground_marked + out0;
   int* NP = A.neighbor_picked + out0;
   int* INP = A.inten_neighbor_picked + out0;
   int* LB = A.label + out0;
@@ -543,56 +567,66 @@ __global__ void __launch_bounds__(128) k_feat_select(const int* __restrict__ sca
     const int sp = ss + (se - ss) * j / 6;
     const int ep = ss + (se - ss) * (j + 1) / 6 - 1;
     const int len = ep - sp + 1;
-    if (len > kSegCap) {
-      if (threadIdx.x == 0) atomicExch(err_flag, 1);
-      return;
+    if (len <= 0) continue;  // uniform across the block
+    const int w0 = sp - 5, wn = len + 10;
+    for (int t = threadIdx.x; t < wn; t += blockDim.x) {
+      const int g = w0 + t;
+      S.pt[t] = C[g];
+      S.cv[t] = A.curvature[out0 + g];
+      S.c2[t] = A.curvature2[out0 + g];
+      S.ci[t] = A.inten_curvature[out0 + g];
+      S.in[t] = A.intensity_num[out0 + g];
+      S.np[t] = (signed char)NP[g];
+      S.inp[t] = (signed char)INP[g];
+      S.lb[t] = (signed char)LB[g];
+      S.ilb[t] = (signed char)ILB[g];
+      S.gm[t] = (signed char)A.ground_marked[out0 + g];
     }
     int npad = 1;
     while (npad < len) npad <<= 1;
+    __syncthreads();
     for (int t = threadIdx.x; t < npad; t += blockDim.x) {
       const bool in = t < len;
-      k1[t] = in ? CV[sp + t] : INFINITY;
-      i1[t] = in ? sp + t : 0x7fffffff;
-      k2[t] = in ? CI[sp + t] : INFINITY;
-      i2[t] = in ? sp + t : 0x7fffffff;
+      S.k1[t] = in ? S.cv[t + 5] : INFINITY;
+      S.i1[t] = in ? t + 5 : 0x7fffffff;  // window-relative index (same order as the global index)
+      S.k2[t] = in ? S.ci[t + 5] : INFINITY;
+      S.i2[t] = in ? t + 5 : 0x7fffffff;
     }
     __syncthreads();
-    if (len > 0) {
-      bitonic_sort(k1, i1, npad);
-      bitonic_sort(k2, i2, npad);
-    }
-    if (threadIdx.x == 0 && len > 0) {
+    bitonic_sort(S.k1, S.i1, npad);
+    bitonic_sort(S.k2, S.i2, npad);
+    if (threadIdx.x == 0) {
       const int seg = seg0 + j;
       int* cnt = A.seg_counts + seg * 5;
       auto gap2 = [&](int a, int bb) {
-        const float4 pa = C[a], pb = C[bb];
+        const float4 pa = S.pt[a], pb = S.pt[bb];
         const float dx = fsub(pa.x, pb.x), dy = fsub(pa.y, pb.y), dz = fsub(pa.z, pb.z);
         return fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
       };
       auto suppress = [&](int ind) {  // :517-534 / :564-581
-        NP[ind] = 1;
+        S.np[ind] = 1;
         for (int l = 1; l <= 5; l++) {
           if ((double)gap2(ind + l, ind + l - 1) > 0.05) break;
-          NP[ind + l] = 1;
+          S.np[ind + l] = 1;
         }
         for (int l = -1; l >= -5; l--) {
           if ((double)gap2(ind + l, ind + l + 1) > 0.05) break;
-          NP[ind + l] = 1;
+          S.np[ind + l] = 1;
         }
       };
       // sharp / less sharp (:485-536)
       int largest = 0, n_sharp = 0, n_less = 0;
       for (int k = len - 1; k >= 0; k--) {
-        const int ind = i1[k];
-        if (NP[ind] == 0 && GM[ind] != 1 && (double)CV[ind] > 0.1 && (double)C2[ind] > 0.3) {
+        const int ind = S.i1[k];
+        if (S.np[ind] == 0 && S.gm[ind] != 1 && (double)S.cv[ind] > 0.1 && (double)S.c2[ind] > 0.3) {
           largest++;
           if (largest <= 20) {
-            LB[ind] = 2;
-            A.seg_sharp[seg * 20 + n_sharp++] = ind;
-            A.seg_less[seg * 22 + n_less++] = ind;
+            S.lb[ind] = 2;
+            A.seg_sharp[seg * 20 + n_sharp++] = w0 + ind;
+            A.seg_less[seg * 22 + n_less++] = w0 + ind;
           } else if (largest <= 21) {
-            LB[ind] = 1;
-            A.seg_less[seg * 22 + n_less++] = ind;
+            S.lb[ind] = 1;
+            A.seg_less[seg * 22 + n_less++] = w0 + ind;
           } else {
             break;
           }
@@ -602,12 +636,12 @@ __global__ void __launch_bounds__(128) k_feat_select(const int* __restrict__ sca
       // flat (:538-583)
       int smallest = 0, n_flat = 0;
       for (int k = 0; k < len; k++) {
-        const int ind = i1[k];
-        if (NP[ind] == 0 && (double)CV[ind] < 0.3 && (double)C2[ind] < 0.4) {
+        const int ind = S.i1[k];
+        if (S.np[ind] == 0 && (double)S.cv[ind] < 0.3 && (double)S.c2[ind] < 0.4) {
           smallest++;
           if (smallest <= 40) {
-            LB[ind] = -1;
-            A.seg_flat[seg * 40 + n_flat++] = ind;
+            S.lb[ind] = -1;
+            A.seg_flat[seg * 40 + n_flat++] = w0 + ind;
           } else {
             break;
           }
@@ -617,35 +651,42 @@ __global__ void __launch_bounds__(128) k_feat_select(const int* __restrict__ sca
       // intensity edges (:594-641)
       int largest2 = 0, n_inten = 0, n_inten_less = 0;
       for (int k = len - 1; k >= 0; k--) {
-        const int ind = i2[k];
-        if (INP[ind] == 0 && GM[ind] != 1 && CI[ind] > 65 && LB[ind] != 2 && LB[ind] != 1) {
+        const int ind = S.i2[k];
+        if (S.inp[ind] == 0 && S.gm[ind] != 1 && S.ci[ind] > 65 && S.lb[ind] != 2 && S.lb[ind] != 1) {
           largest2++;
           if (largest2 <= 20) {
-            ILB[ind] = 2;
-            A.seg_inten[seg * 20 + n_inten++] = ind;
-            A.seg_inten_less[seg * 21 + n_inten_less++] = ind;
+            S.ilb[ind] = 2;
+            A.seg_inten[seg * 20 + n_inten++] = w0 + ind;
+            A.seg_inten_less[seg * 21 + n_inten_less++] = w0 + ind;
           } else if (largest2 <= 21) {
-            ILB[ind] = 1;
-            A.seg_inten_less[seg * 21 + n_inten_less++] = ind;
-            A.seg_less[seg * 22 + n_less++] = ind;  // cornerPointsLessSharp (:617)
+            S.ilb[ind] = 1;
+            A.seg_inten_less[seg * 21 + n_inten_less++] = w0 + ind;
+            A.seg_less[seg * 22 + n_less++] = w0 + ind;  // cornerPointsLessSharp (:617)
           } else {
             break;
           }
-          INP[ind] = 1;
+          S.inp[ind] = 1;
           for (int l = 1; l <= 5; l++) {
-            const float dI = (float)(IN[ind + l] - IN[ind + l - 1]);
+            const float dI = (float)(S.in[ind + l] - S.in[ind + l - 1]);
             if (absf(dI) > 35) break;
-            INP[ind + l] = 1;
+            S.inp[ind + l] = 1;
           }
           for (int l = -1; l >= -5; l--) {
-            const float dI = (float)(IN[ind + l] - IN[ind + l + 1]);
+            const float dI = (float)(S.in[ind + l] - S.in[ind + l + 1]);
             if (absf(dI) > 35) break;
-            INP[ind + l] = 1;
+            S.inp[ind + l] = 1;
           }
         }
       }
       cnt[0] = n_sharp; cnt[1] = n_less; cnt[2] = n_flat; cnt[3] = n_inten; cnt[4] = n_inten_less;
-      __threadfence_block();
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < wn; t += blockDim.x) {
+      const int g = w0 + t;
+      NP[g] = S.np[t];
+      INP[g] = S.inp[t];
+      LB[g] = S.lb[t];
+      ILB[g] = S.ilb[t];
     }
     __syncthreads();
   }
@@ -774,8 +815,10 @@ extern "C" int rgc_feat_extract(rgc_ctx* c, const rgc_scan_batch* batch, rgc_fea
   CK(c, cudaMemsetAsync(d_err, 0, 4, st));
 
   const int pt_blocks = (int)((total_out + 255) / 256);
-  k_feat_rings<<<nb, 256, 0, st>>>(d_raw, d_off, nr, (float)batch->minimum_range, (float)batch->maximum_range, tmp_ring, tmp_inten, A);
+  k_feat_rings<<<nb, 256, 0, st>>>(d_raw, d_off, nr, (float)batch->minimum_range, (float)batch->maximum_range, tmp_ring, tmp_inten, d_err, A);
   CKL(c);
+  int max_seg = 0;  // read back while the per-point passes run
+  CK(c, cudaMemcpyAsync(&max_seg, d_err, 4, cudaMemcpyDeviceToHost, st));
   k_feat_pass_a<<<pt_blocks, 256, 0, st>>>(d_off, nb, (int)total_out, A);
   CKL(c);
   k_feat_pass_b<<<pt_blocks, 256, 0, st>>>(d_off, nb, (int)total_out, A);
@@ -784,8 +827,16 @@ extern "C" int rgc_feat_extract(rgc_ctx* c, const rgc_scan_batch* batch, rgc_fea
   CKL(c);
   k_feat_occlusion<<<pt_blocks, 256, 0, st>>>(d_off, nb, (int)total_out, A);
   CKL(c);
-  const size_t sel_smem = (size_t)kSegCap * 16;
-  k_feat_select<<<nb * nr, 128, sel_smem, st>>>(d_off, nr, A, d_err);
+  CK(c, cudaStreamSynchronize(st));  // max_seg (one 4-byte readback per batch)
+  if (max_seg > kSegCap) {
+    release();
+    FAIL(c, RGC_ERR_UNSUPPORTED, "a ring sextant is longer than 2048 points");
+  }
+  int cap = 64;
+  while (cap < max_seg) cap <<= 1;
+  const size_t sel_smem = sel_smem_bytes(cap);
+  CK(c, cudaFuncSetAttribute(k_feat_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
+  k_feat_select<<<nb * nr, kSelThreads, sel_smem, st>>>(d_off, nr, cap, A);
   CKL(c);
   k_feat_compact<<<nb, 128, 0, st>>>(nr, A);
   CKL(c);
@@ -796,8 +847,7 @@ extern "C" int rgc_feat_extract(rgc_ctx* c, const rgc_scan_batch* batch, rgc_fea
   }
   CK(c, cudaEventRecord(c->ev[1], st));
 
-  int h_err = 0;
-  CK(c, cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, st));
+
   auto d2h = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
     return dst ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st) : cudaSuccess;
   };
@@ -826,7 +876,6 @@ extern "C" int rgc_feat_extract(rgc_ctx* c, const rgc_scan_batch* batch, rgc_fea
     c->err = std::string("rgc_feat_extract: ") + cudaGetErrorString(e);
     return RGC_ERR_CUDA;
   }
-  if (h_err) FAIL(c, RGC_ERR_UNSUPPORTED, "a ring sextant is longer than 2048 points");
   int* lists[5] = {out->n_corner_sharp, out->n_corner_less_sharp, out->n_surf_flat, out->n_inten_sharp, out->n_inten_less_sharp};
   for (int L = 0; L < 5; L++)
     if (lists[L])
