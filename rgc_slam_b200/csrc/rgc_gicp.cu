@@ -209,8 +209,11 @@ static int launch_knn(rgc_ctx* c, const GridView& v, const float4* queries, int 
 // self-kNN of a whole cloud: the warp-cooperative tile kernel (RGC_KNN_THREAD=1 selects the
 // thread-per-query kernel instead, for A/B profiling)
 static int launch_knn_self(rgc_ctx* c, const GridView& v, int n, int k, int* nbr) {
+  // small clouds: one query per (sparse) warp walks the tree with the shortest dependent chain;
+  // large clouds: the warp-cooperative tile kernel has the throughput
   static const bool per_thread = std::getenv("RGC_KNN_THREAD") != nullptr;
-  if (per_thread) return launch_knn<true>(c, v, nullptr, n, k, nbr, nullptr);
+  static const bool force_tile = std::getenv("RGC_KNN_TILE") != nullptr;
+  if (per_thread || (!force_tile && query_spread(n) >= 8)) return launch_knn<true>(c, v, nullptr, n, k, nbr, nullptr);
   if (k > 32) FAIL(c, RGC_ERR_UNSUPPORTED, "k_correspondences > 32 is not supported");
   const size_t per_warp = sizeof(float4) * KT_CAND + sizeof(TileNode) * KT_STACK + (size_t)(k + KT_PEND) * 32 * 8;
   const size_t smem = per_warp * KT_WARPS;
@@ -826,6 +829,29 @@ int rgc_debug_tile_stats(rgc_ctx* c, const void* points, size_t n, size_t stride
   c->put(d_stats);
   cloud_release(c, cl);
   return RGC_OK;
+}
+
+// debug aid: per-query statistics of one correspondence search at pose T16 (column-major);
+// stats: n_source x 4 int64 {cycles, nodes, table probes, candidates}, source in SORTED order
+int rgc_debug_correspond_stats(rgc_reg* r, const double* T16, long long* stats) {
+  if (!r || !T16 || !stats) return RGC_ERR_INVALID;
+  rgc_ctx* c = r->ctx;
+  CK(c, cudaSetDevice(c->device));
+  TRY(reg_ready(r));
+  const size_t n = (size_t)r->src.n;
+  long long* d_stats = (long long*)c->get(sizeof(long long) * 4 * n);
+  if (!d_stats) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (debug)");
+  CK(c, cudaMemsetAsync(d_stats, 0, sizeof(long long) * 4 * n, c->stream));
+  CK(c, cudaMemcpyToSymbolAsync(g_tile_dbg, &d_stats, sizeof(d_stats), 0, cudaMemcpyHostToDevice, c->stream));
+  double T[16], e;
+  colmajor_to_row(T16, T);
+  int rc = reg_linearize(r, T, &e, nullptr, nullptr);
+  long long* null_ptr = nullptr;
+  CK(c, cudaMemcpyToSymbolAsync(g_tile_dbg, &null_ptr, sizeof(null_ptr), 0, cudaMemcpyHostToDevice, c->stream));
+  CK(c, cudaMemcpyAsync(stats, d_stats, sizeof(long long) * 4 * n, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  c->put(d_stats);
+  return rc;
 }
 
 int rgc_reg_set_owner_slab(rgc_reg* r, int axis, float lo, float hi) {

@@ -20,14 +20,24 @@
 
 namespace rgc {
 
+// debug statistics buffer (rgc_debug_*_stats); null in normal operation
+__device__ long long* g_tile_dbg = nullptr;
+
 constexpr int kBboxBlocks = 296;  // 2 x 148 SMs
 constexpr int kThreads = 128;
 
-// Small clouds (one LiDAR sweep) cannot fill 148 SMs with one query per thread: the search kernels
-// are then bound by the latency of a few divergent warps.  `spread` (power of two) leaves only
-// every spread-th lane active, so the same queries occupy spread x more warps, each with fewer
-// divergent paths to serialise.  Large clouds use spread = 1 (throughput-bound).
-__host__ __device__ inline int query_spread(int n) { return n <= 12000 ? 8 : (n <= 48000 ? 4 : (n <= 96000 ? 2 : 1)); }
+// Small clouds (one LiDAR sweep) cannot fill 148 SMs with one query per thread, and the tree walk of
+// one lane does not overlap with its warp-mates' (divergent paths execute one after the other:
+// per-query statistics showed 2100 cycles per dependent load with 8 queries per warp against ~270
+// with one).  `spread` (power of two, <= 32) leaves only every spread-th lane active, so the same
+// queries occupy spread x more warps; it is chosen so that a kernel fills the machine ~2.5 times.
+// Large clouds use spread = 1 (throughput-bound).
+__host__ __device__ inline int query_spread(int n) {
+  const long long target_threads = 148LL * 64 * 32 * 5 / 2;
+  int s = 1;
+  while (s < 32 && (long long)n * (s * 2) <= target_threads) s *= 2;
+  return s;
+}
 
 // ------------------------------------------------------------------------------------------------
 // ingest: raw[n] with byte stride (xyz at offset 0, as every PCL point type) -> float4(x,y,z,1)
@@ -354,9 +364,6 @@ __device__ __forceinline__ float warp_min(float v) {
   return v;
 }
 
-// debug: per-warp {cycles, nodes visited, candidates gathered, heap inserts} (rgc_debug_tile_stats)
-__device__ long long* g_tile_dbg = nullptr;
-
 __global__ void __launch_bounds__(KT_WARPS * 32) k_knn_tile(GridView g, int n, int k, int* __restrict__ out_idx) {
   extern __shared__ __align__(16) unsigned char tile_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -665,7 +672,18 @@ __global__ void __launch_bounds__(kThreads, 8) k_correspond(GridView tgt, const 
   transform_f(Tf.m, p.x, p.y, p.z, qx, qy, qz);
   Best1 top;
   top.reset(1, thr2);
-  if (slab_owns(slab, qx, qy, qz)) knn_search(tgt, qx, qy, qz, 1, thr2, -1, top);
+  if (g_tile_dbg) {  // debug statistics (rgc_debug_correspond_stats): cycles, nodes, lookups, candidates
+    SearchStats st{0, 0, 0};
+    const long long t0 = clock64();
+    if (slab_owns(slab, qx, qy, qz)) knn_search(tgt, qx, qy, qz, 1, thr2, -1, top, &st);
+    long long* o = g_tile_dbg + (size_t)i * 4;
+    o[0] = clock64() - t0;
+    o[1] = st.nodes;
+    o[2] = st.lookups;
+    o[3] = st.candidates;
+  } else if (slab_owns(slab, qx, qy, qz)) {
+    knn_search(tgt, qx, qy, qz, 1, thr2, -1, top);
+  }
   corr[i] = (top.id0 >= 0 && top.d0 < thr2) ? top.id0 : -1;
   sqd[i] = top.d0;
 }
