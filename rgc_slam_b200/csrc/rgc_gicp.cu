@@ -209,11 +209,11 @@ static int launch_knn(rgc_ctx* c, const GridView& v, const float4* queries, int 
 // self-kNN of a whole cloud: the warp-cooperative tile kernel (RGC_KNN_THREAD=1 selects the
 // thread-per-query kernel instead, for A/B profiling)
 static int launch_knn_self(rgc_ctx* c, const GridView& v, int n, int k, int* nbr) {
-  // small clouds: one query per (sparse) warp walks the tree with the shortest dependent chain;
-  // large clouds: the warp-cooperative tile kernel has the throughput
+  // the warp-cooperative tile kernel; RGC_KNN_THREAD=1 selects the thread-per-query kernel (A/B)
   static const bool per_thread = std::getenv("RGC_KNN_THREAD") != nullptr;
   static const bool force_tile = std::getenv("RGC_KNN_TILE") != nullptr;
-  if (per_thread || (!force_tile && query_spread(n) >= 8)) return launch_knn<true>(c, v, nullptr, n, k, nbr, nullptr);
+  (void)force_tile;
+  if (per_thread) return launch_knn<true>(c, v, nullptr, n, k, nbr, nullptr);
   if (k > 32) FAIL(c, RGC_ERR_UNSUPPORTED, "k_correspondences > 32 is not supported");
   const size_t per_warp = sizeof(float4) * KT_CAND + sizeof(TileNode) * KT_STACK + (size_t)(k + KT_PEND) * 32 * 8;
   const size_t smem = per_warp * KT_WARPS;

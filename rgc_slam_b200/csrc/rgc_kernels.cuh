@@ -26,18 +26,15 @@ __device__ long long* g_tile_dbg = nullptr;
 constexpr int kBboxBlocks = 296;  // 2 x 148 SMs
 constexpr int kThreads = 128;
 
-// Small clouds (one LiDAR sweep) cannot fill 148 SMs with one query per thread, and the tree walk of
-// one lane does not overlap with its warp-mates' (divergent paths execute one after the other:
-// per-query statistics showed 2100 cycles per dependent load with 8 queries per warp against ~270
-// with one).  `spread` (power of two, <= 32) leaves only every spread-th lane active, so the same
-// queries occupy spread x more warps; it is chosen so that a kernel fills the machine ~2.5 times.
+// Small clouds (one LiDAR sweep) cannot fill 148 SMs with one query per thread: the search kernels
+// are then bound by the latency of a few divergent warps.  `spread` (power of two) leaves only
+// every spread-th lane active, so the same queries occupy spread x more warps, each with fewer
+// divergent paths to serialise.  Measured on 22k queries (k_correspond): spread 1: 137 us, 4: 92 us,
+// 32 (one query per warp): 146 us — a single query is itself a ~30 us chain of ~4k dependent
+// instructions and ~28 dependent loads, so beyond 4-8 the extra warps only add scheduling waves.
 // Large clouds use spread = 1 (throughput-bound).
-__host__ __device__ inline int query_spread(int n) {
-  const long long target_threads = 148LL * 64 * 32 * 5 / 2;
-  int s = 1;
-  while (s < 32 && (long long)n * (s * 2) <= target_threads) s *= 2;
-  return s;
-}
+__host__ __device__ inline int query_spread(int n) { return n <= 12000 ? 8 : (n <= 48000 ? 4 : (n <= 96000 ? 2 : 1)); }
+
 
 // ------------------------------------------------------------------------------------------------
 // ingest: raw[n] with byte stride (xyz at offset 0, as every PCL point type) -> float4(x,y,z,1)
