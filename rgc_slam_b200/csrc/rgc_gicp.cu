@@ -160,13 +160,18 @@ static int cloud_build(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, s
     if (l < v.nlevels) {
       ts.table[l] = cl.tables + off;
       ts.mask[l] = (uint32_t)(slots[l] - 1);
+      int lg = 0;
+      while (((size_t)1 << lg) < slots[l]) lg++;
+      ts.shift[l] = (uint32_t)(64 - lg);
       off += slots[l];
     } else {
       ts.table[l] = nullptr;
       ts.mask[l] = 0;
+      ts.shift[l] = 63;
     }
     v.table[l] = ts.table[l];
     v.mask[l] = ts.mask[l];
+    v.shift[l] = ts.shift[l];
   }
   k_build_tables<<<dim3(div_up(n, 256), v.nlevels), 256, 0, st>>>(kin, n, ts);
   CKL(c);

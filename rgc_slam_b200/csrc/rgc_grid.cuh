@@ -52,7 +52,8 @@ struct GridView {
   int nbits;          // cells per axis at level 0 = 1 << nbits
   int nlevels;        // nbits + 1
   const GridSlot* table[kMaxLevels];
-  uint32_t mask[kMaxLevels];  // table size - 1 (power of two)
+  uint32_t mask[kMaxLevels];   // table size - 1 (power of two)
+  uint32_t shift[kMaxLevels];  // 64 - log2(table size)
 };
 
 // Grid geometry from a bounding box (host side; shared by the library and tests/hostsim so both
@@ -90,14 +91,10 @@ RGC_HD uint64_t spread3(uint32_t v) {  // 21 bits -> every third bit
 }
 RGC_HD uint64_t morton3(uint32_t x, uint32_t y, uint32_t z) { return spread3(x) | (spread3(y) << 1) | (spread3(z) << 2); }
 
-RGC_HD uint64_t mix64(uint64_t k) {  // murmur3 fmix64
-  k ^= k >> 33;
-  k *= 0xff51afd7ed558ccdull;
-  k ^= k >> 33;
-  k *= 0xc4ceb9fe1a85ec53ull;
-  k ^= k >> 33;
-  return k;
-}
+// table slot of a Morton key: Fibonacci (multiplicative) hashing — one 64-bit multiply, top bits.
+// `shift` = 64 - log2(table size).  (murmur's fmix64, used first, cost two multiplies and three
+// xor-shifts on the critical path of every probe.)
+RGC_HD uint32_t slot_of(uint64_t key, uint32_t shift) { return (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> shift); }
 
 // fine-level integer cell coordinate of a float coordinate.  Monotone non-decreasing in x
 // (float subtract, multiply and floor are monotone), which is what the face bounds rely on.
@@ -136,7 +133,7 @@ RGC_HD bool grid_lookup(const GridView& g, int l, int cx, int cy, int cz, uint32
   const uint64_t key = morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
   const GridSlot* tab = g.table[l];
   const uint32_t mask = g.mask[l];
-  uint32_t h = (uint32_t)mix64(key) & mask;
+  uint32_t h = slot_of(key, g.shift[l]);
   for (;;) {
     GridSlot s = load_slot(tab + h);
     if (s.key == kEmptyKey) return false;
@@ -154,7 +151,7 @@ RGC_HD bool grid_lookup(const GridView& g, int l, int cx, int cy, int cz, uint32
 RGC_HD bool grid_lookup_key(const GridView& g, int l, uint64_t key, uint32_t& start, uint32_t& end, uint32_t& cmask) {
   const GridSlot* tab = g.table[l];
   const uint32_t mask = g.mask[l];
-  uint32_t h = (uint32_t)mix64(key) & mask;
+  uint32_t h = slot_of(key, g.shift[l]);
   for (;;) {
     GridSlot s = load_slot(tab + h);
     if (s.key == kEmptyKey) return false;
@@ -464,8 +461,10 @@ RGC_HD void knn_search(const GridView& g, float qx, float qy, float qz, int k, f
       // NaN (inf - inf) cannot occur: r = +inf gives tl = -inf, th = +inf
       int il = tl < 0.f ? 0 : (tl >= (float)ncell ? ncell : (int)tl);
       int ih = th < 0.f ? -1 : (th >= (float)ncell ? ncell - 1 : (int)th);
-      lo[a] = il > 0 ? il - 1 : 0;                  // one cell of slack against float rounding
-      hi[a] = ih < ncell - 1 ? ih + 1 : ncell - 1;
+      // no extra slack cell: r already carries 2 margins, orders of magnitude above the rounding
+      // error of this index computation
+      lo[a] = il;
+      hi[a] = ih < ncell - 1 ? ih : ncell - 1;
       if (ih < 0 || il >= ncell) hi[a] = lo[a] - 1;  // ball misses the grid on this axis
     }
   }

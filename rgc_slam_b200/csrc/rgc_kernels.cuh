@@ -238,11 +238,12 @@ __global__ void __launch_bounds__(256) k_count_cells(const uint64_t* __restrict_
 struct TableSet {
   GridSlot* table[kMaxLevels];
   uint32_t mask[kMaxLevels];
+  uint32_t shift[kMaxLevels];
   int nlevels;
 };
 
-__device__ __forceinline__ GridSlot* slot_insert_or_find(GridSlot* tab, uint32_t mask, uint64_t key) {
-  uint32_t h = (uint32_t)mix64(key) & mask;
+__device__ __forceinline__ GridSlot* slot_insert_or_find(GridSlot* tab, uint32_t mask, uint32_t shift, uint64_t key) {
+  uint32_t h = slot_of(key, shift);
   for (;;) {
     unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long*>(&tab[h].key), (unsigned long long)kEmptyKey, (unsigned long long)key);
     if (prev == kEmptyKey || prev == key) return &tab[h];
@@ -265,10 +266,10 @@ __global__ void __launch_bounds__(256) k_build_tables(const uint64_t* __restrict
     opens = (key >> (3 * l)) != (prev >> (3 * l));
   }
   if (opens) {
-    slot_insert_or_find(ts.table[l], ts.mask[l], key >> (3 * l))->start = (uint32_t)i;
-    if (i > 0) slot_insert_or_find(ts.table[l], ts.mask[l], prev >> (3 * l))->end = (uint32_t)i;
+    slot_insert_or_find(ts.table[l], ts.mask[l], ts.shift[l], key >> (3 * l))->start = (uint32_t)i;
+    if (i > 0) slot_insert_or_find(ts.table[l], ts.mask[l], ts.shift[l], prev >> (3 * l))->end = (uint32_t)i;
   }
-  if (i == n - 1) slot_insert_or_find(ts.table[l], ts.mask[l], key >> (3 * l))->end = (uint32_t)n;
+  if (i == n - 1) slot_insert_or_find(ts.table[l], ts.mask[l], ts.shift[l], key >> (3 * l))->end = (uint32_t)n;
 }
 
 // second pass (tables complete): every cell sets its bit in its parent's occupied-children mask
@@ -287,7 +288,7 @@ __global__ void __launch_bounds__(256) k_child_masks(const uint64_t* __restrict_
     const uint64_t ck = key >> (3 * l), pk = ck >> 3;
     GridSlot* tab = ts.table[l + 1];
     const uint32_t mask = ts.mask[l + 1];
-    uint32_t h = (uint32_t)mix64(pk) & mask;
+    uint32_t h = slot_of(pk, ts.shift[l + 1]);
     while ((tab[h].key & kKeyMask) != pk) h = (h + 1) & mask;  // parent exists by construction
     // the mask lives in the top byte of the 64-bit key word = top byte of its high 32-bit half
     atomicOr(reinterpret_cast<unsigned int*>(&tab[h].key) + 1, 1u << (24 + (int)(ck & 7)));
@@ -465,8 +466,8 @@ __global__ void __launch_bounds__(KT_WARPS * 32) k_knn_tile(GridView g, int n, i
         const float tl = (l3[a] - o3[a]) * inv_cs, th = (h3[a] - o3[a]) * inv_cs;
         const int il = tl < 0.f ? 0 : (tl >= (float)ncell ? ncell : (int)tl);
         const int ih = th < 0.f ? -1 : (th >= (float)ncell ? ncell - 1 : (int)th);
-        rlo[a] = il > 0 ? il - 1 : 0;
-        rhi[a] = ih < ncell - 1 ? ih + 1 : ncell - 1;
+        rlo[a] = il;
+        rhi[a] = ih < ncell - 1 ? ih : ncell - 1;
         if (ih < 0 || il >= ncell) rhi[a] = rlo[a] - 1;
       }
     }
@@ -758,8 +759,8 @@ __global__ void __launch_bounds__(KT_WARPS * 32) k_correspond_tile(GridView g, c
         const float tl = (l3[a] - o3[a]) * inv_cs, th = (h3[a] - o3[a]) * inv_cs;
         const int il = tl < 0.f ? 0 : (tl >= (float)ncell ? ncell : (int)tl);
         const int ih = th < 0.f ? -1 : (th >= (float)ncell ? ncell - 1 : (int)th);
-        rlo[a] = il > 0 ? il - 1 : 0;
-        rhi[a] = ih < ncell - 1 ? ih + 1 : ncell - 1;
+        rlo[a] = il;
+        rhi[a] = ih < ncell - 1 ? ih : ncell - 1;
         if (ih < 0 || il >= ncell) rhi[a] = rlo[a] - 1;
       }
     }

@@ -59,11 +59,14 @@ static void sim_build(const float* xyzw, int n, float cell, SimCloud& c) {
     auto& t = c.tables[l];
     t.assign(s, GridSlot{kEmptyKey, 0, 0});
     uint32_t mask = (uint32_t)(s - 1);
+    int lg = 0;
+    while (((size_t)1 << lg) < s) lg++;
+    v.shift[l] = (uint32_t)(64 - lg);
     int start = 0;
     for (int i = 1; i <= n; i++) {
       if (i == n || (ks[i] >> (3 * l)) != (ks[i - 1] >> (3 * l))) {
         uint64_t key = ks[i - 1] >> (3 * l);
-        uint32_t h = (uint32_t)mix64(key) & mask;
+        uint32_t h = slot_of(key, v.shift[l]);
         while (t[h].key != kEmptyKey) h = (h + 1) & mask;
         t[h] = GridSlot{key, (uint32_t)start, (uint32_t)i};
         start = i;
@@ -79,7 +82,7 @@ static void sim_build(const float* xyzw, int n, float cell, SimCloud& c) {
         uint64_t ck = ks[i] >> (3 * l), pk = ck >> 3;
         auto& t = c.tables[l + 1];
         uint32_t mask = (uint32_t)(t.size() - 1);
-        uint32_t hh = (uint32_t)mix64(pk) & mask;
+        uint32_t hh = slot_of(pk, v.shift[l + 1]);
         while ((t[hh].key & kKeyMask) != pk) hh = (hh + 1) & mask;
         t[hh].key |= (uint64_t)1 << (56 + (int)(ck & 7));
       }
