@@ -328,7 +328,8 @@ static int reg_linearize(rgc_reg* r, const double* T, double* err, double* H, do
   // queries: its serial node-by-node walk has a longer dependent-load chain); RGC_CORR_TILE=1 selects it
   static const bool corr_tile = std::getenv("RGC_CORR_TILE") != nullptr;
   if (!corr_tile)
-    k_correspond<<<div_up(r->src.n * spread, kThreads), kThreads, 0, c->stream>>>(r->tgt.view, r->src.sorted, r->src.n, spread, Tf, thr2, r->slab, r->corr, r->sqd);
+    k_correspond<<<div_up(r->src.n * spread, kThreads), kThreads, 0, c->stream>>>(r->tgt.view, r->src.sorted, r->src.n, spread, Tf, thr2, r->slab, r->have_corr ? 1 : 0, r->corr,
+                                                                                  r->sqd);
   else
     k_correspond_tile<<<div_up(r->src.n, KT_WARPS * 32), KT_WARPS * 32, 0, c->stream>>>(r->tgt.view, r->src.sorted, r->src.n, Tf, thr2, r->slab, r->corr, r->sqd);
   CKL(c);
