@@ -48,6 +48,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         cmd += ["-ccbin", "/usr/bin/g++"]
     if verbose:
         cmd += ["-Xptxas", "-v"]
+    cmd += os.environ.get("RGC_NVCC_EXTRA", "").split()  # tuning experiments: -DRGC_KT_PEND=8 ...
     cmd += ["-o", LIB] + sources()
     subprocess.check_call(cmd)
     return LIB

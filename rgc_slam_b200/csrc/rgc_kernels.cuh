@@ -340,12 +340,28 @@ __global__ void __launch_bounds__(kThreads, 8) k_knn(GridView g, const float4* _
 //            into their heaps together, tightening the balls.
 // Exactness is unchanged: a point is dropped only if its cell is outside every ball or its d2
 // exceeds the lane's current k-th distance; ties are resolved by (d2, original index) in the heap.
+#ifndef RGC_KT_CAND
+#define RGC_KT_CAND 128
+#endif
+#ifndef RGC_KT_STACK
+#define RGC_KT_STACK 40
+#endif
+#ifndef RGC_KT_SEEDS
+#define RGC_KT_SEEDS 128
+#endif
+#ifndef RGC_KT_PEND
+#define RGC_KT_PEND 8
+#endif
+#ifndef RGC_KT_LEAF
+#define RGC_KT_LEAF 64
+#endif
+// defaults from a parameter sweep on the C2 workload (tools/tile_variants.sh; profiles/README.md)
 constexpr int KT_WARPS = 4;
-constexpr int KT_CAND = 160;    // candidate buffer entries per warp
-constexpr int KT_STACK = 64;    // DFS stack entries per warp
-constexpr int KT_SEEDS = 64;    // Morton-adjacent seed points per warp
-constexpr int KT_PEND = 12;     // pending slots per lane
-constexpr int KT_LEAF = 32;     // cells with <= this many points are gathered whole
+constexpr int KT_CAND = RGC_KT_CAND;    // candidate buffer entries per warp (>= KT_SEEDS)
+constexpr int KT_STACK = RGC_KT_STACK;  // DFS stack entries per warp
+constexpr int KT_SEEDS = RGC_KT_SEEDS;  // Morton-adjacent seed points per warp
+constexpr int KT_PEND = RGC_KT_PEND;    // pending slots per lane
+constexpr int KT_LEAF = RGC_KT_LEAF;    // cells with <= this many points are gathered whole
 
 struct TileNode {
   uint32_t cx_lvl, cy_mask, cz, start, end;

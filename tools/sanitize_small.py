@@ -1,0 +1,21 @@
+"""Small end-to-end run for compute-sanitizer (memcheck / racecheck / initcheck / synccheck):
+one quarter-resolution align + fitness + correspondences + a 3-scan feature batch."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import rgc_slam_b200 as rgc
+from rgc_slam_b200 import synth
+from rgc_slam_b200.features import extract_features
+scene = synth.Scene.make(synth.BASE_SEED)
+traj = synth.trajectory(8, seed=1)
+tgt = synth.to_xyz1(synth.lidar_scan(scene, traj[3], n_azimuth=300, seed=1))
+src = synth.to_xyz1(synth.lidar_scan(scene, traj[4], n_azimuth=300, seed=2))
+g = rgc.FastGICP()
+g.setMaxCorrespondenceDistance(2.0)
+g.setInputTarget(tgt); g.setInputSource(src)
+T = g.align(want_output=True)
+print("align", g.last_result, g.getFitnessScore(), (g.correspondences()[0] >= 0).sum())
+print("knn", rgc.knn(tgt, src[:500], 5)[0].sum(), rgc.knn_self(tgt, 20).sum())
+scans = [synth.lidar_scan(scene, traj[f], n_azimuth=400, seed=50 + f) for f in range(3)]
+r, ms = extract_features(scans)
+print("features", [x["cloud_size"] for x in r], [len(x["corner_sharp"]) for x in r])
