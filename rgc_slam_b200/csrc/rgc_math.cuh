@@ -121,9 +121,87 @@ RGC_HD Sym3 recompose(const double V[3][3], const double val[3], const double sg
   return r;
 }
 
+// Unit eigenvector of the SMALLEST eigenvalue of a symmetric PSD 3x3 — all the PLANE regularisation
+// needs (U diag(1,1,1e-3) V^T == I - (1 - 1e-3) n n^T).  A full Jacobi decomposition costs ~1000 fp64
+// instructions per point and made k_covariance fp64-pipe bound at 17 % of HBM peak; this costs ~250:
+//   lambda : Newton on the characteristic polynomial from 0 (for a PSD matrix the polynomial is
+//            convex and decreasing on [0, lambda_min], so Newton climbs monotonically to the root),
+//   n      : the largest cross product of two rows of (C - lambda I), polished by one inverse-iteration
+//            step with the cofactor matrix of (C - lambda' I).
+// Returns false (caller falls back to Jacobi) when the matrix is numerically rank <= 1 or the two
+// smallest eigenvalues are too close for this shortcut to be trusted.
+RGC_HD bool smallest_eigvec_sym3(const Sym3& Cin, double n[3], double& lambda_out) {
+  const double tr = Cin.xx + Cin.yy + Cin.zz;
+  if (!(tr > 0.0)) return false;
+  const double is = fast_rcp(tr);  // scale to trace 1
+  const Sym3 C = {Cin.xx * is, Cin.xy * is, Cin.xz * is, Cin.yy * is, Cin.yz * is, Cin.zz * is};
+  // det(C - l I) = -l^3 + c2 l^2 - c1 l + c0
+  const double c2 = 1.0;
+  const double c1 = (C.xx * C.yy - C.xy * C.xy) + (C.xx * C.zz - C.xz * C.xz) + (C.yy * C.zz - C.yz * C.yz);
+  const double c0 = C.xx * (C.yy * C.zz - C.yz * C.yz) - C.xy * (C.xy * C.zz - C.yz * C.xz) + C.xz * (C.xy * C.yz - C.yy * C.xz);
+  double l = 0.0;
+#pragma unroll 1
+  for (int it = 0; it < 12; it++) {
+    const double f = ((-l + c2) * l - c1) * l + c0;
+    const double fp = (-3.0 * l + 2.0 * c2) * l - c1;
+    if (!(fp < 0.0)) break;
+    const double step = f * fast_rcp(fp);
+    l -= step;
+    if (fabs(step) <= 1e-17) break;
+  }
+  if (!(l > -1e-12) || !(l < 0.34)) return false;
+  // the second eigenvalue must be clearly separated: l2 + l1 = 1 - l, l1 l2 = c0 / l (or via c1)
+  // => gap test on the reduced quadratic  m^2 - (1 - l) m + (c1 - l (1 - l)) = 0
+  const double sum = 1.0 - l, prod = c1 - l * sum;
+  const double disc = sum * sum - 4.0 * prod;
+  const double l2 = 0.5 * (sum - sqrt(disc > 0.0 ? disc : 0.0));
+  if (!(l2 - l > 1e-7)) return false;  // near-degenerate pair: let Jacobi decide
+  auto eigvec = [&](double mu, double v[3]) {
+    const double r0[3] = {C.xx - mu, C.xy, C.xz}, r1[3] = {C.xy, C.yy - mu, C.yz}, r2[3] = {C.xz, C.yz, C.zz - mu};
+    const double a[3] = {r0[1] * r1[2] - r0[2] * r1[1], r0[2] * r1[0] - r0[0] * r1[2], r0[0] * r1[1] - r0[1] * r1[0]};
+    const double b[3] = {r0[1] * r2[2] - r0[2] * r2[1], r0[2] * r2[0] - r0[0] * r2[2], r0[0] * r2[1] - r0[1] * r2[0]};
+    const double c[3] = {r1[1] * r2[2] - r1[2] * r2[1], r1[2] * r2[0] - r1[0] * r2[2], r1[0] * r2[1] - r1[1] * r2[0]};
+    const double na = a[0] * a[0] + a[1] * a[1] + a[2] * a[2], nb = b[0] * b[0] + b[1] * b[1] + b[2] * b[2], nc = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
+    const double* best = a;
+    double nbest = na;
+    if (nb > nbest) { best = b; nbest = nb; }
+    if (nc > nbest) { best = c; nbest = nc; }
+    const double inv = fast_rsqrt(nbest);
+    v[0] = best[0] * inv; v[1] = best[1] * inv; v[2] = best[2] * inv;
+    return nbest;
+  };
+  double v[3];
+  const double nb0 = eigvec(l, v);
+  if (!(nb0 > 1e-24)) return false;  // (C - l I) numerically rank <= 1
+  // one inverse-iteration polish: y = adj(C - mu I) v with mu just below l (adjugate ~ n n^T / gap)
+  {
+    const double mu = l - 1e-9 * (l2 - l) - 1e-18;
+    const double a = C.xx - mu, b = C.yy - mu, c = C.zz - mu;
+    const double A00 = b * c - C.yz * C.yz, A01 = C.xz * C.yz - C.xy * c, A02 = C.xy * C.yz - C.xz * b;
+    const double A11 = a * c - C.xz * C.xz, A12 = C.xy * C.xz - a * C.yz, A22 = a * b - C.xy * C.xy;
+    const double y0 = A00 * v[0] + A01 * v[1] + A02 * v[2], y1 = A01 * v[0] + A11 * v[1] + A12 * v[2], y2 = A02 * v[0] + A12 * v[1] + A22 * v[2];
+    const double ny = y0 * y0 + y1 * y1 + y2 * y2;
+    if (ny > 1e-60) {
+      const double inv = fast_rsqrt(ny);
+      v[0] = y0 * inv; v[1] = y1 * inv; v[2] = y2 * inv;
+    }
+  }
+  n[0] = v[0]; n[1] = v[1]; n[2] = v[2];
+  lambda_out = l * tr;
+  return true;
+}
+
 // fast_gicp_impl.hpp:264-293
 RGC_HD Sym3 regularize_cov(const Sym3& cov, int method) {
   if (method == REG_NONE) return cov;
+  if (method == REG_PLANE) {
+    double n[3], lam;
+    if (smallest_eigvec_sym3(cov, n, lam)) {
+      // I - (1 - s 1e-3) n n^T, s = sign pairing of the reference's SVD (negative only through round-off)
+      const double f = 1.0 - (lam < 0.0 ? -1e-3 : 1e-3);
+      return Sym3{1.0 - f * n[0] * n[0], -f * n[0] * n[1], -f * n[0] * n[2], 1.0 - f * n[1] * n[1], -f * n[1] * n[2], 1.0 - f * n[2] * n[2]};
+    }
+  }
   if (method == REG_FROBENIUS) {
     const double lambda = 1e-3;
     Sym3 C = cov;
