@@ -239,7 +239,10 @@ static int cloud_covariances(rgc_ctx* c, Cloud& cl, int k, int method) {
   CK(c, cudaEventRecord(c->ev[2], st));
   TRY(launch_knn_self(c, cl.view, cl.n, k, nbr));
   CK(c, cudaEventRecord(c->ev[3], st));
-  k_covariance<<<div_up(cl.n, kThreads), kThreads, 0, st>>>(cl.sorted, nbr, cl.n, k, method, cl.cov);
+  if (k <= 20)
+    k_covariance<20><<<div_up(cl.n, kThreads), kThreads, 0, st>>>(cl.sorted, nbr, cl.n, k, method, cl.cov);
+  else
+    k_covariance<32><<<div_up(cl.n, kThreads), kThreads, 0, st>>>(cl.sorted, nbr, cl.n, k, method, cl.cov);
   CKL(c);
   CK(c, cudaEventRecord(c->ev[4], st));
   c->put(nbr);
