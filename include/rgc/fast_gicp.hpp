@@ -206,11 +206,31 @@ class FastGICP {
   }
   const rgc_result& lastResult() const { return core_.res_; }
 
+ protected:
+  detail::Core& core() { return core_; }
+
  private:
   detail::Core core_;
   PointCloudSourceConstPtr source_;
   PointCloudTargetConstPtr target_;
   Matrix4 final_ = identity4();
+};
+
+// fast_gicp::FastVGICP (fast_vgicp.hpp:24-80): voxelised correspondences, what RGC_odometer.cpp:998 uses
+enum class NeighborSearchMethod { DIRECT27, DIRECT7, DIRECT1 };                       // gicp_settings.hpp:8
+enum class VoxelAccumulationMode { ADDITIVE, ADDITIVE_WEIGHTED, MULTIPLICATIVE };     // gicp_settings.hpp:10
+template <class PointSource, class PointTarget>
+class FastVGICP : public FastGICP<PointSource, PointTarget> {
+ public:
+  explicit FastVGICP(int device = 0) : FastGICP<PointSource, PointTarget>(device) { push(); }
+  void setResolution(double r) { res_ = r; push(); }
+  void setNeighborSearchMethod(NeighborSearchMethod m) { search_ = (int)m; push(); }
+  void setVoxelAccumulationMode(VoxelAccumulationMode m) { mode_ = (int)m; push(); }
+
+ private:
+  void push() { detail::check(this->core().ctx_, rgc_reg_set_vgicp(this->core().reg_, 1, res_, search_, mode_)); }
+  double res_ = 1.0;
+  int search_ = 2, mode_ = 0;
 };
 
 #else  // RGC_WITH_PCL ---------------------------------------------------------------------------

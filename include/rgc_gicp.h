@@ -130,6 +130,10 @@ int rgc_reg_compute_error(rgc_reg* reg, const double* T16, double* err);
  * sq_dist is +inf where no target lies within max_correspondence_distance)                  */
 int rgc_reg_get_correspondences(rgc_reg* reg, int32_t* corr, float* sq_dist);
 
+/* number of correspondences the last linearize used (points within max_correspondence_distance,
+ * or (point, voxel) pairs in voxelised mode) */
+int rgc_reg_last_inliers(const rgc_reg* reg, int* n);
+
 /* pcl::Registration::getFitnessScore(max_range) with the final transformation of the last
  * align (callers: SRC/RGC_odometer.cpp:1010, SRC/RGC_mapping.cpp:2070)                        */
 int rgc_reg_fitness(rgc_reg* reg, double max_range, double* score);
@@ -139,6 +143,18 @@ int rgc_reg_get_final_transformation(const rgc_reg* reg, float* T16);
  * idx/d2: m x k row-major; rows are padded with -1 / +inf when k > n.  Test hook + public op. */
 int rgc_knn(rgc_ctx* ctx, const void* points, size_t n, size_t stride_bytes, const void* queries, size_t m, size_t qstride_bytes, int k,
             int32_t* idx, float* d2, float grid_cell);
+
+/* ---- voxelised GICP: fast_gicp::FastVGICP (FG/fast_vgicp.hpp:24, FGI/fast_vgicp_impl.hpp:17-204) — the
+ * class SRC/RGC_odometer.cpp:998 instantiates.  When enabled, linearize / compute_error / align use
+ * voxel correspondences (GaussianVoxelMap, FG/fast_vgicp_voxel.hpp:129-160) instead of the exact 1-NN:
+ *   resolution        setResolution               (1.0)
+ *   neighbor_search   setNeighborSearchMethod     0 = DIRECT27, 1 = DIRECT7, 2 = DIRECT1 (default)   (FG/gicp_settings.hpp:8)
+ *   accumulation_mode setVoxelAccumulationMode    0 = ADDITIVE (default), 1 = ADDITIVE_WEIGHTED, 2 = MULTIPLICATIVE (:10)
+ * max_correspondence_distance is ignored in this mode, as in the reference.                          */
+int rgc_reg_set_vgicp(rgc_reg* reg, int enabled, double resolution, int neighbor_search, int accumulation_mode);
+/* test hook: the Gaussian voxels of the target (unordered): coords 3 ints, num_points, mean 3 doubles,
+ * covariance upper triangle 6 doubles per voxel; n_voxels is always set.                             */
+int rgc_reg_get_voxels(rgc_reg* reg, int32_t* coords3, int32_t* num_points, double* mean3, double* cov6, size_t cap, size_t* n_voxels);
 
 /* k nearest neighbours of every point of a cloud within the cloud itself (self included, rank 0),
  * through the same warp-cooperative kernel calculate_covariances uses (FGI/fast_gicp_impl.hpp:254).

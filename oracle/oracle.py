@@ -215,6 +215,76 @@ class FastGICP:
         return lib().orc_gicp_fitness(self._h, max_range)
 
 
+DIRECT27, DIRECT7, DIRECT1 = 0, 1, 2
+ADDITIVE, ADDITIVE_WEIGHTED, MULTIPLICATIVE = 0, 1, 2
+
+
+class FastVGICP(FastGICP):
+    """Mirror of fast_gicp::FastVGICP (voxelised GICP) driven through the CPU oracle."""
+
+    def __init__(self, resolution=1.0, search_method=DIRECT1, voxel_mode=ADDITIVE, **kw):
+        L = lib()
+        L.orc_vgicp_create.restype = C.c_void_p
+        L.orc_vgicp_destroy.argtypes = [C.c_void_p]
+        L.orc_vgicp_set_voxel_params.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int]
+        L.orc_vgicp_set_target.argtypes = [C.c_void_p, _f32p, C.c_int]
+        L.orc_vgicp_linearize.argtypes = [C.c_void_p, _f64p, C.c_void_p, C.c_void_p]
+        L.orc_vgicp_linearize.restype = C.c_double
+        L.orc_vgicp_compute_error.argtypes = [C.c_void_p, _f64p]
+        L.orc_vgicp_compute_error.restype = C.c_double
+        L.orc_vgicp_num_correspondences.argtypes = [C.c_void_p]
+        L.orc_vgicp_get_voxels.argtypes = [C.c_void_p, C.c_int, _i32p, _i32p, _f64p, _f64p]
+        L.orc_vgicp_align.argtypes = [C.c_void_p, _f32p, _f32p, _i32p]
+        L.orc_vgicp_align.restype = C.c_double
+        self._h = C.c_void_p(L.orc_vgicp_create())
+        self.params = dict(max_iterations=64, rotation_epsilon=2e-3, transformation_epsilon=5e-4, corr_dist=np.finfo(np.float32).max,
+                           k=20, regularization=REG_PLANE, optimizer=OPT_LM, lm_max_iterations=10, lm_init_lambda_factor=1e-9, num_threads=0)
+        self.params.update(kw)
+        self._apply()
+        self.n_src = self.n_tgt = 0
+        L.orc_vgicp_set_voxel_params(self._h, resolution, search_method, voxel_mode)
+
+    def __del__(self):
+        try:
+            lib().orc_vgicp_destroy(self._h)
+        except Exception:
+            pass
+
+    def setInputTarget(self, pts):
+        p = _pts(pts)
+        self.n_tgt = p.shape[0]
+        lib().orc_vgicp_set_target(self._h, p, p.shape[0])
+
+    def linearize(self, T, want_Hb=True):
+        T = np.ascontiguousarray(T, np.float64).reshape(-1)
+        if want_Hb:
+            H, b = np.empty((6, 6)), np.empty(6)
+            e = lib().orc_vgicp_linearize(self._h, T, H.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p))
+            return e, H, b
+        return lib().orc_vgicp_linearize(self._h, T, None, None)
+
+    def compute_error(self, T):
+        return lib().orc_vgicp_compute_error(self._h, np.ascontiguousarray(T, np.float64).reshape(-1))
+
+    def num_correspondences(self):
+        return lib().orc_vgicp_num_correspondences(self._h)
+
+    def voxels(self):
+        cap = max(self.n_tgt, 1)
+        coords, num = np.zeros((cap, 3), np.int32), np.zeros(cap, np.int32)
+        mean, cov = np.zeros((cap, 3)), np.zeros((cap, 6))
+        nv = lib().orc_vgicp_get_voxels(self._h, cap, coords.reshape(-1), num, mean.reshape(-1), cov.reshape(-1))
+        return coords[:nv], num[:nv], mean[:nv], cov[:nv]
+
+    def align(self, guess=None):
+        g = np.eye(4, dtype=np.float32) if guess is None else np.ascontiguousarray(guess, np.float32)
+        T = np.empty((4, 4), np.float32)
+        res = np.zeros(4, np.int32)
+        secs = lib().orc_vgicp_align(self._h, g.reshape(-1), T.reshape(-1), res)
+        self.last = dict(converged=bool(res[0]), iterations=int(res[1]), n_linearize=int(res[2]), n_compute_error=int(res[3]), seconds=secs)
+        return T
+
+
 # ------------------------------------------------------------------ A-LOAM features
 class _FeatArrays(C.Structure):
     _fields_ = ([(n, C.c_void_p) for n in (

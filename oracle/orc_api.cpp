@@ -144,6 +144,57 @@ double orc_gicp_align(void* h, const float* guess, float* final_T, float* out_po
 }
 double orc_gicp_fitness(void* h, double max_range) { return ((FastGICP*)h)->fitness(max_range); }
 
+// ---- FastVGICP object ----
+void* orc_vgicp_create() { return new FastVGICP(); }
+void orc_vgicp_destroy(void* h) { delete (FastVGICP*)h; }
+void orc_vgicp_set_voxel_params(void* h, double resolution, int search_method, int voxel_mode) {
+  FastVGICP* g = (FastVGICP*)h;
+  g->voxel_resolution_ = resolution;
+  g->search_method_ = search_method;
+  g->voxel_mode_ = voxel_mode;
+  g->have_voxelmap_ = false;
+}
+void orc_vgicp_set_target(void* h, const float* xyzw, int n) { ((FastVGICP*)h)->setInputTargetV(xyzw, n); }
+double orc_vgicp_linearize(void* h, const double* trans, double* H, double* b) {
+  FastVGICP* g = (FastVGICP*)h;
+  g->ensure_covariances();
+  return g->linearize(trans, H, b);
+}
+double orc_vgicp_compute_error(void* h, const double* trans) { return ((FastVGICP*)h)->compute_error(trans); }
+int orc_vgicp_num_correspondences(void* h) { return (int)((FastVGICP*)h)->voxel_correspondences_.size(); }
+// voxels sorted by (x, y, z): coords 3 ints, num, mean 3, cov 6 (upper triangle) per voxel
+int orc_vgicp_get_voxels(void* h, int cap, int* coords, int* num, double* mean3, double* cov6) {
+  FastVGICP* g = (FastVGICP*)h;
+  g->ensure_covariances();
+  if (!g->have_voxelmap_) g->create_voxelmap();
+  int i = 0;
+  for (auto& kv : g->voxels_) {
+    if (i >= cap) break;
+    coords[3 * i] = kv.first.x; coords[3 * i + 1] = kv.first.y; coords[3 * i + 2] = kv.first.z;
+    num[i] = kv.second.num_points;
+    for (int d = 0; d < 3; d++) mean3[3 * i + d] = kv.second.mean[d];
+    const double* c = kv.second.cov;
+    cov6[6 * i] = c[0]; cov6[6 * i + 1] = c[1]; cov6[6 * i + 2] = c[2]; cov6[6 * i + 3] = c[5]; cov6[6 * i + 4] = c[6]; cov6[6 * i + 5] = c[10];
+    i++;
+  }
+  return (int)g->voxels_.size();
+}
+double orc_vgicp_align(void* h, const float* guess, float* final_T, int* result4) {
+  FastVGICP* g = (FastVGICP*)h;
+  g->n_linearize_ = g->n_compute_error_ = 0;
+  auto t0 = std::chrono::steady_clock::now();
+  g->align(guess, nullptr);
+  auto t1 = std::chrono::steady_clock::now();
+  std::memcpy(final_T, g->final_transformation_, sizeof(float) * 16);
+  if (result4) {
+    result4[0] = g->converged_ ? 1 : 0;
+    result4[1] = g->nr_iterations_;
+    result4[2] = g->n_linearize_;
+    result4[3] = g->n_compute_error_;
+  }
+  return std::chrono::duration<double>(t1 - t0).count();
+}
+
 // ---- A-LOAM feature extraction ----
 struct orc_feat_arrays {
   // all arrays caller-allocated with capacity n_in + 8

@@ -19,6 +19,7 @@
 #include <cmath>
 #include <cstdio>
 #include <limits>
+#include <map>
 #include <vector>
 
 #include "orc_kdtree.hpp"
@@ -458,6 +459,253 @@ class FastGICP {
         nr++;
       }
     return nr > 0 ? s / nr : std::numeric_limits<double>::max();
+  }
+};
+
+
+// ------------------------------------------------------------------------------------------------
+// FastVGICP (what RGC_odometer.cpp:998 actually instantiates) — SURVEY.md §8f N1.
+//   rgc_slam/include/fast_gicp/gicp/impl/fast_vgicp_impl.hpp:73-204
+//   rgc_slam/include/fast_gicp/gicp/fast_vgicp_voxel.hpp:10-183
+enum NeighborSearch { DIRECT27 = 0, DIRECT7 = 1, DIRECT1 = 2 };                  // gicp_settings.hpp:8
+enum VoxelMode { ADDITIVE = 0, ADDITIVE_WEIGHTED = 1, MULTIPLICATIVE = 2 };      // gicp_settings.hpp:10
+
+struct GaussianVoxel {
+  int num_points = 0;
+  double mean[4] = {0, 0, 0, 0};
+  double cov[16] = {0};
+};
+
+class FastVGICP : public FastGICP {
+ public:
+  double voxel_resolution_ = 1.0;   // fast_vgicp_impl.hpp:20
+  int search_method_ = DIRECT1;     // :21
+  int voxel_mode_ = ADDITIVE;       // :22
+  struct Key {
+    int x, y, z;
+    bool operator<(const Key& o) const { return x != o.x ? x < o.x : (y != o.y ? y < o.y : z < o.z); }
+  };
+  std::map<Key, GaussianVoxel> voxels_;
+  bool have_voxelmap_ = false;
+  std::vector<std::pair<int, const GaussianVoxel*>> voxel_correspondences_;
+  std::vector<Mat4d> voxel_mahalanobis_;
+
+  // fast_vgicp_voxel.hpp:158-160
+  Key voxel_coord(const double* x) const {
+    return Key{(int)std::floor(x[0] / voxel_resolution_ - 0.5), (int)std::floor(x[1] / voxel_resolution_ - 0.5),
+               (int)std::floor(x[2] / voxel_resolution_ - 0.5)};
+  }
+  static std::vector<Key> neighbor_offsets(int method) {  // fast_vgicp_voxel.hpp:10-44
+    if (method == DIRECT1) return {{0, 0, 0}};
+    if (method == DIRECT7) return {{0, 0, 0}, {1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
+    std::vector<Key> o;
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++)
+        for (int k = 0; k < 3; k++) o.push_back(Key{i - 1, j - 1, k - 1});
+    return o;
+  }
+  // fast_vgicp_voxel.hpp:129-156 (sequential, points appended in index order)
+  void create_voxelmap() {
+    voxels_.clear();
+    const int n = n_target();
+    for (int i = 0; i < n; i++) {
+      double m[4];
+      for (int d = 0; d < 4; d++) m[d] = (double)target_[4 * (size_t)i + d];
+      GaussianVoxel& v = voxels_[voxel_coord(m)];
+      const double* c = target_covs_[i].m;
+      v.num_points++;
+      if (voxel_mode_ == MULTIPLICATIVE) {  // :86-93
+        double ci[16], inv[16];
+        std::memcpy(ci, c, sizeof(ci));
+        ci[15] = 1;
+        inverse4(ci, inv);
+        for (int j = 0; j < 16; j++) v.cov[j] += inv[j];
+        for (int r = 0; r < 4; r++)
+          for (int cc = 0; cc < 4; cc++) v.mean[r] += inv[r * 4 + cc] * m[cc];
+      } else {  // :110-114
+        for (int d = 0; d < 4; d++) v.mean[d] += m[d];
+        for (int j = 0; j < 16; j++) v.cov[j] += c[j];
+      }
+    }
+    for (auto& kv : voxels_) {
+      GaussianVoxel& v = kv.second;
+      if (voxel_mode_ == MULTIPLICATIVE) {  // :95-100
+        v.cov[15] = 1;
+        v.mean[3] = 1;
+        double inv[16], mm[4];
+        inverse4(v.cov, inv);
+        std::memcpy(v.cov, inv, sizeof(inv));
+        for (int r = 0; r < 4; r++) {
+          mm[r] = 0;
+          for (int cc = 0; cc < 4; cc++) mm[r] += v.cov[r * 4 + cc] * v.mean[cc];
+        }
+        std::memcpy(v.mean, mm, sizeof(mm));
+      } else {  // :116-119
+        for (int d = 0; d < 4; d++) v.mean[d] /= v.num_points;
+        for (int j = 0; j < 16; j++) v.cov[j] /= v.num_points;
+      }
+    }
+    have_voxelmap_ = true;
+  }
+  void setInputTargetV(const float* xyzw, int n) {
+    setInputTarget(xyzw, n);
+    have_voxelmap_ = false;
+  }
+
+  // fast_vgicp_impl.hpp:73-116 (correspondences kept in (point, offset) order: the reference's order
+  // depends on the OpenMP schedule)
+  void update_correspondences_v(const double* trans) {
+    voxel_correspondences_.clear();
+    const auto offsets = neighbor_offsets(search_method_);
+    const int n = n_source();
+    for (int i = 0; i < n; i++) {
+      double tA[4];
+      for (int r = 0; r < 3; r++) {
+        double s = 0.0;
+        for (int c = 0; c < 4; c++) s += trans[r * 4 + c] * (double)input_[4 * (size_t)i + c];
+        tA[r] = s;
+      }
+      tA[3] = 1.0;
+      const Key coord = voxel_coord(tA);
+      for (const Key& o : offsets) {
+        auto it = voxels_.find(Key{coord.x + o.x, coord.y + o.y, coord.z + o.z});
+        if (it != voxels_.end()) voxel_correspondences_.push_back({i, &it->second});
+      }
+    }
+    voxel_mahalanobis_.resize(voxel_correspondences_.size());
+#pragma omp parallel for num_threads(num_threads_) schedule(guided, 8)
+    for (int i = 0; i < (int)voxel_correspondences_.size(); i++) {
+      const double* cov_A = source_covs_[voxel_correspondences_[i].first].m;
+      const double* cov_B = voxel_correspondences_[i].second->cov;
+      double TC[16], Tt[16], RCR[16];
+      mat4_mul(trans, cov_A, TC);
+      for (int a = 0; a < 4; a++)
+        for (int b = 0; b < 4; b++) Tt[a * 4 + b] = trans[b * 4 + a];
+      mat4_mul(TC, Tt, RCR);
+      for (int j = 0; j < 16; j++) RCR[j] = cov_B[j] + RCR[j];
+      RCR[15] = 1.0;
+      inverse4(RCR, voxel_mahalanobis_[i].m);
+      voxel_mahalanobis_[i].m[15] = 0.0;
+    }
+  }
+
+  double accumulate_v(const double* trans, double* H, double* b) {
+    double sum_errors = 0.0;
+    if (H && b) {
+      for (int i = 0; i < 36; i++) H[i] = 0.0;
+      for (int i = 0; i < 6; i++) b[i] = 0.0;
+    }
+    for (size_t ci = 0; ci < voxel_correspondences_.size(); ci++) {
+      const int i = voxel_correspondences_[ci].first;
+      const GaussianVoxel* vx = voxel_correspondences_[ci].second;
+      double tA[4], err[4];
+      for (int r = 0; r < 3; r++) {
+        double s = 0.0;
+        for (int c = 0; c < 4; c++) s += trans[r * 4 + c] * (double)input_[4 * (size_t)i + c];
+        tA[r] = s;
+      }
+      tA[3] = (double)input_[4 * (size_t)i + 3];
+      for (int d = 0; d < 4; d++) err[d] = vx->mean[d] - tA[d];
+      const double* M = voxel_mahalanobis_[ci].m;
+      const double w = std::sqrt((double)vx->num_points);
+      double Me[4];
+      for (int r = 0; r < 4; r++) {
+        double s = 0.0;
+        for (int c = 0; c < 4; c++) s += M[r * 4 + c] * err[c];
+        Me[r] = s;
+      }
+      sum_errors += w * (err[0] * Me[0] + err[1] * Me[1] + err[2] * Me[2] + err[3] * Me[3]);
+      if (!H || !b) continue;
+      double J[24] = {0};
+      J[0 * 6 + 1] = -tA[2]; J[0 * 6 + 2] = tA[1];
+      J[1 * 6 + 0] = tA[2];  J[1 * 6 + 2] = -tA[0];
+      J[2 * 6 + 0] = -tA[1]; J[2 * 6 + 1] = tA[0];
+      J[0 * 6 + 3] = -1.0; J[1 * 6 + 4] = -1.0; J[2 * 6 + 5] = -1.0;
+      double MJ[24];
+      for (int r = 0; r < 4; r++)
+        for (int c = 0; c < 6; c++) {
+          double s = 0.0;
+          for (int k = 0; k < 4; k++) s += M[r * 4 + k] * J[k * 6 + c];
+          MJ[r * 6 + c] = s;
+        }
+      for (int r = 0; r < 6; r++) {
+        for (int c = 0; c < 6; c++) {
+          double s = 0.0;
+          for (int k = 0; k < 4; k++) s += J[k * 6 + r] * MJ[k * 6 + c];
+          H[r * 6 + c] += w * s;
+        }
+        double s = 0.0;
+        for (int k = 0; k < 4; k++) s += J[k * 6 + r] * Me[k];
+        b[r] += w * s;
+      }
+    }
+    return sum_errors;
+  }
+  // fast_vgicp_impl.hpp:119-180
+  double linearize(const double* trans, double* H, double* b) {
+    n_linearize_++;
+    if (!have_voxelmap_) create_voxelmap();
+    update_correspondences_v(trans);
+    return accumulate_v(trans, H, b);
+  }
+  // :183-204
+  double compute_error(const double* trans) {
+    n_compute_error_++;
+    return accumulate_v(trans, nullptr, nullptr);
+  }
+  // lsq_registration_impl.hpp:106-172 with the voxelised linearize / compute_error
+  bool step_lm_v(double* x0, double* delta) {
+    double H[36], b[6];
+    double y0 = linearize(x0, H, b);
+    if (lm_lambda_ < 0.0) {
+      double mx = 0.0;
+      for (int i = 0; i < 6; i++) mx = std::max(mx, std::fabs(H[i * 6 + i]));
+      lm_lambda_ = lm_init_lambda_factor_ * mx;
+    }
+    double nu = 2.0;
+    for (int i = 0; i < lm_max_iterations_; i++) {
+      double A[36], nb[6], d[6], xi[16];
+      for (int j = 0; j < 36; j++) A[j] = H[j] + ((j % 7 == 0) ? lm_lambda_ : 0.0);
+      for (int j = 0; j < 6; j++) nb[j] = -b[j];
+      ldlt6_solve(A, nb, d);
+      make_delta(d, delta);
+      mat4_mul(delta, x0, xi);
+      double yi = compute_error(xi);
+      double denom = 0.0;
+      for (int j = 0; j < 6; j++) denom += d[j] * (lm_lambda_ * d[j] - b[j]);
+      double rho = (y0 - yi) / denom;
+      if (rho < 0) {
+        if (is_converged(delta)) return true;
+        lm_lambda_ = nu * lm_lambda_;
+        nu = 2 * nu;
+        continue;
+      }
+      std::memcpy(x0, xi, sizeof(xi));
+      lm_lambda_ = lm_lambda_ * std::max(1.0 / 3.0, 1 - std::pow(2 * rho - 1, 3));
+      std::memcpy(final_hessian_, H, sizeof(H));
+      return true;
+    }
+    return false;
+  }
+  void align(const float* guess, float* out_points) {
+    have_voxelmap_ = false;  // computeTransformation resets the voxel map (fast_vgicp_impl.hpp:66-70)
+    ensure_covariances();
+    double x0[16];
+    for (int i = 0; i < 16; i++) x0[i] = (double)guess[i];
+    lm_lambda_ = -1.0;
+    converged_ = false;
+    nr_iterations_ = 0;
+    for (int i = 0; i < max_iterations_ && !converged_; i++) {
+      nr_iterations_ = i;
+      double delta[16];
+      if (!step_lm_v(x0, delta)) {
+        std::fprintf(stderr, "lm not converged!!\n");
+        break;
+      }
+      converged_ = is_converged(delta);
+    }
+    for (int i = 0; i < 16; i++) final_transformation_[i] = (float)x0[i];
+    if (out_points) transform_cloud(final_transformation_, out_points);
   }
 };
 

@@ -82,6 +82,9 @@ def lib():
         L.rgc_knn.argtypes = [vp, vp, sz, sz, vp, sz, sz, C.c_int, vp, vp, C.c_float]
         L.rgc_reg_stage_ms.argtypes = [vp, vp]
         L.rgc_knn_self.argtypes = [vp, vp, sz, sz, C.c_int, vp, C.c_float]
+        L.rgc_reg_set_vgicp.argtypes = [vp, C.c_int, C.c_double, C.c_int, C.c_int]
+        L.rgc_reg_last_inliers.argtypes = [vp, C.POINTER(C.c_int)]
+        L.rgc_reg_get_voxels.argtypes = [vp, vp, vp, vp, vp, sz, C.POINTER(sz)]
         _LIB = L
     return _LIB
 
@@ -94,7 +97,7 @@ EXPORTED_SYMBOLS = [
     "rgc_reg_set_source_covs", "rgc_reg_set_target_covs", "rgc_reg_get_source_covs", "rgc_reg_get_target_covs",
     "rgc_reg_align", "rgc_reg_linearize", "rgc_reg_compute_error", "rgc_reg_get_correspondences", "rgc_reg_fitness",
     "rgc_reg_get_final_transformation", "rgc_knn", "rgc_reg_stage_ms", "rgc_knn_self", "rgc_reg_set_owner_slab", "rgc_reg_set_allreduce",
-    "rgc_ctx_set_profiling", "rgc_ctx_last_kernel_ms",
+    "rgc_ctx_set_profiling", "rgc_ctx_last_kernel_ms", "rgc_reg_set_vgicp", "rgc_reg_get_voxels", "rgc_reg_last_inliers",
 ]
 
 
@@ -327,6 +330,12 @@ class FastGICP:
         return dict(converged=bool(r.converged), iterations=r.iterations, n_linearize=r.n_linearize, n_compute_error=r.n_compute_error,
                     n_inliers=r.n_inliers, final_error=r.final_error, device_ms=r.device_ms)
 
+    def last_inliers(self):
+        """number of correspondences the last linearize used"""
+        n = C.c_int()
+        self.ctx.check(lib().rgc_reg_last_inliers(self._h, C.byref(n)))
+        return n.value
+
     def getFitnessScore(self, max_range=np.finfo(np.float64).max):
         s = C.c_double()
         self.ctx.check(lib().rgc_reg_fitness(self._h, float(max_range), C.byref(s)))
@@ -363,6 +372,43 @@ class FastGICP:
         ms = np.zeros(7, np.float32)
         lib().rgc_reg_stage_ms(self._h, ms.ctypes.data)
         return dict(zip(("src_build", "src_knn", "src_cov", "tgt_build", "tgt_knn", "tgt_cov", "lm"), ms.tolist()))
+
+
+DIRECT27, DIRECT7, DIRECT1 = 0, 1, 2                      # fast_gicp::NeighborSearchMethod (gicp_settings.hpp:8)
+ADDITIVE, ADDITIVE_WEIGHTED, MULTIPLICATIVE = 0, 1, 2     # fast_gicp::VoxelAccumulationMode (gicp_settings.hpp:10)
+
+
+class FastVGICP(FastGICP):
+    """Mirror of ``fast_gicp::FastVGICP`` (fast_vgicp.hpp:24-80): the voxelised variant the odometry node
+    instantiates (RGC_odometer.cpp:998-1011)."""
+
+    def __init__(self, ctx: Context | None = None, device: int = 0):
+        super().__init__(ctx, device)
+        self._res, self._search, self._mode = 1.0, DIRECT1, ADDITIVE
+        self._push_vox()
+
+    def _push_vox(self):
+        self.ctx.check(lib().rgc_reg_set_vgicp(self._h, 1, self._res, self._search, self._mode))
+
+    def setResolution(self, r):
+        self._res = float(r); self._push_vox()
+
+    def setNeighborSearchMethod(self, m):
+        self._search = int(m); self._push_vox()
+
+    def setVoxelAccumulationMode(self, m):
+        self._mode = int(m); self._push_vox()
+
+    def voxels(self):
+        """(coords (nv,3) int32, num_points, mean (nv,3), cov upper triangle (nv,6)) sorted by coords."""
+        nv = C.c_size_t()
+        self.ctx.check(lib().rgc_reg_get_voxels(self._h, None, None, None, None, 0, C.byref(nv)))
+        n = nv.value
+        coords, num = np.zeros((n, 3), np.int32), np.zeros(n, np.int32)
+        mean, cov = np.zeros((n, 3)), np.zeros((n, 6))
+        self.ctx.check(lib().rgc_reg_get_voxels(self._h, coords.ctypes.data, num.ctypes.data, mean.ctypes.data, cov.ctypes.data, n, C.byref(nv)))
+        o = np.lexsort((coords[:, 2], coords[:, 1], coords[:, 0]))
+        return coords[o], num[o], mean[o], cov[o]
 
 
 def knn(points, queries, k, ctx: Context | None = None, grid_cell: float = 0.0):

@@ -19,6 +19,7 @@
 #include "rgc_ctx.hpp"
 #include "rgc_kernels.cuh"
 #include "rgc_lm.hpp"
+#include "rgc_vgicp.cuh"
 
 using namespace rgc;
 
@@ -50,6 +51,7 @@ struct Cloud {
   double* cov = nullptr;  // 6 doubles per sorted point
   bool has_cov = false;
   float build_ms = 0, knn_ms = 0, cov_ms = 0;
+  float bb_min[3] = {0, 0, 0}, bb_max[3] = {0, 0, 0};
 };
 
 static void cloud_release(rgc_ctx* c, Cloud& cl) {
@@ -58,6 +60,30 @@ static void cloud_release(rgc_ctx* c, Cloud& cl) {
   c->put(cl.tables);
   c->put(cl.cov);
   cl = Cloud();
+}
+
+// stable LSD radix sort of (64-bit key, 32-bit value) pairs on the ctx stream; `hist` holds
+// 256 * (tiles + 1) counters.  On return *kout / *vout point at the buffers with the sorted data.
+static int radix_sort_pairs(rgc_ctx* c, uint64_t* keys_a, uint64_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, uint32_t* hist, int n, int key_bits,
+                            uint64_t** kout, uint32_t** vout) {
+  const int nblk = div_up(n, RS_TILE);
+  uint32_t* digit_total = hist + 256 * (size_t)nblk;
+  const int passes = div_up(key_bits, 8);
+  uint64_t *kin = keys_a, *ko = keys_b;
+  uint32_t *vin = vals_a, *vo = vals_b;
+  for (int p = 0; p < passes; p++) {
+    k_rs_hist<<<nblk, 256, 0, c->stream>>>(kin, n, 8 * p, hist, nblk);
+    CKL(c);
+    k_rs_scan<<<256, 256, 0, c->stream>>>(hist, nblk, digit_total);
+    CKL(c);
+    k_rs_scatter<<<nblk, 256, 0, c->stream>>>(kin, vin, ko, vo, hist, digit_total, n, 8 * p, nblk);
+    CKL(c);
+    std::swap(kin, ko);
+    std::swap(vin, vo);
+  }
+  *kout = kin;
+  *vout = vin;
+  return RGC_OK;
 }
 
 // upload (or adopt a device pointer), Morton-sort, build the level tables
@@ -87,7 +113,6 @@ static int cloud_build(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, s
   uint32_t* vals_b = (uint32_t*)c->get(4 * n_sz);
   const int nblk = div_up(n, RS_TILE);
   uint32_t* hist = (uint32_t*)c->get(4 * 256 * ((size_t)nblk + 1));
-  uint32_t* digit_total = hist ? hist + 256 * (size_t)nblk : nullptr;
   uint32_t* d_counts = (uint32_t*)c->get(4 * kMaxLevels);
   cl.sorted = (float4*)c->get(sizeof(float4) * n_sz);
   cl.inv = (int*)c->get(sizeof(int) * n_sz);
@@ -108,6 +133,10 @@ static int cloud_build(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, s
   for (int a = 0; a < 3; a++)
     if (!std::isfinite(mn[a]) || !std::isfinite(mx[a])) FAIL(c, RGC_ERR_INVALID, "point cloud contains non-finite coordinates");
 
+  for (int a = 0; a < 3; a++) {
+    cl.bb_min[a] = mn[a];
+    cl.bb_max[a] = mx[a];
+  }
   // ---- grid geometry ----
   GridView& v = cl.view;
   v.n = n;
@@ -118,19 +147,9 @@ static int cloud_build(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, s
   // ---- Morton keys + LSD radix sort ----
   k_morton<<<div_up(n, 256), 256, 0, st>>>(orig, n, geom, keys_a, vals_a);
   CKL(c);
-  const int passes = div_up(3 * nbits, 8);
-  uint64_t *kin = keys_a, *kout = keys_b;
-  uint32_t *vin = vals_a, *vout = vals_b;
-  for (int p = 0; p < passes; p++) {
-    k_rs_hist<<<nblk, 256, 0, st>>>(kin, n, 8 * p, hist, nblk);
-    CKL(c);
-    k_rs_scan<<<256, 256, 0, st>>>(hist, nblk, digit_total);
-    CKL(c);
-    k_rs_scatter<<<nblk, 256, 0, st>>>(kin, vin, kout, vout, hist, digit_total, n, 8 * p, nblk);
-    CKL(c);
-    std::swap(kin, kout);
-    std::swap(vin, vout);
-  }
+  uint64_t* kin = keys_a;
+  uint32_t* vin = vals_a;
+  TRY(radix_sort_pairs(c, keys_a, keys_b, vals_a, vals_b, hist, n, 3 * nbits, &kin, &vin));
   k_gather_sorted<<<div_up(n, 256), 256, 0, st>>>(orig, vin, n, cl.sorted, cl.inv);
   CKL(c);
 
@@ -272,6 +291,18 @@ struct rgc_reg {
   bool converged = false;
   int n_linearize = 0, n_compute_error = 0, last_inliers = 0;
   float lm_ms = 0;
+  // voxelised GICP (FastVGICP)
+  bool vgicp = false;
+  double vox_res = 1.0;
+  int vox_search = 2;  // DIRECT1
+  int vox_mode = 0;    // ADDITIVE
+  VoxelSlot* vox_slots = nullptr;
+  VoxelMapView vox{};
+  bool vox_valid = false;
+  int vox_count = 0;
+  int* vox_corr = nullptr;
+  double* vox_maha = nullptr;
+  size_t vox_cap = 0;
   // sharded target (config C5)
   Slab slab{-1, 0.f, 0.f};
   rgc_reduce_fn reduce_fn = nullptr;
@@ -315,9 +346,143 @@ static void to_rt(const double* T /*row-major 4x4*/, Rt& d, RtF& f) {
   }
 }
 
+static int vgicp_n_off(const rgc_reg* r) { return r->vox_search == 2 ? 1 : (r->vox_search == 1 ? 7 : 27); }
+
+// GaussianVoxelMap::create_voxelmap (fast_vgicp_voxel.hpp:129-156) on the device
+static int vgicp_build(rgc_reg* r) {
+  rgc_ctx* c = r->ctx;
+  if (r->vox_valid) return RGC_OK;
+  Cloud& t = r->tgt;
+  const int n = t.n;
+  cudaStream_t st = c->stream;
+  VoxGeom g;
+  g.res = r->vox_res;
+  int total_bits = 0;
+  for (int a = 0; a < 3; a++) {
+    const int lo = (int)std::floor((double)t.bb_min[a] / g.res - 0.5), hi = (int)std::floor((double)t.bb_max[a] / g.res - 0.5);
+    g.lo[a] = lo;
+    g.dim[a] = hi - lo + 1;
+    int b = 1;
+    while ((1 << b) < g.dim[a]) b++;
+    g.bits[a] = b;
+    total_bits += b;
+  }
+  if (total_bits > 62) FAIL(c, RGC_ERR_UNSUPPORTED, "voxel grid too large for a 62-bit key (resolution too small for this extent)");
+  const size_t n_sz = (size_t)n;
+  uint64_t* keys_a = (uint64_t*)c->get(8 * n_sz);
+  uint64_t* keys_b = (uint64_t*)c->get(8 * n_sz);
+  uint32_t* vals_a = (uint32_t*)c->get(4 * n_sz);
+  uint32_t* vals_b = (uint32_t*)c->get(4 * n_sz);
+  uint32_t* hist = (uint32_t*)c->get(4 * 256 * ((size_t)div_up(n, RS_TILE) + 1));
+  unsigned int* d_cnt = (unsigned int*)c->get(4);
+  if (!keys_a || !keys_b || !vals_a || !vals_b || !hist || !d_cnt) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (voxel map)");
+  k_vox_keys<<<div_up(n, 256), 256, 0, st>>>(t.sorted, n, g, keys_a, vals_a);
+  CKL(c);
+  uint64_t* ks = keys_a;
+  uint32_t* vs = vals_a;
+  TRY(radix_sort_pairs(c, keys_a, keys_b, vals_a, vals_b, hist, n, total_bits, &ks, &vs));
+  CK(c, cudaMemsetAsync(d_cnt, 0, 4, st));
+  k_vox_count<<<div_up(n, 256), 256, 0, st>>>(ks, n, d_cnt);
+  CKL(c);
+  CK(c, cudaMemcpyAsync(c->h_counts, d_cnt, 4, cudaMemcpyDeviceToHost, st));
+  CK(c, cudaStreamSynchronize(st));
+  const int nv = (int)c->h_counts[0];
+  size_t slots = 8;
+  int lg = 3;
+  while (slots < 2 * (size_t)nv) {
+    slots <<= 1;
+    lg++;
+  }
+  c->put(r->vox_slots);
+  r->vox_slots = (VoxelSlot*)c->get(slots * sizeof(VoxelSlot));
+  if (!r->vox_slots) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (voxel table)");
+  CK(c, cudaMemsetAsync(r->vox_slots, 0xff, slots * sizeof(VoxelSlot), st));
+  k_vox_reduce<<<div_up(n, 128), 128, 0, st>>>(ks, vs, n, t.sorted, t.inv, t.cov, r->vox_mode, r->vox_slots, (uint32_t)(slots - 1), (uint32_t)(64 - lg));
+  CKL(c);
+  r->vox = VoxelMapView{r->vox_slots, (uint32_t)(slots - 1), (uint32_t)(64 - lg), g};
+  r->vox_count = nv;
+  r->vox_valid = true;
+  c->put(keys_a);
+  c->put(keys_b);
+  c->put(vals_a);
+  c->put(vals_b);
+  c->put(hist);
+  c->put(d_cnt);
+  return RGC_OK;
+}
+
+static int vgicp_ensure_work(rgc_reg* r) {
+  rgc_ctx* c = r->ctx;
+  const size_t need = (size_t)r->src.n * vgicp_n_off(r);
+  if (r->vox_cap >= need && r->vox_corr) return RGC_OK;
+  c->put(r->vox_corr);
+  c->put(r->vox_maha);
+  c->put(r->partials);
+  r->vox_corr = (int*)c->get(4 * need);
+  r->vox_maha = (double*)c->get(48 * need);
+  r->partials = (double*)c->get(sizeof(double) * kLinN * (size_t)(148 * 8 + 8));
+  r->cap_src = 0;  // the GICP work buffers (sharing `partials`) must be re-made if that path is used later
+  if (!r->vox_corr || !r->vox_maha || !r->partials) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (vgicp work buffers)");
+  r->vox_cap = need;
+  return RGC_OK;
+}
+
+// FastVGICP::linearize (fast_vgicp_impl.hpp:119-180)
+static int vgicp_linearize(rgc_reg* r, const double* T, double* err, double* H, double* b) {
+  rgc_ctx* c = r->ctx;
+  TRY(vgicp_build(r));
+  TRY(vgicp_ensure_work(r));
+  Rt Td;
+  RtF Tf;
+  to_rt(T, Td, Tf);
+  const int want = (H && b) ? 1 : 0;
+  const int n_off = vgicp_n_off(r);
+  const long long total = (long long)r->src.n * n_off;
+  const int grid = (int)std::min<long long>((total + kThreads - 1) / kThreads, 148 * 8);
+  k_vgicp_linearize<<<grid, kThreads, 0, c->stream>>>(r->vox, r->src.sorted, r->src.cov, r->src.n, r->vox_search, n_off, Td, want, r->vox_corr, r->vox_maha,
+                                                     r->partials, c->d_ticket, reg_result_ptr(r));
+  CKL(c);
+  TRY(reg_finish_reduce(r, kLinN));
+  r->n_linearize++;
+  r->have_corr = true;
+  const double* res = c->h_result;
+  *err = res[0];
+  r->last_inliers = (int)res[kAccN];
+  if (want) {
+    int o = 1;
+    for (int i = 0; i < 6; i++)
+      for (int j = i; j < 6; j++) {
+        H[i * 6 + j] = H[j * 6 + i] = res[o];
+        o++;
+      }
+    for (int i = 0; i < 6; i++) b[i] = res[22 + i];
+  }
+  return RGC_OK;
+}
+
+// FastVGICP::compute_error (fast_vgicp_impl.hpp:183-204)
+static int vgicp_compute_error(rgc_reg* r, const double* T, double* err) {
+  rgc_ctx* c = r->ctx;
+  if (!r->have_corr || !r->vox_valid) FAIL(c, RGC_ERR_STATE, "compute_error before any linearize");
+  Rt Td;
+  RtF Tf;
+  to_rt(T, Td, Tf);
+  const int n_off = vgicp_n_off(r);
+  const long long total = (long long)r->src.n * n_off;
+  const int grid = (int)std::min<long long>((total + kThreads - 1) / kThreads, 148 * 8);
+  k_vgicp_compute_error<<<grid, kThreads, 0, c->stream>>>(r->vox, r->src.sorted, r->src.n, n_off, Td, r->vox_corr, r->vox_maha, r->partials, c->d_ticket,
+                                                         reg_result_ptr(r));
+  CKL(c);
+  TRY(reg_finish_reduce(r, 1));
+  r->n_compute_error++;
+  *err = c->h_result[0];
+  return RGC_OK;
+}
+
 // FastGICP::linearize (fast_gicp_impl.hpp:155-211); H row-major 6x6
 static int reg_linearize(rgc_reg* r, const double* T, double* err, double* H, double* b) {
   rgc_ctx* c = r->ctx;
+  if (r->vgicp) return vgicp_linearize(r, T, err, H, b);
   TRY(reg_ensure_work(r));
   Rt Td;
   RtF Tf;
@@ -366,6 +531,7 @@ static int reg_linearize(rgc_reg* r, const double* T, double* err, double* H, do
 // FastGICP::compute_error (fast_gicp_impl.hpp:214-237)
 static int reg_compute_error(rgc_reg* r, const double* T, double* err) {
   rgc_ctx* c = r->ctx;
+  if (r->vgicp) return vgicp_compute_error(r, T, err);
   if (!r->have_corr) FAIL(c, RGC_ERR_STATE, "compute_error before any linearize");
   Rt Td;
   RtF Tf;
@@ -549,6 +715,9 @@ int rgc_reg_destroy(rgc_reg* r) {
   c->put(r->sqd);
   c->put(r->maha);
   c->put(r->partials);
+  c->put(r->vox_slots);
+  c->put(r->vox_corr);
+  c->put(r->vox_maha);
   delete r;
   return RGC_OK;
 }
@@ -571,6 +740,7 @@ static int set_cloud(rgc_reg* r, Cloud& cl, const void* pts, size_t n, size_t st
   CK(c, cudaSetDevice(c->device));
   if (key != 0 && cl.valid && cl.key == key) return RGC_OK;  // fast_gicp_impl.hpp:73-75 / :84-86
   r->have_corr = false;
+  if (&cl == &r->tgt) r->vox_valid = false;  // FastVGICP::setInputTarget resets the voxel map (fast_vgicp_impl.hpp:57-64)
   return cloud_build(c, cl, pts, n, stride, on_device, key, r->prm.grid_cell);
 }
 int rgc_reg_set_source(rgc_reg* r, const void* p, size_t n, size_t s, uint64_t key) { return r ? set_cloud(r, r->src, p, n, s, key, false) : RGC_ERR_INVALID; }
@@ -582,6 +752,7 @@ int rgc_reg_swap_source_and_target(rgc_reg* r) {
   if (!r) return RGC_ERR_INVALID;
   std::swap(r->src, r->tgt);
   r->have_corr = false;  // correspondences_.clear(); sq_distances_.clear();
+  r->vox_valid = false;  // voxelmap_.reset() (fast_vgicp_impl.hpp:46-54)
   return RGC_OK;
 }
 int rgc_reg_clear_source(rgc_reg* r) {
@@ -594,6 +765,7 @@ int rgc_reg_clear_target(rgc_reg* r) {
   if (!r) return RGC_ERR_INVALID;
   cloud_release(r->ctx, r->tgt);
   r->have_corr = false;
+  r->vox_valid = false;
   return RGC_OK;
 }
 
@@ -611,6 +783,7 @@ static int set_covs(rgc_reg* r, Cloud& cl, const double* m, size_t n) {
   CK(c, cudaStreamSynchronize(c->stream));
   c->put(stage);
   cl.has_cov = true;
+  if (&cl == &r->tgt) r->vox_valid = false;
   return RGC_OK;
 }
 static int get_covs(rgc_reg* r, Cloud& cl, double* m, size_t n) {
@@ -725,6 +898,7 @@ int rgc_reg_get_correspondences(rgc_reg* r, int32_t* corr, float* sq_dist) {
   if (!r || !corr) return RGC_ERR_INVALID;
   rgc_ctx* c = r->ctx;
   CK(c, cudaSetDevice(c->device));
+  if (r->vgicp) FAIL(c, RGC_ERR_UNSUPPORTED, "point correspondences do not exist in voxelised mode");
   if (!r->have_corr) FAIL(c, RGC_ERR_STATE, "no correspondences yet (call linearize or align first)");
   const size_t n = (size_t)r->src.n;
   int* d_c = (int*)c->get(4 * n);
@@ -861,6 +1035,57 @@ int rgc_debug_correspond_stats(rgc_reg* r, const double* T16, long long* stats) 
   CK(c, cudaStreamSynchronize(c->stream));
   c->put(d_stats);
   return rc;
+}
+
+int rgc_reg_last_inliers(const rgc_reg* r, int* n) {
+  if (!r || !n) return RGC_ERR_INVALID;
+  *n = r->last_inliers;
+  return RGC_OK;
+}
+
+int rgc_reg_set_vgicp(rgc_reg* r, int enabled, double resolution, int neighbor_search, int accumulation_mode) {
+  if (!r) return RGC_ERR_INVALID;
+  if (enabled && (!(resolution > 0.0) || neighbor_search < 0 || neighbor_search > 2 || accumulation_mode < 0 || accumulation_mode > 2))
+    FAIL(r->ctx, RGC_ERR_INVALID, "bad voxel parameters");
+  r->vgicp = enabled != 0;
+  r->vox_res = resolution;
+  r->vox_search = neighbor_search;
+  r->vox_mode = accumulation_mode;
+  r->vox_valid = false;
+  r->have_corr = false;
+  return RGC_OK;
+}
+
+int rgc_reg_get_voxels(rgc_reg* r, int32_t* coords3, int32_t* num_points, double* mean3, double* cov6, size_t cap, size_t* n_voxels) {
+  if (!r || !n_voxels) return RGC_ERR_INVALID;
+  rgc_ctx* c = r->ctx;
+  CK(c, cudaSetDevice(c->device));
+  if (!r->vgicp) FAIL(c, RGC_ERR_STATE, "voxelised mode is off (rgc_reg_set_vgicp)");
+  if (!r->tgt.valid) FAIL(c, RGC_ERR_STATE, "no target cloud");
+  TRY(cloud_covariances(c, r->tgt, r->prm.k_correspondences, r->prm.regularization));
+  TRY(vgicp_build(r));
+  *n_voxels = (size_t)r->vox_count;
+  if (!coords3 || cap == 0) return RGC_OK;
+  int *d_c = (int*)c->get(12 * cap), *d_n = (int*)c->get(4 * cap);
+  double *d_m = (double*)c->get(24 * cap), *d_v = (double*)c->get(48 * cap);
+  unsigned int* d_cnt = (unsigned int*)c->get(4);
+  if (!d_c || !d_n || !d_m || !d_v || !d_cnt) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (voxel export)");
+  CK(c, cudaMemsetAsync(d_cnt, 0, 4, c->stream));
+  const uint32_t nslots = r->vox.mask + 1;
+  k_vox_dump<<<div_up((int)nslots, 256), 256, 0, c->stream>>>(r->vox_slots, nslots, r->vox.geom, d_cnt, d_c, d_n, d_m, d_v, (unsigned)cap);
+  CKL(c);
+  const size_t m = std::min(cap, (size_t)r->vox_count);
+  CK(c, cudaMemcpyAsync(coords3, d_c, 12 * m, cudaMemcpyDeviceToHost, c->stream));
+  if (num_points) CK(c, cudaMemcpyAsync(num_points, d_n, 4 * m, cudaMemcpyDeviceToHost, c->stream));
+  if (mean3) CK(c, cudaMemcpyAsync(mean3, d_m, 24 * m, cudaMemcpyDeviceToHost, c->stream));
+  if (cov6) CK(c, cudaMemcpyAsync(cov6, d_v, 48 * m, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  c->put(d_c);
+  c->put(d_n);
+  c->put(d_m);
+  c->put(d_v);
+  c->put(d_cnt);
+  return RGC_OK;
 }
 
 int rgc_reg_set_owner_slab(rgc_reg* r, int axis, float lo, float hi) {

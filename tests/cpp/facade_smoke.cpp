@@ -51,5 +51,19 @@ int main(int argc, char** argv) {
     for (int r = 0; r < 4; r++) std::printf("%.9g %.9g %.9g %.9g\n", T[r], T[4 + r], T[8 + r], T[12 + r]);
     vgicp.setInputTarget(target);  // same shared_ptr: must be a no-op
   }
+  {  // the exact sequence of RGC_odometer.cpp:998-1011, voxelised variant
+    rgc::FastVGICP<PointT, PointT> vgicp;
+    vgicp.setResolution(1);
+    vgicp.setMaximumIterations(25);
+    vgicp.setMaxCorrespondenceDistance(2);
+    vgicp.setTransformationEpsilon(1e-6);
+    vgicp.setNumThreads(14);
+    vgicp.setInputTarget(target);
+    vgicp.setInputSource(source);
+    vgicp.align(aligned, T2);
+    const rgc::Matrix4f& T = vgicp.getFinalTransformation();
+    std::printf("vgicp converged %d iterations %d fitness %.9g\n", (int)vgicp.hasConverged(), vgicp.lastResult().iterations, vgicp.getFitnessScore());
+    for (int r = 0; r < 4; r++) std::printf("%.9g %.9g %.9g %.9g\n", T[r], T[4 + r], T[8 + r], T[12 + r]);
+  }
   return 0;
 }

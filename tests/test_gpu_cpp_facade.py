@@ -33,3 +33,12 @@ def test_cpp_facade_matches_oracle(small_pair, tmp_path):
     assert np.abs(T[:3, 3] - To[:3, 3]).max() < 1e-4 and rot_angle(T[:3, :3], To[:3, :3]) < 1e-5
     assert abs(float(head[5]) - o.getFitnessScore()) < 1e-6 * o.getFitnessScore()
     assert int(head[7]) == len(src) and int(head[9]) == 1
+    # second block: rgc::FastVGICP driven exactly like RGC_odometer.cpp:998-1011
+    vhead = out[5].split()
+    Tv = np.array([[float(v) for v in out[6 + r].split()] for r in range(4)])
+    ov = orc.FastVGICP(resolution=1.0, max_iterations=25, transformation_epsilon=1e-6)
+    ov.setInputTarget(tgt)
+    ov.setInputSource(src)
+    Tov = ov.align()
+    assert vhead[0] == "vgicp" and int(vhead[2]) == int(ov.last["converged"]) and int(vhead[4]) == ov.last["iterations"]
+    assert np.abs(Tv[:3, 3] - Tov[:3, 3]).max() < 1e-4 and rot_angle(Tv[:3, :3], Tov[:3, :3]) < 1e-5
