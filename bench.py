@@ -272,6 +272,40 @@ def run_ours(args, rank, world):
     res = g.last_result
     d2h = 64 + (res["n_linearize"] * 29 + res["n_compute_error"]) * 8 + 296 * 24 * 2 + 22 * 4 * 2
 
+    # ---------------- FastVGICP (what RGC_odometer.cpp:998 instantiates), same workload, cold
+    vg = None
+    if world == 1:
+        def vstep(i):
+            p, cl = pairs[i % len(pairs)], dev[i % len(pairs)]
+            v = rgc.FastVGICP(ctx)
+            v.setResolution(1.0)
+            v.setMaximumIterations(CALL_SITE["max_iterations"])
+            v.setMaxCorrespondenceDistance(CALL_SITE["corr_dist"])
+            v.setTransformationEpsilon(CALL_SITE["transformation_epsilon"])
+            v.setInputTarget(cl["tgt"][:])
+            v.setInputSource(cl["src"][:])
+            return v, v.align(p["guess"])
+        v = None
+        for i in range(3):
+            v = None
+            v, _ = vstep(i)
+        vms = 0.0
+        nv = max(3, min(args.steps, 10))
+        for i in range(nv):
+            with torch.cuda.stream(ext):
+                flush.zero_()
+            ctx.synchronize()
+            v = None
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(ext)
+            v, Tv = vstep(i)
+            e1.record(ext)
+            e1.synchronize()
+            vms += e0.elapsed_time(e1)
+        vg = {"cold_ms_per_align": vms / nv, "aligns_per_s": nv / (vms * 1e-3), "iterations": v.last_result["iterations"],
+              "stage_ms": v.stage_ms(), "params": "resolution 1.0, DIRECT1, ADDITIVE, 25 it, trans_eps 1e-6 (RGC_odometer.cpp:1000-1006)"}
+        v = None
+
     # ---------------- per-kernel roofline (live CUDA-event stage times from the library)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -348,6 +382,7 @@ def run_ours(args, rank, world):
             "roofline": roofline,
             "cpu_baseline": cpu,
             "warm_ms_per_align": warm_ms,
+            "vgicp": vg,
             "stage_ms": st,
             "lm_iterations_mean": float(np.mean(iters)),
             "wall_s_timed_region": wall,
@@ -372,7 +407,16 @@ def cpu_baseline(pairs, n_aligns=2):
         o.setInputSource(p["src"])
         o.align(p["guess"])          # lazy covariances + LM (fast_gicp_impl.hpp:103-112)
         secs.append(time.perf_counter() - t0)
-    return {"value": 1.0 / float(np.mean(secs)), "unit": "aligns/s", "cores": threads, "kind": "port",
+    vsecs = []
+    for i in range(1):
+        p = pairs[i % len(pairs)]
+        ov = orc.FastVGICP(resolution=1.0, max_iterations=CALL_SITE["max_iterations"], transformation_epsilon=CALL_SITE["transformation_epsilon"])
+        t0 = time.perf_counter()
+        ov.setInputTarget(p["tgt"])
+        ov.setInputSource(p["src"])
+        ov.align(p["guess"])
+        vsecs.append(time.perf_counter() - t0)
+    return {"value": 1.0 / float(np.mean(secs)), "unit": "aligns/s", "cores": threads, "kind": "port", "vgicp_aligns_per_s": 1.0 / float(np.mean(vsecs)),
             "sample": f"{n_aligns} cold aligns of the same C2 pairs (sweep vs {len(pairs[0]['tgt'])}-pt submap), OpenMP guided,8 on all "
                       f"{threads} host threads; the reference call site asks for 14 threads (RGC_odometer.cpp:1006)",
             "seconds_per_align": [float(s) for s in secs]}
