@@ -375,14 +375,15 @@ static int vgicp_build(rgc_reg* r) {
   uint32_t* vals_b = (uint32_t*)c->get(4 * n_sz);
   uint32_t* hist = (uint32_t*)c->get(4 * 256 * ((size_t)div_up(n, RS_TILE) + 1));
   unsigned int* d_cnt = (unsigned int*)c->get(4);
-  if (!keys_a || !keys_b || !vals_a || !vals_b || !hist || !d_cnt) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (voxel map)");
+  int* heads = (int*)c->get(4 * n_sz);
+  if (!keys_a || !keys_b || !vals_a || !vals_b || !hist || !d_cnt || !heads) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (voxel map)");
   k_vox_keys<<<div_up(n, 256), 256, 0, st>>>(t.sorted, n, g, keys_a, vals_a);
   CKL(c);
   uint64_t* ks = keys_a;
   uint32_t* vs = vals_a;
   TRY(radix_sort_pairs(c, keys_a, keys_b, vals_a, vals_b, hist, n, total_bits, &ks, &vs));
   CK(c, cudaMemsetAsync(d_cnt, 0, 4, st));
-  k_vox_count<<<div_up(n, 256), 256, 0, st>>>(ks, n, d_cnt);
+  k_vox_count<<<div_up(n, 256), 256, 0, st>>>(ks, n, d_cnt, heads);
   CKL(c);
   CK(c, cudaMemcpyAsync(c->h_counts, d_cnt, 4, cudaMemcpyDeviceToHost, st));
   CK(c, cudaStreamSynchronize(st));
@@ -397,7 +398,8 @@ static int vgicp_build(rgc_reg* r) {
   r->vox_slots = (VoxelSlot*)c->get(slots * sizeof(VoxelSlot));
   if (!r->vox_slots) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (voxel table)");
   CK(c, cudaMemsetAsync(r->vox_slots, 0xff, slots * sizeof(VoxelSlot), st));
-  k_vox_reduce<<<div_up(n, 128), 128, 0, st>>>(ks, vs, n, t.sorted, t.inv, t.cov, r->vox_mode, r->vox_slots, (uint32_t)(slots - 1), (uint32_t)(64 - lg));
+  k_vox_reduce<<<div_up(nv * 32, 128), 128, 0, st>>>(ks, vs, n, heads, nv, t.sorted, t.inv, t.cov, r->vox_mode, r->vox_slots, (uint32_t)(slots - 1),
+                                                     (uint32_t)(64 - lg));
   CKL(c);
   r->vox = VoxelMapView{r->vox_slots, (uint32_t)(slots - 1), (uint32_t)(64 - lg), g};
   r->vox_count = nv;
@@ -408,6 +410,7 @@ static int vgicp_build(rgc_reg* r) {
   c->put(vals_b);
   c->put(hist);
   c->put(d_cnt);
+  c->put(heads);
   return RGC_OK;
 }
 

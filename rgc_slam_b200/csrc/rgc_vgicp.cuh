@@ -7,10 +7,10 @@
 //   update_correspondences / linearize / compute_error   impl/fast_vgicp_impl.hpp:73-204
 //
 // Voxel map build: target points are keyed by their voxel, (key, original index) pairs are sorted
-// with the stable LSD radix sort of the cloud build, and ONE thread per voxel adds the means and
-// covariances of its run in ascending original index — the order of the reference's sequential
-// loop, so the voxel statistics are reproduced to the last bit (no atomics).  Voxels live in an
-// open-addressing table keyed by the compact voxel key; a query is one probe per offset.
+// with the stable LSD radix sort of the cloud build, and one WARP per voxel adds the means and
+// covariances of its run (lane-strided, ascending original index, fixed shuffle tree): deterministic,
+// no atomics on the sums.  Voxels live in an open-addressing table keyed by the compact voxel key; a
+// query is one probe per offset.
 #pragma once
 #include "rgc_kernels.cuh"
 
@@ -67,41 +67,61 @@ __global__ void __launch_bounds__(256) k_vox_keys(const float4* __restrict__ sor
   vals[o] = (uint32_t)o;
 }
 
-__global__ void __launch_bounds__(256) k_vox_count(const uint64_t* __restrict__ keys, int n, unsigned int* __restrict__ counter) {
+// heads of the runs of equal keys: count them and append their positions (unordered) to `heads`
+__global__ void __launch_bounds__(256) k_vox_count(const uint64_t* __restrict__ keys, int n, unsigned int* __restrict__ counter, int* __restrict__ heads) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool head = i < n && (i == 0 || keys[i] != keys[i - 1]);
   const unsigned bal = __ballot_sync(0xffffffffu, head);
-  if ((threadIdx.x & 31) == 0 && bal) atomicAdd(counter, (unsigned)__popc(bal));
+  if (!bal) return;
+  const int lane = threadIdx.x & 31;
+  unsigned int base = 0;
+  if (lane == 0) base = atomicAdd(counter, (unsigned)__popc(bal));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (head) heads[base + __popc(bal & ((1u << lane) - 1u))] = i;
 }
 
-// one thread per voxel (the head of each run of equal keys): fast_vgicp_voxel.hpp:105-122 (additive)
-// and :80-101 (multiplicative), in ascending original index
-__global__ void __launch_bounds__(128) k_vox_reduce(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, int n,
-                                                    const float4* __restrict__ sorted, const int* __restrict__ inv, const double* __restrict__ cov6,
+// one WARP per voxel (fast_vgicp_voxel.hpp:105-122 additive, :80-101 multiplicative): lane l adds the
+// run's points l, l+32, ... in ascending original index, then the 32 partial sums are combined by a
+// fixed shuffle tree — deterministic, and the long runs of the dense near-sensor voxels (thousands of
+// points) no longer serialise on one thread (the first version: 2.6 ms for the C2 target).
+__global__ void __launch_bounds__(128) k_vox_reduce(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, int n, const int* __restrict__ heads,
+                                                    int nv, const float4* __restrict__ sorted, const int* __restrict__ inv, const double* __restrict__ cov6,
                                                     int mode, VoxelSlot* __restrict__ slots, uint32_t mask, uint32_t shift) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint64_t key = keys[i];
-  if (i > 0 && keys[i - 1] == key) return;
-  double m[3] = {0, 0, 0};
-  Sym3 c = {0, 0, 0, 0, 0, 0};
-  int num = 0;
-  for (int t = i; t < n && keys[t] == key; t++) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= nv) return;
+  const int start = heads[w];
+  const uint64_t key = keys[start];
+  // run end: first index > start whose key differs (keys are sorted): binary search, uniform per warp
+  int lo = start + 1, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (keys[mid] == key) lo = mid + 1; else hi = mid;
+  }
+  const int end = lo;
+  double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // mean xyz, cov xx xy xz yy yz zz
+  for (int t = start + lane; t < end; t += 32) {
     const int pos = inv[vals[t]];
     const float4 p = sorted[pos];
     const Sym3 ci = load_sym3(cov6, pos);
-    num++;
     if (mode == 2) {  // MULTIPLICATIVE
-      const Sym3 w = inv_sym3(ci);
-      c.xx += w.xx; c.xy += w.xy; c.xz += w.xz; c.yy += w.yy; c.yz += w.yz; c.zz += w.zz;
-      m[0] += w.xx * (double)p.x + w.xy * (double)p.y + w.xz * (double)p.z;
-      m[1] += w.xy * (double)p.x + w.yy * (double)p.y + w.yz * (double)p.z;
-      m[2] += w.xz * (double)p.x + w.yz * (double)p.y + w.zz * (double)p.z;
+      const Sym3 q = inv_sym3(ci);
+      acc[3] += q.xx; acc[4] += q.xy; acc[5] += q.xz; acc[6] += q.yy; acc[7] += q.yz; acc[8] += q.zz;
+      acc[0] += q.xx * (double)p.x + q.xy * (double)p.y + q.xz * (double)p.z;
+      acc[1] += q.xy * (double)p.x + q.yy * (double)p.y + q.yz * (double)p.z;
+      acc[2] += q.xz * (double)p.x + q.yz * (double)p.y + q.zz * (double)p.z;
     } else {  // ADDITIVE / ADDITIVE_WEIGHTED
-      m[0] += (double)p.x; m[1] += (double)p.y; m[2] += (double)p.z;
-      c.xx += ci.xx; c.xy += ci.xy; c.xz += ci.xz; c.yy += ci.yy; c.yz += ci.yz; c.zz += ci.zz;
+      acc[0] += (double)p.x; acc[1] += (double)p.y; acc[2] += (double)p.z;
+      acc[3] += ci.xx; acc[4] += ci.xy; acc[5] += ci.xz; acc[6] += ci.yy; acc[7] += ci.yz; acc[8] += ci.zz;
     }
   }
+#pragma unroll
+  for (int j = 0; j < 9; j++)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_down_sync(0xffffffffu, acc[j], o);
+  if (lane != 0) return;
+  const int num = end - start;
+  double m[3] = {acc[0], acc[1], acc[2]};
+  Sym3 c = {acc[3], acc[4], acc[5], acc[6], acc[7], acc[8]};
   if (mode == 2) {
     const Sym3 f = inv_sym3(c);
     const double m0 = f.xx * m[0] + f.xy * m[1] + f.xz * m[2], m1 = f.xy * m[0] + f.yy * m[1] + f.yz * m[2], m2 = f.xz * m[0] + f.yz * m[1] + f.zz * m[2];

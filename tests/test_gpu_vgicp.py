@@ -24,7 +24,7 @@ def test_voxel_map_matches_oracle(small_pair, mode):
     assert np.array_equal(coords, oc) and np.array_equal(num, on)      # voxel keys and populations: bit-exact
     assert np.abs(mean - om).max() <= 1e-9 * max(1.0, np.abs(om).max())
     assert np.abs(cov - ov).max() <= 1e-8 * np.abs(ov).max()
-    if mode == 0:  # additive sums run in the reference's order on exactly representable inputs
+    if mode == 0:  # additive sums: same terms, different (fixed) order
         assert np.abs(mean - om).max() <= 1e-12 * max(1.0, np.abs(om).max())
 
 
