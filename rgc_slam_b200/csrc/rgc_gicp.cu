@@ -242,7 +242,9 @@ static int launch_knn_self(rgc_ctx* c, const GridView& v, int n, int k, int* nbr
   const size_t per_warp = sizeof(float4) * KT_CAND + sizeof(TileNode) * KT_STACK + (size_t)(k + KT_PEND) * 32 * 8;
   const size_t smem = per_warp * KT_WARPS;
   CK(c, cudaFuncSetAttribute(k_knn_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_knn_tile<<<div_up(n, KT_WARPS * 32), KT_WARPS * 32, smem, c->stream>>>(v, n, k, nbr);
+  // more seeds pay off on a single sweep (sparse rings: tighter start bounds), fewer on dense maps (sweep in profiles/README.md)
+  const int n_seeds = n < 100000 ? KT_SEEDS : (KT_SEEDS > 64 ? 64 : KT_SEEDS);
+  k_knn_tile<<<div_up(n, KT_WARPS * 32), KT_WARPS * 32, smem, c->stream>>>(v, n, k, n_seeds, nbr);
   CKL(c);
   return RGC_OK;
 }

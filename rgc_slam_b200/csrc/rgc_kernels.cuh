@@ -378,7 +378,7 @@ __device__ __forceinline__ float warp_min(float v) {
   return v;
 }
 
-__global__ void __launch_bounds__(KT_WARPS * 32) k_knn_tile(GridView g, int n, int k, int* __restrict__ out_idx) {
+__global__ void __launch_bounds__(KT_WARPS * 32) k_knn_tile(GridView g, int n, int k, int n_seeds, int* __restrict__ out_idx) {
   extern __shared__ __align__(16) unsigned char tile_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long dbg_t0 = clock64();
@@ -401,17 +401,12 @@ __global__ void __launch_bounds__(KT_WARPS * 32) k_knn_tile(GridView g, int n, i
   heap.init(hk + lane, 32, k);
   int npend = 0;
 
-  // ---- seeds: Morton neighbours of the tile, folded in lockstep
-  const int ns = min(KT_SEEDS, n);
-  const int s0 = max(0, min(first - (KT_SEEDS - 32) / 2, n - ns));
+  // ---- seeds: the Morton neighbours of the tile go through the same append / fold path as every
+  // other candidate (the first k fill the heap, later ones are appended only if they beat the
+  // current k-th best), which gives every lane a tight bound before any tree node is touched
+  const int ns = min(n_seeds, n);
+  const int s0 = max(0, min(first - (n_seeds - 32) / 2, n - ns));
   for (int j = lane; j < ns; j += 32) cand[j] = pts4[s0 + j];
-  __syncwarp();
-  for (int j = 0; j < ns; j++) {
-    const float4 c = cand[j];
-    heap.insert(pack_key(dist2_ref(q.x, q.y, q.z, c.x, c.y, c.z), __float_as_int(c.w)));
-  }
-  __syncwarp();
-
   auto fold = [&]() {
     const int mx = __reduce_max_sync(0xffffffffu, npend);
     for (int e = 0; e < mx; e++)
@@ -419,6 +414,25 @@ __global__ void __launch_bounds__(KT_WARPS * 32) k_knn_tile(GridView g, int n, i
     dbg_ins += mx;
     npend = 0;
   };
+  {
+    __syncwarp();
+    unsigned long long bk = ~0ull;
+    for (int j = 0; j < ns; j++) {
+      const float4 c = cand[j];
+      const unsigned long long key = pack_key(dist2_ref(q.x, q.y, q.z, c.x, c.y, c.z), __float_as_int(c.w));
+      if (key < bk) {
+        hk[(k + npend) * 32 + lane] = key;
+        npend++;
+      }
+      if (__any_sync(0xffffffffu, npend == KT_PEND)) {
+        fold();
+        bk = heap.cnt == k ? hk[lane] : ~0ull;
+      }
+    }
+    fold();
+    __syncwarp();
+  }
+
   // ---- geometric cap: the smallest cell around q that holds >= k points bounds the k-th distance
   // by its diagonal.  Lanes whose Morton neighbours lie across a Z-curve jump get a loose bound from
   // the seeds (per-warp stats showed 1 % of the tiles gathering 10-40x the usual candidates because
