@@ -2,6 +2,7 @@
 // (device, stream, pooled device memory, pinned result buffers) and the error-handling macros.
 #pragma once
 #include <cuda_runtime.h>
+#include <cstdlib>
 
 #include <cstdint>
 #include <map>
@@ -28,6 +29,7 @@ struct rgc_ctx {
   cudaEvent_t ev[8];
   cudaEvent_t evk[4];       // per-kernel timing of the last linearize / compute_error (profiling only)
   bool profile = false;     // rgc_ctx_set_profiling
+  int knn_defer = std::getenv("RGC_KNN_DEFER") ? std::atoi(std::getenv("RGC_KNN_DEFER")) : 600;  // rgc_debug_set_knn_defer
   float last_kernel_ms[3] = {0, 0, 0};  // k_correspond, k_linearize, k_compute_error
 
   void* get(size_t bytes) {

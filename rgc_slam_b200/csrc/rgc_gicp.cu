@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <cfloat>
+#include <climits>
 #include <chrono>
 #include <cstdlib>
 #include <cstdio>
@@ -244,8 +245,20 @@ static int launch_knn_self(rgc_ctx* c, const GridView& v, int n, int k, int* nbr
   CK(c, cudaFuncSetAttribute(k_knn_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // more seeds pay off on a single sweep (sparse rings: tighter start bounds), fewer on dense maps (sweep in profiles/README.md)
   const int n_seeds = n < 100000 ? KT_SEEDS : (KT_SEEDS > 64 ? 64 : KT_SEEDS);
-  k_knn_tile<<<div_up(n, KT_WARPS * 32), KT_WARPS * 32, smem, c->stream>>>(v, n, k, n_seeds, nbr);
+  // tiles that gather more than `defer` candidates are finished by k_knn_warp (one warp per query):
+  // they are the sparse-region tiles that used to form a 40 % tail of this launch (profiles/README.md)
+  const int defer = c->knn_defer > 0 ? c->knn_defer : INT_MAX;
+  const int ntiles = div_up(n, 32);
+  int* dq = (int*)c->get(sizeof(int) * (size_t)(ntiles + 1));  // [0] = count, [1..] = tile ids
+  if (!dq) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (knn defer list)");
+  CK(c, cudaMemsetAsync(dq, 0, sizeof(int), c->stream));
+  k_knn_tile<<<div_up(n, KT_WARPS * 32), KT_WARPS * 32, smem, c->stream>>>(v, n, k, n_seeds, defer, dq, dq + 1, nbr);
   CKL(c);
+  if (defer != INT_MAX) {
+    k_knn_warp<<<std::min(div_up(n, KW_WARPS), 148 * 4), KW_WARPS * 32, 0, c->stream>>>(v, n, k, dq, dq + 1, nbr);
+    CKL(c);
+  }
+  c->put(dq);
   return RGC_OK;
 }
 
@@ -992,6 +1005,14 @@ int rgc_knn_self(rgc_ctx* c, const void* points, size_t n, size_t stride, int k,
   c->put(nbr);
   c->put(d_idx);
   cloud_release(c, cl);
+  return RGC_OK;
+}
+
+// debug aid: candidate count above which the tile kNN hands a tile to the warp-per-query kernel
+// (<= 0: never); the default comes from RGC_KNN_DEFER or 600
+int rgc_debug_set_knn_defer(rgc_ctx* c, int cands) {
+  if (!c) return RGC_ERR_INVALID;
+  c->knn_defer = cands;
   return RGC_OK;
 }
 

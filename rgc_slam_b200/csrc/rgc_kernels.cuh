@@ -378,10 +378,13 @@ __device__ __forceinline__ float warp_min(float v) {
   return v;
 }
 
-__global__ void __launch_bounds__(KT_WARPS * 32) k_knn_tile(GridView g, int n, int k, int n_seeds, int* __restrict__ out_idx) {
+__global__ void __launch_bounds__(KT_WARPS * 32) k_knn_tile(GridView g, int n, int k, int n_seeds, int defer_cands, int* __restrict__ defer_count, int* __restrict__ defer_tiles,
+                                                           int* __restrict__ out_idx) {
   extern __shared__ __align__(16) unsigned char tile_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long dbg_t0 = clock64();
+  unsigned long long dbg_g0 = 0;
+  if (g_tile_dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_g0));
   int dbg_nodes = 0, dbg_cands = 0, dbg_ins = 0;
   const int cap = k + KT_PEND;
   // per-warp carve-up: candidate buffer | DFS stack | [cap][32] packed heap / pending keys
@@ -531,6 +534,22 @@ __global__ void __launch_bounds__(KT_WARPS * 32) k_knn_tile(GridView g, int n, i
       __syncwarp();
       // ---- depth-first walk of everything pushed so far
       while (sp > 0) {
+        if (dbg_cands > defer_cands) {
+          // this tile's queries do not share a neighbourhood (sparse region: the union of the 32
+          // balls keeps growing); hand it to k_knn_warp, one warp per query, instead of becoming
+          // the tail of this launch
+          if (lane == 0) {
+            defer_tiles[atomicAdd(defer_count, 1)] = first / 32;
+            if (g_tile_dbg) {
+              long long* o = g_tile_dbg + (size_t)(first / 32) * 4;
+              o[0] = clock64() - dbg_t0;
+              o[1] = dbg_nodes;
+              o[2] = (long long)dbg_cands | (1ll << 40);
+              o[3] = (long long)dbg_ins | ((long long)((dbg_g0 >> 6) & 0x3fffffff) << 32);
+            }
+          }
+          return;
+        }
         const TileNode nd = stack[--sp];
         __syncwarp();
         dbg_nodes++;
@@ -575,10 +594,209 @@ __global__ void __launch_bounds__(KT_WARPS * 32) k_knn_tile(GridView g, int n, i
     for (int j = 0; j < k; j++) out_idx[(size_t)j * n + t] = j < heap.cnt ? __ldg(&g.inv[(unsigned)(hk[j * 32 + lane] & 0xffffffffull)]) : -1;
   if (g_tile_dbg && lane == 0) {
     long long* o = g_tile_dbg + (size_t)(first / 32) * 4;
+    // level of the smallest cell holding the whole tile, and the launch-relative start time
+    const float4 pa = pts4[first], pb = pts4[min(first + 31, n - 1)];
+    const uint64_t ma = morton3(cell_coord(pa.x, g.ox, g.inv_s0), cell_coord(pa.y, g.oy, g.inv_s0), cell_coord(pa.z, g.oz, g.inv_s0));
+    const uint64_t mb = morton3(cell_coord(pb.x, g.ox, g.inv_s0), cell_coord(pb.y, g.oy, g.inv_s0), cell_coord(pb.z, g.oz, g.inv_s0));
+    const int lca = ma == mb ? 0 : (63 - __clzll((long long)(ma ^ mb))) / 3 + 1;
     o[0] = clock64() - dbg_t0;
-    o[1] = dbg_nodes;
+    o[1] = (long long)dbg_nodes | ((long long)lca << 40);
     o[2] = dbg_cands;
-    o[3] = dbg_ins;
+    o[3] = (long long)dbg_ins | ((long long)((dbg_g0 >> 6) & 0x3fffffff) << 32);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// One warp per query, for the tiles k_knn_tile deferred (k <= 32).  The k best keys live in
+// registers, lane j holding the j-th smallest; candidates are tested 32 at a time and the few that
+// pass are inserted with a ballot (rank) and one shuffle (shift).  Tree nodes are expanded with
+// lanes 0-7 probing the eight children in parallel.  Same keys, same distance arithmetic, same
+// conservative box test as the tile kernel, hence the same neighbour lists.
+constexpr int KW_WARPS = 8;
+constexpr int KW_STACK = 64;
+constexpr int KW_LEAF = 64;
+constexpr int KW_SEEDS = 64;
+
+__device__ __forceinline__ unsigned long long shfl64(unsigned long long v, int src) {
+  return ((unsigned long long)__shfl_sync(0xffffffffu, (unsigned)(v >> 32), src) << 32) | __shfl_sync(0xffffffffu, (unsigned)v, src);
+}
+__device__ __forceinline__ unsigned long long shfl64_up1(unsigned long long v) {
+  return ((unsigned long long)__shfl_up_sync(0xffffffffu, (unsigned)(v >> 32), 1) << 32) | __shfl_up_sync(0xffffffffu, (unsigned)v, 1);
+}
+
+__global__ void __launch_bounds__(KW_WARPS * 32) k_knn_warp(GridView g, int n, int k, const int* __restrict__ defer_count, const int* __restrict__ defer_tiles,
+                                                           int* __restrict__ out_idx) {
+  __shared__ TileNode stacks[KW_WARPS][KW_STACK];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  TileNode* stack = stacks[warp];
+  const float4* pts4 = reinterpret_cast<const float4*>(g.pts);
+  const int nq = *defer_count * 32;
+  for (int w = blockIdx.x * KW_WARPS + warp; w < nq; w += gridDim.x * KW_WARPS) {
+    const int t = defer_tiles[w >> 5] * 32 + (w & 31);
+    if (t >= n) continue;
+    const float4 q = pts4[t];
+    unsigned long long mine = ~0ull;  // lane j: j-th smallest key so far (~0 = empty)
+    unsigned long long capk = ~0ull;
+    float cap2 = INFINITY;
+    auto offer = [&](unsigned long long ck, bool valid) {
+      unsigned long long wk = shfl64(mine, k - 1);
+      unsigned acc = __ballot_sync(0xffffffffu, valid && ck < wk && ck <= capk);
+      while (acc) {
+        const int src = __ffs(acc) - 1;
+        const unsigned long long nk = shfl64(ck, src);
+        const int pos = __popc(__ballot_sync(0xffffffffu, mine < nk));
+        const unsigned long long up = shfl64_up1(mine);
+        if (lane == pos) mine = nk;
+        else if (lane > pos) mine = up;
+        wk = shfl64(mine, k - 1);
+        acc &= acc - 1;
+        acc &= __ballot_sync(0xffffffffu, ck < wk);
+      }
+    };
+    auto bound = [&]() {
+      const unsigned long long wk = shfl64(mine, k - 1);
+      return fminf(wk == ~0ull ? INFINITY : key_d2(wk), cap2);
+    };
+    // seeds: Morton neighbours of the query
+    const int ns = min(KW_SEEDS, n);
+    const int s0 = max(0, min(t - KW_SEEDS / 2, n - ns));
+    for (int j0 = 0; j0 < ns; j0 += 32) {
+      const bool take = j0 + lane < ns;
+      unsigned long long key = ~0ull;
+      if (take) {
+        const float4 c = pts4[s0 + j0 + lane];
+        key = pack_key(dist2_ref(q.x, q.y, q.z, c.x, c.y, c.z), __float_as_int(c.w));
+      }
+      offer(key, take);
+    }
+    if (n > ns) {
+      // geometric cap (see k_knn_tile): lane l probes the level-l cell of the query
+      {
+        const int fx = cell_coord(q.x, g.ox, g.inv_s0), fy = cell_coord(q.y, g.oy, g.inv_s0), fz = cell_coord(q.z, g.oz, g.inv_s0);
+        bool enough = false;
+        if (lane < g.nlevels) {
+          uint32_t s, e, m;
+          enough = grid_lookup(g, lane, fx >> lane, fy >> lane, fz >> lane, s, e, m) && (int)(e - s) >= k;
+        }
+        const unsigned hit = __ballot_sync(0xffffffffu, enough);
+        if (hit) {
+          const int l = __ffs(hit) - 1;
+          const float edge = g.s0 * (float)(1 << l) + 2.f * g.margin;
+          cap2 = 3.f * edge * edge * 1.0001f;
+          capk = pack_key(cap2, 0x7fffffff);
+        }
+      }
+      const float b0 = bound();
+      const float r = b0 < INFINITY ? sqrtf(b0) * 1.00001f + 2.f * g.margin : INFINITY;
+      const int top_level = g.nlevels - 1;
+      int lb = 0;
+      while (lb < top_level && !(g.s0 * (float)(1 << lb) >= r)) lb++;
+      const float inv_cs = g.inv_s0 / (float)(1 << lb);
+      const int ncell = 1 << (g.nbits - lb);
+      int rlo[3], rhi[3];
+      {
+        const float q3[3] = {q.x, q.y, q.z}, o3[3] = {g.ox, g.oy, g.oz};
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+          const float tl = (q3[a] - r - o3[a]) * inv_cs, th = (q3[a] + r - o3[a]) * inv_cs;
+          const int il = !(tl >= 0.f) ? 0 : (tl >= (float)ncell ? ncell : (int)tl);
+          const int ih = !(th >= 0.f) ? (th != th || r == INFINITY ? ncell - 1 : -1) : (th >= (float)ncell ? ncell - 1 : (int)th);
+          rlo[a] = il;
+          rhi[a] = ih < ncell - 1 ? ih : ncell - 1;
+          if (ih < 0 || il >= ncell) rhi[a] = rlo[a] - 1;
+        }
+      }
+      const int nx = rhi[0] - rlo[0] + 1, ny = rhi[1] - rlo[1] + 1, nz = rhi[2] - rlo[2] + 1;
+      const int nroots = (nx > 0 && ny > 0 && nz > 0) ? nx * ny * nz : 0;
+      int sp = 0;
+      for (int r0 = 0; r0 < nroots; r0 += 32) {
+        const int ri = r0 + lane;
+        uint32_t s = 0, e = 0, m = 0;
+        int rx = 0, ry = 0, rz = 0;
+        bool have = false;
+        if (ri < nroots) {
+          rx = rlo[0] + ri % nx;
+          ry = rlo[1] + (ri / nx) % ny;
+          rz = rlo[2] + ri / (nx * ny);
+          have = grid_lookup(g, lb, rx, ry, rz, s, e, m);
+        }
+        const float bnd = bound();
+        have = have && box_dist2(g, lb, rx, ry, rz, q.x, q.y, q.z) <= bnd;
+        const unsigned hv = __ballot_sync(0xffffffffu, have);
+        const int room = KW_STACK - sp;
+        const int slot = __popc(hv & ((1u << lane) - 1u));
+        if (have && slot < room) stack[sp + slot] = TileNode{(uint32_t)rx | ((uint32_t)lb << 24), (uint32_t)ry | (m << 24), (uint32_t)rz, s, e};
+        const int pushed = min(__popc(hv), room);
+        // roots that do not fit on the stack (cannot happen for nroots <= 27 unless a previous
+        // batch left entries) are scanned directly
+        unsigned over = hv;
+        for (int i = 0; i < pushed; i++) over &= over - 1;
+        sp += pushed;
+        __syncwarp();
+        while (over) {
+          const int src = __ffs(over) - 1;
+          over &= over - 1;
+          const uint32_t os = __shfl_sync(0xffffffffu, s, src), oe = __shfl_sync(0xffffffffu, e, src);
+          for (uint32_t p0 = os; p0 < oe; p0 += 32) {
+            const uint32_t p = p0 + lane;
+            const bool take = p < oe && (uint32_t)((int)p - s0) >= (uint32_t)ns;
+            unsigned long long key = ~0ull;
+            if (take) {
+              const float4 c = pts4[p];
+              key = pack_key(dist2_ref(q.x, q.y, q.z, c.x, c.y, c.z), __float_as_int(c.w));
+            }
+            offer(key, take);
+          }
+        }
+        while (sp > 0) {
+          const TileNode nd = stack[--sp];
+          __syncwarp();
+          const int l = (int)(nd.cx_lvl >> 24);
+          const int cx = (int)(nd.cx_lvl & 0xffffffu), cy = (int)(nd.cy_mask & 0xffffffu), cz = (int)nd.cz;
+          const uint32_t cm = nd.cy_mask >> 24;
+          const float bd = bound();
+          if (!(box_dist2(g, l, cx, cy, cz, q.x, q.y, q.z) <= bd)) continue;
+          if (l == 0 || nd.end - nd.start <= (uint32_t)KW_LEAF || sp + 8 > KW_STACK) {
+            for (uint32_t p0 = nd.start; p0 < nd.end; p0 += 32) {
+              const uint32_t p = p0 + lane;
+              const bool take = p < nd.end && (uint32_t)((int)p - s0) >= (uint32_t)ns;
+              unsigned long long key = ~0ull;
+              if (take) {
+                const float4 c = pts4[p];
+                key = pack_key(dist2_ref(q.x, q.y, q.z, c.x, c.y, c.z), __float_as_int(c.w));
+              }
+              offer(key, take);
+            }
+            continue;
+          }
+          // expand: lane c < 8 resolves and tests child c; the survivors are pushed farthest first
+          const uint64_t pkey = morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz) << 3;
+          uint32_t cs = 0, ce = 0, cmk = 0;
+          bool hc = false;
+          float dc = INFINITY;
+          const int ccx = 2 * cx + (lane & 1), ccy = 2 * cy + ((lane >> 1) & 1), ccz = 2 * cz + ((lane >> 2) & 1);
+          if (lane < 8 && ((cm >> lane) & 1u)) {
+            hc = grid_lookup_key(g, l - 1, pkey | (uint64_t)lane, cs, ce, cmk);
+            if (hc) {
+              dc = box_dist2(g, l - 1, ccx, ccy, ccz, q.x, q.y, q.z);
+              hc = dc <= bd;
+            }
+          }
+          const unsigned hvc = __ballot_sync(0xffffffffu, hc);
+          int rank = 0;
+#pragma unroll
+          for (int c = 0; c < 8; c++) {
+            const float dother = __shfl_sync(0xffffffffu, dc, c);
+            if (((hvc >> c) & 1u) && (dother > dc || (dother == dc && c < lane))) rank++;
+          }
+          if (hc) stack[sp + rank] = TileNode{(uint32_t)ccx | ((uint32_t)(l - 1) << 24), (uint32_t)ccy | (cmk << 24), (uint32_t)ccz, cs, ce};
+          sp += __popc(hvc);
+          __syncwarp();
+        }
+      }
+    }
+    if (lane < k) out_idx[(size_t)lane * n + t] = mine != ~0ull ? __ldg(&g.inv[(unsigned)(mine & 0xffffffffull)]) : -1;
+    __syncwarp();
   }
 }
 

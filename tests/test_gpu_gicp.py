@@ -41,9 +41,27 @@ def test_knn_bitexact_self(rgc, orc, scan_pair, k):
     assert np.array_equal(d2, od)
 
 
+@pytest.fixture
+def knn_defer(rgc):
+    """sets the candidate count at which the tile kernel hands a tile to the warp-per-query kernel"""
+    import ctypes as C
+    from rgc_slam_b200 import api
+    L = api.lib()
+    L.rgc_debug_set_knn_defer.argtypes = [C.c_void_p, C.c_int]
+    ctx = api.default_context()
+
+    def set_(v):
+        ctx.check(L.rgc_debug_set_knn_defer(ctx._h, v))
+    yield set_
+    set_(600)
+
+
+@pytest.mark.parametrize("defer", [600, 1, 40, 0])
 @pytest.mark.parametrize("k", [1, 7, 20, 32])
-def test_knn_self_tile_kernel_bitexact(rgc, orc, scan_pair, k):
-    """the production self-kNN (warp-cooperative tile kernel used by calculate_covariances)"""
+def test_knn_self_tile_kernel_bitexact(rgc, orc, scan_pair, k, defer, knn_defer):
+    """the production self-kNN (warp-cooperative tile kernel used by calculate_covariances);
+    defer=1 sends nearly every tile through the warp-per-query kernel, 0 none"""
+    knn_defer(defer)
     src, tgt, _ = scan_pair
     for cloud in (tgt, src[:1000], src[:33], src[:5]):
         idx = rgc.knn_self(cloud, k)

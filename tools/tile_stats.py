@@ -14,7 +14,14 @@ for name in ("tgt", "src"):
     st = np.zeros((nw, 4), np.int64)
     for rep in range(2):
         ctx.check(L.rgc_debug_tile_stats(ctx._h, P.ctypes.data, len(P), 16, 20, st.ctypes.data, 0.0))
-    cyc, nodes, cands, ins = st.T
+    cyc, nodes, cands, ins = st.T.copy()
+    lca = nodes >> 40
+    nodes = nodes & ((1 << 40) - 1)
+    start = (ins >> 32) * 64e-3  # us
+    start = start - start.min()
+    ins = ins & 0xffffffff
+    os.makedirs("gpurun_out", exist_ok=True)
+    np.savez_compressed(f"gpurun_out/tile_stats_{name}.npz", cyc=cyc, nodes=nodes, cands=cands, ins=ins, lca=lca, start=start)
     print(name, "warps", nw)
     for nm, v in (("cycles", cyc), ("nodes", nodes), ("cands", cands), ("fold steps", ins)):
         print(f"  {nm:10s} mean {v.mean():10.1f} p50 {np.percentile(v,50):10.0f} p90 {np.percentile(v,90):10.0f} p99 {np.percentile(v,99):10.0f} max {v.max():10d} sum {v.sum():14d}")
