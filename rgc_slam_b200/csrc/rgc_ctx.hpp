@@ -8,6 +8,8 @@
 #include <map>
 #include <string>
 #include <unordered_map>
+#include <utility>
+#include <vector>
 
 #include "../../include/rgc_gicp.h"
 
@@ -17,9 +19,29 @@ struct rgc_ctx {
   cudaStream_t stream = nullptr;
   std::string err;
   uint64_t launches = 0;
-  // pooled device memory: power-of-two size classes, never returned to the driver before destroy
+  // pooled device memory: power-of-two size classes, never returned to the driver before destroy.
+  // The context has two LANES (stream + block pool + pinned scratch): lane 0 is the main stream,
+  // lane 1 carries the source-cloud preparation so that it overlaps the (much larger) target-cloud
+  // preparation.  `stream`, `free_blocks`, `h_bbox`, `h_counts` always describe the CURRENT lane;
+  // the other lane's copies are parked in `parked`.  A block always returns to the pool of the
+  // lane that allocated it, so a pool's blocks are only ever reused in that lane's stream order.
   std::multimap<size_t, void*> free_blocks;
-  std::unordered_map<void*, size_t> block_size;
+  struct BlockInfo {
+    size_t size;
+    int lane;
+  };
+  std::unordered_map<void*, BlockInfo> block_info;
+  struct Parked {
+    cudaStream_t stream = nullptr;
+    std::multimap<size_t, void*> free_blocks;
+    float* h_bbox = nullptr;
+    uint32_t* h_counts = nullptr;
+  } parked;
+  int lane = 0;
+  cudaEvent_t join_ev = nullptr;  // end of the last lane-1 work
+  bool side_pending = false;      // lane-1 work not yet joined into the main stream
+  bool overlap = std::getenv("RGC_NO_OVERLAP") == nullptr;
+  std::vector<cudaEvent_t> free_events;
   // pinned, device-mapped result area the reduction kernels write straight into
   double* h_result = nullptr;
   double* d_result = nullptr;  // device alias of h_result
@@ -32,6 +54,14 @@ struct rgc_ctx {
   int knn_defer = std::getenv("RGC_KNN_DEFER") ? std::atoi(std::getenv("RGC_KNN_DEFER")) : 600;  // rgc_debug_set_knn_defer
   float last_kernel_ms[3] = {0, 0, 0};  // k_correspond, k_linearize, k_compute_error
 
+  void switch_lane(int to) {
+    if (to == lane) return;
+    std::swap(stream, parked.stream);
+    std::swap(free_blocks, parked.free_blocks);
+    std::swap(h_bbox, parked.h_bbox);
+    std::swap(h_counts, parked.h_counts);
+    lane = to;
+  }
   void* get(size_t bytes) {
     size_t cls = 4096;
     while (cls < bytes) cls <<= 1;
@@ -46,12 +76,29 @@ struct rgc_ctx {
       cudaGetLastError();
       return nullptr;
     }
-    block_size[p] = cls;
+    block_info[p] = BlockInfo{cls, lane};
     return p;
   }
   void put(void* p) {
     if (!p) return;
-    free_blocks.insert({block_size[p], p});
+    const BlockInfo bi = block_info[p];
+    (bi.lane == lane ? free_blocks : parked.free_blocks).insert({bi.size, p});
+  }
+  cudaEvent_t get_event() {
+    if (!free_events.empty()) {
+      cudaEvent_t e = free_events.back();
+      free_events.pop_back();
+      return e;
+    }
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    return e;
+  }
+  void put_event(cudaEvent_t e) {
+    if (e) free_events.push_back(e);
   }
 };
 

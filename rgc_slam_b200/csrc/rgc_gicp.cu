@@ -51,15 +51,57 @@ struct Cloud {
   GridView view{};
   double* cov = nullptr;  // 6 doubles per sorted point
   bool has_cov = false;
+  bool cov_speculative = false;  // computed at set_input time, before any align has used them
+  int cov_k = 0, cov_method = 0;
   float build_ms = 0, knn_ms = 0, cov_ms = 0;
   float bb_min[3] = {0, 0, 0}, bb_max[3] = {0, 0, 0};
+  // stage timing: build begin / end, kNN begin, kNN end (= covariance begin), covariance end.
+  // Read back lazily (cloud_times) so that nothing here makes the host wait for the device.
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool build_timed = false, cov_timed = false;
 };
+
+static void cloud_times(Cloud& cl) {
+  if (!cl.valid) return;
+  if (cl.build_timed && cudaEventSynchronize(cl.ev[1]) == cudaSuccess) {
+    cudaEventElapsedTime(&cl.build_ms, cl.ev[0], cl.ev[1]);
+    cl.build_timed = false;
+  }
+  if (cl.cov_timed && cudaEventSynchronize(cl.ev[4]) == cudaSuccess) {
+    cudaEventElapsedTime(&cl.knn_ms, cl.ev[2], cl.ev[3]);
+    cudaEventElapsedTime(&cl.cov_ms, cl.ev[3], cl.ev[4]);
+    cl.cov_timed = false;
+  }
+}
+
+// runs the enclosed work on lane 1 (rgc_ctx.hpp); the main stream picks it up with join_side()
+struct SideLane {
+  rgc_ctx* c;
+  bool on;
+  SideLane(rgc_ctx* c_, bool on_) : c(c_), on(on_ && c_->overlap) {
+    if (on) c->switch_lane(1);
+  }
+  ~SideLane() {
+    if (!on) return;
+    cudaEventRecord(c->join_ev, c->stream);
+    c->side_pending = true;
+    c->switch_lane(0);
+  }
+};
+static int join_side(rgc_ctx* c) {
+  if (c->side_pending) {
+    CK(c, cudaStreamWaitEvent(c->stream, c->join_ev, 0));
+    c->side_pending = false;
+  }
+  return RGC_OK;
+}
 
 static void cloud_release(rgc_ctx* c, Cloud& cl) {
   c->put(cl.sorted);
   c->put(cl.inv);
   c->put(cl.tables);
   c->put(cl.cov);
+  for (int i = 0; i < 5; i++) c->put_event(cl.ev[i]);
   cl = Cloud();
 }
 
@@ -96,7 +138,9 @@ static int cloud_build(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, s
   const int n = (int)n_sz;
   cudaStream_t st = c->stream;
   Tracer tr;
-  CK(c, cudaEventRecord(c->ev[0], st));
+  for (int i = 0; i < 5; i++)
+    if (!(cl.ev[i] = c->get_event())) FAIL(c, RGC_ERR_CUDA, "cudaEventCreate failed");
+  CK(c, cudaEventRecord(cl.ev[0], st));
 
   const unsigned char* d_raw = (const unsigned char*)points;
   void* staging = nullptr;
@@ -213,10 +257,8 @@ static int cloud_build(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, s
   cl.key = key;
   cl.valid = true;
   tr.lap("tables launches");
-  CK(c, cudaEventRecord(c->ev[1], st));
-  CK(c, cudaEventSynchronize(c->ev[1]));
-  tr.lap("tables sync");
-  CK(c, cudaEventElapsedTime(&cl.build_ms, c->ev[0], c->ev[1]));
+  CK(c, cudaEventRecord(cl.ev[1], st));
+  cl.build_timed = true;
   return RGC_OK;
 }
 
@@ -263,27 +305,34 @@ static int launch_knn_self(rgc_ctx* c, const GridView& v, int n, int k, int* nbr
 }
 
 // FastGICP::calculate_covariances (fast_gicp_impl.hpp:241-299)
-static int cloud_covariances(rgc_ctx* c, Cloud& cl, int k, int method) {
-  if (cl.has_cov) return RGC_OK;
+static int cloud_covariances(rgc_ctx* c, Cloud& cl, int k, int method, bool speculative = false) {
+  // covariances computed ahead of time (set_input) are redone if the parameters changed before the
+  // first align; once an align has used them they stay, like the reference's (recomputed only when
+  // the cloud changes)
+  if (cl.has_cov && !(cl.cov_speculative && (cl.cov_k != k || cl.cov_method != method))) {
+    if (!speculative) cl.cov_speculative = false;
+    return RGC_OK;
+  }
   if (k < 1) FAIL(c, RGC_ERR_INVALID, "k_correspondences must be >= 1");
   cudaStream_t st = c->stream;
   int* nbr = (int*)c->get(sizeof(int) * (size_t)k * cl.n);
   if (!cl.cov) cl.cov = (double*)c->get(sizeof(double) * 6 * (size_t)cl.n);
   if (!nbr || !cl.cov) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (covariances)");
-  CK(c, cudaEventRecord(c->ev[2], st));
+  CK(c, cudaEventRecord(cl.ev[2], st));
   TRY(launch_knn_self(c, cl.view, cl.n, k, nbr));
-  CK(c, cudaEventRecord(c->ev[3], st));
+  CK(c, cudaEventRecord(cl.ev[3], st));
   if (k <= 20)
     k_covariance<20><<<div_up(cl.n, kThreads), kThreads, 0, st>>>(cl.sorted, nbr, cl.n, k, method, cl.cov);
   else
     k_covariance<32><<<div_up(cl.n, kThreads), kThreads, 0, st>>>(cl.sorted, nbr, cl.n, k, method, cl.cov);
   CKL(c);
-  CK(c, cudaEventRecord(c->ev[4], st));
+  CK(c, cudaEventRecord(cl.ev[4], st));
   c->put(nbr);
   cl.has_cov = true;
-  CK(c, cudaEventSynchronize(c->ev[4]));
-  CK(c, cudaEventElapsedTime(&cl.knn_ms, c->ev[2], c->ev[3]));
-  CK(c, cudaEventElapsedTime(&cl.cov_ms, c->ev[3], c->ev[4]));
+  cl.cov_speculative = speculative;
+  cl.cov_k = k;
+  cl.cov_method = method;
+  cl.cov_timed = true;
   return RGC_OK;
 }
 
@@ -569,7 +618,9 @@ static int reg_compute_error(rgc_reg* r, const double* T, double* err) {
 static int reg_ready(rgc_reg* r) {
   rgc_ctx* c = r->ctx;
   if (!r->src.valid || !r->tgt.valid) FAIL(c, RGC_ERR_STATE, "source and target clouds must both be set");
-  // fast_gicp_impl.hpp:104-109 — covariances are computed lazily, source first
+  TRY(join_side(c));
+  // fast_gicp_impl.hpp:104-109 — covariances are computed lazily, source first (normally both
+  // were already started by set_input, see set_cloud)
   TRY(cloud_covariances(c, r->src, r->prm.k_correspondences, r->prm.regularization));
   TRY(cloud_covariances(c, r->tgt, r->prm.k_correspondences, r->prm.regularization));
   return RGC_OK;
@@ -652,6 +703,10 @@ int rgc_ctx_create(int device, rgc_ctx** out) {
             cudaHostAlloc((void**)&c->h_bbox, sizeof(float) * 6 * kBboxBlocks, cudaHostAllocDefault) == cudaSuccess &&
             cudaHostAlloc((void**)&c->h_counts, sizeof(uint32_t) * kMaxLevels, cudaHostAllocDefault) == cudaSuccess &&
             cudaMalloc((void**)&c->d_ticket, 64) == cudaSuccess && cudaMemset(c->d_ticket, 0, 64) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&c->parked.stream, cudaStreamNonBlocking) == cudaSuccess &&
+       cudaHostAlloc((void**)&c->parked.h_bbox, sizeof(float) * 6 * kBboxBlocks, cudaHostAllocDefault) == cudaSuccess &&
+       cudaHostAlloc((void**)&c->parked.h_counts, sizeof(uint32_t) * kMaxLevels, cudaHostAllocDefault) == cudaSuccess &&
+       cudaEventCreateWithFlags(&c->join_ev, cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; ok && i < 8; i++) ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
   for (int i = 0; ok && i < 4; i++) ok = cudaEventCreate(&c->evk[i]) == cudaSuccess;
   c->profile = std::getenv("RGC_PROFILE") != nullptr;
@@ -668,10 +723,16 @@ int rgc_ctx_destroy(rgc_ctx* c) {
   if (!c) return RGC_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  for (auto& kv : c->block_size) cudaFree(kv.first);
+  cudaStreamSynchronize(c->parked.stream);
+  for (auto& kv : c->block_info) cudaFree(kv.first);
   cudaFreeHost(c->h_result);
   cudaFreeHost(c->h_bbox);
   cudaFreeHost(c->h_counts);
+  cudaFreeHost(c->parked.h_bbox);
+  cudaFreeHost(c->parked.h_counts);
+  cudaEventDestroy(c->join_ev);
+  for (cudaEvent_t e : c->free_events) cudaEventDestroy(e);
+  cudaStreamDestroy(c->parked.stream);
   cudaFree(c->d_ticket);
   for (int i = 0; i < 8; i++) cudaEventDestroy(c->ev[i]);
   for (int i = 0; i < 4; i++) cudaEventDestroy(c->evk[i]);
@@ -682,6 +743,7 @@ int rgc_ctx_destroy(rgc_ctx* c) {
 
 const char* rgc_last_error(const rgc_ctx* c) { return c ? c->err.c_str() : "null context"; }
 int rgc_ctx_synchronize(rgc_ctx* c) {
+  CK(c, cudaStreamSynchronize(c->parked.stream));
   CK(c, cudaStreamSynchronize(c->stream));
   return RGC_OK;
 }
@@ -759,7 +821,12 @@ static int set_cloud(rgc_reg* r, Cloud& cl, const void* pts, size_t n, size_t st
   if (key != 0 && cl.valid && cl.key == key) return RGC_OK;  // fast_gicp_impl.hpp:73-75 / :84-86
   r->have_corr = false;
   if (&cl == &r->tgt) r->vox_valid = false;  // FastVGICP::setInputTarget resets the voxel map (fast_vgicp_impl.hpp:57-64)
-  return cloud_build(c, cl, pts, n, stride, on_device, key, r->prm.grid_cell);
+  // The source cloud is prepared on lane 1, the target on the main stream, and the covariances
+  // (fast_gicp_impl.hpp:104-109 computes them at the first align) are STARTED here without waiting:
+  // the kNN of a 500k-point target then runs while the host uploads and sorts the source.
+  SideLane side(c, &cl == &r->src);
+  TRY(cloud_build(c, cl, pts, n, stride, on_device, key, r->prm.grid_cell));
+  return cloud_covariances(c, cl, r->prm.k_correspondences, r->prm.regularization, true);
 }
 int rgc_reg_set_source(rgc_reg* r, const void* p, size_t n, size_t s, uint64_t key) { return r ? set_cloud(r, r->src, p, n, s, key, false) : RGC_ERR_INVALID; }
 int rgc_reg_set_target(rgc_reg* r, const void* p, size_t n, size_t s, uint64_t key) { return r ? set_cloud(r, r->tgt, p, n, s, key, false) : RGC_ERR_INVALID; }
@@ -792,6 +859,7 @@ static int set_covs(rgc_reg* r, Cloud& cl, const double* m, size_t n) {
   CK(c, cudaSetDevice(c->device));
   if (!cl.valid) FAIL(c, RGC_ERR_STATE, "set the point cloud before its covariances");
   if ((int)n != cl.n) FAIL(c, RGC_ERR_INVALID, "covariance count does not match the cloud size");
+  TRY(join_side(c));
   double* stage = (double*)c->get(128 * n);
   if (!cl.cov) cl.cov = (double*)c->get(48 * n);
   if (!stage || !cl.cov) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (covariance import)");
@@ -801,6 +869,9 @@ static int set_covs(rgc_reg* r, Cloud& cl, const double* m, size_t n) {
   CK(c, cudaStreamSynchronize(c->stream));
   c->put(stage);
   cl.has_cov = true;
+  cl.cov_speculative = false;  // user-provided: kept whatever the parameters
+  cl.cov_timed = false;
+  cl.knn_ms = cl.cov_ms = 0.f;
   if (&cl == &r->tgt) r->vox_valid = false;
   return RGC_OK;
 }
@@ -809,6 +880,7 @@ static int get_covs(rgc_reg* r, Cloud& cl, double* m, size_t n) {
   CK(c, cudaSetDevice(c->device));
   if (!cl.valid) FAIL(c, RGC_ERR_STATE, "no point cloud set");
   if ((int)n != cl.n) FAIL(c, RGC_ERR_INVALID, "covariance count does not match the cloud size");
+  TRY(join_side(c));
   TRY(cloud_covariances(c, cl, r->prm.k_correspondences, r->prm.regularization));
   double* stage = (double*)c->get(128 * n);
   if (!stage) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (covariance export)");
@@ -907,6 +979,7 @@ int rgc_reg_compute_error(rgc_reg* r, const double* T16, double* err) {
   if (!r || !T16 || !err) return RGC_ERR_INVALID;
   rgc_ctx* c = r->ctx;
   CK(c, cudaSetDevice(c->device));
+  TRY(join_side(c));
   double T[16];
   colmajor_to_row(T16, T);
   return reg_compute_error(r, T, err);
@@ -916,6 +989,7 @@ int rgc_reg_get_correspondences(rgc_reg* r, int32_t* corr, float* sq_dist) {
   if (!r || !corr) return RGC_ERR_INVALID;
   rgc_ctx* c = r->ctx;
   CK(c, cudaSetDevice(c->device));
+  TRY(join_side(c));
   if (r->vgicp) FAIL(c, RGC_ERR_UNSUPPORTED, "point correspondences do not exist in voxelised mode");
   if (!r->have_corr) FAIL(c, RGC_ERR_STATE, "no correspondences yet (call linearize or align first)");
   const size_t n = (size_t)r->src.n;
@@ -936,6 +1010,7 @@ int rgc_reg_fitness(rgc_reg* r, double max_range, double* score) {
   if (!r || !score) return RGC_ERR_INVALID;
   rgc_ctx* c = r->ctx;
   CK(c, cudaSetDevice(c->device));
+  TRY(join_side(c));
   if (!r->src.valid || !r->tgt.valid) FAIL(c, RGC_ERR_STATE, "source and target clouds must both be set");
   TRY(reg_ensure_work(r));
   RtF Tf;
@@ -1086,6 +1161,7 @@ int rgc_reg_get_voxels(rgc_reg* r, int32_t* coords3, int32_t* num_points, double
   if (!r || !n_voxels) return RGC_ERR_INVALID;
   rgc_ctx* c = r->ctx;
   CK(c, cudaSetDevice(c->device));
+  TRY(join_side(c));
   if (!r->vgicp) FAIL(c, RGC_ERR_STATE, "voxelised mode is off (rgc_reg_set_vgicp)");
   if (!r->tgt.valid) FAIL(c, RGC_ERR_STATE, "no target cloud");
   TRY(cloud_covariances(c, r->tgt, r->prm.k_correspondences, r->prm.regularization));
@@ -1130,6 +1206,8 @@ int rgc_reg_set_allreduce(rgc_reg* r, rgc_reduce_fn fn, void* user, void* d_buf)
 
 int rgc_reg_stage_ms(const rgc_reg* r, float* ms7) {
   if (!r || !ms7) return RGC_ERR_INVALID;
+  cloud_times(const_cast<Cloud&>(r->src));
+  cloud_times(const_cast<Cloud&>(r->tgt));
   ms7[0] = r->src.build_ms;
   ms7[1] = r->src.knn_ms;
   ms7[2] = r->src.cov_ms;
