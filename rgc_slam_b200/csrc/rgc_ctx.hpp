@@ -41,6 +41,7 @@ struct rgc_ctx {
   cudaEvent_t join_ev = nullptr;  // end of the last lane-1 work
   bool side_pending = false;      // lane-1 work not yet joined into the main stream
   bool overlap = std::getenv("RGC_NO_OVERLAP") == nullptr;
+  bool look_ahead = std::getenv("RGC_NO_LOOKAHEAD") == nullptr;  // step_lm: linearize issued behind compute_error
   std::vector<cudaEvent_t> free_events;
   // pinned, device-mapped result area the reduction kernels write straight into
   double* h_result = nullptr;

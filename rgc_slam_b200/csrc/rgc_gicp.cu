@@ -348,6 +348,13 @@ struct rgc_reg {
   double* partials = nullptr;
   int cap_src = 0;
   bool have_corr = false;
+  // second set of per-point buffers + results of a linearize issued ahead of time (step_lm)
+  int* corr2 = nullptr;
+  float* sqd2 = nullptr;
+  double* maha2 = nullptr;
+  bool spec_ready = false;
+  double spec_H[36], spec_b[6], spec_y0 = 0.0;
+  int spec_inliers = 0;
   // LsqRegistration state
   double lm_lambda = -1.0;
   double final_hessian[36];  // row-major (symmetric)
@@ -375,6 +382,7 @@ struct rgc_reg {
 };
 
 // where the reduction kernels write, and (sharded) the cross-rank sum before the host reads it
+constexpr int kSpecSlot = 32;  // doubles: results of the look-ahead linearize live at h_result + 32
 static double* reg_result_ptr(rgc_reg* r) { return r->reduce_fn ? r->reduce_buf : r->ctx->d_result; }
 static int reg_finish_reduce(rgc_reg* r, int n_doubles) {
   rgc_ctx* c = r->ctx;
@@ -392,11 +400,18 @@ static int reg_ensure_work(rgc_reg* r) {
   c->put(r->corr);
   c->put(r->sqd);
   c->put(r->maha);
+  c->put(r->corr2);
+  c->put(r->sqd2);
+  c->put(r->maha2);
   c->put(r->partials);
   const size_t n = (size_t)r->src.n;
   r->corr = (int*)c->get(4 * n);
   r->sqd = (float*)c->get(4 * n);
   r->maha = (double*)c->get(48 * n);
+  r->corr2 = (int*)c->get(4 * n);
+  r->sqd2 = (float*)c->get(4 * n);
+  r->maha2 = (double*)c->get(48 * n);
+  if (!r->corr2 || !r->sqd2 || !r->maha2) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (work buffers)");
   r->partials = (double*)c->get(sizeof(double) * kLinN * (size_t)div_up(r->src.n * query_spread(r->src.n), kThreads));
   if (!r->corr || !r->sqd || !r->maha || !r->partials) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (work buffers)");
   r->cap_src = r->src.n;
@@ -546,44 +561,36 @@ static int vgicp_compute_error(rgc_reg* r, const double* T, double* err) {
   return RGC_OK;
 }
 
-// FastGICP::linearize (fast_gicp_impl.hpp:155-211); H row-major 6x6
-static int reg_linearize(rgc_reg* r, const double* T, double* err, double* H, double* b) {
+// FastGICP::linearize (fast_gicp_impl.hpp:155-211), launch half: correspondences (seeded by `hint`)
+// into corr/sqd, then the per-point terms and their reduction into `result`
+static int gicp_linearize_launch(rgc_reg* r, const double* T, int want, const int* hint, int* corr, float* sqd, double* maha, double* result) {
   rgc_ctx* c = r->ctx;
-  if (r->vgicp) return vgicp_linearize(r, T, err, H, b);
-  TRY(reg_ensure_work(r));
   Rt Td;
   RtF Tf;
   to_rt(T, Td, Tf);
   const float thr = r->prm.max_correspondence_distance;
   const float thr2 = thr * thr;  // float product, +inf for the FLT_MAX default (fast_gicp_impl.hpp:136)
-  const int want = (H && b) ? 1 : 0;
   const int spread = query_spread(r->src.n);
   if (c->profile) CK(c, cudaEventRecord(c->evk[0], c->stream));
   // the warp-cooperative variant is exact too but measured slower on one sweep (155 vs 92 us for 22k
   // queries: its serial node-by-node walk has a longer dependent-load chain); RGC_CORR_TILE=1 selects it
   static const bool corr_tile = std::getenv("RGC_CORR_TILE") != nullptr;
   if (!corr_tile)
-    k_correspond<<<div_up(r->src.n * spread, kThreads), kThreads, 0, c->stream>>>(r->tgt.view, r->src.sorted, r->src.n, spread, Tf, thr2, r->slab, r->have_corr ? 1 : 0, r->corr,
-                                                                                  r->sqd);
+    k_correspond<<<div_up(r->src.n * spread, kThreads), kThreads, 0, c->stream>>>(r->tgt.view, r->src.sorted, r->src.n, spread, Tf, thr2, r->slab, hint, corr, sqd);
   else
-    k_correspond_tile<<<div_up(r->src.n, KT_WARPS * 32), KT_WARPS * 32, 0, c->stream>>>(r->tgt.view, r->src.sorted, r->src.n, Tf, thr2, r->slab, r->corr, r->sqd);
+    k_correspond_tile<<<div_up(r->src.n, KT_WARPS * 32), KT_WARPS * 32, 0, c->stream>>>(r->tgt.view, r->src.sorted, r->src.n, Tf, thr2, r->slab, corr, sqd);
   CKL(c);
   if (c->profile) CK(c, cudaEventRecord(c->evk[1], c->stream));
-  k_linearize<<<reduce_grid(r->src.n), kThreads, 0, c->stream>>>(r->tgt.sorted, r->src.sorted, r->src.cov, r->tgt.cov, r->src.n, Td, want, r->corr, r->maha,
-                                                                     r->partials, c->d_ticket, reg_result_ptr(r));
+  k_linearize<<<reduce_grid(r->src.n), kThreads, 0, c->stream>>>(r->tgt.sorted, r->src.sorted, r->src.cov, r->tgt.cov, r->src.n, Td, want, corr, maha, r->partials,
+                                                                     c->d_ticket, result);
   CKL(c);
   if (c->profile) CK(c, cudaEventRecord(c->evk[2], c->stream));
-  TRY(reg_finish_reduce(r, kLinN));
-  if (c->profile) {
-    cudaEventElapsedTime(&c->last_kernel_ms[0], c->evk[0], c->evk[1]);
-    cudaEventElapsedTime(&c->last_kernel_ms[1], c->evk[1], c->evk[2]);
-  }
-  r->n_linearize++;
-  r->have_corr = true;
-  const double* res = c->h_result;
+  return RGC_OK;
+}
+static void gicp_linearize_unpack(const double* res, double* err, int* inliers, double* H, double* b) {
   *err = res[0];
-  r->last_inliers = (int)res[kAccN];
-  if (want) {
+  *inliers = (int)res[kAccN];
+  if (H && b) {
     int o = 1;
     for (int i = 0; i < 6; i++)
       for (int j = i; j < 6; j++) {
@@ -592,11 +599,32 @@ static int reg_linearize(rgc_reg* r, const double* T, double* err, double* H, do
       }
     for (int i = 0; i < 6; i++) b[i] = res[22 + i];
   }
+}
+
+// H row-major 6x6
+static int reg_linearize(rgc_reg* r, const double* T, double* err, double* H, double* b) {
+  rgc_ctx* c = r->ctx;
+  if (r->vgicp) return vgicp_linearize(r, T, err, H, b);
+  TRY(reg_ensure_work(r));
+  TRY(gicp_linearize_launch(r, T, (H && b) ? 1 : 0, r->have_corr ? r->corr : nullptr, r->corr, r->sqd, r->maha, reg_result_ptr(r)));
+  TRY(reg_finish_reduce(r, kLinN));
+  if (c->profile) {
+    cudaEventElapsedTime(&c->last_kernel_ms[0], c->evk[0], c->evk[1]);
+    cudaEventElapsedTime(&c->last_kernel_ms[1], c->evk[1], c->evk[2]);
+  }
+  r->n_linearize++;
+  r->have_corr = true;
+  gicp_linearize_unpack(c->h_result, err, &r->last_inliers, H, b);
   return RGC_OK;
 }
 
 // FastGICP::compute_error (fast_gicp_impl.hpp:214-237)
-static int reg_compute_error(rgc_reg* r, const double* T, double* err) {
+// With `ahead`, the linearize at the same pose is issued right behind the error kernel, into the
+// second buffer set, and both are collected with ONE wait: if the LM step is then accepted (the
+// usual case) the next iteration's H, b are already on the host.  lsq_registration_impl.hpp:125-172
+// calls compute_error(xi) and, after an accepted step, linearize(xi) at the start of the next
+// iteration: same kernels, same inputs, same results, one host round trip less per iteration.
+static int reg_compute_error(rgc_reg* r, const double* T, double* err, bool ahead = false) {
   rgc_ctx* c = r->ctx;
   if (r->vgicp) return vgicp_compute_error(r, T, err);
   if (!r->have_corr) FAIL(c, RGC_ERR_STATE, "compute_error before any linearize");
@@ -608,11 +636,22 @@ static int reg_compute_error(rgc_reg* r, const double* T, double* err) {
                                                                          c->d_ticket, reg_result_ptr(r));
   CKL(c);
   if (c->profile) CK(c, cudaEventRecord(c->evk[1], c->stream));
+  if (ahead) TRY(gicp_linearize_launch(r, T, 1, r->corr, r->corr2, r->sqd2, r->maha2, c->d_result + kSpecSlot));
   TRY(reg_finish_reduce(r, 1));
   if (c->profile) cudaEventElapsedTime(&c->last_kernel_ms[2], c->evk[0], c->evk[1]);
   r->n_compute_error++;
   *err = c->h_result[0];
+  if (ahead) gicp_linearize_unpack(c->h_result + kSpecSlot, &r->spec_y0, &r->spec_inliers, r->spec_H, r->spec_b);
   return RGC_OK;
+}
+// an accepted step makes the look-ahead linearize the current one
+static void reg_adopt_ahead(rgc_reg* r) {
+  std::swap(r->corr, r->corr2);
+  std::swap(r->sqd, r->sqd2);
+  std::swap(r->maha, r->maha2);
+  r->last_inliers = r->spec_inliers;
+  r->n_linearize++;
+  r->spec_ready = true;
 }
 
 static int reg_ready(rgc_reg* r) {
@@ -639,15 +678,24 @@ static int step_gn(rgc_reg* r, double* x0, double* delta) {
 }
 
 // lsq_registration_impl.hpp:125-172 ; returns 1 = step taken, 0 = "lm not converged", <0 = error
-static int step_lm(rgc_reg* r, double* x0, double* delta, double* y0_out) {
+static int step_lm(rgc_reg* r, double* x0, double* delta, double* y0_out, bool more_iterations) {
   double H[36], b[6], y0;
-  TRY(reg_linearize(r, x0, &y0, H, b));
+  if (r->spec_ready) {  // linearized at x0 behind the previous step's compute_error
+    std::memcpy(H, r->spec_H, sizeof(H));
+    std::memcpy(b, r->spec_b, sizeof(b));
+    y0 = r->spec_y0;
+    r->spec_ready = false;
+  } else {
+    TRY(reg_linearize(r, x0, &y0, H, b));
+  }
   *y0_out = y0;
   if (r->lm_lambda < 0.0) {
     double mx = 0.0;
     for (int i = 0; i < 6; i++) mx = std::max(mx, std::fabs(H[i * 7]));
     r->lm_lambda = r->prm.lm_init_lambda_factor * mx;
   }
+  // the look-ahead needs the plain single-GPU GICP path (no all-reduce hook, no per-kernel timing)
+  const bool can_look_ahead = more_iterations && r->ctx->look_ahead && !r->vgicp && !r->reduce_fn && !r->ctx->profile;
   double nu = 2.0;
   for (int i = 0; i < r->prm.lm_max_iterations; i++) {
     double A[36], nb[6], d[6], xi[16], yi;
@@ -659,7 +707,9 @@ static int step_lm(rgc_reg* r, double* x0, double* delta, double* y0_out) {
     lm::solve_ldlt6(A, nb, d);
     lm::se3_delta(d, delta);
     lm::mul4(delta, x0, xi);
-    TRY(reg_compute_error(r, xi, &yi));
+    // if this step is accepted and does not end the outer loop, the next thing needed is linearize(xi)
+    const bool ahead = can_look_ahead && !lm::is_converged(delta, r->prm.rotation_epsilon, r->prm.transformation_epsilon);
+    TRY(reg_compute_error(r, xi, &yi, ahead));
     double denom = 0.0;
     for (int j = 0; j < 6; j++) denom += d[j] * (r->lm_lambda * d[j] - b[j]);
     const double rho = (y0 - yi) / denom;
@@ -678,6 +728,7 @@ static int step_lm(rgc_reg* r, double* x0, double* delta, double* y0_out) {
     std::memcpy(x0, xi, sizeof(xi));
     r->lm_lambda = r->lm_lambda * std::max(1.0 / 3.0, 1 - std::pow(2 * rho - 1, 3));
     std::memcpy(r->final_hessian, H, sizeof(H));
+    if (ahead) reg_adopt_ahead(r);
     return 1;
   }
   return 0;
@@ -794,6 +845,9 @@ int rgc_reg_destroy(rgc_reg* r) {
   c->put(r->corr);
   c->put(r->sqd);
   c->put(r->maha);
+  c->put(r->corr2);
+  c->put(r->sqd2);
+  c->put(r->maha2);
   c->put(r->partials);
   c->put(r->vox_slots);
   c->put(r->vox_corr);
@@ -913,6 +967,7 @@ int rgc_reg_align(rgc_reg* r, const float* guess, float* final_T16, rgc_result* 
     for (int cc = 0; cc < 4; cc++) x0[rr * 4 + cc] = guess ? (double)guess[cc * 4 + rr] : (rr == cc ? 1.0 : 0.0);
   r->lm_lambda = -1.0;
   r->converged = false;
+  r->spec_ready = false;
   r->n_linearize = r->n_compute_error = 0;
   int iterations = 0;
   double last_y0 = 0.0;
@@ -920,7 +975,7 @@ int rgc_reg_align(rgc_reg* r, const float* guess, float* final_T16, rgc_result* 
   for (int i = 0; i < r->prm.max_iterations && !r->converged; i++) {
     iterations = i;
     double delta[16];
-    int rc = (r->prm.optimizer == RGC_OPT_GAUSS_NEWTON) ? step_gn(r, x0, delta) : step_lm(r, x0, delta, &last_y0);
+    int rc = (r->prm.optimizer == RGC_OPT_GAUSS_NEWTON) ? step_gn(r, x0, delta) : step_lm(r, x0, delta, &last_y0, i + 1 < r->prm.max_iterations);
     if (rc < 0) return rc;
     if (rc == 0) {
       std::fprintf(stderr, "lm not converged!!\n");  // lsq_registration_impl.hpp:69-72

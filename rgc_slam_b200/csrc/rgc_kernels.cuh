@@ -971,7 +971,7 @@ constexpr int kLinN = kAccN + 1;  // + inlier count
 // with the tightest possible ball and skips the climb.  Any real point is a valid bound: the
 // result is the same exact nearest neighbour.
 __global__ void __launch_bounds__(kThreads, 8) k_correspond(GridView tgt, const float4* __restrict__ src, int n_src, int spread, RtF Tf, float thr2, Slab slab,
-                                                            int use_hint, int* __restrict__ corr, float* __restrict__ sqd) {
+                                                            const int* hint, int* corr, float* __restrict__ sqd) {
   const int gt = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = gt / spread;
   if ((gt & (spread - 1)) != 0 || i >= n_src) return;
@@ -983,14 +983,14 @@ __global__ void __launch_bounds__(kThreads, 8) k_correspond(GridView tgt, const 
   if (g_tile_dbg) {  // debug statistics (rgc_debug_correspond_stats): cycles, nodes, lookups, candidates
     SearchStats st{0, 0, 0};
     const long long t0 = clock64();
-    if (slab_owns(slab, qx, qy, qz)) knn_search(tgt, qx, qy, qz, 1, thr2, use_hint ? corr[i] : -1, top, &st);
+    if (slab_owns(slab, qx, qy, qz)) knn_search(tgt, qx, qy, qz, 1, thr2, hint ? hint[i] : -1, top, &st);
     long long* o = g_tile_dbg + (size_t)i * 4;
     o[0] = clock64() - t0;
     o[1] = st.nodes;
     o[2] = st.lookups;
     o[3] = st.candidates;
   } else if (slab_owns(slab, qx, qy, qz)) {
-    knn_search(tgt, qx, qy, qz, 1, thr2, use_hint ? corr[i] : -1, top);
+    knn_search(tgt, qx, qy, qz, 1, thr2, hint ? hint[i] : -1, top);
   }
   corr[i] = (top.id0 >= 0 && top.d0 < thr2) ? top.id0 : -1;
   sqd[i] = top.d0;
