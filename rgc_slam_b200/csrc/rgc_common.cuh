@@ -12,9 +12,11 @@
 #if defined(__CUDACC__)
 #define RGC_HD __host__ __device__ __forceinline__
 #define RGC_D __device__ __forceinline__
+#define RGC_HD_NOINLINE inline __host__ __device__ __noinline__
 #else
 #define RGC_HD inline
 #define RGC_D inline
+#define RGC_HD_NOINLINE inline
 #endif
 
 namespace rgc {

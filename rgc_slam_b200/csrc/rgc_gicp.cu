@@ -289,7 +289,9 @@ static int launch_knn_self(rgc_ctx* c, const GridView& v, int n, int k, int* nbr
   const int n_seeds = n < 100000 ? KT_SEEDS : (KT_SEEDS > 64 ? 64 : KT_SEEDS);
   // tiles that gather more than `defer` candidates are finished by k_knn_warp (one warp per query):
   // they are the sparse-region tiles that used to form a 40 % tail of this launch (profiles/README.md)
-  const int defer = c->knn_defer > 0 ? c->knn_defer : INT_MAX;
+  // (the tail is one slow tile long, ~0.3 ms, whatever n is, while deferring costs ~8 % extra work:
+  // it pays below a few million points; measured 13.1 vs 14.4 ms at 8 M points, 1.33 vs 0.98 ms at 500 k)
+  const int defer = (c->knn_defer > 0 && n < 2000000) ? c->knn_defer : INT_MAX;
   const int ntiles = div_up(n, 32);
   int* dq = (int*)c->get(sizeof(int) * (size_t)(ntiles + 1));  // [0] = count, [1..] = tile ids
   if (!dq) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (knn defer list)");
@@ -321,10 +323,12 @@ static int cloud_covariances(rgc_ctx* c, Cloud& cl, int k, int method, bool spec
   CK(c, cudaEventRecord(cl.ev[2], st));
   TRY(launch_knn_self(c, cl.view, cl.n, k, nbr));
   CK(c, cudaEventRecord(cl.ev[3], st));
-  if (k <= 20)
-    k_covariance<20><<<div_up(cl.n, kThreads), kThreads, 0, st>>>(cl.sorted, nbr, cl.n, k, method, cl.cov);
+  if (k == 20 && cl.n >= k)  // the default k_correspondences, every slot filled
+    k_covariance<20, true><<<div_up(cl.n, kThreads), kThreads, 0, st>>>(cl.sorted, nbr, cl.n, k, method, cl.cov);
+  else if (k <= 20)
+    k_covariance<20, false><<<div_up(cl.n, kThreads), kThreads, 0, st>>>(cl.sorted, nbr, cl.n, k, method, cl.cov);
   else
-    k_covariance<32><<<div_up(cl.n, kThreads), kThreads, 0, st>>>(cl.sorted, nbr, cl.n, k, method, cl.cov);
+    k_covariance<32, false><<<div_up(cl.n, kThreads), kThreads, 0, st>>>(cl.sorted, nbr, cl.n, k, method, cl.cov);
   CKL(c);
   CK(c, cudaEventRecord(cl.ev[4], st));
   c->put(nbr);

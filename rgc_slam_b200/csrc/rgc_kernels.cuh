@@ -804,49 +804,67 @@ __global__ void __launch_bounds__(KW_WARPS * 32) k_knn_warp(GridView g, int n, i
 // All k index loads are issued first, then all k point gathers (fully unrolled, KCAP is a compile
 // time bound on k): the first version walked the neighbours in a serial loop of dependent
 // index -> point loads and was latency-bound at 17 % of HBM peak however cheap the fp64 part became.
-template <int KCAP>
-__global__ void __launch_bounds__(kThreads, 4) k_covariance(const float4* __restrict__ pts, const int* __restrict__ nbr, int n, int k, int method,
+#ifndef RGC_COV_MINB
+#define RGC_COV_MINB 6
+#endif
+#ifndef RGC_COV_BATCH
+#define RGC_COV_BATCH 5
+#endif
+// FULL: k == KCAP and the cloud has at least k points, so every neighbour slot is valid (no predicates).
+template <int KCAP, bool FULL>
+__global__ void __launch_bounds__(kThreads, RGC_COV_MINB) k_covariance(const float4* __restrict__ pts, const int* __restrict__ nbr, int n, int k, int method,
                                                             double* __restrict__ cov) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
+  // all k index loads first (coalesced, k-major), then the point gathers in batches of kBatch:
+  // a float4 gather holds four registers while in flight, 20 at once cost 128 registers / thread
+  // and a third of the occupancy
+  constexpr int kBatch = RGC_COV_BATCH;
   int id[KCAP];
 #pragma unroll
-  for (int j = 0; j < KCAP; j++) id[j] = j < k ? __ldg(&nbr[(size_t)j * n + t]) : -1;
-  float px[KCAP], py[KCAP], pz[KCAP];
-#pragma unroll
-  for (int j = 0; j < KCAP; j++) {
-    if (id[j] >= 0) {
-      const float4 p = __ldg(&pts[id[j]]);
-      px[j] = p.x;
-      py[j] = p.y;
-      pz[j] = p.z;
-    } else {
-      px[j] = py[j] = pz[j] = 0.f;
-    }
-  }
+  for (int j = 0; j < KCAP; j++) id[j] = (FULL || j < k) ? __ldg(&nbr[(size_t)j * n + t]) : -1;
   // same arithmetic as covariance_from_points (rgc_math.cuh): moments about neighbour 0, then re-centre
   int found = 0;
-#pragma unroll
-  for (int j = 0; j < KCAP; j++) found += (id[j] >= 0) ? 1 : 0;  // valid entries are a prefix
   Sym3 c = {0, 0, 0, 0, 0, 0};
-  if (found > 0) {
-    const double ox = (double)px[0], oy = (double)py[0], oz = (double)pz[0];
-    double sx = 0.0, sy = 0.0, sz = 0.0;
+  double ox = 0.0, oy = 0.0, oz = 0.0, sx = 0.0, sy = 0.0, sz = 0.0;
 #pragma unroll
-    for (int j = 1; j < KCAP; j++) {
-      if (id[j] >= 0) {
-        const double dx = (double)px[j] - ox, dy = (double)py[j] - oy, dz = (double)pz[j] - oz;
-        sx += dx;
-        sy += dy;
-        sz += dz;
-        c.xx += dx * dx;
-        c.xy += dx * dy;
-        c.xz += dx * dz;
-        c.yy += dy * dy;
-        c.yz += dy * dz;
-        c.zz += dz * dz;
+  for (int j0 = 0; j0 < KCAP; j0 += kBatch) {
+    float px[kBatch], py[kBatch], pz[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; u++) {
+      const int j = j0 + u;
+      px[u] = py[u] = pz[u] = 0.f;
+      if (j < KCAP && (FULL || id[j] >= 0)) {
+        const float4 p = __ldg(&pts[id[j]]);
+        px[u] = p.x;
+        py[u] = p.y;
+        pz[u] = p.z;
       }
     }
+#pragma unroll
+    for (int u = 0; u < kBatch; u++) {
+      const int j = j0 + u;
+      if (j >= KCAP || (!FULL && id[j] < 0)) continue;  // valid entries are a prefix
+      found++;
+      if (j == 0) {
+        ox = (double)px[0];
+        oy = (double)py[0];
+        oz = (double)pz[0];
+        continue;
+      }
+      const double dx = (double)px[u] - ox, dy = (double)py[u] - oy, dz = (double)pz[u] - oz;
+      sx += dx;
+      sy += dy;
+      sz += dz;
+      c.xx += dx * dx;
+      c.xy += dx * dy;
+      c.xz += dx * dz;
+      c.yy += dy * dy;
+      c.yz += dy * dz;
+      c.zz += dz * dz;
+    }
+  }
+  if (found > 0) {
     const int missing = k - found;
     if (missing > 0) {
       const double m = (double)missing;

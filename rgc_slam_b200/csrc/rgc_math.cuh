@@ -191,17 +191,10 @@ RGC_HD bool smallest_eigvec_sym3(const Sym3& Cin, double n[3], double& lambda_ou
   return true;
 }
 
-// fast_gicp_impl.hpp:264-293
-RGC_HD Sym3 regularize_cov(const Sym3& cov, int method) {
-  if (method == REG_NONE) return cov;
-  if (method == REG_PLANE) {
-    double n[3], lam;
-    if (smallest_eigvec_sym3(cov, n, lam)) {
-      // I - (1 - s 1e-3) n n^T, s = sign pairing of the reference's SVD (negative only through round-off)
-      const double f = 1.0 - (lam < 0.0 ? -1e-3 : 1e-3);
-      return Sym3{1.0 - f * n[0] * n[0], -f * n[0] * n[1], -f * n[0] * n[2], 1.0 - f * n[1] * n[1], -f * n[1] * n[2], 1.0 - f * n[2] * n[2]};
-    }
-  }
+// fast_gicp_impl.hpp:264-293, every method through the full eigen-decomposition.  Kept out of line:
+// on the device it is the rare path (non-PLANE methods, degenerate neighbourhoods) and inlining it
+// into k_covariance cost that kernel a third of its occupancy in registers.
+RGC_HD_NOINLINE Sym3 regularize_cov_general(const Sym3& cov, int method) {
   if (method == REG_FROBENIUS) {
     const double lambda = 1e-3;
     Sym3 C = cov;
@@ -244,6 +237,19 @@ RGC_HD Sym3 regularize_cov(const Sym3& cov, int method) {
     }
   }
   return recompose(V, val, sgn);
+}
+
+RGC_HD Sym3 regularize_cov(const Sym3& cov, int method) {
+  if (method == REG_NONE) return cov;
+  if (method == REG_PLANE) {
+    double n[3], lam;
+    if (smallest_eigvec_sym3(cov, n, lam)) {
+      // I - (1 - s 1e-3) n n^T, s = sign pairing of the reference's SVD (negative only through round-off)
+      const double f = 1.0 - (lam < 0.0 ? -1e-3 : 1e-3);
+      return Sym3{1.0 - f * n[0] * n[0], -f * n[0] * n[1], -f * n[0] * n[2], 1.0 - f * n[1] * n[1], -f * n[1] * n[2], 1.0 - f * n[2] * n[2]};
+    }
+  }
+  return regularize_cov_general(cov, method);
 }
 
 // Row-major 3x4 rigid transform in double.

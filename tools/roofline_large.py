@@ -8,6 +8,8 @@ import json
 import os
 import sys
 
+os.environ.setdefault("RGC_NO_OVERLAP", "1")  # clean per-stage times: source and target on one stream
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
