@@ -306,6 +306,44 @@ def run_ours(args, rank, world):
               "stage_ms": v.stage_ms(), "params": "resolution 1.0, DIRECT1, ADDITIVE, 25 it, trans_eps 1e-6 (RGC_odometer.cpp:1000-1006)"}
         v = None
 
+    # ---------------- throughput with several registrations in flight (SURVEY §8e C4 pattern on the C2
+    # workload): T host threads, each with its own context (stream pair + pool), pinned host clouds,
+    # cold target every align.  The sequential `value` / `e2e` above are latency-bound (one LM loop at
+    # a time leaves most SMs idle); this is what a batch consumer (loop-closure verification, bag
+    # replay) gets from one GPU.
+    conc = None
+    if world == 1 and args.concurrent > 1:
+        import threading
+        nthr = args.concurrent
+        ctxs = [rgc.Context(local) for _ in range(nthr)]
+        per_thread = max(4, args.steps // 2)
+
+        def worker(tid, n):
+            for i in range(n):
+                p, c = pairs[(i + tid) % len(pairs)], pin[(i + tid) % len(pairs)]
+                gg = new_reg(rgc, ctxs[tid])
+                gg.setInputTarget(c["tgt"][:])
+                gg.setInputSource(c["src"][:])
+                gg.align(p["guess"])
+                gg = None
+
+        for tid in range(nthr):
+            worker(tid, 2)
+        torch.cuda.synchronize()
+        th = [threading.Thread(target=worker, args=(tid, per_thread)) for tid in range(nthr)]
+        t0 = time.perf_counter()
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        for cx in ctxs:
+            cx.synchronize()
+        dtc = time.perf_counter() - t0
+        conc = {"threads": nthr, "aligns": nthr * per_thread, "aligns_per_s": nthr * per_thread / dtc,
+                "timing": "wall clock, pinned host clouds, cold target every align, one context per host thread"}
+        for cx in ctxs:
+            cx.close()
+
     # ---------------- per-kernel roofline (live CUDA-event stage times from the library)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -382,8 +420,11 @@ def run_ours(args, rank, world):
             "roofline": roofline,
             "cpu_baseline": cpu,
             "warm_ms_per_align": warm_ms,
+            "concurrent": conc,
             "vgicp": vg,
             "stage_ms": st,
+            "stage_ms_note": "per-stage CUDA-event times on each stage's own stream; the source stages run on a second "
+                             "stream concurrently with the target stages, so the stages do not add up to ms_per_step",
             "lm_iterations_mean": float(np.mean(iters)),
             "wall_s_timed_region": wall,
             "pose_err_vs_truth_m": float(np.abs(T[:3, 3] - Tt[:3, 3]).max()),
@@ -468,6 +509,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--submap-points", type=int, default=N_SUBMAP)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--concurrent", type=int, default=4, help="host threads of the concurrent-throughput leg (0/1 = skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
