@@ -38,7 +38,8 @@ class _Result(C.Structure):
 
 
 def lib_path() -> str:
-    return os.path.join(_PKG, "librgc_gicp.so")
+    # RGC_LIB: A/B timing of two builds of this same library inside one GPU session (tools/)
+    return os.environ.get("RGC_LIB") or os.path.join(_PKG, "librgc_gicp.so")
 
 
 def lib():

@@ -758,7 +758,12 @@ int rgc_ctx_create(int device, rgc_ctx** out) {
             cudaHostAlloc((void**)&c->h_bbox, sizeof(float) * 6 * kBboxBlocks, cudaHostAllocDefault) == cudaSuccess &&
             cudaHostAlloc((void**)&c->h_counts, sizeof(uint32_t) * kMaxLevels, cudaHostAllocDefault) == cudaSuccess &&
             cudaMalloc((void**)&c->d_ticket, 64) == cudaSuccess && cudaMemset(c->d_ticket, 0, 64) == cudaSuccess;
-  ok = ok && cudaStreamCreateWithFlags(&c->parked.stream, cudaStreamNonBlocking) == cudaSuccess &&
+  // lane 1 (source cloud: ~25 small kernels) gets the higher priority, so that its blocks are
+  // dispatched ahead of the thousands of pending blocks of the target's kNN launch on lane 0
+  // (without it the source build took 0.87 ms instead of 0.19 ms when overlapped)
+  int prio_lo = 0, prio_hi = 0;
+  ok = ok && cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) == cudaSuccess &&
+       cudaStreamCreateWithPriority(&c->parked.stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
        cudaHostAlloc((void**)&c->parked.h_bbox, sizeof(float) * 6 * kBboxBlocks, cudaHostAllocDefault) == cudaSuccess &&
        cudaHostAlloc((void**)&c->parked.h_counts, sizeof(uint32_t) * kMaxLevels, cudaHostAllocDefault) == cudaSuccess &&
        cudaEventCreateWithFlags(&c->join_ev, cudaEventDisableTiming) == cudaSuccess;
