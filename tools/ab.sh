@@ -3,5 +3,5 @@ run() { timeout 300 python bench.py --steps 30 --warmup 4 --no-cpu --concurrent 
 for r in $(seq 1 ${1:-2}); do
   RGC_LIB=$PWD/rgc_slam_b200/librgc_gicp_prev.so run prev
   run new
-  RGC_KNN_DEFER=450 run new450
+
 done

@@ -16,6 +16,20 @@ g.setInputTarget(tgt); g.setInputSource(src)
 T = g.align(want_output=True)
 print("align", g.last_result, g.getFitnessScore(), (g.correspondences()[0] >= 0).sum())
 print("knn", rgc.knn(tgt, src[:500], 5)[0].sum(), rgc.knn_self(tgt, 20).sum())
+# the warp-per-query kernel that finishes deferred tiles: force every tile through it once
+import ctypes as C
+from rgc_slam_b200 import api
+L = api.lib()
+L.rgc_debug_set_knn_defer.argtypes = [C.c_void_p, C.c_int]
+L.rgc_debug_set_knn_defer(api.default_context()._h, 1)
+print("knn (deferred path)", rgc.knn_self(tgt, 20).sum())
+L.rgc_debug_set_knn_defer(api.default_context()._h, 600)
+v = rgc.FastVGICP()
+v.setResolution(1.0)
+v.setMaxCorrespondenceDistance(2.0)
+v.setInputTarget(tgt); v.setInputSource(src)
+v.align()
+print("vgicp", v.last_result)
 scans = [synth.lidar_scan(scene, traj[f], n_azimuth=400, seed=50 + f) for f in range(3)]
 r, ms = extract_features(scans)
 print("features", [x["cloud_size"] for x in r], [len(x["corner_sharp"]) for x in r])
