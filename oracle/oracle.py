@@ -341,5 +341,30 @@ def extract_features(scan_xyzi, n_scans=16, min_range=0.5, max_range=80.0, use_i
     return out
 
 
+def deskew(xyzi, q_wxyz, t, scan_period=0.1):
+    """RGC_odometer.cpp:1441-1481 (adjustDistortion) for one cloud; xyzi: [n, 4] float32"""
+    P = np.ascontiguousarray(xyzi, np.float32)
+    out = np.empty_like(P)
+    q = np.ascontiguousarray(q_wxyz, np.float64)
+    tt = np.ascontiguousarray(t, np.float64)
+    L = lib()
+    L.orc_deskew.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
+    L.orc_deskew.restype = None
+    L.orc_deskew(P.ctypes.data, len(P), q.ctypes.data, tt.ctypes.data, scan_period, out.ctypes.data)
+    return out
+
+
+def voxel_grid(xyzi, leaf):
+    """pcl::VoxelGrid<PointXYZI>::filter, downsample_all_data, min_points_per_voxel 0; returns [m, 4]"""
+    P = np.ascontiguousarray(xyzi, np.float32)
+    out = np.empty_like(P)
+    pt = C.c_int(0)
+    L = lib()
+    L.orc_voxel_grid.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p]
+    L.orc_voxel_grid.restype = C.c_int
+    m = L.orc_voxel_grid(P.ctypes.data, len(P), leaf, out.ctypes.data, C.byref(pt))
+    return out[:m].copy()
+
+
 def max_threads() -> int:
     return lib().orc_max_threads()

@@ -6,6 +6,7 @@
 
 #include "orc_features.hpp"
 #include "orc_gicp.hpp"
+#include "orc_preprocess.hpp"
 
 using namespace orc;
 
@@ -15,6 +16,10 @@ static void cp(T* dst, const std::vector<T>& v) {
 }
 
 extern "C" {
+
+// ---- pre-step: de-skew and pcl::VoxelGrid ----
+void orc_deskew(const float* xyzi, int n, const double* q_wxyz, const double* t3, float scan_period, float* out) { deskew(xyzi, n, q_wxyz, t3, scan_period, out); }
+int orc_voxel_grid(const float* xyzi, int n, float leaf, float* out, int* passthrough) { return voxel_grid(xyzi, n, leaf, out, passthrough); }
 
 // ---- linear algebra probes (checked against numpy/scipy in tests/test_oracle_linalg.py) ----
 void orc_jacobi_svd3(const double* A, double* U, double* sv, double* V) { jacobi_svd3(A, U, sv, V); }

@@ -86,6 +86,10 @@ def lib():
         L.rgc_reg_set_vgicp.argtypes = [vp, C.c_int, C.c_double, C.c_int, C.c_int]
         L.rgc_reg_last_inliers.argtypes = [vp, C.POINTER(C.c_int)]
         L.rgc_reg_get_voxels.argtypes = [vp, vp, vp, vp, vp, sz, C.POINTER(sz)]
+        L.rgc_voxel_grid.argtypes = [vp, vp, sz, sz, sz, C.c_float, vp, sz, C.POINTER(sz), C.POINTER(C.c_int)]
+        L.rgc_deskew.argtypes = [vp, vp, sz, sz, sz, vp, vp, C.c_float, vp]
+        for name in ("rgc_reg_set_source_filtered", "rgc_reg_set_target_filtered"):
+            getattr(L, name).argtypes = [vp, vp, sz, sz, sz, C.c_float, vp, vp, C.c_float, u64, C.POINTER(sz)]
         _LIB = L
     return _LIB
 
@@ -99,6 +103,7 @@ EXPORTED_SYMBOLS = [
     "rgc_reg_align", "rgc_reg_linearize", "rgc_reg_compute_error", "rgc_reg_get_correspondences", "rgc_reg_fitness",
     "rgc_reg_get_final_transformation", "rgc_knn", "rgc_reg_stage_ms", "rgc_knn_self", "rgc_reg_set_owner_slab", "rgc_reg_set_allreduce",
     "rgc_ctx_set_profiling", "rgc_ctx_last_kernel_ms", "rgc_reg_set_vgicp", "rgc_reg_get_voxels", "rgc_reg_last_inliers",
+    "rgc_voxel_grid", "rgc_deskew", "rgc_reg_set_source_filtered", "rgc_reg_set_target_filtered",
 ]
 
 
@@ -265,6 +270,30 @@ class FastGICP:
         else:
             self._tgt, self._tgt_id, self._n_tgt = keep, (key, cloud), n
 
+    def _set_filtered(self, which, xyzi, leaf, q_wxyz, t, scan_period):
+        """[de-skew] -> [pcl::VoxelGrid] -> setInput*, on the device (include/rgc_preprocess.h).
+        xyzi: host [n, 4] float32 (x, y, z, intensity).  Returns the size of the filtered cloud."""
+        P = np.ascontiguousarray(xyzi, np.float32)
+        if P.ndim != 2 or P.shape[1] != 4:
+            raise RgcError("filtered input must be [n, 4] float32 (x, y, z, intensity)")
+        q = None if q_wxyz is None else np.ascontiguousarray(q_wxyz, np.float64)
+        tt = None if t is None else np.ascontiguousarray(t, np.float64)
+        m = C.c_size_t(0)
+        fn = getattr(lib(), f"rgc_reg_set_{which}_filtered")
+        self.ctx.check(fn(self._h, P.ctypes.data, len(P), 16, 12, float(leaf), None if q is None else q.ctypes.data,
+                          None if tt is None else tt.ctypes.data, float(scan_period), id(xyzi), C.byref(m)))
+        if which == "source":
+            self._src, self._src_id, self._n_src = P, (id(xyzi), xyzi), m.value
+        else:
+            self._tgt, self._tgt_id, self._n_tgt = P, (id(xyzi), xyzi), m.value
+        return m.value
+
+    def setInputSourceFiltered(self, xyzi, leaf, q_last_curr=None, t_last_curr=None, scan_period=0.1):
+        return self._set_filtered("source", xyzi, leaf, q_last_curr, t_last_curr, scan_period)
+
+    def setInputTargetFiltered(self, xyzi, leaf, q_last_curr=None, t_last_curr=None, scan_period=0.1):
+        return self._set_filtered("target", xyzi, leaf, q_last_curr, t_last_curr, scan_period)
+
     def setInputSource(self, cloud):
         self._set("source", cloud)
 
@@ -423,6 +452,27 @@ def knn(points, queries, k, ctx: Context | None = None, grid_cell: float = 0.0):
     d2 = np.empty((m, k), np.float32)
     ctx.check(lib().rgc_knn(ctx._h, pp, n, ps, qp, m, qs, k, idx.ctypes.data, d2.ctypes.data, grid_cell))
     return idx, d2
+
+
+def voxel_grid(xyzi, leaf, ctx: Context | None = None):
+    """pcl::VoxelGrid<PointXYZI>::filter on the GPU: [n, 4] float32 -> [m, 4] centroids in voxel-index order"""
+    ctx = ctx or default_context(0)
+    P = np.ascontiguousarray(xyzi, np.float32)
+    out = np.empty_like(P)
+    m, pt = C.c_size_t(0), C.c_int(0)
+    ctx.check(lib().rgc_voxel_grid(ctx._h, P.ctypes.data, len(P), 16, 12, float(leaf), out.ctypes.data, len(P), C.byref(m), C.byref(pt)))
+    return out[:m.value].copy()
+
+
+def deskew(xyzi, q_last_curr_wxyz, t_last_curr, scan_period=0.1, ctx: Context | None = None):
+    """RGC_odometer::adjustDistortion for one cloud on the GPU: [n, 4] float32 -> [n, 4]"""
+    ctx = ctx or default_context(0)
+    P = np.ascontiguousarray(xyzi, np.float32)
+    out = np.empty_like(P)
+    q = np.ascontiguousarray(q_last_curr_wxyz, np.float64)
+    t = np.ascontiguousarray(t_last_curr, np.float64)
+    ctx.check(lib().rgc_deskew(ctx._h, P.ctypes.data, len(P), 16, 12, q.ctypes.data, t.ctypes.data, float(scan_period), out.ctypes.data))
+    return out
 
 
 def knn_self(points, k, ctx: Context | None = None, grid_cell: float = 0.0):

@@ -20,6 +20,7 @@
 #include "rgc_ctx.hpp"
 #include "rgc_kernels.cuh"
 #include "rgc_lm.hpp"
+#include "rgc_preprocess.cuh"
 #include "rgc_vgicp.cuh"
 
 using namespace rgc;
@@ -259,6 +260,122 @@ static int cloud_build(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, s
   tr.lap("tables launches");
   CK(c, cudaEventRecord(cl.ev[1], st));
   cl.build_timed = true;
+  return RGC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pre-step: host cloud -> [de-skew] -> [pcl::VoxelGrid centroids] as a pooled device
+// buffer of float4 (x, y, z, intensity) on the current lane.  *d_out must be given back with c->put().
+static int pre_filter(rgc_ctx* c, const void* points, size_t n_sz, size_t stride, size_t inten_off, float leaf, const double* q_wxyz, const double* t3,
+                      float scan_period, float4** d_out, int* n_out, int* passthrough) {
+  *d_out = nullptr;
+  *n_out = 0;
+  if (passthrough) *passthrough = 0;
+  if (n_sz == 0 || points == nullptr) FAIL(c, RGC_ERR_INVALID, "empty point cloud");
+  if (n_sz > 0x7fffffff / 32) FAIL(c, RGC_ERR_UNSUPPORTED, "point cloud too large for 32-bit indexing");
+  if (stride < 12 || stride % 4) FAIL(c, RGC_ERR_INVALID, "point stride must be a multiple of 4 and >= 12 bytes");
+  if (inten_off != kNoIntensity && (inten_off % 4 || inten_off + 4 > stride)) FAIL(c, RGC_ERR_INVALID, "intensity offset outside the point record");
+  if (q_wxyz && (!t3 || !(scan_period > 0.f))) FAIL(c, RGC_ERR_INVALID, "de-skew needs q, t and a positive scan period");
+  if (q_wxyz && inten_off == kNoIntensity) FAIL(c, RGC_ERR_INVALID, "de-skew needs the intensity channel (ring + relative time)");
+  const int n = (int)n_sz;
+  cudaStream_t st = c->stream;
+  DeskewParams D{};
+  if (q_wxyz) {
+    const double qw = q_wxyz[0], qx = q_wxyz[1], qy = q_wxyz[2], qz = q_wxyz[3];
+    const double n2 = ((qx * qx + qy * qy) + qz * qz) + qw * qw;  // Eigen squaredNorm, coefficient order x y z w
+    D.enabled = 1;
+    if (n2 > 0.0) {
+      D.iw = qw / n2;
+      D.ix = -qx / n2;
+      D.iy = -qy / n2;
+      D.iz = -qz / n2;
+    }
+    D.tx = t3[0];
+    D.ty = t3[1];
+    D.tz = t3[2];
+    D.scan_period = scan_period;
+  }
+  void* staging = c->get(n_sz * stride);
+  float4* pts = (float4*)c->get(sizeof(float4) * n_sz);
+  float* d_bbox = (float*)c->get(sizeof(float) * 6 * kBboxBlocks);
+  if (!staging || !pts || !d_bbox) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (pre-step)");
+  CK(c, cudaMemcpyAsync(staging, points, n_sz * stride, cudaMemcpyHostToDevice, st));
+  k_pre_ingest<<<kBboxBlocks, 256, 0, st>>>((const unsigned char*)staging, stride, inten_off, n, D, pts, d_bbox);
+  CKL(c);
+  c->put(staging);
+  if (!(leaf > 0.f)) {  // de-skew only
+    c->put(d_bbox);
+    *d_out = pts;
+    *n_out = n;
+    return RGC_OK;
+  }
+  CK(c, cudaMemcpyAsync(c->h_bbox, d_bbox, sizeof(float) * 6 * kBboxBlocks, cudaMemcpyDeviceToHost, st));
+  CK(c, cudaStreamSynchronize(st));
+  c->put(d_bbox);
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (int b = 0; b < kBboxBlocks; b++)
+    for (int a = 0; a < 3; a++) {
+      mn[a] = std::min(mn[a], c->h_bbox[b * 6 + a]);
+      mx[a] = std::max(mx[a], c->h_bbox[b * 6 + 3 + a]);
+    }
+  // pcl::VoxelGrid::applyFilter (filters/impl/voxel_grid.hpp): float arithmetic throughout
+  VgGeom vg;
+  vg.inv_leaf = 1.0f / leaf;
+  long long dd[3];
+  for (int a = 0; a < 3; a++) dd[a] = (long long)((mx[a] - mn[a]) * vg.inv_leaf) + 1;
+  if (dd[0] * dd[1] * dd[2] > (long long)INT_MAX) {
+    // "Leaf size is too small for the input dataset. Integer indices would overflow.": PCL returns the input
+    if (passthrough) *passthrough = 1;
+    *d_out = pts;
+    *n_out = n;
+    return RGC_OK;
+  }
+  int div_b[3];
+  for (int a = 0; a < 3; a++) {
+    vg.min_b[a] = (int)std::floor(mn[a] * vg.inv_leaf);
+    div_b[a] = (int)std::floor(mx[a] * vg.inv_leaf) - vg.min_b[a] + 1;
+  }
+  vg.mul1 = div_b[0];
+  vg.mul2 = div_b[0] * div_b[1];
+  int key_bits = 1;
+  while (key_bits < 32 && (1ll << key_bits) < (long long)div_b[0] * div_b[1] * div_b[2]) key_bits++;
+  const int nblk_rs = div_up(n, RS_TILE), nblk_sc = div_up(n, 256 * kScanItems);
+  uint64_t* keys_a = (uint64_t*)c->get(8 * n_sz);
+  uint64_t* keys_b = (uint64_t*)c->get(8 * n_sz);
+  uint32_t* vals_a = (uint32_t*)c->get(4 * n_sz);
+  uint32_t* vals_b = (uint32_t*)c->get(4 * n_sz);
+  uint32_t* hist = (uint32_t*)c->get(4 * 256 * ((size_t)nblk_rs + 1));
+  unsigned int* blk = (unsigned int*)c->get(4 * ((size_t)nblk_sc + 1));
+  int* heads = (int*)c->get(4 * n_sz);
+  if (!keys_a || !keys_b || !vals_a || !vals_b || !hist || !blk || !heads) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (voxel filter)");
+  k_vg_keys<<<div_up(n, 256), 256, 0, st>>>(pts, n, vg, keys_a, vals_a);
+  CKL(c);
+  uint64_t* ks = keys_a;
+  uint32_t* vs = vals_a;
+  TRY(radix_sort_pairs(c, keys_a, keys_b, vals_a, vals_b, hist, n, key_bits, &ks, &vs));
+  k_vg_head_count<<<nblk_sc, 256, 0, st>>>(ks, n, blk);
+  CKL(c);
+  k_vg_scan_blocks<<<1, 1024, 0, st>>>(blk, nblk_sc);
+  CKL(c);
+  k_vg_heads<<<nblk_sc, 256, 0, st>>>(ks, n, blk, heads);
+  CKL(c);
+  CK(c, cudaMemcpyAsync(c->h_counts, blk + nblk_sc, 4, cudaMemcpyDeviceToHost, st));
+  CK(c, cudaStreamSynchronize(st));
+  const int nv = (int)c->h_counts[0];
+  float4* out = (float4*)c->get(sizeof(float4) * (size_t)nv);
+  if (!out) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (voxel filter output)");
+  k_vg_centroid<<<div_up(nv, 128), 128, 0, st>>>(pts, vs, heads, nv, n, out);
+  CKL(c);
+  c->put(keys_a);
+  c->put(keys_b);
+  c->put(vals_a);
+  c->put(vals_b);
+  c->put(hist);
+  c->put(blk);
+  c->put(heads);
+  c->put(pts);
+  *d_out = out;
+  *n_out = nv;
   return RGC_OK;
 }
 
@@ -1266,6 +1383,58 @@ int rgc_reg_set_allreduce(rgc_reg* r, rgc_reduce_fn fn, void* user, void* d_buf)
   r->reduce_user = user;
   r->reduce_buf = (double*)d_buf;
   return RGC_OK;
+}
+
+// ---- pre-step (include/rgc_preprocess.h) ----
+static int pre_to_host(rgc_ctx* c, const void* pts, size_t n, size_t stride, size_t inten_off, float leaf, const double* q, const double* t, float period,
+                       float* out_xyzi, size_t cap, size_t* n_out, int* passthrough) {
+  if (!c || !n_out) return RGC_ERR_INVALID;
+  CK(c, cudaSetDevice(c->device));
+  float4* d = nullptr;
+  int m = 0;
+  TRY(pre_filter(c, pts, n, stride, inten_off, leaf, q, t, period, &d, &m, passthrough));
+  *n_out = (size_t)m;
+  if (out_xyzi && cap > 0) CK(c, cudaMemcpyAsync(out_xyzi, d, sizeof(float4) * std::min((size_t)m, cap), cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  c->put(d);
+  return RGC_OK;
+}
+int rgc_voxel_grid(rgc_ctx* c, const void* pts, size_t n, size_t stride, size_t inten_off, float leaf, float* out_xyzi, size_t cap, size_t* n_out, int* passthrough) {
+  if (c && !(leaf > 0.f)) FAIL(c, RGC_ERR_INVALID, "leaf size must be positive");
+  return pre_to_host(c, pts, n, stride, inten_off, leaf, nullptr, nullptr, 0.f, out_xyzi, cap, n_out, passthrough);
+}
+int rgc_deskew(rgc_ctx* c, const void* pts, size_t n, size_t stride, size_t inten_off, const double* q_wxyz, const double* t3, float scan_period, float* out_xyzi) {
+  if (!q_wxyz || !t3 || !out_xyzi) return RGC_ERR_INVALID;
+  size_t m = 0;
+  return pre_to_host(c, pts, n, stride, inten_off, 0.f, q_wxyz, t3, scan_period, out_xyzi, n, &m, nullptr);
+}
+static int set_cloud_filtered(rgc_reg* r, Cloud& cl, const void* pts, size_t n, size_t stride, size_t inten_off, float leaf, const double* q, const double* t,
+                              float period, uint64_t key, size_t* n_out) {
+  rgc_ctx* c = r->ctx;
+  CK(c, cudaSetDevice(c->device));
+  if (key != 0 && cl.valid && cl.key == key) {
+    if (n_out) *n_out = (size_t)cl.n;
+    return RGC_OK;
+  }
+  r->have_corr = false;
+  if (&cl == &r->tgt) r->vox_valid = false;
+  SideLane side(c, &cl == &r->src);
+  float4* d = nullptr;
+  int m = 0;
+  TRY(pre_filter(c, pts, n, stride, inten_off, leaf, q, t, period, &d, &m, nullptr));
+  int rc = cloud_build(c, cl, d, (size_t)m, sizeof(float4), true, key, r->prm.grid_cell);
+  c->put(d);  // same lane, stream-ordered reuse
+  if (rc != RGC_OK) return rc;
+  if (n_out) *n_out = (size_t)m;
+  return cloud_covariances(c, cl, r->prm.k_correspondences, r->prm.regularization, true);
+}
+int rgc_reg_set_source_filtered(rgc_reg* r, const void* pts, size_t n, size_t stride, size_t inten_off, float leaf, const double* q_wxyz, const double* t3,
+                                float scan_period, uint64_t key, size_t* n_out) {
+  return r ? set_cloud_filtered(r, r->src, pts, n, stride, inten_off, leaf, q_wxyz, t3, scan_period, key, n_out) : RGC_ERR_INVALID;
+}
+int rgc_reg_set_target_filtered(rgc_reg* r, const void* pts, size_t n, size_t stride, size_t inten_off, float leaf, const double* q_wxyz, const double* t3,
+                                float scan_period, uint64_t key, size_t* n_out) {
+  return r ? set_cloud_filtered(r, r->tgt, pts, n, stride, inten_off, leaf, q_wxyz, t3, scan_period, key, n_out) : RGC_ERR_INVALID;
 }
 
 int rgc_reg_stage_ms(const rgc_reg* r, float* ms7) {

@@ -1,0 +1,113 @@
+"""GPU parity of the pre-step (include/rgc_preprocess.h) against the oracle:
+pcl::VoxelGrid centroids bit-exact, de-skew within one float ulp, and the fused
+de-skew -> voxel filter -> setInput* path against the same stages run one by one."""
+import numpy as np
+import pytest
+
+from conftest import rot_angle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rgc():
+    import rgc_slam_b200
+    return rgc_slam_b200
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import oracle
+    return oracle
+
+
+def _stamp(xyz1, seed):
+    """(x, y, z, ring + 0.1 * relative time), the intensity channel scanRegistration.cpp:207-210 writes"""
+    rng = np.random.default_rng(seed)
+    P = np.array(xyz1, np.float32, copy=True)
+    P[:, 3] = rng.integers(0, 16, len(P)) + np.float32(0.1) * rng.uniform(0, 1, len(P)).astype(np.float32)
+    return P
+
+
+@pytest.mark.parametrize("leaf", [0.2, 0.3, 1.0])
+def test_voxel_grid_bitexact(rgc, orc, scan_pair, leaf):
+    src, tgt, _ = scan_pair
+    for cloud in (_stamp(tgt, 1), _stamp(src[:1000], 2), _stamp(src[:1], 3)):
+        V = rgc.voxel_grid(cloud, leaf)
+        W = orc.voxel_grid(cloud, leaf)
+        assert V.shape == W.shape and np.array_equal(V, W)
+    assert len(rgc.voxel_grid(_stamp(tgt, 1), leaf)) < len(tgt)
+
+
+def test_voxel_grid_submap_and_edges(rgc, orc):
+    import bench
+    tgt = _stamp(bench.build_workload(0, 200_000, 1)[0]["tgt"], 4)
+    V, W = rgc.voxel_grid(tgt, 0.3), orc.voxel_grid(tgt, 0.3)
+    assert np.array_equal(V, W) and len(V) < len(tgt) // 2          # the submap really is thinned
+    one = np.array([[1.0, 2.0, 3.0, 7.0]], np.float32)
+    assert np.array_equal(rgc.voxel_grid(np.repeat(one, 9, 0), 0.2), one)
+    far = np.array([[0, 0, 0, 0], [3000, 3000, 3000, 1]], np.float32)
+    assert np.array_equal(rgc.voxel_grid(far, 0.001), far)          # int32 index overflow: input returned (PCL)
+    with pytest.raises(rgc.RgcError):
+        rgc.voxel_grid(one, 0.0)
+    rng = np.random.default_rng(0)                                  # many points per voxel, long sequential sums
+    D = np.zeros((50000, 4), np.float32)
+    D[:, :3] = rng.uniform(0, 2, (50000, 3))
+    D[:, 3] = rng.uniform(0, 255, 50000)
+    assert np.array_equal(rgc.voxel_grid(D, 0.5), orc.voxel_grid(D, 0.5))
+
+
+def test_deskew(rgc, orc, scan_pair):
+    src, _, _ = scan_pair
+    P = _stamp(src, 5)
+    q = np.array([0.99968, 0.004, -0.011, 0.0225])
+    q /= np.linalg.norm(q)
+    t = np.array([0.31, -0.04, 0.012])
+    G, O = rgc.deskew(P, q, t), orc.deskew(P, q, t)
+    assert np.array_equal(G[:, 3], P[:, 3])
+    ulp = np.spacing(np.abs(O[:, :3]).astype(np.float32))
+    assert (np.abs(G[:, :3] - O[:, :3]) <= ulp).all()               # device sin / acos vs glibc: at most the last bit
+    assert (G[:, :3] == O[:, :3]).mean() > 0.999
+    assert np.array_equal(rgc.deskew(P, [1, 0, 0, 0], [0, 0, 0]), P)
+    assert np.abs(G[:, :3] - P[:, :3]).max() > 0.05                 # and it does move points
+
+
+def test_fused_front_end_equals_staged(rgc, orc, scan_pair):
+    src, tgt, _ = scan_pair
+    S, T = _stamp(src, 6), _stamp(tgt, 7)
+    q = np.array([0.99995, 0.001, -0.002, 0.009])
+    q /= np.linalg.norm(q)
+    t = np.array([0.12, 0.01, -0.004])
+
+    def xyz1(V):
+        W = V.copy()
+        W[:, 3] = 1.0
+        return W
+
+    # staged on the GPU: each stage returns to the host
+    Sg = rgc.voxel_grid(rgc.deskew(S, q, t), 0.2)
+    Tg = rgc.voxel_grid(T, 0.3)
+    a = rgc.FastGICP()
+    a.setMaxCorrespondenceDistance(2.0)
+    a.setInputTarget(xyz1(Tg))
+    a.setInputSource(xyz1(Sg))
+    Ta = a.align()
+    # fused: raw clouds in, nothing leaves the device between de-skew, filter and the registration
+    b = rgc.FastGICP()
+    b.setMaxCorrespondenceDistance(2.0)
+    assert b.setInputTargetFiltered(T, 0.3) == len(Tg)
+    assert b.setInputSourceFiltered(S, 0.2, q, t) == len(Sg)
+    Tb = b.align()
+    assert np.array_equal(Ta, Tb)
+    assert a.last_result["iterations"] == b.last_result["iterations"]
+    # the oracle pipeline (its de-skew may differ in the last float bit of a few points)
+    o = orc.FastGICP(corr_dist=2.0)
+    o.setInputTarget(xyz1(orc.voxel_grid(T, 0.3)))
+    o.setInputSource(xyz1(orc.voxel_grid(orc.deskew(S, q, t), 0.2)))
+    To = o.align()
+    assert np.abs(Tb[:3, 3].astype(np.float64) - To[:3, 3]).max() < 1e-4
+    assert rot_angle(Tb[:3, :3], To[:3, :3]) < 1e-5
+    # identity caching: the same array object again is a no-op (no kernel is launched)
+    n0 = b.ctx.launch_count
+    assert b.setInputSourceFiltered(S, 0.2, q, t) == len(Sg)
+    assert b.ctx.launch_count == n0
