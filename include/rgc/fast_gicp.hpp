@@ -29,9 +29,11 @@
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../rgc_gicp.h"
+#include "../rgc_preprocess.h"
 
 #if !defined(RGC_WITH_PCL) && defined(__has_include)
 #if __has_include(<pcl/registration/registration.h>)
@@ -77,6 +79,13 @@ class Core {
   void push() { check(ctx_, rgc_reg_set_params(reg_, &prm_)); }
   void setSource(const void* pts, size_t n, size_t stride, uint64_t key) { check(ctx_, rgc_reg_set_source(reg_, pts, n, stride, key)); n_src_ = n; }
   void setTarget(const void* pts, size_t n, size_t stride, uint64_t key) { check(ctx_, rgc_reg_set_target(reg_, pts, n, stride, key)); n_tgt_ = n; }
+  size_t setFiltered(bool source, const void* pts, size_t n, size_t stride, size_t inten_off, float leaf, const double* q_wxyz, const double* t3,
+                     float scan_period, uint64_t key) {
+    size_t m = 0;
+    check(ctx_, (source ? rgc_reg_set_source_filtered : rgc_reg_set_target_filtered)(reg_, pts, n, stride, inten_off, leaf, q_wxyz, t3, scan_period, key, &m));
+    (source ? n_src_ : n_tgt_) = m;
+    return m;
+  }
   void align(const float* guess16, float* final16, float* out_points) {
     check(ctx_, rgc_reg_align(reg_, guess16, final16, &res_, out_points));
   }
@@ -95,6 +104,19 @@ class Core {
   rgc_params prm_;
   rgc_result res_{};
   size_t n_src_ = 0, n_tgt_ = 0;
+};
+
+// byte offset of PointT::intensity, or RGC_NO_INTENSITY for point types without one
+template <class P, class = void>
+struct IntensityOffset {
+  static size_t get() { return RGC_NO_INTENSITY; }
+};
+template <class P>
+struct IntensityOffset<P, decltype((void)std::declval<P&>().intensity)> {
+  static size_t get() {
+    P p{};
+    return (size_t)(reinterpret_cast<const char*>(&p.intensity) - reinterpret_cast<const char*>(&p));
+  }
 };
 }  // namespace detail
 
@@ -149,11 +171,29 @@ class FastGICP {
   // shared_ptr identity decides whether anything is recomputed (fast_gicp_impl.hpp:72-91)
   void setInputSource(const PointCloudSourceConstPtr& cloud) {
     source_ = cloud;
+    filtered_source_ = false;
     core_.setSource(cloud->points.data(), cloud->size(), sizeof(PointSource), (uint64_t)(uintptr_t)cloud.get());
   }
   void setInputTarget(const PointCloudTargetConstPtr& cloud) {
     target_ = cloud;
     core_.setTarget(cloud->points.data(), cloud->size(), sizeof(PointTarget), (uint64_t)(uintptr_t)cloud.get());
+  }
+  // The frame's front end fused into setInput* (include/rgc_preprocess.h): [adjustDistortion with
+  // q_last_curr (w, x, y, z) / t_last_curr, RGC_odometer.cpp:1441-1481] -> pcl::VoxelGrid(leaf)
+  // (:975-991) -> setInputSource / setInputTarget, without the cloud leaving the device.  Returns
+  // the size of the filtered cloud.  align()'s output cloud then has that many points.
+  size_t setInputSourceFiltered(const PointCloudSourceConstPtr& cloud, float leaf, const double* q_last_curr_wxyz = nullptr,
+                                const double* t_last_curr = nullptr, float scan_period = 0.1f) {
+    source_ = cloud;
+    filtered_source_ = true;
+    return core_.setFiltered(true, cloud->points.data(), cloud->size(), sizeof(PointSource), detail::IntensityOffset<PointSource>::get(), leaf,
+                             q_last_curr_wxyz, t_last_curr, scan_period, (uint64_t)(uintptr_t)cloud.get());
+  }
+  size_t setInputTargetFiltered(const PointCloudTargetConstPtr& cloud, float leaf, const double* q_last_curr_wxyz = nullptr,
+                                const double* t_last_curr = nullptr, float scan_period = 0.1f) {
+    target_ = cloud;
+    return core_.setFiltered(false, cloud->points.data(), cloud->size(), sizeof(PointTarget), detail::IntensityOffset<PointTarget>::get(), leaf,
+                             q_last_curr_wxyz, t_last_curr, scan_period, (uint64_t)(uintptr_t)cloud.get());
   }
   void swapSourceAndTarget() {
     detail::check(core_.ctx_, rgc_reg_swap_source_and_target(core_.reg_));
@@ -181,7 +221,8 @@ class FastGICP {
   void align(PointCloudSource& output, const Matrix4& guess) {
     std::vector<float> pts(4 * core_.n_src_);
     core_.align(guess.data(), final_.data(), pts.data());
-    if (source_) output = *source_;  // copies the non-geometric fields, like PCL
+    if (source_ && !filtered_source_) output = *source_;  // copies the non-geometric fields, like PCL
+    else output = PointCloudSource();                     // filtered source: centroids have no per-point fields to copy
     output.resize(core_.n_src_);
     for (size_t i = 0; i < core_.n_src_; i++) {
       output[i].x = pts[4 * i];
@@ -212,6 +253,7 @@ class FastGICP {
  private:
   detail::Core core_;
   PointCloudSourceConstPtr source_;
+  bool filtered_source_ = false;
   PointCloudTargetConstPtr target_;
   Matrix4 final_ = identity4();
 };

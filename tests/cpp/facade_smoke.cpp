@@ -65,5 +65,16 @@ int main(int argc, char** argv) {
     std::printf("vgicp converged %d iterations %d fitness %.9g\n", (int)vgicp.hasConverged(), vgicp.lastResult().iterations, vgicp.getFitnessScore());
     for (int r = 0; r < 4; r++) std::printf("%.9g %.9g %.9g %.9g\n", T[r], T[4 + r], T[8 + r], T[12 + r]);
   }
+  {  // the frame's front end fused into setInput* (voxel filters of RGC_odometer.cpp:975-991)
+    rgc::FastGICP<PointT, PointT> gicp;
+    gicp.setMaxCorrespondenceDistance(2);
+    const size_t nt = gicp.setInputTargetFiltered(target, 0.3f);
+    const size_t ns = gicp.setInputSourceFiltered(source, 0.2f);
+    gicp.align(aligned, T2);
+    const rgc::Matrix4f& T = gicp.getFinalTransformation();
+    std::printf("filtered converged %d iterations %d n_source %zu n_target %zu aligned %zu\n", (int)gicp.hasConverged(), gicp.lastResult().iterations, ns, nt,
+                aligned.size());
+    for (int r = 0; r < 4; r++) std::printf("%.9g %.9g %.9g %.9g\n", T[r], T[4 + r], T[8 + r], T[12 + r]);
+  }
   return 0;
 }

@@ -42,3 +42,18 @@ def test_cpp_facade_matches_oracle(small_pair, tmp_path):
     Tov = ov.align()
     assert vhead[0] == "vgicp" and int(vhead[2]) == int(ov.last["converged"]) and int(vhead[4]) == ov.last["iterations"]
     assert np.abs(Tv[:3, 3] - Tov[:3, 3]).max() < 1e-4 and rot_angle(Tv[:3, :3], Tov[:3, :3]) < 1e-5
+    # third block: the fused front end (voxel filters + setInput*) equals the Python binding's
+    fhead = out[10].split()
+    Tf = np.array([[float(v) for v in out[11 + r].split()] for r in range(4)])
+    import rgc_slam_b200 as rgc
+    S, T_ = src.copy(), tgt.copy()
+    S[:, 3] = np.arange(len(S), dtype=np.float32)      # facade_smoke.cpp's load() stores the point index as intensity
+    T_[:, 3] = np.arange(len(T_), dtype=np.float32)
+    g = rgc.FastGICP()
+    g.setMaxCorrespondenceDistance(2.0)
+    nt = g.setInputTargetFiltered(T_, 0.3)
+    ns = g.setInputSourceFiltered(S, 0.2)
+    Tg = g.align()
+    assert fhead[0] == "filtered" and int(fhead[6]) == ns and int(fhead[8]) == nt and int(fhead[10]) == ns
+    assert int(fhead[4]) == g.last_result["iterations"]
+    assert np.abs(Tf - Tg).max() < 1e-6
