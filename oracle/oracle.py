@@ -366,5 +366,39 @@ def voxel_grid(xyzi, leaf):
     return out[:m].copy()
 
 
+def _assoc(fn_name, map_pts, feats, q_wxyz, t, n_out2):
+    M, F = _pts(map_pts), np.ascontiguousarray(feats, np.float32)
+    q, tt = np.ascontiguousarray(q_wxyz, np.float64), np.ascontiguousarray(t, np.float64)
+    n = len(F)
+    valid = np.zeros(n, np.int32)
+    o1 = np.zeros((n, 3), np.float64)
+    o2 = np.zeros((n, 3) if n_out2 == 3 else (n,), np.float64)
+    fn = getattr(lib(), fn_name)
+    fn.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    fn.restype = None
+    fn(M.ctypes.data, len(M), F.ctypes.data, n, q.ctypes.data, tt.ctypes.data, valid.ctypes.data, o1.ctypes.data, o2.ctypes.data)
+    return valid.astype(bool), o1, o2
+
+
+def assoc_edges(map_pts, feats, q_wxyz, t):
+    """RGC_mapping.cpp:1093-1136: (valid, point_a, point_b) per edge feature (x, y, z, weight)"""
+    return _assoc("orc_assoc_edges", map_pts, feats, q_wxyz, t, 3)
+
+
+def assoc_planes(map_pts, feats, q_wxyz, t):
+    """RGC_mapping.cpp:1192-1240: (valid, unit normal, negative_OA_dot_norm) per planar feature"""
+    return _assoc("orc_assoc_planes", map_pts, feats, q_wxyz, t, 1)
+
+
+def colpiv_qr_solve_5x3(A, b):
+    A, b = np.ascontiguousarray(A, np.float64), np.ascontiguousarray(b, np.float64)
+    x = np.zeros(3)
+    L = lib()
+    L.orc_colpiv_qr_solve_5x3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_colpiv_qr_solve_5x3.restype = None
+    L.orc_colpiv_qr_solve_5x3(A.ctypes.data, b.ctypes.data, x.ctypes.data)
+    return x
+
+
 def max_threads() -> int:
     return lib().orc_max_threads()

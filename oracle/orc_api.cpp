@@ -6,6 +6,7 @@
 
 #include "orc_features.hpp"
 #include "orc_gicp.hpp"
+#include "orc_mapping.hpp"
 #include "orc_preprocess.hpp"
 
 using namespace orc;
@@ -16,6 +17,19 @@ static void cp(T* dst, const std::vector<T>& v) {
 }
 
 extern "C" {
+
+// ---- mapping-node association ----
+void orc_assoc_edges(const float* map, int nm, const float* feats, int n, const double* q, const double* t, int* valid, double* pa, double* pb) {
+  MapAssoc m;
+  m.build(map, nm);
+  m.edges(feats, n, q, t, valid, pa, pb);
+}
+void orc_assoc_planes(const float* map, int nm, const float* feats, int n, const double* q, const double* t, int* valid, double* norm, double* dist) {
+  MapAssoc m;
+  m.build(map, nm);
+  m.planes(feats, n, q, t, valid, norm, dist);
+}
+void orc_colpiv_qr_solve_5x3(const double* A, const double* b, double* x) { colpiv_qr_solve_5x3(A, b, x); }
 
 // ---- pre-step: de-skew and pcl::VoxelGrid ----
 void orc_deskew(const float* xyzi, int n, const double* q_wxyz, const double* t3, float scan_period, float* out) { deskew(xyzi, n, q_wxyz, t3, scan_period, out); }

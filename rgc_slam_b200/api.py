@@ -86,6 +86,10 @@ def lib():
         L.rgc_reg_set_vgicp.argtypes = [vp, C.c_int, C.c_double, C.c_int, C.c_int]
         L.rgc_reg_last_inliers.argtypes = [vp, C.POINTER(C.c_int)]
         L.rgc_reg_get_voxels.argtypes = [vp, vp, vp, vp, vp, sz, C.POINTER(sz)]
+        L.rgc_map_create.argtypes = [vp, vp, sz, sz, C.POINTER(vp)]
+        L.rgc_map_destroy.argtypes = [vp]
+        for name in ("rgc_map_associate_edges", "rgc_map_associate_planes"):
+            getattr(L, name).argtypes = [vp, vp, sz, sz, vp, vp, vp, vp, vp, C.POINTER(sz)]
         L.rgc_voxel_grid.argtypes = [vp, vp, sz, sz, sz, C.c_float, vp, sz, C.POINTER(sz), C.POINTER(C.c_int)]
         L.rgc_deskew.argtypes = [vp, vp, sz, sz, sz, vp, vp, C.c_float, vp]
         for name in ("rgc_reg_set_source_filtered", "rgc_reg_set_target_filtered"):
@@ -104,6 +108,7 @@ EXPORTED_SYMBOLS = [
     "rgc_reg_get_final_transformation", "rgc_knn", "rgc_reg_stage_ms", "rgc_knn_self", "rgc_reg_set_owner_slab", "rgc_reg_set_allreduce",
     "rgc_ctx_set_profiling", "rgc_ctx_last_kernel_ms", "rgc_reg_set_vgicp", "rgc_reg_get_voxels", "rgc_reg_last_inliers",
     "rgc_voxel_grid", "rgc_deskew", "rgc_reg_set_source_filtered", "rgc_reg_set_target_filtered",
+    "rgc_map_create", "rgc_map_destroy", "rgc_map_associate_edges", "rgc_map_associate_planes",
 ]
 
 
@@ -452,6 +457,48 @@ def knn(points, queries, k, ctx: Context | None = None, grid_cell: float = 0.0):
     d2 = np.empty((m, k), np.float32)
     ctx.check(lib().rgc_knn(ctx._h, pp, n, ps, qp, m, qs, k, idx.ctypes.data, d2.ctypes.data, grid_cell))
     return idx, d2
+
+
+class FeatureMap:
+    """kdtree*FromMap of the mapping node (RGC_mapping.cpp:1073-1074) + the association loops that query it
+    (include/rgc_mapping.h).  points: [n, >=3] float32 map points; features: [m, >=3] float32."""
+
+    def __init__(self, points, ctx: Context | None = None):
+        self.ctx = ctx or default_context(0)
+        P = np.ascontiguousarray(points, np.float32)
+        self._h = C.c_void_p()
+        self.ctx.check(lib().rgc_map_create(self.ctx._h, P.ctypes.data, P.shape[0], P.strides[0], C.byref(self._h)))
+        self.n = P.shape[0]
+
+    def close(self):
+        if self._h and self.ctx._h:
+            lib().rgc_map_destroy(self._h)
+        self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _assoc(self, fn, feats, q_wxyz, t, plane):
+        F = np.ascontiguousarray(feats, np.float32)
+        q, tt = np.ascontiguousarray(q_wxyz, np.float64), np.ascontiguousarray(t, np.float64)
+        n = F.shape[0]
+        valid = np.zeros(n, np.int32)
+        o1 = np.zeros((n, 3), np.float64)
+        o2 = np.zeros(n if plane else (n, 3), np.float64)
+        nv = C.c_size_t(0)
+        self.ctx.check(fn(self._h, F.ctypes.data, n, F.strides[0], q.ctypes.data, tt.ctypes.data, valid.ctypes.data, o1.ctypes.data, o2.ctypes.data, C.byref(nv)))
+        return valid.astype(bool), o1, o2
+
+    def associate_edges(self, feats, q_w_curr_wxyz, t_w_curr):
+        """-> (valid, point_a, point_b): the arguments of LidarEdgeFactor::Create per feature"""
+        return self._assoc(lib().rgc_map_associate_edges, feats, q_w_curr_wxyz, t_w_curr, False)
+
+    def associate_planes(self, feats, q_w_curr_wxyz, t_w_curr):
+        """-> (valid, norm, negative_OA_dot_norm): the arguments of LidarPlaneNormFactor::Create per feature"""
+        return self._assoc(lib().rgc_map_associate_planes, feats, q_w_curr_wxyz, t_w_curr, True)
 
 
 def voxel_grid(xyzi, leaf, ctx: Context | None = None):

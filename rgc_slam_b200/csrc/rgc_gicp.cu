@@ -20,6 +20,9 @@
 #include "rgc_ctx.hpp"
 #include "rgc_kernels.cuh"
 #include "rgc_lm.hpp"
+#include "../../include/rgc_mapping.h"
+#include "../../include/rgc_preprocess.h"
+#include "rgc_mapping.cuh"
 #include "rgc_preprocess.cuh"
 #include "rgc_vgicp.cuh"
 
@@ -1435,6 +1438,83 @@ int rgc_reg_set_source_filtered(rgc_reg* r, const void* pts, size_t n, size_t st
 int rgc_reg_set_target_filtered(rgc_reg* r, const void* pts, size_t n, size_t stride, size_t inten_off, float leaf, const double* q_wxyz, const double* t3,
                                 float scan_period, uint64_t key, size_t* n_out) {
   return r ? set_cloud_filtered(r, r->tgt, pts, n, stride, inten_off, leaf, q_wxyz, t3, scan_period, key, n_out) : RGC_ERR_INVALID;
+}
+
+// ---- mapping-node association (include/rgc_mapping.h) ----
+struct rgc_map {
+  rgc_ctx* ctx = nullptr;
+  Cloud cl;
+};
+int rgc_map_create(rgc_ctx* c, const void* pts, size_t n, size_t stride, rgc_map** out) {
+  if (!c || !out) return RGC_ERR_INVALID;
+  *out = nullptr;
+  CK(c, cudaSetDevice(c->device));
+  rgc_map* m = new rgc_map();
+  m->ctx = c;
+  int rc = cloud_build(c, m->cl, pts, n, stride, false, 0, 0.f);
+  if (rc != RGC_OK) {
+    cloud_release(c, m->cl);
+    delete m;
+    return rc;
+  }
+  *out = m;
+  return RGC_OK;
+}
+int rgc_map_destroy(rgc_map* m) {
+  if (!m) return RGC_OK;
+  cudaSetDevice(m->ctx->device);
+  cloud_release(m->ctx, m->cl);
+  delete m;
+  return RGC_OK;
+}
+}  // extern "C" (templates need C++ linkage)
+template <bool PLANE>
+static int map_associate(rgc_map* m, const void* feats, size_t n_sz, size_t stride, const double* q, const double* t, int32_t* valid, double* o1, double* o2,
+                         size_t* n_valid) {
+  if (!m || !feats || !q || !t || !valid || !o1 || !o2) return RGC_ERR_INVALID;
+  rgc_ctx* c = m->ctx;
+  CK(c, cudaSetDevice(c->device));
+  if (n_sz == 0 || n_sz > 0x7fffffff / 32) FAIL(c, RGC_ERR_INVALID, "feature count out of range");
+  if (stride < 12 || stride % 4) FAIL(c, RGC_ERR_INVALID, "point stride must be a multiple of 4 and >= 12 bytes");
+  const int n = (int)n_sz;
+  const size_t w2 = PLANE ? 1 : 3;
+  void* staging = c->get(n_sz * stride);
+  int* d_valid = (int*)c->get(4 * n_sz);
+  double* d_o1 = (double*)c->get(24 * n_sz);
+  double* d_o2 = (double*)c->get(8 * w2 * n_sz);
+  if (!staging || !d_valid || !d_o1 || !d_o2) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (association)");
+  cudaStream_t st = c->stream;
+  CK(c, cudaMemcpyAsync(staging, feats, n_sz * stride, cudaMemcpyHostToDevice, st));
+  CK(c, cudaMemsetAsync(d_o1, 0, 24 * n_sz, st));
+  CK(c, cudaMemsetAsync(d_o2, 0, 8 * w2 * n_sz, st));
+  const PoseQ T{q[0], q[1], q[2], q[3], t[0], t[1], t[2]};
+  const int spread = query_spread(n);
+  k_map_assoc<PLANE><<<div_up(n * spread, kThreads), kThreads, (size_t)5 * kThreads * 8, st>>>(m->cl.view, (const unsigned char*)staging, stride, n, spread, T, d_valid,
+                                                                                          d_o1, d_o2);
+  CKL(c);
+  CK(c, cudaMemcpyAsync(valid, d_valid, 4 * n_sz, cudaMemcpyDeviceToHost, st));
+  CK(c, cudaMemcpyAsync(o1, d_o1, 24 * n_sz, cudaMemcpyDeviceToHost, st));
+  CK(c, cudaMemcpyAsync(o2, d_o2, 8 * w2 * n_sz, cudaMemcpyDeviceToHost, st));
+  CK(c, cudaStreamSynchronize(st));
+  c->put(staging);
+  c->put(d_valid);
+  c->put(d_o1);
+  c->put(d_o2);
+  if (n_valid) {
+    size_t k = 0;
+    for (size_t i = 0; i < n_sz; i++) k += valid[i] != 0;
+    *n_valid = k;
+  }
+  return RGC_OK;
+}
+extern "C" {
+int rgc_map_associate_edges(rgc_map* m, const void* feats, size_t n, size_t stride, const double* q, const double* t, int32_t* valid, double* pa, double* pb,
+                            size_t* n_valid) {
+  return map_associate<false>(m, feats, n, stride, q, t, valid, pa, pb, n_valid);
+}
+int rgc_map_associate_planes(rgc_map* m, const void* feats, size_t n, size_t stride, const double* q, const double* t, int32_t* valid, double* norm, double* dist,
+                             size_t* n_valid) {
+  return map_associate<true>(m, feats, n, stride, q, t, valid, norm, dist, n_valid);
 }
 
 int rgc_reg_stage_ms(const rgc_reg* r, float* ms7) {
