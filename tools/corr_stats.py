@@ -20,3 +20,9 @@ print("slowest:", [(int(cyc[i]), int(nodes[i]), int(look[i]), int(cand[i])) for 
 w = cyc.reshape(-1)[: (n // 32) * 32].reshape(-1, 32)
 print("per-warp(32 consecutive) max cycles: mean %.0f p50 %.0f p99 %.0f max %d" % (w.max(1).mean(), np.percentile(w.max(1), 50), np.percentile(w.max(1), 99), w.max()))
 print("cycles per lookup+cand (mean)", cyc.mean() / (look.mean() + cand.mean()))
+# who is slow: distance of the found neighbour, and whether there is one at all (after 3 reps the search is hinted)
+corr, d2 = g.correspondences()
+inv = np.empty(n, np.int64)
+# stats are in SORTED source order; correspondences come back in original order: compare distributions only
+print("matched %.3f, d2 quantiles (matched) p50 %.4f p90 %.4f p99 %.4f max %.3f" % ((corr >= 0).mean(), *np.percentile(d2[corr >= 0], [50, 90, 99]), d2[corr >= 0].max()))
+print("cycle quantiles p99.9/p50 = %.1f ; share of total cycles in the slowest 1%% of queries: %.3f" % (np.percentile(cyc, 99.9) / np.percentile(cyc, 50), np.sort(cyc)[-n // 100:].sum() / cyc.sum()))
