@@ -46,18 +46,25 @@ namespace rgc {
 enum class RegularizationMethod { NONE, MIN_EIG, NORMALIZED_MIN_EIG, PLANE, FROBENIUS };  // gicp_settings.hpp:6
 enum class LSQ_OPTIMIZER_TYPE { GaussNewton, LevenbergMarquardt };                        // lsq_registration.hpp:13
 
-// process-wide context per device (the caller constructs a registration object every frame,
-// RGC_odometer.cpp:998, so nothing expensive may live in the object itself)
+// One context per (host thread, device): the caller constructs a registration object every frame
+// (RGC_odometer.cpp:998), so nothing expensive may live in the object itself, and a context (streams,
+// memory pool, pinned result buffers) must not be shared by threads running concurrently.  Threads
+// that each run their own registrations (batched loop-closure verification) overlap on the GPU.
 inline rgc_ctx* shared_context(int device = 0) {
-  static std::mutex mu;
-  static std::vector<rgc_ctx*> ctxs;
-  std::lock_guard<std::mutex> lock(mu);
-  if ((int)ctxs.size() <= device) ctxs.resize(device + 1, nullptr);
-  if (!ctxs[device]) {
-    if (rgc_ctx_create(device, &ctxs[device]) != RGC_OK)
+  struct Holder {
+    std::vector<rgc_ctx*> ctxs;
+    ~Holder() {
+      for (rgc_ctx* c : ctxs)
+        if (c) rgc_ctx_destroy(c);
+    }
+  };
+  static thread_local Holder h;
+  if ((int)h.ctxs.size() <= device) h.ctxs.resize(device + 1, nullptr);
+  if (!h.ctxs[device]) {
+    if (rgc_ctx_create(device, &h.ctxs[device]) != RGC_OK)
       throw std::runtime_error("rgc: no usable CUDA device " + std::to_string(device) + " (there is no CPU fallback)");
   }
-  return ctxs[device];
+  return h.ctxs[device];
 }
 
 namespace detail {

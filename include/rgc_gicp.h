@@ -17,7 +17,17 @@
  *     floats of every point (pcl::PointXYZ 16 B, PointXYZI 32 B, PointNormal 48 B —
  *     SRC/fast_gicp/gicp/fast_gicp.cpp:4-6).  The homogeneous coordinate is taken as 1.
  *   - there is NO CPU fallback: with no usable CUDA device rgc_ctx_create fails.
- *   - one rgc_reg per host thread; a ctx may serve several regs sequentially.
+ *   - threading: a context (its two CUDA streams, device-memory pool and pinned result buffers) and the
+ *     objects created from it belong to ONE host thread at a time, like the reference's registration
+ *     objects.  A context may serve any number of rgc_reg / rgc_map objects sequentially.  To run
+ *     registrations concurrently on one GPU (batched loop-closure verification) give every host thread
+ *     its own context: their kernels overlap on the device (tools/bench_c4.py).
+ *   - asynchrony: rgc_reg_set_source / set_target return once the cloud is uploaded and sorted; its
+ *     k-NN / covariance kernels keep running (source and target on separate streams) and are joined by
+ *     the first call that needs them (align, linearize, get_*_covs ...).  The input buffers are not
+ *     referenced after a setter returns.
+ *   - a call that fails part-way (allocation failure, CUDA error) does not recycle the pool blocks it had
+ *     taken; they are released with the context.
  */
 #ifndef RGC_GICP_H
 #define RGC_GICP_H
