@@ -90,7 +90,7 @@ class ClockSampler:
         self._stop = threading.Event()
         self.thr = None
         self.how = "nvml"
-        self.interval = float(os.environ.get("RGC_CLOCK_INTERVAL", "0.05"))
+        self.interval = float(os.environ.get("RGC_CLOCK_INTERVAL", "0.02"))
         self._nv = None
 
     def prepare(self):
