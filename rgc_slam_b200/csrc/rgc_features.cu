@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(256) k_feat_rings(const float4* __restrict__ r
   const float4* P = raw + in0;
   int* ring = tmp_ring + in0;
   float* inten = tmp_inten + in0;
-  __shared__ int s_first, s_last, s_half, s_count;
+  __shared__ int s_first, s_last, s_half;
   __shared__ int s_ring_cnt[kMaxRings], s_ring_off[kMaxRings + 1], s_ring_run[kMaxRings];
   __shared__ int s_warp_cnt[8][kMaxRings];
   __shared__ float s_start_ori, s_end_ori;
@@ -73,7 +73,6 @@ __global__ void __launch_bounds__(256) k_feat_rings(const float4* __restrict__ r
     s_first = 0x7fffffff;
     s_last = -1;
     s_half = 0x7fffffff;
-    s_count = 0;
   }
   if (tid < kMaxRings) s_ring_cnt[tid] = 0;
   __syncthreads();
@@ -439,7 +438,7 @@ __global__ void __launch_bounds__(256) k_feat_ground(const int* __restrict__ sca
   });
   __syncthreads();
   block_sum<6>(cov, s_out);
-  __shared__ double s_V[3][3], s_w[3];
+  __shared__ double s_V[3][3];
   __shared__ int s_order[3];
   if (threadIdx.x == 0) {
     Sym3 Cm = {s_out[0] / groundweights, s_out[1] / groundweights, s_out[2] / groundweights,
@@ -452,7 +451,6 @@ __global__ void __launch_bounds__(256) k_feat_ground(const int* __restrict__ sca
     if (w[o[1]] < w[o[0]]) { int t = o[0]; o[0] = o[1]; o[1] = t; }
     for (int c = 0; c < 3; c++) {
       s_order[c] = o[c];
-      s_w[c] = w[c];
       for (int rr = 0; rr < 3; rr++) s_V[rr][c] = V[rr][c];
     }
     double n0 = V[0][o[0]], n1 = V[1][o[0]], n2 = V[2][o[0]];
@@ -711,10 +709,7 @@ __global__ void __launch_bounds__(128) k_feat_compact(int n_rings, FeatArrays A)
   int* dst[5] = {A.corner_sharp + (size_t)b * RGC_FEAT_CAP_SHARP(n_rings), A.corner_less_sharp + (size_t)b * RGC_FEAT_CAP_LESS_SHARP(n_rings),
                  A.surf_flat + (size_t)b * RGC_FEAT_CAP_FLAT(n_rings), A.inten_sharp + (size_t)b * RGC_FEAT_CAP_INTEN(n_rings),
                  A.inten_less_sharp + (size_t)b * RGC_FEAT_CAP_LESS_INTEN(n_rings)};
-  float* wdst[5] = {A.corner_sharp_w + (size_t)b * RGC_FEAT_CAP_SHARP(n_rings), nullptr, A.surf_flat_w + (size_t)b * RGC_FEAT_CAP_FLAT(n_rings),
-                    A.inten_sharp_w + (size_t)b * RGC_FEAT_CAP_INTEN(n_rings), nullptr};
-  const int out0 = 0;  // weights are looked up through the scan's per-point arrays below
-  (void)out0;
+  // (the per-feature weights are filled by k_feat_weights from the scan's per-point arrays)
   for (int s = threadIdx.x; s < nseg; s += blockDim.x)
     for (int L = 0; L < 5; L++) {
       const int c = A.seg_counts[(seg0 + s) * 5 + L];
@@ -725,7 +720,6 @@ __global__ void __launch_bounds__(128) k_feat_compact(int n_rings, FeatArrays A)
     const double sharp = (double)s_off[0][nseg], plane = (double)s_off[2][nseg];
     A.inten_merged[b] = (sharp / plane < 0.3) ? 1 : 0;  // :650-656 (NaN / inf compare false)
   }
-  (void)wdst;
 }
 
 // weights of the compacted lists (normal_x fields :501,:554,:609); one thread per list entry

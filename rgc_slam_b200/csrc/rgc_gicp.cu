@@ -398,8 +398,6 @@ static int launch_knn(rgc_ctx* c, const GridView& v, const float4* queries, int 
 static int launch_knn_self(rgc_ctx* c, const GridView& v, int n, int k, int* nbr) {
   // the warp-cooperative tile kernel; RGC_KNN_THREAD=1 selects the thread-per-query kernel (A/B)
   static const bool per_thread = std::getenv("RGC_KNN_THREAD") != nullptr;
-  static const bool force_tile = std::getenv("RGC_KNN_TILE") != nullptr;
-  (void)force_tile;
   if (per_thread) return launch_knn<true>(c, v, nullptr, n, k, nbr, nullptr);
   if (k > 32) FAIL(c, RGC_ERR_UNSUPPORTED, "k_correspondences > 32 is not supported");
   const size_t per_warp = sizeof(float4) * KT_CAND + sizeof(TileNode) * KT_STACK + (size_t)(k + KT_PEND) * 32 * 8;
@@ -696,13 +694,9 @@ static int gicp_linearize_launch(rgc_reg* r, const double* T, int want, const in
   const float thr2 = thr * thr;  // float product, +inf for the FLT_MAX default (fast_gicp_impl.hpp:136)
   const int spread = query_spread(r->src.n);
   if (c->profile) CK(c, cudaEventRecord(c->evk[0], c->stream));
-  // the warp-cooperative variant is exact too but measured slower on one sweep (155 vs 92 us for 22k
-  // queries: its serial node-by-node walk has a longer dependent-load chain); RGC_CORR_TILE=1 selects it
-  static const bool corr_tile = std::getenv("RGC_CORR_TILE") != nullptr;
-  if (!corr_tile)
-    k_correspond<<<div_up(r->src.n * spread, kThreads), kThreads, 0, c->stream>>>(r->tgt.view, r->src.sorted, r->src.n, spread, Tf, thr2, r->slab, hint, corr, sqd);
-  else
-    k_correspond_tile<<<div_up(r->src.n, KT_WARPS * 32), KT_WARPS * 32, 0, c->stream>>>(r->tgt.view, r->src.sorted, r->src.n, Tf, thr2, r->slab, corr, sqd);
+  // (a warp-cooperative variant of this search, one warp per 32 Morton-adjacent source points, was exact
+  // too but slower on one sweep, 155 vs 92 us: profiles/README.md; it was removed)
+  k_correspond<<<div_up(r->src.n * spread, kThreads), kThreads, 0, c->stream>>>(r->tgt.view, r->src.sorted, r->src.n, spread, Tf, thr2, r->slab, hint, corr, sqd);
   CKL(c);
   if (c->profile) CK(c, cudaEventRecord(c->evk[1], c->stream));
   k_linearize<<<reduce_grid(r->src.n), kThreads, 0, c->stream>>>(r->tgt.sorted, r->src.sorted, r->src.cov, r->tgt.cov, r->src.n, Td, want, corr, maha, r->partials,

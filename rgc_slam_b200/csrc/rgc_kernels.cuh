@@ -1014,151 +1014,6 @@ __global__ void __launch_bounds__(kThreads, 8) k_correspond(GridView tgt, const 
   sqd[i] = top.d0;
 }
 
-// Warp-cooperative version of k_correspond: one warp owns 32 Morton-adjacent source points, whose
-// transformed positions are spatially coherent, and walks the target octree ONCE for all of them
-// (same gather / lockstep-consume scheme as k_knn_tile, with k = 1 the "heap" is one packed key in
-// a register).  Table probes of a node's children (and of the root cells) are issued by different
-// lanes in parallel, which shortens the dependent-load chain that bounds the per-thread kernel on a
-// single sweep (91 us for 22k queries).
-__global__ void __launch_bounds__(KT_WARPS * 32) k_correspond_tile(GridView g, const float4* __restrict__ src, int n_src, RtF Tf, float thr2, Slab slab,
-                                                                   int* __restrict__ corr, float* __restrict__ sqd) {
-  __shared__ __align__(16) float4 s_cand[KT_WARPS][KT_CAND];
-  __shared__ TileNode s_stack[KT_WARPS][KT_STACK];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float4* cand = s_cand[warp];
-  TileNode* stack = s_stack[warp];
-  const int first = (blockIdx.x * KT_WARPS + warp) * 32;
-  if (first >= n_src) return;
-  const int i = first + lane;
-  const float4* pts4 = reinterpret_cast<const float4*>(g.pts);
-  float qx = 0.f, qy = 0.f, qz = 0.f;
-  bool need = false;
-  if (i < n_src) {
-    const float4 p = __ldg(&src[i]);
-    transform_f(Tf.m, p.x, p.y, p.z, qx, qy, qz);
-    need = slab_owns(slab, qx, qy, qz);
-  }
-  // ---- per-lane radius: the first non-empty cell around q bounds the NN distance by its diagonal
-  float lim2 = need ? thr2 : -1.f;  // inclusive; -1 = this lane never needs anything
-  if (need) {
-    const int fx = cell_coord(qx, g.ox, g.inv_s0), fy = cell_coord(qy, g.oy, g.inv_s0), fz = cell_coord(qz, g.oz, g.inv_s0);
-    for (int l = 0; l < g.nlevels; l++) {
-      const float edge = g.s0 * (float)(1 << l) + 2.f * g.margin;
-      const float diag2 = 3.f * edge * edge * 1.0001f;
-      if (diag2 >= lim2) break;
-      uint32_t s, e, m;
-      if (grid_lookup(g, l, fx >> l, fy >> l, fz >> l, s, e, m)) {
-        lim2 = diag2;
-        break;
-      }
-    }
-  }
-  unsigned long long best = ~0ull;
-  auto bound = [&]() { return best == ~0ull ? lim2 : fminf(key_d2(best), lim2); };
-  int ncand = 0;
-  auto consume = [&]() {
-    __syncwarp();
-    for (int j = 0; j < ncand; j++) {
-      const float4 c = cand[j];
-      const float d2 = dist2_ref(qx, qy, qz, c.x, c.y, c.z);
-      const unsigned long long key = pack_key(d2, __float_as_int(c.w));
-      if (d2 <= lim2 && key < best) best = key;
-    }
-    ncand = 0;
-    __syncwarp();
-  };
-  if (__any_sync(0xffffffffu, need)) {
-    // ---- roots covering the union of the balls
-    const float r = lim2 >= 0.f ? (lim2 < INFINITY ? sqrtf(lim2) * 1.00001f + 2.f * g.margin : INFINITY) : 0.f;
-    const float big = 3.0e38f;
-    const float lox = warp_min(need ? qx - r : big), loy = warp_min(need ? qy - r : big), loz = warp_min(need ? qz - r : big);
-    const float hix = warp_max(need ? qx + r : -big), hiy = warp_max(need ? qy + r : -big), hiz = warp_max(need ? qz + r : -big);
-    const float ext = fmaxf(fmaxf(hix - lox, hiy - loy), hiz - loz);
-    const int top_level = g.nlevels - 1;
-    int lb = 0;
-    while (lb < top_level && !(g.s0 * (float)(1 << lb) >= 0.5f * ext)) lb++;
-    const float inv_cs = g.inv_s0 / (float)(1 << lb);
-    const int ncell = 1 << (g.nbits - lb);
-    int rlo[3], rhi[3];
-    {
-      const float l3[3] = {lox, loy, loz}, h3[3] = {hix, hiy, hiz}, o3[3] = {g.ox, g.oy, g.oz};
-#pragma unroll
-      for (int a = 0; a < 3; a++) {
-        const float tl = (l3[a] - o3[a]) * inv_cs, th = (h3[a] - o3[a]) * inv_cs;
-        const int il = tl < 0.f ? 0 : (tl >= (float)ncell ? ncell : (int)tl);
-        const int ih = th < 0.f ? -1 : (th >= (float)ncell ? ncell - 1 : (int)th);
-        rlo[a] = il;
-        rhi[a] = ih < ncell - 1 ? ih : ncell - 1;
-        if (ih < 0 || il >= ncell) rhi[a] = rlo[a] - 1;
-      }
-    }
-    const int nx = rhi[0] - rlo[0] + 1, ny = rhi[1] - rlo[1] + 1, nz = rhi[2] - rlo[2] + 1;
-    const int nroots = (nx > 0 && ny > 0 && nz > 0) ? nx * ny * nz : 0;
-    int sp = 0;
-    for (int r0 = 0; r0 < nroots; r0 += 32) {
-      const int ri = r0 + lane;
-      uint32_t s = 0, e = 0, m = 0;
-      int rx = 0, ry = 0, rz = 0;
-      bool have = false;
-      if (ri < nroots) {
-        rx = rlo[0] + ri % nx;
-        ry = rlo[1] + (ri / nx) % ny;
-        rz = rlo[2] + ri / (nx * ny);
-        have = grid_lookup(g, lb, rx, ry, rz, s, e, m);
-      }
-      uint32_t hv = __ballot_sync(0xffffffffu, have);
-      while (hv) {
-        const int sl = __ffs(hv) - 1;
-        hv &= hv - 1;
-        const int bx = __shfl_sync(0xffffffffu, rx, sl), by = __shfl_sync(0xffffffffu, ry, sl), bz = __shfl_sync(0xffffffffu, rz, sl);
-        if (!__any_sync(0xffffffffu, box_dist2(g, lb, bx, by, bz, qx, qy, qz) <= bound())) continue;
-        if (sp < KT_STACK) {
-          if (lane == sl) stack[sp] = TileNode{(uint32_t)rx | ((uint32_t)lb << 24), (uint32_t)ry | (m << 24), (uint32_t)rz, s, e};
-          sp++;
-        }
-      }
-      __syncwarp();
-      while (sp > 0) {
-        const TileNode nd = stack[--sp];
-        __syncwarp();
-        const int l = (int)(nd.cx_lvl >> 24);
-        const int cx = (int)(nd.cx_lvl & 0xffffffu), cy = (int)(nd.cy_mask & 0xffffffu), cz = (int)nd.cz;
-        const uint32_t cm = nd.cy_mask >> 24;
-        if (!__any_sync(0xffffffffu, box_dist2(g, l, cx, cy, cz, qx, qy, qz) <= bound())) continue;
-        if (l == 0 || nd.end - nd.start <= (uint32_t)KT_LEAF || sp + 8 > KT_STACK) {
-          for (uint32_t p0 = nd.start; p0 < nd.end; p0 += 32) {
-            const uint32_t p = p0 + lane;
-            if (p < nd.end) cand[ncand + lane] = pts4[p];
-            ncand += min(32u, nd.end - p0);
-            if (ncand >= 32) consume();  // consume early: every fold-in tightens the balls
-          }
-          continue;
-        }
-        const uint64_t pkey = morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz) << 3;
-        uint32_t cs = 0, ce = 0, cmk = 0;
-        bool hc = false;
-        if (lane < 8 && ((cm >> lane) & 1u)) hc = grid_lookup_key(g, l - 1, pkey | (uint64_t)lane, cs, ce, cmk);
-        const uint32_t hvc = __ballot_sync(0xffffffffu, hc);
-        // push the children farthest-first from the warp's first active query so the nearest is popped first
-        for (int c = 7; c >= 0; c--) {
-          if (!((hvc >> c) & 1u)) continue;
-          const int ccx = 2 * cx + (c & 1), ccy = 2 * cy + ((c >> 1) & 1), ccz = 2 * cz + ((c >> 2) & 1);
-          if (!__any_sync(0xffffffffu, box_dist2(g, l - 1, ccx, ccy, ccz, qx, qy, qz) <= bound())) continue;
-          if (lane == c) stack[sp] = TileNode{(uint32_t)ccx | ((uint32_t)(l - 1) << 24), (uint32_t)ccy | (cmk << 24), (uint32_t)ccz, cs, ce};
-          sp++;
-        }
-        __syncwarp();
-      }
-    }
-    consume();
-  }
-  if (i < n_src) {
-    const float d2 = best == ~0ull ? INFINITY : key_d2(best);
-    corr[i] = (best != ~0ull && d2 < thr2) ? __ldg(&g.inv[(unsigned)(best & 0xffffffffull)]) : -1;
-    sqd[i] = d2;
-  }
-}
-
 // Mahalanobis part of update_correspondences + linearize (fast_gicp_impl.hpp:139-211), fused:
 // per correspondence M = (C_B + R C_A R^T)^-1 (stored for compute_error), e^T M e, the 21 unique
 // entries of H = J^T M J and b = J^T M e, reduced deterministically.  Streams p, C_A, corr; gathers
