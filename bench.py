@@ -435,14 +435,21 @@ def run_ours(args, rank, world):
         dist.destroy_process_group()
 
 
+def host_threads() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline(pairs, n_aligns=2):
     from oracle import oracle as orc
-    threads = orc.max_threads()
+    threads = host_threads()
     secs = []
     for i in range(n_aligns):
         p = pairs[i % len(pairs)]
         o = orc.FastGICP(max_iterations=CALL_SITE["max_iterations"], corr_dist=CALL_SITE["corr_dist"],
-                         transformation_epsilon=CALL_SITE["transformation_epsilon"])
+                         transformation_epsilon=CALL_SITE["transformation_epsilon"], num_threads=threads)
         t0 = time.perf_counter()
         o.setInputTarget(p["tgt"])   # kd-tree build (fast_gicp_impl.hpp:88)
         o.setInputSource(p["src"])
@@ -451,7 +458,8 @@ def cpu_baseline(pairs, n_aligns=2):
     vsecs = []
     for i in range(1):
         p = pairs[i % len(pairs)]
-        ov = orc.FastVGICP(resolution=1.0, max_iterations=CALL_SITE["max_iterations"], transformation_epsilon=CALL_SITE["transformation_epsilon"])
+        ov = orc.FastVGICP(resolution=1.0, max_iterations=CALL_SITE["max_iterations"], transformation_epsilon=CALL_SITE["transformation_epsilon"],
+                           num_threads=threads)
         t0 = time.perf_counter()
         ov.setInputTarget(p["tgt"])
         ov.setInputSource(p["src"])
@@ -470,12 +478,13 @@ def run_reference(args, rank, world):
         return
     from oracle import oracle as orc
     pairs = build_workload(0, args.submap_points)
-    threads = orc.max_threads()
+    # all host threads this process may use, asked for explicitly: torchrun exports OMP_NUM_THREADS=1
+    threads = host_threads()
 
     def step(i):
         p = pairs[i % len(pairs)]
         o = orc.FastGICP(max_iterations=CALL_SITE["max_iterations"], corr_dist=CALL_SITE["corr_dist"],
-                         transformation_epsilon=CALL_SITE["transformation_epsilon"])
+                         transformation_epsilon=CALL_SITE["transformation_epsilon"], num_threads=threads)
         o.setInputTarget(p["tgt"])
         o.setInputSource(p["src"])
         o.align(p["guess"])
