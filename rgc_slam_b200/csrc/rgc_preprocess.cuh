@@ -193,12 +193,19 @@ __global__ void __launch_bounds__(128) k_vg_centroid(const float4* __restrict__ 
   if (v >= nv) return;
   const int s = heads[v], e = v + 1 < nv ? heads[v + 1] : n;
   float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
-  for (int j = s; j < e; j++) {
-    const float4 p = __ldg(&pts[vals[j]]);
-    sx = fadd(sx, p.x);
-    sy = fadd(sy, p.y);
-    sz = fadd(sz, p.z);
-    si = fadd(si, p.w);
+  // gathers in batches of 8 (independent loads in flight), additions strictly in input order
+  for (int j0 = s; j0 < e; j0 += 8) {
+    float4 p[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) p[u] = j0 + u < e ? __ldg(&pts[vals[j0 + u]]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+      if (j0 + u < e) {
+        sx = fadd(sx, p[u].x);
+        sy = fadd(sy, p[u].y);
+        sz = fadd(sz, p[u].z);
+        si = fadd(si, p[u].w);
+      }
   }
   const float cnt = (float)(e - s);
   out[v] = make_float4(sx / cnt, sy / cnt, sz / cnt, si / cnt);
