@@ -388,12 +388,14 @@ def run_ours(args, rank, world):
         "linearize() call incl. launch+sync": {"ms": lin_ms}, "compute_error() call incl. launch+sync": {"ms": ce_ms},
     }
     dom = "k_knn_tile k=20 (target)"
-    traffic = None
+    traffic, sm_side = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(dom, {}).get("bytes")
+        ent = json.load(open(tpath)).get(dom, {})
+        traffic = ent.get("bytes")
+        sm_side = {k: ent[k] for k in ("sm_issue_active_pct", "sm_throughput_pct", "warp_instructions", "active_lanes_per_instruction", "sm_source") if k in ent}
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
-                "frac": kernels[dom]["GBps"] / peak, "traffic": traffic, "peak_source": peak_src,
+                "frac": kernels[dom]["GBps"] / peak, "traffic": traffic, "peak_source": peak_src, "sm": sm_side,
                 "note": "dominant kernel is the k=20 kNN, which is SM/latency-bound (north_star: report SM throughput); "
                         "HBM-bound kernels are listed under `kernels`; ncu summaries in profiles/",
                 "kernels": kernels}
