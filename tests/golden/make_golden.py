@@ -45,7 +45,34 @@ def features_small():
     np.savez_compressed(os.path.join(HERE, "features_small.npz"), **out)
 
 
+def frontend_small():
+    """pre-step (de-skew + voxel filter) and mapping association (N4)"""
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE)))
+    from test_oracle_mapping import _pose, _scene
+    scene = synth.Scene.make(synth.BASE_SEED + 3)
+    traj = synth.trajectory(12, seed=11)
+    rng = np.random.default_rng(77)
+    scan = synth.lidar_scan(scene, traj[4], n_azimuth=400, seed=301)
+    scan[:, 3] = rng.integers(0, 16, len(scan)) + np.float32(0.1) * rng.uniform(0, 1, len(scan)).astype(np.float32)
+    q = np.array([0.99995, 0.001, -0.002, 0.009])
+    q /= np.linalg.norm(q)
+    t = np.array([0.12, 0.01, -0.004])
+    desk = orc.deskew(scan, q, t)
+    corner, surf, r2 = _scene(21)
+    rot, qm, tm = _pose(r2)
+    fe = np.zeros((300, 4), np.float32)
+    fe[:, :3] = rot.inv().apply(corner[r2.choice(len(corner), 300), :3] + r2.normal(0, 0.05, (300, 3)) - tm)
+    fp = np.zeros((600, 4), np.float32)
+    fp[:, :3] = rot.inv().apply(surf[r2.choice(len(surf), 600), :3] + r2.normal(0, 0.03, (600, 3)) - tm)
+    ev, ea, eb = orc.assoc_edges(corner, fe, qm, tm)
+    pv, pn, pd = orc.assoc_planes(surf, fp, qm, tm)
+    np.savez_compressed(os.path.join(HERE, "frontend_small.npz"), scan=scan, q=q, t=t, deskewed=desk, vg02=orc.voxel_grid(desk, 0.2), vg03=orc.voxel_grid(scan, 0.3),
+                        corner=corner, surf=surf, qm=qm, tm=tm, edge_feats=fe, plane_feats=fp, edge_valid=ev, edge_a=ea, edge_b=eb,
+                        plane_valid=pv, plane_norm=pn, plane_d=pd)
+
+
 if __name__ == "__main__":
     gicp_small()
     features_small()
+    frontend_small()
     print("golden vectors written to", HERE)

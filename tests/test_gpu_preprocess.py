@@ -111,3 +111,24 @@ def test_fused_front_end_equals_staged(rgc, orc, scan_pair):
     n0 = b.ctx.launch_count
     assert b.setInputSourceFiltered(S, 0.2, q, t) == len(Sg)
     assert b.ctx.launch_count == n0
+
+
+def test_frontend_against_golden_fixture(rgc):
+    """the committed fixture (tests/golden/frontend_small.npz): de-skew, both voxel filters, edge / plane association"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "frontend_small.npz"))
+    D = rgc.deskew(g["scan"], g["q"], g["t"])
+    ulp = np.spacing(np.abs(g["deskewed"][:, :3]).astype(np.float32))
+    assert (np.abs(D[:, :3] - g["deskewed"][:, :3]) <= ulp).all() and np.array_equal(D[:, 3], g["deskewed"][:, 3])
+    assert np.array_equal(rgc.voxel_grid(g["deskewed"], 0.2), g["vg02"])
+    assert np.array_equal(rgc.voxel_grid(g["scan"], 0.3), g["vg03"])
+    mc, ms = rgc.FeatureMap(g["corner"]), rgc.FeatureMap(g["surf"])
+    ev, ea, eb = mc.associate_edges(g["edge_feats"], g["qm"], g["tm"])
+    pv, pn, pd = ms.associate_planes(g["plane_feats"], g["qm"], g["tm"])
+    assert np.array_equal(ev, g["edge_valid"]) and np.array_equal(pv, g["plane_valid"])
+    same = np.abs(ea[ev] - g["edge_a"][ev]).max(1) < 1e-9
+    swap = np.abs(ea[ev] - g["edge_b"][ev]).max(1) < 1e-9
+    assert (same | swap).all()
+    assert np.abs(pn[pv] - g["plane_norm"][pv]).max() < 1e-9 and np.abs(pd[pv] - g["plane_d"][pv]).max() < 1e-9 * max(1.0, g["plane_d"][pv].max())
+    mc.close()
+    ms.close()

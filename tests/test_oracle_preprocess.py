@@ -86,3 +86,17 @@ def test_deskew_matches_scipy():
     s0 = float(np.float32(1) - (Q[0, 3] - np.float32(3)) / np.float32(0.1))
     assert abs(s0) < 1e-5 and np.abs(o[0, :3] - Q[0, :3]).max() < 1e-4
     assert np.abs(o[1, :3] - rot.inv().apply(Q[1, :3].astype(np.float64) - t)).max() < 1e-5
+
+
+def test_frontend_golden_vectors():
+    """Frozen oracle outputs (tests/golden/make_golden.py: frontend_small): protects the oracle from drift."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "frontend_small.npz"))
+    assert np.array_equal(orc.deskew(g["scan"], g["q"], g["t"]), g["deskewed"])
+    assert np.array_equal(orc.voxel_grid(g["deskewed"], 0.2), g["vg02"])
+    assert np.array_equal(orc.voxel_grid(g["scan"], 0.3), g["vg03"])
+    ev, ea, eb = orc.assoc_edges(g["corner"], g["edge_feats"], g["qm"], g["tm"])
+    assert np.array_equal(ev, g["edge_valid"]) and np.array_equal(ea[ev], g["edge_a"][ev]) and np.array_equal(eb[ev], g["edge_b"][ev])
+    pv, pn, pd = orc.assoc_planes(g["surf"], g["plane_feats"], g["qm"], g["tm"])
+    assert np.array_equal(pv, g["plane_valid"]) and np.array_equal(pn[pv], g["plane_norm"][pv]) and np.array_equal(pd[pv], g["plane_d"][pv])
+    assert ev.sum() > 20 and pv.sum() > 100
