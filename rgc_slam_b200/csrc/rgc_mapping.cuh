@@ -20,7 +20,7 @@ struct PoseQ {
 };
 
 // Eigen ColPivHouseholderQR<Matrix<double,5,3>>::solve for a full-rank system (oracle/orc_mapping.hpp)
-__device__ __forceinline__ void colpiv_qr_solve_5x3(double A[5][3], double b[5], double x[3]) {
+RGC_HD void colpiv_qr_solve_5x3(double A[5][3], double b[5], double x[3]) {
   int perm[3] = {0, 1, 2};
 #pragma unroll
   for (int k = 0; k < 3; k++) {
@@ -93,6 +93,79 @@ __device__ __forceinline__ void colpiv_qr_solve_5x3(double A[5][3], double b[5],
   }
 }
 
+// pointAssociateToMap (RGC_mapping.cpp:1811-1820): q * p + t in double (Eigen _transformVector), stored as float
+RGC_HD void associate_to_map(const PoseQ& T, float px, float py, float pz, float& qx, float& qy, float& qz) {
+  const double vx = (double)px, vy = (double)py, vz = (double)pz;
+  double ux = dsub(dmul(T.y, vz), dmul(T.z, vy)), uy = dsub(dmul(T.z, vx), dmul(T.x, vz)), uz = dsub(dmul(T.x, vy), dmul(T.y, vx));
+  ux = dadd(ux, ux);
+  uy = dadd(uy, uy);
+  uz = dadd(uz, uz);
+  qx = (float)dadd(dadd(dadd(vx, dmul(T.w, ux)), dsub(dmul(T.y, uz), dmul(T.z, uy))), T.tx);
+  qy = (float)dadd(dadd(dadd(vy, dmul(T.w, uy)), dsub(dmul(T.z, ux), dmul(T.x, uz))), T.ty);
+  qz = (float)dadd(dadd(dadd(vz, dmul(T.w, uz)), dsub(dmul(T.x, uy), dmul(T.y, ux))), T.tz);
+}
+
+// :1100-1133 — P: the 5 neighbours, nearest first.  Returns 1 and point_a / point_b if they form a line.
+RGC_HD int edge_fit(const double P[5][3], double pa[3], double pb[3]) {
+  double c[3] = {0.0, 0.0, 0.0};
+  for (int j = 0; j < 5; j++) {
+    c[0] += P[j][0];
+    c[1] += P[j][1];
+    c[2] += P[j][2];
+  }
+  c[0] /= 5.0;
+  c[1] /= 5.0;
+  c[2] /= 5.0;
+  Sym3 M = {0, 0, 0, 0, 0, 0};
+  for (int j = 0; j < 5; j++) {
+    const double zx = P[j][0] - c[0], zy = P[j][1] - c[1], zz = P[j][2] - c[2];
+    M.xx += zx * zx;
+    M.xy += zx * zy;
+    M.xz += zx * zz;
+    M.yy += zy * zy;
+    M.yz += zy * zz;
+    M.zz += zz * zz;
+  }
+  double w[3], V[3][3];
+  eig_sym3(M, w, V);
+  // largest and middle eigenvalue (SelfAdjointEigenSolver sorts ascending)
+  int hi = 0;
+  if (w[1] > w[hi]) hi = 1;
+  if (w[2] > w[hi]) hi = 2;
+  const int a = (hi + 1) % 3, b = (hi + 2) % 3;
+  const double mid = w[a] > w[b] ? w[a] : w[b];
+  if (!(w[hi] > 3 * mid)) return 0;
+  for (int r = 0; r < 3; r++) {
+    const double dir = hi == 0 ? V[r][0] : (hi == 1 ? V[r][1] : V[r][2]);
+    pa[r] = 0.1 * dir + c[r];
+    pb[r] = -0.1 * dir + c[r];
+  }
+  return 1;
+}
+
+// :1199-1230 — returns 1 and the unit normal / negative_OA_dot_norm if the 5 neighbours fit a plane to 0.2 m
+RGC_HD int plane_fit(const double P[5][3], double nrm[3], double& dist) {
+  double A[5][3], b[5] = {-1.0, -1.0, -1.0, -1.0, -1.0}, x[3] = {0.0, 0.0, 0.0};
+  for (int j = 0; j < 5; j++) {
+    A[j][0] = P[j][0];
+    A[j][1] = P[j][1];
+    A[j][2] = P[j][2];
+  }
+  colpiv_qr_solve_5x3(A, b, x);
+  const double nn = sqrt((x[0] * x[0] + x[1] * x[1]) + x[2] * x[2]);
+  const double d = 1 / nn;
+  const double nx = x[0] / nn, ny = x[1] / nn, nz = x[2] / nn;
+  int ok = 1;
+  for (int j = 0; j < 5; j++)
+    if (fabs(((nx * P[j][0] + ny * P[j][1]) + nz * P[j][2]) + d) > 0.2) ok = 0;
+  nrm[0] = nx;
+  nrm[1] = ny;
+  nrm[2] = nz;
+  dist = d;
+  return ok;
+}
+
+#if defined(__CUDACC__)
 template <bool PLANE>
 __global__ void __launch_bounds__(kThreads, 4) k_map_assoc(GridView g, const unsigned char* __restrict__ feats, size_t stride, int n, int spread, PoseQ T,
                                                            int* __restrict__ valid, double* __restrict__ o1, double* __restrict__ o2) {
@@ -102,15 +175,8 @@ __global__ void __launch_bounds__(kThreads, 4) k_map_assoc(GridView g, const uns
   const int i = gt / spread;
   if (i >= n) return;
   const float* f = reinterpret_cast<const float*>(feats + (size_t)i * stride);
-  // pointAssociateToMap: q * p + t in double (Eigen _transformVector), stored as float
-  const double vx = (double)f[0], vy = (double)f[1], vz = (double)f[2];
-  double ux = dsub(dmul(T.y, vz), dmul(T.z, vy)), uy = dsub(dmul(T.z, vx), dmul(T.x, vz)), uz = dsub(dmul(T.x, vy), dmul(T.y, vx));
-  ux = dadd(ux, ux);
-  uy = dadd(uy, uy);
-  uz = dadd(uz, uz);
-  const float qx = (float)dadd(dadd(dadd(vx, dmul(T.w, ux)), dsub(dmul(T.y, uz), dmul(T.z, uy))), T.tx);
-  const float qy = (float)dadd(dadd(dadd(vy, dmul(T.w, uy)), dsub(dmul(T.z, ux), dmul(T.x, uz))), T.ty);
-  const float qz = (float)dadd(dadd(dadd(vz, dmul(T.w, uz)), dsub(dmul(T.x, uy), dmul(T.y, ux))), T.tz);
+  float qx, qy, qz;
+  associate_to_map(T, f[0], f[1], f[2], qx, qy, qz);
   HeapK top;
   top.init(heap_smem + threadIdx.x, reinterpret_cast<int*>(heap_smem + (size_t)5 * kThreads) + threadIdx.x, kThreads);
   knn_search(g, qx, qy, qz, 5, INFINITY, -1, top);
@@ -127,69 +193,28 @@ __global__ void __launch_bounds__(kThreads, 4) k_map_assoc(GridView g, const uns
       P[j][2] = (double)p.z;
     }
     if (!PLANE) {
-      double c[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-      for (int j = 0; j < 5; j++) {
-        c[0] += P[j][0];
-        c[1] += P[j][1];
-        c[2] += P[j][2];
-      }
-      c[0] /= 5.0;
-      c[1] /= 5.0;
-      c[2] /= 5.0;
-      Sym3 M = {0, 0, 0, 0, 0, 0};
-#pragma unroll
-      for (int j = 0; j < 5; j++) {
-        const double zx = P[j][0] - c[0], zy = P[j][1] - c[1], zz = P[j][2] - c[2];
-        M.xx += zx * zx;
-        M.xy += zx * zy;
-        M.xz += zx * zz;
-        M.yy += zy * zy;
-        M.yz += zy * zz;
-        M.zz += zz * zz;
-      }
-      double w[3], V[3][3];
-      eig_sym3(M, w, V);
-      // largest and middle eigenvalue (SelfAdjointEigenSolver sorts ascending)
-      int hi = 0;
-      if (w[1] > w[hi]) hi = 1;
-      if (w[2] > w[hi]) hi = 2;
-      const int a = (hi + 1) % 3, b = (hi + 2) % 3;
-      const double mid = w[a] > w[b] ? w[a] : w[b];
-      if (w[hi] > 3 * mid) {
-        ok = 1;
+      double pa[3], pb[3];
+      ok = edge_fit(P, pa, pb);
+      if (ok) {
 #pragma unroll
         for (int r = 0; r < 3; r++) {
-          const double dir = hi == 0 ? V[r][0] : (hi == 1 ? V[r][1] : V[r][2]);
-          o1[3 * (size_t)i + r] = 0.1 * dir + c[r];
-          o2[3 * (size_t)i + r] = -0.1 * dir + c[r];
+          o1[3 * (size_t)i + r] = pa[r];
+          o2[3 * (size_t)i + r] = pb[r];
         }
       }
     } else {
-      double A[5][3], b[5] = {-1.0, -1.0, -1.0, -1.0, -1.0}, x[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-      for (int j = 0; j < 5; j++) {
-        A[j][0] = P[j][0];
-        A[j][1] = P[j][1];
-        A[j][2] = P[j][2];
-      }
-      colpiv_qr_solve_5x3(A, b, x);
-      const double nn = sqrt((x[0] * x[0] + x[1] * x[1]) + x[2] * x[2]);
-      const double d = 1 / nn;
-      const double nx = x[0] / nn, ny = x[1] / nn, nz = x[2] / nn;
-      ok = 1;
-#pragma unroll
-      for (int j = 0; j < 5; j++)
-        if (fabs(((nx * P[j][0] + ny * P[j][1]) + nz * P[j][2]) + d) > 0.2) ok = 0;
+      double nrm[3], d;
+      ok = plane_fit(P, nrm, d);
       if (ok) {
-        o1[3 * (size_t)i] = nx;
-        o1[3 * (size_t)i + 1] = ny;
-        o1[3 * (size_t)i + 2] = nz;
+        o1[3 * (size_t)i] = nrm[0];
+        o1[3 * (size_t)i + 1] = nrm[1];
+        o1[3 * (size_t)i + 2] = nrm[2];
         o2[i] = d;
       }
     }
   }
   valid[i] = ok;
 }
+#endif  // __CUDACC__
 
 }  // namespace rgc

@@ -24,7 +24,7 @@ struct DeskewParams {
 
 // Eigen 3.3 QuaternionBase::slerp(s, other) from the identity, then _transformVector on (p - s t);
 // every double operation explicitly rounded (no FMA contraction), as the oracle is compiled.
-__device__ __forceinline__ void deskew_point(const DeskewParams& D, float inten, float& x, float& y, float& z) {
+RGC_HD void deskew_point(const DeskewParams& D, float inten, float& x, float& y, float& z) {
   const float sf = 1 - (inten - (float)(int)inten) / D.scan_period;  // float arithmetic (SCAN_PERIOD is a float)
   const double s = (double)sf;
   const double d = D.iw, absd = fabs(d);
@@ -50,6 +50,7 @@ __device__ __forceinline__ void deskew_point(const DeskewParams& D, float inten,
   z = (float)dadd(dadd(vz, dmul(qw, uz)), dsub(dmul(qx, uy), dmul(qy, ux)));
 }
 
+#if defined(__CUDACC__)
 // raw[n] (any PCL stride, xyz at byte 0, intensity at `inten_off` or absent) -> float4 (x, y, z, intensity),
 // optionally de-skewed, plus per-block min/max partials of the OUTPUT coordinates
 __global__ void __launch_bounds__(256) k_pre_ingest(const unsigned char* __restrict__ raw, size_t stride, size_t inten_off, int n, DeskewParams D,
@@ -87,20 +88,28 @@ __global__ void __launch_bounds__(256) k_pre_ingest(const unsigned char* __restr
   }
 }
 
+#endif  // __CUDACC__
+
 struct VgGeom {  // pcl::VoxelGrid::applyFilter: min_b_, divb_mul_, inverse_leaf_size_
   float inv_leaf;
   int min_b[3];
   int mul1, mul2;
 };
 
+// pcl::VoxelGrid voxel index of a point (float arithmetic of filters/impl/voxel_grid.hpp)
+RGC_HD unsigned vg_index(const VgGeom& g, float x, float y, float z) {
+  const int i0 = (int)fsub(floorf(fmul(x, g.inv_leaf)), (float)g.min_b[0]);
+  const int i1 = (int)fsub(floorf(fmul(y, g.inv_leaf)), (float)g.min_b[1]);
+  const int i2 = (int)fsub(floorf(fmul(z, g.inv_leaf)), (float)g.min_b[2]);
+  return (unsigned)(i0 + i1 * g.mul1 + i2 * g.mul2);
+}
+
+#if defined(__CUDACC__)
 __global__ void __launch_bounds__(256) k_vg_keys(const float4* __restrict__ pts, int n, VgGeom g, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4 p = pts[i];
-  const int i0 = (int)fsub(floorf(fmul(p.x, g.inv_leaf)), (float)g.min_b[0]);
-  const int i1 = (int)fsub(floorf(fmul(p.y, g.inv_leaf)), (float)g.min_b[1]);
-  const int i2 = (int)fsub(floorf(fmul(p.z, g.inv_leaf)), (float)g.min_b[2]);
-  keys[i] = (uint64_t)(unsigned)(i0 + i1 * g.mul1 + i2 * g.mul2);
+  keys[i] = (uint64_t)vg_index(g, p.x, p.y, p.z);
   vals[i] = (uint32_t)i;
 }
 
@@ -210,5 +219,7 @@ __global__ void __launch_bounds__(128) k_vg_centroid(const float4* __restrict__ 
   const float cnt = (float)(e - s);
   out[v] = make_float4(sx / cnt, sy / cnt, sz / cnt, si / cnt);
 }
+
+#endif  // __CUDACC__
 
 }  // namespace rgc

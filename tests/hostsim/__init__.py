@@ -30,6 +30,10 @@ def lib():
         L.sim_solve_ldlt6.argtypes = [_f64p, _f64p, _f64p]
         L.sim_se3_delta.argtypes = [_f64p, _f64p]
         L.sim_is_converged.argtypes = [_f64p, C.c_double, C.c_double]
+        L.sim_deskew.argtypes = [_f32p, C.c_int, _f64p, _f64p, C.c_float, _f32p]
+        L.sim_voxel_grid.argtypes = [_f32p, C.c_int, C.c_float, _f32p]
+        L.sim_voxel_grid.restype = C.c_int
+        L.sim_map_assoc.argtypes = [_f32p, C.c_int, _f32p, C.c_int, _f64p, _f64p, C.c_int, _i32p, _f64p, _f64p]
         _LIB = L
     return _LIB
 
@@ -62,3 +66,28 @@ def linearize(src, tgt, cov_a, cov_b, T, thr, cell=0.0):
     lib().sim_linearize(s, len(s), t, len(t), np.ascontiguousarray(cov_a, np.float64).reshape(-1), np.ascontiguousarray(cov_b, np.float64).reshape(-1),
                         np.ascontiguousarray(T, np.float64).reshape(-1), thr, cell, e, H, b, corr)
     return e[0], H.reshape(6, 6), b, corr
+
+
+def deskew(xyzi, q_wxyz, t, scan_period=0.1):
+    P = np.ascontiguousarray(xyzi, np.float32)
+    out = np.empty_like(P)
+    lib().sim_deskew(P, len(P), np.ascontiguousarray(q_wxyz, np.float64), np.ascontiguousarray(t, np.float64), scan_period, out)
+    return out
+
+
+def voxel_grid(xyzi, leaf):
+    P = np.ascontiguousarray(xyzi, np.float32)
+    out = np.empty_like(P)
+    m = lib().sim_voxel_grid(P, len(P), leaf, out)
+    return out[:m].copy()
+
+
+def map_assoc(map_xyz1, feats, q_wxyz, t, plane):
+    M = np.ascontiguousarray(map_xyz1, np.float32)
+    F = np.ascontiguousarray(feats, np.float32)
+    n = len(F)
+    valid = np.zeros(n, np.int32)
+    o1 = np.zeros((n, 3), np.float64)
+    o2 = np.zeros(n if plane else (n, 3), np.float64)
+    lib().sim_map_assoc(M, len(M), F, n, np.ascontiguousarray(q_wxyz, np.float64), np.ascontiguousarray(t, np.float64), int(bool(plane)), valid, o1, o2)
+    return valid.astype(bool), o1, o2

@@ -12,6 +12,8 @@
 
 #include "../../rgc_slam_b200/csrc/rgc_grid.cuh"
 #include "../../rgc_slam_b200/csrc/rgc_math.cuh"
+#include "../../rgc_slam_b200/csrc/rgc_mapping.cuh"
+#include "../../rgc_slam_b200/csrc/rgc_preprocess.cuh"
 
 using namespace rgc;
 
@@ -195,3 +197,129 @@ void sim_solve_ldlt6(const double* A, const double* rhs, double* x) { rgc::lm::s
 void sim_se3_delta(const double* d, double* delta16) { rgc::lm::se3_delta(d, delta16); }
 int sim_is_converged(const double* delta16, double rot_eps, double trans_eps) { return rgc::lm::is_converged(delta16, rot_eps, trans_eps) ? 1 : 0; }
 }
+
+// ---- pre-step and mapping association: the product's host/device arithmetic, one "thread" per point ----
+extern "C" {
+
+// rgc_gicp.cu pre_filter + k_pre_ingest: de-skew of every point (q = q_last_curr as w, x, y, z)
+void sim_deskew(const float* xyzi, int n, const double* q, const double* t3, float period, float* out) {
+  DeskewParams D{};
+  const double n2 = ((q[1] * q[1] + q[2] * q[2]) + q[3] * q[3]) + q[0] * q[0];
+  D.enabled = 1;
+  if (n2 > 0.0) {
+    D.iw = q[0] / n2;
+    D.ix = -q[1] / n2;
+    D.iy = -q[2] / n2;
+    D.iz = -q[3] / n2;
+  }
+  D.tx = t3[0];
+  D.ty = t3[1];
+  D.tz = t3[2];
+  D.scan_period = period;
+  for (int i = 0; i < n; i++) {
+    float x = xyzi[4 * (size_t)i], y = xyzi[4 * (size_t)i + 1], z = xyzi[4 * (size_t)i + 2];
+    const float inten = xyzi[4 * (size_t)i + 3];
+    deskew_point(D, inten, x, y, z);
+    out[4 * (size_t)i] = x;
+    out[4 * (size_t)i + 1] = y;
+    out[4 * (size_t)i + 2] = z;
+    out[4 * (size_t)i + 3] = inten;
+  }
+}
+
+// pre_filter's grid set-up + vg_index + the stable sort / in-order float sums of k_vg_centroid
+int sim_voxel_grid(const float* xyzi, int n, float leaf, float* out) {
+  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int i = 0; i < n; i++)
+    for (int a = 0; a < 3; a++) {
+      mn[a] = std::min(mn[a], xyzi[4 * (size_t)i + a]);
+      mx[a] = std::max(mx[a], xyzi[4 * (size_t)i + a]);
+    }
+  VgGeom g;
+  g.inv_leaf = 1.0f / leaf;
+  long long dd[3];
+  for (int a = 0; a < 3; a++) dd[a] = (long long)((mx[a] - mn[a]) * g.inv_leaf) + 1;
+  if (dd[0] * dd[1] * dd[2] > 2147483647ll) {
+    std::copy(xyzi, xyzi + 4 * (size_t)n, out);
+    return n;
+  }
+  int div_b[3];
+  for (int a = 0; a < 3; a++) {
+    g.min_b[a] = (int)std::floor(mn[a] * g.inv_leaf);
+    div_b[a] = (int)std::floor(mx[a] * g.inv_leaf) - g.min_b[a] + 1;
+  }
+  g.mul1 = div_b[0];
+  g.mul2 = div_b[0] * div_b[1];
+  std::vector<unsigned> key(n);
+  std::vector<int> order(n);
+  for (int i = 0; i < n; i++) {
+    key[i] = vg_index(g, xyzi[4 * (size_t)i], xyzi[4 * (size_t)i + 1], xyzi[4 * (size_t)i + 2]);
+    order[i] = i;
+  }
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
+  int m = 0;
+  for (int s = 0; s < n;) {
+    int e = s + 1;
+    while (e < n && key[order[e]] == key[order[s]]) e++;
+    float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+    for (int j = s; j < e; j++) {
+      const float* p = xyzi + 4 * (size_t)order[j];
+      sx = fadd(sx, p[0]);
+      sy = fadd(sy, p[1]);
+      sz = fadd(sz, p[2]);
+      si = fadd(si, p[3]);
+    }
+    const float cnt = (float)(e - s);
+    out[4 * (size_t)m] = sx / cnt;
+    out[4 * (size_t)m + 1] = sy / cnt;
+    out[4 * (size_t)m + 2] = sz / cnt;
+    out[4 * (size_t)m + 3] = si / cnt;
+    m++;
+    s = e;
+  }
+  return m;
+}
+
+// k_map_assoc on the host: pose transform, exact 5-NN through knn_search, edge / plane fit
+void sim_map_assoc(const float* map_xyz1, int nm, const float* feats, int n, const double* q, const double* t3, int plane, int* valid, double* o1, double* o2) {
+  SimCloud c;
+  sim_build(map_xyz1, nm, 0.f, c);
+  const PoseQ T{q[0], q[1], q[2], q[3], t3[0], t3[1], t3[2]};
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n; i++) {
+    valid[i] = 0;
+    float qx, qy, qz;
+    associate_to_map(T, feats[4 * (size_t)i], feats[4 * (size_t)i + 1], feats[4 * (size_t)i + 2], qx, qy, qz);
+    float hd[8];
+    int hi[8];
+    HeapK top;
+    top.init(hd, hi, 1);
+    knn_search(c.v, qx, qy, qz, 5, INFINITY, -1, top);
+    top.sort_ascending(c.v.pts);
+    if (!(top.cnt == 5 && hd[4] < (plane ? 2.0f : 1.0f))) continue;
+    double P[5][3];
+    for (int j = 0; j < 5; j++) {
+      const F4 p = c.sorted[hi[j]];
+      P[j][0] = (double)p.x;
+      P[j][1] = (double)p.y;
+      P[j][2] = (double)p.z;
+    }
+    if (!plane) {
+      double pa[3], pb[3];
+      if (!edge_fit(P, pa, pb)) continue;
+      valid[i] = 1;
+      for (int r = 0; r < 3; r++) {
+        o1[3 * (size_t)i + r] = pa[r];
+        o2[3 * (size_t)i + r] = pb[r];
+      }
+    } else {
+      double nrm[3], d;
+      if (!plane_fit(P, nrm, d)) continue;
+      valid[i] = 1;
+      for (int r = 0; r < 3; r++) o1[3 * (size_t)i + r] = nrm[r];
+      o2[i] = d;
+    }
+  }
+}
+
+}  // extern "C"

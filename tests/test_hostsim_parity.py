@@ -1,4 +1,4 @@
-"""CPU: the PRODUCT's host/device headers (rgc_grid.cuh, rgc_math.cuh, rgc_lm.hpp), compiled by g++
+"""CPU: the PRODUCT's host/device headers (rgc_grid.cuh, rgc_math.cuh, rgc_lm.hpp, rgc_preprocess.cuh, rgc_mapping.cuh), compiled by g++
 in tests/hostsim and run one simulated thread per point, against the oracle.  This is the no-GPU
 check of the search / algebra logic; the real parity tests (-m gpu) call the CUDA path."""
 import numpy as np
@@ -117,3 +117,56 @@ def test_host_lm_helpers():
     D[0, 3] = 0
     D[0, 1] = 3e-3
     assert L.sim_is_converged(D.reshape(-1), 2e-3, 5e-4) == 0
+
+
+# ---- pre-step and mapping association: the product's host/device arithmetic on the CPU ----
+def _stamped(n, seed, spread=8.0):
+    rng = np.random.default_rng(seed)
+    P = np.zeros((n, 4), np.float32)
+    P[:, :3] = rng.normal(0, spread, (n, 3))
+    P[:, 3] = rng.integers(0, 16, n) + np.float32(0.1) * rng.uniform(0, 1, n).astype(np.float32)
+    return P
+
+
+def test_hostsim_deskew_is_the_oracles():
+    from oracle import oracle as orc
+    P = _stamped(5000, 1, 25.0)
+    q = np.array([0.9998, 0.004, -0.011, 0.0125])
+    q /= np.linalg.norm(q)
+    t = np.array([0.31, -0.04, 0.012])
+    assert np.array_equal(hostsim.deskew(P, q, t), orc.deskew(P, q, t))          # same libm, same rounding: bit-exact
+    assert np.array_equal(hostsim.deskew(P, [1, 0, 0, 0], [0, 0, 0]), P)
+
+
+@pytest.mark.parametrize("leaf", [0.2, 0.3, 1.5])
+def test_hostsim_voxel_grid_is_the_oracles(leaf):
+    from oracle import oracle as orc
+    P = _stamped(8000, 2, 5.0)
+    assert np.array_equal(hostsim.voxel_grid(P, leaf), orc.voxel_grid(P, leaf))
+    far = np.array([[0, 0, 0, 0], [3000, 3000, 3000, 1]], np.float32)
+    assert np.array_equal(hostsim.voxel_grid(far, 0.001), far)
+
+
+def test_hostsim_map_association_matches_oracle():
+    from oracle import oracle as orc
+    from test_oracle_mapping import _pose, _scene
+    corner, surf, rng = _scene(31)
+    rot, q, t = _pose(rng)
+    fe = np.zeros((500, 4), np.float32)
+    fe[:, :3] = rot.inv().apply(corner[rng.choice(len(corner), 500), :3] + rng.normal(0, 0.05, (500, 3)) - t)
+    fe[250:, :3] += rng.normal(0, 3, (250, 3))
+    fp = np.zeros((800, 4), np.float32)
+    fp[:, :3] = rot.inv().apply(surf[rng.choice(len(surf), 800), :3] + rng.normal(0, 0.03, (800, 3)) - t)
+    fp[400:, :3] += rng.normal(0, 4, (400, 3))
+    v, a, b = hostsim.map_assoc(corner, fe, q, t, plane=False)
+    ov, oa, ob = orc.assoc_edges(corner, fe, q, t)
+    assert (v != ov).sum() <= 1 and v.sum() > 50
+    both = v & ov
+    same = np.abs(a[both] - oa[both]).max(1) < 1e-9
+    swap = np.abs(a[both] - ob[both]).max(1) < 1e-9
+    assert (same | swap).all()
+    v, nrm, d = hostsim.map_assoc(surf, fp, q, t, plane=True)
+    ov, on, od = orc.assoc_planes(surf, fp, q, t)
+    assert (v != ov).sum() <= 1 and v.sum() > 100
+    both = v & ov
+    assert np.abs(nrm[both] - on[both]).max() < 1e-10 and np.abs(d[both] - od[both]).max() < 1e-9
