@@ -323,19 +323,25 @@ struct HeapK64 {
     cnt = 0;
   }
   RGC_HD bool full() const { return cnt == k; }
+  // 4-ary max-heap: k = 20 is two levels below the root (1 + 4 + 15), so a replacement is two rounds of
+  // four independent loads instead of four dependent rounds of two (the sift was 37 % of the tile
+  // kernel's instructions and a chain of dependent shared-memory accesses)
   RGC_HD void sift_down(unsigned long long key, int size) {
     int j = 0;
     for (;;) {
-      int c = 2 * j + 1;
-      if (c >= size) break;
-      unsigned long long kc = h[c * stride];
-      if (c + 1 < size) {
-        const unsigned long long k2 = h[(c + 1) * stride];
-        if (k2 > kc) {
-          kc = k2;
-          c++;
+      const int c0 = 4 * j + 1;
+      if (c0 >= size) break;
+      int c = c0;
+      unsigned long long kc = h[c0 * stride];
+#pragma unroll
+      for (int u = 1; u < 4; u++)
+        if (c0 + u < size) {
+          const unsigned long long ku = h[(c0 + u) * stride];
+          if (ku > kc) {
+            kc = ku;
+            c = c0 + u;
+          }
         }
-      }
       if (kc <= key) break;
       h[j * stride] = kc;
       j = c;
@@ -346,7 +352,7 @@ struct HeapK64 {
     if (cnt < k) {
       int j = cnt++;
       while (j > 0) {
-        const int p = (j - 1) >> 1;
+        const int p = (j - 1) >> 2;
         const unsigned long long kp = h[p * stride];
         if (kp >= key) break;
         h[j * stride] = kp;

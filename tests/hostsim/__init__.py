@@ -30,6 +30,8 @@ def lib():
         L.sim_solve_ldlt6.argtypes = [_f64p, _f64p, _f64p]
         L.sim_se3_delta.argtypes = [_f64p, _f64p]
         L.sim_is_converged.argtypes = [_f64p, C.c_double, C.c_double]
+        L.sim_heap64_topk.argtypes = [np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS"), C.c_int, C.c_int, C.c_int,
+                                      np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")]
         L.sim_deskew.argtypes = [_f32p, C.c_int, _f64p, _f64p, C.c_float, _f32p]
         L.sim_voxel_grid.argtypes = [_f32p, C.c_int, C.c_float, _f32p]
         L.sim_voxel_grid.restype = C.c_int
@@ -91,3 +93,10 @@ def map_assoc(map_xyz1, feats, q_wxyz, t, plane):
     o2 = np.zeros(n if plane else (n, 3), np.float64)
     lib().sim_map_assoc(M, len(M), F, n, np.ascontiguousarray(q_wxyz, np.float64), np.ascontiguousarray(t, np.float64), int(bool(plane)), valid, o1, o2)
     return valid.astype(bool), o1, o2
+
+
+def heap64_topk(keys, k, stride=1):
+    K = np.ascontiguousarray(keys, np.uint64)
+    out = np.zeros(k, np.uint64)
+    lib().sim_heap64_topk(K, len(K), k, stride, out)
+    return out

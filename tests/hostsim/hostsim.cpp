@@ -323,3 +323,14 @@ void sim_map_assoc(const float* map_xyz1, int nm, const float* feats, int n, con
 }
 
 }  // extern "C"
+
+// HeapK64 (the tile kernel's per-lane container) driven on the host: k smallest of n keys, ascending
+extern "C" void sim_heap64_topk(const unsigned long long* keys, int n, int k, int stride, unsigned long long* out) {
+  std::vector<unsigned long long> store((size_t)k * stride, 0ull);
+  HeapK64 hp;
+  hp.init(store.data(), stride, k);
+  for (int i = 0; i < n; i++) hp.insert(keys[i]);
+  hp.sort_ascending();
+  for (int j = 0; j < hp.cnt; j++) out[j] = store[(size_t)j * stride];
+  for (int j = hp.cnt; j < k; j++) out[j] = ~0ull;
+}

@@ -170,3 +170,18 @@ def test_hostsim_map_association_matches_oracle():
     assert (v != ov).sum() <= 1 and v.sum() > 100
     both = v & ov
     assert np.abs(nrm[both] - on[both]).max() < 1e-10 and np.abs(d[both] - od[both]).max() < 1e-9
+
+
+@pytest.mark.parametrize("k", [1, 2, 5, 20, 21, 32])
+def test_heap64_selects_the_k_smallest(k):
+    """the tile kernel's packed-key heap (HeapK64): any insertion order, duplicates of the d2 half, k > n"""
+    rng = np.random.default_rng(k)
+    for n in (0, 1, k - 1, k, k + 1, 5 * k + 3, 1000):
+        if n < 0:
+            continue
+        d2 = rng.integers(0, 50, n).astype(np.uint64)              # many equal distances
+        keys = (d2 << np.uint64(32)) | rng.permutation(n).astype(np.uint64)
+        exp = np.sort(keys)[:k]
+        got = hostsim.heap64_topk(keys, k, stride=int(rng.integers(1, 4)))
+        assert np.array_equal(got[: len(exp)], exp)
+        assert (got[len(exp):] == np.uint64(0xFFFFFFFFFFFFFFFF)).all()
