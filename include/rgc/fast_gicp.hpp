@@ -50,6 +50,8 @@ enum class LSQ_OPTIMIZER_TYPE { GaussNewton, LevenbergMarquardt };              
 // (RGC_odometer.cpp:998), so nothing expensive may live in the object itself, and a context (streams,
 // memory pool, pinned result buffers) must not be shared by threads running concurrently.  Threads
 // that each run their own registrations (batched loop-closure verification) overlap on the GPU.
+// The context is destroyed when its thread ends: registration objects are meant to be locals (as at the
+// reference's call site) and must not outlive the thread that created them.
 inline rgc_ctx* shared_context(int device = 0) {
   struct Holder {
     std::vector<rgc_ctx*> ctxs;
