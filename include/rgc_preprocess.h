@@ -13,6 +13,8 @@
  * Points are records of `stride` bytes with x, y, z (float) at byte 0 and the intensity (float) at
  * byte `intensity_offset` (16 for pcl::PointXYZI; RGC_NO_INTENSITY if the type has none, in which case
  * the filter averages zeros and de-skew is refused).  Outputs are packed (x, y, z, intensity) floats.
+ * Points must be finite (the reference removes NaNs in scanRegistration before these stages; PCL's
+ * is_dense = false filtering of non-finite points is not reproduced).
  * Same conventions as rgc_gicp.h: int status, rgc_last_error(ctx), host memory in and out.
  */
 #ifndef RGC_PREPROCESS_H
