@@ -71,8 +71,30 @@ def frontend_small():
                         plane_valid=pv, plane_norm=pn, plane_d=pd)
 
 
+def vgicp_small():
+    """FastVGICP on the clouds of gicp_small.npz: voxel map, one linearize, one align"""
+    z = np.load(os.path.join(HERE, "gicp_small.npz"))
+    src, tgt = z["src"], z["tgt"]
+    out = {}
+    for name, search in (("d1", orc.DIRECT1), ("d7", orc.DIRECT7)):
+        v = orc.FastVGICP(resolution=1.0, search_method=search)
+        v.setInputTarget(tgt)
+        v.setInputSource(src)
+        e, H, b = v.linearize(z["T_lin"])
+        ncorr = v.num_correspondences()
+        coords, num, mean, cov = v.voxels()
+        order = np.lexsort((coords[:, 2], coords[:, 1], coords[:, 0]))
+        T = v.align()
+        out.update({f"{name}_err": e, f"{name}_H": H, f"{name}_b": b, f"{name}_ncorr": ncorr, f"{name}_T": T,
+                    f"{name}_iterations": v.last["iterations"]})
+        if name == "d1":
+            out.update(vox_coords=coords[order], vox_num=num[order], vox_mean=mean[order], vox_cov=cov[order])
+    np.savez_compressed(os.path.join(HERE, "vgicp_small.npz"), **out)
+
+
 if __name__ == "__main__":
     gicp_small()
     features_small()
     frontend_small()
+    vgicp_small()
     print("golden vectors written to", HERE)

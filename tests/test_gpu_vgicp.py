@@ -83,3 +83,29 @@ def test_vgicp_align_call_site(scan_pair, search):
     assert np.abs(T[:3, 3] - Ttrue[:3, 3]).max() < 0.06
     with pytest.raises(rgc.RgcError):
         g.correspondences()
+
+
+def test_vgicp_against_golden_fixture():
+    """the committed fixture tests/golden/vgicp_small.npz (oracle outputs frozen by make_golden.py)"""
+    import os
+    import rgc_slam_b200 as rgc
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    z, v = np.load(os.path.join(gold, "gicp_small.npz")), np.load(os.path.join(gold, "vgicp_small.npz"))
+    for name, search in (("d1", rgc.DIRECT1), ("d7", rgc.DIRECT7)):
+        g = rgc.FastVGICP()
+        g.setNeighborSearchMethod(search)
+        g.setInputTarget(z["tgt"])
+        g.setInputSource(z["src"])
+        e, H, b = g.linearize(z["T_lin"])
+        assert g.last_inliers() == int(v[f"{name}_ncorr"])
+        assert abs(e - v[f"{name}_err"]) <= 1e-9 * abs(v[f"{name}_err"])
+        assert np.abs(H - v[f"{name}_H"]).max() <= 1e-9 * np.abs(v[f"{name}_H"]).max()
+        assert np.abs(b - v[f"{name}_b"]).max() <= 1e-9 * np.abs(v[f"{name}_b"]).max()
+        if name == "d1":
+            coords, num, mean, cov = g.voxels()
+            assert np.array_equal(coords, v["vox_coords"]) and np.array_equal(num, v["vox_num"])
+            assert np.abs(mean - v["vox_mean"]).max() <= 1e-9 and np.abs(cov - v["vox_cov"]).max() <= 1e-8 * np.abs(v["vox_cov"]).max()
+        T = g.align()
+        To = v[f"{name}_T"]
+        assert np.abs(T[:3, 3].astype(np.float64) - To[:3, 3]).max() < 1e-4 and rot_angle(T[:3, :3], To[:3, :3]) < 1e-5
+        assert g.last_result["iterations"] == int(v[f"{name}_iterations"])

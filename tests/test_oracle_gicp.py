@@ -129,3 +129,25 @@ def test_golden_vectors():
     T = o.align()
     assert np.abs(T - z["T_final"]).max() < 1e-6
     assert o.last["iterations"] == int(z["iterations"])
+
+
+def test_vgicp_golden_vectors():
+    """Frozen FastVGICP oracle outputs (tests/golden/make_golden.py: vgicp_small)."""
+    z = np.load(os.path.join(GOLD, "gicp_small.npz"))
+    v = np.load(os.path.join(GOLD, "vgicp_small.npz"))
+    for name, search in (("d1", orc.DIRECT1), ("d7", orc.DIRECT7)):
+        o = orc.FastVGICP(resolution=1.0, search_method=search)
+        o.setInputTarget(z["tgt"])
+        o.setInputSource(z["src"])
+        e, H, b = o.linearize(z["T_lin"])
+        assert np.allclose(e, v[f"{name}_err"], rtol=1e-10)
+        assert np.allclose(H, v[f"{name}_H"], rtol=1e-9, atol=1e-9 * np.abs(v[f"{name}_H"]).max())
+        assert np.allclose(b, v[f"{name}_b"], rtol=1e-9, atol=1e-9 * np.abs(v[f"{name}_b"]).max())
+        assert o.num_correspondences() == int(v[f"{name}_ncorr"])
+        if name == "d1":
+            coords, num, mean, cov = o.voxels()
+            order = np.lexsort((coords[:, 2], coords[:, 1], coords[:, 0]))
+            assert np.array_equal(coords[order], v["vox_coords"]) and np.array_equal(num[order], v["vox_num"])
+            assert np.allclose(mean[order], v["vox_mean"], rtol=0, atol=1e-12) and np.allclose(cov[order], v["vox_cov"], rtol=0, atol=1e-12)
+        T = o.align()
+        assert np.abs(T - v[f"{name}_T"]).max() < 1e-6 and o.last["iterations"] == int(v[f"{name}_iterations"])
