@@ -40,42 +40,9 @@ N_PAIRS = 2  # distinct (sweep, submap) pairs cycled through
 
 
 def build_workload(rank: int, n_submap: int, n_pairs: int = N_PAIRS):
-    """Seeded synthetic stream: sweeps along a trajectory, submap = accumulation of the preceding
-    sweeps in the previous frame's coordinates, subsampled to exactly n_submap points."""
-    scene = synth.Scene.make(synth.BASE_SEED + 2000)
-    need = int(np.ceil(n_submap * 1.03 / 20000.0)) + 2
-    traj = synth.trajectory(need + n_pairs + 8 + rank, seed=2)
-    scans = {}
-
-    def scan(f):
-        if f not in scans:
-            scans[f] = synth.lidar_scan(scene, traj[f], seed=synth.BASE_SEED + 2000 + f)
-        return scans[f]
-
-    pairs = []
-    for p in range(n_pairs):
-        frame = need + p * 3 + rank
-        ref = traj[frame - 1]
-        chunks, total, f = [], 0, frame - 1
-        while total < n_submap * 1.02 and f >= 0:
-            sc = scan(f)
-            Tr = synth.relative_pose(traj[f], ref)
-            chunks.append((sc[:, :3].astype(np.float64) @ Tr[:3, :3].T + Tr[:3, 3]).astype(np.float32))
-            total += len(sc)
-            f -= 1
-        pts = np.concatenate(chunks, 0)
-        if len(pts) < n_submap:
-            raise RuntimeError("not enough points for the submap")
-        rng = np.random.Generator(np.random.PCG64(1234 + p + 100 * rank))
-        sel = np.sort(rng.permutation(len(pts))[:n_submap])
-        tgt = np.ones((n_submap, 4), np.float32)
-        tgt[:, :3] = pts[sel]
-        src = synth.to_xyz1(scan(frame))
-        # guess = previous frame-to-frame motion (SURVEY §8d C2)
-        guess = synth.relative_pose(traj[frame - 1], traj[frame - 2]).astype(np.float32)
-        truth = synth.relative_pose(traj[frame], traj[frame - 1])
-        pairs.append(dict(src=src, tgt=tgt, guess=guess, truth=truth))
-    return pairs
+    """config C2 stream (rgc_slam_b200/workloads.py): sweeps along a trajectory vs the accumulated submap"""
+    from rgc_slam_b200 import workloads
+    return workloads.build_c2_pairs(rank, n_submap, n_pairs)
 
 
 class ClockSampler:

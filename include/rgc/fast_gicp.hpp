@@ -127,6 +127,16 @@ struct IntensityOffset<P, decltype((void)std::declval<P&>().intensity)> {
     return (size_t)(reinterpret_cast<const char*>(&p.intensity) - reinterpret_cast<const char*>(&p));
   }
 };
+// swapSourceAndTarget on the host-side handles: same pointer type -> swap, different -> both reset
+template <class A>
+inline void swap_handles(A& a, A& b) {
+  std::swap(a, b);
+}
+template <class A, class B>
+inline void swap_handles(A& a, B& b) {
+  a.reset();
+  b.reset();
+}
 }  // namespace detail
 
 #if !defined(RGC_WITH_PCL)
@@ -185,6 +195,7 @@ class FastGICP {
   }
   void setInputTarget(const PointCloudTargetConstPtr& cloud) {
     target_ = cloud;
+    filtered_target_ = false;
     core_.setTarget(cloud->points.data(), cloud->size(), sizeof(PointTarget), (uint64_t)(uintptr_t)cloud.get());
   }
   // The frame's front end fused into setInput* (include/rgc_preprocess.h): [adjustDistortion with
@@ -201,12 +212,18 @@ class FastGICP {
   size_t setInputTargetFiltered(const PointCloudTargetConstPtr& cloud, float leaf, const double* q_last_curr_wxyz = nullptr,
                                 const double* t_last_curr = nullptr, float scan_period = 0.1f) {
     target_ = cloud;
+    filtered_target_ = true;
     return core_.setFiltered(false, cloud->points.data(), cloud->size(), sizeof(PointTarget), detail::IntensityOffset<PointTarget>::get(), leaf,
                              q_last_curr_wxyz, t_last_curr, scan_period, (uint64_t)(uintptr_t)cloud.get());
   }
+  // fast_gicp_impl.hpp:49-57.  The cloud handles follow the device-side swap, so that align() copies
+  // the per-point fields of the cloud that is now the source (same point type), or none (different
+  // point types / a filtered cloud: its centroids have no per-point fields).
   void swapSourceAndTarget() {
     detail::check(core_.ctx_, rgc_reg_swap_source_and_target(core_.reg_));
     std::swap(core_.n_src_, core_.n_tgt_);
+    detail::swap_handles(source_, target_);
+    std::swap(filtered_source_, filtered_target_);
   }
   void clearSource() { detail::check(core_.ctx_, rgc_reg_clear_source(core_.reg_)); source_.reset(); }
   void clearTarget() { detail::check(core_.ctx_, rgc_reg_clear_target(core_.reg_)); target_.reset(); }
@@ -262,7 +279,7 @@ class FastGICP {
  private:
   detail::Core core_;
   PointCloudSourceConstPtr source_;
-  bool filtered_source_ = false;
+  bool filtered_source_ = false, filtered_target_ = false;
   PointCloudTargetConstPtr target_;
   Matrix4 final_ = identity4();
 };

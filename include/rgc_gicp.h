@@ -26,8 +26,9 @@
  *     k-NN / covariance kernels keep running (source and target on separate streams) and are joined by
  *     the first call that needs them (align, linearize, get_*_covs ...).  The input buffers are not
  *     referenced after a setter returns.
- *   - a call that fails part-way (allocation failure, CUDA error) does not recycle the pool blocks it had
- *     taken; they are released with the context.
+ *   - scratch blocks of a call go back to the context's pool on every exit path, failures included.
+ *   - clouds must be finite: a NaN / inf coordinate makes set_source / set_target fail with
+ *     RGC_ERR_INVALID (a NaN candidate would silently break the exactness of the k-NN).
  */
 #ifndef RGC_GICP_H
 #define RGC_GICP_H
@@ -139,6 +140,19 @@ int rgc_reg_compute_error(rgc_reg* reg, const double* T16, double* err);
 /* correspondences_ / sq_distances_ of the last linearize, caller's index space (-1 = none;
  * sq_dist is +inf where no target lies within max_correspondence_distance)                  */
 int rgc_reg_get_correspondences(rgc_reg* reg, int32_t* corr, float* sq_dist);
+
+/* How the TARGET covariances of the exact-1-NN FastGICP path are produced.
+ *   on_demand = 1 (default): FastGICP::linearize reads target_covs_[target_index] only at the current
+ *     correspondences (FGI/fast_gicp_impl.hpp:139-146), so the k-NN + covariance of a target point is
+ *     computed the first time it becomes a correspondence, by the same kernels with the parameters in
+ *     force at the first align — the values linearize sees are bit-identical to the eager pass, but a
+ *     500k-point submap costs <= n_source k-NN queries per align instead of 500k per frame.
+ *   on_demand = 0: reference schedule, all n_target covariances at the first align (:107-109).
+ * get_target_covs, the voxelised mode, swap_source_and_target and user-supplied covariances always see /
+ * produce the complete set.  Environment RGC_EAGER_TARGET_COV=1 makes 0 the default.            */
+int rgc_reg_set_target_covariance_mode(rgc_reg* reg, int on_demand);
+/* profiling (rgc_ctx_set_profiling): device time of the on-demand k-NN + covariance kernels of the last linearize */
+int rgc_ctx_last_ondemand_ms(const rgc_ctx* ctx, float* ms);
 
 /* number of correspondences the last linearize used (points within max_correspondence_distance,
  * or (point, voxel) pairs in voxelised mode) */

@@ -85,6 +85,8 @@ def lib():
         L.rgc_knn_self.argtypes = [vp, vp, sz, sz, C.c_int, vp, C.c_float]
         L.rgc_reg_set_vgicp.argtypes = [vp, C.c_int, C.c_double, C.c_int, C.c_int]
         L.rgc_reg_last_inliers.argtypes = [vp, C.POINTER(C.c_int)]
+        L.rgc_reg_set_target_covariance_mode.argtypes = [vp, C.c_int]
+        L.rgc_ctx_last_ondemand_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.rgc_reg_get_voxels.argtypes = [vp, vp, vp, vp, vp, sz, C.POINTER(sz)]
         L.rgc_map_create.argtypes = [vp, vp, sz, sz, C.POINTER(vp)]
         L.rgc_map_destroy.argtypes = [vp]
@@ -109,6 +111,7 @@ EXPORTED_SYMBOLS = [
     "rgc_ctx_set_profiling", "rgc_ctx_last_kernel_ms", "rgc_reg_set_vgicp", "rgc_reg_get_voxels", "rgc_reg_last_inliers",
     "rgc_voxel_grid", "rgc_deskew", "rgc_reg_set_source_filtered", "rgc_reg_set_target_filtered",
     "rgc_map_create", "rgc_map_destroy", "rgc_map_associate_edges", "rgc_map_associate_planes",
+    "rgc_reg_set_target_covariance_mode", "rgc_ctx_last_ondemand_ms",
 ]
 
 
@@ -144,7 +147,11 @@ class Context:
     def last_kernel_ms(self):
         ms = np.zeros(3, np.float32)
         lib().rgc_ctx_last_kernel_ms(self._h, ms.ctypes.data)
-        return dict(zip(("k_correspond", "k_linearize", "k_compute_error"), ms.tolist()))
+        d = dict(zip(("k_correspond", "k_linearize", "k_compute_error"), ms.tolist()))
+        od = C.c_float(0.0)
+        lib().rgc_ctx_last_ondemand_ms(self._h, C.byref(od))
+        d["ondemand_knn_cov"] = od.value
+        return d
 
     def close(self):
         if self._h:
@@ -262,12 +269,24 @@ class FastGICP:
     def setGridCell(self, s):
         self._p.grid_cell = float(s); self._push()
 
+    def setTargetCovarianceMode(self, on_demand: bool):
+        """True (default): target covariances are computed the first time a target point becomes a
+        correspondence; False: all of them at the first align, the reference's schedule
+        (fast_gicp_impl.hpp:107-109).  linearize sees bit-identical values either way."""
+        self.ctx.check(lib().rgc_reg_set_target_covariance_mode(self._h, int(bool(on_demand))))
+
     # ---- clouds ----
-    def _set(self, which, cloud):
+    def _set(self, which, cloud, force=False):
         ptr, n, stride, on_dev, keep = _as_cloud(cloud)
         # object identity plays the shared_ptr identity (fast_gicp_impl.hpp:73,84); we keep a
-        # reference to the object so its id() cannot be recycled while it is the current cloud
-        key = id(cloud)
+        # reference to the object so its id() cannot be recycled while it is the current cloud.
+        # Python has no way to say "same buffer, new contents" (the reference's callers allocate a new
+        # cloud per frame): `force=True` rebuilds regardless, for callers that refill a buffer in place.
+        key = 0 if force else id(cloud)
+        if on_dev:
+            # the library reads the tensor on ITS stream: order it after whatever torch has queued
+            import torch
+            torch.cuda.current_stream(keep.device).synchronize()
         fn = getattr(lib(), f"rgc_reg_set_{which}" + ("_device" if on_dev else ""))
         self.ctx.check(fn(self._h, ptr, n, stride, key))
         if which == "source":
@@ -275,7 +294,7 @@ class FastGICP:
         else:
             self._tgt, self._tgt_id, self._n_tgt = keep, (key, cloud), n
 
-    def _set_filtered(self, which, xyzi, leaf, q_wxyz, t, scan_period):
+    def _set_filtered(self, which, xyzi, leaf, q_wxyz, t, scan_period, force=False):
         """[de-skew] -> [pcl::VoxelGrid] -> setInput*, on the device (include/rgc_preprocess.h).
         xyzi: host [n, 4] float32 (x, y, z, intensity).  Returns the size of the filtered cloud."""
         P = np.ascontiguousarray(xyzi, np.float32)
@@ -286,24 +305,26 @@ class FastGICP:
         m = C.c_size_t(0)
         fn = getattr(lib(), f"rgc_reg_set_{which}_filtered")
         self.ctx.check(fn(self._h, P.ctypes.data, len(P), 16, 12, float(leaf), None if q is None else q.ctypes.data,
-                          None if tt is None else tt.ctypes.data, float(scan_period), id(xyzi), C.byref(m)))
+                          None if tt is None else tt.ctypes.data, float(scan_period), 0 if force else id(xyzi), C.byref(m)))
         if which == "source":
             self._src, self._src_id, self._n_src = P, (id(xyzi), xyzi), m.value
         else:
             self._tgt, self._tgt_id, self._n_tgt = P, (id(xyzi), xyzi), m.value
         return m.value
 
-    def setInputSourceFiltered(self, xyzi, leaf, q_last_curr=None, t_last_curr=None, scan_period=0.1):
-        return self._set_filtered("source", xyzi, leaf, q_last_curr, t_last_curr, scan_period)
+    def setInputSourceFiltered(self, xyzi, leaf, q_last_curr=None, t_last_curr=None, scan_period=0.1, force=False):
+        return self._set_filtered("source", xyzi, leaf, q_last_curr, t_last_curr, scan_period, force)
 
-    def setInputTargetFiltered(self, xyzi, leaf, q_last_curr=None, t_last_curr=None, scan_period=0.1):
-        return self._set_filtered("target", xyzi, leaf, q_last_curr, t_last_curr, scan_period)
+    def setInputTargetFiltered(self, xyzi, leaf, q_last_curr=None, t_last_curr=None, scan_period=0.1, force=False):
+        return self._set_filtered("target", xyzi, leaf, q_last_curr, t_last_curr, scan_period, force)
 
-    def setInputSource(self, cloud):
-        self._set("source", cloud)
+    def setInputSource(self, cloud, force=False):
+        """`force=True`: rebuild even if `cloud` is the same Python object as last time (a buffer that
+        was refilled in place); the default keeps the reference's pointer-identity caching."""
+        self._set("source", cloud, force)
 
-    def setInputTarget(self, cloud):
-        self._set("target", cloud)
+    def setInputTarget(self, cloud, force=False):
+        self._set("target", cloud, force)
 
     def swapSourceAndTarget(self):
         self.ctx.check(lib().rgc_reg_swap_source_and_target(self._h))
@@ -396,6 +417,16 @@ class FastGICP:
         err = C.c_double()
         self.ctx.check(lib().rgc_reg_compute_error(self._h, Tc.ctypes.data, C.byref(err)))
         return err.value
+
+    def target_cov_state(self):
+        """test hook: (covariances (n, 4, 4) as they currently are on the device, computed-flag (n,)),
+        without triggering any computation"""
+        L = lib()
+        L.rgc_debug_get_target_cov_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        c = np.empty((self._n_tgt, 4, 4), np.float64)
+        st = np.empty(self._n_tgt, np.int32)
+        self.ctx.check(L.rgc_debug_get_target_cov_state(self._h, c.ctypes.data, st.ctypes.data))
+        return c, st
 
     def correspondences(self):
         corr = np.empty(self._n_src, np.int32)

@@ -49,11 +49,18 @@ struct rgc_ctx {
   float* h_bbox = nullptr;     // pinned: kBboxBlocks x 6
   uint32_t* h_counts = nullptr;  // pinned: kMaxLevels
   unsigned int* d_ticket = nullptr;
+  // completion word of the reduction kernels (mapped pinned memory): the last block stores `seq` there
+  // after its results are visible, and the host polls it instead of a cudaStreamSynchronize per LM step
+  unsigned long long* h_seq = nullptr;
+  unsigned long long* d_seq = nullptr;  // device alias of h_seq
+  unsigned long long seq = 0;
+  bool spin_wait = std::getenv("RGC_NO_SPIN") == nullptr;
   cudaEvent_t ev[8];
   cudaEvent_t evk[4];       // per-kernel timing of the last linearize / compute_error (profiling only)
   bool profile = false;     // rgc_ctx_set_profiling
   int knn_defer = std::getenv("RGC_KNN_DEFER") ? std::atoi(std::getenv("RGC_KNN_DEFER")) : 600;  // rgc_debug_set_knn_defer
   float last_kernel_ms[3] = {0, 0, 0};  // k_correspond, k_linearize, k_compute_error
+  float last_ondemand_ms = 0;           // on-demand target kNN + covariances of the last linearize (profiling only)
 
   void switch_lane(int to) {
     if (to == lane) return;
@@ -100,6 +107,32 @@ struct rgc_ctx {
   }
   void put_event(cudaEvent_t e) {
     if (e) free_events.push_back(e);
+  }
+};
+
+// pooled scratch blocks of one call: every exit path (FAIL / CK / TRY included) gives them back
+struct Scratch {
+  rgc_ctx* c;
+  std::vector<void*> blocks;
+  explicit Scratch(rgc_ctx* c_) : c(c_) {}
+  Scratch(const Scratch&) = delete;
+  Scratch& operator=(const Scratch&) = delete;
+  void* get(size_t bytes) {
+    void* p = c->get(bytes);
+    if (p) blocks.push_back(p);
+    return p;
+  }
+  // hand a block over to the caller (it is no longer returned to the pool by this object)
+  void* release(void* p) {
+    for (size_t i = 0; i < blocks.size(); i++)
+      if (blocks[i] == p) {
+        blocks.erase(blocks.begin() + (long)i);
+        break;
+      }
+    return p;
+  }
+  ~Scratch() {
+    for (void* p : blocks) c->put(p);
   }
 };
 

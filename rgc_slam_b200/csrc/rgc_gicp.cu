@@ -54,6 +54,11 @@ struct Cloud {
   GridSlot* tables = nullptr;
   GridView view{};
   double* cov = nullptr;  // 6 doubles per sorted point
+  // on-demand mode (target of FastGICP): cov[] is valid only where cov_state[] == 1; has_cov stays false,
+  // so every consumer that needs ALL covariances (getTargetCovariances, the voxel map, a swap) still
+  // triggers the whole-cloud pass
+  int* cov_state = nullptr;
+  bool lazy_cov = false;
   bool has_cov = false;
   bool cov_speculative = false;  // computed at set_input time, before any align has used them
   int cov_k = 0, cov_method = 0;
@@ -105,9 +110,18 @@ static void cloud_release(rgc_ctx* c, Cloud& cl) {
   c->put(cl.inv);
   c->put(cl.tables);
   c->put(cl.cov);
+  c->put(cl.cov_state);
   for (int i = 0; i < 5; i++) c->put_event(cl.ev[i]);
   cl = Cloud();
 }
+
+// a cloud that lives for one call (rgc_knn, debug hooks): released on every exit path
+struct TmpCloud {
+  rgc_ctx* c;
+  Cloud cl;
+  explicit TmpCloud(rgc_ctx* c_) : c(c_) {}
+  ~TmpCloud() { cloud_release(c, cl); }
+};
 
 // stable LSD radix sort of (64-bit key, 32-bit value) pairs on the ctx stream; `hist` holds
 // 256 * (tiles + 1) counters.  On return *kout / *vout point at the buffers with the sorted data.
@@ -147,22 +161,22 @@ static int cloud_build(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, s
   CK(c, cudaEventRecord(cl.ev[0], st));
 
   const unsigned char* d_raw = (const unsigned char*)points;
-  void* staging = nullptr;
+  Scratch tmp(c);  // returned to the pool on every exit path
   if (!on_device) {
-    staging = c->get(n_sz * stride);
+    void* staging = tmp.get(n_sz * stride);
     if (!staging) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (staging)");
     CK(c, cudaMemcpyAsync(staging, points, n_sz * stride, cudaMemcpyHostToDevice, st));
     d_raw = (const unsigned char*)staging;
   }
-  float4* orig = (float4*)c->get(sizeof(float4) * n_sz);
-  float* d_bbox = (float*)c->get(sizeof(float) * 6 * kBboxBlocks);
-  uint64_t* keys_a = (uint64_t*)c->get(8 * n_sz);
-  uint64_t* keys_b = (uint64_t*)c->get(8 * n_sz);
-  uint32_t* vals_a = (uint32_t*)c->get(4 * n_sz);
-  uint32_t* vals_b = (uint32_t*)c->get(4 * n_sz);
+  float4* orig = (float4*)tmp.get(sizeof(float4) * n_sz);
+  float* d_bbox = (float*)tmp.get(sizeof(float) * 6 * kBboxBlocks);
+  uint64_t* keys_a = (uint64_t*)tmp.get(8 * n_sz);
+  uint64_t* keys_b = (uint64_t*)tmp.get(8 * n_sz);
+  uint32_t* vals_a = (uint32_t*)tmp.get(4 * n_sz);
+  uint32_t* vals_b = (uint32_t*)tmp.get(4 * n_sz);
   const int nblk = div_up(n, RS_TILE);
-  uint32_t* hist = (uint32_t*)c->get(4 * 256 * ((size_t)nblk + 1));
-  uint32_t* d_counts = (uint32_t*)c->get(4 * kMaxLevels);
+  uint32_t* hist = (uint32_t*)tmp.get(4 * 256 * ((size_t)nblk + 1));
+  uint32_t* d_counts = (uint32_t*)tmp.get(4 * kMaxLevels);
   cl.sorted = (float4*)c->get(sizeof(float4) * n_sz);
   cl.inv = (int*)c->get(sizeof(int) * n_sz);
   if (!cl.inv || !orig || !d_bbox || !keys_a || !keys_b || !vals_a || !vals_b || !hist || !d_counts || !cl.sorted) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (build)");
@@ -174,13 +188,15 @@ static int cloud_build(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, s
   CK(c, cudaStreamSynchronize(st));
   tr.lap("ingest+bbox sync");
   float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  bool finite = true;  // a block that saw NaN / inf writes NaN partials (k_ingest)
   for (int b = 0; b < kBboxBlocks; b++)
     for (int a = 0; a < 3; a++) {
+      finite = finite && !std::isnan(c->h_bbox[b * 6 + a]) && !std::isnan(c->h_bbox[b * 6 + 3 + a]);
       mn[a] = std::min(mn[a], c->h_bbox[b * 6 + a]);
       mx[a] = std::max(mx[a], c->h_bbox[b * 6 + 3 + a]);
     }
   for (int a = 0; a < 3; a++)
-    if (!std::isfinite(mn[a]) || !std::isfinite(mx[a])) FAIL(c, RGC_ERR_INVALID, "point cloud contains non-finite coordinates");
+    if (!finite || !std::isfinite(mn[a]) || !std::isfinite(mx[a])) FAIL(c, RGC_ERR_INVALID, "point cloud contains non-finite coordinates");
 
   for (int a = 0; a < 3; a++) {
     cl.bb_min[a] = mn[a];
@@ -248,15 +264,6 @@ static int cloud_build(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, s
   v.pts = reinterpret_cast<const F4*>(cl.sorted);
   v.inv = cl.inv;
 
-  c->put(staging);
-  c->put(orig);
-  c->put(d_bbox);
-  c->put(keys_a);
-  c->put(keys_b);
-  c->put(vals_a);
-  c->put(vals_b);
-  c->put(hist);
-  c->put(d_counts);
   cl.n = n;
   cl.key = key;
   cl.valid = true;
@@ -298,26 +305,27 @@ static int pre_filter(rgc_ctx* c, const void* points, size_t n_sz, size_t stride
     D.tz = t3[2];
     D.scan_period = scan_period;
   }
-  void* staging = c->get(n_sz * stride);
-  float4* pts = (float4*)c->get(sizeof(float4) * n_sz);
-  float* d_bbox = (float*)c->get(sizeof(float) * 6 * kBboxBlocks);
+  Scratch tmp(c);  // returned to the pool on every exit path; the block handed to the caller is release()d
+  void* staging = tmp.get(n_sz * stride);
+  float4* pts = (float4*)tmp.get(sizeof(float4) * n_sz);
+  float* d_bbox = (float*)tmp.get(sizeof(float) * 6 * kBboxBlocks);
   if (!staging || !pts || !d_bbox) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (pre-step)");
   CK(c, cudaMemcpyAsync(staging, points, n_sz * stride, cudaMemcpyHostToDevice, st));
   k_pre_ingest<<<kBboxBlocks, 256, 0, st>>>((const unsigned char*)staging, stride, inten_off, n, D, pts, d_bbox);
   CKL(c);
-  c->put(staging);
   if (!(leaf > 0.f)) {  // de-skew only
-    c->put(d_bbox);
-    *d_out = pts;
+    *d_out = (float4*)tmp.release(pts);
     *n_out = n;
     return RGC_OK;
   }
   CK(c, cudaMemcpyAsync(c->h_bbox, d_bbox, sizeof(float) * 6 * kBboxBlocks, cudaMemcpyDeviceToHost, st));
   CK(c, cudaStreamSynchronize(st));
-  c->put(d_bbox);
   float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
   for (int b = 0; b < kBboxBlocks; b++)
     for (int a = 0; a < 3; a++) {
+      // pcl::VoxelGrid skips non-finite points of a non-dense cloud; this interface requires finite input
+      // (include/rgc_preprocess.h) and says so instead of silently mis-binning them
+      if (std::isnan(c->h_bbox[b * 6 + a]) || std::isnan(c->h_bbox[b * 6 + 3 + a])) FAIL(c, RGC_ERR_INVALID, "point cloud contains non-finite coordinates");
       mn[a] = std::min(mn[a], c->h_bbox[b * 6 + a]);
       mx[a] = std::max(mx[a], c->h_bbox[b * 6 + 3 + a]);
     }
@@ -329,7 +337,7 @@ static int pre_filter(rgc_ctx* c, const void* points, size_t n_sz, size_t stride
   if (dd[0] * dd[1] * dd[2] > (long long)INT_MAX) {
     // "Leaf size is too small for the input dataset. Integer indices would overflow.": PCL returns the input
     if (passthrough) *passthrough = 1;
-    *d_out = pts;
+    *d_out = (float4*)tmp.release(pts);
     *n_out = n;
     return RGC_OK;
   }
@@ -343,13 +351,13 @@ static int pre_filter(rgc_ctx* c, const void* points, size_t n_sz, size_t stride
   int key_bits = 1;
   while (key_bits < 32 && (1ll << key_bits) < (long long)div_b[0] * div_b[1] * div_b[2]) key_bits++;
   const int nblk_rs = div_up(n, RS_TILE), nblk_sc = div_up(n, 256 * kScanItems);
-  uint64_t* keys_a = (uint64_t*)c->get(8 * n_sz);
-  uint64_t* keys_b = (uint64_t*)c->get(8 * n_sz);
-  uint32_t* vals_a = (uint32_t*)c->get(4 * n_sz);
-  uint32_t* vals_b = (uint32_t*)c->get(4 * n_sz);
-  uint32_t* hist = (uint32_t*)c->get(4 * 256 * ((size_t)nblk_rs + 1));
-  unsigned int* blk = (unsigned int*)c->get(4 * ((size_t)nblk_sc + 1));
-  int* heads = (int*)c->get(4 * n_sz);
+  uint64_t* keys_a = (uint64_t*)tmp.get(8 * n_sz);
+  uint64_t* keys_b = (uint64_t*)tmp.get(8 * n_sz);
+  uint32_t* vals_a = (uint32_t*)tmp.get(4 * n_sz);
+  uint32_t* vals_b = (uint32_t*)tmp.get(4 * n_sz);
+  uint32_t* hist = (uint32_t*)tmp.get(4 * 256 * ((size_t)nblk_rs + 1));
+  unsigned int* blk = (unsigned int*)tmp.get(4 * ((size_t)nblk_sc + 1));
+  int* heads = (int*)tmp.get(4 * n_sz);
   if (!keys_a || !keys_b || !vals_a || !vals_b || !hist || !blk || !heads) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (voxel filter)");
   k_vg_keys<<<div_up(n, 256), 256, 0, st>>>(pts, n, vg, keys_a, vals_a);
   CKL(c);
@@ -368,15 +376,11 @@ static int pre_filter(rgc_ctx* c, const void* points, size_t n_sz, size_t stride
   float4* out = (float4*)c->get(sizeof(float4) * (size_t)nv);
   if (!out) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (voxel filter output)");
   k_vg_centroid<<<div_up(nv, 128), 128, 0, st>>>(pts, vs, heads, nv, n, out);
-  CKL(c);
-  c->put(keys_a);
-  c->put(keys_b);
-  c->put(vals_a);
-  c->put(vals_b);
-  c->put(hist);
-  c->put(blk);
-  c->put(heads);
-  c->put(pts);
+  c->launches++;
+  if (cudaGetLastError() != cudaSuccess) {
+    c->put(out);
+    FAIL(c, RGC_ERR_CUDA, "kernel launch: k_vg_centroid");
+  }
   *d_out = out;
   *n_out = nv;
   return RGC_OK;
@@ -411,16 +415,16 @@ static int launch_knn_self(rgc_ctx* c, const GridView& v, int n, int k, int* nbr
   // it pays below a few million points; measured 13.1 vs 14.4 ms at 8 M points, 1.33 vs 0.98 ms at 500 k)
   const int defer = (c->knn_defer > 0 && n < 2000000) ? c->knn_defer : INT_MAX;
   const int ntiles = div_up(n, 32);
-  int* dq = (int*)c->get(sizeof(int) * (size_t)(ntiles + 1));  // [0] = count, [1..] = tile ids
+  Scratch tmp(c);
+  int* dq = (int*)tmp.get(sizeof(int) * (size_t)(ntiles + 1));  // [0] = count, [1..] = tile ids
   if (!dq) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (knn defer list)");
   CK(c, cudaMemsetAsync(dq, 0, sizeof(int), c->stream));
   k_knn_tile<<<div_up(n, KT_WARPS * 32), KT_WARPS * 32, smem, c->stream>>>(v, n, k, n_seeds, defer, dq, dq + 1, nbr);
   CKL(c);
   if (defer != INT_MAX) {
-    k_knn_warp<<<std::min(div_up(n, KW_WARPS), 148 * 4), KW_WARPS * 32, 0, c->stream>>>(v, n, k, dq, dq + 1, nbr);
+    k_knn_warp<<<std::min(div_up(n, KW_WARPS), 148 * 4), KW_WARPS * 32, 0, c->stream>>>(v, n, k, dq, dq + 1, nullptr, 0, nbr);
     CKL(c);
   }
-  c->put(dq);
   return RGC_OK;
 }
 
@@ -435,22 +439,23 @@ static int cloud_covariances(rgc_ctx* c, Cloud& cl, int k, int method, bool spec
   }
   if (k < 1) FAIL(c, RGC_ERR_INVALID, "k_correspondences must be >= 1");
   cudaStream_t st = c->stream;
-  int* nbr = (int*)c->get(sizeof(int) * (size_t)k * cl.n);
+  Scratch tmp(c);
+  int* nbr = (int*)tmp.get(sizeof(int) * (size_t)k * cl.n);
   if (!cl.cov) cl.cov = (double*)c->get(sizeof(double) * 6 * (size_t)cl.n);
   if (!nbr || !cl.cov) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (covariances)");
   CK(c, cudaEventRecord(cl.ev[2], st));
   TRY(launch_knn_self(c, cl.view, cl.n, k, nbr));
   CK(c, cudaEventRecord(cl.ev[3], st));
   if (k == 20 && cl.n >= k)  // the default k_correspondences, every slot filled
-    k_covariance<20, true><<<div_up(cl.n, kThreads), kThreads, 0, st>>>(cl.sorted, nbr, cl.n, k, method, cl.cov);
+    k_covariance<20, true><<<div_up(cl.n, kThreads), kThreads, 0, st>>>(cl.sorted, nbr, cl.n, k, method, cl.cov, nullptr, nullptr);
   else if (k <= 20)
-    k_covariance<20, false><<<div_up(cl.n, kThreads), kThreads, 0, st>>>(cl.sorted, nbr, cl.n, k, method, cl.cov);
+    k_covariance<20, false><<<div_up(cl.n, kThreads), kThreads, 0, st>>>(cl.sorted, nbr, cl.n, k, method, cl.cov, nullptr, nullptr);
   else
-    k_covariance<32, false><<<div_up(cl.n, kThreads), kThreads, 0, st>>>(cl.sorted, nbr, cl.n, k, method, cl.cov);
+    k_covariance<32, false><<<div_up(cl.n, kThreads), kThreads, 0, st>>>(cl.sorted, nbr, cl.n, k, method, cl.cov, nullptr, nullptr);
   CKL(c);
   CK(c, cudaEventRecord(cl.ev[4], st));
-  c->put(nbr);
   cl.has_cov = true;
+  cl.lazy_cov = false;
   cl.cov_speculative = speculative;
   cl.cov_k = k;
   cl.cov_method = method;
@@ -467,9 +472,17 @@ struct rgc_reg {
   int* corr = nullptr;
   float* sqd = nullptr;
   double* maha = nullptr;
-  double* partials = nullptr;
+  double* partials = nullptr;      // per-block partial sums of k_linearize / k_compute_error (GICP path only)
+  double* fit_partials = nullptr;  // k_fitness: 2 doubles per block (its own buffer: ADVICE r1, shared `partials` overflow)
+  size_t fit_cap = 0;              // blocks
   int cap_src = 0;
   bool have_corr = false;
+  // on-demand target covariances (FastGICP only): requests of the current linearize
+  bool lazy_target = std::getenv("RGC_EAGER_TARGET_COV") == nullptr;
+  int* need_list = nullptr;   // sorted target positions whose covariance is being computed
+  int* need_count = nullptr;  // device counter (zeroed by k_linearize's last block)
+  int* need_nbr = nullptr;    // k-major neighbour lists of need_list, stride cap_src
+  int need_k = 0;
   // second set of per-point buffers + results of a linearize issued ahead of time (step_lm)
   int* corr2 = nullptr;
   float* sqd2 = nullptr;
@@ -495,6 +508,7 @@ struct rgc_reg {
   int vox_count = 0;
   int* vox_corr = nullptr;
   double* vox_maha = nullptr;
+  double* vox_partials = nullptr;  // (148 * 8 + 8) x kLinN
   size_t vox_cap = 0;
   // sharded target (config C5)
   Slab slab{-1, 0.f, 0.f};
@@ -506,11 +520,32 @@ struct rgc_reg {
 // where the reduction kernels write, and (sharded) the cross-rank sum before the host reads it
 constexpr int kSpecSlot = 32;  // doubles: results of the look-ahead linearize live at h_result + 32
 static double* reg_result_ptr(rgc_reg* r) { return r->reduce_fn ? r->reduce_buf : r->ctx->d_result; }
+// completion word for the next reduction kernel (null when the sharded all-reduce hook is on, or
+// polling is disabled: the host then waits on the stream)
+static DoneFlag reg_next_done(rgc_reg* r) {
+  rgc_ctx* c = r->ctx;
+  if (r->reduce_fn || !c->spin_wait) return DoneFlag{nullptr, 0ull};
+  return DoneFlag{c->d_seq, ++c->seq};
+}
 static int reg_finish_reduce(rgc_reg* r, int n_doubles) {
   rgc_ctx* c = r->ctx;
   if (r->reduce_fn) {
     if (r->reduce_fn(r->reduce_user, r->reduce_buf, n_doubles) != 0) FAIL(c, RGC_ERR_STATE, "all-reduce hook failed");
     CK(c, cudaMemcpyAsync(c->h_result, r->reduce_buf, sizeof(double) * n_doubles, cudaMemcpyDeviceToHost, c->stream));
+  } else if (c->spin_wait) {
+    // the last block of the last reduction kernel stored c->seq into mapped pinned memory after its
+    // results: poll that word (an LM step is ~60 us of device work; a stream synchronize adds several us
+    // of wake-up latency to every one of them)
+    volatile unsigned long long* flag = c->h_seq;
+    for (unsigned spins = 0; *flag != c->seq; spins++) {
+      if ((spins & 0x3fff) == 0x3fff) {  // a failed launch / device fault never stores the word
+        cudaError_t e = cudaStreamQuery(c->stream);
+        if (e == cudaSuccess) break;
+        if (e != cudaErrorNotReady) CK(c, e);
+      }
+    }
+    if (*flag != c->seq) CK(c, cudaStreamSynchronize(c->stream));
+    return RGC_OK;
   }
   CK(c, cudaStreamSynchronize(c->stream));
   return RGC_OK;
@@ -518,7 +553,8 @@ static int reg_finish_reduce(rgc_reg* r, int n_doubles) {
 
 static int reg_ensure_work(rgc_reg* r) {
   rgc_ctx* c = r->ctx;
-  if (r->cap_src >= r->src.n && r->corr) return RGC_OK;
+  const int k = std::max(r->prm.k_correspondences, r->tgt.lazy_cov ? r->tgt.cov_k : 0);  // on-demand covariances keep their latched k
+  if (r->cap_src >= r->src.n && r->corr && r->need_k >= k) return RGC_OK;
   c->put(r->corr);
   c->put(r->sqd);
   c->put(r->maha);
@@ -526,6 +562,9 @@ static int reg_ensure_work(rgc_reg* r) {
   c->put(r->sqd2);
   c->put(r->maha2);
   c->put(r->partials);
+  c->put(r->need_list);
+  c->put(r->need_nbr);
+  r->cap_src = 0;
   const size_t n = (size_t)r->src.n;
   r->corr = (int*)c->get(4 * n);
   r->sqd = (float*)c->get(4 * n);
@@ -533,12 +572,36 @@ static int reg_ensure_work(rgc_reg* r) {
   r->corr2 = (int*)c->get(4 * n);
   r->sqd2 = (float*)c->get(4 * n);
   r->maha2 = (double*)c->get(48 * n);
-  if (!r->corr2 || !r->sqd2 || !r->maha2) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (work buffers)");
-  r->partials = (double*)c->get(sizeof(double) * kLinN * (size_t)div_up(r->src.n * query_spread(r->src.n), kThreads));
-  if (!r->corr || !r->sqd || !r->maha || !r->partials) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (work buffers)");
+  r->partials = (double*)c->get(sizeof(double) * kLinN * (size_t)reduce_grid(r->src.n));
+  r->need_list = (int*)c->get(4 * n);
+  r->need_nbr = (int*)c->get(4 * n * (size_t)k);
+  if (!r->need_count) {
+    r->need_count = (int*)c->get(4);
+    if (r->need_count) CK(c, cudaMemsetAsync(r->need_count, 0, 4, c->stream));
+  }
+  if (!r->corr || !r->sqd || !r->maha || !r->corr2 || !r->sqd2 || !r->maha2 || !r->partials || !r->need_list || !r->need_nbr || !r->need_count)
+    FAIL(c, RGC_ERR_NOMEM, "device allocation failed (work buffers)");
   r->cap_src = r->src.n;
+  r->need_k = k;
   return RGC_OK;
 }
+
+// scratch of k_fitness only (it launches one block per 128 queries, unlike the persistent linearize grid)
+static int reg_ensure_fitness(rgc_reg* r, int blocks) {
+  rgc_ctx* c = r->ctx;
+  if (r->fit_partials && r->fit_cap >= (size_t)blocks) return RGC_OK;
+  c->put(r->fit_partials);
+  r->fit_cap = 0;
+  r->fit_partials = (double*)c->get(sizeof(double) * 2 * (size_t)blocks);
+  if (!r->fit_partials) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (fitness scratch)");
+  r->fit_cap = (size_t)blocks;
+  return RGC_OK;
+}
+
+// can the target's covariances be computed on demand?  Only the exact-1-NN FastGICP path reads C_B at
+// correspondences alone; the voxel map averages ALL of them, and covariances the user supplied or that
+// were already computed for the whole cloud are simply used.
+static bool target_lazy(const rgc_reg* r) { return r->lazy_target && !r->vgicp && !r->tgt.has_cov; }
 
 static void to_rt(const double* T /*row-major 4x4*/, Rt& d, RtF& f) {
   for (int i = 0; i < 12; i++) {
@@ -570,13 +633,14 @@ static int vgicp_build(rgc_reg* r) {
   }
   if (total_bits > 62) FAIL(c, RGC_ERR_UNSUPPORTED, "voxel grid too large for a 62-bit key (resolution too small for this extent)");
   const size_t n_sz = (size_t)n;
-  uint64_t* keys_a = (uint64_t*)c->get(8 * n_sz);
-  uint64_t* keys_b = (uint64_t*)c->get(8 * n_sz);
-  uint32_t* vals_a = (uint32_t*)c->get(4 * n_sz);
-  uint32_t* vals_b = (uint32_t*)c->get(4 * n_sz);
-  uint32_t* hist = (uint32_t*)c->get(4 * 256 * ((size_t)div_up(n, RS_TILE) + 1));
-  unsigned int* d_cnt = (unsigned int*)c->get(4);
-  int* heads = (int*)c->get(4 * n_sz);
+  Scratch tmp(c);
+  uint64_t* keys_a = (uint64_t*)tmp.get(8 * n_sz);
+  uint64_t* keys_b = (uint64_t*)tmp.get(8 * n_sz);
+  uint32_t* vals_a = (uint32_t*)tmp.get(4 * n_sz);
+  uint32_t* vals_b = (uint32_t*)tmp.get(4 * n_sz);
+  uint32_t* hist = (uint32_t*)tmp.get(4 * 256 * ((size_t)div_up(n, RS_TILE) + 1));
+  unsigned int* d_cnt = (unsigned int*)tmp.get(4);
+  int* heads = (int*)tmp.get(4 * n_sz);
   if (!keys_a || !keys_b || !vals_a || !vals_b || !hist || !d_cnt || !heads) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (voxel map)");
   k_vox_keys<<<div_up(n, 256), 256, 0, st>>>(t.sorted, n, g, keys_a, vals_a);
   CKL(c);
@@ -605,13 +669,6 @@ static int vgicp_build(rgc_reg* r) {
   r->vox = VoxelMapView{r->vox_slots, (uint32_t)(slots - 1), (uint32_t)(64 - lg), g};
   r->vox_count = nv;
   r->vox_valid = true;
-  c->put(keys_a);
-  c->put(keys_b);
-  c->put(vals_a);
-  c->put(vals_b);
-  c->put(hist);
-  c->put(d_cnt);
-  c->put(heads);
   return RGC_OK;
 }
 
@@ -621,12 +678,11 @@ static int vgicp_ensure_work(rgc_reg* r) {
   if (r->vox_cap >= need && r->vox_corr) return RGC_OK;
   c->put(r->vox_corr);
   c->put(r->vox_maha);
-  c->put(r->partials);
+  r->vox_cap = 0;
   r->vox_corr = (int*)c->get(4 * need);
   r->vox_maha = (double*)c->get(48 * need);
-  r->partials = (double*)c->get(sizeof(double) * kLinN * (size_t)(148 * 8 + 8));
-  r->cap_src = 0;  // the GICP work buffers (sharing `partials`) must be re-made if that path is used later
-  if (!r->vox_corr || !r->vox_maha || !r->partials) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (vgicp work buffers)");
+  if (!r->vox_partials) r->vox_partials = (double*)c->get(sizeof(double) * kLinN * (size_t)(148 * 8 + 8));
+  if (!r->vox_corr || !r->vox_maha || !r->vox_partials) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (vgicp work buffers)");
   r->vox_cap = need;
   return RGC_OK;
 }
@@ -644,7 +700,7 @@ static int vgicp_linearize(rgc_reg* r, const double* T, double* err, double* H, 
   const long long total = (long long)r->src.n * n_off;
   const int grid = (int)std::min<long long>((total + kThreads - 1) / kThreads, 148 * 8);
   k_vgicp_linearize<<<grid, kThreads, 0, c->stream>>>(r->vox, r->src.sorted, r->src.cov, r->src.n, r->vox_search, n_off, Td, want, r->vox_corr, r->vox_maha,
-                                                     r->partials, c->d_ticket, reg_result_ptr(r));
+                                                     r->vox_partials, c->d_ticket, reg_result_ptr(r), reg_next_done(r));
   CKL(c);
   TRY(reg_finish_reduce(r, kLinN));
   r->n_linearize++;
@@ -674,8 +730,8 @@ static int vgicp_compute_error(rgc_reg* r, const double* T, double* err) {
   const int n_off = vgicp_n_off(r);
   const long long total = (long long)r->src.n * n_off;
   const int grid = (int)std::min<long long>((total + kThreads - 1) / kThreads, 148 * 8);
-  k_vgicp_compute_error<<<grid, kThreads, 0, c->stream>>>(r->vox, r->src.sorted, r->src.n, n_off, Td, r->vox_corr, r->vox_maha, r->partials, c->d_ticket,
-                                                         reg_result_ptr(r));
+  k_vgicp_compute_error<<<grid, kThreads, 0, c->stream>>>(r->vox, r->src.sorted, r->src.n, n_off, Td, r->vox_corr, r->vox_maha, r->vox_partials, c->d_ticket,
+                                                         reg_result_ptr(r), reg_next_done(r));
   CKL(c);
   TRY(reg_finish_reduce(r, 1));
   r->n_compute_error++;
@@ -693,14 +749,34 @@ static int gicp_linearize_launch(rgc_reg* r, const double* T, int want, const in
   const float thr = r->prm.max_correspondence_distance;
   const float thr2 = thr * thr;  // float product, +inf for the FLT_MAX default (fast_gicp_impl.hpp:136)
   const int spread = query_spread(r->src.n);
+  const bool lazy = r->tgt.lazy_cov;
   if (c->profile) CK(c, cudaEventRecord(c->evk[0], c->stream));
   // (a warp-cooperative variant of this search, one warp per 32 Morton-adjacent source points, was exact
   // too but slower on one sweep, 155 vs 92 us: profiles/README.md; it was removed)
-  k_correspond<<<div_up(r->src.n * spread, kThreads), kThreads, 0, c->stream>>>(r->tgt.view, r->src.sorted, r->src.n, spread, Tf, thr2, r->slab, hint, corr, sqd);
+  k_correspond<<<div_up(r->src.n * spread, kThreads), kThreads, 0, c->stream>>>(r->tgt.view, r->src.sorted, r->src.n, spread, Tf, thr2, r->slab, hint, corr, sqd,
+                                                                               lazy ? r->tgt.cov_state : nullptr, r->need_list, r->need_count);
   CKL(c);
   if (c->profile) CK(c, cudaEventRecord(c->evk[1], c->stream));
+  if (lazy) {
+    // on-demand target covariances: exact k-NN (one warp per query) + covariance of exactly the target
+    // points that became correspondences for the first time.  The launches are sized for the worst case
+    // (every source point a new target point) and read the real count from the device: nothing here
+    // makes the host wait.  After the first linearize of an align the list is nearly empty.
+    const int k = r->tgt.cov_k, method = r->tgt.cov_method, cap = r->cap_src, n_t = r->tgt.n;
+    k_knn_warp<<<std::min(div_up(r->src.n, KW_WARPS), 148 * 4), KW_WARPS * 32, 0, c->stream>>>(r->tgt.view, n_t, k, r->need_count, nullptr, r->need_list, cap, r->need_nbr);
+    CKL(c);
+    const int grid = div_up(r->src.n, kThreads);
+    if (k == 20 && n_t >= k)
+      k_covariance<20, true><<<grid, kThreads, 0, c->stream>>>(r->tgt.sorted, r->need_nbr, cap, k, method, r->tgt.cov, r->need_list, r->need_count);
+    else if (k <= 20)
+      k_covariance<20, false><<<grid, kThreads, 0, c->stream>>>(r->tgt.sorted, r->need_nbr, cap, k, method, r->tgt.cov, r->need_list, r->need_count);
+    else
+      k_covariance<32, false><<<grid, kThreads, 0, c->stream>>>(r->tgt.sorted, r->need_nbr, cap, k, method, r->tgt.cov, r->need_list, r->need_count);
+    CKL(c);
+    if (c->profile) CK(c, cudaEventRecord(c->evk[3], c->stream));
+  }
   k_linearize<<<reduce_grid(r->src.n), kThreads, 0, c->stream>>>(r->tgt.sorted, r->src.sorted, r->src.cov, r->tgt.cov, r->src.n, Td, want, corr, maha, r->partials,
-                                                                     c->d_ticket, result);
+                                                                     c->d_ticket, result, reg_next_done(r), lazy ? r->need_count : nullptr);
   CKL(c);
   if (c->profile) CK(c, cudaEventRecord(c->evk[2], c->stream));
   return RGC_OK;
@@ -727,8 +803,15 @@ static int reg_linearize(rgc_reg* r, const double* T, double* err, double* H, do
   TRY(gicp_linearize_launch(r, T, (H && b) ? 1 : 0, r->have_corr ? r->corr : nullptr, r->corr, r->sqd, r->maha, reg_result_ptr(r)));
   TRY(reg_finish_reduce(r, kLinN));
   if (c->profile) {
+    cudaEventSynchronize(c->evk[2]);
     cudaEventElapsedTime(&c->last_kernel_ms[0], c->evk[0], c->evk[1]);
-    cudaEventElapsedTime(&c->last_kernel_ms[1], c->evk[1], c->evk[2]);
+    if (r->tgt.lazy_cov) {
+      cudaEventElapsedTime(&c->last_ondemand_ms, c->evk[1], c->evk[3]);
+      cudaEventElapsedTime(&c->last_kernel_ms[1], c->evk[3], c->evk[2]);
+    } else {
+      c->last_ondemand_ms = 0.f;
+      cudaEventElapsedTime(&c->last_kernel_ms[1], c->evk[1], c->evk[2]);
+    }
   }
   r->n_linearize++;
   r->have_corr = true;
@@ -751,12 +834,15 @@ static int reg_compute_error(rgc_reg* r, const double* T, double* err, bool ahea
   to_rt(T, Td, Tf);
   if (c->profile) CK(c, cudaEventRecord(c->evk[0], c->stream));
   k_compute_error<<<reduce_grid(r->src.n), kThreads, 0, c->stream>>>(r->tgt.sorted, r->src.sorted, r->src.n, Td, r->corr, r->maha, r->partials,
-                                                                         c->d_ticket, reg_result_ptr(r));
+                                                                         c->d_ticket, reg_result_ptr(r), reg_next_done(r));
   CKL(c);
   if (c->profile) CK(c, cudaEventRecord(c->evk[1], c->stream));
   if (ahead) TRY(gicp_linearize_launch(r, T, 1, r->corr, r->corr2, r->sqd2, r->maha2, c->d_result + kSpecSlot));
   TRY(reg_finish_reduce(r, 1));
-  if (c->profile) cudaEventElapsedTime(&c->last_kernel_ms[2], c->evk[0], c->evk[1]);
+  if (c->profile) {
+    cudaEventSynchronize(c->evk[1]);
+    cudaEventElapsedTime(&c->last_kernel_ms[2], c->evk[0], c->evk[1]);
+  }
   r->n_compute_error++;
   *err = c->h_result[0];
   if (ahead) gicp_linearize_unpack(c->h_result + kSpecSlot, &r->spec_y0, &r->spec_inliers, r->spec_H, r->spec_b);
@@ -779,7 +865,27 @@ static int reg_ready(rgc_reg* r) {
   // fast_gicp_impl.hpp:104-109 — covariances are computed lazily, source first (normally both
   // were already started by set_input, see set_cloud)
   TRY(cloud_covariances(c, r->src, r->prm.k_correspondences, r->prm.regularization));
-  TRY(cloud_covariances(c, r->tgt, r->prm.k_correspondences, r->prm.regularization));
+  if (target_lazy(r)) {
+    // Target covariances on demand: linearize reads target_covs_[target_index] only at the current
+    // correspondences (fast_gicp_impl.hpp:139-146), <= n_source of the n_target covariances the
+    // reference computes up front (:107-109).  Each one is still the covariance of that point's exact
+    // k nearest neighbours with the parameters in force at the first align, computed by the same
+    // kernels: the values linearize sees are bit-identical to the eager pass.
+    Cloud& t = r->tgt;
+    if (!t.lazy_cov) {
+      const int k = r->prm.k_correspondences;
+      if (k < 1) FAIL(c, RGC_ERR_INVALID, "k_correspondences must be >= 1");
+      if (!t.cov) t.cov = (double*)c->get(sizeof(double) * 6 * (size_t)t.n);
+      if (!t.cov_state) t.cov_state = (int*)c->get(sizeof(int) * (size_t)t.n);
+      if (!t.cov || !t.cov_state) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (on-demand covariances)");
+      CK(c, cudaMemsetAsync(t.cov_state, 0, sizeof(int) * (size_t)t.n, c->stream));
+      t.cov_k = k;  // latched like the reference's covariances: computed once per cloud
+      t.cov_method = r->prm.regularization;
+      t.lazy_cov = true;
+    }
+  } else {
+    TRY(cloud_covariances(c, r->tgt, r->prm.k_correspondences, r->prm.regularization));
+  }
   return RGC_OK;
 }
 
@@ -871,7 +977,10 @@ int rgc_ctx_create(int device, rgc_ctx** out) {
             cudaHostGetDevicePointer((void**)&c->d_result, c->h_result, 0) == cudaSuccess &&
             cudaHostAlloc((void**)&c->h_bbox, sizeof(float) * 6 * kBboxBlocks, cudaHostAllocDefault) == cudaSuccess &&
             cudaHostAlloc((void**)&c->h_counts, sizeof(uint32_t) * kMaxLevels, cudaHostAllocDefault) == cudaSuccess &&
-            cudaMalloc((void**)&c->d_ticket, 64) == cudaSuccess && cudaMemset(c->d_ticket, 0, 64) == cudaSuccess;
+            cudaMalloc((void**)&c->d_ticket, 64) == cudaSuccess && cudaMemset(c->d_ticket, 0, 64) == cudaSuccess &&
+            cudaHostAlloc((void**)&c->h_seq, 64, cudaHostAllocMapped) == cudaSuccess &&
+            cudaHostGetDevicePointer((void**)&c->d_seq, c->h_seq, 0) == cudaSuccess;
+  if (ok) *c->h_seq = 0ull;
   // lane 1 (source cloud: ~25 small kernels) gets the higher priority, so that its blocks are
   // dispatched ahead of the thousands of pending blocks of the target's kNN launch on lane 0
   // (without it the source build took 0.87 ms instead of 0.19 ms when overlapped)
@@ -900,6 +1009,7 @@ int rgc_ctx_destroy(rgc_ctx* c) {
   cudaStreamSynchronize(c->parked.stream);
   for (auto& kv : c->block_info) cudaFree(kv.first);
   cudaFreeHost(c->h_result);
+  cudaFreeHost(c->h_seq);
   cudaFreeHost(c->h_bbox);
   cudaFreeHost(c->h_counts);
   cudaFreeHost(c->parked.h_bbox);
@@ -972,9 +1082,14 @@ int rgc_reg_destroy(rgc_reg* r) {
   c->put(r->sqd2);
   c->put(r->maha2);
   c->put(r->partials);
+  c->put(r->fit_partials);
+  c->put(r->need_list);
+  c->put(r->need_count);
+  c->put(r->need_nbr);
   c->put(r->vox_slots);
   c->put(r->vox_corr);
   c->put(r->vox_maha);
+  c->put(r->vox_partials);
   delete r;
   return RGC_OK;
 }
@@ -1003,6 +1118,7 @@ static int set_cloud(rgc_reg* r, Cloud& cl, const void* pts, size_t n, size_t st
   // the kNN of a 500k-point target then runs while the host uploads and sorts the source.
   SideLane side(c, &cl == &r->src);
   TRY(cloud_build(c, cl, pts, n, stride, on_device, key, r->prm.grid_cell));
+  if (&cl == &r->tgt && target_lazy(r)) return RGC_OK;  // computed on demand inside linearize (reg_ready)
   return cloud_covariances(c, cl, r->prm.k_correspondences, r->prm.regularization, true);
 }
 int rgc_reg_set_source(rgc_reg* r, const void* p, size_t n, size_t s, uint64_t key) { return r ? set_cloud(r, r->src, p, n, s, key, false) : RGC_ERR_INVALID; }
@@ -1037,15 +1153,16 @@ static int set_covs(rgc_reg* r, Cloud& cl, const double* m, size_t n) {
   if (!cl.valid) FAIL(c, RGC_ERR_STATE, "set the point cloud before its covariances");
   if ((int)n != cl.n) FAIL(c, RGC_ERR_INVALID, "covariance count does not match the cloud size");
   TRY(join_side(c));
-  double* stage = (double*)c->get(128 * n);
+  Scratch tmp(c);
+  double* stage = (double*)tmp.get(128 * n);
   if (!cl.cov) cl.cov = (double*)c->get(48 * n);
   if (!stage || !cl.cov) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (covariance import)");
   CK(c, cudaMemcpyAsync(stage, m, 128 * n, cudaMemcpyHostToDevice, c->stream));
   k_cov_import<<<div_up(cl.n, 256), 256, 0, c->stream>>>(cl.sorted, cl.n, stage, cl.cov);
   CKL(c);
   CK(c, cudaStreamSynchronize(c->stream));
-  c->put(stage);
   cl.has_cov = true;
+  cl.lazy_cov = false;
   cl.cov_speculative = false;  // user-provided: kept whatever the parameters
   cl.cov_timed = false;
   cl.knn_ms = cl.cov_ms = 0.f;
@@ -1059,13 +1176,13 @@ static int get_covs(rgc_reg* r, Cloud& cl, double* m, size_t n) {
   if ((int)n != cl.n) FAIL(c, RGC_ERR_INVALID, "covariance count does not match the cloud size");
   TRY(join_side(c));
   TRY(cloud_covariances(c, cl, r->prm.k_correspondences, r->prm.regularization));
-  double* stage = (double*)c->get(128 * n);
+  Scratch tmp(c);
+  double* stage = (double*)tmp.get(128 * n);
   if (!stage) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (covariance export)");
   k_cov_export<<<div_up(cl.n, 256), 256, 0, c->stream>>>(cl.sorted, cl.n, cl.cov, stage);
   CKL(c);
   CK(c, cudaMemcpyAsync(m, stage, 128 * n, cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
-  c->put(stage);
   return RGC_OK;
 }
 int rgc_reg_set_source_covs(rgc_reg* r, const double* m, size_t n) { return (r && m) ? set_covs(r, r->src, m, n) : RGC_ERR_INVALID; }
@@ -1110,12 +1227,12 @@ int rgc_reg_align(rgc_reg* r, const float* guess, float* final_T16, rgc_result* 
   if (out_points) {
     RtF Tf;
     for (int i = 0; i < 12; i++) Tf.m[i] = r->final_T[i];
-    float4* d_out = (float4*)c->get(sizeof(float4) * (size_t)r->src.n);
+    Scratch tmp(c);
+    float4* d_out = (float4*)tmp.get(sizeof(float4) * (size_t)r->src.n);
     if (!d_out) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (output cloud)");
     k_transform_out<<<div_up(r->src.n, 256), 256, 0, c->stream>>>(r->src.sorted, r->src.n, Tf, d_out);
     CKL(c);
     CK(c, cudaMemcpyAsync(out_points, d_out, sizeof(float4) * (size_t)r->src.n, cudaMemcpyDeviceToHost, c->stream));
-    c->put(d_out);
   }
   CK(c, cudaEventRecord(c->ev[7], c->stream));
   CK(c, cudaEventSynchronize(c->ev[7]));
@@ -1171,16 +1288,15 @@ int rgc_reg_get_correspondences(rgc_reg* r, int32_t* corr, float* sq_dist) {
   if (r->vgicp) FAIL(c, RGC_ERR_UNSUPPORTED, "point correspondences do not exist in voxelised mode");
   if (!r->have_corr) FAIL(c, RGC_ERR_STATE, "no correspondences yet (call linearize or align first)");
   const size_t n = (size_t)r->src.n;
-  int* d_c = (int*)c->get(4 * n);
-  float* d_s = (float*)c->get(4 * n);
+  Scratch tmp(c);
+  int* d_c = (int*)tmp.get(4 * n);
+  float* d_s = (float*)tmp.get(4 * n);
   if (!d_c || !d_s) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (correspondence export)");
   k_corr_to_orig<<<div_up(r->src.n, 256), 256, 0, c->stream>>>(r->src.sorted, r->tgt.sorted, r->corr, r->sqd, r->src.n, d_c, d_s);
   CKL(c);
   CK(c, cudaMemcpyAsync(corr, d_c, 4 * n, cudaMemcpyDeviceToHost, c->stream));
   if (sq_dist) CK(c, cudaMemcpyAsync(sq_dist, d_s, 4 * n, cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
-  c->put(d_c);
-  c->put(d_s);
   return RGC_OK;
 }
 
@@ -1190,12 +1306,13 @@ int rgc_reg_fitness(rgc_reg* r, double max_range, double* score) {
   CK(c, cudaSetDevice(c->device));
   TRY(join_side(c));
   if (!r->src.valid || !r->tgt.valid) FAIL(c, RGC_ERR_STATE, "source and target clouds must both be set");
-  TRY(reg_ensure_work(r));
   RtF Tf;
   for (int i = 0; i < 12; i++) Tf.m[i] = r->final_T[i];
   const int spread = query_spread(r->src.n);
-  k_fitness<<<div_up(r->src.n * spread, kThreads), kThreads, 0, c->stream>>>(r->tgt.view, r->src.sorted, r->src.n, spread, Tf, max_range, r->slab, r->partials, c->d_ticket,
-                                                                            reg_result_ptr(r));
+  const int blocks = div_up(r->src.n * spread, kThreads);
+  TRY(reg_ensure_fitness(r, blocks));
+  k_fitness<<<blocks, kThreads, 0, c->stream>>>(r->tgt.view, r->src.sorted, r->src.n, spread, Tf, max_range, r->slab, r->fit_partials, c->d_ticket,
+                                                reg_result_ptr(r), reg_next_done(r));
   CKL(c);
   TRY(reg_finish_reduce(r, 2));
   const double sum = c->h_result[0], nr = c->h_result[1];
@@ -1216,13 +1333,15 @@ int rgc_knn(rgc_ctx* c, const void* points, size_t n, size_t stride, const void*
   CK(c, cudaSetDevice(c->device));
   if (k > 32) FAIL(c, RGC_ERR_UNSUPPORTED, "k > 32 is not supported");
   if (qstride < 12 || qstride % 4) FAIL(c, RGC_ERR_INVALID, "query stride must be a multiple of 4 and >= 12 bytes");
-  Cloud cl;
+  TmpCloud tc(c);
+  Cloud& cl = tc.cl;
   TRY(cloud_build(c, cl, points, n, stride, false, 0, grid_cell));
-  void* qraw = c->get(m * qstride);
-  float4* q4 = (float4*)c->get(sizeof(float4) * m);
-  float* bb = (float*)c->get(sizeof(float) * 6 * kBboxBlocks);
-  int* d_idx = (int*)c->get(4 * m * (size_t)k);
-  float* d_d2 = (float*)c->get(4 * m * (size_t)k);
+  Scratch tmp(c);
+  void* qraw = tmp.get(m * qstride);
+  float4* q4 = (float4*)tmp.get(sizeof(float4) * m);
+  float* bb = (float*)tmp.get(sizeof(float) * 6 * kBboxBlocks);
+  int* d_idx = (int*)tmp.get(4 * m * (size_t)k);
+  float* d_d2 = (float*)tmp.get(4 * m * (size_t)k);
   if (!qraw || !q4 || !bb || !d_idx || !d_d2) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (knn)");
   CK(c, cudaMemcpyAsync(qraw, queries, m * qstride, cudaMemcpyHostToDevice, c->stream));
   k_ingest<<<kBboxBlocks, 256, 0, c->stream>>>((const unsigned char*)qraw, qstride, (int)m, q4, bb);
@@ -1231,12 +1350,6 @@ int rgc_knn(rgc_ctx* c, const void* points, size_t n, size_t stride, const void*
   CK(c, cudaMemcpyAsync(idx, d_idx, 4 * m * (size_t)k, cudaMemcpyDeviceToHost, c->stream));
   if (d2) CK(c, cudaMemcpyAsync(d2, d_d2, 4 * m * (size_t)k, cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
-  c->put(qraw);
-  c->put(q4);
-  c->put(bb);
-  c->put(d_idx);
-  c->put(d_d2);
-  cloud_release(c, cl);
   return RGC_OK;
 }
 
@@ -1245,19 +1358,18 @@ int rgc_knn(rgc_ctx* c, const void* points, size_t n, size_t stride, const void*
 int rgc_knn_self(rgc_ctx* c, const void* points, size_t n, size_t stride, int k, int32_t* idx, float grid_cell) {
   if (!c || !points || !idx || k < 1) return RGC_ERR_INVALID;
   CK(c, cudaSetDevice(c->device));
-  Cloud cl;
+  TmpCloud tc(c);
+  Cloud& cl = tc.cl;
   TRY(cloud_build(c, cl, points, n, stride, false, 0, grid_cell));
-  int* nbr = (int*)c->get(sizeof(int) * (size_t)k * n);
-  int* d_idx = (int*)c->get(sizeof(int) * (size_t)k * n);
+  Scratch tmp(c);
+  int* nbr = (int*)tmp.get(sizeof(int) * (size_t)k * n);
+  int* d_idx = (int*)tmp.get(sizeof(int) * (size_t)k * n);
   if (!nbr || !d_idx) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (knn_self)");
   TRY(launch_knn_self(c, cl.view, cl.n, k, nbr));
   k_nbr_to_orig<<<div_up(cl.n, 256), 256, 0, c->stream>>>(cl.sorted, nbr, cl.n, k, d_idx);
   CKL(c);
   CK(c, cudaMemcpyAsync(idx, d_idx, sizeof(int) * (size_t)k * n, cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
-  c->put(nbr);
-  c->put(d_idx);
-  cloud_release(c, cl);
   return RGC_OK;
 }
 
@@ -1274,11 +1386,13 @@ int rgc_debug_set_knn_defer(rgc_ctx* c, int cands) {
 int rgc_debug_tile_stats(rgc_ctx* c, const void* points, size_t n, size_t stride, int k, long long* stats, float grid_cell) {
   if (!c || !points || !stats) return RGC_ERR_INVALID;
   CK(c, cudaSetDevice(c->device));
-  Cloud cl;
+  TmpCloud tc(c);
+  Cloud& cl = tc.cl;
   TRY(cloud_build(c, cl, points, n, stride, false, 0, grid_cell));
   const size_t nw = (n + 31) / 32;
-  int* nbr = (int*)c->get(sizeof(int) * (size_t)k * n);
-  long long* d_stats = (long long*)c->get(sizeof(long long) * 4 * nw);
+  Scratch tmp(c);
+  int* nbr = (int*)tmp.get(sizeof(int) * (size_t)k * n);
+  long long* d_stats = (long long*)tmp.get(sizeof(long long) * 4 * nw);
   if (!nbr || !d_stats) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (debug)");
   CK(c, cudaMemsetAsync(d_stats, 0, sizeof(long long) * 4 * nw, c->stream));
   CK(c, cudaMemcpyToSymbolAsync(g_tile_dbg, &d_stats, sizeof(d_stats), 0, cudaMemcpyHostToDevice, c->stream));
@@ -1287,9 +1401,6 @@ int rgc_debug_tile_stats(rgc_ctx* c, const void* points, size_t n, size_t stride
   CK(c, cudaMemcpyToSymbolAsync(g_tile_dbg, &null_ptr, sizeof(null_ptr), 0, cudaMemcpyHostToDevice, c->stream));
   CK(c, cudaMemcpyAsync(stats, d_stats, sizeof(long long) * 4 * nw, cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
-  c->put(nbr);
-  c->put(d_stats);
-  cloud_release(c, cl);
   return RGC_OK;
 }
 
@@ -1301,7 +1412,8 @@ int rgc_debug_correspond_stats(rgc_reg* r, const double* T16, long long* stats) 
   CK(c, cudaSetDevice(c->device));
   TRY(reg_ready(r));
   const size_t n = (size_t)r->src.n;
-  long long* d_stats = (long long*)c->get(sizeof(long long) * 4 * n);
+  Scratch tmp(c);
+  long long* d_stats = (long long*)tmp.get(sizeof(long long) * 4 * n);
   if (!d_stats) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (debug)");
   CK(c, cudaMemsetAsync(d_stats, 0, sizeof(long long) * 4 * n, c->stream));
   CK(c, cudaMemcpyToSymbolAsync(g_tile_dbg, &d_stats, sizeof(d_stats), 0, cudaMemcpyHostToDevice, c->stream));
@@ -1312,8 +1424,45 @@ int rgc_debug_correspond_stats(rgc_reg* r, const double* T16, long long* stats) 
   CK(c, cudaMemcpyToSymbolAsync(g_tile_dbg, &null_ptr, sizeof(null_ptr), 0, cudaMemcpyHostToDevice, c->stream));
   CK(c, cudaMemcpyAsync(stats, d_stats, sizeof(long long) * 4 * n, cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
-  c->put(d_stats);
   return rc;
+}
+
+int rgc_reg_set_target_covariance_mode(rgc_reg* r, int on_demand) {
+  if (!r) return RGC_ERR_INVALID;
+  r->lazy_target = on_demand != 0;
+  return RGC_OK;
+}
+int rgc_ctx_last_ondemand_ms(const rgc_ctx* c, float* ms) {
+  if (!c || !ms) return RGC_ERR_INVALID;
+  *ms = c->last_ondemand_ms;
+  return RGC_OK;
+}
+
+// test hook (not part of the documented ABI): the target covariances AS THEY ARE on the device, without
+// triggering any computation, in the caller's order; state[i] = 1 where covariance i has been computed
+int rgc_debug_get_target_cov_state(rgc_reg* r, double* m4x4, int32_t* state) {
+  if (!r || !m4x4 || !state) return RGC_ERR_INVALID;
+  rgc_ctx* c = r->ctx;
+  CK(c, cudaSetDevice(c->device));
+  TRY(join_side(c));
+  Cloud& t = r->tgt;
+  if (!t.valid) FAIL(c, RGC_ERR_STATE, "no target cloud");
+  const size_t n = (size_t)t.n;
+  Scratch tmp(c);
+  double* stage = (double*)tmp.get(128 * n);
+  int* d_state = (int*)tmp.get(4 * n);
+  if (!stage || !d_state) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (debug)");
+  CK(c, cudaMemsetAsync(stage, 0, 128 * n, c->stream));
+  if (t.cov) {
+    k_cov_export<<<div_up(t.n, 256), 256, 0, c->stream>>>(t.sorted, t.n, t.cov, stage);
+    CKL(c);
+  }
+  k_flags_to_orig<<<div_up(t.n, 256), 256, 0, c->stream>>>(t.sorted, t.n, (t.lazy_cov && !t.has_cov) ? t.cov_state : nullptr, t.has_cov ? 1 : 0, d_state);
+  CKL(c);
+  CK(c, cudaMemcpyAsync(m4x4, stage, 128 * n, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaMemcpyAsync(state, d_state, 4 * n, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  return RGC_OK;
 }
 
 int rgc_reg_last_inliers(const rgc_reg* r, int* n) {
@@ -1346,9 +1495,10 @@ int rgc_reg_get_voxels(rgc_reg* r, int32_t* coords3, int32_t* num_points, double
   TRY(vgicp_build(r));
   *n_voxels = (size_t)r->vox_count;
   if (!coords3 || cap == 0) return RGC_OK;
-  int *d_c = (int*)c->get(12 * cap), *d_n = (int*)c->get(4 * cap);
-  double *d_m = (double*)c->get(24 * cap), *d_v = (double*)c->get(48 * cap);
-  unsigned int* d_cnt = (unsigned int*)c->get(4);
+  Scratch tmp(c);
+  int *d_c = (int*)tmp.get(12 * cap), *d_n = (int*)tmp.get(4 * cap);
+  double *d_m = (double*)tmp.get(24 * cap), *d_v = (double*)tmp.get(48 * cap);
+  unsigned int* d_cnt = (unsigned int*)tmp.get(4);
   if (!d_c || !d_n || !d_m || !d_v || !d_cnt) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (voxel export)");
   CK(c, cudaMemsetAsync(d_cnt, 0, 4, c->stream));
   const uint32_t nslots = r->vox.mask + 1;
@@ -1360,11 +1510,6 @@ int rgc_reg_get_voxels(rgc_reg* r, int32_t* coords3, int32_t* num_points, double
   if (mean3) CK(c, cudaMemcpyAsync(mean3, d_m, 24 * m, cudaMemcpyDeviceToHost, c->stream));
   if (cov6) CK(c, cudaMemcpyAsync(cov6, d_v, 48 * m, cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
-  c->put(d_c);
-  c->put(d_n);
-  c->put(d_m);
-  c->put(d_v);
-  c->put(d_cnt);
   return RGC_OK;
 }
 
@@ -1390,10 +1535,11 @@ static int pre_to_host(rgc_ctx* c, const void* pts, size_t n, size_t stride, siz
   float4* d = nullptr;
   int m = 0;
   TRY(pre_filter(c, pts, n, stride, inten_off, leaf, q, t, period, &d, &m, passthrough));
+  Scratch tmp(c);
+  tmp.blocks.push_back(d);  // handed over by pre_filter
   *n_out = (size_t)m;
   if (out_xyzi && cap > 0) CK(c, cudaMemcpyAsync(out_xyzi, d, sizeof(float4) * std::min((size_t)m, cap), cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
-  c->put(d);
   return RGC_OK;
 }
 int rgc_voxel_grid(rgc_ctx* c, const void* pts, size_t n, size_t stride, size_t inten_off, float leaf, float* out_xyzi, size_t cap, size_t* n_out, int* passthrough) {
@@ -1423,6 +1569,7 @@ static int set_cloud_filtered(rgc_reg* r, Cloud& cl, const void* pts, size_t n, 
   c->put(d);  // same lane, stream-ordered reuse
   if (rc != RGC_OK) return rc;
   if (n_out) *n_out = (size_t)m;
+  if (&cl == &r->tgt && target_lazy(r)) return RGC_OK;
   return cloud_covariances(c, cl, r->prm.k_correspondences, r->prm.regularization, true);
 }
 int rgc_reg_set_source_filtered(rgc_reg* r, const void* pts, size_t n, size_t stride, size_t inten_off, float leaf, const double* q_wxyz, const double* t3,
@@ -1472,10 +1619,11 @@ static int map_associate(rgc_map* m, const void* feats, size_t n_sz, size_t stri
   if (stride < 12 || stride % 4) FAIL(c, RGC_ERR_INVALID, "point stride must be a multiple of 4 and >= 12 bytes");
   const int n = (int)n_sz;
   const size_t w2 = PLANE ? 1 : 3;
-  void* staging = c->get(n_sz * stride);
-  int* d_valid = (int*)c->get(4 * n_sz);
-  double* d_o1 = (double*)c->get(24 * n_sz);
-  double* d_o2 = (double*)c->get(8 * w2 * n_sz);
+  Scratch tmp(c);
+  void* staging = tmp.get(n_sz * stride);
+  int* d_valid = (int*)tmp.get(4 * n_sz);
+  double* d_o1 = (double*)tmp.get(24 * n_sz);
+  double* d_o2 = (double*)tmp.get(8 * w2 * n_sz);
   if (!staging || !d_valid || !d_o1 || !d_o2) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (association)");
   cudaStream_t st = c->stream;
   CK(c, cudaMemcpyAsync(staging, feats, n_sz * stride, cudaMemcpyHostToDevice, st));
@@ -1490,10 +1638,6 @@ static int map_associate(rgc_map* m, const void* feats, size_t n_sz, size_t stri
   CK(c, cudaMemcpyAsync(o1, d_o1, 24 * n_sz, cudaMemcpyDeviceToHost, st));
   CK(c, cudaMemcpyAsync(o2, d_o2, 8 * w2 * n_sz, cudaMemcpyDeviceToHost, st));
   CK(c, cudaStreamSynchronize(st));
-  c->put(staging);
-  c->put(d_valid);
-  c->put(d_o1);
-  c->put(d_o2);
   if (n_valid) {
     size_t k = 0;
     for (size_t i = 0; i < n_sz; i++) k += valid[i] != 0;

@@ -39,17 +39,10 @@ __host__ __device__ inline int query_spread(int n) { return n <= 12000 ? 8 : (n 
 // ------------------------------------------------------------------------------------------------
 // ingest: raw[n] with byte stride (xyz at offset 0, as every PCL point type) -> float4(x,y,z,1)
 // plus per-block min/max partials (reduced on the host: 296 x 6 floats).
-__global__ void __launch_bounds__(256) k_ingest(const unsigned char* __restrict__ raw, size_t stride, int n, float4* __restrict__ out,
-                                                float* __restrict__ bbox_partials) {
-  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const float* p = reinterpret_cast<const float*>(raw + (size_t)i * stride);
-    float x = p[0], y = p[1], z = p[2];
-    if (out) out[i] = make_float4(x, y, z, 1.0f);
-    mn[0] = fminf(mn[0], x); mx[0] = fmaxf(mx[0], x);
-    mn[1] = fminf(mn[1], y); mx[1] = fmaxf(mx[1], y);
-    mn[2] = fminf(mn[2], z); mx[2] = fmaxf(mx[2], z);
-  }
+// block reduction of per-thread bbox partials; a block that saw a non-finite coordinate writes NaN
+// partials (fminf / fmaxf drop NaN operands, so the flag travels separately) and the host rejects the
+// cloud: a NaN candidate would silently break the exactness of the k-NN heaps
+__device__ __forceinline__ void bbox_block_reduce(float mn[3], float mx[3], bool bad, float* __restrict__ bbox_partials) {
   __shared__ float sm[8][6];
 #pragma unroll
   for (int a = 0; a < 3; a++)
@@ -63,12 +56,28 @@ __global__ void __launch_bounds__(256) k_ingest(const unsigned char* __restrict_
       sm[warp][a] = mn[a];
       sm[warp][3 + a] = mx[a];
     }
-  __syncthreads();
+  const bool any_bad = __syncthreads_or(bad) != 0;
   if (threadIdx.x < 6) {
     float v = sm[0][threadIdx.x];
     for (int w = 1; w < (int)(blockDim.x >> 5); w++) v = threadIdx.x < 3 ? fminf(v, sm[w][threadIdx.x]) : fmaxf(v, sm[w][threadIdx.x]);
-    bbox_partials[blockIdx.x * 6 + threadIdx.x] = v;
+    bbox_partials[blockIdx.x * 6 + threadIdx.x] = any_bad ? NAN : v;
   }
+}
+
+__global__ void __launch_bounds__(256) k_ingest(const unsigned char* __restrict__ raw, size_t stride, int n, float4* __restrict__ out,
+                                                float* __restrict__ bbox_partials) {
+  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  bool bad = false;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float* p = reinterpret_cast<const float*>(raw + (size_t)i * stride);
+    float x = p[0], y = p[1], z = p[2];
+    if (out) out[i] = make_float4(x, y, z, 1.0f);
+    bad |= !(isfinite(x) && isfinite(y) && isfinite(z));
+    mn[0] = fminf(mn[0], x); mx[0] = fmaxf(mx[0], x);
+    mn[1] = fminf(mn[1], y); mx[1] = fmaxf(mx[1], y);
+    mn[2] = fminf(mn[2], z); mx[2] = fmaxf(mx[2], z);
+  }
+  bbox_block_reduce(mn, mx, bad, bbox_partials);
 }
 
 struct GridGeom {
@@ -624,15 +633,19 @@ __device__ __forceinline__ unsigned long long shfl64_up1(unsigned long long v) {
   return ((unsigned long long)__shfl_up_sync(0xffffffffu, (unsigned)(v >> 32), 1) << 32) | __shfl_up_sync(0xffffffffu, (unsigned)v, 1);
 }
 
+// Two ways of naming the queries: `defer_tiles` (tiles of 32 consecutive sorted positions handed over by
+// k_knn_tile; results k-major with stride n at the query's own position) or, with `qlist` set, an
+// explicit list of sorted positions (on-demand target covariances: the correspondences of one
+// linearize; results k-major with stride `out_stride` at the LIST index).
 __global__ void __launch_bounds__(KW_WARPS * 32) k_knn_warp(GridView g, int n, int k, const int* __restrict__ defer_count, const int* __restrict__ defer_tiles,
-                                                           int* __restrict__ out_idx) {
+                                                           const int* __restrict__ qlist, int out_stride, int* __restrict__ out_idx) {
   __shared__ TileNode stacks[KW_WARPS][KW_STACK];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   TileNode* stack = stacks[warp];
   const float4* pts4 = reinterpret_cast<const float4*>(g.pts);
-  const int nq = *defer_count * 32;
+  const int nq = qlist ? *defer_count : *defer_count * 32;
   for (int w = blockIdx.x * KW_WARPS + warp; w < nq; w += gridDim.x * KW_WARPS) {
-    const int t = defer_tiles[w >> 5] * 32 + (w & 31);
+    const int t = qlist ? qlist[w] : defer_tiles[w >> 5] * 32 + (w & 31);
     if (t >= n) continue;
     const float4 q = pts4[t];
     unsigned long long mine = ~0ull;  // lane j: j-th smallest key so far (~0 = empty)
@@ -795,7 +808,7 @@ __global__ void __launch_bounds__(KW_WARPS * 32) k_knn_warp(GridView g, int n, i
         }
       }
     }
-    if (lane < k) out_idx[(size_t)lane * n + t] = mine != ~0ull ? __ldg(&g.inv[(unsigned)(mine & 0xffffffffull)]) : -1;
+    if (lane < k) out_idx[qlist ? (size_t)lane * out_stride + w : (size_t)lane * n + t] = mine != ~0ull ? __ldg(&g.inv[(unsigned)(mine & 0xffffffffull)]) : -1;
     __syncwarp();
   }
 }
@@ -811,11 +824,14 @@ __global__ void __launch_bounds__(KW_WARPS * 32) k_knn_warp(GridView g, int n, i
 #define RGC_COV_BATCH 5
 #endif
 // FULL: k == KCAP and the cloud has at least k points, so every neighbour slot is valid (no predicates).
+// `qlist` / `qcount` (nullable): compute only the listed sorted positions (on-demand mode); thread e then
+// reads its neighbours at nbr[j * n + e] (n = the list's stride) and writes cov[qlist[e]].  Same code,
+// same neighbour order, hence bit-identical values to the whole-cloud launch.
 template <int KCAP, bool FULL>
 __global__ void __launch_bounds__(kThreads, RGC_COV_MINB) k_covariance(const float4* __restrict__ pts, const int* __restrict__ nbr, int n, int k, int method,
-                                                            double* __restrict__ cov) {
+                                                            double* __restrict__ cov, const int* __restrict__ qlist, const int* __restrict__ qcount) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n) return;
+  if (t >= (qlist ? *qcount : n)) return;
   // all k index loads first (coalesced, k-major), then the point gathers in batches of kBatch:
   // a float4 gather holds four registers while in flight, 20 at once cost 128 registers / thread
   // and a third of the occupancy
@@ -888,7 +904,7 @@ __global__ void __launch_bounds__(kThreads, RGC_COV_MINB) k_covariance(const flo
     c.zz = c.zz * ik - mz * mz;
   }
   const Sym3 r = regularize_cov(c, method);
-  double2* o = reinterpret_cast<double2*>(cov + (size_t)t * 6);
+  double2* o = reinterpret_cast<double2*>(cov + (size_t)(qlist ? qlist[t] : t) * 6);
   o[0] = make_double2(r.xx, r.xy);
   o[1] = make_double2(r.xz, r.yy);
   o[2] = make_double2(r.yz, r.zz);
@@ -911,8 +927,15 @@ __device__ __forceinline__ void store_sym3(double* __restrict__ base, size_t i, 
 // -> the last block to finish sums the partials in block order and writes `result` (which may be
 // mapped pinned host memory).  The order is fixed by the launch shape, so results are
 // bit-reproducible run to run (the reference's OpenMP sums are not).
+// `done`: optional sequence word in mapped pinned host memory, written after the results are visible
+// system-wide, so the host can poll it instead of paying a cudaStreamSynchronize per LM step.
+struct DoneFlag {
+  unsigned long long* flag;
+  unsigned long long value;
+};
 template <int NV>
-__device__ __forceinline__ void grid_reduce(double* v, double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ result) {
+__device__ __forceinline__ void grid_reduce(double* v, double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ result,
+                                            DoneFlag done = DoneFlag{nullptr, 0ull}, int* __restrict__ zero_me = nullptr) {
   __shared__ double sm[kThreads / 32][NV];
   __shared__ bool is_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -952,7 +975,13 @@ __device__ __forceinline__ void grid_reduce(double* v, double* __restrict__ part
       for (int w = 1; w < G; w++) tot += sm[w][threadIdx.x];
       result[threadIdx.x] = tot;
     }
-    if (threadIdx.x == 0) *ticket = 0;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      *ticket = 0;
+      if (zero_me) *zero_me = 0;
+      if (done.flag) *reinterpret_cast<volatile unsigned long long*>(done.flag) = done.value;
+    }
     __threadfence_system();
   }
 }
@@ -988,8 +1017,16 @@ constexpr int kLinN = kAccN + 1;  // + inlier count
 // excellent first candidate (the pose moves little between LM iterations), so the search starts
 // with the tightest possible ball and skips the climb.  Any real point is a valid bound: the
 // result is the same exact nearest neighbour.
-__global__ void __launch_bounds__(kThreads, 8) k_correspond(GridView tgt, const float4* __restrict__ src, int n_src, int spread, RtF Tf, float thr2, Slab slab,
-                                                            const int* hint, int* corr, float* __restrict__ sqd) {
+// `need_state` (nullable): on-demand target covariances.  A correspondence whose target point has no
+// covariance yet claims it (0 -> 1) and appends its sorted position to `need_list`; the kNN +
+// covariance kernels that follow compute exactly those (linearize reads C_B only at correspondences,
+// fast_gicp_impl.hpp:139-146, so the values it sees are the ones the eager pass would have produced).
+#ifndef RGC_CORR_MINB
+#define RGC_CORR_MINB 5
+#endif
+__global__ void __launch_bounds__(kThreads, RGC_CORR_MINB) k_correspond(GridView tgt, const float4* __restrict__ src, int n_src, int spread, RtF Tf, float thr2, Slab slab,
+                                                            const int* hint, int* corr, float* __restrict__ sqd, int* __restrict__ need_state,
+                                                            int* __restrict__ need_list, int* __restrict__ need_count) {
   const int gt = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = gt / spread;
   if ((gt & (spread - 1)) != 0 || i >= n_src) return;
@@ -1010,8 +1047,22 @@ __global__ void __launch_bounds__(kThreads, 8) k_correspond(GridView tgt, const 
   } else if (slab_owns(slab, qx, qy, qz)) {
     knn_search(tgt, qx, qy, qz, 1, thr2, hint ? hint[i] : -1, top);
   }
-  corr[i] = (top.id0 >= 0 && top.d0 < thr2) ? top.id0 : -1;
+  const int pos = (top.id0 >= 0 && top.d0 < thr2) ? top.id0 : -1;
+  corr[i] = pos;
   sqd[i] = top.d0;
+  if (need_state) {
+    const bool claim = pos >= 0 && need_state[pos] == 0 && atomicCAS(&need_state[pos], 0, 1) == 0;
+    // one atomicAdd per group of lanes that reach this point together
+    const unsigned act = __activemask();
+    const unsigned m = __ballot_sync(act, claim);
+    if (m) {
+      const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(need_count, __popc(m));
+      base = __shfl_sync(act, base, leader);
+      if (claim) need_list[base + __popc(m & ((1u << lane) - 1u))] = pos;
+    }
+  }
 }
 
 // Mahalanobis part of update_correspondences + linearize (fast_gicp_impl.hpp:139-211), fused:
@@ -1021,7 +1072,7 @@ __global__ void __launch_bounds__(kThreads, 8) k_correspond(GridView tgt, const 
 __global__ void __launch_bounds__(kThreads, 4) k_linearize(const float4* __restrict__ tgt_pts, const float4* __restrict__ src, const double* __restrict__ src_cov,
                                                            const double* __restrict__ tgt_cov, int n_src, Rt Td, int want_hb, const int* __restrict__ corr,
                                                            double* __restrict__ maha, double* __restrict__ partials, unsigned int* __restrict__ ticket,
-                                                           double* __restrict__ result) {
+                                                           double* __restrict__ result, DoneFlag done, int* __restrict__ zero_me) {
   double acc[kLinN];
 #pragma unroll
   for (int j = 0; j < kLinN; j++) acc[j] = 0.0;
@@ -1041,13 +1092,14 @@ __global__ void __launch_bounds__(kThreads, 4) k_linearize(const float4* __restr
       acc[kAccN] += 1.0;
     }
   }
-  grid_reduce<kLinN>(acc, partials, ticket, result);
+  grid_reduce<kLinN>(acc, partials, ticket, result, done, zero_me);
 }
 
 // fast_gicp_impl.hpp:214-237 — correspondences and M frozen from the last k_linearize
 __global__ void __launch_bounds__(kThreads) k_compute_error(const float4* __restrict__ tgt_pts, const float4* __restrict__ src, int n_src, Rt Td,
                                                             const int* __restrict__ corr, const double* __restrict__ maha,
-                                                            double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ result) {
+                                                            double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ result,
+                                                            DoneFlag done) {
   double acc[1] = {0.0};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_src; i += gridDim.x * blockDim.x) {
     const int pos = __ldg(&corr[i]);
@@ -1058,12 +1110,13 @@ __global__ void __launch_bounds__(kThreads) k_compute_error(const float4* __rest
       acc[0] += gicp_error_term(Td, M, p.x, p.y, p.z, q.x, q.y, q.z);
     }
   }
-  grid_reduce<1>(acc, partials, ticket, result);
+  grid_reduce<1>(acc, partials, ticket, result, done);
 }
 
 // pcl::Registration::getFitnessScore: [sum d2, count] over 1-NN d2 <= max_range
-__global__ void __launch_bounds__(kThreads, 8) k_fitness(GridView tgt, const float4* __restrict__ src, int n_src, int spread, RtF Tf, double max_range, Slab slab,
-                                                      double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ result) {
+__global__ void __launch_bounds__(kThreads, RGC_CORR_MINB) k_fitness(GridView tgt, const float4* __restrict__ src, int n_src, int spread, RtF Tf, double max_range, Slab slab,
+                                                      double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ result,
+                                                      DoneFlag done) {
   double acc[2] = {0.0, 0.0};
   const int gt = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = gt / spread;
@@ -1079,7 +1132,7 @@ __global__ void __launch_bounds__(kThreads, 8) k_fitness(GridView tgt, const flo
       acc[1] = 1.0;
     }
   }
-  grid_reduce<2>(acc, partials, ticket, result);
+  grid_reduce<2>(acc, partials, ticket, result, done);
 }
 
 __global__ void __launch_bounds__(256) k_transform_out(const float4* __restrict__ src_sorted, int n, RtF Tf, float4* __restrict__ out_orig_order) {
@@ -1131,6 +1184,13 @@ __global__ void __launch_bounds__(256) k_cov_export(const float4* __restrict__ s
   m[4] = c[1]; m[5] = c[3]; m[6] = c[4]; m[7] = 0.0;
   m[8] = c[2]; m[9] = c[4]; m[10] = c[5]; m[11] = 0.0;
   m[12] = 0.0; m[13] = 0.0; m[14] = 0.0; m[15] = 0.0;
+}
+
+// per-point int flags, sorted order -> the caller's order (test hook for the on-demand covariance state)
+__global__ void __launch_bounds__(256) k_flags_to_orig(const float4* __restrict__ sorted, int n, const int* __restrict__ flags, int fill, int* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[__float_as_int(sorted[i].w)] = flags ? flags[i] : fill;
 }
 
 }  // namespace rgc

@@ -56,6 +56,7 @@ RGC_HD void deskew_point(const DeskewParams& D, float inten, float& x, float& y,
 __global__ void __launch_bounds__(256) k_pre_ingest(const unsigned char* __restrict__ raw, size_t stride, size_t inten_off, int n, DeskewParams D,
                                                     float4* __restrict__ out, float* __restrict__ bbox_partials) {
   float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  bool bad = false;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const unsigned char* rec = raw + (size_t)i * stride;
     const float* p = reinterpret_cast<const float*>(rec);
@@ -63,29 +64,12 @@ __global__ void __launch_bounds__(256) k_pre_ingest(const unsigned char* __restr
     const float inten = inten_off == kNoIntensity ? 0.f : *reinterpret_cast<const float*>(rec + inten_off);
     if (D.enabled) deskew_point(D, inten, x, y, z);
     out[i] = make_float4(x, y, z, inten);
+    bad |= !(isfinite(x) && isfinite(y) && isfinite(z));
     mn[0] = fminf(mn[0], x); mx[0] = fmaxf(mx[0], x);
     mn[1] = fminf(mn[1], y); mx[1] = fmaxf(mx[1], y);
     mn[2] = fminf(mn[2], z); mx[2] = fmaxf(mx[2], z);
   }
-  __shared__ float sm[8][6];
-#pragma unroll
-  for (int a = 0; a < 3; a++)
-    for (int o = 16; o > 0; o >>= 1) {
-      mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
-      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
-    }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0)
-    for (int a = 0; a < 3; a++) {
-      sm[warp][a] = mn[a];
-      sm[warp][3 + a] = mx[a];
-    }
-  __syncthreads();
-  if (threadIdx.x < 6) {
-    float v = sm[0][threadIdx.x];
-    for (int w = 1; w < (int)(blockDim.x >> 5); w++) v = threadIdx.x < 3 ? fminf(v, sm[w][threadIdx.x]) : fmaxf(v, sm[w][threadIdx.x]);
-    bbox_partials[blockIdx.x * 6 + threadIdx.x] = v;
-  }
+  bbox_block_reduce(mn, mx, bad, bbox_partials);
 }
 
 #endif  // __CUDACC__

@@ -192,7 +192,7 @@ __device__ __forceinline__ void vgicp_terms(const Rt& T, const Sym3& M, float px
 __global__ void __launch_bounds__(kThreads, 4) k_vgicp_linearize(VoxelMapView vm, const float4* __restrict__ src, const double* __restrict__ src_cov, int n_src,
                                                                  int method, int n_off, Rt Td, int want_hb, int* __restrict__ corr_slot,
                                                                  double* __restrict__ maha, double* __restrict__ partials, unsigned int* __restrict__ ticket,
-                                                                 double* __restrict__ result) {
+                                                                 double* __restrict__ result, DoneFlag done) {
   double acc[kLinN];
 #pragma unroll
   for (int j = 0; j < kLinN; j++) acc[j] = 0.0;
@@ -217,13 +217,14 @@ __global__ void __launch_bounds__(kThreads, 4) k_vgicp_linearize(VoxelMapView vm
     vgicp_terms(Td, M, p.x, p.y, p.z, q, sqrt((double)vs->num), want_hb, acc);
     acc[kAccN] += 1.0;
   }
-  grid_reduce<kLinN>(acc, partials, ticket, result);
+  grid_reduce<kLinN>(acc, partials, ticket, result, done);
 }
 
 // fast_vgicp_impl.hpp:183-204: correspondences and Mahalanobis matrices frozen
 __global__ void __launch_bounds__(kThreads) k_vgicp_compute_error(VoxelMapView vm, const float4* __restrict__ src, int n_src, int n_off, Rt Td,
                                                                   const int* __restrict__ corr_slot, const double* __restrict__ maha,
-                                                                  double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ result) {
+                                                                  double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ result,
+                                                                  DoneFlag done) {
   double acc[1] = {0.0};
   const long long total = (long long)n_src * n_off;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(kThreads) k_vgicp_compute_error(VoxelMapView v
     const double q[3] = {vs->mean[0], vs->mean[1], vs->mean[2]};
     vgicp_terms(Td, M, p.x, p.y, p.z, q, sqrt((double)vs->num), 0, acc);
   }
-  grid_reduce<1>(acc, partials, ticket, result);
+  grid_reduce<1>(acc, partials, ticket, result, done);
 }
 
 // test hook: dump the occupied voxels (unordered)

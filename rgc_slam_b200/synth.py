@@ -26,6 +26,10 @@ def beam_elevations_deg(n_beams: int) -> np.ndarray:
         return -15.0 + 2.0 * np.arange(16)
     if n_beams == 32:  # scanID = int((v + 92/3) * 3/4), scanRegistration.cpp:156 -> bin centres
         return -92.0 / 3.0 + (np.arange(32) + 0.5) * 4.0 / 3.0
+    if n_beams == 64:  # HDL-64 split fan, scanRegistration.cpp:160-170: 1/3 deg steps down to -8.83 deg, then 1/2 deg steps
+        upper = 2.0 - np.arange(33) / 3.0                  # scanID = int((2 - v) * 3 + 0.5) = 0..32
+        lower = -8.83 - np.arange(1, 32) / 2.0             # scanID = 32 + int((-8.83 - v) * 2 + 0.5) = 33..63 (> 50 is dropped there)
+        return np.concatenate([upper, lower])
     # generic: uniform fan (used for the 128-beam GICP-only config C5)
     return np.linspace(-25.0, 25.0, n_beams)
 

@@ -76,5 +76,15 @@ int main(int argc, char** argv) {
                 aligned.size());
     for (int r = 0; r < 4; r++) std::printf("%.9g %.9g %.9g %.9g\n", T[r], T[4 + r], T[8 + r], T[12 + r]);
   }
+  {  // swapSourceAndTarget (fast_gicp_impl.hpp:49-57): the output cloud is the OLD target, fields included
+    rgc::FastGICP<PointT, PointT> gicp;
+    gicp.setMaxCorrespondenceDistance(2);
+    gicp.setInputTarget(target);
+    gicp.setInputSource(source);
+    gicp.swapSourceAndTarget();
+    gicp.align(aligned);
+    std::printf("swap converged %d aligned %zu expect %zu intensity_kept %d\n", (int)gicp.hasConverged(), aligned.size(), target->size(),
+                (int)(aligned.size() == target->size() && aligned[aligned.size() - 1].intensity == (float)(target->size() - 1)));
+  }
   return 0;
 }

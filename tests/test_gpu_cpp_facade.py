@@ -57,3 +57,6 @@ def test_cpp_facade_matches_oracle(small_pair, tmp_path):
     assert fhead[0] == "filtered" and int(fhead[6]) == ns and int(fhead[8]) == nt and int(fhead[10]) == ns
     assert int(fhead[4]) == g.last_result["iterations"]
     assert np.abs(Tf - Tg).max() < 1e-6
+    # fourth block: swapSourceAndTarget swaps the host-side cloud handles too
+    shead = out[15].split()
+    assert shead[0] == "swap" and int(shead[4]) == len(tgt) and int(shead[6]) == len(tgt) and int(shead[8]) == 1
