@@ -126,11 +126,21 @@ RGC_HD F4 load_pt(const F4* p) {
 #endif
 }
 
+// A grid may hold SEVERAL clouds (batched registration, rgc_batch.cuh): the clouds share the geometry,
+// cloud c's points are the sorted positions [lo, hi) and its cells carry the key prefix
+// c << 3 * nbits (at level l: prefix >> 3 l), so a search confined to one cloud never sees another
+// cloud's points.  A single-cloud grid is the range {0, n, 0}.
+struct CloudRange {
+  int lo, hi;
+  uint64_t prefix;
+};
+RGC_HD uint64_t prefix_at(const CloudRange& cr, int l) { return cr.prefix >> (3 * l); }
+
 // cell (cx,cy,cz) at level l -> [start,end) + child mask ; false if the cell is empty / out of range
-RGC_HD bool grid_lookup(const GridView& g, int l, int cx, int cy, int cz, uint32_t& start, uint32_t& end, uint32_t& cmask) {
+RGC_HD bool grid_lookup(const GridView& g, int l, int cx, int cy, int cz, uint32_t& start, uint32_t& end, uint32_t& cmask, uint64_t pfx = 0ull) {
   const int ncell = 1 << (g.nbits - l);
   if ((unsigned)cx >= (unsigned)ncell || (unsigned)cy >= (unsigned)ncell || (unsigned)cz >= (unsigned)ncell) return false;
-  const uint64_t key = morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
+  const uint64_t key = morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz) | pfx;
   const GridSlot* tab = g.table[l];
   const uint32_t mask = g.mask[l];
   uint32_t h = slot_of(key, g.shift[l]);
@@ -162,45 +172,6 @@ RGC_HD bool grid_lookup_key(const GridView& g, int l, uint64_t key, uint32_t& st
       return true;
     }
     h = (h + 1) & mask;
-  }
-}
-
-// Four cells of one level at once: the first slot of every probe sequence is loaded before any of
-// them is examined, so the four L2 round trips overlap (a search is a chain of ~20 dependent L2
-// accesses at ~1.3 k cycles each — tools/corr_stats.py — and nothing else; a collision falls back to
-// the sequential probe).  key[u] is ignored where want[u] is false.
-struct Probe4 {
-  bool ok[4];
-  uint32_t start[4], end[4], cmask[4];
-};
-RGC_HD void grid_lookup_key4(const GridView& g, int l, const uint64_t key[4], const bool want[4], Probe4& out) {
-  const GridSlot* tab = g.table[l];
-  const uint32_t mask = g.mask[l], shift = g.shift[l];
-  uint32_t h[4];
-  GridSlot sl[4];
-#pragma unroll
-  for (int u = 0; u < 4; u++) h[u] = slot_of(key[u], shift);
-#pragma unroll
-  for (int u = 0; u < 4; u++)
-    if (want[u]) sl[u] = load_slot(tab + h[u]);
-#pragma unroll
-  for (int u = 0; u < 4; u++) {
-    out.ok[u] = false;
-    if (!want[u]) continue;
-    GridSlot s = sl[u];
-    uint32_t hh = h[u];
-    for (;;) {
-      if (s.key == kEmptyKey) break;
-      if ((s.key & kKeyMask) == key[u]) {
-        out.ok[u] = true;
-        out.start[u] = s.start;
-        out.end[u] = s.end;
-        out.cmask[u] = (uint32_t)(s.key >> 56);
-        break;
-      }
-      hh = (hh + 1) & mask;
-      s = load_slot(tab + hh);
-    }
   }
 }
 
@@ -445,39 +416,14 @@ struct StackEntry {  // 24 bytes
   uint32_t pad;
 };
 
-#ifndef RGC_KNN_BATCH
-#define RGC_KNN_BATCH 1
-#endif
 template <class Top>
 RGC_HD void scan_range(const GridView& g, uint32_t s, uint32_t e, float qx, float qy, float qz, Top& top, SearchStats* st) {
-#if RGC_KNN_BATCH
-  // four candidates in flight per round (the insert is branchy, so the compiler does not overlap the loads itself)
-  uint32_t p = s;
-  for (; p + 4 <= e; p += 4) {
-    F4 c[4];
-#pragma unroll
-    for (int u = 0; u < 4; u++) c[u] = load_pt(g.pts + p + u);
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const float d2 = dist2_ref(qx, qy, qz, c[u].x, c[u].y, c[u].z);
-      top.insert(d2, (int)(p + u), f2i_bits(c[u].w), g.pts);
-    }
-    if (st) st->candidates += 4;
-  }
-  for (; p < e; p++) {
-    const F4 c = load_pt(g.pts + p);
-    const float d2 = dist2_ref(qx, qy, qz, c.x, c.y, c.z);
-    if (st) st->candidates++;
-    top.insert(d2, (int)p, f2i_bits(c.w), g.pts);
-  }
-#else
   for (uint32_t p = s; p < e; p++) {
     const F4 c = load_pt(g.pts + p);
     const float d2 = dist2_ref(qx, qy, qz, c.x, c.y, c.z);
     if (st) st->candidates++;
     top.insert(d2, (int)p, f2i_bits(c.w), g.pts);
   }
-#endif
 }
 
 // Exact kNN of (qx,qy,qz) in grid g into the heap `top` (call top.sort_ascending() for ordered output).
@@ -485,70 +431,28 @@ RGC_HD void scan_range(const GridView& g, uint32_t s, uint32_t e, float qx, floa
 // position known to be spatially close to q (the query's own position for self-kNN), or -1.
 template <class Top>
 RGC_HD void knn_search(const GridView& g, float qx, float qy, float qz, int k, float max_d2, int near_pos, Top& top,
-                       SearchStats* st = nullptr) {
+                       SearchStats* st = nullptr, const CloudRange* range = nullptr) {
   const int top_level = g.nlevels - 1;
+  const CloudRange cr = range ? *range : CloudRange{0, g.n, 0ull};
   // ---- 1. initial bound from k Morton-adjacent points
   float bound = max_d2;
-  if (g.n >= k) {
+  if (cr.hi - cr.lo >= k) {
     int p0;
     if (near_pos >= 0) {
       p0 = near_pos - (k >> 1);
     } else {
       const int fx = cell_coord(qx, g.ox, g.inv_s0), fy = cell_coord(qy, g.oy, g.inv_s0), fz = cell_coord(qz, g.oz, g.inv_s0);
-      p0 = 0;
-#if RGC_KNN_BATCH
-      // the smallest occupied cell around q: the probes of four consecutive levels are independent of
-      // each other, so they are issued together
-      bool found = false;
-      for (int l0 = 0; l0 <= top_level && !found; l0 += 4) {
-        uint64_t key[4];
-        uint32_t h[4];
-        bool want[4];
-        GridSlot sl[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const int l = l0 + u;
-          const int ncell_l = l <= top_level ? 1 << (g.nbits - l) : 0;
-          const int cx = fx >> (l & 31), cy = fy >> (l & 31), cz = fz >> (l & 31);
-          want[u] = l <= top_level && (unsigned)cx < (unsigned)ncell_l && (unsigned)cy < (unsigned)ncell_l && (unsigned)cz < (unsigned)ncell_l;
-          key[u] = want[u] ? morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz) : 0ull;
-          h[u] = want[u] ? slot_of(key[u], g.shift[l]) : 0u;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++)
-          if (want[u]) sl[u] = load_slot(g.table[l0 + u] + h[u]);
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-          if (found || !want[u]) continue;
-          if (st) st->lookups++;
-          const GridSlot* tab = g.table[l0 + u];
-          const uint32_t mask = g.mask[l0 + u];
-          GridSlot sc = sl[u];
-          uint32_t hh = h[u];
-          for (;;) {
-            if (sc.key == kEmptyKey) break;
-            if ((sc.key & kKeyMask) == key[u]) {
-              p0 = (int)sc.start - (k >> 1) + (int)((sc.end - sc.start) >> 1);
-              found = true;
-              break;
-            }
-            hh = (hh + 1) & mask;
-            sc = load_slot(tab + hh);
-          }
-        }
-      }
-#else
+      p0 = cr.lo;
       for (int l = 0; l <= top_level; l++) {
         uint32_t s, e, m;
         if (st) st->lookups++;
-        if (grid_lookup(g, l, fx >> l, fy >> l, fz >> l, s, e, m)) {
+        if (grid_lookup(g, l, fx >> l, fy >> l, fz >> l, s, e, m, prefix_at(cr, l))) {
           p0 = (int)s - (k >> 1) + (int)((e - s) >> 1);
           break;
         }
       }
-#endif
     }
-    p0 = p0 < 0 ? 0 : (p0 > g.n - k ? g.n - k : p0);
+    p0 = p0 < cr.lo ? cr.lo : (p0 > cr.hi - k ? cr.hi - k : p0);
     float far = 0.f;
     for (int j = 0; j < k; j++) {
       const F4 c = load_pt(g.pts + p0 + j);
@@ -583,82 +487,6 @@ RGC_HD void knn_search(const GridView& g, float qx, float qy, float qz, int k, f
   }
 
   StackEntry stack[kStackCap];
-#if RGC_KNN_BATCH
-  // the depth-first descent from one resolved root cell
-  auto descend = [&](int rx, int ry, int rz, uint32_t s0, uint32_t e0, uint32_t m0) {
-    int sp = 0;
-    stack[sp++] = StackEntry{(uint32_t)rx | ((uint32_t)lb << 24), (uint32_t)ry | (m0 << 24), (uint32_t)rz, s0, e0, 0u};
-    while (sp > 0) {
-      const StackEntry n = stack[--sp];
-      const int l = (int)(n.cx_lvl >> 24);
-      const int cx = (int)(n.cx_lvl & 0xffffffu), cy = (int)(n.cy_mask & 0xffffffu), cz = (int)n.cz;
-      const uint32_t cm = n.cy_mask >> 24;
-      const float cur = top.bound();
-      if (box_dist2(g, l, cx, cy, cz, qx, qy, qz) > cur) continue;
-      if (st) st->nodes++;
-      if (l == 0 || n.end - n.start <= (uint32_t)kLeafPoints || sp + 8 > kStackCap) {
-        scan_range(g, n.start, n.end, qx, qy, qz, top, st);
-        continue;
-      }
-      // children, nearest octant first (pushed in reverse so it is popped first); the hash probes of
-      // the surviving children are issued four at a time
-      const float half = g.s0 * (float)(1 << (l - 1));
-      const float mx = g.ox + (float)(2 * cx + 1) * half, my = g.oy + (float)(2 * cy + 1) * half, mz = g.oz + (float)(2 * cz + 1) * half;
-      const int first = (qx >= mx ? 1 : 0) | (qy >= my ? 2 : 0) | (qz >= mz ? 4 : 0);
-      const uint64_t pkey = morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz) << 3;
-#pragma unroll
-      for (int j0 = 7; j0 >= 0; j0 -= 4) {
-        uint64_t key[4];
-        bool want[4];
-        int ccx[4], ccy[4], ccz[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const int ci = first ^ (j0 - u);
-          ccx[u] = 2 * cx + (ci & 1);
-          ccy[u] = 2 * cy + ((ci >> 1) & 1);
-          ccz[u] = 2 * cz + ((ci >> 2) & 1);
-          key[u] = pkey | (uint64_t)ci;
-          want[u] = ((cm >> ci) & 1u) && !(box_dist2(g, l - 1, ccx[u], ccy[u], ccz[u], qx, qy, qz) > cur);
-        }
-        Probe4 pr;
-        grid_lookup_key4(g, l - 1, key, want, pr);
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-          if (st && want[u]) st->lookups++;
-          if (want[u] && pr.ok[u])
-            stack[sp++] = StackEntry{(uint32_t)ccx[u] | ((uint32_t)(l - 1) << 24), (uint32_t)ccy[u] | (pr.cmask[u] << 24), (uint32_t)ccz[u], pr.start[u], pr.end[u], 0u};
-        }
-      }
-    }
-  };
-  // root cells, four probes in flight at a time, visited in the same z / y / x order as before
-  const int nx = hi[0] - lo[0] + 1, ny = hi[1] - lo[1] + 1, nz = hi[2] - lo[2] + 1;
-  const int nroots = (nx > 0 && ny > 0 && nz > 0) ? nx * ny * nz : 0;
-  for (int r0 = 0; r0 < nroots; r0 += 4) {
-    uint64_t key[4];
-    bool want[4];
-    int rx[4], ry[4], rz[4];
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const int ri = r0 + u;
-      rx[u] = lo[0] + ri % nx;
-      ry[u] = lo[1] + (ri / nx) % ny;
-      rz[u] = lo[2] + ri / (nx * ny);
-      want[u] = ri < nroots && (unsigned)rx[u] < (unsigned)ncell && (unsigned)ry[u] < (unsigned)ncell && (unsigned)rz[u] < (unsigned)ncell &&
-                !(box_dist2(g, lb, rx[u], ry[u], rz[u], qx, qy, qz) > top.bound());
-      key[u] = want[u] ? morton3((uint32_t)rx[u], (uint32_t)ry[u], (uint32_t)rz[u]) : 0ull;
-    }
-    Probe4 pr;
-    grid_lookup_key4(g, lb, key, want, pr);
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      if (st && want[u]) st->lookups++;
-      if (!want[u] || !pr.ok[u]) continue;
-      if (box_dist2(g, lb, rx[u], ry[u], rz[u], qx, qy, qz) > top.bound()) continue;  // the bound may have tightened meanwhile
-      descend(rx[u], ry[u], rz[u], pr.start[u], pr.end[u], pr.cmask[u]);
-    }
-  }
-#else
   for (int rz = lo[2]; rz <= hi[2]; rz++)
     for (int ry = lo[1]; ry <= hi[1]; ry++)
       for (int rx = lo[0]; rx <= hi[0]; rx++) {
@@ -667,7 +495,7 @@ RGC_HD void knn_search(const GridView& g, float qx, float qy, float qz, int k, f
         }
         uint32_t s, e, m;
         if (st) st->lookups++;
-        if (!grid_lookup(g, lb, rx, ry, rz, s, e, m)) continue;
+        if (!grid_lookup(g, lb, rx, ry, rz, s, e, m, prefix_at(cr, lb))) continue;
         int sp = 0;
         stack[sp++] = StackEntry{(uint32_t)rx | ((uint32_t)lb << 24), (uint32_t)ry | (m << 24), (uint32_t)rz, s, e, 0u};
         // ---- 3. depth-first descent
@@ -687,7 +515,7 @@ RGC_HD void knn_search(const GridView& g, float qx, float qy, float qz, int k, f
           const float half = g.s0 * (float)(1 << (l - 1));
           const float mx = g.ox + (float)(2 * cx + 1) * half, my = g.oy + (float)(2 * cy + 1) * half, mz = g.oz + (float)(2 * cz + 1) * half;
           const int first = (qx >= mx ? 1 : 0) | (qy >= my ? 2 : 0) | (qz >= mz ? 4 : 0);
-          const uint64_t pkey = morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz) << 3;
+          const uint64_t pkey = (morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz) | prefix_at(cr, l)) << 3;
           for (int j = 7; j >= 0; j--) {
             const int ci = first ^ j;
             if (!((cm >> ci) & 1u)) continue;
@@ -700,7 +528,6 @@ RGC_HD void knn_search(const GridView& g, float qx, float qy, float qz, int k, f
           }
         }
       }
-#endif
 }
 
 }  // namespace rgc

@@ -1022,7 +1022,7 @@ constexpr int kLinN = kAccN + 1;  // + inlier count
 // covariance kernels that follow compute exactly those (linearize reads C_B only at correspondences,
 // fast_gicp_impl.hpp:139-146, so the values it sees are the ones the eager pass would have produced).
 #ifndef RGC_CORR_MINB
-#define RGC_CORR_MINB 5
+#define RGC_CORR_MINB 8
 #endif
 __global__ void __launch_bounds__(kThreads, RGC_CORR_MINB) k_correspond(GridView tgt, const float4* __restrict__ src, int n_src, int spread, RtF Tf, float thr2, Slab slab,
                                                             const int* hint, int* corr, float* __restrict__ sqd, int* __restrict__ need_state,
