@@ -419,10 +419,10 @@ static int launch_knn_self(rgc_ctx* c, const GridView& v, int n, int k, int* nbr
   int* dq = (int*)tmp.get(sizeof(int) * (size_t)(ntiles + 1));  // [0] = count, [1..] = tile ids
   if (!dq) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (knn defer list)");
   CK(c, cudaMemsetAsync(dq, 0, sizeof(int), c->stream));
-  k_knn_tile<<<div_up(n, KT_WARPS * 32), KT_WARPS * 32, smem, c->stream>>>(v, n, k, n_seeds, defer, dq, dq + 1, nbr);
+  k_knn_tile<<<div_up(n, KT_WARPS * 32), KT_WARPS * 32, smem, c->stream>>>(v, n, k, n_seeds, defer, dq, dq + 1, nbr, nullptr, 0);
   CKL(c);
   if (defer != INT_MAX) {
-    k_knn_warp<<<std::min(div_up(n, KW_WARPS), 148 * 4), KW_WARPS * 32, 0, c->stream>>>(v, n, k, dq, dq + 1, nullptr, 0, nbr);
+    k_knn_warp<<<std::min(div_up(n, KW_WARPS), 148 * 4), KW_WARPS * 32, 0, c->stream>>>(v, n, k, dq, dq + 1, nullptr, 0, nbr, nullptr, nullptr, 0);
     CKL(c);
   }
   return RGC_OK;
@@ -763,7 +763,7 @@ static int gicp_linearize_launch(rgc_reg* r, const double* T, int want, const in
     // (every source point a new target point) and read the real count from the device: nothing here
     // makes the host wait.  After the first linearize of an align the list is nearly empty.
     const int k = r->tgt.cov_k, method = r->tgt.cov_method, cap = r->cap_src, n_t = r->tgt.n;
-    k_knn_warp<<<std::min(div_up(r->src.n, KW_WARPS), 148 * 4), KW_WARPS * 32, 0, c->stream>>>(r->tgt.view, n_t, k, r->need_count, nullptr, r->need_list, cap, r->need_nbr);
+    k_knn_warp<<<std::min(div_up(r->src.n, KW_WARPS), 148 * 4), KW_WARPS * 32, 0, c->stream>>>(r->tgt.view, n_t, k, r->need_count, nullptr, r->need_list, cap, r->need_nbr, nullptr, nullptr, 0);
     CKL(c);
     const int grid = div_up(r->src.n, kThreads);
     if (k == 20 && n_t >= k)

@@ -375,6 +375,12 @@ constexpr int KT_LEAF = RGC_KT_LEAF;    // cells with <= this many points are ga
 struct TileNode {
   uint32_t cx_lvl, cy_mask, cz, start, end;
 };
+// one tile of a multi-cloud grid (batched registration): 32 consecutive sorted positions starting at
+// `first`, all inside cloud [lo, hi) whose cells carry `prefix` (rgc_grid.cuh: CloudRange)
+struct TileDesc {
+  int first, lo, hi, pad;
+  uint64_t prefix;
+};
 
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
@@ -388,7 +394,7 @@ __device__ __forceinline__ float warp_min(float v) {
 }
 
 __global__ void __launch_bounds__(KT_WARPS * 32) k_knn_tile(GridView g, int n, int k, int n_seeds, int defer_cands, int* __restrict__ defer_count, int* __restrict__ defer_tiles,
-                                                           int* __restrict__ out_idx) {
+                                                           int* __restrict__ out_idx, const TileDesc* __restrict__ tiles, int ntiles) {
   extern __shared__ __align__(16) unsigned char tile_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long dbg_t0 = clock64();
@@ -403,9 +409,20 @@ __global__ void __launch_bounds__(KT_WARPS * 32) k_knn_tile(GridView g, int n, i
   TileNode* stack = reinterpret_cast<TileNode*>(base + sizeof(float4) * KT_CAND);
   unsigned long long* hk = reinterpret_cast<unsigned long long*>(base + sizeof(float4) * KT_CAND + sizeof(TileNode) * KT_STACK);
 
-  const int first = (blockIdx.x * KT_WARPS + warp) * 32;
-  if (first >= n) return;
-  const int t = min(first + lane, n - 1);  // tail lanes shadow the last query (no output)
+  const int tile_id = blockIdx.x * KT_WARPS + warp;
+  int first = tile_id * 32, lo = 0, hi = n;
+  uint64_t prefix = 0ull;
+  if (tiles) {  // multi-cloud grid: the tile list says where each tile lives
+    if (tile_id >= ntiles) return;
+    const TileDesc td = tiles[tile_id];
+    first = td.first;
+    lo = td.lo;
+    hi = td.hi;
+    prefix = td.prefix;
+  } else if (first >= n) {
+    return;
+  }
+  const int t = min(first + lane, hi - 1);  // tail lanes shadow the last query (no output)
   const float4 q = reinterpret_cast<const float4*>(g.pts)[t];
   const float4* pts4 = reinterpret_cast<const float4*>(g.pts);
 
@@ -416,8 +433,8 @@ __global__ void __launch_bounds__(KT_WARPS * 32) k_knn_tile(GridView g, int n, i
   // ---- seeds: the Morton neighbours of the tile go through the same append / fold path as every
   // other candidate (the first k fill the heap, later ones are appended only if they beat the
   // current k-th best), which gives every lane a tight bound before any tree node is touched
-  const int ns = min(n_seeds, n);
-  const int s0 = max(0, min(first - (n_seeds - 32) / 2, n - ns));
+  const int ns = min(n_seeds, hi - lo);
+  const int s0 = max(lo, min(first - (n_seeds - 32) / 2, hi - ns));
   for (int j = lane; j < ns; j += 32) cand[j] = pts4[s0 + j];
   auto fold = [&]() {
     const int mx = __reduce_max_sync(0xffffffffu, npend);
@@ -458,7 +475,7 @@ __global__ void __launch_bounds__(KT_WARPS * 32) k_knn_tile(GridView g, int n, i
       const float diag2 = 3.f * edge * edge * 1.0001f;
       if (diag2 >= seed_b) break;  // cannot improve on the seed bound any more
       uint32_t s, e, m;
-      if (grid_lookup(g, l, fx >> l, fy >> l, fz >> l, s, e, m) && (int)(e - s) >= k) {
+      if (grid_lookup(g, l, fx >> l, fy >> l, fz >> l, s, e, m, prefix >> (3 * l)) && (int)(e - s) >= k) {
         cap2 = diag2;
         break;
       }
@@ -488,7 +505,7 @@ __global__ void __launch_bounds__(KT_WARPS * 32) k_knn_tile(GridView g, int n, i
     __syncwarp();
   };
 
-  if (n > ns) {
+  if (hi - lo > ns) {
     // ---- roots: cells covering the union of the balls, at a level where that is <= 4 cells per axis
     const float b0 = bound();
     const float r = b0 < INFINITY ? sqrtf(b0) * 1.00001f + 2.f * g.margin : INFINITY;
@@ -526,7 +543,7 @@ __global__ void __launch_bounds__(KT_WARPS * 32) k_knn_tile(GridView g, int n, i
         rx = rlo[0] + ri % nx;
         ry = rlo[1] + (ri / nx) % ny;
         rz = rlo[2] + ri / (nx * ny);
-        have = grid_lookup(g, lb, rx, ry, rz, s, e, m);
+        have = grid_lookup(g, lb, rx, ry, rz, s, e, m, prefix >> (3 * lb));
       }
       uint32_t hv = __ballot_sync(0xffffffffu, have);
       while (hv) {
@@ -548,9 +565,9 @@ __global__ void __launch_bounds__(KT_WARPS * 32) k_knn_tile(GridView g, int n, i
           // balls keeps growing); hand it to k_knn_warp, one warp per query, instead of becoming
           // the tail of this launch
           if (lane == 0) {
-            defer_tiles[atomicAdd(defer_count, 1)] = first / 32;
+            defer_tiles[atomicAdd(defer_count, 1)] = tile_id;
             if (g_tile_dbg) {
-              long long* o = g_tile_dbg + (size_t)(first / 32) * 4;
+              long long* o = g_tile_dbg + (size_t)tile_id * 4;
               o[0] = clock64() - dbg_t0;
               o[1] = dbg_nodes;
               o[2] = (long long)dbg_cands | (1ll << 40);
@@ -580,7 +597,7 @@ __global__ void __launch_bounds__(KT_WARPS * 32) k_knn_tile(GridView g, int n, i
           continue;
         }
         // expand: lane c < 8 resolves child c (mask bit -> hash lookup); the others wait
-        const uint64_t pkey = morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz) << 3;
+        const uint64_t pkey = (morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz) | (prefix >> (3 * l))) << 3;
         uint32_t cs = 0, ce = 0, cmk = 0;
         bool hc = false;
         if (lane < 8 && ((cm >> lane) & 1u)) hc = grid_lookup_key(g, l - 1, pkey | (uint64_t)lane, cs, ce, cmk);
@@ -599,12 +616,12 @@ __global__ void __launch_bounds__(KT_WARPS * 32) k_knn_tile(GridView g, int n, i
   }
   fold();
   heap.sort_ascending();
-  if (first + lane < n)
+  if (first + lane < hi)
     for (int j = 0; j < k; j++) out_idx[(size_t)j * n + t] = j < heap.cnt ? __ldg(&g.inv[(unsigned)(hk[j * 32 + lane] & 0xffffffffull)]) : -1;
   if (g_tile_dbg && lane == 0) {
-    long long* o = g_tile_dbg + (size_t)(first / 32) * 4;
+    long long* o = g_tile_dbg + (size_t)tile_id * 4;
     // level of the smallest cell holding the whole tile, and the launch-relative start time
-    const float4 pa = pts4[first], pb = pts4[min(first + 31, n - 1)];
+    const float4 pa = pts4[first], pb = pts4[min(first + 31, hi - 1)];
     const uint64_t ma = morton3(cell_coord(pa.x, g.ox, g.inv_s0), cell_coord(pa.y, g.oy, g.inv_s0), cell_coord(pa.z, g.oz, g.inv_s0));
     const uint64_t mb = morton3(cell_coord(pb.x, g.ox, g.inv_s0), cell_coord(pb.y, g.oy, g.inv_s0), cell_coord(pb.z, g.oz, g.inv_s0));
     const int lca = ma == mb ? 0 : (63 - __clzll((long long)(ma ^ mb))) / 3 + 1;
@@ -637,16 +654,41 @@ __device__ __forceinline__ unsigned long long shfl64_up1(unsigned long long v) {
 // k_knn_tile; results k-major with stride n at the query's own position) or, with `qlist` set, an
 // explicit list of sorted positions (on-demand target covariances: the correspondences of one
 // linearize; results k-major with stride `out_stride` at the LIST index).
+// Multi-cloud grids: `tiles` (deferred mode) or `cloud_off` (list mode: n_clouds + 1 sorted-position
+// offsets, the query's cloud is found by bisection) confine every search to the query's own cloud.
 __global__ void __launch_bounds__(KW_WARPS * 32) k_knn_warp(GridView g, int n, int k, const int* __restrict__ defer_count, const int* __restrict__ defer_tiles,
-                                                           const int* __restrict__ qlist, int out_stride, int* __restrict__ out_idx) {
+                                                           const int* __restrict__ qlist, int out_stride, int* __restrict__ out_idx,
+                                                           const TileDesc* __restrict__ tiles, const int* __restrict__ cloud_off, int n_clouds) {
   __shared__ TileNode stacks[KW_WARPS][KW_STACK];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   TileNode* stack = stacks[warp];
   const float4* pts4 = reinterpret_cast<const float4*>(g.pts);
   const int nq = qlist ? *defer_count : *defer_count * 32;
   for (int w = blockIdx.x * KW_WARPS + warp; w < nq; w += gridDim.x * KW_WARPS) {
-    const int t = qlist ? qlist[w] : defer_tiles[w >> 5] * 32 + (w & 31);
-    if (t >= n) continue;
+    int t, lo = 0, hi = n;
+    uint64_t prefix = 0ull;
+    if (qlist) {
+      t = qlist[w];
+      if (cloud_off) {
+        int a = 0, b = n_clouds;  // cloud_off[a] <= t < cloud_off[b]
+        while (b - a > 1) {
+          const int mid = (a + b) >> 1;
+          if (cloud_off[mid] <= t) a = mid; else b = mid;
+        }
+        lo = cloud_off[a];
+        hi = cloud_off[a + 1];
+        prefix = (uint64_t)a << (3 * g.nbits);
+      }
+    } else if (tiles) {
+      const TileDesc td = tiles[defer_tiles[w >> 5]];
+      t = td.first + (w & 31);
+      lo = td.lo;
+      hi = td.hi;
+      prefix = td.prefix;
+    } else {
+      t = defer_tiles[w >> 5] * 32 + (w & 31);
+    }
+    if (t >= hi) continue;
     const float4 q = pts4[t];
     unsigned long long mine = ~0ull;  // lane j: j-th smallest key so far (~0 = empty)
     unsigned long long capk = ~0ull;
@@ -671,8 +713,8 @@ __global__ void __launch_bounds__(KW_WARPS * 32) k_knn_warp(GridView g, int n, i
       return fminf(wk == ~0ull ? INFINITY : key_d2(wk), cap2);
     };
     // seeds: Morton neighbours of the query
-    const int ns = min(KW_SEEDS, n);
-    const int s0 = max(0, min(t - KW_SEEDS / 2, n - ns));
+    const int ns = min(KW_SEEDS, hi - lo);
+    const int s0 = max(lo, min(t - KW_SEEDS / 2, hi - ns));
     for (int j0 = 0; j0 < ns; j0 += 32) {
       const bool take = j0 + lane < ns;
       unsigned long long key = ~0ull;
@@ -682,14 +724,14 @@ __global__ void __launch_bounds__(KW_WARPS * 32) k_knn_warp(GridView g, int n, i
       }
       offer(key, take);
     }
-    if (n > ns) {
+    if (hi - lo > ns) {
       // geometric cap (see k_knn_tile): lane l probes the level-l cell of the query
       {
         const int fx = cell_coord(q.x, g.ox, g.inv_s0), fy = cell_coord(q.y, g.oy, g.inv_s0), fz = cell_coord(q.z, g.oz, g.inv_s0);
         bool enough = false;
         if (lane < g.nlevels) {
           uint32_t s, e, m;
-          enough = grid_lookup(g, lane, fx >> lane, fy >> lane, fz >> lane, s, e, m) && (int)(e - s) >= k;
+          enough = grid_lookup(g, lane, fx >> lane, fy >> lane, fz >> lane, s, e, m, prefix >> (3 * lane)) && (int)(e - s) >= k;
         }
         const unsigned hit = __ballot_sync(0xffffffffu, enough);
         if (hit) {
@@ -731,7 +773,7 @@ __global__ void __launch_bounds__(KW_WARPS * 32) k_knn_warp(GridView g, int n, i
           rx = rlo[0] + ri % nx;
           ry = rlo[1] + (ri / nx) % ny;
           rz = rlo[2] + ri / (nx * ny);
-          have = grid_lookup(g, lb, rx, ry, rz, s, e, m);
+          have = grid_lookup(g, lb, rx, ry, rz, s, e, m, prefix >> (3 * lb));
         }
         const float bnd = bound();
         have = have && box_dist2(g, lb, rx, ry, rz, q.x, q.y, q.z) <= bnd;
@@ -783,7 +825,7 @@ __global__ void __launch_bounds__(KW_WARPS * 32) k_knn_warp(GridView g, int n, i
             continue;
           }
           // expand: lane c < 8 resolves and tests child c; the survivors are pushed farthest first
-          const uint64_t pkey = morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz) << 3;
+          const uint64_t pkey = (morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz) | (prefix >> (3 * l))) << 3;
           uint32_t cs = 0, ce = 0, cmk = 0;
           bool hc = false;
           float dc = INFINITY;
