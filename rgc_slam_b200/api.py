@@ -112,6 +112,7 @@ EXPORTED_SYMBOLS = [
     "rgc_voxel_grid", "rgc_deskew", "rgc_reg_set_source_filtered", "rgc_reg_set_target_filtered",
     "rgc_map_create", "rgc_map_destroy", "rgc_map_associate_edges", "rgc_map_associate_planes",
     "rgc_reg_set_target_covariance_mode", "rgc_ctx_last_ondemand_ms",
+    "rgc_batch_align", "rgc_batch_last_stage_ms",
 ]
 
 

@@ -58,7 +58,9 @@ struct rgc_ctx {
   cudaEvent_t ev[8];
   cudaEvent_t evk[4];       // per-kernel timing of the last linearize / compute_error (profiling only)
   bool profile = false;     // rgc_ctx_set_profiling
-  int knn_defer = std::getenv("RGC_KNN_DEFER") ? std::atoi(std::getenv("RGC_KNN_DEFER")) : 600;  // rgc_debug_set_knn_defer
+  // candidate count at which a tile of the self-kNN is handed to the warp-per-query kernel; -1 = by cloud
+  // size (rgc_debug_set_knn_defer / RGC_KNN_DEFER override)
+  int knn_defer = std::getenv("RGC_KNN_DEFER") ? std::atoi(std::getenv("RGC_KNN_DEFER")) : -1;
   float last_kernel_ms[3] = {0, 0, 0};  // k_correspond, k_linearize, k_compute_error
   float last_ondemand_ms = 0;           // on-demand target kNN + covariances of the last linearize (profiling only)
 

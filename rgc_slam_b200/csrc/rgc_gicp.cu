@@ -25,6 +25,8 @@
 #include "rgc_mapping.cuh"
 #include "rgc_preprocess.cuh"
 #include "rgc_vgicp.cuh"
+#include "../../include/rgc_batch.h"
+#include "rgc_batch.cuh"
 
 using namespace rgc;
 
@@ -64,6 +66,13 @@ struct Cloud {
   int cov_k = 0, cov_method = 0;
   float build_ms = 0, knn_ms = 0, cov_ms = 0;
   float bb_min[3] = {0, 0, 0}, bb_max[3] = {0, 0, 0};
+  // multi-cloud grid (batched registration): n_clouds clouds concatenated; cloud c = sorted positions
+  // [h_off[c], h_off[c + 1]); d_off is the device copy, tiles the tile list of the self-kNN kernel
+  int n_clouds = 0;
+  std::vector<int> h_off;
+  int* d_off = nullptr;
+  TileDesc* d_tiles = nullptr;
+  int n_tiles = 0;
   // stage timing: build begin / end, kNN begin, kNN end (= covariance begin), covariance end.
   // Read back lazily (cloud_times) so that nothing here makes the host wait for the device.
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -111,6 +120,8 @@ static void cloud_release(rgc_ctx* c, Cloud& cl) {
   c->put(cl.tables);
   c->put(cl.cov);
   c->put(cl.cov_state);
+  c->put(cl.d_off);
+  c->put(cl.d_tiles);
   for (int i = 0; i < 5; i++) c->put_event(cl.ev[i]);
   cl = Cloud();
 }
@@ -148,7 +159,10 @@ static int radix_sort_pairs(rgc_ctx* c, uint64_t* keys_a, uint64_t* keys_b, uint
 }
 
 // upload (or adopt a device pointer), Morton-sort, build the level tables
-static int cloud_build(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, size_t stride, bool on_device, uint64_t key, float cell) {
+// `offsets` (nullable, n_clouds + 1 entries): the input is the concatenation of n_clouds clouds that
+// become one multi-cloud grid (rgc_grid.cuh: CloudRange)
+static int cloud_build(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, size_t stride, bool on_device, uint64_t key, float cell,
+                       const int* offsets = nullptr, int n_clouds = 0) {
   cloud_release(c, cl);
   if (n_sz == 0 || points == nullptr) FAIL(c, RGC_ERR_INVALID, "empty point cloud");
   if (n_sz > 0x7fffffff / 32) FAIL(c, RGC_ERR_UNSUPPORTED, "point cloud too large for 32-bit indexing");
@@ -205,16 +219,25 @@ static int cloud_build(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, s
   // ---- grid geometry ----
   GridView& v = cl.view;
   v.n = n;
-  grid_geometry(mn, mx, cell, v);
+  int cloud_bits = 0;
+  if (offsets) {
+    while ((1 << cloud_bits) < n_clouds) cloud_bits++;
+    cl.n_clouds = n_clouds;
+    cl.h_off.assign(offsets, offsets + n_clouds + 1);
+    cl.d_off = (int*)c->get(sizeof(int) * (size_t)(n_clouds + 1));
+    if (!cl.d_off) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (cloud offsets)");
+    CK(c, cudaMemcpyAsync(cl.d_off, offsets, sizeof(int) * (size_t)(n_clouds + 1), cudaMemcpyHostToDevice, st));
+  }
+  grid_geometry(mn, mx, cell, v, std::min(kMaxBits, (56 - cloud_bits) / 3));  // key = cloud id | 3 * nbits Morton bits <= 56 bits
   const int nbits = v.nbits;
   GridGeom geom{v.ox, v.oy, v.oz, v.inv_s0, nbits};
 
   // ---- Morton keys + LSD radix sort ----
-  k_morton<<<div_up(n, 256), 256, 0, st>>>(orig, n, geom, keys_a, vals_a);
+  k_morton<<<div_up(n, 256), 256, 0, st>>>(orig, n, geom, keys_a, vals_a, cl.d_off, n_clouds);
   CKL(c);
   uint64_t* kin = keys_a;
   uint32_t* vin = vals_a;
-  TRY(radix_sort_pairs(c, keys_a, keys_b, vals_a, vals_b, hist, n, 3 * nbits, &kin, &vin));
+  TRY(radix_sort_pairs(c, keys_a, keys_b, vals_a, vals_b, hist, n, 3 * nbits + cloud_bits, &kin, &vin));
   k_gather_sorted<<<div_up(n, 256), 256, 0, st>>>(orig, vin, n, cl.sorted, cl.inv);
   CKL(c);
 
@@ -399,32 +422,56 @@ static int launch_knn(rgc_ctx* c, const GridView& v, const float4* queries, int 
 
 // self-kNN of a whole cloud: the warp-cooperative tile kernel (RGC_KNN_THREAD=1 selects the
 // thread-per-query kernel instead, for A/B profiling)
-static int launch_knn_self(rgc_ctx* c, const GridView& v, int n, int k, int* nbr) {
-  // the warp-cooperative tile kernel; RGC_KNN_THREAD=1 selects the thread-per-query kernel (A/B)
+static int launch_knn_self(rgc_ctx* c, const GridView& v, int n, int k, int* nbr, const TileDesc* tiles = nullptr, int n_tiles = 0, int n_clouds = 1) {
+  // the warp-cooperative tile kernel; RGC_KNN_THREAD=1 selects the thread-per-query kernel (A/B, single clouds only)
   static const bool per_thread = std::getenv("RGC_KNN_THREAD") != nullptr;
-  if (per_thread) return launch_knn<true>(c, v, nullptr, n, k, nbr, nullptr);
+  if (per_thread && !tiles) return launch_knn<true>(c, v, nullptr, n, k, nbr, nullptr);
   if (k > 32) FAIL(c, RGC_ERR_UNSUPPORTED, "k_correspondences > 32 is not supported");
   const size_t per_warp = sizeof(float4) * KT_CAND + sizeof(TileNode) * KT_STACK + (size_t)(k + KT_PEND) * 32 * 8;
   const size_t smem = per_warp * KT_WARPS;
   CK(c, cudaFuncSetAttribute(k_knn_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int n_cloud = n / std::max(n_clouds, 1);  // typical size of ONE cloud (a multi-cloud grid holds many)
   // more seeds pay off on a single sweep (sparse rings: tighter start bounds), fewer on dense maps (sweep in profiles/README.md)
-  const int n_seeds = n < 100000 ? KT_SEEDS : (KT_SEEDS > 64 ? 64 : KT_SEEDS);
+  const int n_seeds = n_cloud < 100000 ? KT_SEEDS : (KT_SEEDS > 64 ? 64 : KT_SEEDS);
   // tiles that gather more than `defer` candidates are finished by k_knn_warp (one warp per query):
   // they are the sparse-region tiles that used to form a 40 % tail of this launch (profiles/README.md)
   // (the tail is one slow tile long, ~0.3 ms, whatever n is, while deferring costs ~8 % extra work:
   // it pays below a few million points; measured 13.1 vs 14.4 ms at 8 M points, 1.33 vs 0.98 ms at 500 k)
-  const int defer = (c->knn_defer > 0 && n < 2000000) ? c->knn_defer : INT_MAX;
-  const int ntiles = div_up(n, 32);
+  // single sweeps (sparse rings, < 1 wave of tiles): an early hand-over shortens the launch, 0.23 -> 0.14 ms
+  // on a 22k-point sweep; dense maps keep their tiles longer (600: 2.7 vs 1.7 ms on the 500k submap at 150)
+  const int auto_defer = n_cloud < 100000 ? 150 : 600;
+  const int want_defer = c->knn_defer < 0 ? auto_defer : c->knn_defer;
+  const int defer = (want_defer > 0 && n_cloud < 2000000) ? want_defer : INT_MAX;
+  const int ntiles = tiles ? n_tiles : div_up(n, 32);
   Scratch tmp(c);
   int* dq = (int*)tmp.get(sizeof(int) * (size_t)(ntiles + 1));  // [0] = count, [1..] = tile ids
   if (!dq) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (knn defer list)");
   CK(c, cudaMemsetAsync(dq, 0, sizeof(int), c->stream));
-  k_knn_tile<<<div_up(n, KT_WARPS * 32), KT_WARPS * 32, smem, c->stream>>>(v, n, k, n_seeds, defer, dq, dq + 1, nbr, nullptr, 0);
+  k_knn_tile<<<div_up(ntiles, KT_WARPS), KT_WARPS * 32, smem, c->stream>>>(v, n, k, n_seeds, defer, dq, dq + 1, nbr, tiles, ntiles);
   CKL(c);
   if (defer != INT_MAX) {
-    k_knn_warp<<<std::min(div_up(n, KW_WARPS), 148 * 4), KW_WARPS * 32, 0, c->stream>>>(v, n, k, dq, dq + 1, nullptr, 0, nbr, nullptr, nullptr, 0);
+    k_knn_warp<<<std::min(div_up(n, KW_WARPS), 148 * 4), KW_WARPS * 32, 0, c->stream>>>(v, n, k, dq, dq + 1, nullptr, 0, nbr, tiles, nullptr, 0);
     CKL(c);
   }
+  return RGC_OK;
+}
+
+// tile list of a multi-cloud grid for the self-kNN: tiles of 32 consecutive sorted positions, none straddling two clouds
+static int cloud_tiles(rgc_ctx* c, Cloud& cl) {
+  if (cl.n_clouds <= 0) return RGC_OK;
+  std::vector<TileDesc> t;
+  t.reserve((size_t)cl.n / 32 + (size_t)cl.n_clouds);
+  for (int q = 0; q < cl.n_clouds; q++) {
+    const int lo = cl.h_off[q], hi = cl.h_off[q + 1];
+    const uint64_t prefix = (uint64_t)q << (3 * cl.view.nbits);
+    for (int first = lo; first < hi; first += 32) t.push_back(TileDesc{first, lo, hi, 0, prefix});
+  }
+  c->put(cl.d_tiles);
+  cl.n_tiles = (int)t.size();
+  cl.d_tiles = (TileDesc*)c->get(sizeof(TileDesc) * t.size());
+  if (!cl.d_tiles) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (tile list)");
+  // pageable source: the copy is staged before the call returns, so the vector may go out of scope
+  CK(c, cudaMemcpyAsync(cl.d_tiles, t.data(), sizeof(TileDesc) * t.size(), cudaMemcpyHostToDevice, c->stream));
   return RGC_OK;
 }
 
@@ -444,9 +491,11 @@ static int cloud_covariances(rgc_ctx* c, Cloud& cl, int k, int method, bool spec
   if (!cl.cov) cl.cov = (double*)c->get(sizeof(double) * 6 * (size_t)cl.n);
   if (!nbr || !cl.cov) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (covariances)");
   CK(c, cudaEventRecord(cl.ev[2], st));
-  TRY(launch_knn_self(c, cl.view, cl.n, k, nbr));
+  TRY(launch_knn_self(c, cl.view, cl.n, k, nbr, cl.d_tiles, cl.n_tiles, std::max(cl.n_clouds, 1)));
   CK(c, cudaEventRecord(cl.ev[3], st));
-  if (k == 20 && cl.n >= k)  // the default k_correspondences, every slot filled
+  int min_cloud = cl.n;  // smallest cloud of a multi-cloud grid: every neighbour slot is filled iff it has >= k points
+  for (int q = 0; q < cl.n_clouds; q++) min_cloud = std::min(min_cloud, cl.h_off[q + 1] - cl.h_off[q]);
+  if (k == 20 && min_cloud >= k)  // the default k_correspondences, every slot filled
     k_covariance<20, true><<<div_up(cl.n, kThreads), kThreads, 0, st>>>(cl.sorted, nbr, cl.n, k, method, cl.cov, nullptr, nullptr);
   else if (k <= 20)
     k_covariance<20, false><<<div_up(cl.n, kThreads), kThreads, 0, st>>>(cl.sorted, nbr, cl.n, k, method, cl.cov, nullptr, nullptr);
@@ -1670,3 +1719,5 @@ int rgc_reg_stage_ms(const rgc_reg* r, float* ms7) {
 }
 
 }  // extern "C"
+
+#include "rgc_batch.inl"

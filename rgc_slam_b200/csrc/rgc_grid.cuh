@@ -58,7 +58,7 @@ struct GridView {
 
 // Grid geometry from a bounding box (host side; shared by the library and tests/hostsim so both
 // place every point in the same cell).  Sets origin, cell size, nbits/nlevels and the margin.
-inline void grid_geometry(const float mn[3], const float mx[3], float cell, GridView& v) {
+inline void grid_geometry(const float mn[3], const float mx[3], float cell, GridView& v, int max_bits = kMaxBits) {
   float s0 = cell > 0.f ? cell : 0.05f;
   float extent = 0.f, maxabs = 0.f;
   for (int a = 0; a < 3; a++) {
@@ -66,9 +66,9 @@ inline void grid_geometry(const float mn[3], const float mx[3], float cell, Grid
     maxabs = fmaxf(maxabs, fmaxf(fabsf(mn[a]), fabsf(mx[a])));
   }
   extent += 2.f * s0;
-  if (extent / s0 > (float)(1 << kMaxBits)) s0 = extent / (float)(1 << kMaxBits) * 1.001f;
+  if (extent / s0 > (float)(1 << max_bits)) s0 = extent / (float)(1 << max_bits) * 1.001f;
   int nbits = 1;
-  while ((float)(1 << nbits) * s0 < extent && nbits < kMaxBits) nbits++;
+  while ((float)(1 << nbits) * s0 < extent && nbits < max_bits) nbits++;
   v.ox = mn[0] - s0;
   v.oy = mn[1] - s0;
   v.oz = mn[2] - s0;

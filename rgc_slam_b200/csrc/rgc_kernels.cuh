@@ -85,7 +85,10 @@ struct GridGeom {
   int nbits;
 };
 
-__global__ void __launch_bounds__(256) k_morton(const float4* __restrict__ pts, int n, GridGeom g, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+// `cloud_off` (nullable, n_clouds + 1 offsets into pts): a multi-cloud grid — point i of cloud c gets
+// the key prefix c << 3 * nbits, so the sort groups the clouds and every cell belongs to one cloud
+__global__ void __launch_bounds__(256) k_morton(const float4* __restrict__ pts, int n, GridGeom g, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                                const int* __restrict__ cloud_off, int n_clouds) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float4 p = pts[i];
@@ -93,7 +96,16 @@ __global__ void __launch_bounds__(256) k_morton(const float4* __restrict__ pts, 
   int cx = min(max(cell_coord(p.x, g.ox, g.inv_s0), 0), hi);
   int cy = min(max(cell_coord(p.y, g.oy, g.inv_s0), 0), hi);
   int cz = min(max(cell_coord(p.z, g.oz, g.inv_s0), 0), hi);
-  keys[i] = morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
+  uint64_t key = morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
+  if (cloud_off) {
+    int a = 0, b = n_clouds;  // cloud_off[a] <= i < cloud_off[b]
+    while (b - a > 1) {
+      const int mid = (a + b) >> 1;
+      if (cloud_off[mid] <= i) a = mid; else b = mid;
+    }
+    key |= (uint64_t)a << (3 * g.nbits);
+  }
+  keys[i] = key;
   vals[i] = (uint32_t)i;
 }
 
@@ -975,9 +987,12 @@ struct DoneFlag {
   unsigned long long* flag;
   unsigned long long value;
 };
+// `block_id` / `n_blocks`: the position of this block in the (possibly virtual) grid whose partials are
+// summed together — the whole launch for the single-registration kernels, one pair's slice of the launch
+// for the batched ones (rgc_batch.cuh), which therefore add in exactly the same order.
 template <int NV>
-__device__ __forceinline__ void grid_reduce(double* v, double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ result,
-                                            DoneFlag done = DoneFlag{nullptr, 0ull}, int* __restrict__ zero_me = nullptr) {
+__device__ __forceinline__ void grid_reduce_at(double* v, double* __restrict__ partials, unsigned block_id, unsigned n_blocks, unsigned int* __restrict__ ticket,
+                                               double* __restrict__ result, DoneFlag done = DoneFlag{nullptr, 0ull}, int* __restrict__ zero_me = nullptr) {
   __shared__ double sm[kThreads / 32][NV];
   __shared__ bool is_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -993,11 +1008,11 @@ __device__ __forceinline__ void grid_reduce(double* v, double* __restrict__ part
     double s = sm[0][threadIdx.x];
 #pragma unroll
     for (int w = 1; w < kThreads / 32; w++) s += sm[w][threadIdx.x];
-    partials[(size_t)blockIdx.x * NV + threadIdx.x] = s;
+    partials[(size_t)block_id * NV + threadIdx.x] = s;
   }
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == n_blocks - 1);
   __syncthreads();
   if (is_last) {
     __threadfence();
@@ -1008,7 +1023,7 @@ __device__ __forceinline__ void grid_reduce(double* v, double* __restrict__ part
     const int j = threadIdx.x & 31, grp = threadIdx.x >> 5;
     double s = 0.0;
     if (j < NV)
-      for (unsigned b = grp; b < gridDim.x; b += G) s += __ldcg(&partials[(size_t)b * NV + j]);
+      for (unsigned b = grp; b < n_blocks; b += G) s += __ldcg(&partials[(size_t)b * NV + j]);
     if (j < NV) sm[grp][j] = s;
     __syncthreads();
     if (threadIdx.x < NV) {
@@ -1026,6 +1041,12 @@ __device__ __forceinline__ void grid_reduce(double* v, double* __restrict__ part
     }
     __threadfence_system();
   }
+}
+
+template <int NV>
+__device__ __forceinline__ void grid_reduce(double* v, double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ result,
+                                            DoneFlag done = DoneFlag{nullptr, 0ull}, int* __restrict__ zero_me = nullptr) {
+  grid_reduce_at<NV>(v, partials, blockIdx.x, gridDim.x, ticket, result, done, zero_me);
 }
 
 // grid size of the reduction kernels: enough blocks to fill the machine, few enough that the

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _declared():
     out = []
-    for h in ("rgc_gicp.h", "rgc_features.h", "rgc_preprocess.h", "rgc_mapping.h"):
+    for h in ("rgc_gicp.h", "rgc_features.h", "rgc_preprocess.h", "rgc_mapping.h", "rgc_batch.h"):
         p = os.path.join(ROOT, "include", h)
         if os.path.exists(p):
             text = re.sub(r"/\*.*?\*/", "", open(p).read(), flags=re.S)

@@ -15,7 +15,8 @@ def _compare(g, o, tag):
     assert np.array_equal(g["scan_start"], o["scan_start"]) and np.array_equal(g["scan_end"], o["scan_end"]), tag
     assert np.array_equal(g["cloud"][:, :3], o["cloud"][:, :3]), tag
     # intensity = scanID + 0.1 * relTime: atan2 comes from libm on the CPU and from CUDA on the GPU
-    assert np.abs(g["cloud"][:, 3] - o["cloud"][:, 3]).max() < 2e-6, tag
+    # (at most one float ulp: 1.9e-6 on rings 16-31, 3.8e-6 on rings 32-63)
+    assert (np.abs(g["cloud"][:, 3] - o["cloud"][:, 3]) <= np.spacing(np.maximum(np.abs(o["cloud"][:, 3]), np.float32(1.0)))).all(), tag
     assert np.array_equal(np.floor(g["cloud"][:, 3]), np.floor(o["cloud"][:, 3])), tag
     for k in EXACT:
         assert np.array_equal(g[k], o[k]), f"{tag}: {k} differs ({(np.asarray(g[k]) != np.asarray(o[k])).sum()} entries)"

@@ -53,7 +53,7 @@ def knn_defer(rgc):
     def set_(v):
         ctx.check(L.rgc_debug_set_knn_defer(ctx._h, v))
     yield set_
-    set_(600)
+    set_(-1)  # back to the size-dependent default
 
 
 @pytest.mark.parametrize("defer", [600, 1, 40, 0])
