@@ -69,6 +69,18 @@ RGC_HD double dsub(double a, double b) {
 #endif
 }
 
+// fused multiply-add, always: the fp64 algebra of linearize / compute_error is written with explicit
+// dfma / dmul / dadd so that every kernel that inlines it (single registration, batched, voxelised)
+// performs the SAME roundings — left to the compiler, the choice of which product of a sum gets fused
+// varies with the inlining context and two kernels disagree in the last bit.
+RGC_HD double dfma(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+  return __fma_rn(a, b, c);
+#else
+  return std::fma(a, b, c);
+#endif
+}
+
 RGC_HD int f2i_bits(float f) {
 #if defined(__CUDA_ARCH__)
   return __float_as_int(f);

@@ -87,19 +87,24 @@ RGC_HD void eig_sym3(const Sym3& A, double w[3], double V[3][3]) {
   w[2] = a[2][2];
 }
 
+// a * b - c * d with pinned roundings: fma(a, b, -(c * d))
+RGC_HD double dprod_diff(double a, double b, double c, double d) { return dfma(a, b, -dmul(c, d)); }
+// a0 * b0 + a1 * b1 + a2 * b2 with pinned roundings: fma(a2, b2, fma(a1, b1, a0 * b0))
+RGC_HD double ddot3(double a0, double b0, double a1, double b1, double a2, double b2) { return dfma(a2, b2, dfma(a1, b1, dmul(a0, b0))); }
+
 RGC_HD Sym3 inv_sym3(const Sym3& m) {
-  double c00 = m.yy * m.zz - m.yz * m.yz;
-  double c01 = m.xz * m.yz - m.xy * m.zz;
-  double c02 = m.xy * m.yz - m.xz * m.yy;
-  double det = m.xx * c00 + m.xy * c01 + m.xz * c02;
-  double id = 1.0 / det;
+  const double c00 = dprod_diff(m.yy, m.zz, m.yz, m.yz);
+  const double c01 = dprod_diff(m.xz, m.yz, m.xy, m.zz);
+  const double c02 = dprod_diff(m.xy, m.yz, m.xz, m.yy);
+  const double det = ddot3(m.xx, c00, m.xy, c01, m.xz, c02);
+  const double id = 1.0 / det;
   Sym3 r;
-  r.xx = c00 * id;
-  r.xy = c01 * id;
-  r.xz = c02 * id;
-  r.yy = (m.xx * m.zz - m.xz * m.xz) * id;
-  r.yz = (m.xy * m.xz - m.xx * m.yz) * id;
-  r.zz = (m.xx * m.yy - m.xy * m.xy) * id;
+  r.xx = dmul(c00, id);
+  r.xy = dmul(c01, id);
+  r.xz = dmul(c02, id);
+  r.yy = dmul(dprod_diff(m.xx, m.zz, m.xz, m.xz), id);
+  r.yz = dmul(dprod_diff(m.xy, m.xz, m.xx, m.yz), id);
+  r.zz = dmul(dprod_diff(m.xx, m.yy, m.xy, m.xy), id);
   return r;
 }
 
@@ -258,9 +263,9 @@ struct Rt {
 };
 
 RGC_HD void transform_d(const Rt& T, double x, double y, double z, double& ox, double& oy, double& oz) {
-  ox = ((T.m[0] * x + T.m[1] * y) + T.m[2] * z) + T.m[3];
-  oy = ((T.m[4] * x + T.m[5] * y) + T.m[6] * z) + T.m[7];
-  oz = ((T.m[8] * x + T.m[9] * y) + T.m[10] * z) + T.m[11];
+  ox = dadd(ddot3(T.m[0], x, T.m[1], y, T.m[2], z), T.m[3]);
+  oy = dadd(ddot3(T.m[4], x, T.m[5], y, T.m[6], z), T.m[7]);
+  oz = dadd(ddot3(T.m[8], x, T.m[9], y, T.m[10], z), T.m[11]);
 }
 
 // M = (C_B + R C_A R^T)^-1 (the 4x4 of the reference is block diagonal with a pinned 1, so its
@@ -272,14 +277,14 @@ RGC_HD Sym3 gicp_mahalanobis(const Rt& T, const Sym3& CA, const Sym3& CB) {
 #pragma unroll
   for (int i = 0; i < 3; i++)
 #pragma unroll
-    for (int j = 0; j < 3; j++) RC[i][j] = R[i * 4 + 0] * A[0][j] + R[i * 4 + 1] * A[1][j] + R[i * 4 + 2] * A[2][j];
+    for (int j = 0; j < 3; j++) RC[i][j] = ddot3(R[i * 4 + 0], A[0][j], R[i * 4 + 1], A[1][j], R[i * 4 + 2], A[2][j]);
   Sym3 S;
-  S.xx = CB.xx + (RC[0][0] * R[0] + RC[0][1] * R[1] + RC[0][2] * R[2]);
-  S.xy = CB.xy + (RC[0][0] * R[4] + RC[0][1] * R[5] + RC[0][2] * R[6]);
-  S.xz = CB.xz + (RC[0][0] * R[8] + RC[0][1] * R[9] + RC[0][2] * R[10]);
-  S.yy = CB.yy + (RC[1][0] * R[4] + RC[1][1] * R[5] + RC[1][2] * R[6]);
-  S.yz = CB.yz + (RC[1][0] * R[8] + RC[1][1] * R[9] + RC[1][2] * R[10]);
-  S.zz = CB.zz + (RC[2][0] * R[8] + RC[2][1] * R[9] + RC[2][2] * R[10]);
+  S.xx = dadd(CB.xx, ddot3(RC[0][0], R[0], RC[0][1], R[1], RC[0][2], R[2]));
+  S.xy = dadd(CB.xy, ddot3(RC[0][0], R[4], RC[0][1], R[5], RC[0][2], R[6]));
+  S.xz = dadd(CB.xz, ddot3(RC[0][0], R[8], RC[0][1], R[9], RC[0][2], R[10]));
+  S.yy = dadd(CB.yy, ddot3(RC[1][0], R[4], RC[1][1], R[5], RC[1][2], R[6]));
+  S.yz = dadd(CB.yz, ddot3(RC[1][0], R[8], RC[1][1], R[9], RC[1][2], R[10]));
+  S.zz = dadd(CB.zz, ddot3(RC[2][0], R[8], RC[2][1], R[9], RC[2][2], R[10]));
   return inv_sym3(S);
 }
 
@@ -292,40 +297,52 @@ constexpr int kAccN = 28;
 RGC_HD double gicp_error_term(const Rt& T, const Sym3& M, float px, float py, float pz, float qx, float qy, float qz) {
   double ax, ay, az;
   transform_d(T, (double)px, (double)py, (double)pz, ax, ay, az);
-  const double ex = (double)qx - ax, ey = (double)qy - ay, ez = (double)qz - az;
-  const double mx = M.xx * ex + M.xy * ey + M.xz * ez;
-  const double my = M.xy * ex + M.yy * ey + M.yz * ez;
-  const double mz = M.xz * ex + M.yz * ey + M.zz * ez;
-  return ex * mx + ey * my + ez * mz;
+  const double ex = dsub((double)qx, ax), ey = dsub((double)qy, ay), ez = dsub((double)qz, az);
+  const double mx = ddot3(M.xx, ex, M.xy, ey, M.xz, ez);
+  const double my = ddot3(M.xy, ex, M.yy, ey, M.yz, ez);
+  const double mz = ddot3(M.xz, ex, M.yz, ey, M.zz, ez);
+  return ddot3(ex, mx, ey, my, ez, mz);
+}
+
+// sum_i J[i][c] * v_i for J = [skew(a) | -I] (3x6): the only products that are not 0 or -v survive, with
+// pinned roundings.  c is a compile-time constant at every call site (fully unrolled loops).
+RGC_HD double jt_dot(int c, const double a[3], double v0, double v1, double v2) {
+  switch (c) {
+    case 0: return dprod_diff(a[2], v1, a[1], v2);   //  a2 v1 - a1 v2
+    case 1: return dprod_diff(a[0], v2, a[2], v0);   //  a0 v2 - a2 v0
+    case 2: return dprod_diff(a[1], v0, a[0], v1);   //  a1 v0 - a0 v1
+    case 3: return -v0;
+    case 4: return -v1;
+    default: return -v2;
+  }
 }
 
 // acc += terms of one correspondence.  J = [skew(a) | -I], a = T p.
 RGC_HD void gicp_point_terms(const Rt& T, const Sym3& M, float px, float py, float pz, float qx, float qy, float qz, double* acc) {
   double a[3];
   transform_d(T, (double)px, (double)py, (double)pz, a[0], a[1], a[2]);
-  const double e[3] = {(double)qx - a[0], (double)qy - a[1], (double)qz - a[2]};
+  const double e[3] = {dsub((double)qx, a[0]), dsub((double)qy, a[1]), dsub((double)qz, a[2])};
   const double Mm[3][3] = {{M.xx, M.xy, M.xz}, {M.xy, M.yy, M.yz}, {M.xz, M.yz, M.zz}};
   double Me[3];
 #pragma unroll
-  for (int i = 0; i < 3; i++) Me[i] = Mm[i][0] * e[0] + Mm[i][1] * e[1] + Mm[i][2] * e[2];
-  acc[0] += e[0] * Me[0] + e[1] * Me[1] + e[2] * Me[2];
-  // J (3x6): columns 0..2 = skew(a), columns 3..5 = -I
-  const double J[3][6] = {{0.0, -a[2], a[1], -1.0, 0.0, 0.0}, {a[2], 0.0, -a[0], 0.0, -1.0, 0.0}, {-a[1], a[0], 0.0, 0.0, 0.0, -1.0}};
+  for (int i = 0; i < 3; i++) Me[i] = ddot3(Mm[i][0], e[0], Mm[i][1], e[1], Mm[i][2], e[2]);
+  acc[0] = dadd(acc[0], ddot3(e[0], Me[0], e[1], Me[1], e[2], Me[2]));
+  // MJ = M J (3x6); H = J^T (M J), upper triangle; b = J^T (M e)
   double MJ[3][6];
 #pragma unroll
   for (int i = 0; i < 3; i++)
 #pragma unroll
-    for (int c = 0; c < 6; c++) MJ[i][c] = Mm[i][0] * J[0][c] + Mm[i][1] * J[1][c] + Mm[i][2] * J[2][c];
+    for (int c = 0; c < 6; c++) MJ[i][c] = jt_dot(c, a, Mm[i][0], Mm[i][1], Mm[i][2]);
   int o = 1;
 #pragma unroll
   for (int r = 0; r < 6; r++)
 #pragma unroll
     for (int c = r; c < 6; c++) {
-      acc[o] += J[0][r] * MJ[0][c] + J[1][r] * MJ[1][c] + J[2][r] * MJ[2][c];
+      acc[o] = dadd(acc[o], jt_dot(r, a, MJ[0][c], MJ[1][c], MJ[2][c]));
       o++;
     }
 #pragma unroll
-  for (int r = 0; r < 6; r++) acc[22 + r] += J[0][r] * Me[0] + J[1][r] * Me[1] + J[2][r] * Me[2];
+  for (int r = 0; r < 6; r++) acc[22 + r] = dadd(acc[22 + r], jt_dot(r, a, Me[0], Me[1], Me[2]));
 }
 
 // Centred covariance of `found` gathered points (k columns; missing columns are zero, matching
