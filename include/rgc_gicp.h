@@ -22,10 +22,15 @@
  *     objects.  A context may serve any number of rgc_reg / rgc_map objects sequentially.  To run
  *     registrations concurrently on one GPU (batched loop-closure verification) give every host thread
  *     its own context: their kernels overlap on the device (tools/bench_c4.py).
- *   - asynchrony: rgc_reg_set_source / set_target return once the cloud is uploaded and sorted; its
- *     k-NN / covariance kernels keep running (source and target on separate streams) and are joined by
- *     the first call that needs them (align, linearize, get_*_covs ...).  The input buffers are not
- *     referenced after a setter returns.
+ *   - asynchrony: rgc_reg_set_source / set_target return as soon as the upload and the first kernels of the
+ *     cloud's build are ISSUED; the rest of the build (sort, voxel hash), the source k-NN / covariances and the
+ *     host waits in between are driven by the first call that needs the cloud (align, linearize, get_*_covs,
+ *     rgc_reg_sync_inputs ...), which interleaves source and target so each host wait overlaps the other
+ *     cloud's device work.  Consequences: (1) a HOST buffer passed to a setter must stay valid and unchanged
+ *     until that next call returns — exactly the lifetime the reference's shared_ptr gives the cloud
+ *     (pageable memory is staged by the driver before the setter returns, pinned memory is read by DMA later);
+ *     (2) a failure of the deferred part (non-finite coordinates, out of memory) is reported by that next call.
+ *     Environment RGC_SYNC_BUILD=1 makes the setters complete the build before returning.
  *   - scratch blocks of a call go back to the context's pool on every exit path, failures included.
  *   - clouds must be finite: a NaN / inf coordinate makes set_source / set_target fail with
  *     RGC_ERR_INVALID (a NaN candidate would silently break the exactness of the k-NN).
@@ -114,6 +119,9 @@ int rgc_reg_set_target(rgc_reg* reg, const void* points, size_t n, size_t stride
 /* same, but `points` is a DEVICE pointer (cloud already resident in HBM) */
 int rgc_reg_set_source_device(rgc_reg* reg, const void* d_points, size_t n, size_t stride_bytes, uint64_t identity_key);
 int rgc_reg_set_target_device(rgc_reg* reg, const void* d_points, size_t n, size_t stride_bytes, uint64_t identity_key);
+
+/* complete the deferred part of set_source / set_target now (see "asynchrony" above) and report its status */
+int rgc_reg_sync_inputs(rgc_reg* reg);
 
 int rgc_reg_swap_source_and_target(rgc_reg* reg); /* FGI/fast_gicp_impl.hpp:49-57 */
 int rgc_reg_clear_source(rgc_reg* reg);           /* :59-63 */

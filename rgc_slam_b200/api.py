@@ -70,7 +70,7 @@ def lib():
         L.rgc_reg_get_params.argtypes = [vp, C.POINTER(_Params)]
         for name in ("rgc_reg_set_source", "rgc_reg_set_target", "rgc_reg_set_source_device", "rgc_reg_set_target_device"):
             getattr(L, name).argtypes = [vp, vp, sz, sz, u64]
-        for name in ("rgc_reg_swap_source_and_target", "rgc_reg_clear_source", "rgc_reg_clear_target"):
+        for name in ("rgc_reg_swap_source_and_target", "rgc_reg_clear_source", "rgc_reg_clear_target", "rgc_reg_sync_inputs"):
             getattr(L, name).argtypes = [vp]
         for name in ("rgc_reg_set_source_covs", "rgc_reg_set_target_covs", "rgc_reg_get_source_covs", "rgc_reg_get_target_covs"):
             getattr(L, name).argtypes = [vp, vp, sz]
@@ -112,7 +112,7 @@ EXPORTED_SYMBOLS = [
     "rgc_voxel_grid", "rgc_deskew", "rgc_reg_set_source_filtered", "rgc_reg_set_target_filtered",
     "rgc_map_create", "rgc_map_destroy", "rgc_map_associate_edges", "rgc_map_associate_planes",
     "rgc_reg_set_target_covariance_mode", "rgc_ctx_last_ondemand_ms",
-    "rgc_batch_align", "rgc_batch_last_stage_ms",
+    "rgc_batch_align", "rgc_batch_last_stage_ms", "rgc_reg_sync_inputs",
 ]
 
 
@@ -326,6 +326,11 @@ class FastGICP:
 
     def setInputTarget(self, cloud, force=False):
         self._set("target", cloud, force)
+
+    def waitInputs(self):
+        """Complete the deferred part of setInputSource / setInputTarget now (sort, voxel hash, source
+        covariances) and raise if it failed; otherwise the next align / linearize does both."""
+        self.ctx.check(lib().rgc_reg_sync_inputs(self._h))
 
     def swapSourceAndTarget(self):
         self.ctx.check(lib().rgc_reg_swap_source_and_target(self._h))

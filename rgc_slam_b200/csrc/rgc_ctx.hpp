@@ -43,6 +43,10 @@ struct rgc_ctx {
   bool overlap = std::getenv("RGC_NO_OVERLAP") == nullptr;
   bool look_ahead = std::getenv("RGC_NO_LOOKAHEAD") == nullptr;  // step_lm: linearize issued behind compute_error
   std::vector<cudaEvent_t> free_events;
+  // small pinned slots (8 KB) for the host copies a cloud build waits on (bounding-box partials, per-level
+  // cell counts): one per build in flight, so that deferred builds of different clouds never share one
+  std::vector<float*> free_hslots;
+  bool defer_builds = std::getenv("RGC_SYNC_BUILD") == nullptr;  // set_source / set_target return before the build's host waits
   // pinned, device-mapped result area the reduction kernels write straight into
   double* h_result = nullptr;
   double* d_result = nullptr;  // device alias of h_result
@@ -110,6 +114,31 @@ struct rgc_ctx {
   void put_event(cudaEvent_t e) {
     if (e) free_events.push_back(e);
   }
+  static constexpr size_t kHslotBytes = 8192;
+  float* get_hslot() {
+    if (!free_hslots.empty()) {
+      float* p = free_hslots.back();
+      free_hslots.pop_back();
+      return p;
+    }
+    float* p = nullptr;
+    if (cudaHostAlloc((void**)&p, kHslotBytes, cudaHostAllocDefault) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    return p;
+  }
+  void put_hslot(float* p) {
+    if (p) free_hslots.push_back(p);
+  }
+};
+
+// run the enclosed work on lane `to`, then return to the lane that was current
+struct LaneScope {
+  rgc_ctx* c;
+  int prev;
+  LaneScope(rgc_ctx* c_, int to) : c(c_), prev(c_->lane) { c->switch_lane(to); }
+  ~LaneScope() { c->switch_lane(prev); }
 };
 
 // pooled scratch blocks of one call: every exit path (FAIL / CK / TRY included) gives them back

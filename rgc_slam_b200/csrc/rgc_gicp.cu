@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstdio>
 #include <map>
+#include <memory>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -47,7 +48,30 @@ struct Tracer {
 };
 
 // ------------------------------------------------------------------------------------------------
+// A cloud build in flight.  The build has two points where the HOST needs a number from the device (the
+// bounding box -> grid geometry and number of sort passes; the per-level cell counts -> table sizes).  With
+// deferred builds (the default) a setter issues the work up to the first of them and returns; the rest is
+// driven by the next call that needs the cloud (reg_drain), which interleaves the builds of source and
+// target so that each host wait overlaps the other cloud's device work (they used to run back to back:
+// 0.6 ms of prologue for a cold align instead of ~0.35).
+struct BuildJob {
+  Scratch tmp;
+  int stage = 0;  // 1: ingest issued, waiting for the bounding box; 2: sort issued, waiting for the level counts
+  int lane = 0;
+  int n = 0, cloud_bits = 0, n_clouds = 0;
+  uint64_t key = 0;
+  float cell = 0.f;
+  float4* orig = nullptr;
+  float* d_bbox = nullptr;
+  uint64_t *keys_a = nullptr, *keys_b = nullptr, *kin = nullptr;
+  uint32_t *vals_a = nullptr, *vals_b = nullptr, *vin = nullptr, *hist = nullptr, *d_counts = nullptr;
+  float* h_slot = nullptr;     // pinned: 6 x kBboxBlocks floats, then kMaxLevels counters
+  cudaEvent_t ready = nullptr;  // the host copy the next phase waits for has landed
+  explicit BuildJob(rgc_ctx* c) : tmp(c) {}
+};
+
 struct Cloud {
+  std::unique_ptr<BuildJob> job;  // non-null while the build is in flight (valid is false until it completes)
   int n = 0;
   uint64_t key = 0;
   bool valid = false;
@@ -115,6 +139,11 @@ static int join_side(rgc_ctx* c) {
 }
 
 static void cloud_release(rgc_ctx* c, Cloud& cl) {
+  if (cl.job) {  // a build in flight: its scratch goes back to the pool (stream-ordered reuse), the rest below
+    c->put_hslot(cl.job->h_slot);
+    c->put_event(cl.job->ready);
+    cl.job.reset();
+  }
   c->put(cl.sorted);
   c->put(cl.inv);
   c->put(cl.tables);
@@ -158,102 +187,120 @@ static int radix_sort_pairs(rgc_ctx* c, uint64_t* keys_a, uint64_t* keys_b, uint
   return RGC_OK;
 }
 
-// upload (or adopt a device pointer), Morton-sort, build the level tables
+// upload (or adopt a device pointer), Morton-sort, build the level tables — in three phases separated by
+// the two host waits (see BuildJob).  All phases of a cloud run on the lane that was current in phase 1.
 // `offsets` (nullable, n_clouds + 1 entries): the input is the concatenation of n_clouds clouds that
 // become one multi-cloud grid (rgc_grid.cuh: CloudRange)
-static int cloud_build(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, size_t stride, bool on_device, uint64_t key, float cell,
-                       const int* offsets = nullptr, int n_clouds = 0) {
+static int build_phase1(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, size_t stride, bool on_device, uint64_t key, float cell, const int* offsets,
+                        int n_clouds) {
   cloud_release(c, cl);
   if (n_sz == 0 || points == nullptr) FAIL(c, RGC_ERR_INVALID, "empty point cloud");
   if (n_sz > 0x7fffffff / 32) FAIL(c, RGC_ERR_UNSUPPORTED, "point cloud too large for 32-bit indexing");
   if (stride < 12 || stride % 4) FAIL(c, RGC_ERR_INVALID, "point stride must be a multiple of 4 and >= 12 bytes");
   const int n = (int)n_sz;
   cudaStream_t st = c->stream;
-  Tracer tr;
   for (int i = 0; i < 5; i++)
     if (!(cl.ev[i] = c->get_event())) FAIL(c, RGC_ERR_CUDA, "cudaEventCreate failed");
   CK(c, cudaEventRecord(cl.ev[0], st));
-
-  const unsigned char* d_raw = (const unsigned char*)points;
-  Scratch tmp(c);  // returned to the pool on every exit path
-  if (!on_device) {
-    void* staging = tmp.get(n_sz * stride);
-    if (!staging) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (staging)");
-    CK(c, cudaMemcpyAsync(staging, points, n_sz * stride, cudaMemcpyHostToDevice, st));
-    d_raw = (const unsigned char*)staging;
-  }
-  float4* orig = (float4*)tmp.get(sizeof(float4) * n_sz);
-  float* d_bbox = (float*)tmp.get(sizeof(float) * 6 * kBboxBlocks);
-  uint64_t* keys_a = (uint64_t*)tmp.get(8 * n_sz);
-  uint64_t* keys_b = (uint64_t*)tmp.get(8 * n_sz);
-  uint32_t* vals_a = (uint32_t*)tmp.get(4 * n_sz);
-  uint32_t* vals_b = (uint32_t*)tmp.get(4 * n_sz);
-  const int nblk = div_up(n, RS_TILE);
-  uint32_t* hist = (uint32_t*)tmp.get(4 * 256 * ((size_t)nblk + 1));
-  uint32_t* d_counts = (uint32_t*)tmp.get(4 * kMaxLevels);
-  cl.sorted = (float4*)c->get(sizeof(float4) * n_sz);
-  cl.inv = (int*)c->get(sizeof(int) * n_sz);
-  if (!cl.inv || !orig || !d_bbox || !keys_a || !keys_b || !vals_a || !vals_b || !hist || !d_counts || !cl.sorted) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (build)");
-
-  tr.lap("alloc");
-  k_ingest<<<kBboxBlocks, 256, 0, st>>>(d_raw, stride, n, orig, d_bbox);
-  CKL(c);
-  CK(c, cudaMemcpyAsync(c->h_bbox, d_bbox, sizeof(float) * 6 * kBboxBlocks, cudaMemcpyDeviceToHost, st));
-  CK(c, cudaStreamSynchronize(st));
-  tr.lap("ingest+bbox sync");
-  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-  bool finite = true;  // a block that saw NaN / inf writes NaN partials (k_ingest)
-  for (int b = 0; b < kBboxBlocks; b++)
-    for (int a = 0; a < 3; a++) {
-      finite = finite && !std::isnan(c->h_bbox[b * 6 + a]) && !std::isnan(c->h_bbox[b * 6 + 3 + a]);
-      mn[a] = std::min(mn[a], c->h_bbox[b * 6 + a]);
-      mx[a] = std::max(mx[a], c->h_bbox[b * 6 + 3 + a]);
-    }
-  for (int a = 0; a < 3; a++)
-    if (!finite || !std::isfinite(mn[a]) || !std::isfinite(mx[a])) FAIL(c, RGC_ERR_INVALID, "point cloud contains non-finite coordinates");
-
-  for (int a = 0; a < 3; a++) {
-    cl.bb_min[a] = mn[a];
-    cl.bb_max[a] = mx[a];
-  }
-  // ---- grid geometry ----
-  GridView& v = cl.view;
-  v.n = n;
-  int cloud_bits = 0;
+  cl.job.reset(new BuildJob(c));
+  BuildJob& j = *cl.job;
+  j.stage = 1;
+  j.lane = c->lane;
+  j.n = n;
+  j.key = key;
+  j.cell = cell;
+  j.h_slot = c->get_hslot();
+  j.ready = c->get_event();
+  if (!j.h_slot || !j.ready) FAIL(c, RGC_ERR_NOMEM, "pinned slot / event allocation failed (build)");
   if (offsets) {
-    while ((1 << cloud_bits) < n_clouds) cloud_bits++;
+    while ((1 << j.cloud_bits) < n_clouds) j.cloud_bits++;
+    j.n_clouds = n_clouds;
     cl.n_clouds = n_clouds;
     cl.h_off.assign(offsets, offsets + n_clouds + 1);
     cl.d_off = (int*)c->get(sizeof(int) * (size_t)(n_clouds + 1));
     if (!cl.d_off) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (cloud offsets)");
     CK(c, cudaMemcpyAsync(cl.d_off, offsets, sizeof(int) * (size_t)(n_clouds + 1), cudaMemcpyHostToDevice, st));
   }
-  grid_geometry(mn, mx, cell, v, std::min(kMaxBits, (56 - cloud_bits) / 3));  // key = cloud id | 3 * nbits Morton bits <= 56 bits
+  const unsigned char* d_raw = (const unsigned char*)points;
+  if (!on_device) {
+    void* staging = j.tmp.get(n_sz * stride);
+    if (!staging) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (staging)");
+    CK(c, cudaMemcpyAsync(staging, points, n_sz * stride, cudaMemcpyHostToDevice, st));
+    d_raw = (const unsigned char*)staging;
+  }
+  j.orig = (float4*)j.tmp.get(sizeof(float4) * n_sz);
+  j.d_bbox = (float*)j.tmp.get(sizeof(float) * 6 * kBboxBlocks);
+  j.keys_a = (uint64_t*)j.tmp.get(8 * n_sz);
+  j.keys_b = (uint64_t*)j.tmp.get(8 * n_sz);
+  j.vals_a = (uint32_t*)j.tmp.get(4 * n_sz);
+  j.vals_b = (uint32_t*)j.tmp.get(4 * n_sz);
+  j.hist = (uint32_t*)j.tmp.get(4 * 256 * ((size_t)div_up(n, RS_TILE) + 1));
+  j.d_counts = (uint32_t*)j.tmp.get(4 * kMaxLevels);
+  cl.sorted = (float4*)c->get(sizeof(float4) * n_sz);
+  cl.inv = (int*)c->get(sizeof(int) * n_sz);
+  if (!cl.inv || !j.orig || !j.d_bbox || !j.keys_a || !j.keys_b || !j.vals_a || !j.vals_b || !j.hist || !j.d_counts || !cl.sorted)
+    FAIL(c, RGC_ERR_NOMEM, "device allocation failed (build)");
+  k_ingest<<<kBboxBlocks, 256, 0, st>>>(d_raw, stride, n, j.orig, j.d_bbox);
+  CKL(c);
+  CK(c, cudaMemcpyAsync(j.h_slot, j.d_bbox, sizeof(float) * 6 * kBboxBlocks, cudaMemcpyDeviceToHost, st));
+  CK(c, cudaEventRecord(j.ready, st));
+  return RGC_OK;
+}
+
+// bounding box on the host -> grid geometry, Morton keys, radix sort, per-level cell counts
+static int build_phase2(rgc_ctx* c, Cloud& cl) {
+  BuildJob& j = *cl.job;
+  CK(c, cudaEventSynchronize(j.ready));
+  cudaStream_t st = c->stream;
+  const int n = j.n;
+  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  bool finite = true;  // a block that saw NaN / inf writes NaN partials (k_ingest)
+  for (int b = 0; b < kBboxBlocks; b++)
+    for (int a = 0; a < 3; a++) {
+      finite = finite && !std::isnan(j.h_slot[b * 6 + a]) && !std::isnan(j.h_slot[b * 6 + 3 + a]);
+      mn[a] = std::min(mn[a], j.h_slot[b * 6 + a]);
+      mx[a] = std::max(mx[a], j.h_slot[b * 6 + 3 + a]);
+    }
+  for (int a = 0; a < 3; a++)
+    if (!finite || !std::isfinite(mn[a]) || !std::isfinite(mx[a])) FAIL(c, RGC_ERR_INVALID, "point cloud contains non-finite coordinates");
+  for (int a = 0; a < 3; a++) {
+    cl.bb_min[a] = mn[a];
+    cl.bb_max[a] = mx[a];
+  }
+  GridView& v = cl.view;
+  v.n = n;
+  grid_geometry(mn, mx, j.cell, v, std::min(kMaxBits, (56 - j.cloud_bits) / 3));  // key = cloud id | 3 * nbits Morton bits <= 56 bits
   const int nbits = v.nbits;
-  GridGeom geom{v.ox, v.oy, v.oz, v.inv_s0, nbits};
+  GridGeom geom{v.inv_s0, v.bias, nbits};
+  k_morton<<<div_up(n, 256), 256, 0, st>>>(j.orig, n, geom, j.keys_a, j.vals_a, cl.d_off, j.n_clouds);
+  CKL(c);
+  j.kin = j.keys_a;
+  j.vin = j.vals_a;
+  TRY(radix_sort_pairs(c, j.keys_a, j.keys_b, j.vals_a, j.vals_b, j.hist, n, 3 * nbits + j.cloud_bits, &j.kin, &j.vin));
+  k_gather_sorted<<<div_up(n, 256), 256, 0, st>>>(j.orig, j.vin, n, cl.sorted, cl.inv);
+  CKL(c);
+  CK(c, cudaMemsetAsync(j.d_counts, 0, 4 * kMaxLevels, st));
+  k_count_cells<<<div_up(n, 256), 256, 0, st>>>(j.kin, n, v.nlevels, j.d_counts);
+  CKL(c);
+  CK(c, cudaMemcpyAsync(j.h_slot + 6 * kBboxBlocks, j.d_counts, 4 * kMaxLevels, cudaMemcpyDeviceToHost, st));
+  CK(c, cudaEventRecord(j.ready, st));
+  j.stage = 2;
+  return RGC_OK;
+}
 
-  // ---- Morton keys + LSD radix sort ----
-  k_morton<<<div_up(n, 256), 256, 0, st>>>(orig, n, geom, keys_a, vals_a, cl.d_off, n_clouds);
-  CKL(c);
-  uint64_t* kin = keys_a;
-  uint32_t* vin = vals_a;
-  TRY(radix_sort_pairs(c, keys_a, keys_b, vals_a, vals_b, hist, n, 3 * nbits + cloud_bits, &kin, &vin));
-  k_gather_sorted<<<div_up(n, 256), 256, 0, st>>>(orig, vin, n, cl.sorted, cl.inv);
-  CKL(c);
-
-  // ---- level tables ----
-  CK(c, cudaMemsetAsync(d_counts, 0, 4 * kMaxLevels, st));
-  k_count_cells<<<div_up(n, 256), 256, 0, st>>>(kin, n, v.nlevels, d_counts);
-  CKL(c);
-  CK(c, cudaMemcpyAsync(c->h_counts, d_counts, 4 * kMaxLevels, cudaMemcpyDeviceToHost, st));
-  tr.lap("sort launches");
-  CK(c, cudaStreamSynchronize(st));
-  tr.lap("sort+count sync");
+// level counts on the host -> table sizes, table build, child masks; the cloud becomes valid
+static int build_phase3(rgc_ctx* c, Cloud& cl) {
+  BuildJob& j = *cl.job;
+  CK(c, cudaEventSynchronize(j.ready));
+  cudaStream_t st = c->stream;
+  const int n = j.n;
+  GridView& v = cl.view;
+  const uint32_t* h_counts = reinterpret_cast<const uint32_t*>(j.h_slot + 6 * kBboxBlocks);
   size_t total_slots = 0;
   size_t slots[kMaxLevels];
   for (int l = 0; l < v.nlevels; l++) {
     size_t s = 8;
-    while (s < 2 * (size_t)c->h_counts[l]) s <<= 1;
+    while (s < 2 * (size_t)h_counts[l]) s <<= 1;
     slots[l] = s;
     total_slots += s;
   }
@@ -280,20 +327,31 @@ static int cloud_build(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, s
     v.mask[l] = ts.mask[l];
     v.shift[l] = ts.shift[l];
   }
-  k_build_tables<<<dim3(div_up(n, 256), v.nlevels), 256, 0, st>>>(kin, n, ts);
+  k_build_tables<<<dim3(div_up(n, 256), v.nlevels), 256, 0, st>>>(j.kin, n, ts);
   CKL(c);
-  k_child_masks<<<div_up(n, 256), 256, 0, st>>>(kin, n, ts);
+  k_child_masks<<<div_up(n, 256), 256, 0, st>>>(j.kin, n, ts);
   CKL(c);
   v.pts = reinterpret_cast<const F4*>(cl.sorted);
   v.inv = cl.inv;
-
   cl.n = n;
-  cl.key = key;
+  cl.key = j.key;
   cl.valid = true;
-  tr.lap("tables launches");
   CK(c, cudaEventRecord(cl.ev[1], st));
   cl.build_timed = true;
+  c->put_hslot(j.h_slot);
+  c->put_event(j.ready);
+  cl.job.reset();  // scratch back to the pool (the kernels above are ordered before any reuse on this lane)
   return RGC_OK;
+}
+
+// the whole build, synchronously, on the current lane
+static int cloud_build(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, size_t stride, bool on_device, uint64_t key, float cell,
+                       const int* offsets = nullptr, int n_clouds = 0) {
+  int rc = build_phase1(c, cl, points, n_sz, stride, on_device, key, cell, offsets, n_clouds);
+  if (rc == RGC_OK) rc = build_phase2(c, cl);
+  if (rc == RGC_OK) rc = build_phase3(c, cl);
+  if (rc != RGC_OK) cloud_release(c, cl);
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -907,8 +965,61 @@ static void reg_adopt_ahead(rgc_reg* r) {
   r->spec_ready = true;
 }
 
+// what follows a finished build: the covariances are STARTED right away (fast_gicp_impl.hpp:104-109
+// computes them at the first align; they are redone if k / regularisation change before that), except a
+// target whose covariances are computed on demand; a source build ends with the event the main stream joins
+static int post_build(rgc_reg* r, Cloud& cl) {
+  rgc_ctx* c = r->ctx;
+  int rc = RGC_OK;
+  if (!(&cl == &r->tgt && target_lazy(r))) rc = cloud_covariances(c, cl, r->prm.k_correspondences, r->prm.regularization, true);
+  if (c->lane == 1) {
+    cudaEventRecord(c->join_ev, c->stream);
+    c->side_pending = true;
+  }
+  return rc;
+}
+
+// run the next phase of a cloud's build (its host wait has been satisfied or is about to be)
+static int build_advance(rgc_reg* r, Cloud& cl) {
+  rgc_ctx* c = r->ctx;
+  LaneScope ls(c, cl.job->lane);
+  int rc = cl.job->stage == 1 ? build_phase2(c, cl) : build_phase3(c, cl);
+  if (rc == RGC_OK && !cl.job) rc = post_build(r, cl);
+  if (rc != RGC_OK) cloud_release(c, cl);
+  return rc;
+}
+
+// complete the builds in flight.  Whichever cloud's awaited host copy has landed goes first, so while the
+// host sleeps on one cloud's copy the device works on the other cloud's kernels.
+static int reg_drain(rgc_reg* r) {
+  rgc_ctx* c = r->ctx;
+  for (;;) {
+    Cloud* cls[2] = {&r->tgt, &r->src};
+    bool pending = false, progressed = false;
+    for (Cloud* cl : cls) {
+      if (!cl->job) continue;
+      pending = true;
+      const cudaError_t q = cudaEventQuery(cl->job->ready);
+      if (q == cudaSuccess) {
+        TRY(build_advance(r, *cl));
+        progressed = true;
+      } else if (q == cudaErrorNotReady) {
+        cudaGetLastError();  // not an error
+      } else {
+        CK(c, q);
+      }
+    }
+    if (!pending) return RGC_OK;
+    if (!progressed) {
+      Cloud* w = r->tgt.job ? &r->tgt : &r->src;
+      TRY(build_advance(r, *w));  // blocks on that cloud's event
+    }
+  }
+}
+
 static int reg_ready(rgc_reg* r) {
   rgc_ctx* c = r->ctx;
+  TRY(reg_drain(r));
   if (!r->src.valid || !r->tgt.valid) FAIL(c, RGC_ERR_STATE, "source and target clouds must both be set");
   TRY(join_side(c));
   // fast_gicp_impl.hpp:104-109 — covariances are computed lazily, source first (normally both
@@ -1065,6 +1176,7 @@ int rgc_ctx_destroy(rgc_ctx* c) {
   cudaFreeHost(c->parked.h_counts);
   cudaEventDestroy(c->join_ev);
   for (cudaEvent_t e : c->free_events) cudaEventDestroy(e);
+  for (float* p : c->free_hslots) cudaFreeHost(p);
   cudaStreamDestroy(c->parked.stream);
   cudaFree(c->d_ticket);
   for (int i = 0; i < 8; i++) cudaEventDestroy(c->ev[i]);
@@ -1159,24 +1271,34 @@ int rgc_reg_get_params(const rgc_reg* r, rgc_params* p) {
 static int set_cloud(rgc_reg* r, Cloud& cl, const void* pts, size_t n, size_t stride, uint64_t key, bool on_device) {
   rgc_ctx* c = r->ctx;
   CK(c, cudaSetDevice(c->device));
-  if (key != 0 && cl.valid && cl.key == key) return RGC_OK;  // fast_gicp_impl.hpp:73-75 / :84-86
+  if (key != 0 && (cl.valid || cl.job) && (cl.job ? cl.job->key : cl.key) == key) return RGC_OK;  // fast_gicp_impl.hpp:73-75 / :84-86
   r->have_corr = false;
   if (&cl == &r->tgt) r->vox_valid = false;  // FastVGICP::setInputTarget resets the voxel map (fast_vgicp_impl.hpp:57-64)
-  // The source cloud is prepared on lane 1, the target on the main stream, and the covariances
-  // (fast_gicp_impl.hpp:104-109 computes them at the first align) are STARTED here without waiting:
-  // the kNN of a 500k-point target then runs while the host uploads and sorts the source.
-  SideLane side(c, &cl == &r->src);
-  TRY(cloud_build(c, cl, pts, n, stride, on_device, key, r->prm.grid_cell));
-  if (&cl == &r->tgt && target_lazy(r)) return RGC_OK;  // computed on demand inside linearize (reg_ready)
-  return cloud_covariances(c, cl, r->prm.k_correspondences, r->prm.regularization, true);
+  // The source cloud is prepared on lane 1, the target on the main stream.  Only the first phase of the
+  // build (upload, ingest) is issued here; the rest, and the covariances, follow in reg_drain.
+  {
+    LaneScope ls(c, (&cl == &r->src && c->overlap) ? 1 : 0);
+    int rc = build_phase1(c, cl, pts, n, stride, on_device, key, r->prm.grid_cell, nullptr, 0);
+    if (rc != RGC_OK) {
+      cloud_release(c, cl);
+      return rc;
+    }
+  }
+  return c->defer_builds ? RGC_OK : reg_drain(r);
 }
 int rgc_reg_set_source(rgc_reg* r, const void* p, size_t n, size_t s, uint64_t key) { return r ? set_cloud(r, r->src, p, n, s, key, false) : RGC_ERR_INVALID; }
 int rgc_reg_set_target(rgc_reg* r, const void* p, size_t n, size_t s, uint64_t key) { return r ? set_cloud(r, r->tgt, p, n, s, key, false) : RGC_ERR_INVALID; }
 int rgc_reg_set_source_device(rgc_reg* r, const void* p, size_t n, size_t s, uint64_t key) { return r ? set_cloud(r, r->src, p, n, s, key, true) : RGC_ERR_INVALID; }
 int rgc_reg_set_target_device(rgc_reg* r, const void* p, size_t n, size_t s, uint64_t key) { return r ? set_cloud(r, r->tgt, p, n, s, key, true) : RGC_ERR_INVALID; }
 
+int rgc_reg_sync_inputs(rgc_reg* r) {
+  if (!r) return RGC_ERR_INVALID;
+  CK(r->ctx, cudaSetDevice(r->ctx->device));
+  return reg_drain(r);
+}
 int rgc_reg_swap_source_and_target(rgc_reg* r) {
   if (!r) return RGC_ERR_INVALID;
+  TRY(reg_drain(r));
   std::swap(r->src, r->tgt);
   r->have_corr = false;  // correspondences_.clear(); sq_distances_.clear();
   r->vox_valid = false;  // voxelmap_.reset() (fast_vgicp_impl.hpp:46-54)
@@ -1199,6 +1321,7 @@ int rgc_reg_clear_target(rgc_reg* r) {
 static int set_covs(rgc_reg* r, Cloud& cl, const double* m, size_t n) {
   rgc_ctx* c = r->ctx;
   CK(c, cudaSetDevice(c->device));
+  TRY(reg_drain(r));
   if (!cl.valid) FAIL(c, RGC_ERR_STATE, "set the point cloud before its covariances");
   if ((int)n != cl.n) FAIL(c, RGC_ERR_INVALID, "covariance count does not match the cloud size");
   TRY(join_side(c));
@@ -1221,6 +1344,7 @@ static int set_covs(rgc_reg* r, Cloud& cl, const double* m, size_t n) {
 static int get_covs(rgc_reg* r, Cloud& cl, double* m, size_t n) {
   rgc_ctx* c = r->ctx;
   CK(c, cudaSetDevice(c->device));
+  TRY(reg_drain(r));
   if (!cl.valid) FAIL(c, RGC_ERR_STATE, "no point cloud set");
   if ((int)n != cl.n) FAIL(c, RGC_ERR_INVALID, "covariance count does not match the cloud size");
   TRY(join_side(c));
@@ -1323,6 +1447,7 @@ int rgc_reg_compute_error(rgc_reg* r, const double* T16, double* err) {
   if (!r || !T16 || !err) return RGC_ERR_INVALID;
   rgc_ctx* c = r->ctx;
   CK(c, cudaSetDevice(c->device));
+  TRY(reg_drain(r));
   TRY(join_side(c));
   double T[16];
   colmajor_to_row(T16, T);
@@ -1333,6 +1458,7 @@ int rgc_reg_get_correspondences(rgc_reg* r, int32_t* corr, float* sq_dist) {
   if (!r || !corr) return RGC_ERR_INVALID;
   rgc_ctx* c = r->ctx;
   CK(c, cudaSetDevice(c->device));
+  TRY(reg_drain(r));
   TRY(join_side(c));
   if (r->vgicp) FAIL(c, RGC_ERR_UNSUPPORTED, "point correspondences do not exist in voxelised mode");
   if (!r->have_corr) FAIL(c, RGC_ERR_STATE, "no correspondences yet (call linearize or align first)");
@@ -1353,6 +1479,7 @@ int rgc_reg_fitness(rgc_reg* r, double max_range, double* score) {
   if (!r || !score) return RGC_ERR_INVALID;
   rgc_ctx* c = r->ctx;
   CK(c, cudaSetDevice(c->device));
+  TRY(reg_drain(r));
   TRY(join_side(c));
   if (!r->src.valid || !r->tgt.valid) FAIL(c, RGC_ERR_STATE, "source and target clouds must both be set");
   RtF Tf;
@@ -1493,6 +1620,7 @@ int rgc_debug_get_target_cov_state(rgc_reg* r, double* m4x4, int32_t* state) {
   if (!r || !m4x4 || !state) return RGC_ERR_INVALID;
   rgc_ctx* c = r->ctx;
   CK(c, cudaSetDevice(c->device));
+  TRY(reg_drain(r));
   TRY(join_side(c));
   Cloud& t = r->tgt;
   if (!t.valid) FAIL(c, RGC_ERR_STATE, "no target cloud");
@@ -1537,6 +1665,7 @@ int rgc_reg_get_voxels(rgc_reg* r, int32_t* coords3, int32_t* num_points, double
   if (!r || !n_voxels) return RGC_ERR_INVALID;
   rgc_ctx* c = r->ctx;
   CK(c, cudaSetDevice(c->device));
+  TRY(reg_drain(r));
   TRY(join_side(c));
   if (!r->vgicp) FAIL(c, RGC_ERR_STATE, "voxelised mode is off (rgc_reg_set_vgicp)");
   if (!r->tgt.valid) FAIL(c, RGC_ERR_STATE, "no target cloud");

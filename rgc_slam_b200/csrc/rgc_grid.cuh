@@ -46,7 +46,8 @@ struct GridView {
   const int* inv;  // original index -> sorted position
   const F4* pts;   // sorted points, w = original index bits
   int n;
-  float ox, oy, oz;   // origin
+  float ox, oy, oz;   // origin (metres) = -bias * s0 on every axis: the cells are ABSOLUTE, see grid_geometry
+  int bias;           // fine cell of coordinate x = floor(x * inv_s0) + bias
   float s0, inv_s0;   // finest cell size
   float margin;       // slack (metres) covering float rounding of the cell-coordinate map
   int nbits;          // cells per axis at level 0 = 1 << nbits
@@ -57,7 +58,12 @@ struct GridView {
 };
 
 // Grid geometry from a bounding box (host side; shared by the library and tests/hostsim so both
-// place every point in the same cell).  Sets origin, cell size, nbits/nlevels and the margin.
+// place every point in the same cell).  The grid is ABSOLUTE: the fine cell of a coordinate x is
+// floor(x * inv_s0) + bias with bias = 2^(nbits-1), whatever the cloud — the bounding box only decides how
+// many bits are needed.  Consequence: the Morton order of a cloud's points does not depend on what else
+// shares the grid nor on nbits (a larger nbits only inserts, below each axis' top bit, bits that repeat
+// its complement and never decide a comparison), so a cloud is sorted the same way alone and inside the
+// multi-cloud grid of a batch, and every fixed-order reduction over its points adds in the same order.
 inline void grid_geometry(const float mn[3], const float mx[3], float cell, GridView& v, int max_bits = kMaxBits) {
   float s0 = cell > 0.f ? cell : 0.05f;
   float extent = 0.f, maxabs = 0.f;
@@ -65,16 +71,18 @@ inline void grid_geometry(const float mn[3], const float mx[3], float cell, Grid
     extent = fmaxf(extent, mx[a] - mn[a]);
     maxabs = fmaxf(maxabs, fmaxf(fabsf(mn[a]), fabsf(mx[a])));
   }
-  extent += 2.f * s0;
-  if (extent / s0 > (float)(1 << max_bits)) s0 = extent / (float)(1 << max_bits) * 1.001f;
-  int nbits = 1;
-  while ((float)(1 << nbits) * s0 < extent && nbits < max_bits) nbits++;
-  v.ox = mn[0] - s0;
-  v.oy = mn[1] - s0;
-  v.oz = mn[2] - s0;
+  // cells floor(x / s0) of all points must lie in [-bias, bias): bias * s0 > maxabs + s0
+  int nbits = 2;
+  for (;;) {
+    while (nbits < max_bits && (float)(1 << (nbits - 1)) * s0 <= maxabs + 2.f * s0) nbits++;
+    if ((float)(1 << (nbits - 1)) * s0 > maxabs + 2.f * s0) break;
+    s0 *= 2.f;  // coarser cells (a power-of-two ladder) once max_bits cannot cover the extent
+  }
+  v.bias = 1 << (nbits - 1);
+  v.ox = v.oy = v.oz = -(float)v.bias * s0;
   v.s0 = s0;
   v.inv_s0 = 1.0f / s0;
-  v.margin = 2e-6f * (maxabs + extent) + 1e-6f;
+  v.margin = 2e-6f * (2.f * maxabs + extent) + 1e-6f;
   v.nbits = nbits;
   v.nlevels = nbits + 1;
 }
@@ -96,12 +104,13 @@ RGC_HD uint64_t morton3(uint32_t x, uint32_t y, uint32_t z) { return spread3(x) 
 // xor-shifts on the critical path of every probe.)
 RGC_HD uint32_t slot_of(uint64_t key, uint32_t shift) { return (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> shift); }
 
-// fine-level integer cell coordinate of a float coordinate.  Monotone non-decreasing in x
-// (float subtract, multiply and floor are monotone), which is what the face bounds rely on.
-RGC_HD int cell_coord(float x, float o, float inv_s) {
-  float t = fmul(fsub(x, o), inv_s);
+// fine-level integer cell coordinate of a float coordinate: floor(x * inv_s) + bias.  Monotone
+// non-decreasing in x (float multiply and floor are monotone), which is what the face bounds rely on;
+// the only rounding is that of x * inv_s (<= 6e-8 |x| metres, covered by GridView::margin).
+RGC_HD int cell_coord(float x, float inv_s, int bias) {
+  float t = fmul(x, inv_s);
   t = t < -1.0e9f ? -1.0e9f : (t > 1.0e9f ? 1.0e9f : t);
-  return (int)floorf(t);
+  return (int)floorf(t) + bias;
 }
 
 RGC_HD GridSlot load_slot(const GridSlot* p) {
@@ -441,7 +450,7 @@ RGC_HD void knn_search(const GridView& g, float qx, float qy, float qz, int k, f
     if (near_pos >= 0) {
       p0 = near_pos - (k >> 1);
     } else {
-      const int fx = cell_coord(qx, g.ox, g.inv_s0), fy = cell_coord(qy, g.oy, g.inv_s0), fz = cell_coord(qz, g.oz, g.inv_s0);
+      const int fx = cell_coord(qx, g.inv_s0, g.bias), fy = cell_coord(qy, g.inv_s0, g.bias), fz = cell_coord(qz, g.inv_s0, g.bias);
       p0 = cr.lo;
       for (int l = 0; l <= top_level; l++) {
         uint32_t s, e, m;

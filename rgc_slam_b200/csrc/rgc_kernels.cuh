@@ -81,8 +81,8 @@ __global__ void __launch_bounds__(256) k_ingest(const unsigned char* __restrict_
 }
 
 struct GridGeom {
-  float ox, oy, oz, inv_s0;
-  int nbits;
+  float inv_s0;
+  int bias, nbits;
 };
 
 // `cloud_off` (nullable, n_clouds + 1 offsets into pts): a multi-cloud grid — point i of cloud c gets
@@ -93,9 +93,9 @@ __global__ void __launch_bounds__(256) k_morton(const float4* __restrict__ pts, 
   if (i >= n) return;
   float4 p = pts[i];
   const int hi = (1 << g.nbits) - 1;
-  int cx = min(max(cell_coord(p.x, g.ox, g.inv_s0), 0), hi);
-  int cy = min(max(cell_coord(p.y, g.oy, g.inv_s0), 0), hi);
-  int cz = min(max(cell_coord(p.z, g.oz, g.inv_s0), 0), hi);
+  int cx = min(max(cell_coord(p.x, g.inv_s0, g.bias), 0), hi);
+  int cy = min(max(cell_coord(p.y, g.inv_s0, g.bias), 0), hi);
+  int cz = min(max(cell_coord(p.z, g.inv_s0, g.bias), 0), hi);
   uint64_t key = morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
   if (cloud_off) {
     int a = 0, b = n_clouds;  // cloud_off[a] <= i < cloud_off[b]
@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(KT_WARPS * 32) k_knn_tile(GridView g, int n, i
   // of one such lane); this cap costs a handful of probes and removes that tail.
   float cap2 = INFINITY;
   {
-    const int fx = cell_coord(q.x, g.ox, g.inv_s0), fy = cell_coord(q.y, g.oy, g.inv_s0), fz = cell_coord(q.z, g.oz, g.inv_s0);
+    const int fx = cell_coord(q.x, g.inv_s0, g.bias), fy = cell_coord(q.y, g.inv_s0, g.bias), fz = cell_coord(q.z, g.inv_s0, g.bias);
     const float seed_b = heap.cnt == k ? key_d2(hk[lane]) : INFINITY;
     for (int l = 0; l < g.nlevels; l++) {
       const float edge = g.s0 * (float)(1 << l) + 2.f * g.margin;
@@ -634,8 +634,8 @@ __global__ void __launch_bounds__(KT_WARPS * 32) k_knn_tile(GridView g, int n, i
     long long* o = g_tile_dbg + (size_t)tile_id * 4;
     // level of the smallest cell holding the whole tile, and the launch-relative start time
     const float4 pa = pts4[first], pb = pts4[min(first + 31, hi - 1)];
-    const uint64_t ma = morton3(cell_coord(pa.x, g.ox, g.inv_s0), cell_coord(pa.y, g.oy, g.inv_s0), cell_coord(pa.z, g.oz, g.inv_s0));
-    const uint64_t mb = morton3(cell_coord(pb.x, g.ox, g.inv_s0), cell_coord(pb.y, g.oy, g.inv_s0), cell_coord(pb.z, g.oz, g.inv_s0));
+    const uint64_t ma = morton3(cell_coord(pa.x, g.inv_s0, g.bias), cell_coord(pa.y, g.inv_s0, g.bias), cell_coord(pa.z, g.inv_s0, g.bias));
+    const uint64_t mb = morton3(cell_coord(pb.x, g.inv_s0, g.bias), cell_coord(pb.y, g.inv_s0, g.bias), cell_coord(pb.z, g.inv_s0, g.bias));
     const int lca = ma == mb ? 0 : (63 - __clzll((long long)(ma ^ mb))) / 3 + 1;
     o[0] = clock64() - dbg_t0;
     o[1] = (long long)dbg_nodes | ((long long)lca << 40);
@@ -739,7 +739,7 @@ __global__ void __launch_bounds__(KW_WARPS * 32) k_knn_warp(GridView g, int n, i
     if (hi - lo > ns) {
       // geometric cap (see k_knn_tile): lane l probes the level-l cell of the query
       {
-        const int fx = cell_coord(q.x, g.ox, g.inv_s0), fy = cell_coord(q.y, g.oy, g.inv_s0), fz = cell_coord(q.z, g.oz, g.inv_s0);
+        const int fx = cell_coord(q.x, g.inv_s0, g.bias), fy = cell_coord(q.y, g.inv_s0, g.bias), fz = cell_coord(q.z, g.inv_s0, g.bias);
         bool enough = false;
         if (lane < g.nlevels) {
           uint32_t s, e, m;

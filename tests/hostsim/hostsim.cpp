@@ -37,9 +37,9 @@ static void sim_build(const float* xyzw, int n, float cell, SimCloud& c) {
   std::vector<uint64_t> keys(n);
   std::vector<int> order(n);
   for (int i = 0; i < n; i++) {
-    int cx = std::min(std::max(cell_coord(xyzw[4 * (size_t)i], v.ox, v.inv_s0), 0), hi);
-    int cy = std::min(std::max(cell_coord(xyzw[4 * (size_t)i + 1], v.oy, v.inv_s0), 0), hi);
-    int cz = std::min(std::max(cell_coord(xyzw[4 * (size_t)i + 2], v.oz, v.inv_s0), 0), hi);
+    int cx = std::min(std::max(cell_coord(xyzw[4 * (size_t)i], v.inv_s0, v.bias), 0), hi);
+    int cy = std::min(std::max(cell_coord(xyzw[4 * (size_t)i + 1], v.inv_s0, v.bias), 0), hi);
+    int cz = std::min(std::max(cell_coord(xyzw[4 * (size_t)i + 2], v.inv_s0, v.bias), 0), hi);
     keys[i] = morton3(cx, cy, cz);
     order[i] = i;
   }

@@ -197,6 +197,7 @@ def test_non_finite_input_is_rejected(rgc, small_pair):
             cloud[len(cloud) // 3, 1] = bad
             with pytest.raises(rgc.RgcError, match="non-finite"):
                 getattr(g, "setInputSource" if which == "source" else "setInputTarget")(cloud)
+                g.waitInputs()  # the bounding box of a deferred build is examined by the next call
     raw = np.concatenate([src[:, :3], np.zeros((len(src), 1), np.float32)], 1)
     raw[5, 0] = np.nan
     with pytest.raises(rgc.RgcError, match="non-finite"):
