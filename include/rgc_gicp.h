@@ -198,11 +198,33 @@ int rgc_knn_self(rgc_ctx* ctx, const void* points, size_t n, size_t stride_bytes
  * one whose slab [lo, hi) along `axis` (0/1/2) contains its TRANSFORMED position (computed in float,
  * identically on every rank).  axis < 0 switches sharding off.                                      */
 int rgc_reg_set_owner_slab(rgc_reg* reg, int axis, float lo, float hi);
-/* After every linearize / compute_error / fitness kernel the partial sums (n doubles: 29 / 1 / 2)
- * sit in `d_buf` (device memory, caller-owned, >= 29 doubles); `fn` must sum them across ranks IN
- * PLACE on the context's stream (one NCCL all-reduce; the caller owns the communicator, e.g.
- * torch.distributed) before returning 0.  The host LM loop then proceeds on the reduced values, so
- * every rank takes identical steps.  fn == NULL switches the hook off.                              */
+/* the same selection done by the library: `points` is the FULL target (host); the points with
+ * lo - halo <= p[axis] < hi + halo are kept ON THE DEVICE (input order) and become this rank's target, and [lo, hi)
+ * (+-inf allowed at the ends) becomes its ownership slab.  halo >= max_correspondence_distance + the k-NN radius of
+ * the covariance neighbourhoods.  n_local / local_index (nullable: original index of each kept point) are outputs. */
+int rgc_reg_set_target_slab(rgc_reg* reg, const void* points, size_t n, size_t stride_bytes, int axis, float lo, float hi, float halo,
+                            uint64_t identity_key, size_t* n_local, int32_t* local_index);
+
+/* Cross-rank sum of the partial (err, H, b).  Preferred: a communicator owned by the library — the partial sums
+ * of linearize (29 doubles), compute_error (1), the two together when the LM loop issues them back to back (30) and
+ * fitness (2) are summed by ONE ncclAllReduce on the context's stream, moved to the host result area by a
+ * one-block kernel and picked up by the host's poll: no host code runs between the reduction kernels and the
+ * totals, and every rank takes identical LM steps.  rank 0 calls rgc_comm_unique_id and hands the 128 bytes to the
+ * other ranks by any side channel (torch.distributed, MPI, a file); every rank then calls rgc_comm_create
+ * (collective).  libnccl.so.2 is opened at run time (RGC_NCCL_LIB overrides the name).                       */
+typedef struct rgc_comm rgc_comm;
+int rgc_comm_unique_id(char* id128);
+int rgc_comm_create(rgc_ctx* ctx, const char* id128, int rank, int world, rgc_comm** out);
+int rgc_comm_destroy(rgc_comm* comm);
+int rgc_comm_info(const rgc_comm* comm, int* rank, int* world, uint64_t* n_allreduce, int* nccl_version);
+int rgc_reg_set_comm(rgc_reg* reg, rgc_comm* comm); /* NULL switches it off */
+/* mean latency (us, CUDA events) of `reps` back-to-back all-reduces of n doubles on the context's stream; collective */
+int rgc_comm_allreduce_us(rgc_comm* comm, int n_doubles, int reps, float* us);
+
+/* Alternative: a caller-supplied reduction.  After every linearize / compute_error / fitness kernel the partial
+ * sums (n doubles: 29 / 1 / 2) sit in `d_buf` (device memory, caller-owned, >= 29 doubles); `fn` must sum them
+ * across ranks IN PLACE on the context's stream before returning 0 (gloo in the CPU tests, any other transport).
+ * fn == NULL switches the hook off.                                                                            */
 typedef int (*rgc_reduce_fn)(void* user, void* d_buf, int n_doubles);
 int rgc_reg_set_allreduce(rgc_reg* reg, rgc_reduce_fn fn, void* user, void* d_buf);
 

@@ -113,6 +113,7 @@ EXPORTED_SYMBOLS = [
     "rgc_map_create", "rgc_map_destroy", "rgc_map_associate_edges", "rgc_map_associate_planes",
     "rgc_reg_set_target_covariance_mode", "rgc_ctx_last_ondemand_ms",
     "rgc_batch_align", "rgc_batch_last_stage_ms", "rgc_reg_sync_inputs",
+    "rgc_reg_set_target_slab", "rgc_comm_unique_id", "rgc_comm_create", "rgc_comm_destroy", "rgc_comm_info", "rgc_reg_set_comm", "rgc_comm_allreduce_us",
 ]
 
 

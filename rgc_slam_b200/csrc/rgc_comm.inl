@@ -1,0 +1,151 @@
+// rgc_comm.inl — NCCL communicator owned by the library (config C5: voxel/slab-sharded target); included by
+// rgc_gicp.cu.  libnccl is opened at run time (dlopen), so the single-GPU library has no NCCL dependency
+// and, inside a PyTorch process, the communicator uses the very libnccl.so.2 torch has already loaded.
+#include <dlfcn.h>
+#include <nccl.h>
+
+namespace {
+
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  ncclResult_t (*GetVersion)(int*) = nullptr;
+  std::string err;
+};
+
+static NcclApi* nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return &api;
+  tried = true;
+  const char* names[] = {std::getenv("RGC_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    if (!n) continue;
+    api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (api.handle) break;
+  }
+  if (!api.handle) {
+    api.err = std::string("cannot open libnccl.so.2: ") + (dlerror() ? dlerror() : "?");
+    return &api;
+  }
+  auto sym = [&](const char* s) { return dlsym(api.handle, s); };
+  api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+  api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+  api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+  api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+  api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+  api.GetVersion = (decltype(api.GetVersion))sym("ncclGetVersion");
+  if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy) api.err = "libnccl lacks the expected symbols";
+  return &api;
+}
+
+}  // namespace
+
+struct rgc_comm {
+  rgc_ctx* ctx = nullptr;
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1;
+  double* d_buf = nullptr;  // 64 doubles: where the reduction kernels put a rank's partial sums
+  uint64_t n_allreduce = 0;
+};
+
+// partial sums -> sum over ranks (in place, on the context's stream)
+static int comm_allreduce(rgc_comm* m, int n_doubles) {
+  rgc_ctx* c = m->ctx;
+  NcclApi* api = nccl_api();
+  const ncclResult_t rc = api->AllReduce(m->d_buf, m->d_buf, (size_t)n_doubles, ncclDouble, ncclSum, m->comm, c->stream);
+  if (rc != ncclSuccess) FAIL(c, RGC_ERR_CUDA, std::string("ncclAllReduce: ") + (api->GetErrorString ? api->GetErrorString(rc) : "error"));
+  m->n_allreduce++;
+  return RGC_OK;
+}
+
+extern "C" {
+
+int rgc_comm_unique_id(char* id128) {
+  if (!id128) return RGC_ERR_INVALID;
+  NcclApi* api = nccl_api();
+  if (!api->err.empty()) {
+    std::fprintf(stderr, "rgc_comm_unique_id: %s\n", api->err.c_str());
+    return RGC_ERR_UNSUPPORTED;
+  }
+  ncclUniqueId id;
+  if (api->GetUniqueId(&id) != ncclSuccess) return RGC_ERR_CUDA;
+  static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
+  std::memcpy(id128, &id, 128);
+  return RGC_OK;
+}
+
+int rgc_comm_create(rgc_ctx* c, const char* id128, int rank, int world, rgc_comm** out) {
+  if (!c || !id128 || !out || world < 1 || rank < 0 || rank >= world) return RGC_ERR_INVALID;
+  *out = nullptr;
+  CK(c, cudaSetDevice(c->device));
+  NcclApi* api = nccl_api();
+  if (!api->err.empty()) FAIL(c, RGC_ERR_UNSUPPORTED, api->err);
+  rgc_comm* m = new rgc_comm();
+  m->ctx = c;
+  m->rank = rank;
+  m->world = world;
+  ncclUniqueId id;
+  std::memcpy(&id, id128, 128);
+  const ncclResult_t rc = api->CommInitRank(&m->comm, world, id, rank);
+  if (rc != ncclSuccess) {
+    delete m;
+    FAIL(c, RGC_ERR_CUDA, std::string("ncclCommInitRank: ") + (api->GetErrorString ? api->GetErrorString(rc) : "error"));
+  }
+  if (cudaMalloc((void**)&m->d_buf, sizeof(double) * 64) != cudaSuccess) {
+    api->CommDestroy(m->comm);
+    delete m;
+    FAIL(c, RGC_ERR_NOMEM, "device allocation failed (communicator buffer)");
+  }
+  CK(c, cudaMemset(m->d_buf, 0, sizeof(double) * 64));
+  *out = m;
+  return RGC_OK;
+}
+
+int rgc_comm_destroy(rgc_comm* m) {
+  if (!m) return RGC_OK;
+  cudaSetDevice(m->ctx->device);
+  cudaStreamSynchronize(m->ctx->stream);
+  if (m->comm) nccl_api()->CommDestroy(m->comm);
+  cudaFree(m->d_buf);
+  delete m;
+  return RGC_OK;
+}
+
+// latency of the all-reduce the LM loop uses (n doubles, in place, on the context's stream): mean over `reps`
+// back-to-back calls, CUDA events; a collective — every rank must call it
+int rgc_comm_allreduce_us(rgc_comm* m, int n_doubles, int reps, float* us) {
+  if (!m || !us || n_doubles < 1 || n_doubles > 64 || reps < 1) return RGC_ERR_INVALID;
+  rgc_ctx* c = m->ctx;
+  CK(c, cudaSetDevice(c->device));
+  const uint64_t keep = m->n_allreduce;
+  for (int i = 0; i < 3; i++) TRY(comm_allreduce(m, n_doubles));
+  CK(c, cudaEventRecord(c->evk[0], c->stream));
+  for (int i = 0; i < reps; i++) TRY(comm_allreduce(m, n_doubles));
+  CK(c, cudaEventRecord(c->evk[1], c->stream));
+  CK(c, cudaEventSynchronize(c->evk[1]));
+  float ms = 0.f;
+  CK(c, cudaEventElapsedTime(&ms, c->evk[0], c->evk[1]));
+  *us = 1e3f * ms / (float)reps;
+  m->n_allreduce = keep;
+  CK(c, cudaMemsetAsync(m->d_buf, 0, sizeof(double) * 64, c->stream));
+  return RGC_OK;
+}
+
+int rgc_comm_info(const rgc_comm* m, int* rank, int* world, uint64_t* n_allreduce, int* nccl_version) {
+  if (!m) return RGC_ERR_INVALID;
+  if (rank) *rank = m->rank;
+  if (world) *world = m->world;
+  if (n_allreduce) *n_allreduce = m->n_allreduce;
+  if (nccl_version) {
+    *nccl_version = 0;
+    if (nccl_api()->GetVersion) nccl_api()->GetVersion(nccl_version);
+  }
+  return RGC_OK;
+}
+
+}  // extern "C"

@@ -31,6 +31,8 @@
 
 using namespace rgc;
 
+#include "rgc_comm.inl"
+
 // RGC_TRACE=1: wall-clock trace of the host side of the build pipeline (debug aid)
 static bool trace_on() {
   static int v = -1;
@@ -619,6 +621,7 @@ struct rgc_reg {
   size_t vox_cap = 0;
   // sharded target (config C5)
   Slab slab{-1, 0.f, 0.f};
+  rgc_comm* comm = nullptr;  // library-owned NCCL communicator: partial sums are all-reduced on the context's stream
   rgc_reduce_fn reduce_fn = nullptr;
   void* reduce_user = nullptr;
   double* reduce_buf = nullptr;  // device, caller-owned
@@ -626,33 +629,50 @@ struct rgc_reg {
 
 // where the reduction kernels write, and (sharded) the cross-rank sum before the host reads it
 constexpr int kSpecSlot = 32;  // doubles: results of the look-ahead linearize live at h_result + 32
-static double* reg_result_ptr(rgc_reg* r) { return r->reduce_fn ? r->reduce_buf : r->ctx->d_result; }
-// completion word for the next reduction kernel (null when the sharded all-reduce hook is on, or
+static double* reg_result_ptr(rgc_reg* r) { return r->comm ? r->comm->d_buf : (r->reduce_fn ? r->reduce_buf : r->ctx->d_result); }
+// where the look-ahead linearize (issued behind compute_error) puts its 29 doubles: right behind the error
+// value in the communicator's buffer, so that ONE all-reduce sums both
+static double* reg_spec_ptr(rgc_reg* r) { return r->comm ? r->comm->d_buf + 1 : r->ctx->d_result + kSpecSlot; }
+// completion word for the next reduction kernel (null when the partial sums still have to cross ranks, or
 // polling is disabled: the host then waits on the stream)
 static DoneFlag reg_next_done(rgc_reg* r) {
   rgc_ctx* c = r->ctx;
-  if (r->reduce_fn || !c->spin_wait) return DoneFlag{nullptr, 0ull};
+  if (r->comm || r->reduce_fn || !c->spin_wait) return DoneFlag{nullptr, 0ull};
   return DoneFlag{c->d_seq, ++c->seq};
 }
-static int reg_finish_reduce(rgc_reg* r, int n_doubles) {
-  rgc_ctx* c = r->ctx;
-  if (r->reduce_fn) {
-    if (r->reduce_fn(r->reduce_user, r->reduce_buf, n_doubles) != 0) FAIL(c, RGC_ERR_STATE, "all-reduce hook failed");
-    CK(c, cudaMemcpyAsync(c->h_result, r->reduce_buf, sizeof(double) * n_doubles, cudaMemcpyDeviceToHost, c->stream));
-  } else if (c->spin_wait) {
-    // the last block of the last reduction kernel stored c->seq into mapped pinned memory after its
-    // results: poll that word (an LM step is ~60 us of device work; a stream synchronize adds several us
-    // of wake-up latency to every one of them)
-    volatile unsigned long long* flag = c->h_seq;
-    for (unsigned spins = 0; *flag != c->seq; spins++) {
-      if ((spins & 0x3fff) == 0x3fff) {  // a failed launch / device fault never stores the word
-        cudaError_t e = cudaStreamQuery(c->stream);
-        if (e == cudaSuccess) break;
-        if (e != cudaErrorNotReady) CK(c, e);
-      }
+static int reg_spin(rgc_ctx* c) {
+  // the last block of the last reduction kernel stored c->seq into mapped pinned memory after its
+  // results: poll that word (an LM step is ~60 us of device work; a stream synchronize adds several us
+  // of wake-up latency to every one of them)
+  volatile unsigned long long* flag = c->h_seq;
+  for (unsigned spins = 0; *flag != c->seq; spins++) {
+    if ((spins & 0x3fff) == 0x3fff) {  // a failed launch / device fault never stores the word
+      cudaError_t e = cudaStreamQuery(c->stream);
+      if (e == cudaSuccess) break;
+      if (e != cudaErrorNotReady) CK(c, e);
+      cudaGetLastError();
     }
-    if (*flag != c->seq) CK(c, cudaStreamSynchronize(c->stream));
-    return RGC_OK;
+  }
+  if (*flag != c->seq) CK(c, cudaStreamSynchronize(c->stream));
+  return RGC_OK;
+}
+// n_a doubles -> h_result[0..), n_b doubles (look-ahead linearize) -> h_result[kSpecSlot..)
+static int reg_finish_reduce(rgc_reg* r, int n_a, int n_b = 0) {
+  rgc_ctx* c = r->ctx;
+  if (r->comm) {
+    // one all-reduce of the n_a + n_b partial sums over NVLink, then a one-block kernel moves the totals into
+    // the mapped host result area and stores the completion word: no host involvement in between
+    TRY(comm_allreduce(r->comm, n_a + n_b));
+    const DoneFlag done = c->spin_wait ? DoneFlag{c->d_seq, ++c->seq} : DoneFlag{nullptr, 0ull};
+    k_publish<<<1, 64, 0, c->stream>>>(r->comm->d_buf, n_a, c->d_result, n_b, c->d_result + kSpecSlot, done);
+    CKL(c);
+    if (c->spin_wait) return reg_spin(c);
+  } else if (r->reduce_fn) {
+    if (n_b) FAIL(c, RGC_ERR_STATE, "look-ahead is not available with an all-reduce callback");
+    if (r->reduce_fn(r->reduce_user, r->reduce_buf, n_a) != 0) FAIL(c, RGC_ERR_STATE, "all-reduce hook failed");
+    CK(c, cudaMemcpyAsync(c->h_result, r->reduce_buf, sizeof(double) * n_a, cudaMemcpyDeviceToHost, c->stream));
+  } else if (c->spin_wait) {
+    return reg_spin(c);
   }
   CK(c, cudaStreamSynchronize(c->stream));
   return RGC_OK;
@@ -944,8 +964,8 @@ static int reg_compute_error(rgc_reg* r, const double* T, double* err, bool ahea
                                                                          c->d_ticket, reg_result_ptr(r), reg_next_done(r));
   CKL(c);
   if (c->profile) CK(c, cudaEventRecord(c->evk[1], c->stream));
-  if (ahead) TRY(gicp_linearize_launch(r, T, 1, r->corr, r->corr2, r->sqd2, r->maha2, c->d_result + kSpecSlot));
-  TRY(reg_finish_reduce(r, 1));
+  if (ahead) TRY(gicp_linearize_launch(r, T, 1, r->corr, r->corr2, r->sqd2, r->maha2, reg_spec_ptr(r)));
+  TRY(reg_finish_reduce(r, 1, ahead ? kLinN : 0));
   if (c->profile) {
     cudaEventSynchronize(c->evk[1]);
     cudaEventElapsedTime(&c->last_kernel_ms[2], c->evk[0], c->evk[1]);
@@ -1695,6 +1715,55 @@ int rgc_reg_set_owner_slab(rgc_reg* r, int axis, float lo, float hi) {
   if (!r || axis > 2) return RGC_ERR_INVALID;
   r->slab = Slab{axis, lo, hi};
   r->have_corr = false;
+  return RGC_OK;
+}
+// config C5: this rank's share of a large target, selected ON THE DEVICE from the full cloud: the points whose
+// `axis` coordinate lies in [lo - halo, hi + halo) are kept (input order), become the target, and [lo, hi) becomes
+// the ownership slab of rgc_reg_set_owner_slab
+int rgc_reg_set_target_slab(rgc_reg* r, const void* pts, size_t n_sz, size_t stride, int axis, float lo, float hi, float halo, uint64_t key, size_t* n_local,
+                            int32_t* local_index) {
+  if (!r || !pts || axis < 0 || axis > 2 || !(halo >= 0.f)) return RGC_ERR_INVALID;
+  rgc_ctx* c = r->ctx;
+  CK(c, cudaSetDevice(c->device));
+  if (n_sz == 0 || n_sz > 0x7fffffffu) FAIL(c, RGC_ERR_INVALID, "target size out of range");
+  if (stride < 12 || stride % 4) FAIL(c, RGC_ERR_INVALID, "point stride must be a multiple of 4 and >= 12 bytes");
+  TRY(reg_drain(r));
+  r->have_corr = false;
+  r->vox_valid = false;
+  r->slab = Slab{axis, lo, hi};
+  const int n = (int)n_sz;
+  cudaStream_t st = c->stream;
+  Scratch tmp(c);
+  const int nblk = div_up(n, 256 * kSlabItems);
+  unsigned char* raw = (unsigned char*)tmp.get(n_sz * stride);
+  unsigned int* blk = (unsigned int*)tmp.get(sizeof(unsigned int) * (size_t)(nblk + 1));
+  if (!raw || !blk) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (slab staging)");
+  CK(c, cudaMemcpyAsync(raw, pts, n_sz * stride, cudaMemcpyHostToDevice, st));
+  const float klo = lo - halo, khi = hi + halo;
+  k_slab_count<<<nblk, 256, 0, st>>>(raw, stride, n, axis, klo, khi, blk);
+  CKL(c);
+  k_vg_scan_blocks<<<1, 1024, 0, st>>>(blk, nblk);
+  CKL(c);
+  CK(c, cudaMemcpyAsync(c->h_counts, blk + nblk, 4, cudaMemcpyDeviceToHost, st));
+  CK(c, cudaStreamSynchronize(st));
+  const size_t m = (size_t)c->h_counts[0];
+  if (n_local) *n_local = m;
+  if (m == 0) FAIL(c, RGC_ERR_INVALID, "no target point falls into this rank's slab + halo");
+  float4* local = (float4*)tmp.get(sizeof(float4) * m);
+  int* d_index = local_index ? (int*)tmp.get(sizeof(int) * m) : nullptr;
+  if (!local || (local_index && !d_index)) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (slab)");
+  k_slab_scatter<<<nblk, 256, 0, st>>>(raw, stride, n, axis, klo, khi, blk, local, d_index);
+  CKL(c);
+  if (local_index) CK(c, cudaMemcpyAsync(local_index, d_index, sizeof(int) * m, cudaMemcpyDeviceToHost, st));
+  TRY(cloud_build(c, r->tgt, local, m, sizeof(float4), true, key, r->prm.grid_cell));
+  if (!target_lazy(r)) TRY(cloud_covariances(c, r->tgt, r->prm.k_correspondences, r->prm.regularization, true));
+  if (local_index) CK(c, cudaStreamSynchronize(st));
+  return RGC_OK;
+}
+
+int rgc_reg_set_comm(rgc_reg* r, rgc_comm* comm) {
+  if (!r || (comm && comm->ctx != r->ctx)) return RGC_ERR_INVALID;
+  r->comm = comm;
   return RGC_OK;
 }
 int rgc_reg_set_allreduce(rgc_reg* r, rgc_reduce_fn fn, void* user, void* d_buf) {

@@ -1249,6 +1249,74 @@ __global__ void __launch_bounds__(256) k_cov_export(const float4* __restrict__ s
   m[12] = 0.0; m[13] = 0.0; m[14] = 0.0; m[15] = 0.0;
 }
 
+// summed partial results (device buffer, after the all-reduce of a sharded registration) -> the mapped host
+// result area: src[0, n_a) -> dst_a, src[n_a, n_a + n_b) -> dst_b, then the completion word
+__global__ void __launch_bounds__(64) k_publish(const double* __restrict__ src, int n_a, double* __restrict__ dst_a, int n_b, double* __restrict__ dst_b, DoneFlag done) {
+  const int t = threadIdx.x;
+  if (t < n_a) dst_a[t] = src[t];
+  if (t < n_b) dst_b[t] = src[n_a + t];
+  __threadfence_system();
+  __syncthreads();
+  if (t == 0 && done.flag) *reinterpret_cast<volatile unsigned long long*>(done.flag) = done.value;
+  __threadfence_system();
+}
+
+// config C5: the points of a raw cloud whose `axis` coordinate lies in [lo, hi) (a rank's slab + halo), kept in
+// input order: per-block counts -> k_vg_scan_blocks -> ordered scatter (+ the index of each kept point)
+constexpr int kSlabItems = 8;
+__device__ __forceinline__ bool slab_keep(const unsigned char* __restrict__ raw, size_t stride, int i, int n, int axis, float lo, float hi) {
+  if (i >= n) return false;
+  const float v = reinterpret_cast<const float*>(raw + (size_t)i * stride)[axis];
+  return v >= lo && v < hi;
+}
+__global__ void __launch_bounds__(256) k_slab_count(const unsigned char* __restrict__ raw, size_t stride, int n, int axis, float lo, float hi,
+                                                    unsigned int* __restrict__ block_counts) {
+  const int base = blockIdx.x * 256 * kSlabItems;
+  int c = 0;
+#pragma unroll
+  for (int u = 0; u < kSlabItems; u++) c += slab_keep(raw, stride, base + u * 256 + threadIdx.x, n, axis, lo, hi) ? 1 : 0;
+  __shared__ int ws[8];
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < 8; w++) t += ws[w];
+    block_counts[blockIdx.x] = (unsigned)t;
+  }
+}
+__global__ void __launch_bounds__(256) k_slab_scatter(const unsigned char* __restrict__ raw, size_t stride, int n, int axis, float lo, float hi,
+                                                      const unsigned int* __restrict__ block_offsets, float4* __restrict__ out, int* __restrict__ index_out) {
+  const int base = blockIdx.x * 256 * kSlabItems;
+  __shared__ int warp_cnt[8];
+  __shared__ int pass_base;
+  if (threadIdx.x == 0) pass_base = (int)block_offsets[blockIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int u = 0; u < kSlabItems; u++) {
+    const int i = base + u * 256 + threadIdx.x;
+    const bool keep = slab_keep(raw, stride, i, n, axis, lo, hi);
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) warp_cnt[warp] = __popc(bal);
+    __syncthreads();
+    int before = pass_base;
+    for (int w = 0; w < warp; w++) before += warp_cnt[w];
+    if (keep) {
+      const int pos = before + __popc(bal & ((1u << lane) - 1u));
+      const float* p = reinterpret_cast<const float*>(raw + (size_t)i * stride);
+      out[pos] = make_float4(p[0], p[1], p[2], 1.0f);
+      if (index_out) index_out[pos] = i;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int w = 0; w < 8; w++) t += warp_cnt[w];
+      pass_base += t;
+    }
+    __syncthreads();
+  }
+}
+
 // per-point int flags, sorted order -> the caller's order (test hook for the on-demand covariance state)
 __global__ void __launch_bounds__(256) k_flags_to_orig(const float4* __restrict__ sorted, int n, const int* __restrict__ flags, int fill, int* __restrict__ out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -86,3 +86,93 @@ def extract_features(scans, n_rings=16, min_range=0.5, max_range=80.0, use_inten
         # surfPointsLessFlatScan (:586-592): every point of a processed sextant whose label is <= 0
         res.append(d)
     return res, float(out.device_ms)
+
+
+class FeatureExtractor:
+    """Batched feature extraction with PREALLOCATED PINNED buffers (config C3 end to end): the raw scans are
+    concatenated once into a pinned input buffer, the outputs a front end consumes — the five feature lists with
+    their weights, the per-point labels, cloud sizes / ring ranges and the ground parameters — land in pinned
+    output buffers; nothing is allocated per call and no pageable copy is made.  `extract_features` above
+    returns every intermediate array and is what the parity tests use."""
+
+    def __init__(self, ctx: api.Context | None = None, n_rings=16, max_scans=1024, max_points=1024 * 30000, min_range=0.5, max_range=80.0,
+                 use_intensity=1, labels=True):
+        import torch
+        self.ctx = ctx or api.default_context(0)
+        self.n_rings, self.max_scans, self.max_points = n_rings, max_scans, max_points
+        self.prm = (min_range, max_range, use_intensity)
+        pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()  # noqa: E731
+        i32, f32, f64 = torch.int32, torch.float32, torch.float64
+        self.raw = pin((max_points, 4), f32)
+        self.offs = pin((max_scans + 1,), i32)
+        self.buf = {"cloud_size": pin((max_scans,), i32), "scan_start": pin((max_scans, 64), i32), "scan_end": pin((max_scans, 64), i32),
+                    "groundparam": pin((max_scans, 11), f64), "ground_size": pin((max_scans,), i32), "inten_merged": pin((max_scans,), i32)}
+        if labels:
+            self.buf["label"] = pin((max_points + 8 * max_scans,), i32)
+        for name, per_seg, has_w in _LISTS:
+            self.buf[name] = pin((max_scans, n_rings * 6 * per_seg), i32)
+            self.buf["n_" + name] = pin((max_scans,), i32)
+            if has_w:
+                self.buf[name + "_w"] = pin((max_scans, n_rings * 6 * per_seg), f32)
+        self.n = 0
+        self.total = 0
+        L = api.lib()
+        L.rgc_feat_extract.argtypes = [C.c_void_p, C.POINTER(_Batch), C.POINTER(_Out)]
+
+    def load(self, scans):
+        """concatenate `scans` (list of (n_i, 4) float32 arrays) into the pinned input buffer"""
+        import torch
+        self.n = len(scans)
+        assert self.n <= self.max_scans
+        o = 0
+        offs = [0]
+        for s in scans:
+            m = len(s)
+            assert o + m <= self.max_points
+            self.raw[o:o + m] = torch.from_numpy(np.ascontiguousarray(s[:, :4], np.float32))
+            o += m
+            offs.append(o)
+        self.offs[:self.n + 1] = torch.tensor(offs, dtype=torch.int32)
+        self.total = o
+
+    @property
+    def h2d_bytes(self):
+        return 16 * self.total + 4 * (self.n + 1)
+
+    @property
+    def d2h_bytes(self):
+        nb, tot = self.n, self.total + 8 * self.n
+        b = 0
+        for k, t in self.buf.items():
+            per = t[0].numel() * t.element_size() if t.dim() > 1 else t.element_size()
+            b += (tot if k == "label" else nb) * per
+        return b
+
+    def run(self) -> float:
+        """one rgc_feat_extract call on the loaded batch; returns the device time (ms) of its kernels"""
+        batch = _Batch(self.raw.data_ptr(), self.offs.data_ptr(), self.n, self.n_rings, self.prm[0], self.prm[1], self.prm[2])
+        out = _Out()
+        for k, t in self.buf.items():
+            setattr(out, k, t.data_ptr())
+        self.ctx.check(api.lib().rgc_feat_extract(self.ctx._h, C.byref(batch), C.byref(out)))
+        return float(out.device_ms)
+
+    def result(self, b: int) -> dict:
+        """views of scan b's outputs (valid until the next run)"""
+        o0 = int(self.offs[b]) + 8 * b
+        m = int(self.buf["cloud_size"][b])
+        d = {"cloud_size": m, "groundparam": self.buf["groundparam"][b].numpy(), "ground_size": int(self.buf["ground_size"][b]),
+             "inten_merged": int(self.buf["inten_merged"][b]), "scan_start": self.buf["scan_start"][b, :self.n_rings].numpy(),
+             "scan_end": self.buf["scan_end"][b, :self.n_rings].numpy()}
+        if "label" in self.buf:
+            d["label"] = self.buf["label"][o0:o0 + m].numpy()
+        for name, per_seg, has_w in _LISTS:
+            c = int(self.buf["n_" + name][b])
+            d[name] = self.buf[name][b, :c].numpy()
+            if has_w:
+                d[name + "_w"] = self.buf[name + "_w"][b, :c].numpy()
+        return d
+
+    def close(self):
+        self.buf = {}
+        self.raw = self.offs = None
