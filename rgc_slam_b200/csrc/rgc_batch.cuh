@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(kThreads, RGC_CORR_MINB) k_bcorrespond(GridVie
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 4) k_blinearize(const float4* __restrict__ tgt_pts, const float4* __restrict__ src, const double* __restrict__ src_cov,
+__global__ void __launch_bounds__(kThreads, RGC_LIN_MINB) k_blinearize(const float4* __restrict__ tgt_pts, const float4* __restrict__ src, const double* __restrict__ src_cov,
                                                             const double* __restrict__ tgt_cov, const BPairInfo* __restrict__ info, const int* __restrict__ blk_pair,
                                                             const BPairRound* __restrict__ rounds, const int* __restrict__ corr0, const int* __restrict__ corr1,
                                                             double* __restrict__ maha0, double* __restrict__ maha1, double* __restrict__ partials,
@@ -117,24 +117,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_blinearize(const float4* __rest
   double acc[kLinN];
 #pragma unroll
   for (int j = 0; j < kLinN; j++) acc[j] = 0.0;
-  const int n_src = pi.src_hi - pi.src_lo;
-  for (int il = vb * kThreads + threadIdx.x; il < n_src; il += pi.nblk * kThreads) {
-    const int i = pi.src_lo + il;
-    const int pos = __ldg(&corr[i]);
-    if (pos >= 0) {
-      const float4 p = __ldg(&src[i]);
-      const float4 q = __ldg(&tgt_pts[pos]);
-      const Sym3 CA = load_sym3(src_cov, i);
-      const Sym3 CB = load_sym3(tgt_cov, pos);
-      const Sym3 M = gicp_mahalanobis(Td, CA, CB);
-      store_sym3(maha, i, M);
-      if (want_hb)
-        gicp_point_terms(Td, M, p.x, p.y, p.z, q.x, q.y, q.z, acc);
-      else
-        acc[0] += gicp_error_term(Td, M, p.x, p.y, p.z, q.x, q.y, q.z);
-      acc[kAccN] += 1.0;
-    }
-  }
+  linearize_points(tgt_pts, src, src_cov, tgt_cov, corr, maha, Td, want_hb, pi.src_lo, vb * kThreads + threadIdx.x, pi.nblk * kThreads, pi.src_hi - pi.src_lo, acc);
   grid_reduce_at<kLinN>(acc, partials + (size_t)pi.blk0 * kLinN, (unsigned)vb, (unsigned)pi.nblk, tickets + pair, results + (size_t)pair * 32);
 }
 
@@ -153,17 +136,7 @@ __global__ void __launch_bounds__(kThreads) k_bcompute_error(const float4* __res
   const int* corr = pr->rsel ? corr1 : corr0;
   const double* maha = pr->rsel ? maha1 : maha0;
   double acc[1] = {0.0};
-  const int n_src = pi.src_hi - pi.src_lo;
-  for (int il = vb * kThreads + threadIdx.x; il < n_src; il += pi.nblk * kThreads) {
-    const int i = pi.src_lo + il;
-    const int pos = __ldg(&corr[i]);
-    if (pos >= 0) {
-      const float4 p = __ldg(&src[i]);
-      const float4 q = __ldg(&tgt_pts[pos]);
-      const Sym3 M = load_sym3(maha, i);
-      acc[0] += gicp_error_term(Td, M, p.x, p.y, p.z, q.x, q.y, q.z);
-    }
-  }
+  compute_error_points(tgt_pts, src, corr, maha, Td, pi.src_lo, vb * kThreads + threadIdx.x, pi.nblk * kThreads, pi.src_hi - pi.src_lo, acc);
   grid_reduce_at<1>(acc, partials + (size_t)pi.blk0, (unsigned)vb, (unsigned)pi.nblk, tickets + pair, results + pair);
 }
 

@@ -1132,47 +1132,98 @@ __global__ void __launch_bounds__(kThreads, RGC_CORR_MINB) k_correspond(GridView
 // per correspondence M = (C_B + R C_A R^T)^-1 (stored for compute_error), e^T M e, the 21 unique
 // entries of H = J^T M J and b = J^T M e, reduced deterministically.  Streams p, C_A, corr; gathers
 // q, C_B; writes M: 184 algorithmic bytes per source point -> HBM-bound once the batch exceeds L2.
-__global__ void __launch_bounds__(kThreads, 4) k_linearize(const float4* __restrict__ tgt_pts, const float4* __restrict__ src, const double* __restrict__ src_cov,
+//
+// The loop over a thread's points (local index il = first, first + stride, ... < n; global = base + il) is
+// software-pipelined: corr[] is read two points ahead and p, C_A and the dependent gathers q, C_B one point
+// ahead, so the loads of the next point are in flight while the ~400 fp64 instructions of the current one
+// issue (the unpipelined loop ran the memory phase and the arithmetic phase of all 16 warps of an SM back to
+// back: 52 % of HBM peak at 2 M points, profiles/README.md).  The terms are added in ascending il, as before.
+#ifndef RGC_LIN_MINB
+#define RGC_LIN_MINB 3
+#endif
+struct LinPoint {
+  float4 p, q;
+  Sym3 CA, CB;
+};
+__device__ __forceinline__ void lin_load(LinPoint& d, const float4* __restrict__ tgt_pts, const float4* __restrict__ src, const double* __restrict__ src_cov,
+                                         const double* __restrict__ tgt_cov, int i, int pos) {
+  d.p = __ldg(&src[i]);
+  d.q = __ldg(&tgt_pts[pos]);
+  d.CA = load_sym3(src_cov, i);
+  d.CB = load_sym3(tgt_cov, pos);
+}
+__device__ __forceinline__ void linearize_points(const float4* __restrict__ tgt_pts, const float4* __restrict__ src, const double* __restrict__ src_cov,
+                                                 const double* __restrict__ tgt_cov, const int* __restrict__ corr, double* __restrict__ maha, const Rt& Td,
+                                                 int want_hb, int base, int first, int stride, int n, double* acc) {
+  int il = first;
+  int c1 = il < n ? __ldg(&corr[base + il]) : -1;
+  int c2 = il + stride < n ? __ldg(&corr[base + il + stride]) : -1;
+  LinPoint cur, nxt;
+  if (c1 >= 0) lin_load(cur, tgt_pts, src, src_cov, tgt_cov, base + il, c1);
+  while (il < n) {
+    const int iln = il + stride;
+    const int c3 = (iln + stride < n) ? __ldg(&corr[base + iln + stride]) : -1;
+    if (c2 >= 0) lin_load(nxt, tgt_pts, src, src_cov, tgt_cov, base + iln, c2);
+    if (c1 >= 0) {
+      const Sym3 M = gicp_mahalanobis(Td, cur.CA, cur.CB);
+      store_sym3(maha, base + il, M);
+      if (want_hb)
+        gicp_point_terms(Td, M, cur.p.x, cur.p.y, cur.p.z, cur.q.x, cur.q.y, cur.q.z, acc);
+      else
+        acc[0] = dadd(acc[0], gicp_error_term(Td, M, cur.p.x, cur.p.y, cur.p.z, cur.q.x, cur.q.y, cur.q.z));
+      acc[kAccN] += 1.0;
+    }
+    cur = nxt;
+    c1 = c2;
+    c2 = c3;
+    il = iln;
+  }
+}
+__global__ void __launch_bounds__(kThreads, RGC_LIN_MINB) k_linearize(const float4* __restrict__ tgt_pts, const float4* __restrict__ src, const double* __restrict__ src_cov,
                                                            const double* __restrict__ tgt_cov, int n_src, Rt Td, int want_hb, const int* __restrict__ corr,
                                                            double* __restrict__ maha, double* __restrict__ partials, unsigned int* __restrict__ ticket,
                                                            double* __restrict__ result, DoneFlag done, int* __restrict__ zero_me) {
   double acc[kLinN];
 #pragma unroll
   for (int j = 0; j < kLinN; j++) acc[j] = 0.0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_src; i += gridDim.x * blockDim.x) {
-    const int pos = __ldg(&corr[i]);
-    if (pos >= 0) {
-      const float4 p = __ldg(&src[i]);
-      const float4 q = __ldg(&tgt_pts[pos]);
-      const Sym3 CA = load_sym3(src_cov, i);
-      const Sym3 CB = load_sym3(tgt_cov, pos);
-      const Sym3 M = gicp_mahalanobis(Td, CA, CB);
-      store_sym3(maha, i, M);
-      if (want_hb)
-        gicp_point_terms(Td, M, p.x, p.y, p.z, q.x, q.y, q.z, acc);
-      else
-        acc[0] += gicp_error_term(Td, M, p.x, p.y, p.z, q.x, q.y, q.z);
-      acc[kAccN] += 1.0;
-    }
-  }
+  linearize_points(tgt_pts, src, src_cov, tgt_cov, corr, maha, Td, want_hb, 0, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, n_src, acc);
   grid_reduce<kLinN>(acc, partials, ticket, result, done, zero_me);
 }
 
-// fast_gicp_impl.hpp:214-237 — correspondences and M frozen from the last k_linearize
+// fast_gicp_impl.hpp:214-237 — correspondences and M frozen from the last k_linearize.  Same pipelining.
+struct CePoint {
+  float4 p, q;
+  Sym3 M;
+};
+__device__ __forceinline__ void compute_error_points(const float4* __restrict__ tgt_pts, const float4* __restrict__ src, const int* __restrict__ corr,
+                                                     const double* __restrict__ maha, const Rt& Td, int base, int first, int stride, int n, double* acc) {
+  int il = first;
+  int c1 = il < n ? __ldg(&corr[base + il]) : -1;
+  int c2 = il + stride < n ? __ldg(&corr[base + il + stride]) : -1;
+  CePoint cur, nxt;
+  auto load = [&](CePoint& d, int i, int pos) {
+    d.p = __ldg(&src[i]);
+    d.q = __ldg(&tgt_pts[pos]);
+    d.M = load_sym3(maha, i);
+  };
+  if (c1 >= 0) load(cur, base + il, c1);
+  while (il < n) {
+    const int iln = il + stride;
+    const int c3 = (iln + stride < n) ? __ldg(&corr[base + iln + stride]) : -1;
+    if (c2 >= 0) load(nxt, base + iln, c2);
+    if (c1 >= 0) acc[0] = dadd(acc[0], gicp_error_term(Td, cur.M, cur.p.x, cur.p.y, cur.p.z, cur.q.x, cur.q.y, cur.q.z));
+    cur = nxt;
+    c1 = c2;
+    c2 = c3;
+    il = iln;
+  }
+}
 __global__ void __launch_bounds__(kThreads) k_compute_error(const float4* __restrict__ tgt_pts, const float4* __restrict__ src, int n_src, Rt Td,
                                                             const int* __restrict__ corr, const double* __restrict__ maha,
                                                             double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ result,
                                                             DoneFlag done) {
   double acc[1] = {0.0};
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_src; i += gridDim.x * blockDim.x) {
-    const int pos = __ldg(&corr[i]);
-    if (pos >= 0) {
-      const float4 p = __ldg(&src[i]);
-      const float4 q = __ldg(&tgt_pts[pos]);
-      const Sym3 M = load_sym3(maha, i);
-      acc[0] += gicp_error_term(Td, M, p.x, p.y, p.z, q.x, q.y, q.z);
-    }
-  }
+  compute_error_points(tgt_pts, src, corr, maha, Td, 0, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, n_src, acc);
   grid_reduce<1>(acc, partials, ticket, result, done);
 }
 

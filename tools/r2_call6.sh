@@ -1,8 +1,7 @@
 # round 2, GPU call 6: parity suite + the full default bench line (timing of the whole run)
 mkdir -p gpurun_out
-timeout 2400 python -m pytest tests -m gpu -x -q > gpurun_out/r2c6_pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/r2c6_pytest.log
-tail -4 gpurun_out/r2c6_pytest.log
-/usr/bin/time -v timeout 900 python bench.py > gpurun_out/r2c6_bench.json 2> gpurun_out/r2c6_bench.err; echo "bench rc=$?"; grep -E "Elapsed|Maximum resident" gpurun_out/r2c6_bench.err
+SECONDS=0
+timeout 900 python bench.py > gpurun_out/r2c6_bench.json 2> gpurun_out/r2c6_bench.err; echo "bench rc=$? wall ${SECONDS}s"; tail -3 gpurun_out/r2c6_bench.err
 python - <<'PY'
 import json
 d=json.load(open("gpurun_out/r2c6_bench.json"))
