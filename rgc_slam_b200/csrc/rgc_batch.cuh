@@ -142,15 +142,20 @@ __global__ void __launch_bounds__(kThreads) k_bcompute_error(const float4* __res
 
 // getFitnessScore of every pair at its final transformation: the thread layout of k_fitness (sparse warps
 // for small clouds included) replayed per pair, so the sums come out bit-identical
+// final_Tf: 16 floats per pair — the final transformation (12) and, as int bits, the buffer set holding the
+// pair's last correspondences (hints, see k_fitness) or -1
 __global__ void __launch_bounds__(kThreads, RGC_CORR_MINB) k_bfitness(GridView tgt, const float4* __restrict__ src, const BPairInfo* __restrict__ info,
                                                                      const int* __restrict__ fblk_pair, const float* __restrict__ final_Tf, double max_range,
+                                                                     const int* __restrict__ corr0, const int* __restrict__ corr1,
                                                                      double* __restrict__ partials, unsigned int* __restrict__ tickets, double* __restrict__ results) {
   const int pair = fblk_pair[blockIdx.x];
   const BPairInfo pi = info[pair];
   const int vb = blockIdx.x - pi.fblk0;
   float Tf[12];
 #pragma unroll
-  for (int j = 0; j < 12; j++) Tf[j] = final_Tf[pair * 12 + j];
+  for (int j = 0; j < 12; j++) Tf[j] = final_Tf[pair * 16 + j];
+  const int hsel = __float_as_int(final_Tf[pair * 16 + 12]);
+  const int* hint = hsel < 0 ? nullptr : (hsel ? corr1 : corr0);
   double acc[2] = {0.0, 0.0};
   const int gt = vb * kThreads + threadIdx.x;
   const int il = gt / pi.spread;
@@ -161,7 +166,7 @@ __global__ void __launch_bounds__(kThreads, RGC_CORR_MINB) k_bfitness(GridView t
     Best1 top;
     top.reset(1, INFINITY);
     const CloudRange cr{pi.tgt_lo, pi.tgt_hi, pi.tgt_prefix};
-    knn_search(tgt, qx, qy, qz, 1, INFINITY, -1, top, nullptr, &cr);
+    knn_search(tgt, qx, qy, qz, 1, INFINITY, hint ? __ldg(&hint[pi.src_lo + il]) : -1, top, nullptr, &cr);
     if (top.id0 >= 0 && (double)top.d0 <= max_range) {
       acc[0] = (double)top.d0;
       acc[1] = 1.0;

@@ -50,14 +50,30 @@ struct Pinned {
   bool alloc(size_t bytes) { return cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess; }
 };
 
-static int batch_chunk(rgc_ctx* c, const rgc_params& prm, const rgc_pair* pairs, int B, int want_fitness, double max_range, bool lazy, rgc_pair_result* out) {
-  cudaStream_t st = c->stream;
-  cudaEvent_t ev[8];
-  for (int i = 0; i < 8; i++) ev[i] = c->ev[i];
-  const int k = prm.k_correspondences;
+// the inputs of one chunk on the device: raw records uploaded and converted on the side lane (so that the
+// upload of chunk i + 1 overlaps the LM rounds of chunk i), then handed to the main stream through `ready`
+struct ChunkIn {
+  Scratch tmp;
+  int B = 0, S = 0, Tn = 0;
+  std::vector<int> soff, toff;
+  float4 *pts_s = nullptr, *pts_t = nullptr;
+  cudaEvent_t begin = nullptr, ready = nullptr;
+  rgc_ctx* c;
+  explicit ChunkIn(rgc_ctx* c_) : tmp(c_), c(c_) {}
+  ~ChunkIn() {
+    c->put_event(begin);
+    c->put_event(ready);
+  }
+};
 
-  // ---- layout of the chunk
-  std::vector<int> soff(B + 1, 0), toff(B + 1, 0);
+static int chunk_upload(rgc_ctx* c, const rgc_pair* pairs, int B, std::unique_ptr<ChunkIn>& out) {
+  out.reset(new ChunkIn(c));
+  ChunkIn& in = *out;
+  LaneScope lane(c, c->overlap ? 1 : 0);
+  cudaStream_t st = c->stream;
+  in.B = B;
+  in.soff.assign(B + 1, 0);
+  in.toff.assign(B + 1, 0);
   std::vector<BCloudSrc> scs(B), tcs(B);
   size_t sbytes = 0, tbytes = 0;
   for (int p = 0; p < B; p++) {
@@ -65,41 +81,55 @@ static int batch_chunk(rgc_ctx* c, const rgc_params& prm, const rgc_pair* pairs,
     if (!q.source || !q.target || q.n_source == 0 || q.n_target == 0) FAIL(c, RGC_ERR_INVALID, "empty point cloud in the batch");
     if (q.source_stride < 12 || q.source_stride % 4 || q.target_stride < 12 || q.target_stride % 4)
       FAIL(c, RGC_ERR_INVALID, "point stride must be a multiple of 4 and >= 12 bytes");
-    if ((size_t)soff[p] + q.n_source > 0x7fffffffu / 32 || (size_t)toff[p] + q.n_target > 0x7fffffffu / 32)
+    if ((size_t)in.soff[p] + q.n_source > 0x7fffffffu / 32 || (size_t)in.toff[p] + q.n_target > 0x7fffffffu / 32)
       FAIL(c, RGC_ERR_UNSUPPORTED, "chunk too large for 32-bit indexing");
-    soff[p + 1] = soff[p] + (int)q.n_source;
-    toff[p + 1] = toff[p] + (int)q.n_target;
+    in.soff[p + 1] = in.soff[p] + (int)q.n_source;
+    in.toff[p + 1] = in.toff[p] + (int)q.n_target;
     scs[p] = BCloudSrc{(unsigned long long)sbytes, (unsigned)q.source_stride, 0u};
     tcs[p] = BCloudSrc{(unsigned long long)tbytes, (unsigned)q.target_stride, 0u};
     sbytes += q.n_source * q.source_stride;
     tbytes += q.n_target * q.target_stride;
   }
-  const int S = soff[B], Tn = toff[B];
-
-  // ---- upload + ingest: raw records -> one float4 array per side
-  Scratch tmp(c);
-  CK(c, cudaEventRecord(ev[0], st));
-  unsigned char* raw_s = (unsigned char*)tmp.get(sbytes);
-  unsigned char* raw_t = (unsigned char*)tmp.get(tbytes);
-  float4* pts_s = (float4*)tmp.get(sizeof(float4) * (size_t)S);
-  float4* pts_t = (float4*)tmp.get(sizeof(float4) * (size_t)Tn);
-  BCloudSrc* d_scs = (BCloudSrc*)tmp.get(sizeof(BCloudSrc) * (size_t)B);
-  BCloudSrc* d_tcs = (BCloudSrc*)tmp.get(sizeof(BCloudSrc) * (size_t)B);
-  int* d_soff = (int*)tmp.get(sizeof(int) * (size_t)(B + 1));
-  int* d_toff = (int*)tmp.get(sizeof(int) * (size_t)(B + 1));
-  if (!raw_s || !raw_t || !pts_s || !pts_t || !d_scs || !d_tcs || !d_soff || !d_toff) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (batch staging)");
+  const int S = in.S = in.soff[B], Tn = in.Tn = in.toff[B];
+  in.begin = c->get_event();
+  in.ready = c->get_event();
+  if (!in.begin || !in.ready) FAIL(c, RGC_ERR_CUDA, "cudaEventCreate failed");
+  CK(c, cudaEventRecord(in.begin, st));
+  unsigned char* raw_s = (unsigned char*)in.tmp.get(sbytes);
+  unsigned char* raw_t = (unsigned char*)in.tmp.get(tbytes);
+  in.pts_s = (float4*)in.tmp.get(sizeof(float4) * (size_t)S);
+  in.pts_t = (float4*)in.tmp.get(sizeof(float4) * (size_t)Tn);
+  BCloudSrc* d_scs = (BCloudSrc*)in.tmp.get(sizeof(BCloudSrc) * (size_t)B);
+  BCloudSrc* d_tcs = (BCloudSrc*)in.tmp.get(sizeof(BCloudSrc) * (size_t)B);
+  int* d_soff = (int*)in.tmp.get(sizeof(int) * (size_t)(B + 1));
+  int* d_toff = (int*)in.tmp.get(sizeof(int) * (size_t)(B + 1));
+  if (!raw_s || !raw_t || !in.pts_s || !in.pts_t || !d_scs || !d_tcs || !d_soff || !d_toff) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (batch staging)");
   for (int p = 0; p < B; p++) {
     CK(c, cudaMemcpyAsync(raw_s + scs[p].byte_off, pairs[p].source, pairs[p].n_source * pairs[p].source_stride, cudaMemcpyHostToDevice, st));
     CK(c, cudaMemcpyAsync(raw_t + tcs[p].byte_off, pairs[p].target, pairs[p].n_target * pairs[p].target_stride, cudaMemcpyHostToDevice, st));
   }
   CK(c, cudaMemcpyAsync(d_scs, scs.data(), sizeof(BCloudSrc) * (size_t)B, cudaMemcpyHostToDevice, st));
   CK(c, cudaMemcpyAsync(d_tcs, tcs.data(), sizeof(BCloudSrc) * (size_t)B, cudaMemcpyHostToDevice, st));
-  CK(c, cudaMemcpyAsync(d_soff, soff.data(), sizeof(int) * (size_t)(B + 1), cudaMemcpyHostToDevice, st));
-  CK(c, cudaMemcpyAsync(d_toff, toff.data(), sizeof(int) * (size_t)(B + 1), cudaMemcpyHostToDevice, st));
-  k_bingest<<<div_up(S, 256), 256, 0, st>>>(raw_s, d_scs, d_soff, B, S, pts_s);
+  CK(c, cudaMemcpyAsync(d_soff, in.soff.data(), sizeof(int) * (size_t)(B + 1), cudaMemcpyHostToDevice, st));
+  CK(c, cudaMemcpyAsync(d_toff, in.toff.data(), sizeof(int) * (size_t)(B + 1), cudaMemcpyHostToDevice, st));
+  k_bingest<<<div_up(S, 256), 256, 0, st>>>(raw_s, d_scs, d_soff, B, S, in.pts_s);
   CKL(c);
-  k_bingest<<<div_up(Tn, 256), 256, 0, st>>>(raw_t, d_tcs, d_toff, B, Tn, pts_t);
+  k_bingest<<<div_up(Tn, 256), 256, 0, st>>>(raw_t, d_tcs, d_toff, B, Tn, in.pts_t);
   CKL(c);
+  CK(c, cudaEventRecord(in.ready, st));
+  return RGC_OK;
+}
+
+static int batch_chunk(rgc_ctx* c, const rgc_params& prm, const rgc_pair* pairs, ChunkIn& in, int want_fitness, double max_range, bool lazy, rgc_pair_result* out) {
+  cudaStream_t st = c->stream;
+  cudaEvent_t ev[8];
+  for (int i = 0; i < 8; i++) ev[i] = c->ev[i];
+  const int k = prm.k_correspondences;
+  const int B = in.B, S = in.S, Tn = in.Tn;
+  const std::vector<int>&soff = in.soff, &toff = in.toff;
+  float4 *pts_s = in.pts_s, *pts_t = in.pts_t;
+  Scratch tmp(c);
+  CK(c, cudaStreamWaitEvent(st, in.ready, 0));
   CK(c, cudaEventRecord(ev[1], st));
 
   // ---- the two multi-cloud grids
@@ -171,7 +201,7 @@ static int batch_chunk(rgc_ctx* c, const rgc_params& prm, const rgc_pair* pairs,
   double* fit_partials = (double*)tmp.get(sizeof(double) * 2 * (size_t)std::max(nfblk, 1));
   unsigned int* tickets = (unsigned int*)tmp.get(sizeof(unsigned int) * 3 * (size_t)B);  // linearize | compute_error | fitness
   double* d_res = (double*)tmp.get(sizeof(double) * 36 * (size_t)B);                     // per pair: 32 linearize | then B compute_error | 2B fitness
-  float* d_final = (float*)tmp.get(sizeof(float) * 12 * (size_t)B);
+  float* d_final = (float*)tmp.get(sizeof(float) * 16 * (size_t)B);
   if (!d_info || !d_blk_pair || !d_fblk_pair || !d_rounds || !corr[1] || !sqd[1] || !maha[1] || !corr[0] || !sqd[0] || !maha[0] || !need_list || !need_nbr ||
       !need_count || !lin_partials || !ce_partials || !fit_partials || !tickets || !d_res || !d_final)
     FAIL(c, RGC_ERR_NOMEM, "device allocation failed (batch work buffers)");
@@ -179,7 +209,7 @@ static int batch_chunk(rgc_ctx* c, const rgc_params& prm, const rgc_pair* pairs,
   double* d_ce_res = d_res + 32 * (size_t)B;       // B
   double* d_fit_res = d_res + 33 * (size_t)B;      // B x 2
   Pinned pin;
-  const size_t pin_bytes = sizeof(BPairRound) * (size_t)B + sizeof(double) * 36 * (size_t)B + sizeof(float) * 12 * (size_t)B;
+  const size_t pin_bytes = sizeof(BPairRound) * (size_t)B + sizeof(double) * 36 * (size_t)B + sizeof(float) * 16 * (size_t)B;
   if (!pin.alloc(pin_bytes)) FAIL(c, RGC_ERR_NOMEM, "pinned allocation failed (batch)");
   BPairRound* h_rounds = (BPairRound*)pin.p;
   double* h_res = (double*)(h_rounds + B);
@@ -366,18 +396,23 @@ static int batch_chunk(rgc_ctx* c, const rgc_params& prm, const rgc_pair* pairs,
   CK(c, cudaEventRecord(ev[5], st));
 
   // ---- getFitnessScore at the final transformations
-  for (int p = 0; p < B; p++)
-    for (int i = 0; i < 12; i++) h_final[p * 12 + i] = (float)lm[p].x0[i];  // final_transformation_ = x0.cast<float>()
+  for (int p = 0; p < B; p++) {
+    for (int i = 0; i < 12; i++) h_final[p * 16 + i] = (float)lm[p].x0[i];  // final_transformation_ = x0.cast<float>()
+    const int hsel = lm[p].n_lin > 0 ? lm[p].cur : -1;
+    std::memcpy(&h_final[p * 16 + 12], &hsel, sizeof(int));
+  }
   if (want_fitness) {
-    CK(c, cudaMemcpyAsync(d_final, h_final, sizeof(float) * 12 * (size_t)B, cudaMemcpyHostToDevice, st));
-    k_bfitness<<<nfblk, kThreads, 0, st>>>(tgts.view, srcs.sorted, d_info, d_fblk_pair, d_final, max_range, fit_partials, tickets + 2 * B, d_fit_res);
+    CK(c, cudaMemcpyAsync(d_final, h_final, sizeof(float) * 16 * (size_t)B, cudaMemcpyHostToDevice, st));
+    k_bfitness<<<nfblk, kThreads, 0, st>>>(tgts.view, srcs.sorted, d_info, d_fblk_pair, d_final, max_range, corr[0], corr[1], fit_partials, tickets + 2 * B,
+                                           d_fit_res);
     CKL(c);
     CK(c, cudaMemcpyAsync(h_res + 33 * (size_t)B, d_fit_res, sizeof(double) * 2 * (size_t)B, cudaMemcpyDeviceToHost, st));
   }
   CK(c, cudaEventRecord(ev[6], st));
   CK(c, cudaEventSynchronize(ev[6]));
   float ms[6];
-  for (int i = 0; i < 6; i++) CK(c, cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+  CK(c, cudaEventElapsedTime(&ms[0], in.begin, in.ready));  // on the side lane: overlaps the previous chunk's rounds
+  for (int i = 1; i < 6; i++) CK(c, cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
   float total = 0.f;
   for (int i = 0; i < 6; i++) {
     g_batch_stats.ms[i] += ms[i];
@@ -427,8 +462,10 @@ int rgc_batch_align(rgc_ctx* c, const rgc_params* prm_in, const rgc_pair* pairs,
   g_batch_stats = BatchStats();
   const bool lazy = std::getenv("RGC_EAGER_TARGET_COV") == nullptr;
   const size_t max_points = 24u << 20;
-  size_t first = 0;
-  while (first < n_pairs) {
+  // chunk boundaries first, then a two-stage pipeline: the upload + ingest of chunk i + 1 is queued on the side
+  // lane before the (host-synchronous) LM rounds of chunk i start on the main stream
+  std::vector<std::pair<size_t, size_t>> chunks;
+  for (size_t first = 0; first < n_pairs;) {
     size_t pts = 0, cnt = 0;
     while (first + cnt < n_pairs && (max_chunk_pairs <= 0 || (int)cnt < max_chunk_pairs) && cnt < 255) {
       const size_t add = pairs[first + cnt].n_source + pairs[first + cnt].n_target;
@@ -436,8 +473,15 @@ int rgc_batch_align(rgc_ctx* c, const rgc_params* prm_in, const rgc_pair* pairs,
       pts += add;
       cnt++;
     }
-    TRY(batch_chunk(c, prm, pairs + first, (int)cnt, want_fitness, fitness_max_range, lazy, out + first));
+    chunks.push_back({first, cnt});
     first += cnt;
+  }
+  std::unique_ptr<ChunkIn> cur, nxt;
+  if (!chunks.empty()) TRY(chunk_upload(c, pairs + chunks[0].first, (int)chunks[0].second, cur));
+  for (size_t i = 0; i < chunks.size(); i++) {
+    if (i + 1 < chunks.size()) TRY(chunk_upload(c, pairs + chunks[i + 1].first, (int)chunks[i + 1].second, nxt));
+    TRY(batch_chunk(c, prm, pairs + chunks[i].first, *cur, want_fitness, fitness_max_range, lazy, out + chunks[i].first));
+    cur = std::move(nxt);
   }
   return RGC_OK;
 }

@@ -1507,7 +1507,8 @@ int rgc_reg_fitness(rgc_reg* r, double max_range, double* score) {
   const int spread = query_spread(r->src.n);
   const int blocks = div_up(r->src.n * spread, kThreads);
   TRY(reg_ensure_fitness(r, blocks));
-  k_fitness<<<blocks, kThreads, 0, c->stream>>>(r->tgt.view, r->src.sorted, r->src.n, spread, Tf, max_range, r->slab, r->fit_partials, c->d_ticket,
+  const int* hint = (!r->vgicp && r->have_corr && r->corr) ? r->corr : nullptr;  // correspondences of the last linearize (same clouds)
+  k_fitness<<<blocks, kThreads, 0, c->stream>>>(r->tgt.view, r->src.sorted, r->src.n, spread, Tf, max_range, r->slab, hint, r->fit_partials, c->d_ticket,
                                                 reg_result_ptr(r), reg_next_done(r));
   CKL(c);
   TRY(reg_finish_reduce(r, 2));

@@ -1016,20 +1016,31 @@ __device__ __forceinline__ void grid_reduce_at(double* v, double* __restrict__ p
   __syncthreads();
   if (is_last) {
     __threadfence();
-    // final pass: value j is summed by the kThreads/32 lanes (j, group g) over blocks b = g, g+G, ...
-    // in ascending order, then the G group sums are added in group order: a fixed order for a
-    // given grid size, whichever block happens to run last.
-    constexpr int G = kThreads / 32;
-    const int j = threadIdx.x & 31, grp = threadIdx.x >> 5;
-    double s = 0.0;
-    if (j < NV)
-      for (unsigned b = grp; b < n_blocks; b += G) s += __ldcg(&partials[(size_t)b * NV + j]);
-    if (j < NV) sm[grp][j] = s;
+    // final pass, all threads: thread t adds the partials of blocks t, t + kThreads, ... (all NV values of a
+    // block at a time: short chains of independent loads), then the same warp tree / warp-order sum as above
+    // combines the kThreads per-thread sums — a fixed order for a given n_blocks, whichever block runs last.
+    // (The first version gave each value to 4 threads that walked n_blocks / 4 partials one dependent add
+    // after the other: ~7 us of a 13 us compute_error on one sweep, ~20 us of 110 us at 2 M points.)
+#pragma unroll
+    for (int j = 0; j < NV; j++) v[j] = 0.0;
+    for (unsigned b = threadIdx.x; b < n_blocks; b += kThreads) {
+      const double* pb = partials + (size_t)b * NV;
+#pragma unroll
+      for (int j = 0; j < NV; j++) v[j] += __ldcg(pb + j);
+    }
+    __syncthreads();  // sm is reused
+#pragma unroll
+    for (int j = 0; j < NV; j++) {
+      double x = v[j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+      if (lane == 0) sm[warp][j] = x;
+    }
     __syncthreads();
     if (threadIdx.x < NV) {
       double tot = sm[0][threadIdx.x];
 #pragma unroll
-      for (int w = 1; w < G; w++) tot += sm[w][threadIdx.x];
+      for (int w = 1; w < kThreads / 32; w++) tot += sm[w][threadIdx.x];
       result[threadIdx.x] = tot;
     }
     __threadfence_system();
@@ -1139,7 +1150,7 @@ __global__ void __launch_bounds__(kThreads, RGC_CORR_MINB) k_correspond(GridView
 // issue (the unpipelined loop ran the memory phase and the arithmetic phase of all 16 warps of an SM back to
 // back: 52 % of HBM peak at 2 M points, profiles/README.md).  The terms are added in ascending il, as before.
 #ifndef RGC_LIN_MINB
-#define RGC_LIN_MINB 3
+#define RGC_LIN_MINB 4
 #endif
 struct LinPoint {
   float4 p, q;
@@ -1227,10 +1238,12 @@ __global__ void __launch_bounds__(kThreads) k_compute_error(const float4* __rest
   grid_reduce<1>(acc, partials, ticket, result, done);
 }
 
-// pcl::Registration::getFitnessScore: [sum d2, count] over 1-NN d2 <= max_range
+// pcl::Registration::getFitnessScore: [sum d2, count] over 1-NN d2 <= max_range.  `hint` (nullable): the
+// correspondences of the last linearize — the final pose is next to that one, so the old neighbour is a tight
+// first bound (any real point is a valid bound: the result is the same exact nearest neighbour)
 __global__ void __launch_bounds__(kThreads, RGC_CORR_MINB) k_fitness(GridView tgt, const float4* __restrict__ src, int n_src, int spread, RtF Tf, double max_range, Slab slab,
-                                                      double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ result,
-                                                      DoneFlag done) {
+                                                      const int* __restrict__ hint, double* __restrict__ partials, unsigned int* __restrict__ ticket,
+                                                      double* __restrict__ result, DoneFlag done) {
   double acc[2] = {0.0, 0.0};
   const int gt = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = gt / spread;
@@ -1240,7 +1253,7 @@ __global__ void __launch_bounds__(kThreads, RGC_CORR_MINB) k_fitness(GridView tg
     transform_f(Tf.m, p.x, p.y, p.z, qx, qy, qz);
     Best1 top;
     top.reset(1, INFINITY);
-    if (slab_owns(slab, qx, qy, qz)) knn_search(tgt, qx, qy, qz, 1, INFINITY, -1, top);
+    if (slab_owns(slab, qx, qy, qz)) knn_search(tgt, qx, qy, qz, 1, INFINITY, hint ? __ldg(&hint[i]) : -1, top);
     if (top.id0 >= 0 && (double)top.d0 <= max_range) {
       acc[0] = (double)top.d0;
       acc[1] = 1.0;
