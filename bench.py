@@ -253,7 +253,7 @@ def run_c4(torch, dist, rgc, local, rank, world, total_pairs):
         return cache[id(a)]
 
     pp = [dict(src=pin(p["src"]), tgt=pin(p["tgt"]), guess=p["guess"]) for p in pairs]
-    batch.align_batch(pp[:min(len(pp), 200)], ctx=ctx, params=prm)  # warm-up with a full-size chunk: the pool's large blocks are cudaMalloc'ed once
+    batch.align_batch(pp, ctx=ctx, params=prm)  # warm-up = the same call once: the pools' large blocks (two chunks in flight) are cudaMalloc'ed here
     ctx.synchronize()
     if world > 1:
         torch.cuda.synchronize()

@@ -49,7 +49,7 @@ def run_batched(pairs, device, chunk=0, pinned=True):
         pp = [dict(src=pin(p["src"]), tgt=pin(p["tgt"]), guess=p["guess"]) for p in pairs]
     else:
         pp = pairs
-    batch.align_batch(pp[:min(len(pp), 200)], ctx=ctx, params=prm)  # warm-up with a full-size chunk: the pool's large blocks are cudaMalloc'ed once
+    batch.align_batch(pp, ctx=ctx, params=prm)  # warm-up = the same call once: the pools' large blocks (two chunks in flight) are cudaMalloc'ed here
     ctx.synchronize()
     t0 = time.perf_counter()
     res = batch.align_batch(pp, ctx=ctx, params=prm, want_fitness=True, max_chunk_pairs=chunk)
