@@ -319,6 +319,12 @@ def run_c5(torch, dist, rgc, local, rank, world):
         e, H, b = gs.linearize(Tg)
         lin.append(time.perf_counter() - t0)
     ar_us = gs.allreduce_us()
+    # the call-site criterion (step < 1e-6 m) is not met in 25 iterations at this size: correspondences keep flipping
+    # and move the optimum by more than that; the library default (5e-4 m, lsq_registration_impl.hpp:13) is
+    gs.setTransformationEpsilon(5e-4)
+    gs.align(case["guess"])
+    default_eps = {"iterations": gs.last_result["iterations"], "converged": gs.hasConverged()}
+    gs.setTransformationEpsilon(1e-6)
     stats = torch.tensor([t_set, t_cold, t_warm, float(np.median(lin)), float(gs.n_local)], dtype=torch.float64, device=f"cuda:{local}")
     dist.all_reduce(stats, op=dist.ReduceOp.MAX)
     out = {"workload": f"C5: 128-beam sweep ({len(case['src'])} pts) vs {len(case['tgt'])}-point map slab-sharded over {world} ranks, corr 2 m, 25 it",
@@ -326,7 +332,7 @@ def run_c5(torch, dist, rgc, local, rank, world):
            "set_target_s_max": float(stats[0].item()), "set_target": "full map from pinned host memory, slab + halo selected on the device, voxel hash built",
            "align_cold_ms_max": 1e3 * float(stats[1].item()), "align_warm_ms_max": 1e3 * float(stats[2].item()),
            "linearize_ms_max": 1e3 * float(stats[3].item()), "iterations": gs.last_result["iterations"], "converged": gs.hasConverged(),
-           "allreduces_per_align": n_ar, "allreduce": gs.allreduce_kind, "allreduce_us": ar_us}
+           "allreduces_per_align": n_ar, "allreduce": gs.allreduce_kind, "allreduce_us": ar_us, "with_default_trans_eps_5e-4": default_eps}
     if rank == 0:  # unsharded on rank 0's GPU: H, b and the final pose must agree
         gu = rgc.FastGICP(ctx)
         gu.setMaximumIterations(25)

@@ -102,6 +102,18 @@ int rgc_comm_create(rgc_ctx* c, const char* id128, int rank, int world, rgc_comm
     FAIL(c, RGC_ERR_NOMEM, "device allocation failed (communicator buffer)");
   }
   CK(c, cudaMemset(m->d_buf, 0, sizeof(double) * 64));
+  // NCCL sets its channels up lazily at the first collective (~1 s): pay that here (rgc_comm_create is itself a
+  // collective), not inside the first align
+  for (int i = 0; i < 2; i++) {
+    const ncclResult_t ar = api->AllReduce(m->d_buf, m->d_buf, 32, ncclDouble, ncclSum, m->comm, c->stream);
+    if (ar != ncclSuccess) {
+      api->CommDestroy(m->comm);
+      cudaFree(m->d_buf);
+      delete m;
+      FAIL(c, RGC_ERR_CUDA, std::string("ncclAllReduce (warm-up): ") + (api->GetErrorString ? api->GetErrorString(ar) : "error"));
+    }
+  }
+  CK(c, cudaStreamSynchronize(c->stream));
   *out = m;
   return RGC_OK;
 }
