@@ -49,9 +49,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += os.environ.get("RGC_NVCC_EXTRA", "").split()  # tuning experiments: -DRGC_KT_PEND=8 ...
-    cmd += ["-o", LIB] + sources()
+    out = os.environ.get("RGC_LIB_OUT", LIB)  # tuning experiments: a variant build beside the product library
+    cmd += ["-o", out] + sources()
     subprocess.check_call(cmd)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

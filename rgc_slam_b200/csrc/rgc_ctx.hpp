@@ -42,11 +42,23 @@ struct rgc_ctx {
   bool side_pending = false;      // lane-1 work not yet joined into the main stream
   bool overlap = std::getenv("RGC_NO_OVERLAP") == nullptr;
   bool look_ahead = std::getenv("RGC_NO_LOOKAHEAD") == nullptr;  // step_lm: linearize issued behind compute_error
+  bool fuse_trial = std::getenv("RGC_NO_FUSE_TRIAL") == nullptr;  // compute_error inside the look-ahead correspondence launch (k_trial_step)
+  bool late_join = std::getenv("RGC_NO_LATE_JOIN") == nullptr;    // main stream joins the source's build first, its covariances at the first k_linearize
   std::vector<cudaEvent_t> free_events;
   // small pinned slots (8 KB) for the host copies a cloud build waits on (bounding-box partials, per-level
   // cell counts): one per build in flight, so that deferred builds of different clouds never share one
   std::vector<float*> free_hslots;
-  bool defer_builds = std::getenv("RGC_SYNC_BUILD") == nullptr;  // set_source / set_target return before the build's host waits
+  bool defer_builds = std::getenv("RGC_SYNC_BUILD") == nullptr;
+  // grid geometry of the last cloud built on each lane: the next build on that lane generates its keys with it
+  // before its own bounding box is known (rgc_gicp.cu: build_phase1 / build_phase3)
+  struct GeomHint {
+    bool valid = false;
+    int nbits = 0;
+    float s0 = 0.f, cell = 0.f;
+    int cloud_bits = 0;
+  } geom_hint[2];
+  bool spec_build = std::getenv("RGC_NO_SPEC_BUILD") == nullptr;
+  uint64_t spec_misses = 0;  // set_source / set_target return before the build's host waits
   // pinned, device-mapped result area the reduction kernels write straight into
   double* h_result = nullptr;
   double* d_result = nullptr;  // device alias of h_result

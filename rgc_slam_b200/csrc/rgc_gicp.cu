@@ -59,6 +59,8 @@ struct Tracer {
 struct BuildJob {
   Scratch tmp;
   int stage = 0;  // 1: ingest issued, waiting for the bounding box; 2: sort issued, waiting for the level counts
+  bool spec = false;      // phase 2 was issued with the previous cloud's grid geometry, before the bounding box was known
+  int max_bits = kMaxBits;
   int lane = 0;
   int n = 0, cloud_bits = 0, n_clouds = 0;
   uint64_t key = 0;
@@ -92,6 +94,7 @@ struct Cloud {
   int cov_k = 0, cov_method = 0;
   float build_ms = 0, knn_ms = 0, cov_ms = 0;
   float bb_min[3] = {0, 0, 0}, bb_max[3] = {0, 0, 0};
+  int lane_built = 0;  // lane (stream) the build and the ahead-of-time covariances were issued on
   // multi-cloud grid (batched registration): n_clouds clouds concatenated; cloud c = sorted positions
   // [h_off[c], h_off[c + 1]); d_off is the device copy, tiles the tile list of the self-kNN kernel
   int n_clouds = 0;
@@ -140,6 +143,14 @@ static int join_side(rgc_ctx* c) {
   return RGC_OK;
 }
 
+// The main stream may read a cloud prepared on lane 1 as soon as its BUILD is done (cl.ev[1]); the covariances
+// that lane 1 is still computing are only needed by the first kernel that reads them, which calls join_side()
+// itself.  side_pending stays set.
+static int join_side_build(rgc_ctx* c, const Cloud& cl) {
+  if (c->side_pending && cl.valid && cl.lane_built == 1 && cl.ev[1]) CK(c, cudaStreamWaitEvent(c->stream, cl.ev[1], 0));
+  return RGC_OK;
+}
+
 static void cloud_release(rgc_ctx* c, Cloud& cl) {
   if (cl.job) {  // a build in flight: its scratch goes back to the pool (stream-ordered reuse), the rest below
     c->put_hslot(cl.job->h_slot);
@@ -165,21 +176,34 @@ struct TmpCloud {
   ~TmpCloud() { cloud_release(c, cl); }
 };
 
-// stable LSD radix sort of (64-bit key, 32-bit value) pairs on the ctx stream; `hist` holds
-// 256 * (tiles + 1) counters.  On return *kout / *vout point at the buffers with the sorted data.
-static int radix_sort_pairs(rgc_ctx* c, uint64_t* keys_a, uint64_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, uint32_t* hist, int n, int key_bits,
-                            uint64_t** kout, uint32_t** vout) {
+// stable LSD radix sort of (64-bit key, 32-bit value) pairs on the ctx stream, one launch per 8-bit digit
+// (k_rs_onesweep).  `scratch`: rs_scratch_words(n, passes) words.  `ghist_ready`: the caller zeroed the scratch
+// and already counted the digit histograms (k_keys_hist).  `gather` (nullable): the last pass writes the points
+// in sorted order + the inverse permutation instead of the value array.  On return *kout / *vout point at the
+// buffers with the sorted data.
+struct SortGather {
+  const float4* pts;
+  float4* sorted;
+  int* inv;
+};
+static inline int sort_passes(int key_bits) { return std::max(1, div_up(key_bits, 8)); }
+static int radix_sort_pairs(rgc_ctx* c, uint64_t* keys_a, uint64_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, uint32_t* scratch, int n, int key_bits,
+                            uint64_t** kout, uint32_t** vout, bool ghist_ready = false, const SortGather* gather = nullptr) {
   const int nblk = div_up(n, RS_TILE);
-  uint32_t* digit_total = hist + 256 * (size_t)nblk;
-  const int passes = div_up(key_bits, 8);
+  const int passes = sort_passes(key_bits);
+  if (passes > RS_MAX_PASSES) FAIL(c, RGC_ERR_UNSUPPORTED, "sort key wider than 64 bits");
+  if (!ghist_ready) {
+    CK(c, cudaMemsetAsync(scratch, 0, sizeof(uint32_t) * rs_scratch_words(n, passes), c->stream));
+    k_rs_ghist<<<std::min(div_up(n, 256 * 8), 148 * 4), 256, 0, c->stream>>>(keys_a, n, passes, scratch);
+    CKL(c);
+  }
   uint64_t *kin = keys_a, *ko = keys_b;
   uint32_t *vin = vals_a, *vo = vals_b;
   for (int p = 0; p < passes; p++) {
-    k_rs_hist<<<nblk, 256, 0, c->stream>>>(kin, n, 8 * p, hist, nblk);
-    CKL(c);
-    k_rs_scan<<<256, 256, 0, c->stream>>>(hist, nblk, digit_total);
-    CKL(c);
-    k_rs_scatter<<<nblk, 256, 0, c->stream>>>(kin, vin, ko, vo, hist, digit_total, n, 8 * p, nblk);
+    if (gather && p == passes - 1)
+      k_rs_onesweep<true><<<nblk, 256, 0, c->stream>>>(kin, vin, ko, vo, scratch, p, n, nblk, gather->pts, gather->sorted, gather->inv);
+    else
+      k_rs_onesweep<false><<<nblk, 256, 0, c->stream>>>(kin, vin, ko, vo, scratch, p, n, nblk, nullptr, nullptr, nullptr);
     CKL(c);
     std::swap(kin, ko);
     std::swap(vin, vo);
@@ -188,6 +212,8 @@ static int radix_sort_pairs(rgc_ctx* c, uint64_t* keys_a, uint64_t* keys_b, uint
   *vout = vin;
   return RGC_OK;
 }
+
+static int build_sort(rgc_ctx* c, Cloud& cl, const unsigned char* raw, size_t stride);
 
 // upload (or adopt a device pointer), Morton-sort, build the level tables — in three phases separated by
 // the two host waits (see BuildJob).  All phases of a cloud run on the lane that was current in phase 1.
@@ -236,12 +262,27 @@ static int build_phase1(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, 
   j.keys_b = (uint64_t*)j.tmp.get(8 * n_sz);
   j.vals_a = (uint32_t*)j.tmp.get(4 * n_sz);
   j.vals_b = (uint32_t*)j.tmp.get(4 * n_sz);
-  j.hist = (uint32_t*)j.tmp.get(4 * 256 * ((size_t)div_up(n, RS_TILE) + 1));
+  j.hist = (uint32_t*)j.tmp.get(4 * rs_scratch_words(n, RS_MAX_PASSES));
   j.d_counts = (uint32_t*)j.tmp.get(4 * kMaxLevels);
   cl.sorted = (float4*)c->get(sizeof(float4) * n_sz);
   cl.inv = (int*)c->get(sizeof(int) * n_sz);
   if (!cl.inv || !j.orig || !j.d_bbox || !j.keys_a || !j.keys_b || !j.vals_a || !j.vals_b || !j.hist || !j.d_counts || !cl.sorted)
     FAIL(c, RGC_ERR_NOMEM, "device allocation failed (build)");
+  j.max_bits = std::min(kMaxBits, (56 - j.cloud_bits) / 3);  // key = cloud id | 3 * nbits Morton bits <= 56 bits
+  // Speculative geometry: successive clouds of a stream (the sweeps / the submaps of a SLAM front end) need the
+  // same grid, so the keys are generated with the previous cloud's (nbits, s0) in the SAME kernel that ingests
+  // the points and reduces the bounding box, and the sort follows without the host waiting for the box.
+  // build_phase3 checks the box against that geometry when it arrives with the level counts (one host wait
+  // per cloud instead of two) and redoes phase 2 the slow way if it does not fit.  A larger grid than needed
+  // is still a valid grid with the same Morton order (rgc_grid.cuh), so the results do not depend on the hint.
+  const rgc_ctx::GeomHint& h = c->geom_hint[c->lane];
+  if (c->spec_build && h.valid && h.cell == cell && h.cloud_bits == j.cloud_bits && h.nbits <= j.max_bits) {
+    j.spec = true;
+    grid_set(cl.view, h.nbits, h.s0);
+    cl.view.n = n;
+    TRY(build_sort(c, cl, d_raw, stride));
+    return RGC_OK;
+  }
   k_ingest<<<kBboxBlocks, 256, 0, st>>>(d_raw, stride, n, j.orig, j.d_bbox);
   CKL(c);
   CK(c, cudaMemcpyAsync(j.h_slot, j.d_bbox, sizeof(float) * 6 * kBboxBlocks, cudaMemcpyDeviceToHost, st));
@@ -249,55 +290,112 @@ static int build_phase1(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, 
   return RGC_OK;
 }
 
-// bounding box on the host -> grid geometry, Morton keys, radix sort, per-level cell counts
-static int build_phase2(rgc_ctx* c, Cloud& cl) {
-  BuildJob& j = *cl.job;
-  CK(c, cudaEventSynchronize(j.ready));
-  cudaStream_t st = c->stream;
-  const int n = j.n;
-  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+// bounding-box partials of a build (pinned copy) -> box; false if any coordinate was not finite
+static bool build_bbox(const BuildJob& j, float mn[3], float mx[3]) {
   bool finite = true;  // a block that saw NaN / inf writes NaN partials (k_ingest)
+  for (int a = 0; a < 3; a++) {
+    mn[a] = INFINITY;
+    mx[a] = -INFINITY;
+  }
   for (int b = 0; b < kBboxBlocks; b++)
     for (int a = 0; a < 3; a++) {
       finite = finite && !std::isnan(j.h_slot[b * 6 + a]) && !std::isnan(j.h_slot[b * 6 + 3 + a]);
       mn[a] = std::min(mn[a], j.h_slot[b * 6 + a]);
       mx[a] = std::max(mx[a], j.h_slot[b * 6 + 3 + a]);
     }
-  for (int a = 0; a < 3; a++)
-    if (!finite || !std::isfinite(mn[a]) || !std::isfinite(mx[a])) FAIL(c, RGC_ERR_INVALID, "point cloud contains non-finite coordinates");
-  for (int a = 0; a < 3; a++) {
-    cl.bb_min[a] = mn[a];
-    cl.bb_max[a] = mx[a];
+  for (int a = 0; a < 3; a++) finite = finite && std::isfinite(mn[a]) && std::isfinite(mx[a]);
+  return finite;
+}
+
+// Morton keys (+ ingest when `raw` is given: the speculative path) -> radix sort with the gather fused into the
+// last pass -> per-level cell counts -> host copies of the box partials and the counts -> `ready`.
+// cl.view holds the geometry (nbits, s0) to use.
+static int build_sort(rgc_ctx* c, Cloud& cl, const unsigned char* raw, size_t stride) {
+  BuildJob& j = *cl.job;
+  cudaStream_t st = c->stream;
+  const int n = j.n;
+  const GridView& v = cl.view;
+  const int key_bits = 3 * v.nbits + j.cloud_bits;
+  const int passes = sort_passes(key_bits);
+  const GridGeom geom{v.inv_s0, v.bias, v.nbits};
+  CK(c, cudaMemsetAsync(j.hist, 0, sizeof(uint32_t) * rs_scratch_words(n, passes), st));
+  if (raw) {
+    k_keys_hist<true><<<kBboxBlocks, 256, 0, st>>>(raw, stride, n, j.orig, j.d_bbox, geom, cl.d_off, j.n_clouds, passes, j.keys_a, j.vals_a, j.hist);
+    CKL(c);
+    CK(c, cudaMemcpyAsync(j.h_slot, j.d_bbox, sizeof(float) * 6 * kBboxBlocks, cudaMemcpyDeviceToHost, st));
+  } else {
+    k_keys_hist<false><<<kBboxBlocks, 256, 0, st>>>(nullptr, 0, n, j.orig, nullptr, geom, cl.d_off, j.n_clouds, passes, j.keys_a, j.vals_a, j.hist);
+    CKL(c);
   }
-  GridView& v = cl.view;
-  v.n = n;
-  grid_geometry(mn, mx, j.cell, v, std::min(kMaxBits, (56 - j.cloud_bits) / 3));  // key = cloud id | 3 * nbits Morton bits <= 56 bits
-  const int nbits = v.nbits;
-  GridGeom geom{v.inv_s0, v.bias, nbits};
-  k_morton<<<div_up(n, 256), 256, 0, st>>>(j.orig, n, geom, j.keys_a, j.vals_a, cl.d_off, j.n_clouds);
-  CKL(c);
   j.kin = j.keys_a;
   j.vin = j.vals_a;
-  TRY(radix_sort_pairs(c, j.keys_a, j.keys_b, j.vals_a, j.vals_b, j.hist, n, 3 * nbits + j.cloud_bits, &j.kin, &j.vin));
-  k_gather_sorted<<<div_up(n, 256), 256, 0, st>>>(j.orig, j.vin, n, cl.sorted, cl.inv);
-  CKL(c);
+  const SortGather gather{j.orig, cl.sorted, cl.inv};
+  TRY(radix_sort_pairs(c, j.keys_a, j.keys_b, j.vals_a, j.vals_b, j.hist, n, key_bits, &j.kin, &j.vin, true, &gather));
   CK(c, cudaMemsetAsync(j.d_counts, 0, 4 * kMaxLevels, st));
   k_count_cells<<<div_up(n, 256), 256, 0, st>>>(j.kin, n, v.nlevels, j.d_counts);
   CKL(c);
+  // level counts, then the sort's error word (a look-back that gave up: cannot happen, but must not pass silently)
   CK(c, cudaMemcpyAsync(j.h_slot + 6 * kBboxBlocks, j.d_counts, 4 * kMaxLevels, cudaMemcpyDeviceToHost, st));
+  CK(c, cudaMemcpyAsync(j.h_slot + 6 * kBboxBlocks + kMaxLevels, j.hist + 8, 4, cudaMemcpyDeviceToHost, st));
   CK(c, cudaEventRecord(j.ready, st));
   j.stage = 2;
   return RGC_OK;
 }
 
-// level counts on the host -> table sizes, table build, child masks; the cloud becomes valid
+// bounding box on the host -> grid geometry, then the sort (non-speculative path)
+static int build_phase2(rgc_ctx* c, Cloud& cl) {
+  BuildJob& j = *cl.job;
+  CK(c, cudaEventSynchronize(j.ready));
+  float mn[3], mx[3];
+  if (!build_bbox(j, mn, mx)) FAIL(c, RGC_ERR_INVALID, "point cloud contains non-finite coordinates");
+  for (int a = 0; a < 3; a++) {
+    cl.bb_min[a] = mn[a];
+    cl.bb_max[a] = mx[a];
+  }
+  GridView& v = cl.view;
+  v.n = j.n;
+  grid_geometry(mn, mx, j.cell, v, j.max_bits);
+  j.spec = false;
+  return build_sort(c, cl, nullptr, 0);
+}
+
+// level counts on the host -> table sizes, table build (with the child masks); the cloud becomes valid
 static int build_phase3(rgc_ctx* c, Cloud& cl) {
   BuildJob& j = *cl.job;
   CK(c, cudaEventSynchronize(j.ready));
   cudaStream_t st = c->stream;
   const int n = j.n;
   GridView& v = cl.view;
+  if (j.spec) {
+    // the bounding box arrived with the counts: does the geometry the keys were made with hold it?
+    float mn[3], mx[3];
+    if (!build_bbox(j, mn, mx)) FAIL(c, RGC_ERR_INVALID, "point cloud contains non-finite coordinates");
+    for (int a = 0; a < 3; a++) {
+      cl.bb_min[a] = mn[a];
+      cl.bb_max[a] = mx[a];
+    }
+    int nbits;
+    float s0;
+    grid_bits(mn, mx, j.cell, j.max_bits, nbits, s0);
+    rgc_ctx::GeomHint& h = c->geom_hint[j.lane];
+    if (s0 != v.s0 || nbits > v.nbits) {  // it does not: sort again with the right geometry (j.orig is intact)
+      c->spec_misses++;
+      grid_geometry(mn, mx, j.cell, v, j.max_bits);
+      v.n = n;
+      j.spec = false;
+      TRY(build_sort(c, cl, nullptr, 0));
+      CK(c, cudaEventSynchronize(j.ready));
+    } else {
+      v.margin = grid_margin(mn, mx);
+      if (nbits + 1 < v.nbits) h.nbits = nbits + 1;  // much smaller clouds now: shrink the hint (with one bit of hysteresis)
+    }
+  }
+  {
+    rgc_ctx::GeomHint& h = c->geom_hint[j.lane];
+    if (!j.spec || !h.valid) h = rgc_ctx::GeomHint{true, v.nbits, v.s0, j.cell, j.cloud_bits};
+  }
   const uint32_t* h_counts = reinterpret_cast<const uint32_t*>(j.h_slot + 6 * kBboxBlocks);
+  if (h_counts[kMaxLevels] != 0) FAIL(c, RGC_ERR_CUDA, "radix sort look-back timed out");
   size_t total_slots = 0;
   size_t slots[kMaxLevels];
   for (int l = 0; l < v.nlevels; l++) {
@@ -331,13 +429,12 @@ static int build_phase3(rgc_ctx* c, Cloud& cl) {
   }
   k_build_tables<<<dim3(div_up(n, 256), v.nlevels), 256, 0, st>>>(j.kin, n, ts);
   CKL(c);
-  k_child_masks<<<div_up(n, 256), 256, 0, st>>>(j.kin, n, ts);
-  CKL(c);
   v.pts = reinterpret_cast<const F4*>(cl.sorted);
   v.inv = cl.inv;
   cl.n = n;
   cl.key = j.key;
   cl.valid = true;
+  cl.lane_built = c->lane;
   CK(c, cudaEventRecord(cl.ev[1], st));
   cl.build_timed = true;
   c->put_hslot(j.h_slot);
@@ -350,7 +447,7 @@ static int build_phase3(rgc_ctx* c, Cloud& cl) {
 static int cloud_build(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, size_t stride, bool on_device, uint64_t key, float cell,
                        const int* offsets = nullptr, int n_clouds = 0) {
   int rc = build_phase1(c, cl, points, n_sz, stride, on_device, key, cell, offsets, n_clouds);
-  if (rc == RGC_OK) rc = build_phase2(c, cl);
+  if (rc == RGC_OK && cl.job->stage == 1) rc = build_phase2(c, cl);
   if (rc == RGC_OK) rc = build_phase3(c, cl);
   if (rc != RGC_OK) cloud_release(c, cl);
   return rc;
@@ -438,7 +535,7 @@ static int pre_filter(rgc_ctx* c, const void* points, size_t n_sz, size_t stride
   uint64_t* keys_b = (uint64_t*)tmp.get(8 * n_sz);
   uint32_t* vals_a = (uint32_t*)tmp.get(4 * n_sz);
   uint32_t* vals_b = (uint32_t*)tmp.get(4 * n_sz);
-  uint32_t* hist = (uint32_t*)tmp.get(4 * 256 * ((size_t)nblk_rs + 1));
+  uint32_t* hist = (uint32_t*)tmp.get(4 * rs_scratch_words(n, RS_MAX_PASSES));
   unsigned int* blk = (unsigned int*)tmp.get(4 * ((size_t)nblk_sc + 1));
   int* heads = (int*)tmp.get(4 * n_sz);
   if (!keys_a || !keys_b || !vals_a || !vals_b || !hist || !blk || !heads) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (voxel filter)");
@@ -510,7 +607,7 @@ static int launch_knn_self(rgc_ctx* c, const GridView& v, int n, int k, int* nbr
   k_knn_tile<<<div_up(ntiles, KT_WARPS), KT_WARPS * 32, smem, c->stream>>>(v, n, k, n_seeds, defer, dq, dq + 1, nbr, tiles, ntiles);
   CKL(c);
   if (defer != INT_MAX) {
-    k_knn_warp<<<std::min(div_up(n, KW_WARPS), 148 * 4), KW_WARPS * 32, 0, c->stream>>>(v, n, k, dq, dq + 1, nullptr, 0, nbr, tiles, nullptr, 0);
+    k_knn_warp<<<std::min(div_up(n, KW_WARPS), 148 * RGC_KW_MINB), KW_WARPS * 32, 0, c->stream>>>(v, n, k, dq, dq + 1, nullptr, 0, nbr, tiles, nullptr, 0);
     CKL(c);
   }
   return RGC_OK;
@@ -765,7 +862,7 @@ static int vgicp_build(rgc_reg* r) {
   uint64_t* keys_b = (uint64_t*)tmp.get(8 * n_sz);
   uint32_t* vals_a = (uint32_t*)tmp.get(4 * n_sz);
   uint32_t* vals_b = (uint32_t*)tmp.get(4 * n_sz);
-  uint32_t* hist = (uint32_t*)tmp.get(4 * 256 * ((size_t)div_up(n, RS_TILE) + 1));
+  uint32_t* hist = (uint32_t*)tmp.get(4 * rs_scratch_words(n, RS_MAX_PASSES));
   unsigned int* d_cnt = (unsigned int*)tmp.get(4);
   int* heads = (int*)tmp.get(4 * n_sz);
   if (!keys_a || !keys_b || !vals_a || !vals_b || !hist || !d_cnt || !heads) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (voxel map)");
@@ -868,7 +965,13 @@ static int vgicp_compute_error(rgc_reg* r, const double* T, double* err) {
 
 // FastGICP::linearize (fast_gicp_impl.hpp:155-211), launch half: correspondences (seeded by `hint`)
 // into corr/sqd, then the per-point terms and their reduction into `result`
-static int gicp_linearize_launch(rgc_reg* r, const double* T, int want, const int* hint, int* corr, float* sqd, double* maha, double* result) {
+struct CeJob {  // compute_error at the same pose, fused into the correspondence launch (k_trial_step)
+  bool on = false;
+  double* result = nullptr;
+  DoneFlag done{nullptr, 0ull};
+};
+static int gicp_linearize_launch(rgc_reg* r, const double* T, int want, const int* hint, int* corr, float* sqd, double* maha, double* result,
+                                 const CeJob& ce = CeJob()) {
   rgc_ctx* c = r->ctx;
   Rt Td;
   RtF Tf;
@@ -880,8 +983,16 @@ static int gicp_linearize_launch(rgc_reg* r, const double* T, int want, const in
   if (c->profile) CK(c, cudaEventRecord(c->evk[0], c->stream));
   // (a warp-cooperative variant of this search, one warp per 32 Morton-adjacent source points, was exact
   // too but slower on one sweep, 155 vs 92 us: profiles/README.md; it was removed)
-  k_correspond<<<div_up(r->src.n * spread, kThreads), kThreads, 0, c->stream>>>(r->tgt.view, r->src.sorted, r->src.n, spread, Tf, thr2, r->slab, hint, corr, sqd,
-                                                                               lazy ? r->tgt.cov_state : nullptr, r->need_list, r->need_count);
+  const int corr_blocks = div_up(r->src.n * spread, kThreads);
+  if (ce.on) {
+    const int ce_blocks = reduce_grid(r->src.n);
+    k_trial_step<<<ce_blocks + corr_blocks, kThreads, 0, c->stream>>>(r->tgt.view, r->src.sorted, r->src.n, spread, Tf, thr2, r->slab, hint, corr, sqd,
+                                                                      lazy ? r->tgt.cov_state : nullptr, r->need_list, r->need_count, ce_blocks, Td, r->maha,
+                                                                      r->partials, c->d_ticket, ce.result, ce.done);
+  } else {
+    k_correspond<<<corr_blocks, kThreads, 0, c->stream>>>(r->tgt.view, r->src.sorted, r->src.n, spread, Tf, thr2, r->slab, hint, corr, sqd,
+                                                          lazy ? r->tgt.cov_state : nullptr, r->need_list, r->need_count);
+  }
   CKL(c);
   if (c->profile) CK(c, cudaEventRecord(c->evk[1], c->stream));
   if (lazy) {
@@ -890,7 +1001,7 @@ static int gicp_linearize_launch(rgc_reg* r, const double* T, int want, const in
     // (every source point a new target point) and read the real count from the device: nothing here
     // makes the host wait.  After the first linearize of an align the list is nearly empty.
     const int k = r->tgt.cov_k, method = r->tgt.cov_method, cap = r->cap_src, n_t = r->tgt.n;
-    k_knn_warp<<<std::min(div_up(r->src.n, KW_WARPS), 148 * 4), KW_WARPS * 32, 0, c->stream>>>(r->tgt.view, n_t, k, r->need_count, nullptr, r->need_list, cap, r->need_nbr, nullptr, nullptr, 0);
+    k_knn_warp<<<std::min(div_up(r->src.n, KW_WARPS), 148 * RGC_KW_MINB), KW_WARPS * 32, 0, c->stream>>>(r->tgt.view, n_t, k, r->need_count, nullptr, r->need_list, cap, r->need_nbr, nullptr, nullptr, 0);
     CKL(c);
     const int grid = div_up(r->src.n, kThreads);
     if (k == 20 && n_t >= k)
@@ -902,6 +1013,7 @@ static int gicp_linearize_launch(rgc_reg* r, const double* T, int want, const in
     CKL(c);
     if (c->profile) CK(c, cudaEventRecord(c->evk[3], c->stream));
   }
+  TRY(join_side(c));  // the source covariances (lane 1) are first read here: reg_ready joined the source's build only
   k_linearize<<<reduce_grid(r->src.n), kThreads, 0, c->stream>>>(r->tgt.sorted, r->src.sorted, r->src.cov, r->tgt.cov, r->src.n, Td, want, corr, maha, r->partials,
                                                                      c->d_ticket, result, reg_next_done(r), lazy ? r->need_count : nullptr);
   CKL(c);
@@ -960,11 +1072,20 @@ static int reg_compute_error(rgc_reg* r, const double* T, double* err, bool ahea
   RtF Tf;
   to_rt(T, Td, Tf);
   if (c->profile) CK(c, cudaEventRecord(c->evk[0], c->stream));
-  k_compute_error<<<reduce_grid(r->src.n), kThreads, 0, c->stream>>>(r->tgt.sorted, r->src.sorted, r->src.n, Td, r->corr, r->maha, r->partials,
-                                                                         c->d_ticket, reg_result_ptr(r), reg_next_done(r));
-  CKL(c);
-  if (c->profile) CK(c, cudaEventRecord(c->evk[1], c->stream));
-  if (ahead) TRY(gicp_linearize_launch(r, T, 1, r->corr, r->corr2, r->sqd2, r->maha2, reg_spec_ptr(r)));
+  if (ahead && c->fuse_trial) {
+    // the error blocks ride in the correspondence launch of the look-ahead linearize (k_trial_step)
+    CeJob ce;
+    ce.on = true;
+    ce.result = reg_result_ptr(r);
+    ce.done = reg_next_done(r);
+    TRY(gicp_linearize_launch(r, T, 1, r->corr, r->corr2, r->sqd2, r->maha2, reg_spec_ptr(r), ce));
+  } else {
+    k_compute_error<<<reduce_grid(r->src.n), kThreads, 0, c->stream>>>(r->tgt.sorted, r->src.sorted, r->src.n, Td, r->corr, r->maha, r->partials,
+                                                                           c->d_ticket, reg_result_ptr(r), reg_next_done(r));
+    CKL(c);
+    if (c->profile) CK(c, cudaEventRecord(c->evk[1], c->stream));
+    if (ahead) TRY(gicp_linearize_launch(r, T, 1, r->corr, r->corr2, r->sqd2, r->maha2, reg_spec_ptr(r)));
+  }
   TRY(reg_finish_reduce(r, 1, ahead ? kLinN : 0));
   if (c->profile) {
     cudaEventSynchronize(c->evk[1]);
@@ -1041,7 +1162,17 @@ static int reg_ready(rgc_reg* r) {
   rgc_ctx* c = r->ctx;
   TRY(reg_drain(r));
   if (!r->src.valid || !r->tgt.valid) FAIL(c, RGC_ERR_STATE, "source and target clouds must both be set");
-  TRY(join_side(c));
+  // FastGICP with the source prepared on lane 1 and its covariances already under way with the right
+  // parameters: the main stream only waits for the source's BUILD, so the first correspondence search and the
+  // on-demand target covariances overlap the source's k-NN; k_linearize joins the rest (gicp_linearize_launch)
+  {
+    const Cloud& s = r->src;
+    const bool cov_ok = s.has_cov && !(s.cov_speculative && (s.cov_k != r->prm.k_correspondences || s.cov_method != r->prm.regularization));
+    if (c->late_join && !r->vgicp && cov_ok && s.lane_built == 1 && r->tgt.lane_built == 0)
+      TRY(join_side_build(c, s));
+    else
+      TRY(join_side(c));
+  }
   // fast_gicp_impl.hpp:104-109 — covariances are computed lazily, source first (normally both
   // were already started by set_input, see set_cloud)
   TRY(cloud_covariances(c, r->src, r->prm.k_correspondences, r->prm.regularization));

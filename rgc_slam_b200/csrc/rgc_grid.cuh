@@ -64,13 +64,29 @@ struct GridView {
 // shares the grid nor on nbits (a larger nbits only inserts, below each axis' top bit, bits that repeat
 // its complement and never decide a comparison), so a cloud is sorted the same way alone and inside the
 // multi-cloud grid of a batch, and every fixed-order reduction over its points adds in the same order.
-inline void grid_geometry(const float mn[3], const float mx[3], float cell, GridView& v, int max_bits = kMaxBits) {
-  float s0 = cell > 0.f ? cell : 0.05f;
+// view fields of a grid with `nbits` bits per axis and finest cell s0
+inline void grid_set(GridView& v, int nbits, float s0) {
+  v.bias = 1 << (nbits - 1);
+  v.ox = v.oy = v.oz = -(float)v.bias * s0;
+  v.s0 = s0;
+  v.inv_s0 = 1.0f / s0;
+  v.nbits = nbits;
+  v.nlevels = nbits + 1;
+}
+// slack (metres) covering the float rounding of the cell-coordinate map over this bounding box
+inline float grid_margin(const float mn[3], const float mx[3]) {
   float extent = 0.f, maxabs = 0.f;
   for (int a = 0; a < 3; a++) {
     extent = fmaxf(extent, mx[a] - mn[a]);
     maxabs = fmaxf(maxabs, fmaxf(fabsf(mn[a]), fabsf(mx[a])));
   }
+  return 2e-6f * (2.f * maxabs + extent) + 1e-6f;
+}
+// smallest (nbits, s0) that holds the bounding box
+inline void grid_bits(const float mn[3], const float mx[3], float cell, int max_bits, int& nbits_out, float& s0_out) {
+  float s0 = cell > 0.f ? cell : 0.05f;
+  float maxabs = 0.f;
+  for (int a = 0; a < 3; a++) maxabs = fmaxf(maxabs, fmaxf(fabsf(mn[a]), fabsf(mx[a])));
   // cells floor(x / s0) of all points must lie in [-bias, bias): bias * s0 > maxabs + s0
   int nbits = 2;
   for (;;) {
@@ -78,13 +94,15 @@ inline void grid_geometry(const float mn[3], const float mx[3], float cell, Grid
     if ((float)(1 << (nbits - 1)) * s0 > maxabs + 2.f * s0) break;
     s0 *= 2.f;  // coarser cells (a power-of-two ladder) once max_bits cannot cover the extent
   }
-  v.bias = 1 << (nbits - 1);
-  v.ox = v.oy = v.oz = -(float)v.bias * s0;
-  v.s0 = s0;
-  v.inv_s0 = 1.0f / s0;
-  v.margin = 2e-6f * (2.f * maxabs + extent) + 1e-6f;
-  v.nbits = nbits;
-  v.nlevels = nbits + 1;
+  nbits_out = nbits;
+  s0_out = s0;
+}
+inline void grid_geometry(const float mn[3], const float mx[3], float cell, GridView& v, int max_bits = kMaxBits) {
+  int nbits;
+  float s0;
+  grid_bits(mn, mx, cell, max_bits, nbits, s0);
+  grid_set(v, nbits, s0);
+  v.margin = grid_margin(mn, mx);
 }
 
 // ---- Morton ------------------------------------------------------------------------------------
@@ -103,6 +121,23 @@ RGC_HD uint64_t morton3(uint32_t x, uint32_t y, uint32_t z) { return spread3(x) 
 // `shift` = 64 - log2(table size).  (murmur's fmix64, used first, cost two multiplies and three
 // xor-shifts on the critical path of every probe.)
 RGC_HD uint32_t slot_of(uint64_t key, uint32_t shift) { return (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> shift); }
+
+// 2^l as a float, built from its bit pattern (l in [-126, 127]): the search code needs cell edges s0 * 2^l at
+// every node, and an int -> float conversion is a quarter-rate instruction on the critical path
+RGC_HD float pow2f(int l) { return i2f_bits((127 + l) << 23); }
+
+// smallest level l in [0, top_level] whose cell edge s0 * 2^l is >= r (top_level if none; r = +inf included).
+// s0 * 2^l is exact, so with l = exponent(r) - exponent(s0) the product has r's exponent and is >= r iff
+// s0's mantissa is: one comparison instead of a loop over the levels (which was 14 % of the hinted
+// correspondence search's instructions, ncu source page of round 2).
+RGC_HD int root_level(float s0, float r, int top_level) {
+  if (!(r > s0)) return 0;
+  if (!(r < INFINITY)) return top_level;
+  int l = ((f2i_bits(r) >> 23) & 0xff) - ((f2i_bits(s0) >> 23) & 0xff);
+  if (l > top_level) return top_level;
+  if (!(s0 * pow2f(l) >= r)) l++;
+  return l < top_level ? l : top_level;
+}
 
 // fine-level integer cell coordinate of a float coordinate: floor(x * inv_s) + bias.  Monotone
 // non-decreasing in x (float multiply and floor are monotone), which is what the face bounds rely on;
@@ -187,7 +222,7 @@ RGC_HD bool grid_lookup_key(const GridView& g, int l, uint64_t key, uint32_t& st
 // conservative squared distance from q to the box of cell (cx,cy,cz) at level l: never larger
 // than the reference-arithmetic d2 of any point stored in that cell
 RGC_HD float box_dist2(const GridView& g, int l, int cx, int cy, int cz, float qx, float qy, float qz) {
-  const float cs = g.s0 * (float)(1 << l);
+  const float cs = g.s0 * pow2f(l);
   const float lox = g.ox + (float)cx * cs, loy = g.oy + (float)cy * cs, loz = g.oz + (float)cz * cs;
   float gx = fmaxf(fmaxf(lox - qx, qx - (lox + cs)) - g.margin, 0.f);
   float gy = fmaxf(fmaxf(loy - qy, qy - (loy + cs)) - g.margin, 0.f);
@@ -473,9 +508,11 @@ RGC_HD void knn_search(const GridView& g, float qx, float qy, float qz, int k, f
 
   // ---- 2. root level: finest level whose cell edge >= ball radius
   const float r = sqrtf(bound) * 1.00001f + 2.f * g.margin;  // +inf when bound is +inf
-  int lb = 0;
-  while (lb < top_level && !(g.s0 * (float)(1 << lb) >= r)) lb++;
-  const float inv_cs = g.inv_s0 / (float)(1 << lb);
+  int lb = root_level(g.s0, r, top_level);
+#ifdef RGC_ROOT_SHIFT  // tuning: start the walk RGC_ROOT_SHIFT levels coarser (fewer, larger root cells)
+  lb = lb + RGC_ROOT_SHIFT < top_level ? lb + RGC_ROOT_SHIFT : top_level;
+#endif
+  const float inv_cs = g.inv_s0 * pow2f(-lb);  // == inv_s0 / 2^lb, exactly
   const int ncell = 1 << (g.nbits - lb);
   int lo[3], hi[3];
   {
@@ -521,7 +558,7 @@ RGC_HD void knn_search(const GridView& g, float qx, float qy, float qz, int k, f
             continue;
           }
           // children, nearest octant first (pushed in reverse so it is popped first)
-          const float half = g.s0 * (float)(1 << (l - 1));
+          const float half = g.s0 * pow2f(l - 1);
           const float mx = g.ox + (float)(2 * cx + 1) * half, my = g.oy + (float)(2 * cy + 1) * half, mz = g.oz + (float)(2 * cz + 1) * half;
           const int first = (qx >= mx ? 1 : 0) | (qy >= my ? 2 : 0) | (qz >= mz ? 4 : 0);
           const uint64_t pkey = (morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz) | prefix_at(cr, l)) << 3;

@@ -225,6 +225,196 @@ __global__ void __launch_bounds__(256) k_rs_scatter(const uint64_t* __restrict__
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Single-pass-per-digit LSD radix sort ("onesweep").  The three launches per digit above (per-tile histogram,
+// scan, scatter: ~18 us per digit on the 500k-point submap, most of it launch gaps and half-empty kernels) become
+// ONE: the global digit histograms of ALL passes are counted up front (k_keys_hist, fused with the key
+// generation, or k_rs_ghist for keys that already exist), and each pass finds its tile's base inside a digit
+// by a decoupled look-back over the tiles before it: a tile first publishes its own per-digit counts
+// (AGGREGATE), then walks back adding predecessors' counts until it meets one that already knows its
+// inclusive PREFIX.  Tile ids come from an atomic counter, so a tile's predecessors have all started and
+// publish their aggregates without waiting for anybody: the look-back always terminates.  Same per-warp
+// match_any ranking as k_rs_scatter: stable.
+// Scratch layout (uint32, zeroed before the first pass): [0, 8) tile counters per pass, [8, 16) error flag + pad,
+// [16, 16 + 8 * 256) global digit histograms per pass, then per pass nblk * 256 status words
+// (flag << 30 | count; flag 1 = aggregate, 2 = inclusive prefix).
+constexpr int RS_MAX_PASSES = 8;
+constexpr int RS_GHIST_OFF = 16;
+constexpr int RS_STATUS_OFF = RS_GHIST_OFF + RS_MAX_PASSES * 256;
+__host__ __device__ inline size_t rs_scratch_words(int n, int passes) { return (size_t)RS_STATUS_OFF + (size_t)passes * (size_t)((n + RS_TILE - 1) / RS_TILE) * 256; }
+
+// digit histograms of all passes for existing keys
+__global__ void __launch_bounds__(256) k_rs_ghist(const uint64_t* __restrict__ keys, int n, int passes, uint32_t* __restrict__ scratch) {
+  __shared__ uint32_t h[RS_MAX_PASSES * 256];
+  for (int i = threadIdx.x; i < passes * 256; i += 256) h[i] = 0;
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint64_t key = keys[i];
+    for (int p = 0; p < passes; p++) atomicAdd(&h[p * 256 + ((uint32_t)(key >> (8 * p)) & 255u)], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < passes * 256; i += 256)
+    if (h[i]) atomicAdd(&scratch[RS_GHIST_OFF + i], h[i]);
+}
+
+// Morton keys + the digit histograms of all sort passes, optionally fused with the ingest (raw AoS -> float4
+// + bounding-box partials) when the grid geometry is known before the bounding box is (speculative build:
+// the geometry of the previous cloud of the same stream, verified on the host once the box has arrived)
+template <bool INGEST>
+__global__ void __launch_bounds__(256) k_keys_hist(const unsigned char* __restrict__ raw, size_t stride, int n, float4* pts, float* __restrict__ bbox_partials,
+                                                   GridGeom g, const int* __restrict__ cloud_off, int n_clouds, int passes, uint64_t* __restrict__ keys,
+                                                   uint32_t* __restrict__ vals, uint32_t* __restrict__ scratch) {
+  __shared__ uint32_t h[RS_MAX_PASSES * 256];
+  for (int i = threadIdx.x; i < passes * 256; i += 256) h[i] = 0;
+  __syncthreads();
+  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  bool bad = false;
+  const int hi = (1 << g.nbits) - 1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float x, y, z;
+    if (INGEST) {
+      const float* p = reinterpret_cast<const float*>(raw + (size_t)i * stride);
+      x = p[0]; y = p[1]; z = p[2];
+      pts[i] = make_float4(x, y, z, 1.0f);
+      bad |= !(isfinite(x) && isfinite(y) && isfinite(z));
+      mn[0] = fminf(mn[0], x); mx[0] = fmaxf(mx[0], x);
+      mn[1] = fminf(mn[1], y); mx[1] = fmaxf(mx[1], y);
+      mn[2] = fminf(mn[2], z); mx[2] = fmaxf(mx[2], z);
+    } else {
+      const float4 p = pts[i];
+      x = p.x; y = p.y; z = p.z;
+    }
+    const int cx = min(max(cell_coord(x, g.inv_s0, g.bias), 0), hi);
+    const int cy = min(max(cell_coord(y, g.inv_s0, g.bias), 0), hi);
+    const int cz = min(max(cell_coord(z, g.inv_s0, g.bias), 0), hi);
+    uint64_t key = morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
+    if (cloud_off) {
+      int a = 0, b = n_clouds;  // cloud_off[a] <= i < cloud_off[b]
+      while (b - a > 1) {
+        const int mid = (a + b) >> 1;
+        if (cloud_off[mid] <= i) a = mid; else b = mid;
+      }
+      key |= (uint64_t)a << (3 * g.nbits);
+    }
+    keys[i] = key;
+    vals[i] = (uint32_t)i;
+    for (int p = 0; p < passes; p++) atomicAdd(&h[p * 256 + ((uint32_t)(key >> (8 * p)) & 255u)], 1u);
+  }
+  if (INGEST) bbox_block_reduce(mn, mx, bad, bbox_partials);
+  __syncthreads();
+  for (int i = threadIdx.x; i < passes * 256; i += 256)
+    if (h[i]) atomicAdd(&scratch[RS_GHIST_OFF + i], h[i]);
+}
+
+// one sort pass.  LAST_GATHER: the final pass also gathers the points into sorted order (float4 with the
+// original index in .w) and writes the inverse permutation, instead of the value array.
+template <bool LAST_GATHER>
+__global__ void __launch_bounds__(256) k_rs_onesweep(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint64_t* __restrict__ keys_out,
+                                                     uint32_t* __restrict__ vals_out, uint32_t* scratch, int pass, int n, int nblk,
+                                                     const float4* __restrict__ pts, float4* __restrict__ sorted, int* __restrict__ inv) {
+  __shared__ uint32_t cnt[8][256];
+  __shared__ uint32_t digit_base[256];
+  __shared__ uint32_t s_tile;
+  const int shift = 8 * pass;
+  if (threadIdx.x == 0) s_tile = atomicAdd(&scratch[pass], 1u);
+  {  // exclusive prefix of this pass's 256 digit totals
+    __shared__ uint32_t ws[8];
+    const uint32_t c = scratch[RS_GHIST_OFF + pass * 256 + threadIdx.x];
+    uint32_t v = c;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+      if ((threadIdx.x & 31) >= o) v += t;
+    }
+    if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = v;
+    __syncthreads();
+    uint32_t before = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); w++) before += ws[w];
+    digit_base[threadIdx.x] = before + v - c;
+  }
+  for (int i = threadIdx.x; i < 8 * 256; i += 256) (&cnt[0][0])[i] = 0;
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp_base = (int)tile * RS_TILE + warp * (32 * RS_ITEMS);
+  uint64_t k[RS_ITEMS];
+  uint32_t d[RS_ITEMS];
+  const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; r++) {
+    const int i = warp_base + r * 32 + lane;
+    const bool valid = i < n;
+    k[r] = valid ? keys_in[i] : 0ull;
+    d[r] = valid ? ((uint32_t)(k[r] >> shift) & 255u) : (256u + lane);  // invalid lanes never match
+    const uint32_t peers = __match_any_sync(0xffffffffu, d[r]);
+    if (valid && (peers & lt_mask) == 0) cnt[warp][d[r]] += __popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
+  {  // thread = digit: publish the tile's count, look back for the count of all tiles before it
+    const uint32_t dg = threadIdx.x;
+    uint32_t agg = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) agg += cnt[w][dg];
+    volatile uint32_t* status = scratch + RS_STATUS_OFF + (size_t)pass * nblk * 256;
+    uint32_t excl = 0;
+    if (tile == 0) {
+      status[dg] = (2u << 30) | agg;
+    } else {
+      status[(size_t)tile * 256 + dg] = (1u << 30) | agg;
+      int p = (int)tile - 1;
+      unsigned spins = 0;
+      for (;;) {
+        const uint32_t v = status[(size_t)p * 256 + dg];
+        const uint32_t f = v >> 30;
+        if (f == 0) {
+          if (++spins > (1u << 22)) {  // a predecessor that never publishes: report instead of hanging (cannot happen, see above)
+            scratch[8] = 1u;
+            break;
+          }
+          continue;
+        }
+        excl += v & 0x3fffffffu;
+        if (f == 2u) break;
+        p--;
+        spins = 0;
+      }
+      status[(size_t)tile * 256 + dg] = (2u << 30) | (excl + agg);
+    }
+    uint32_t base = digit_base[dg] + excl;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+      const uint32_t c = cnt[w][dg];
+      cnt[w][dg] = base;
+      base += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; r++) {
+    const int i = warp_base + r * 32 + lane;
+    const bool valid = i < n;
+    const uint32_t peers = __match_any_sync(0xffffffffu, d[r]);
+    const uint32_t rank = __popc(peers & lt_mask);
+    const uint32_t off = valid ? cnt[warp][d[r]] : 0u;
+    __syncwarp();
+    if (valid && rank == 0) cnt[warp][d[r]] = off + __popc(peers);
+    __syncwarp();
+    if (valid) {
+      const uint32_t dst = off + rank;
+      keys_out[dst] = k[r];
+      const uint32_t o = vals_in[i];
+      if (LAST_GATHER) {
+        float4 pt = pts[o];
+        pt.w = __int_as_float((int)o);
+        sorted[dst] = pt;
+        inv[o] = (int)dst;
+      } else {
+        vals_out[dst] = o;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) k_gather_sorted(const float4* __restrict__ pts, const uint32_t* __restrict__ vals, int n, float4* __restrict__ sorted,
                                                        int* __restrict__ inv) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -267,14 +457,17 @@ __device__ __forceinline__ GridSlot* slot_insert_or_find(GridSlot* tab, uint32_t
   uint32_t h = slot_of(key, shift);
   for (;;) {
     unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long*>(&tab[h].key), (unsigned long long)kEmptyKey, (unsigned long long)key);
-    if (prev == kEmptyKey || prev == key) return &tab[h];
+    // the top byte of a live key word collects the occupied-children bits while the table is being built
+    if (prev == kEmptyKey || (prev & kKeyMask) == key) return &tab[h];
     h = (h + 1) & mask;
   }
 }
 
 // blockIdx.y = level: one (point, level) pair per thread, so no thread walks all the levels
 // serially (the 1-D version was bound by the CAS chain of the few threads that open a cell at
-// every level: 62 us whatever the cloud size).
+// every level: 62 us whatever the cloud size).  The thread that opens a cell also sets the cell's bit in
+// its parent's occupied-children mask (insert-or-find: whoever comes first creates the parent's slot) —
+// this used to be a second kernel over the finished tables (k_child_masks, 13 us on the 500k-point submap).
 __global__ void __launch_bounds__(256) k_build_tables(const uint64_t* __restrict__ keys, int n, TableSet ts) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int l = blockIdx.y;
@@ -287,33 +480,16 @@ __global__ void __launch_bounds__(256) k_build_tables(const uint64_t* __restrict
     opens = (key >> (3 * l)) != (prev >> (3 * l));
   }
   if (opens) {
-    slot_insert_or_find(ts.table[l], ts.mask[l], ts.shift[l], key >> (3 * l))->start = (uint32_t)i;
+    const uint64_t ck = key >> (3 * l);
+    slot_insert_or_find(ts.table[l], ts.mask[l], ts.shift[l], ck)->start = (uint32_t)i;
     if (i > 0) slot_insert_or_find(ts.table[l], ts.mask[l], ts.shift[l], prev >> (3 * l))->end = (uint32_t)i;
+    if (l + 1 < ts.nlevels) {
+      GridSlot* ps = slot_insert_or_find(ts.table[l + 1], ts.mask[l + 1], ts.shift[l + 1], ck >> 3);
+      // the mask lives in the top byte of the 64-bit key word = top byte of its high 32-bit half
+      atomicOr(reinterpret_cast<unsigned int*>(&ps->key) + 1, 1u << (24 + (int)(ck & 7)));
+    }
   }
   if (i == n - 1) slot_insert_or_find(ts.table[l], ts.mask[l], ts.shift[l], key >> (3 * l))->end = (uint32_t)n;
-}
-
-// second pass (tables complete): every cell sets its bit in its parent's occupied-children mask
-__global__ void __launch_bounds__(256) k_child_masks(const uint64_t* __restrict__ keys, int n, TableSet ts) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint64_t key = keys[i];
-  int top;
-  if (i == 0)
-    top = ts.nlevels - 1;
-  else {
-    uint64_t x = key ^ keys[i - 1];
-    top = x ? min((63 - __clzll((long long)x)) / 3, ts.nlevels - 1) : -1;
-  }
-  for (int l = 0; l <= top && l + 1 < ts.nlevels; l++) {
-    const uint64_t ck = key >> (3 * l), pk = ck >> 3;
-    GridSlot* tab = ts.table[l + 1];
-    const uint32_t mask = ts.mask[l + 1];
-    uint32_t h = slot_of(pk, ts.shift[l + 1]);
-    while ((tab[h].key & kKeyMask) != pk) h = (h + 1) & mask;  // parent exists by construction
-    // the mask lives in the top byte of the 64-bit key word = top byte of its high 32-bit half
-    atomicOr(reinterpret_cast<unsigned int*>(&tab[h].key) + 1, 1u << (24 + (int)(ck & 7)));
-  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -483,7 +659,7 @@ __global__ void __launch_bounds__(KT_WARPS * 32) k_knn_tile(GridView g, int n, i
     const int fx = cell_coord(q.x, g.inv_s0, g.bias), fy = cell_coord(q.y, g.inv_s0, g.bias), fz = cell_coord(q.z, g.inv_s0, g.bias);
     const float seed_b = heap.cnt == k ? key_d2(hk[lane]) : INFINITY;
     for (int l = 0; l < g.nlevels; l++) {
-      const float edge = g.s0 * (float)(1 << l) + 2.f * g.margin;
+      const float edge = g.s0 * pow2f(l) + 2.f * g.margin;
       const float diag2 = 3.f * edge * edge * 1.0001f;
       if (diag2 >= seed_b) break;  // cannot improve on the seed bound any more
       uint32_t s, e, m;
@@ -525,9 +701,8 @@ __global__ void __launch_bounds__(KT_WARPS * 32) k_knn_tile(GridView g, int n, i
     const float hix = warp_max(q.x + r), hiy = warp_max(q.y + r), hiz = warp_max(q.z + r);
     const float ext = fmaxf(fmaxf(hix - lox, hiy - loy), hiz - loz);
     const int top_level = g.nlevels - 1;
-    int lb = 0;
-    while (lb < top_level && !(g.s0 * (float)(1 << lb) >= 0.5f * ext)) lb++;
-    const float inv_cs = g.inv_s0 / (float)(1 << lb);
+    const int lb = root_level(g.s0, 0.5f * ext, top_level);
+    const float inv_cs = g.inv_s0 * pow2f(-lb);
     const int ncell = 1 << (g.nbits - lb);
     int rlo[3], rhi[3];
     {
@@ -668,7 +843,10 @@ __device__ __forceinline__ unsigned long long shfl64_up1(unsigned long long v) {
 // linearize; results k-major with stride `out_stride` at the LIST index).
 // Multi-cloud grids: `tiles` (deferred mode) or `cloud_off` (list mode: n_clouds + 1 sorted-position
 // offsets, the query's cloud is found by bisection) confine every search to the query's own cloud.
-__global__ void __launch_bounds__(KW_WARPS * 32) k_knn_warp(GridView g, int n, int k, const int* __restrict__ defer_count, const int* __restrict__ defer_tiles,
+#ifndef RGC_KW_MINB
+#define RGC_KW_MINB 4
+#endif
+__global__ void __launch_bounds__(KW_WARPS * 32, RGC_KW_MINB) k_knn_warp(GridView g, int n, int k, const int* __restrict__ defer_count, const int* __restrict__ defer_tiles,
                                                            const int* __restrict__ qlist, int out_stride, int* __restrict__ out_idx,
                                                            const TileDesc* __restrict__ tiles, const int* __restrict__ cloud_off, int n_clouds) {
   __shared__ TileNode stacks[KW_WARPS][KW_STACK];
@@ -748,7 +926,7 @@ __global__ void __launch_bounds__(KW_WARPS * 32) k_knn_warp(GridView g, int n, i
         const unsigned hit = __ballot_sync(0xffffffffu, enough);
         if (hit) {
           const int l = __ffs(hit) - 1;
-          const float edge = g.s0 * (float)(1 << l) + 2.f * g.margin;
+          const float edge = g.s0 * pow2f(l) + 2.f * g.margin;
           cap2 = 3.f * edge * edge * 1.0001f;
           capk = pack_key(cap2, 0x7fffffff);
         }
@@ -756,9 +934,8 @@ __global__ void __launch_bounds__(KW_WARPS * 32) k_knn_warp(GridView g, int n, i
       const float b0 = bound();
       const float r = b0 < INFINITY ? sqrtf(b0) * 1.00001f + 2.f * g.margin : INFINITY;
       const int top_level = g.nlevels - 1;
-      int lb = 0;
-      while (lb < top_level && !(g.s0 * (float)(1 << lb) >= r)) lb++;
-      const float inv_cs = g.inv_s0 / (float)(1 << lb);
+      const int lb = root_level(g.s0, r, top_level);
+      const float inv_cs = g.inv_s0 * pow2f(-lb);
       const int ncell = 1 << (g.nbits - lb);
       int rlo[3], rhi[3];
       {
@@ -815,18 +992,43 @@ __global__ void __launch_bounds__(KW_WARPS * 32) k_knn_warp(GridView g, int n, i
             offer(key, take);
           }
         }
+        // Depth-first walk, up to four nodes per step: lane group g = lane / 8 takes the g-th node from the top of
+        // the stack.  Leaf nodes of the step are scanned together (32 candidates per round over the
+        // concatenation of their ranges) and the inner nodes are expanded together (lane 8 g + c resolves
+        // and tests child c of group g's node: 32 table probes in flight instead of 8).  One query is a
+        // chain of dependent memory accesses (a short on-demand list ran 17 us however few queries it held);
+        // stepping four nodes at a time cuts the number of links.  Any visiting order gives the same exact
+        // neighbour list: a node is only ever skipped against a bound that is already a valid upper bound.
         while (sp > 0) {
-          const TileNode nd = stack[--sp];
+          int nb = min(sp, 4);
+          while (nb > 1 && (sp - nb) + 8 * nb > KW_STACK) nb--;
+          const int grp = lane >> 3, sub = lane & 7;
+          const bool in = grp < nb;
+          const TileNode nd = stack[sp - 1 - (in ? grp : 0)];
+          sp -= nb;
           __syncwarp();
           const int l = (int)(nd.cx_lvl >> 24);
           const int cx = (int)(nd.cx_lvl & 0xffffffu), cy = (int)(nd.cy_mask & 0xffffffu), cz = (int)nd.cz;
           const uint32_t cm = nd.cy_mask >> 24;
           const float bd = bound();
-          if (!(box_dist2(g, l, cx, cy, cz, q.x, q.y, q.z) <= bd)) continue;
-          if (l == 0 || nd.end - nd.start <= (uint32_t)KW_LEAF || sp + 8 > KW_STACK) {
-            for (uint32_t p0 = nd.start; p0 < nd.end; p0 += 32) {
-              const uint32_t p = p0 + lane;
-              const bool take = p < nd.end && (uint32_t)((int)p - s0) >= (uint32_t)ns;
+          const bool live = in && box_dist2(g, l, cx, cy, cz, q.x, q.y, q.z) <= bd;
+          const bool leaf = live && (l == 0 || nd.end - nd.start <= (uint32_t)KW_LEAF || (nb == 1 && sp + 8 > KW_STACK));
+          // ---- leaves of this step
+          const uint32_t lsz = leaf ? nd.end - nd.start : 0u;
+          const uint32_t z0 = __shfl_sync(0xffffffffu, lsz, 0), z1 = __shfl_sync(0xffffffffu, lsz, 8), z2 = __shfl_sync(0xffffffffu, lsz, 16),
+                         z3 = __shfl_sync(0xffffffffu, lsz, 24);
+          const uint32_t total = z0 + z1 + z2 + z3;
+          if (total) {
+            const uint32_t b0s = __shfl_sync(0xffffffffu, nd.start, 0), b1s = __shfl_sync(0xffffffffu, nd.start, 8),
+                           b2s = __shfl_sync(0xffffffffu, nd.start, 16), b3s = __shfl_sync(0xffffffffu, nd.start, 24);
+            for (uint32_t e0 = 0; e0 < total; e0 += 32) {
+              const uint32_t e = e0 + lane;
+              uint32_t p;
+              if (e < z0) p = b0s + e;
+              else if (e < z0 + z1) p = b1s + (e - z0);
+              else if (e < z0 + z1 + z2) p = b2s + (e - z0 - z1);
+              else p = b3s + (e - z0 - z1 - z2);
+              const bool take = e < total && (uint32_t)((int)p - s0) >= (uint32_t)ns;
               unsigned long long key = ~0ull;
               if (take) {
                 const float4 c = pts4[p];
@@ -834,29 +1036,36 @@ __global__ void __launch_bounds__(KW_WARPS * 32) k_knn_warp(GridView g, int n, i
               }
               offer(key, take);
             }
-            continue;
           }
-          // expand: lane c < 8 resolves and tests child c; the survivors are pushed farthest first
-          const uint64_t pkey = (morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz) | (prefix >> (3 * l))) << 3;
+          // ---- inner nodes of this step: lane 8 g + c resolves and tests child c of group g's node; the survivors
+          // of a group are pushed farthest first, the groups deepest first, so the nearest child of the node that
+          // was on top of the stack is popped next
+          const bool inner = live && !leaf;
+          if (!__any_sync(0xffffffffu, inner)) continue;
+          const float bd2 = total ? bound() : bd;
           uint32_t cs = 0, ce = 0, cmk = 0;
           bool hc = false;
           float dc = INFINITY;
-          const int ccx = 2 * cx + (lane & 1), ccy = 2 * cy + ((lane >> 1) & 1), ccz = 2 * cz + ((lane >> 2) & 1);
-          if (lane < 8 && ((cm >> lane) & 1u)) {
-            hc = grid_lookup_key(g, l - 1, pkey | (uint64_t)lane, cs, ce, cmk);
+          const int ccx = 2 * cx + (sub & 1), ccy = 2 * cy + ((sub >> 1) & 1), ccz = 2 * cz + ((sub >> 2) & 1);
+          if (inner && ((cm >> sub) & 1u)) {
+            const uint64_t pkey = (morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz) | (prefix >> (3 * l))) << 3;
+            hc = grid_lookup_key(g, l - 1, pkey | (uint64_t)sub, cs, ce, cmk);
             if (hc) {
               dc = box_dist2(g, l - 1, ccx, ccy, ccz, q.x, q.y, q.z);
-              hc = dc <= bd;
+              hc = dc <= bd2;
             }
           }
           const unsigned hvc = __ballot_sync(0xffffffffu, hc);
+          const unsigned mine_grp = (hvc >> (8 * grp)) & 0xffu;
           int rank = 0;
 #pragma unroll
           for (int c = 0; c < 8; c++) {
-            const float dother = __shfl_sync(0xffffffffu, dc, c);
-            if (((hvc >> c) & 1u) && (dother > dc || (dother == dc && c < lane))) rank++;
+            const float dother = __shfl_sync(0xffffffffu, dc, c, 8);
+            if (((mine_grp >> c) & 1u) && (dother > dc || (dother == dc && c < sub))) rank++;
           }
-          if (hc) stack[sp + rank] = TileNode{(uint32_t)ccx | ((uint32_t)(l - 1) << 24), (uint32_t)ccy | (cmk << 24), (uint32_t)ccz, cs, ce};
+          // groups above this one in the stack order (pushed earlier): those with a HIGHER group index
+          const int before = grp < 3 ? __popc(hvc >> (8 * (grp + 1))) : 0;
+          if (hc) stack[sp + before + rank] = TileNode{(uint32_t)ccx | ((uint32_t)(l - 1) << 24), (uint32_t)ccy | (cmk << 24), (uint32_t)ccz, cs, ce};
           sp += __popc(hvc);
           __syncwarp();
         }
@@ -1098,10 +1307,9 @@ constexpr int kLinN = kAccN + 1;  // + inlier count
 #ifndef RGC_CORR_MINB
 #define RGC_CORR_MINB 8
 #endif
-__global__ void __launch_bounds__(kThreads, RGC_CORR_MINB) k_correspond(GridView tgt, const float4* __restrict__ src, int n_src, int spread, RtF Tf, float thr2, Slab slab,
-                                                            const int* hint, int* corr, float* __restrict__ sqd, int* __restrict__ need_state,
-                                                            int* __restrict__ need_list, int* __restrict__ need_count) {
-  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void correspond_query(const GridView& tgt, const float4* __restrict__ src, int n_src, int spread, const RtF& Tf, float thr2, const Slab& slab,
+                                                 const int* hint, int* corr, float* __restrict__ sqd, int* __restrict__ need_state, int* __restrict__ need_list,
+                                                 int* __restrict__ need_count, int gt) {
   const int i = gt / spread;
   if ((gt & (spread - 1)) != 0 || i >= n_src) return;
   const float4 p = __ldg(&src[i]);
@@ -1137,6 +1345,11 @@ __global__ void __launch_bounds__(kThreads, RGC_CORR_MINB) k_correspond(GridView
       if (claim) need_list[base + __popc(m & ((1u << lane) - 1u))] = pos;
     }
   }
+}
+__global__ void __launch_bounds__(kThreads, RGC_CORR_MINB) k_correspond(GridView tgt, const float4* __restrict__ src, int n_src, int spread, RtF Tf, float thr2, Slab slab,
+                                                            const int* hint, int* corr, float* __restrict__ sqd, int* __restrict__ need_state,
+                                                            int* __restrict__ need_list, int* __restrict__ need_count) {
+  correspond_query(tgt, src, n_src, spread, Tf, thr2, slab, hint, corr, sqd, need_state, need_list, need_count, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 // Mahalanobis part of update_correspondences + linearize (fast_gicp_impl.hpp:139-211), fused:
@@ -1236,6 +1449,27 @@ __global__ void __launch_bounds__(kThreads) k_compute_error(const float4* __rest
   double acc[1] = {0.0};
   compute_error_points(tgt_pts, src, corr, maha, Td, 0, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, n_src, acc);
   grid_reduce<1>(acc, partials, ticket, result, done);
+}
+
+// One launch for the two independent jobs of an LM trial step at pose xi (lsq_registration_impl.hpp:141-143 and,
+// if the step is accepted, :127 of the next iteration): blocks [0, ce_blocks) evaluate compute_error(xi) on the
+// frozen correspondences / Mahalanobis matrices of the last linearize — the same virtual grid, thread mapping and
+// reduction order as k_compute_error, hence the same bits — while the remaining blocks search the correspondences
+// of linearize(xi) (hinted by the frozen ones) into the second buffer set.  Run back to back the error kernel was
+// a 10 us latency chain in front of a 55 us one; side by side it disappears behind the search.
+__global__ void __launch_bounds__(kThreads, RGC_CORR_MINB) k_trial_step(GridView tgt, const float4* __restrict__ src, int n_src, int spread, RtF Tf, float thr2, Slab slab,
+                                                            const int* hint, int* corr, float* __restrict__ sqd, int* __restrict__ need_state,
+                                                            int* __restrict__ need_list, int* __restrict__ need_count, int ce_blocks, Rt Td,
+                                                            const double* __restrict__ ce_maha, double* __restrict__ partials, unsigned int* __restrict__ ticket,
+                                                            double* __restrict__ ce_result, DoneFlag ce_done) {
+  if ((int)blockIdx.x < ce_blocks) {
+    double acc[1] = {0.0};
+    compute_error_points(reinterpret_cast<const float4*>(tgt.pts), src, hint, ce_maha, Td, 0, blockIdx.x * blockDim.x + threadIdx.x, ce_blocks * blockDim.x, n_src, acc);
+    grid_reduce_at<1>(acc, partials, blockIdx.x, (unsigned)ce_blocks, ticket, ce_result, ce_done);
+    return;
+  }
+  correspond_query(tgt, src, n_src, spread, Tf, thr2, slab, hint, corr, sqd, need_state, need_list, need_count,
+                   ((int)blockIdx.x - ce_blocks) * blockDim.x + threadIdx.x);
 }
 
 // pcl::Registration::getFitnessScore: [sum d2, count] over 1-NN d2 <= max_range.  `hint` (nullable): the
