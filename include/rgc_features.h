@@ -74,6 +74,12 @@ typedef struct {
   int32_t* surf_flat;         float* surf_flat_w;    int32_t* n_surf_flat;         /* normal_x = distance_source (:554) */
   int32_t* inten_sharp;       float* inten_sharp_w;  int32_t* n_inten_sharp;       /* normal_x = other_source (:609) */
   int32_t* inten_less_sharp;                         int32_t* n_inten_less_sharp;
+  /* ---- the two unbounded clouds of the handler, as index lists ---- */
+  int32_t* surf_less_flat;   /* surfPointsLessFlatScan (:586-592): per-point capacity layout (like `label`), ascending */
+  int32_t* n_surf_less_flat; /* n_scans */
+  int32_t* ground_points;    /* GroundPoints (:338), the cloud published on /laser_cloud_ground (:714-717): n_scans x ground_cap
+                                indices in push order, duplicates included; scan b holds min(ground_size[b], ground_cap) entries */
+  int32_t ground_cap;        /* slots per scan in ground_points (a sample is appended up to 10 times: 10 x the points of rings 0-6 at most) */
   float device_ms; /* out: CUDA-event time of all kernels of this call */
 } rgc_feat_out;
 

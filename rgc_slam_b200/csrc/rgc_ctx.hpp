@@ -2,6 +2,8 @@
 // (device, stream, pooled device memory, pinned result buffers) and the error-handling macros.
 #pragma once
 #include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 #include <cstdint>
@@ -58,7 +60,7 @@ struct rgc_ctx {
     int cloud_bits = 0;
   } geom_hint[2];
   bool spec_build = std::getenv("RGC_NO_SPEC_BUILD") == nullptr;
-  uint64_t spec_misses = 0;  // set_source / set_target return before the build's host waits
+  uint64_t spec_builds = 0, spec_misses = 0;  // set_source / set_target return before the build's host waits
   // pinned, device-mapped result area the reduction kernels write straight into
   double* h_result = nullptr;
   double* d_result = nullptr;  // device alias of h_result
@@ -79,6 +81,45 @@ struct rgc_ctx {
   int knn_defer = std::getenv("RGC_KNN_DEFER") ? std::atoi(std::getenv("RGC_KNN_DEFER")) : -1;
   float last_kernel_ms[3] = {0, 0, 0};  // k_correspond, k_linearize, k_compute_error
   float last_ondemand_ms = 0;           // on-demand target kNN + covariances of the last linearize (profiling only)
+
+  // RGC_TIMELINE=1: device timeline of one align (debug aid): events recorded behind the kernels of the build,
+  // the covariance passes and the LM loop on whichever lane issues them, printed at the end of rgc_reg_align
+  bool timeline = std::getenv("RGC_TIMELINE") != nullptr;
+  struct Mark {
+    const char* what;
+    int lane;
+    cudaEvent_t ev;
+  };
+  std::vector<Mark> marks;
+  void mark(const char* what) {
+    if (!timeline) return;
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, stream);
+    marks.push_back(Mark{what, lane, e});
+  }
+  void print_marks() {
+    if (!timeline || marks.empty()) return;
+    cudaEventSynchronize(marks.back().ev);
+    for (auto& m : marks) cudaEventSynchronize(m.ev);
+    // sort by completion time relative to the first mark
+    std::vector<std::pair<float, size_t>> order;
+    for (size_t i = 0; i < marks.size(); i++) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, marks[0].ev, marks[i].ev);
+      order.push_back({ms, i});
+    }
+    std::sort(order.begin(), order.end());
+    std::fprintf(stderr, "[rgc timeline] %zu marks (us since the first; lane 0 = main stream, 1 = source lane)\n", marks.size());
+    float last[2] = {0.f, 0.f};
+    for (auto& o : order) {
+      const Mark& m = marks[o.second];
+      std::fprintf(stderr, "[rgc timeline] %9.1f  (+%7.1f on lane %d)  %s\n", o.first * 1e3f, (o.first - last[m.lane]) * 1e3f, m.lane, m.what);
+      last[m.lane] = o.first;
+    }
+    for (auto& m : marks) cudaEventDestroy(m.ev);
+    marks.clear();
+  }
 
   void switch_lane(int to) {
     if (to == lane) return;
@@ -133,12 +174,22 @@ struct rgc_ctx {
       free_hslots.pop_back();
       return p;
     }
+    // mapped: the build kernels write the bounding-box partials and the level counts straight into it (a
+    // cudaMemcpyAsync of a few bytes costs ~8 us of stream time)
     float* p = nullptr;
-    if (cudaHostAlloc((void**)&p, kHslotBytes, cudaHostAllocDefault) != cudaSuccess) {
+    if (cudaHostAlloc((void**)&p, kHslotBytes, cudaHostAllocMapped) != cudaSuccess) {
       cudaGetLastError();
       return nullptr;
     }
     return p;
+  }
+  static float* hslot_device(float* h) {
+    float* d = nullptr;
+    if (!h || cudaHostGetDevicePointer((void**)&d, h, 0) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    return d;
   }
   void put_hslot(float* p) {
     if (p) free_hslots.push_back(p);

@@ -50,6 +50,9 @@ struct FeatArrays {  // device pointers, per-point arrays in the "8 slots of sla
   int *corner_sharp, *corner_less_sharp, *surf_flat, *inten_sharp, *inten_less_sharp;
   float *corner_sharp_w, *surf_flat_w, *inten_sharp_w;
   int* list_counts;  // [scan][5]
+  // surfPointsLessFlatScan (:586-592) in the per-point capacity layout, GroundPoints (:338) with `ground_cap` slots per scan
+  int *surf_less_flat, *n_surf_less_flat, *ground_points;
+  int ground_cap;
 };
 
 __device__ __forceinline__ float absf(float v) { return v < 0 ? -v : v; }
@@ -743,6 +746,94 @@ __global__ void __launch_bounds__(256) k_feat_weights(const int* __restrict__ sc
   }
 }
 
+// exclusive prefix sum of one int per thread over a 256-thread block; `total` = the block's sum
+__device__ __forceinline__ int block_excl_scan256(int v, int& total) {
+  __shared__ int ws[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += t;
+  }
+  __syncthreads();  // ws may still be read by the previous call
+  if (lane == 31) ws[warp] = x;
+  __syncthreads();
+  int before = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < 8; w++) {
+    const int sw = ws[w];
+    if (w < warp) before += sw;
+    tot += sw;
+  }
+  total = tot;
+  return before + x - v;
+}
+
+// One block per scan: the two clouds of the reference that are not bounded feature lists.
+//  * surfPointsLessFlatScan (:586-592): after the picks of a sextant, every point k of it with cloudLabel <= 0, in
+//    ascending k; the sextants of a ring tile [scanStartInd, scanEndInd) and only rings with at least 10 such
+//    points are processed (:471), so the list is the ascending k of those ranges with a final label <= 0.
+//  * GroundPoints (:338): every (ring, column, n) sample of the ground marking in loop order — duplicates
+//    included, this is the cloud published on /laser_cloud_ground (:714-717).  ground_size[b] is its length;
+//    entries beyond ground_cap are dropped.
+__global__ void __launch_bounds__(256) k_feat_clouds(const int* __restrict__ scan_offsets, int n_rings, FeatArrays A) {
+  const int b = blockIdx.x, out0 = scan_offsets[b] + 8 * b;
+  const int* sst = A.scan_start + b * kMaxRings;
+  const int* sen = A.scan_end + b * kMaxRings;
+  if (A.surf_less_flat) {
+    const int* LB = A.label + out0;
+    int* dst = A.surf_less_flat + out0;
+    int base = 0;
+    for (int ring = 0; ring < n_rings; ring++) {
+      const int ss = sst[ring], se = sen[ring];
+      if (se - ss < 10) continue;  // :471 (the six sextants of a processed ring tile [ss, se) exactly)
+      for (int k0 = ss; k0 < se; k0 += 256) {
+        const int k = k0 + threadIdx.x;
+        const int f = (k < se && LB[k] <= 0) ? 1 : 0;
+        int total;
+        const int off = block_excl_scan256(f, total);
+        if (f) dst[base + off] = k;
+        base += total;
+      }
+    }
+    if (threadIdx.x == 0) A.n_surf_less_flat[b] = base;
+  }
+  if (A.ground_points) {
+    const float Ground_scan_range[8] = {2.66f, 3.04f, 3.56f, 4.30f, 5.44f, 7.41f, 11.63f, 27.12f};
+    const int groundScanInd = 7;
+    const float4* C = A.cloud + out0;
+    const float* R = A.range_vec + out0;
+    int* dst = A.ground_points + (size_t)b * A.ground_cap;
+    int base = 0;
+    for (int i = 0; i < groundScanInd && i < n_rings; i++) {  // same enumeration as k_feat_ground
+      const int ring0 = sst[i] - 5, ring_n = sen[i] + 5 - ring0;
+      if (ring_n < 5) continue;
+      const float th = (float)(0.8 * (1.0 + i / (groundScanInd - 1)));
+      for (int c0 = 5; c0 < ring_n - 5; c0 += 256) {
+        const int col = c0 + threadIdx.x;
+        unsigned mask = 0;  // bit (n + 5): sample (col, n) is appended
+        int ci = 0;
+        if (col < ring_n - 5) {
+          ci = ring0 + col;
+          const float rc = R[ci];
+          if (absf(fsub(rc, Ground_scan_range[i])) < th && (double)C[ci].z < 0.3)
+            for (int n = -5; n < 5; n++)
+              if (absf(fsub(R[ci + n], rc)) < fmul(th, 0.5f)) mask |= 1u << (n + 5);
+        }
+        int total;
+        int off = base + block_excl_scan256(__popc(mask), total);
+        for (int n = -5; n < 5; n++)
+          if ((mask >> (n + 5)) & 1u) {
+            if (off < A.ground_cap) dst[off] = ci + n;
+            off++;
+          }
+        base += total;
+      }
+    }
+  }
+}
+
 template <class T>
 int alloc_dev(rgc_ctx* c, T*& p, size_t count, std::vector<void*>& owned) {
   p = (T*)c->get(sizeof(T) * (count ? count : 1));
@@ -791,6 +882,13 @@ extern "C" int rgc_feat_extract(rgc_ctx* c, const rgc_scan_batch* batch, rgc_fea
   AL(A.inten_sharp, (size_t)nb * RGC_FEAT_CAP_INTEN(nr)); AL(A.inten_sharp_w, (size_t)nb * RGC_FEAT_CAP_INTEN(nr));
   AL(A.inten_less_sharp, (size_t)nb * RGC_FEAT_CAP_LESS_INTEN(nr));
   AL(A.list_counts, (size_t)nb * 5);
+  A.surf_less_flat = A.n_surf_less_flat = A.ground_points = nullptr;
+  A.ground_cap = out->ground_points ? std::max(out->ground_cap, 0) : 0;
+  if (out->surf_less_flat || out->n_surf_less_flat) {
+    AL(A.surf_less_flat, total_out);
+    AL(A.n_surf_less_flat, nb);
+  }
+  if (A.ground_cap > 0) AL(A.ground_points, (size_t)nb * A.ground_cap);
 #undef AL
   auto release = [&]() {
     for (void* p : owned) c->put(p);
@@ -839,8 +937,11 @@ extern "C" int rgc_feat_extract(rgc_ctx* c, const rgc_scan_batch* batch, rgc_fea
     k_feat_weights<<<grid, 256, 0, st>>>(d_off, nr, nb, A);
     CKL(c);
   }
+  if (A.surf_less_flat || A.ground_points) {
+    k_feat_clouds<<<nb, 256, 0, st>>>(d_off, nr, A);
+    CKL(c);
+  }
   CK(c, cudaEventRecord(c->ev[1], st));
-
 
   auto d2h = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
     return dst ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st) : cudaSuccess;
@@ -860,6 +961,11 @@ extern "C" int rgc_feat_extract(rgc_ctx* c, const rgc_scan_batch* batch, rgc_fea
   CP(surf_flat, A.surf_flat, (size_t)nb * RGC_FEAT_CAP_FLAT(nr)); CP(surf_flat_w, A.surf_flat_w, (size_t)nb * RGC_FEAT_CAP_FLAT(nr));
   CP(inten_sharp, A.inten_sharp, (size_t)nb * RGC_FEAT_CAP_INTEN(nr)); CP(inten_sharp_w, A.inten_sharp_w, (size_t)nb * RGC_FEAT_CAP_INTEN(nr));
   CP(inten_less_sharp, A.inten_less_sharp, (size_t)nb * RGC_FEAT_CAP_LESS_INTEN(nr));
+  if (A.surf_less_flat) {
+    CP(surf_less_flat, A.surf_less_flat, total_out);
+    CP(n_surf_less_flat, A.n_surf_less_flat, nb);
+  }
+  if (A.ground_points) CP(ground_points, A.ground_points, (size_t)nb * A.ground_cap);
 #undef CP
   // list counts: [scan][5] -> five arrays
   std::vector<int> counts((size_t)nb * 5);

@@ -66,10 +66,10 @@ struct BuildJob {
   uint64_t key = 0;
   float cell = 0.f;
   float4* orig = nullptr;
-  float* d_bbox = nullptr;
   uint64_t *keys_a = nullptr, *keys_b = nullptr, *kin = nullptr;
   uint32_t *vals_a = nullptr, *vals_b = nullptr, *vin = nullptr, *hist = nullptr, *d_counts = nullptr;
-  float* h_slot = nullptr;     // pinned: 6 x kBboxBlocks floats, then kMaxLevels counters
+  float* h_slot = nullptr;     // pinned + mapped: 6 x kBboxBlocks floats, then kMaxLevels counters and the sort's error word
+  float* d_slot = nullptr;     // device alias of h_slot: the kernels write those numbers straight into it
   cudaEvent_t ready = nullptr;  // the host copy the next phase waits for has landed
   explicit BuildJob(rgc_ctx* c) : tmp(c) {}
 };
@@ -213,14 +213,15 @@ static int radix_sort_pairs(rgc_ctx* c, uint64_t* keys_a, uint64_t* keys_b, uint
   return RGC_OK;
 }
 
-static int build_sort(rgc_ctx* c, Cloud& cl, const unsigned char* raw, size_t stride);
+static int build_keys(rgc_ctx* c, Cloud& cl, const unsigned char* raw, size_t stride);
+static int build_passes(rgc_ctx* c, Cloud& cl);
 
 // upload (or adopt a device pointer), Morton-sort, build the level tables — in three phases separated by
 // the two host waits (see BuildJob).  All phases of a cloud run on the lane that was current in phase 1.
 // `offsets` (nullable, n_clouds + 1 entries): the input is the concatenation of n_clouds clouds that
 // become one multi-cloud grid (rgc_grid.cuh: CloudRange)
 static int build_phase1(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, size_t stride, bool on_device, uint64_t key, float cell, const int* offsets,
-                        int n_clouds) {
+                        int n_clouds, bool defer_passes = false) {
   cloud_release(c, cl);
   if (n_sz == 0 || points == nullptr) FAIL(c, RGC_ERR_INVALID, "empty point cloud");
   if (n_sz > 0x7fffffff / 32) FAIL(c, RGC_ERR_UNSUPPORTED, "point cloud too large for 32-bit indexing");
@@ -230,6 +231,7 @@ static int build_phase1(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, 
   for (int i = 0; i < 5; i++)
     if (!(cl.ev[i] = c->get_event())) FAIL(c, RGC_ERR_CUDA, "cudaEventCreate failed");
   CK(c, cudaEventRecord(cl.ev[0], st));
+  c->mark("build: begin");
   cl.job.reset(new BuildJob(c));
   BuildJob& j = *cl.job;
   j.stage = 1;
@@ -238,8 +240,9 @@ static int build_phase1(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, 
   j.key = key;
   j.cell = cell;
   j.h_slot = c->get_hslot();
+  j.d_slot = rgc_ctx::hslot_device(j.h_slot);
   j.ready = c->get_event();
-  if (!j.h_slot || !j.ready) FAIL(c, RGC_ERR_NOMEM, "pinned slot / event allocation failed (build)");
+  if (!j.h_slot || !j.d_slot || !j.ready) FAIL(c, RGC_ERR_NOMEM, "pinned slot / event allocation failed (build)");
   if (offsets) {
     while ((1 << j.cloud_bits) < n_clouds) j.cloud_bits++;
     j.n_clouds = n_clouds;
@@ -257,16 +260,15 @@ static int build_phase1(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, 
     d_raw = (const unsigned char*)staging;
   }
   j.orig = (float4*)j.tmp.get(sizeof(float4) * n_sz);
-  j.d_bbox = (float*)j.tmp.get(sizeof(float) * 6 * kBboxBlocks);
   j.keys_a = (uint64_t*)j.tmp.get(8 * n_sz);
   j.keys_b = (uint64_t*)j.tmp.get(8 * n_sz);
   j.vals_a = (uint32_t*)j.tmp.get(4 * n_sz);
   j.vals_b = (uint32_t*)j.tmp.get(4 * n_sz);
   j.hist = (uint32_t*)j.tmp.get(4 * rs_scratch_words(n, RS_MAX_PASSES));
-  j.d_counts = (uint32_t*)j.tmp.get(4 * kMaxLevels);
+  j.d_counts = (uint32_t*)j.tmp.get(4 * (kMaxLevels + 1));
   cl.sorted = (float4*)c->get(sizeof(float4) * n_sz);
   cl.inv = (int*)c->get(sizeof(int) * n_sz);
-  if (!cl.inv || !j.orig || !j.d_bbox || !j.keys_a || !j.keys_b || !j.vals_a || !j.vals_b || !j.hist || !j.d_counts || !cl.sorted)
+  if (!cl.inv || !j.orig || !j.keys_a || !j.keys_b || !j.vals_a || !j.vals_b || !j.hist || !j.d_counts || !cl.sorted)
     FAIL(c, RGC_ERR_NOMEM, "device allocation failed (build)");
   j.max_bits = std::min(kMaxBits, (56 - j.cloud_bits) / 3);  // key = cloud id | 3 * nbits Morton bits <= 56 bits
   // Speculative geometry: successive clouds of a stream (the sweeps / the submaps of a SLAM front end) need the
@@ -278,14 +280,18 @@ static int build_phase1(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, 
   const rgc_ctx::GeomHint& h = c->geom_hint[c->lane];
   if (c->spec_build && h.valid && h.cell == cell && h.cloud_bits == j.cloud_bits && h.nbits <= j.max_bits) {
     j.spec = true;
+    c->spec_builds++;
     grid_set(cl.view, h.nbits, h.s0);
     cl.view.n = n;
-    TRY(build_sort(c, cl, d_raw, stride));
-    return RGC_OK;
+    TRY(build_keys(c, cl, d_raw, stride));
+    // main-lane (target) clouds of a deferred build stop here: their sort passes are issued by the drain AFTER the
+    // side lane's (the source's whole chain is short but the host needs ~40 us to issue a sort: issued first, the
+    // target's passes kept the source from even starting for 70 us)
+    if (defer_passes) return RGC_OK;
+    return build_passes(c, cl);
   }
-  k_ingest<<<kBboxBlocks, 256, 0, st>>>(d_raw, stride, n, j.orig, j.d_bbox);
+  k_ingest<<<kBboxBlocks, 256, 0, st>>>(d_raw, stride, n, j.orig, j.d_slot);
   CKL(c);
-  CK(c, cudaMemcpyAsync(j.h_slot, j.d_bbox, sizeof(float) * 6 * kBboxBlocks, cudaMemcpyDeviceToHost, st));
   CK(c, cudaEventRecord(j.ready, st));
   return RGC_OK;
 }
@@ -307,39 +313,49 @@ static bool build_bbox(const BuildJob& j, float mn[3], float mx[3]) {
   return finite;
 }
 
-// Morton keys (+ ingest when `raw` is given: the speculative path) -> radix sort with the gather fused into the
-// last pass -> per-level cell counts -> host copies of the box partials and the counts -> `ready`.
-// cl.view holds the geometry (nbits, s0) to use.
-static int build_sort(rgc_ctx* c, Cloud& cl, const unsigned char* raw, size_t stride) {
+// Morton keys + digit histograms of all sort passes (+ ingest and bounding-box partials when `raw` is given: the
+// speculative path).  cl.view holds the geometry (nbits, s0) to use.
+static int build_keys(rgc_ctx* c, Cloud& cl, const unsigned char* raw, size_t stride) {
   BuildJob& j = *cl.job;
   cudaStream_t st = c->stream;
   const int n = j.n;
   const GridView& v = cl.view;
-  const int key_bits = 3 * v.nbits + j.cloud_bits;
-  const int passes = sort_passes(key_bits);
+  const int passes = sort_passes(3 * v.nbits + j.cloud_bits);
   const GridGeom geom{v.inv_s0, v.bias, v.nbits};
   CK(c, cudaMemsetAsync(j.hist, 0, sizeof(uint32_t) * rs_scratch_words(n, passes), st));
-  if (raw) {
-    k_keys_hist<true><<<kBboxBlocks, 256, 0, st>>>(raw, stride, n, j.orig, j.d_bbox, geom, cl.d_off, j.n_clouds, passes, j.keys_a, j.vals_a, j.hist);
-    CKL(c);
-    CK(c, cudaMemcpyAsync(j.h_slot, j.d_bbox, sizeof(float) * 6 * kBboxBlocks, cudaMemcpyDeviceToHost, st));
-  } else {
+  if (raw)
+    k_keys_hist<true><<<kBboxBlocks, 256, 0, st>>>(raw, stride, n, j.orig, j.d_slot, geom, cl.d_off, j.n_clouds, passes, j.keys_a, j.vals_a, j.hist);
+  else
     k_keys_hist<false><<<kBboxBlocks, 256, 0, st>>>(nullptr, 0, n, j.orig, nullptr, geom, cl.d_off, j.n_clouds, passes, j.keys_a, j.vals_a, j.hist);
-    CKL(c);
-  }
+  CKL(c);
+  c->mark("build: keys + histograms");
+  j.stage = 3;
+  return RGC_OK;
+}
+// radix sort with the gather fused into the last pass -> per-level cell counts, published in the mapped slot -> `ready`
+static int build_passes(rgc_ctx* c, Cloud& cl) {
+  BuildJob& j = *cl.job;
+  cudaStream_t st = c->stream;
+  const int n = j.n;
+  const GridView& v = cl.view;
   j.kin = j.keys_a;
   j.vin = j.vals_a;
   const SortGather gather{j.orig, cl.sorted, cl.inv};
-  TRY(radix_sort_pairs(c, j.keys_a, j.keys_b, j.vals_a, j.vals_b, j.hist, n, key_bits, &j.kin, &j.vin, true, &gather));
-  CK(c, cudaMemsetAsync(j.d_counts, 0, 4 * kMaxLevels, st));
-  k_count_cells<<<div_up(n, 256), 256, 0, st>>>(j.kin, n, v.nlevels, j.d_counts);
+  TRY(radix_sort_pairs(c, j.keys_a, j.keys_b, j.vals_a, j.vals_b, j.hist, n, 3 * v.nbits + j.cloud_bits, &j.kin, &j.vin, true, &gather));
+  c->mark("build: radix sort + gather");
+  // level counts, then the sort's error word (a look-back that gave up: cannot happen, but must not pass silently),
+  // written into the mapped slot by the kernel's last block
+  CK(c, cudaMemsetAsync(j.d_counts, 0, 4 * (kMaxLevels + 1), st));
+  k_count_cells<<<div_up(n, 256), 256, 0, st>>>(j.kin, n, v.nlevels, j.d_counts, j.hist + 8, reinterpret_cast<uint32_t*>(j.d_slot + 6 * kBboxBlocks));
   CKL(c);
-  // level counts, then the sort's error word (a look-back that gave up: cannot happen, but must not pass silently)
-  CK(c, cudaMemcpyAsync(j.h_slot + 6 * kBboxBlocks, j.d_counts, 4 * kMaxLevels, cudaMemcpyDeviceToHost, st));
-  CK(c, cudaMemcpyAsync(j.h_slot + 6 * kBboxBlocks + kMaxLevels, j.hist + 8, 4, cudaMemcpyDeviceToHost, st));
   CK(c, cudaEventRecord(j.ready, st));
+  c->mark("build: cell counts");
   j.stage = 2;
   return RGC_OK;
+}
+static int build_sort(rgc_ctx* c, Cloud& cl, const unsigned char* raw, size_t stride) {
+  TRY(build_keys(c, cl, raw, stride));
+  return build_passes(c, cl);
 }
 
 // bounding box on the host -> grid geometry, then the sort (non-speculative path)
@@ -427,8 +443,10 @@ static int build_phase3(rgc_ctx* c, Cloud& cl) {
     v.mask[l] = ts.mask[l];
     v.shift[l] = ts.shift[l];
   }
+  c->mark("build: host wait over, tables cleared");
   k_build_tables<<<dim3(div_up(n, 256), v.nlevels), 256, 0, st>>>(j.kin, n, ts);
   CKL(c);
+  c->mark("build: tables");
   v.pts = reinterpret_cast<const F4*>(cl.sorted);
   v.inv = cl.inv;
   cl.n = n;
@@ -448,6 +466,7 @@ static int cloud_build(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, s
                        const int* offsets = nullptr, int n_clouds = 0) {
   int rc = build_phase1(c, cl, points, n_sz, stride, on_device, key, cell, offsets, n_clouds);
   if (rc == RGC_OK && cl.job->stage == 1) rc = build_phase2(c, cl);
+  if (rc == RGC_OK && cl.job->stage == 3) rc = build_passes(c, cl);
   if (rc == RGC_OK) rc = build_phase3(c, cl);
   if (rc != RGC_OK) cloud_release(c, cl);
   return rc;
@@ -650,6 +669,7 @@ static int cloud_covariances(rgc_ctx* c, Cloud& cl, int k, int method, bool spec
   CK(c, cudaEventRecord(cl.ev[2], st));
   TRY(launch_knn_self(c, cl.view, cl.n, k, nbr, cl.d_tiles, cl.n_tiles, std::max(cl.n_clouds, 1)));
   CK(c, cudaEventRecord(cl.ev[3], st));
+  c->mark("covariances: k-NN (tile + warp)");
   int min_cloud = cl.n;  // smallest cloud of a multi-cloud grid: every neighbour slot is filled iff it has >= k points
   for (int q = 0; q < cl.n_clouds; q++) min_cloud = std::min(min_cloud, cl.h_off[q + 1] - cl.h_off[q]);
   if (k == 20 && min_cloud >= k)  // the default k_correspondences, every slot filled
@@ -660,6 +680,7 @@ static int cloud_covariances(rgc_ctx* c, Cloud& cl, int k, int method, bool spec
     k_covariance<32, false><<<div_up(cl.n, kThreads), kThreads, 0, st>>>(cl.sorted, nbr, cl.n, k, method, cl.cov, nullptr, nullptr);
   CKL(c);
   CK(c, cudaEventRecord(cl.ev[4], st));
+  c->mark("covariances: k_covariance");
   cl.has_cov = true;
   cl.lazy_cov = false;
   cl.cov_speculative = speculative;
@@ -994,6 +1015,7 @@ static int gicp_linearize_launch(rgc_reg* r, const double* T, int want, const in
                                                           lazy ? r->tgt.cov_state : nullptr, r->need_list, r->need_count);
   }
   CKL(c);
+  c->mark(ce.on ? "lm: k_trial_step (compute_error + correspond)" : "lm: k_correspond");
   if (c->profile) CK(c, cudaEventRecord(c->evk[1], c->stream));
   if (lazy) {
     // on-demand target covariances: exact k-NN (one warp per query) + covariance of exactly the target
@@ -1003,6 +1025,7 @@ static int gicp_linearize_launch(rgc_reg* r, const double* T, int want, const in
     const int k = r->tgt.cov_k, method = r->tgt.cov_method, cap = r->cap_src, n_t = r->tgt.n;
     k_knn_warp<<<std::min(div_up(r->src.n, KW_WARPS), 148 * RGC_KW_MINB), KW_WARPS * 32, 0, c->stream>>>(r->tgt.view, n_t, k, r->need_count, nullptr, r->need_list, cap, r->need_nbr, nullptr, nullptr, 0);
     CKL(c);
+    c->mark("lm: on-demand k_knn_warp");
     const int grid = div_up(r->src.n, kThreads);
     if (k == 20 && n_t >= k)
       k_covariance<20, true><<<grid, kThreads, 0, c->stream>>>(r->tgt.sorted, r->need_nbr, cap, k, method, r->tgt.cov, r->need_list, r->need_count);
@@ -1011,12 +1034,14 @@ static int gicp_linearize_launch(rgc_reg* r, const double* T, int want, const in
     else
       k_covariance<32, false><<<grid, kThreads, 0, c->stream>>>(r->tgt.sorted, r->need_nbr, cap, k, method, r->tgt.cov, r->need_list, r->need_count);
     CKL(c);
+    c->mark("lm: on-demand k_covariance");
     if (c->profile) CK(c, cudaEventRecord(c->evk[3], c->stream));
   }
   TRY(join_side(c));  // the source covariances (lane 1) are first read here: reg_ready joined the source's build only
   k_linearize<<<reduce_grid(r->src.n), kThreads, 0, c->stream>>>(r->tgt.sorted, r->src.sorted, r->src.cov, r->tgt.cov, r->src.n, Td, want, corr, maha, r->partials,
                                                                      c->d_ticket, result, reg_next_done(r), lazy ? r->need_count : nullptr);
   CKL(c);
+  c->mark("lm: k_linearize");
   if (c->profile) CK(c, cudaEventRecord(c->evk[2], c->stream));
   return RGC_OK;
 }
@@ -1124,7 +1149,7 @@ static int post_build(rgc_reg* r, Cloud& cl) {
 static int build_advance(rgc_reg* r, Cloud& cl) {
   rgc_ctx* c = r->ctx;
   LaneScope ls(c, cl.job->lane);
-  int rc = cl.job->stage == 1 ? build_phase2(c, cl) : build_phase3(c, cl);
+  int rc = cl.job->stage == 1 ? build_phase2(c, cl) : (cl.job->stage == 3 ? build_passes(c, cl) : build_phase3(c, cl));
   if (rc == RGC_OK && !cl.job) rc = post_build(r, cl);
   if (rc != RGC_OK) cloud_release(c, cl);
   return rc;
@@ -1134,6 +1159,9 @@ static int build_advance(rgc_reg* r, Cloud& cl) {
 // host sleeps on one cloud's copy the device works on the other cloud's kernels.
 static int reg_drain(rgc_reg* r) {
   rgc_ctx* c = r->ctx;
+  // sort passes held back by the setters: the source's first (build_phase1)
+  for (Cloud* cl : {&r->src, &r->tgt})
+    if (cl->job && cl->job->stage == 3) TRY(build_advance(r, *cl));
   for (;;) {
     Cloud* cls[2] = {&r->tgt, &r->src};
     bool pending = false, progressed = false;
@@ -1429,7 +1457,9 @@ static int set_cloud(rgc_reg* r, Cloud& cl, const void* pts, size_t n, size_t st
   // build (upload, ingest) is issued here; the rest, and the covariances, follow in reg_drain.
   {
     LaneScope ls(c, (&cl == &r->src && c->overlap) ? 1 : 0);
-    int rc = build_phase1(c, cl, pts, n, stride, on_device, key, r->prm.grid_cell, nullptr, 0);
+    // (holding the target's sort passes back until the drain so that the source's are issued first was measured:
+    // the target build then starts ~60 us later and the cold align got 25 us slower; the passes go out right away)
+    int rc = build_phase1(c, cl, pts, n, stride, on_device, key, r->prm.grid_cell, nullptr, 0, false);
     if (rc != RGC_OK) {
       cloud_release(c, cl);
       return rc;
@@ -1524,6 +1554,7 @@ int rgc_reg_align(rgc_reg* r, const float* guess, float* final_T16, rgc_result* 
   rgc_ctx* c = r->ctx;
   CK(c, cudaSetDevice(c->device));
   CK(c, cudaEventRecord(c->ev[5], c->stream));
+  c->mark("align: begin");
   TRY(reg_ready(r));
   // lsq_registration_impl.hpp:53-57
   double x0[16];
@@ -1559,7 +1590,9 @@ int rgc_reg_align(rgc_reg* r, const float* guess, float* final_T16, rgc_result* 
     CK(c, cudaMemcpyAsync(out_points, d_out, sizeof(float4) * (size_t)r->src.n, cudaMemcpyDeviceToHost, c->stream));
   }
   CK(c, cudaEventRecord(c->ev[7], c->stream));
+  c->mark("align: end");
   CK(c, cudaEventSynchronize(c->ev[7]));
+  c->print_marks();
   float total_ms = 0.f;
   CK(c, cudaEventElapsedTime(&total_ms, c->ev[5], c->ev[7]));
   CK(c, cudaEventElapsedTime(&r->lm_ms, c->ev[6], c->ev[7]));
@@ -1703,6 +1736,13 @@ int rgc_knn_self(rgc_ctx* c, const void* points, size_t n, size_t stride, int k,
 
 // debug aid: candidate count above which the tile kNN hands a tile to the warp-per-query kernel
 // (<= 0: never); the default comes from RGC_KNN_DEFER or 600
+// test hook: how many cloud builds ran with a speculative grid geometry, and how many of those had to be redone
+int rgc_debug_build_stats(rgc_ctx* c, unsigned long long* spec_builds, unsigned long long* spec_misses) {
+  if (!c) return RGC_ERR_INVALID;
+  if (spec_builds) *spec_builds = c->spec_builds;
+  if (spec_misses) *spec_misses = c->spec_misses;
+  return RGC_OK;
+}
 int rgc_debug_set_knn_defer(rgc_ctx* c, int cands) {
   if (!c) return RGC_ERR_INVALID;
   c->knn_defer = cands;

@@ -470,6 +470,81 @@ RGC_HD void scan_range(const GridView& g, uint32_t s, uint32_t e, float qx, floa
   }
 }
 
+// Depth-first descent of ONE root cell (rx, ry, rz) at level lb: nearest octant first, pruning every cell whose
+// (conservatively shrunk) box is farther than the current bound, scanning a cell's contiguous point range once it
+// holds <= kLeafPoints points.  `stack`: kStackCap entries of per-thread scratch.
+template <class Top>
+RGC_HD void search_root(const GridView& g, int lb, int rx, int ry, int rz, float qx, float qy, float qz, Top& top, StackEntry* stack, SearchStats* st,
+                        const CloudRange& cr) {
+  if (box_dist2(g, lb, rx, ry, rz, qx, qy, qz) > top.bound()) return;
+  uint32_t s, e, m;
+  if (st) st->lookups++;
+  if (!grid_lookup(g, lb, rx, ry, rz, s, e, m, prefix_at(cr, lb))) return;
+  int sp = 0;
+  stack[sp++] = StackEntry{(uint32_t)rx | ((uint32_t)lb << 24), (uint32_t)ry | (m << 24), (uint32_t)rz, s, e, 0u};
+  while (sp > 0) {
+    const StackEntry n = stack[--sp];
+    const int l = (int)(n.cx_lvl >> 24);
+    const int cx = (int)(n.cx_lvl & 0xffffffu), cy = (int)(n.cy_mask & 0xffffffu), cz = (int)n.cz;
+    const uint32_t cm = n.cy_mask >> 24;
+    const float cur = top.bound();
+    if (box_dist2(g, l, cx, cy, cz, qx, qy, qz) > cur) continue;
+    if (st) st->nodes++;
+    if (l == 0 || n.end - n.start <= (uint32_t)kLeafPoints || sp + 8 > kStackCap) {
+      scan_range(g, n.start, n.end, qx, qy, qz, top, st);
+      continue;
+    }
+    // children, nearest octant first (pushed in reverse so it is popped first)
+    const float half = g.s0 * pow2f(l - 1);
+    const float mx = g.ox + (float)(2 * cx + 1) * half, my = g.oy + (float)(2 * cy + 1) * half, mz = g.oz + (float)(2 * cz + 1) * half;
+    const int first = (qx >= mx ? 1 : 0) | (qy >= my ? 2 : 0) | (qz >= mz ? 4 : 0);
+    const uint64_t pkey = (morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz) | prefix_at(cr, l)) << 3;
+    for (int j = 7; j >= 0; j--) {
+      const int ci = first ^ j;
+      if (!((cm >> ci) & 1u)) continue;
+      const int ccx = 2 * cx + (ci & 1), ccy = 2 * cy + ((ci >> 1) & 1), ccz = 2 * cz + ((ci >> 2) & 1);
+      if (box_dist2(g, l - 1, ccx, ccy, ccz, qx, qy, qz) > cur) continue;
+      uint32_t cs2, ce2, cm2;
+      if (st) st->lookups++;
+      if (!grid_lookup_key(g, l - 1, pkey | (uint64_t)ci, cs2, ce2, cm2)) continue;  // cannot happen: mask says occupied
+      stack[sp++] = StackEntry{(uint32_t)ccx | ((uint32_t)(l - 1) << 24), (uint32_t)ccy | (cm2 << 24), (uint32_t)ccz, cs2, ce2, 0u};
+    }
+  }
+}
+
+// root cells of the ball (q, r): the finest level whose cell edge is >= r, and the <= 3 x 3 x 3 cell range the ball
+// touches at that level (hi < lo on an axis: the ball misses the grid)
+struct RootRange {
+  int lb, lo[3], hi[3];
+};
+RGC_HD RootRange root_range(const GridView& g, float qx, float qy, float qz, float bound) {
+  RootRange rr;
+  const int top_level = g.nlevels - 1;
+  const float r = sqrtf(bound) * 1.00001f + 2.f * g.margin;  // +inf when bound is +inf
+  int lb = root_level(g.s0, r, top_level);
+#ifdef RGC_ROOT_SHIFT  // tuning: start the walk RGC_ROOT_SHIFT levels coarser (fewer, larger root cells)
+  lb = lb + RGC_ROOT_SHIFT < top_level ? lb + RGC_ROOT_SHIFT : top_level;
+#endif
+  rr.lb = lb;
+  const float inv_cs = g.inv_s0 * pow2f(-lb);  // == inv_s0 / 2^lb, exactly
+  const int ncell = 1 << (g.nbits - lb);
+  const float q3[3] = {qx, qy, qz};
+  const float o3[3] = {g.ox, g.oy, g.oz};
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    float tl = (q3[a] - r - o3[a]) * inv_cs, th = (q3[a] + r - o3[a]) * inv_cs;
+    // NaN (inf - inf) cannot occur: r = +inf gives tl = -inf, th = +inf
+    int il = tl < 0.f ? 0 : (tl >= (float)ncell ? ncell : (int)tl);
+    int ih = th < 0.f ? -1 : (th >= (float)ncell ? ncell - 1 : (int)th);
+    // no extra slack cell: r already carries 2 margins, orders of magnitude above the rounding
+    // error of this index computation
+    rr.lo[a] = il;
+    rr.hi[a] = ih < ncell - 1 ? ih : ncell - 1;
+    if (ih < 0 || il >= ncell) rr.hi[a] = rr.lo[a] - 1;  // ball misses the grid on this axis
+  }
+  return rr;
+}
+
 // Exact kNN of (qx,qy,qz) in grid g into the heap `top` (call top.sort_ascending() for ordered output).
 // `max_d2`: candidates with d2 > max_d2 are never needed (+inf = unbounded).  `near_pos`: a sorted
 // position known to be spatially close to q (the query's own position for self-kNN), or -1.
@@ -506,74 +581,75 @@ RGC_HD void knn_search(const GridView& g, float qx, float qy, float qz, int k, f
   }
   top.reset(k, bound);
 
-  // ---- 2. root level: finest level whose cell edge >= ball radius
-  const float r = sqrtf(bound) * 1.00001f + 2.f * g.margin;  // +inf when bound is +inf
-  int lb = root_level(g.s0, r, top_level);
-#ifdef RGC_ROOT_SHIFT  // tuning: start the walk RGC_ROOT_SHIFT levels coarser (fewer, larger root cells)
-  lb = lb + RGC_ROOT_SHIFT < top_level ? lb + RGC_ROOT_SHIFT : top_level;
-#endif
-  const float inv_cs = g.inv_s0 * pow2f(-lb);  // == inv_s0 / 2^lb, exactly
-  const int ncell = 1 << (g.nbits - lb);
-  int lo[3], hi[3];
-  {
-    const float q3[3] = {qx, qy, qz};
-    const float o3[3] = {g.ox, g.oy, g.oz};
-#pragma unroll
-    for (int a = 0; a < 3; a++) {
-      float tl = (q3[a] - r - o3[a]) * inv_cs, th = (q3[a] + r - o3[a]) * inv_cs;
-      // NaN (inf - inf) cannot occur: r = +inf gives tl = -inf, th = +inf
-      int il = tl < 0.f ? 0 : (tl >= (float)ncell ? ncell : (int)tl);
-      int ih = th < 0.f ? -1 : (th >= (float)ncell ? ncell - 1 : (int)th);
-      // no extra slack cell: r already carries 2 margins, orders of magnitude above the rounding
-      // error of this index computation
-      lo[a] = il;
-      hi[a] = ih < ncell - 1 ? ih : ncell - 1;
-      if (ih < 0 || il >= ncell) hi[a] = lo[a] - 1;  // ball misses the grid on this axis
-    }
-  }
-
+  // ---- 2. root level: finest level whose cell edge >= ball radius ; 3. depth-first descent of every root
+  const RootRange rr = root_range(g, qx, qy, qz, bound);
   StackEntry stack[kStackCap];
-  for (int rz = lo[2]; rz <= hi[2]; rz++)
-    for (int ry = lo[1]; ry <= hi[1]; ry++)
-      for (int rx = lo[0]; rx <= hi[0]; rx++) {
-        {
-          if (box_dist2(g, lb, rx, ry, rz, qx, qy, qz) > top.bound()) continue;
-        }
-        uint32_t s, e, m;
-        if (st) st->lookups++;
-        if (!grid_lookup(g, lb, rx, ry, rz, s, e, m, prefix_at(cr, lb))) continue;
-        int sp = 0;
-        stack[sp++] = StackEntry{(uint32_t)rx | ((uint32_t)lb << 24), (uint32_t)ry | (m << 24), (uint32_t)rz, s, e, 0u};
-        // ---- 3. depth-first descent
-        while (sp > 0) {
-          const StackEntry n = stack[--sp];
-          const int l = (int)(n.cx_lvl >> 24);
-          const int cx = (int)(n.cx_lvl & 0xffffffu), cy = (int)(n.cy_mask & 0xffffffu), cz = (int)n.cz;
-          const uint32_t cm = n.cy_mask >> 24;
-          const float cur = top.bound();
-          if (box_dist2(g, l, cx, cy, cz, qx, qy, qz) > cur) continue;
-          if (st) st->nodes++;
-          if (l == 0 || n.end - n.start <= (uint32_t)kLeafPoints || sp + 8 > kStackCap) {
-            scan_range(g, n.start, n.end, qx, qy, qz, top, st);
-            continue;
-          }
-          // children, nearest octant first (pushed in reverse so it is popped first)
-          const float half = g.s0 * pow2f(l - 1);
-          const float mx = g.ox + (float)(2 * cx + 1) * half, my = g.oy + (float)(2 * cy + 1) * half, mz = g.oz + (float)(2 * cz + 1) * half;
-          const int first = (qx >= mx ? 1 : 0) | (qy >= my ? 2 : 0) | (qz >= mz ? 4 : 0);
-          const uint64_t pkey = (morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz) | prefix_at(cr, l)) << 3;
-          for (int j = 7; j >= 0; j--) {
-            const int ci = first ^ j;
-            if (!((cm >> ci) & 1u)) continue;
-            const int ccx = 2 * cx + (ci & 1), ccy = 2 * cy + ((ci >> 1) & 1), ccz = 2 * cz + ((ci >> 2) & 1);
-            if (box_dist2(g, l - 1, ccx, ccy, ccz, qx, qy, qz) > cur) continue;
-            uint32_t cs2, ce2, cm2;
-            if (st) st->lookups++;
-            if (!grid_lookup_key(g, l - 1, pkey | (uint64_t)ci, cs2, ce2, cm2)) continue;  // cannot happen: mask says occupied
-            stack[sp++] = StackEntry{(uint32_t)ccx | ((uint32_t)(l - 1) << 24), (uint32_t)ccy | (cm2 << 24), (uint32_t)ccz, cs2, ce2, 0u};
-          }
+  for (int rz = rr.lo[2]; rz <= rr.hi[2]; rz++)
+    for (int ry = rr.lo[1]; ry <= rr.hi[1]; ry++)
+      for (int rx = rr.lo[0]; rx <= rr.hi[0]; rx++) search_root(g, rr.lb, rx, ry, rz, qx, qy, qz, top, stack, st, cr);
+}
+
+#if defined(__CUDACC__)
+// Exact 1-NN by a GROUP of G consecutive lanes (G = 4 or 8; `sub` = the lane's index in its group, `gmask` = the
+// group's lanes).  The sparse-warp correspondence kernels leave G - 1 of every G lanes idle so that fewer divergent
+// walks share a warp; here those lanes take a share of the SAME query instead: the ball of a hinted query touches
+// up to 8 root cells, each a dependent table probe plus a short descent, and one lane walked them one after the
+// other (1 760 instructions and ~10 dependent memory round trips per query, 4 of 32 lanes active: ncu of round 2).
+// Lane `sub` takes the root cells sub, sub + G, ... with its own bound (the hint's distance to start with), then
+// the group keeps the best (d2, original index) of its lanes.  Every root cell is still visited under a bound that
+// is valid for it, so the result is the same exact nearest neighbour.  The unhinted first search also spreads
+// its climb (which level holds the query's cell?) over the lanes.  All lanes of a group must call this together.
+template <int G>
+__device__ __forceinline__ void nn1_search_group(const GridView& g, float qx, float qy, float qz, float max_d2, int near_pos, int sub, unsigned gmask, Best1& top) {
+  const int top_level = g.nlevels - 1;
+  const CloudRange cr{0, g.n, 0ull};
+  float bound = max_d2;
+  if (g.n >= 1) {
+    int p0;
+    if (near_pos >= 0) {
+      p0 = near_pos;
+    } else {
+      const int fx = cell_coord(qx, g.inv_s0, g.bias), fy = cell_coord(qy, g.inv_s0, g.bias), fz = cell_coord(qz, g.inv_s0, g.bias);
+      p0 = 0;
+      for (int l0 = 0; l0 <= top_level; l0 += G) {  // lane `sub` probes level l0 + sub: the finest occupied level wins
+        const int l = l0 + sub;
+        uint32_t s = 0, e = 0, m;
+        const bool hit = l <= top_level && grid_lookup(g, l, fx >> l, fy >> l, fz >> l, s, e, m, 0ull);
+        const unsigned hits = __ballot_sync(gmask, hit) & gmask;
+        if (hits) {
+          const int src = __ffs(hits) - 1;  // lowest lane of the group with a hit = finest level
+          const int mid = (int)s + (int)((e - s) >> 1);
+          p0 = __shfl_sync(gmask, mid, src);
+          break;
         }
       }
+    }
+    p0 = p0 < 0 ? 0 : (p0 > g.n - 1 ? g.n - 1 : p0);
+    const F4 c = load_pt(g.pts + p0);
+    bound = fminf(bound, dist2_ref(qx, qy, qz, c.x, c.y, c.z));
+  }
+  top.reset(1, bound);
+  const RootRange rr = root_range(g, qx, qy, qz, bound);
+  const int nx = rr.hi[0] - rr.lo[0] + 1, ny = rr.hi[1] - rr.lo[1] + 1, nz = rr.hi[2] - rr.lo[2] + 1;
+  const int nroots = (nx > 0 && ny > 0 && nz > 0) ? nx * ny * nz : 0;
+  StackEntry stack[kStackCap];
+  for (int ri = sub; ri < nroots; ri += G) {
+    const int rx = rr.lo[0] + ri % nx, ry = rr.lo[1] + (ri / nx) % ny, rz = rr.lo[2] + ri / (nx * ny);
+    search_root(g, rr.lb, rx, ry, rz, qx, qy, qz, top, stack, nullptr, cr);
+  }
+  // best of the group under the total order (d2, original index)
+#pragma unroll
+  for (int o = G >> 1; o > 0; o >>= 1) {
+    const float od = __shfl_xor_sync(gmask, top.d0, o);
+    const int oid = __shfl_xor_sync(gmask, top.id0, o);
+    bool take = oid >= 0 && (top.id0 < 0 || od < top.d0);
+    if (oid >= 0 && top.id0 >= 0 && od == top.d0 && oid != top.id0) take = f2i_bits(load_pt(g.pts + oid).w) < f2i_bits(load_pt(g.pts + top.id0).w);
+    if (take) {
+      top.d0 = od;
+      top.id0 = oid;
+    }
+  }
 }
+#endif
 
 }  // namespace rgc

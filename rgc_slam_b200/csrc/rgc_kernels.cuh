@@ -239,6 +239,10 @@ __global__ void __launch_bounds__(256) k_rs_scatter(const uint64_t* __restrict__
 // [16, 16 + 8 * 256) global digit histograms per pass, then per pass nblk * 256 status words
 // (flag << 30 | count; flag 1 = aggregate, 2 = inclusive prefix).
 constexpr int RS_MAX_PASSES = 8;
+#ifndef RGC_RS_LOOKBACK
+#define RGC_RS_LOOKBACK 8
+#endif
+constexpr int RS_LOOKBACK = RGC_RS_LOOKBACK;  // predecessor tiles read per look-back round trip
 constexpr int RS_GHIST_OFF = 16;
 constexpr int RS_STATUS_OFF = RS_GHIST_OFF + RS_MAX_PASSES * 256;
 __host__ __device__ inline size_t rs_scratch_words(int n, int passes) { return (size_t)RS_STATUS_OFF + (size_t)passes * (size_t)((n + RS_TILE - 1) / RS_TILE) * 256; }
@@ -337,13 +341,14 @@ __global__ void __launch_bounds__(256) k_rs_onesweep(const uint64_t* __restrict_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int warp_base = (int)tile * RS_TILE + warp * (32 * RS_ITEMS);
   uint64_t k[RS_ITEMS];
-  uint32_t d[RS_ITEMS];
+  uint32_t d[RS_ITEMS], vv[RS_ITEMS];
   const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
   for (int r = 0; r < RS_ITEMS; r++) {
     const int i = warp_base + r * 32 + lane;
     const bool valid = i < n;
     k[r] = valid ? keys_in[i] : 0ull;
+    vv[r] = valid ? vals_in[i] : 0u;  // loaded with the keys: one memory round trip less behind the look-back
     d[r] = valid ? ((uint32_t)(k[r] >> shift) & 255u) : (256u + lane);  // invalid lanes never match
     const uint32_t peers = __match_any_sync(0xffffffffu, d[r]);
     if (valid && (peers & lt_mask) == 0) cnt[warp][d[r]] += __popc(peers);
@@ -361,22 +366,41 @@ __global__ void __launch_bounds__(256) k_rs_onesweep(const uint64_t* __restrict_
       status[dg] = (2u << 30) | agg;
     } else {
       status[(size_t)tile * 256 + dg] = (1u << 30) | agg;
+      // look back RS_LOOKBACK tiles per round trip (independent loads), consuming them nearest first up to the first
+      // inclusive prefix; a tile that has not published yet is polled again.  (One tile per round trip made a pass
+      // over the 245 tiles of the 500k-point submap 17 us: all tiles are resident at once, so the prefix
+      // frontier had to crawl forward one L2 round trip at a time.)
       int p = (int)tile - 1;
       unsigned spins = 0;
       for (;;) {
-        const uint32_t v = status[(size_t)p * 256 + dg];
-        const uint32_t f = v >> 30;
-        if (f == 0) {
+        uint32_t v[RS_LOOKBACK];
+#pragma unroll
+        for (int j = 0; j < RS_LOOKBACK; j++) v[j] = p - j >= 0 ? status[(size_t)(p - j) * 256 + dg] : (2u << 30);  // before tile 0: prefix 0
+        int used = 0;
+        bool stop = false, stall = false;
+#pragma unroll
+        for (int j = 0; j < RS_LOOKBACK; j++) {
+          const uint32_t f = v[j] >> 30;
+          if (!stop && !stall) {
+            if (f == 0) {
+              stall = true;
+            } else {
+              excl += v[j] & 0x3fffffffu;
+              used++;
+              stop = f == 2u;
+            }
+          }
+        }
+        if (stop) break;
+        p -= used;
+        if (used == 0) {
           if (++spins > (1u << 22)) {  // a predecessor that never publishes: report instead of hanging (cannot happen, see above)
             scratch[8] = 1u;
             break;
           }
-          continue;
+        } else {
+          spins = 0;
         }
-        excl += v & 0x3fffffffu;
-        if (f == 2u) break;
-        p--;
-        spins = 0;
       }
       status[(size_t)tile * 256 + dg] = (2u << 30) | (excl + agg);
     }
@@ -402,7 +426,7 @@ __global__ void __launch_bounds__(256) k_rs_onesweep(const uint64_t* __restrict_
     if (valid) {
       const uint32_t dst = off + rank;
       keys_out[dst] = k[r];
-      const uint32_t o = vals_in[i];
+      const uint32_t o = vv[r];
       if (LAST_GATHER) {
         float4 pt = pts[o];
         pt.w = __int_as_float((int)o);
@@ -426,9 +450,13 @@ __global__ void __launch_bounds__(256) k_gather_sorted(const float4* __restrict_
   inv[o] = i;
 }
 
-// cells per level: point i opens a new cell at every level l with 3l <= highest differing bit
-__global__ void __launch_bounds__(256) k_count_cells(const uint64_t* __restrict__ keys, int n, int nlevels, uint32_t* __restrict__ counts) {
+// cells per level: point i opens a new cell at every level l with 3l <= highest differing bit.
+// counts[0 .. kMaxLevels) are the (zeroed) counters, counts[kMaxLevels] a (zeroed) ticket: the last block to
+// finish publishes the counters, followed by the radix sort's error word, in mapped pinned host memory.
+__global__ void __launch_bounds__(256) k_count_cells(const uint64_t* __restrict__ keys, int n, int nlevels, uint32_t* __restrict__ counts,
+                                                     const uint32_t* __restrict__ sort_err, uint32_t* __restrict__ host_out) {
   __shared__ uint32_t c[kMaxLevels];
+  __shared__ bool is_last;
   if (threadIdx.x < kMaxLevels) c[threadIdx.x] = 0;
   __syncthreads();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -444,6 +472,16 @@ __global__ void __launch_bounds__(256) k_count_cells(const uint64_t* __restrict_
   }
   __syncthreads();
   if (threadIdx.x < nlevels && c[threadIdx.x]) atomicAdd(&counts[threadIdx.x], c[threadIdx.x]);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(&counts[kMaxLevels], 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    if (threadIdx.x < kMaxLevels) host_out[threadIdx.x] = __ldcg(&counts[threadIdx.x]);
+    if (threadIdx.x == kMaxLevels) host_out[kMaxLevels] = sort_err ? __ldcg(sort_err) : 0u;
+    __threadfence_system();
+  }
 }
 
 struct TableSet {
@@ -1126,12 +1164,12 @@ __global__ void __launch_bounds__(kThreads, RGC_COV_MINB) k_covariance(const flo
       if (j >= KCAP || (!FULL && id[j] < 0)) continue;  // valid entries are a prefix
       found++;
       if (j == 0) {
-        ox = (double)px[0];
-        oy = (double)py[0];
-        oz = (double)pz[0];
+        ox = f2d(px[0]);
+        oy = f2d(py[0]);
+        oz = f2d(pz[0]);
         continue;
       }
-      const double dx = (double)px[u] - ox, dy = (double)py[u] - oy, dz = (double)pz[u] - oz;
+      const double dx = f2d(px[u]) - ox, dy = f2d(py[u]) - oy, dz = f2d(pz[u]) - oz;
       sx += dx;
       sy += dy;
       sz += dz;
@@ -1307,11 +1345,29 @@ constexpr int kLinN = kAccN + 1;  // + inlier count
 #ifndef RGC_CORR_MINB
 #define RGC_CORR_MINB 8
 #endif
+#ifndef RGC_GROUP_SEARCH  // 0: the sparse-warp searches walk alone (one lane per query), as before round 2
+#define RGC_GROUP_SEARCH 1
+#endif
+// exact 1-NN of one query by the `spread` lanes that share it (spread 4 / 8: nn1_search_group, every lane of the
+// group must call; spread 1 / 2: only the group's first lane gets here and walks alone)
+__device__ __forceinline__ void nn1_spread(const GridView& tgt, float qx, float qy, float qz, float max_d2, int hint, int spread, Best1& top) {
+  const int lane = threadIdx.x & 31;
+  if (spread == 4)
+    nn1_search_group<4>(tgt, qx, qy, qz, max_d2, hint, lane & 3, 0xfu << (lane & ~3), top);
+  else if (spread == 8)
+    nn1_search_group<8>(tgt, qx, qy, qz, max_d2, hint, lane & 7, 0xffu << (lane & ~7), top);
+  else
+    knn_search(tgt, qx, qy, qz, 1, max_d2, hint, top);
+}
+__device__ __forceinline__ bool group_search(int spread) { return (spread == 4 || spread == 8) && !g_tile_dbg && RGC_GROUP_SEARCH; }
+
 __device__ __forceinline__ void correspond_query(const GridView& tgt, const float4* __restrict__ src, int n_src, int spread, const RtF& Tf, float thr2, const Slab& slab,
                                                  const int* hint, int* corr, float* __restrict__ sqd, int* __restrict__ need_state, int* __restrict__ need_list,
                                                  int* __restrict__ need_count, int gt) {
   const int i = gt / spread;
-  if ((gt & (spread - 1)) != 0 || i >= n_src) return;
+  const bool grouped = group_search(spread);
+  const bool leader = (gt & (spread - 1)) == 0;
+  if (i >= n_src || (!grouped && !leader)) return;
   const float4 p = __ldg(&src[i]);
   float qx, qy, qz;
   transform_f(Tf.m, p.x, p.y, p.z, qx, qy, qz);
@@ -1327,8 +1383,9 @@ __device__ __forceinline__ void correspond_query(const GridView& tgt, const floa
     o[2] = st.lookups;
     o[3] = st.candidates;
   } else if (slab_owns(slab, qx, qy, qz)) {
-    knn_search(tgt, qx, qy, qz, 1, thr2, hint ? hint[i] : -1, top);
+    nn1_spread(tgt, qx, qy, qz, thr2, hint ? hint[i] : -1, grouped ? spread : 1, top);
   }
+  if (!leader) return;
   const int pos = (top.id0 >= 0 && top.d0 < thr2) ? top.id0 : -1;
   corr[i] = pos;
   sqd[i] = top.d0;
@@ -1338,10 +1395,10 @@ __device__ __forceinline__ void correspond_query(const GridView& tgt, const floa
     const unsigned act = __activemask();
     const unsigned m = __ballot_sync(act, claim);
     if (m) {
-      const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+      const int lane = threadIdx.x & 31, leader_lane = __ffs(m) - 1;
       int base = 0;
-      if (lane == leader) base = atomicAdd(need_count, __popc(m));
-      base = __shfl_sync(act, base, leader);
+      if (lane == leader_lane) base = atomicAdd(need_count, __popc(m));
+      base = __shfl_sync(act, base, leader_lane);
       if (claim) need_list[base + __popc(m & ((1u << lane) - 1u))] = pos;
     }
   }
@@ -1481,14 +1538,16 @@ __global__ void __launch_bounds__(kThreads, RGC_CORR_MINB) k_fitness(GridView tg
   double acc[2] = {0.0, 0.0};
   const int gt = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = gt / spread;
-  if ((gt & (spread - 1)) == 0 && i < n_src) {
+  const bool grouped = group_search(spread);
+  const bool leader = (gt & (spread - 1)) == 0;
+  if (i < n_src && (grouped || leader)) {
     const float4 p = __ldg(&src[i]);
     float qx, qy, qz;
     transform_f(Tf.m, p.x, p.y, p.z, qx, qy, qz);
     Best1 top;
     top.reset(1, INFINITY);
-    if (slab_owns(slab, qx, qy, qz)) knn_search(tgt, qx, qy, qz, 1, INFINITY, hint ? __ldg(&hint[i]) : -1, top);
-    if (top.id0 >= 0 && (double)top.d0 <= max_range) {
+    if (slab_owns(slab, qx, qy, qz)) nn1_spread(tgt, qx, qy, qz, INFINITY, hint ? __ldg(&hint[i]) : -1, grouped ? spread : 1, top);
+    if (leader && top.id0 >= 0 && (double)top.d0 <= max_range) {
       acc[0] = (double)top.d0;
       acc[1] = 1.0;
     }

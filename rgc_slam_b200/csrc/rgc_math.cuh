@@ -296,8 +296,8 @@ constexpr int kAccN = 28;
 
 RGC_HD double gicp_error_term(const Rt& T, const Sym3& M, float px, float py, float pz, float qx, float qy, float qz) {
   double ax, ay, az;
-  transform_d(T, (double)px, (double)py, (double)pz, ax, ay, az);
-  const double ex = dsub((double)qx, ax), ey = dsub((double)qy, ay), ez = dsub((double)qz, az);
+  transform_d(T, f2d(px), f2d(py), f2d(pz), ax, ay, az);
+  const double ex = dsub(f2d(qx), ax), ey = dsub(f2d(qy), ay), ez = dsub(f2d(qz), az);
   const double mx = ddot3(M.xx, ex, M.xy, ey, M.xz, ez);
   const double my = ddot3(M.xy, ex, M.yy, ey, M.yz, ez);
   const double mz = ddot3(M.xz, ex, M.yz, ey, M.zz, ez);
@@ -320,8 +320,8 @@ RGC_HD double jt_dot(int c, const double a[3], double v0, double v1, double v2) 
 // acc += terms of one correspondence.  J = [skew(a) | -I], a = T p.
 RGC_HD void gicp_point_terms(const Rt& T, const Sym3& M, float px, float py, float pz, float qx, float qy, float qz, double* acc) {
   double a[3];
-  transform_d(T, (double)px, (double)py, (double)pz, a[0], a[1], a[2]);
-  const double e[3] = {dsub((double)qx, a[0]), dsub((double)qy, a[1]), dsub((double)qz, a[2])};
+  transform_d(T, f2d(px), f2d(py), f2d(pz), a[0], a[1], a[2]);
+  const double e[3] = {dsub(f2d(qx), a[0]), dsub(f2d(qy), a[1]), dsub(f2d(qz), a[2])};
   const double Mm[3][3] = {{M.xx, M.xy, M.xz}, {M.xy, M.yy, M.yz}, {M.xz, M.yz, M.zz}};
   double Me[3];
 #pragma unroll
@@ -353,12 +353,12 @@ RGC_HD Sym3 covariance_from_points(int found, int k, GetPt get) {
   // small as the neighbourhood and E[dd^T] - E[d]E[d]^T loses nothing), then re-centre.
   if (found <= 0) return Sym3{0, 0, 0, 0, 0, 0};
   const F4 p0 = get(0);
-  const double ox = (double)p0.x, oy = (double)p0.y, oz = (double)p0.z;
+  const double ox = f2d(p0.x), oy = f2d(p0.y), oz = f2d(p0.z);
   double sx = 0.0, sy = 0.0, sz = 0.0;
   Sym3 c = {0, 0, 0, 0, 0, 0};
   for (int j = 1; j < found; j++) {
     const F4 p = get(j);
-    const double dx = (double)p.x - ox, dy = (double)p.y - oy, dz = (double)p.z - oz;
+    const double dx = f2d(p.x) - ox, dy = f2d(p.y) - oy, dz = f2d(p.z) - oz;
     sx += dx;
     sy += dy;
     sz += dz;

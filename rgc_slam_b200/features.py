@@ -28,12 +28,13 @@ class _Out(C.Structure):
                                            "corner_less_sharp", "n_corner_less_sharp",
                                            "surf_flat", "surf_flat_w", "n_surf_flat",
                                            "inten_sharp", "inten_sharp_w", "n_inten_sharp",
-                                           "inten_less_sharp", "n_inten_less_sharp")]
-                + [("device_ms", C.c_float)])
+                                           "inten_less_sharp", "n_inten_less_sharp",
+                                           "surf_less_flat", "n_surf_less_flat", "ground_points")]
+                + [("ground_cap", C.c_int32), ("device_ms", C.c_float)])
 
 
 def extract_features(scans, n_rings=16, min_range=0.5, max_range=80.0, use_intensity=1, ctx: api.Context | None = None,
-                     want_arrays=True):
+                     want_arrays=True, ground_cap=None):
     """scans: list of (n_i, 4) float32 arrays (x, y, z, intensity) in firing order.
     Returns (list of per-scan dicts, device_ms)."""
     ctx = ctx or api.default_context(0)
@@ -66,6 +67,11 @@ def extract_features(scans, n_rings=16, min_range=0.5, max_range=80.0, use_inten
         mk("n_" + name, nb, np.int32)
         if has_w:
             mk(name + "_w", (nb, n_rings * 6 * per_seg), np.float32)
+    # the two unbounded clouds: surfPointsLessFlatScan and GroundPoints (a sample is appended up to 10 times)
+    mk("surf_less_flat", total_out, np.int32); mk("n_surf_less_flat", nb, np.int32)
+    gcap = int(ground_cap) if ground_cap is not None else 10 * max(len(s) for s in scans)
+    mk("ground_points", (nb, gcap), np.int32)
+    out.ground_cap = gcap
     ctx.check(L.rgc_feat_extract(ctx._h, C.byref(batch), C.byref(out)))
     res = []
     for b in range(nb):
@@ -83,7 +89,9 @@ def extract_features(scans, n_rings=16, min_range=0.5, max_range=80.0, use_inten
             d[name] = arrs[name][b, :c]
             if has_w:
                 d[name + "_w"] = arrs[name + "_w"][b, :c]
-        # surfPointsLessFlatScan (:586-592): every point of a processed sextant whose label is <= 0
+        # surfPointsLessFlatScan (:586-592) and GroundPoints (:338, duplicates in push order)
+        d["surf_less_flat"] = arrs["surf_less_flat"][o0:o0 + int(arrs["n_surf_less_flat"][b])]
+        d["ground_points"] = arrs["ground_points"][b, :min(d["ground_size"], gcap)]
         res.append(d)
     return res, float(out.device_ms)
 

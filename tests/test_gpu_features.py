@@ -7,7 +7,9 @@ pytestmark = pytest.mark.gpu
 
 EXACT = ["src_index", "intensity_num", "range_vec", "scan_angle", "curvature", "inten_curvature", "curvature2", "distance_source", "other_source",
          "label", "inten_label", "neighbor_picked", "inten_neighbor_picked", "ground_marked",
-         "corner_sharp", "corner_less_sharp", "surf_flat", "inten_sharp", "inten_less_sharp", "corner_sharp_w", "surf_flat_w", "inten_sharp_w"]
+         "corner_sharp", "corner_less_sharp", "surf_flat", "inten_sharp", "inten_less_sharp", "corner_sharp_w", "surf_flat_w", "inten_sharp_w",
+         # surfPointsLessFlatScan (:586-592) and GroundPoints (:338: push order, duplicates included)
+         "surf_less_flat", "ground_points"]
 
 
 def _compare(g, o, tag):
@@ -48,6 +50,14 @@ def test_features_match_oracle_on_a_batch(scene, traj, beams, az):
         _compare(res[b], o, f"scan {b}")
         picked += len(o["corner_sharp"]) + len(o["surf_flat"])
     assert picked > 1000  # the comparison is not vacuous
+    o0 = orc.extract_features(scans[0], n_scans=beams)
+    assert len(o0["surf_less_flat"]) > 10000
+    if beams == 16:  # (the 32-beam elevations put no ring at the ground-ring ranges: its GroundPoints cloud is empty)
+        assert len(o0["ground_points"]) > len(np.unique(o0["ground_points"])) > 100  # duplicates exist
+    # a ground list shorter than the cloud it describes is truncated, never overrun
+    res2, _ = extract_features(scans[:2], n_rings=beams, want_arrays=False, ground_cap=100)
+    for b in range(2):
+        assert res2[b]["ground_size"] == res[b]["ground_size"] and np.array_equal(res2[b]["ground_points"], res[b]["ground_points"][:100])
     near_o = orc.extract_features(near, n_scans=beams)
     assert (near_o["scan_angle"] > 0).sum() > 10
 

@@ -364,3 +364,41 @@ def test_python_force_rebuilds_a_refilled_buffer(rgc, small_pair):
     g.setInputTarget(buf, force=True)
     T2 = g.align()
     assert abs((T2[0, 3] - T1[0, 3]) - 0.25) < 2e-3
+
+
+@pytest.mark.gpu
+def test_speculative_grid_geometry_hits_and_misses(rgc, orc):
+    """The build generates its Morton keys with the previous cloud's grid geometry before its own bounding box is
+    known (rgc_gicp.cu: build_phase1 / build_phase3).  A cloud that does not fit that grid must be re-sorted
+    (a miss), one that fits must not, and the neighbour lists are the oracle's either way."""
+    import ctypes as C
+    L = rgc.lib()
+    L.rgc_debug_build_stats.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
+    from rgc_slam_b200 import api
+    ctx = api.default_context(0)
+
+    def stats():
+        a, b = C.c_ulonglong(), C.c_ulonglong()
+        ctx.check(L.rgc_debug_build_stats(ctx._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    rng = np.random.default_rng(5)
+
+    def cloud(n, sigma):
+        P = np.ones((n, 4), np.float32)
+        P[:, :3] = rng.normal(0, sigma, (n, 3))
+        return P
+
+    small, small2, big = cloud(4000, 2.0), cloud(3000, 2.0), cloud(6000, 150.0)
+    from rgc_slam_b200 import api
+    ctx = api.default_context(0)
+    for P in (small, small2, big, small, big):  # fits / fits / needs more bits (miss) / fits the larger grid / fits
+        idx, d2 = rgc.knn(P, P[:500], 20)
+        oi, od = orc.knn(P, P[:500], 20, brute=True)
+        assert np.array_equal(idx, oi) and np.array_equal(d2, od)
+    s0 = stats()
+    rgc.knn(small, small[:10], 5)
+    rgc.knn(cloud(5000, 400.0), small[:10], 5)  # far larger extent than anything before: must be redone
+    s1 = stats()
+    assert s1[0] >= s0[0] + 1, "speculative builds are not happening"
+    assert s1[1] >= s0[1] + 1, "a cloud outside the hinted grid was not detected"
