@@ -53,7 +53,7 @@ typedef enum {
   RGC_ERR_CUDA = -1,        /* a CUDA call failed (message has the CUDA error string) */
   RGC_ERR_INVALID = -2,     /* bad argument */
   RGC_ERR_STATE = -3,       /* e.g. align() before both clouds are set */
-  RGC_ERR_UNSUPPORTED = -4, /* e.g. k_correspondences > 32 */
+  RGC_ERR_UNSUPPORTED = -4, /* e.g. k_correspondences > 128 */
   RGC_ERR_NOMEM = -5
 } rgc_status;
 
@@ -68,7 +68,7 @@ typedef struct {
   double rotation_epsilon;           /* setRotationEpsilon                  (2e-3)    */
   double transformation_epsilon;     /* pcl setTransformationEpsilon        (5e-4)    */
   float max_correspondence_distance; /* pcl setMaxCorrespondenceDistance    (FLT_MAX) */
-  int k_correspondences;             /* setCorrespondenceRandomness         (20), <= 32 */
+  int k_correspondences;             /* setCorrespondenceRandomness         (20), <= 128 (fast paths: <= 32) */
   int regularization;                /* setRegularizationMethod             (PLANE)   */
   int optimizer;                     /* lsq_optimizer_type_                 (LM)      */
   int lm_max_iterations;             /* lm_max_iterations_                  (10)      */

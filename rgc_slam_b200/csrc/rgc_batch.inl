@@ -247,14 +247,7 @@ static int batch_chunk(rgc_ctx* c, const rgc_params& prm, const rgc_pair* pairs,
     if (lazy) {
       k_knn_warp<<<std::min(div_up(S, KW_WARPS), 148 * 8), KW_WARPS * 32, 0, st>>>(tgts.view, Tn, k, need_count, nullptr, need_list, S, need_nbr, nullptr, tgts.d_off, B);
       CKL(c);
-      const int grid = div_up(S, kThreads);
-      if (k == 20 && min_tgt >= k)
-        k_covariance<20, true><<<grid, kThreads, 0, st>>>(tgts.sorted, need_nbr, S, k, prm.regularization, tgts.cov, need_list, need_count);
-      else if (k <= 20)
-        k_covariance<20, false><<<grid, kThreads, 0, st>>>(tgts.sorted, need_nbr, S, k, prm.regularization, tgts.cov, need_list, need_count);
-      else
-        k_covariance<32, false><<<grid, kThreads, 0, st>>>(tgts.sorted, need_nbr, S, k, prm.regularization, tgts.cov, need_list, need_count);
-      CKL(c);
+      TRY(launch_covariance(c, st, tgts.sorted, need_nbr, S, S, k, min_tgt >= k, prm.regularization, tgts.cov, need_list, need_count));
       CK(c, cudaMemsetAsync(need_count, 0, 4, st));
     }
     k_blinearize<<<nblk, kThreads, 0, st>>>(tgts.sorted, srcs.sorted, srcs.cov, tgts.cov, d_info, d_blk_pair, d_rounds, corr[0], corr[1], maha[0], maha[1], lin_partials,

@@ -19,10 +19,6 @@
 #define RGC_HD_NOINLINE inline
 #endif
 
-#ifndef RGC_F2D_BITS
-#define RGC_F2D_BITS 0
-#endif
-
 namespace rgc {
 
 // ---- float arithmetic with pinned rounding (no FMA contraction) -------------------------------
@@ -104,28 +100,10 @@ RGC_HD float i2f_bits(int i) {
 #endif
 }
 
-// float -> double.  On the device the conversion instruction (F2F.F64.F32) is a quarter-rate operation that the
-// covariance kernel issued 60 times per point; a normal float widens with integer operations on the full-rate
-// pipe instead: same sign, exponent re-biased by 1023 - 127, mantissa shifted into place (exact, like the
-// conversion).  Zero and denormals are widened by hand as well.
-RGC_HD double f2d(float f) {
-#if defined(__CUDA_ARCH__) && RGC_F2D_BITS
-  const unsigned b = (unsigned)__float_as_int(f);
-  const unsigned sign = b & 0x80000000u;
-  unsigned em = b & 0x7fffffffu;  // exponent | mantissa
-  if (__builtin_expect(em < 0x00800000u, 0)) {  // zero or denormal (inf / nan never reach the kernels: rejected at ingest)
-    if (em == 0u) return __hiloint2double((int)sign, 0);
-    const int sh = __clz((int)em) - 8;  // normalise: leading bit to position 23; the value is 1.m x 2^(-126 - sh)
-    const unsigned m = em << sh;
-    const unsigned hi = sign | ((unsigned)(897 - sh) << 20) | ((m & 0x007fffffu) >> 3);
-    return __hiloint2double((int)hi, (int)(m << 29));
-  }
-  const unsigned hi = sign | ((em >> 3) + 0x38000000u);
-  return __hiloint2double((int)hi, (int)(b << 29));
-#else
-  return (double)f;
-#endif
-}
+// float -> double (exact).  Widening by hand with integer operations instead of the quarter-rate conversion
+// instruction (60 per point in k_covariance) was measured and is SLOWER (0.46 -> 0.55 ms at 8 M points): the
+// kernels wait on memory, not on the conversion pipe (profiles/README.md).
+RGC_HD double f2d(float f) { return (double)f; }
 
 struct F4 {  // layout-compatible with float4
   float x, y, z, w;

@@ -585,12 +585,19 @@ static int pre_filter(rgc_ctx* c, const void* points, size_t n_sz, size_t stride
   return RGC_OK;
 }
 
+// Largest k (setCorrespondenceRandomness / rgc_knn).  The fast paths — the warp-per-query kernel that finishes deferred
+// tiles and serves the on-demand target covariances, the unrolled covariance kernels, the batched registration —
+// hold k <= 32; above that the tile kernel alone does the self-kNN (its per-lane heaps live in shared memory:
+// 36 KB per warp at k = 128), the covariances come from the generic kernel and the target's are computed eagerly.
+constexpr int kMaxK = 128;
+
 template <bool SELF>
 static int launch_knn(rgc_ctx* c, const GridView& v, const float4* queries, int m, int k, int* idx, float* d2) {
-  if (k > 32) FAIL(c, RGC_ERR_UNSUPPORTED, "k_correspondences > 32 is not supported");
+  if (k > kMaxK) FAIL(c, RGC_ERR_UNSUPPORTED, "k > 128 is not supported");
   const int spread = query_spread(m);
   const int grid = div_up(m * spread, kThreads);
   const size_t smem = (size_t)k * kThreads * 8;  // per-thread max-heap of k (d2, position) pairs
+  if (smem > 48 * 1024) CK(c, cudaFuncSetAttribute(k_knn<SELF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_knn<SELF><<<grid, kThreads, smem, c->stream>>>(v, queries, m, k, spread, idx, d2);
   CKL(c);
   return RGC_OK;
@@ -602,7 +609,7 @@ static int launch_knn_self(rgc_ctx* c, const GridView& v, int n, int k, int* nbr
   // the warp-cooperative tile kernel; RGC_KNN_THREAD=1 selects the thread-per-query kernel (A/B, single clouds only)
   static const bool per_thread = std::getenv("RGC_KNN_THREAD") != nullptr;
   if (per_thread && !tiles) return launch_knn<true>(c, v, nullptr, n, k, nbr, nullptr);
-  if (k > 32) FAIL(c, RGC_ERR_UNSUPPORTED, "k_correspondences > 32 is not supported");
+  if (k > kMaxK) FAIL(c, RGC_ERR_UNSUPPORTED, "k_correspondences > 128 is not supported");
   const size_t per_warp = sizeof(float4) * KT_CAND + sizeof(TileNode) * KT_STACK + (size_t)(k + KT_PEND) * 32 * 8;
   const size_t smem = per_warp * KT_WARPS;
   CK(c, cudaFuncSetAttribute(k_knn_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -617,7 +624,7 @@ static int launch_knn_self(rgc_ctx* c, const GridView& v, int n, int k, int* nbr
   // on a 22k-point sweep; dense maps keep their tiles longer (600: 2.7 vs 1.7 ms on the 500k submap at 150)
   const int auto_defer = n_cloud < 100000 ? 150 : 600;
   const int want_defer = c->knn_defer < 0 ? auto_defer : c->knn_defer;
-  const int defer = (want_defer > 0 && n_cloud < 2000000) ? want_defer : INT_MAX;
+  const int defer = (want_defer > 0 && n_cloud < 2000000 && k <= 32) ? want_defer : INT_MAX;  // k_knn_warp keeps the k best in one warp's registers
   const int ntiles = tiles ? n_tiles : div_up(n, 32);
   Scratch tmp(c);
   int* dq = (int*)tmp.get(sizeof(int) * (size_t)(ntiles + 1));  // [0] = count, [1..] = tile ids
@@ -651,6 +658,33 @@ static int cloud_tiles(rgc_ctx* c, Cloud& cl) {
   return RGC_OK;
 }
 
+// k_covariance over `grid_threads` threads (whole cloud: thread = sorted point; on-demand: thread = entry of `qlist`).
+// `full`: k == 20 and every neighbour slot is filled (the predicate-free instantiation).
+static int launch_covariance(rgc_ctx* c, cudaStream_t st, const float4* pts, const int* nbr, int n_stride, int grid_threads, int k, bool full, int method,
+                             double* cov, const int* qlist, const int* qcount) {
+  const int grid = div_up(grid_threads, kThreads);
+#if RGC_ASYNC_STAGE
+  const size_t smem20 = sizeof(float4) * 20 * kThreads, smem32 = sizeof(float4) * 32 * kThreads;  // staged neighbour points
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(c, cudaFuncSetAttribute(k_covariance<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
+    attr_set = true;
+  }
+#else
+  const size_t smem20 = 0, smem32 = 0;
+#endif
+  if (k > 32)
+    k_covariance_any<<<grid, kThreads, 0, st>>>(pts, nbr, n_stride, grid_threads, k, method, cov);
+  else if (k == 20 && full)
+    k_covariance<20, true><<<grid, kThreads, smem20, st>>>(pts, nbr, n_stride, k, method, cov, qlist, qcount);
+  else if (k <= 20)
+    k_covariance<20, false><<<grid, kThreads, smem20, st>>>(pts, nbr, n_stride, k, method, cov, qlist, qcount);
+  else
+    k_covariance<32, false><<<grid, kThreads, smem32, st>>>(pts, nbr, n_stride, k, method, cov, qlist, qcount);
+  CKL(c);
+  return RGC_OK;
+}
+
 // FastGICP::calculate_covariances (fast_gicp_impl.hpp:241-299)
 static int cloud_covariances(rgc_ctx* c, Cloud& cl, int k, int method, bool speculative = false) {
   // covariances computed ahead of time (set_input) are redone if the parameters changed before the
@@ -672,13 +706,7 @@ static int cloud_covariances(rgc_ctx* c, Cloud& cl, int k, int method, bool spec
   c->mark("covariances: k-NN (tile + warp)");
   int min_cloud = cl.n;  // smallest cloud of a multi-cloud grid: every neighbour slot is filled iff it has >= k points
   for (int q = 0; q < cl.n_clouds; q++) min_cloud = std::min(min_cloud, cl.h_off[q + 1] - cl.h_off[q]);
-  if (k == 20 && min_cloud >= k)  // the default k_correspondences, every slot filled
-    k_covariance<20, true><<<div_up(cl.n, kThreads), kThreads, 0, st>>>(cl.sorted, nbr, cl.n, k, method, cl.cov, nullptr, nullptr);
-  else if (k <= 20)
-    k_covariance<20, false><<<div_up(cl.n, kThreads), kThreads, 0, st>>>(cl.sorted, nbr, cl.n, k, method, cl.cov, nullptr, nullptr);
-  else
-    k_covariance<32, false><<<div_up(cl.n, kThreads), kThreads, 0, st>>>(cl.sorted, nbr, cl.n, k, method, cl.cov, nullptr, nullptr);
-  CKL(c);
+  TRY(launch_covariance(c, st, cl.sorted, nbr, cl.n, cl.n, k, min_cloud >= k, method, cl.cov, nullptr, nullptr));  // full: the default k, every slot filled
   CK(c, cudaEventRecord(cl.ev[4], st));
   c->mark("covariances: k_covariance");
   cl.has_cov = true;
@@ -846,7 +874,7 @@ static int reg_ensure_fitness(rgc_reg* r, int blocks) {
 // can the target's covariances be computed on demand?  Only the exact-1-NN FastGICP path reads C_B at
 // correspondences alone; the voxel map averages ALL of them, and covariances the user supplied or that
 // were already computed for the whole cloud are simply used.
-static bool target_lazy(const rgc_reg* r) { return r->lazy_target && !r->vgicp && !r->tgt.has_cov; }
+static bool target_lazy(const rgc_reg* r) { return r->lazy_target && !r->vgicp && !r->tgt.has_cov && r->prm.k_correspondences <= 32; }
 
 static void to_rt(const double* T /*row-major 4x4*/, Rt& d, RtF& f) {
   for (int i = 0; i < 12; i++) {
@@ -1026,14 +1054,7 @@ static int gicp_linearize_launch(rgc_reg* r, const double* T, int want, const in
     k_knn_warp<<<std::min(div_up(r->src.n, KW_WARPS), 148 * RGC_KW_MINB), KW_WARPS * 32, 0, c->stream>>>(r->tgt.view, n_t, k, r->need_count, nullptr, r->need_list, cap, r->need_nbr, nullptr, nullptr, 0);
     CKL(c);
     c->mark("lm: on-demand k_knn_warp");
-    const int grid = div_up(r->src.n, kThreads);
-    if (k == 20 && n_t >= k)
-      k_covariance<20, true><<<grid, kThreads, 0, c->stream>>>(r->tgt.sorted, r->need_nbr, cap, k, method, r->tgt.cov, r->need_list, r->need_count);
-    else if (k <= 20)
-      k_covariance<20, false><<<grid, kThreads, 0, c->stream>>>(r->tgt.sorted, r->need_nbr, cap, k, method, r->tgt.cov, r->need_list, r->need_count);
-    else
-      k_covariance<32, false><<<grid, kThreads, 0, c->stream>>>(r->tgt.sorted, r->need_nbr, cap, k, method, r->tgt.cov, r->need_list, r->need_count);
-    CKL(c);
+    TRY(launch_covariance(c, c->stream, r->tgt.sorted, r->need_nbr, cap, r->src.n, k, n_t >= k, method, r->tgt.cov, r->need_list, r->need_count));
     c->mark("lm: on-demand k_covariance");
     if (c->profile) CK(c, cudaEventRecord(c->evk[3], c->stream));
   }
@@ -1436,7 +1457,7 @@ int rgc_reg_destroy(rgc_reg* r) {
 
 int rgc_reg_set_params(rgc_reg* r, const rgc_params* p) {
   if (!r || !p) return RGC_ERR_INVALID;
-  if (p->k_correspondences < 1 || p->k_correspondences > 32) FAIL(r->ctx, RGC_ERR_UNSUPPORTED, "k_correspondences must be in [1, 32]");
+  if (p->k_correspondences < 1 || p->k_correspondences > kMaxK) FAIL(r->ctx, RGC_ERR_UNSUPPORTED, "k_correspondences must be in [1, 128]");
   if (p->regularization < 0 || p->regularization > 4) FAIL(r->ctx, RGC_ERR_INVALID, "unknown regularization method");
   r->prm = *p;
   return RGC_OK;
@@ -1692,7 +1713,7 @@ int rgc_knn(rgc_ctx* c, const void* points, size_t n, size_t stride, const void*
             float grid_cell) {
   if (!c || !points || !queries || !idx || k < 1) return RGC_ERR_INVALID;
   CK(c, cudaSetDevice(c->device));
-  if (k > 32) FAIL(c, RGC_ERR_UNSUPPORTED, "k > 32 is not supported");
+  if (k > kMaxK) FAIL(c, RGC_ERR_UNSUPPORTED, "k > 128 is not supported");
   if (qstride < 12 || qstride % 4) FAIL(c, RGC_ERR_INVALID, "query stride must be a multiple of 4 and >= 12 bytes");
   TmpCloud tc(c);
   Cloud& cl = tc.cl;

@@ -605,9 +605,10 @@ __device__ __forceinline__ void nn1_search_group(const GridView& g, float qx, fl
   const CloudRange cr{0, g.n, 0ull};
   float bound = max_d2;
   if (g.n >= 1) {
+    // every lane of the group evaluates a different seed point; the smallest distance bounds the search of all
     int p0;
     if (near_pos >= 0) {
-      p0 = near_pos;
+      p0 = near_pos + sub;  // the hinted neighbour and the points that follow it in Morton order
     } else {
       const int fx = cell_coord(qx, g.inv_s0, g.bias), fy = cell_coord(qy, g.inv_s0, g.bias), fz = cell_coord(qz, g.inv_s0, g.bias);
       p0 = 0;
@@ -618,15 +619,18 @@ __device__ __forceinline__ void nn1_search_group(const GridView& g, float qx, fl
         const unsigned hits = __ballot_sync(gmask, hit) & gmask;
         if (hits) {
           const int src = __ffs(hits) - 1;  // lowest lane of the group with a hit = finest level
-          const int mid = (int)s + (int)((e - s) >> 1);
-          p0 = __shfl_sync(gmask, mid, src);
+          const int sb = __shfl_sync(gmask, (int)s, src), eb = __shfl_sync(gmask, (int)e, src);
+          p0 = sb + (int)(((long long)(eb - sb) * (2 * sub + 1)) / (2 * G));  // G points spread over that cell's range
           break;
         }
       }
     }
     p0 = p0 < 0 ? 0 : (p0 > g.n - 1 ? g.n - 1 : p0);
     const F4 c = load_pt(g.pts + p0);
-    bound = fminf(bound, dist2_ref(qx, qy, qz, c.x, c.y, c.z));
+    float far = dist2_ref(qx, qy, qz, c.x, c.y, c.z);
+#pragma unroll
+    for (int o = G >> 1; o > 0; o >>= 1) far = fminf(far, __shfl_xor_sync(gmask, far, o));
+    bound = fminf(bound, far);
   }
   top.reset(1, bound);
   const RootRange rr = root_range(g, qx, qy, qz, bound);

@@ -1118,7 +1118,7 @@ __global__ void __launch_bounds__(KW_WARPS * 32, RGC_KW_MINB) k_knn_warp(GridVie
 // All k index loads are issued first, then all k point gathers (fully unrolled, KCAP is a compile
 // time bound on k): the first version walked the neighbours in a serial loop of dependent
 // index -> point loads and was latency-bound at 17 % of HBM peak however cheap the fp64 part became.
-#ifndef RGC_COV_MINB
+#ifndef RGC_COV_MINB  // blocks per SM the register allocation aims at (the staged variant is limited to 5 by its 40 KB of shared memory)
 #define RGC_COV_MINB 6
 #endif
 #ifndef RGC_COV_BATCH
@@ -1144,6 +1144,17 @@ __global__ void __launch_bounds__(kThreads, RGC_COV_MINB) k_covariance(const flo
   int found = 0;
   Sym3 c = {0, 0, 0, 0, 0, 0};
   double ox = 0.0, oy = 0.0, oz = 0.0, sx = 0.0, sy = 0.0, sz = 0.0;
+#if RGC_ASYNC_STAGE
+  // all k neighbour points of this thread are copied global -> shared at once (cp.async: no registers in flight; the
+  // register version had to gather in batches of five, four dependent round trips per point), neighbour-major so
+  // the 128-bit reads back are conflict-free.  KCAP = 20: 40 KB per block.
+  extern __shared__ __align__(16) float4 nb_stage[];  // [KCAP][kThreads]
+#pragma unroll
+  for (int j = 0; j < KCAP; j++)
+    if (FULL || id[j] >= 0) cp_async16(&nb_stage[j * kThreads + threadIdx.x], &pts[id[j]], true);
+  cp_async_commit();
+  cp_async_wait<0>();
+#endif
 #pragma unroll
   for (int j0 = 0; j0 < KCAP; j0 += kBatch) {
     float px[kBatch], py[kBatch], pz[kBatch];
@@ -1152,7 +1163,11 @@ __global__ void __launch_bounds__(kThreads, RGC_COV_MINB) k_covariance(const flo
       const int j = j0 + u;
       px[u] = py[u] = pz[u] = 0.f;
       if (j < KCAP && (FULL || id[j] >= 0)) {
+#if RGC_ASYNC_STAGE
+        const float4 p = nb_stage[j * kThreads + threadIdx.x];
+#else
         const float4 p = __ldg(&pts[id[j]]);
+#endif
         px[u] = p.x;
         py[u] = p.y;
         pz[u] = p.z;
@@ -1211,6 +1226,33 @@ __global__ void __launch_bounds__(kThreads, RGC_COV_MINB) k_covariance(const flo
   o[2] = make_double2(r.yz, r.zz);
 }
 
+// ---- asynchronous global -> shared copies (cp.async, LDGSTS): 16 bytes per instruction, no registers held while the
+// load is in flight.  The streaming kernels of the path (covariance, linearize, compute_error) were latency-bound on
+// their gathers (ncu: long-scoreboard stalls 6-7 of ~10 warp-cycles per issue): a thread could only keep in
+// flight what it had registers for.  Staging through shared memory lets every thread issue ALL the gathers of
+// its next point (20 neighbours / the 128 bytes of a correspondence) at once.  Each thread reads back only the
+// slots it filled itself, so cp.async.wait_group is the only synchronisation needed.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool keep_l1) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  if (keep_l1)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
+  else
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+// MEASURED, NOT THE DEFAULT (round 2, 8 M / 2 M points): staged k_covariance 0.597 ms vs 0.447 ms with register
+// gathers in batches of five, k_linearize 0.109 vs 0.094 ms, k_compute_error 0.059 vs 0.045 ms — the extra
+// shared-memory round trip and the occupancy lost to the 40 KB / 33 KB of staging cost more than the deeper
+// gather queue wins; at 5 or 6 blocks per SM (register cap 96 / 80, spills) k_linearize fell to 0.133 / 0.18 ms.
+// The code stays behind RGC_ASYNC_STAGE=1 for A/B runs (profiles/README.md).
+#ifndef RGC_ASYNC_STAGE
+#define RGC_ASYNC_STAGE 0
+#endif
+
 __device__ __forceinline__ Sym3 load_sym3(const double* __restrict__ base, size_t i) {
   const double2* p = reinterpret_cast<const double2*>(base + i * 6);
   double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
@@ -1222,6 +1264,22 @@ __device__ __forceinline__ void store_sym3(double* __restrict__ base, size_t i, 
   p[1] = make_double2(s.xz, s.yy);
   p[2] = make_double2(s.yz, s.zz);
 }
+
+// any k (32 < k <= 128, whole clouds only): one thread per point walking its neighbour list — the plain
+// covariance_from_points of rgc_math.cuh.  The unrolled kernel above keeps the k indices in registers.
+__global__ void __launch_bounds__(kThreads) k_covariance_any(const float4* __restrict__ pts, const int* __restrict__ nbr, int n_stride, int n, int k, int method,
+                                                             double* __restrict__ cov) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  int found = 0;
+  while (found < k && __ldg(&nbr[(size_t)found * n_stride + t]) >= 0) found++;  // valid entries are a prefix
+  const Sym3 c = covariance_from_points(found, k, [&](int j) {
+    const float4 p = __ldg(&pts[__ldg(&nbr[(size_t)j * n_stride + t])]);
+    return F4{p.x, p.y, p.z, p.w};
+  });
+  store_sym3(cov, t, regularize_cov(c, method));
+}
+
 
 // ------------------------------------------------------------------------------------------------
 // Deterministic grid reduction of NV doubles per thread: warp shuffle -> smem -> per-block partial
@@ -1433,9 +1491,67 @@ __device__ __forceinline__ void lin_load(LinPoint& d, const float4* __restrict__
   d.CA = load_sym3(src_cov, i);
   d.CB = load_sym3(tgt_cov, pos);
 }
+// staged operands of one correspondence: 8 x 16 bytes per thread and stage, chunk-major so that the 128-bit
+// shared-memory reads of a warp are conflict-free: [stage][chunk][thread]
+//   chunk 0: p   1: q   2-4: C_A   5-7: C_B
+constexpr int kLinStages = 2;
+__device__ __forceinline__ void lin_stage_issue(float4 (*st)[kThreads], const float4* __restrict__ tgt_pts, const float4* __restrict__ src,
+                                                const double* __restrict__ src_cov, const double* __restrict__ tgt_cov, int i, int pos) {
+  const int t = threadIdx.x;
+  cp_async16(&st[0][t], &src[i], false);
+  cp_async16(&st[1][t], &tgt_pts[pos], false);
+  const float4* ca = reinterpret_cast<const float4*>(src_cov + (size_t)i * 6);
+  const float4* cb = reinterpret_cast<const float4*>(tgt_cov + (size_t)pos * 6);
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    cp_async16(&st[2 + c][t], ca + c, false);
+    cp_async16(&st[5 + c][t], cb + c, false);
+  }
+}
+__device__ __forceinline__ Sym3 lin_stage_sym3(float4 (*st)[kThreads], int c0) {
+  const int t = threadIdx.x;
+  const double2 a = *reinterpret_cast<const double2*>(&st[c0][t]), b = *reinterpret_cast<const double2*>(&st[c0 + 1][t]),
+                c = *reinterpret_cast<const double2*>(&st[c0 + 2][t]);
+  return Sym3{a.x, a.y, b.x, b.y, c.x, c.y};
+}
 __device__ __forceinline__ void linearize_points(const float4* __restrict__ tgt_pts, const float4* __restrict__ src, const double* __restrict__ src_cov,
                                                  const double* __restrict__ tgt_cov, const int* __restrict__ corr, double* __restrict__ maha, const Rt& Td,
                                                  int want_hb, int base, int first, int stride, int n, double* acc) {
+#if RGC_ASYNC_STAGE
+  // the next point's 128 bytes are copied global -> shared asynchronously (no registers in flight) while the
+  // ~400 fp64 instructions of the current one issue; corr[] is read two points ahead as before.  The terms
+  // are added in ascending il, as before: same bits.
+  __shared__ __align__(16) float4 stage[kLinStages][8][kThreads];
+  int il = first;
+  int c1 = il < n ? __ldg(&corr[base + il]) : -1;
+  int c2 = il + stride < n ? __ldg(&corr[base + il + stride]) : -1;
+  int cur = 0;
+  if (c1 >= 0) lin_stage_issue(stage[0], tgt_pts, src, src_cov, tgt_cov, base + il, c1);
+  cp_async_commit();
+  while (il < n) {
+    const int iln = il + stride;
+    const int c3 = (iln + stride < n) ? __ldg(&corr[base + iln + stride]) : -1;
+    if (c2 >= 0) lin_stage_issue(stage[cur ^ 1], tgt_pts, src, src_cov, tgt_cov, base + iln, c2);
+    cp_async_commit();
+    cp_async_wait<1>();  // everything but the group just committed has landed: the current point
+    if (c1 >= 0) {
+      float4(*st)[kThreads] = stage[cur];
+      const float4 p = st[0][threadIdx.x], q = st[1][threadIdx.x];
+      const Sym3 M = gicp_mahalanobis(Td, lin_stage_sym3(st, 2), lin_stage_sym3(st, 5));
+      store_sym3(maha, base + il, M);
+      if (want_hb)
+        gicp_point_terms(Td, M, p.x, p.y, p.z, q.x, q.y, q.z, acc);
+      else
+        acc[0] = dadd(acc[0], gicp_error_term(Td, M, p.x, p.y, p.z, q.x, q.y, q.z));
+      acc[kAccN] += 1.0;
+    }
+    cur ^= 1;
+    c1 = c2;
+    c2 = c3;
+    il = iln;
+  }
+  cp_async_wait<0>();
+#else
   int il = first;
   int c1 = il < n ? __ldg(&corr[base + il]) : -1;
   int c2 = il + stride < n ? __ldg(&corr[base + il + stride]) : -1;
@@ -1459,6 +1575,7 @@ __device__ __forceinline__ void linearize_points(const float4* __restrict__ tgt_
     c2 = c3;
     il = iln;
   }
+#endif
 }
 __global__ void __launch_bounds__(kThreads, RGC_LIN_MINB) k_linearize(const float4* __restrict__ tgt_pts, const float4* __restrict__ src, const double* __restrict__ src_cov,
                                                            const double* __restrict__ tgt_cov, int n_src, Rt Td, int want_hb, const int* __restrict__ corr,
@@ -1478,6 +1595,42 @@ struct CePoint {
 };
 __device__ __forceinline__ void compute_error_points(const float4* __restrict__ tgt_pts, const float4* __restrict__ src, const int* __restrict__ corr,
                                                      const double* __restrict__ maha, const Rt& Td, int base, int first, int stride, int n, double* acc) {
+#if RGC_ASYNC_STAGE
+  // same staging as linearize_points: p, q and the frozen M of the next point (80 bytes) are copied global -> shared
+  // asynchronously while the current one is evaluated
+  __shared__ __align__(16) float4 stage[2][5][kThreads];
+  const int t = threadIdx.x;
+  auto issue = [&](float4 (*st)[kThreads], int i, int pos) {
+    cp_async16(&st[0][t], &src[i], false);
+    cp_async16(&st[1][t], &tgt_pts[pos], false);
+    const float4* m = reinterpret_cast<const float4*>(maha + (size_t)i * 6);
+#pragma unroll
+    for (int c = 0; c < 3; c++) cp_async16(&st[2 + c][t], m + c, false);
+  };
+  int il = first;
+  int c1 = il < n ? __ldg(&corr[base + il]) : -1;
+  int c2 = il + stride < n ? __ldg(&corr[base + il + stride]) : -1;
+  int cur = 0;
+  if (c1 >= 0) issue(stage[0], base + il, c1);
+  cp_async_commit();
+  while (il < n) {
+    const int iln = il + stride;
+    const int c3 = (iln + stride < n) ? __ldg(&corr[base + iln + stride]) : -1;
+    if (c2 >= 0) issue(stage[cur ^ 1], base + iln, c2);
+    cp_async_commit();
+    cp_async_wait<1>();
+    if (c1 >= 0) {
+      float4(*st)[kThreads] = stage[cur];
+      const float4 p = st[0][t], q = st[1][t];
+      acc[0] = dadd(acc[0], gicp_error_term(Td, lin_stage_sym3(st, 2), p.x, p.y, p.z, q.x, q.y, q.z));
+    }
+    cur ^= 1;
+    c1 = c2;
+    c2 = c3;
+    il = iln;
+  }
+  cp_async_wait<0>();
+#else
   int il = first;
   int c1 = il < n ? __ldg(&corr[base + il]) : -1;
   int c2 = il + stride < n ? __ldg(&corr[base + il + stride]) : -1;
@@ -1498,6 +1651,7 @@ __device__ __forceinline__ void compute_error_points(const float4* __restrict__ 
     c2 = c3;
     il = iln;
   }
+#endif
 }
 __global__ void __launch_bounds__(kThreads) k_compute_error(const float4* __restrict__ tgt_pts, const float4* __restrict__ src, int n_src, Rt Td,
                                                             const int* __restrict__ corr, const double* __restrict__ maha,

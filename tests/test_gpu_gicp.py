@@ -265,7 +265,7 @@ def test_errors_are_loud(rgc):
     with pytest.raises(rgc.RgcError):
         g.align()  # no clouds
     with pytest.raises(rgc.RgcError):
-        g.setCorrespondenceRandomness(64)  # k > 32 unsupported
+        g.setCorrespondenceRandomness(129)  # k > 128 unsupported
     with pytest.raises(rgc.RgcError):
         g.setInputSource(np.zeros((0, 4), np.float32))
 

@@ -402,3 +402,33 @@ def test_speculative_grid_geometry_hits_and_misses(rgc, orc):
     s1 = stats()
     assert s1[0] >= s0[0] + 1, "speculative builds are not happening"
     assert s1[1] >= s0[1] + 1, "a cloud outside the hinted grid was not detected"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", [33, 64, 128])
+def test_k_above_32(rgc, orc, small_pair, k):
+    """setCorrespondenceRandomness accepts any k in the reference (fast_gicp_impl.hpp:38-40); above 32 the tile kernel
+    alone does the self-kNN, the generic covariance kernel follows and the target covariances are computed eagerly."""
+    src, tgt, _ = small_pair
+    idx = rgc.knn_self(tgt, k)
+    oi, _ = orc.knn(tgt, tgt, k)
+    assert np.array_equal(idx, oi)
+    qi, qd = rgc.knn(tgt, src[:700], k)
+    oq, od = orc.knn(tgt, src[:700], k)
+    assert np.array_equal(qi, oq) and np.array_equal(qd, od)
+    g = rgc.FastGICP()
+    g.setCorrespondenceRandomness(k)
+    g.setMaxCorrespondenceDistance(2.0)
+    g.setInputSource(src)
+    g.setInputTarget(tgt)
+    c = g.getTargetCovariances()
+    oc = orc.covariances_from_knn(tgt, oi, 3)
+    scale = np.abs(oc).max(axis=(1, 2), keepdims=True)
+    assert (np.abs(c - oc) / scale).max() < 1e-8
+    if k == 64:
+        T = g.align()
+        o = orc.FastGICP(k=k, corr_dist=2.0)
+        o.setInputSource(src)
+        o.setInputTarget(tgt)
+        To = o.align()
+        _same_run(g, o, T, To)
