@@ -473,13 +473,14 @@ RGC_HD void scan_range(const GridView& g, uint32_t s, uint32_t e, float qx, floa
 // Depth-first descent of ONE root cell (rx, ry, rz) at level lb: nearest octant first, pruning every cell whose
 // (conservatively shrunk) box is farther than the current bound, scanning a cell's contiguous point range once it
 // holds <= kLeafPoints points.  `stack`: kStackCap entries of per-thread scratch.
+// `mkey`: the cell's Morton key (the callers build it incrementally over their root loops; rx, ry, rz are inside the grid)
 template <class Top>
-RGC_HD void search_root(const GridView& g, int lb, int rx, int ry, int rz, float qx, float qy, float qz, Top& top, StackEntry* stack, SearchStats* st,
-                        const CloudRange& cr) {
+RGC_HD void search_root(const GridView& g, int lb, int rx, int ry, int rz, uint64_t mkey, float qx, float qy, float qz, Top& top, StackEntry* stack,
+                        SearchStats* st, const CloudRange& cr) {
   if (box_dist2(g, lb, rx, ry, rz, qx, qy, qz) > top.bound()) return;
   uint32_t s, e, m;
   if (st) st->lookups++;
-  if (!grid_lookup(g, lb, rx, ry, rz, s, e, m, prefix_at(cr, lb))) return;
+  if (!grid_lookup_key(g, lb, mkey | prefix_at(cr, lb), s, e, m)) return;
   int sp = 0;
   stack[sp++] = StackEntry{(uint32_t)rx | ((uint32_t)lb << 24), (uint32_t)ry | (m << 24), (uint32_t)rz, s, e, 0u};
   while (sp > 0) {
@@ -584,9 +585,14 @@ RGC_HD void knn_search(const GridView& g, float qx, float qy, float qz, int k, f
   // ---- 2. root level: finest level whose cell edge >= ball radius ; 3. depth-first descent of every root
   const RootRange rr = root_range(g, qx, qy, qz, bound);
   StackEntry stack[kStackCap];
-  for (int rz = rr.lo[2]; rz <= rr.hi[2]; rz++)
-    for (int ry = rr.lo[1]; ry <= rr.hi[1]; ry++)
-      for (int rx = rr.lo[0]; rx <= rr.hi[0]; rx++) search_root(g, rr.lb, rx, ry, rz, qx, qy, qz, top, stack, st, cr);
+  // (the Morton key of a root is assembled per axis: one bit-spread per loop level instead of three per cell)
+  for (int rz = rr.lo[2]; rz <= rr.hi[2]; rz++) {
+    const uint64_t kz = spread3((uint32_t)rz) << 2;
+    for (int ry = rr.lo[1]; ry <= rr.hi[1]; ry++) {
+      const uint64_t kyz = kz | (spread3((uint32_t)ry) << 1);
+      for (int rx = rr.lo[0]; rx <= rr.hi[0]; rx++) search_root(g, rr.lb, rx, ry, rz, kyz | spread3((uint32_t)rx), qx, qy, qz, top, stack, st, cr);
+    }
+  }
 }
 
 #if defined(__CUDACC__)
@@ -639,7 +645,7 @@ __device__ __forceinline__ void nn1_search_group(const GridView& g, float qx, fl
   StackEntry stack[kStackCap];
   for (int ri = sub; ri < nroots; ri += G) {
     const int rx = rr.lo[0] + ri % nx, ry = rr.lo[1] + (ri / nx) % ny, rz = rr.lo[2] + ri / (nx * ny);
-    search_root(g, rr.lb, rx, ry, rz, qx, qy, qz, top, stack, nullptr, cr);
+    search_root(g, rr.lb, rx, ry, rz, morton3((uint32_t)rx, (uint32_t)ry, (uint32_t)rz), qx, qy, qz, top, stack, nullptr, cr);
   }
   // best of the group under the total order (d2, original index)
 #pragma unroll

@@ -866,7 +866,10 @@ __global__ void __launch_bounds__(KT_WARPS * 32) k_knn_tile(GridView g, int n, i
 constexpr int KW_WARPS = 8;
 constexpr int KW_STACK = 64;
 constexpr int KW_LEAF = 64;
-constexpr int KW_SEEDS = 64;
+#ifndef RGC_KW_SEEDS
+#define RGC_KW_SEEDS 64
+#endif
+constexpr int KW_SEEDS = RGC_KW_SEEDS;
 
 __device__ __forceinline__ unsigned long long shfl64(unsigned long long v, int src) {
   return ((unsigned long long)__shfl_sync(0xffffffffu, (unsigned)(v >> 32), src) << 32) | __shfl_sync(0xffffffffu, (unsigned)v, src);
