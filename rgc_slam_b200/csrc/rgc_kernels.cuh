@@ -27,13 +27,16 @@ constexpr int kBboxBlocks = 296;  // 2 x 148 SMs
 constexpr int kThreads = 128;
 
 // Small clouds (one LiDAR sweep) cannot fill 148 SMs with one query per thread: the search kernels
-// are then bound by the latency of a few divergent warps.  `spread` (power of two) leaves only
-// every spread-th lane active, so the same queries occupy spread x more warps, each with fewer
-// divergent paths to serialise.  Measured on 22k queries (k_correspond): spread 1: 137 us, 4: 92 us,
-// 32 (one query per warp): 146 us — a single query is itself a ~30 us chain of ~4k dependent
-// instructions and ~28 dependent loads, so beyond 4-8 the extra warps only add scheduling waves.
-// Large clouds use spread = 1 (throughput-bound).
-__host__ __device__ inline int query_spread(int n) { return n <= 12000 ? 8 : (n <= 48000 ? 4 : (n <= 96000 ? 2 : 1)); }
+// are then bound by the latency of a few divergent warps.  `spread` (power of two) gives every query
+// `spread` consecutive lanes.  Round 1 left the extra lanes idle (fewer divergent walks per warp; measured on
+// 22k queries with one walking lane: spread 1: 137 us, 4: 92 us, 32: 146 us); since round 2 the lanes of a
+// group share the query (nn1_search_group: each lane takes some of the ball's root cells), and 8 lanes per query
+// beat 4 on the 22k-point sweep (cold align 0.865 -> 0.812 ms, LM loop 0.62 -> 0.575 ms).
+// Large clouds use spread = 1 (throughput-bound, one lane per query).
+#ifndef RGC_SPREAD8_MAX
+#define RGC_SPREAD8_MAX 48000
+#endif
+__host__ __device__ inline int query_spread(int n) { return n <= RGC_SPREAD8_MAX ? 8 : (n <= 96000 ? 4 : 1); }
 
 
 // ------------------------------------------------------------------------------------------------
@@ -870,9 +873,16 @@ constexpr int KW_LEAF = 64;
 #define RGC_KW_SEEDS 64
 #endif
 constexpr int KW_SEEDS = RGC_KW_SEEDS;
+#ifndef RGC_KW_MERGE_MIN
+#define RGC_KW_MERGE_MIN 6
+#endif
+constexpr int KW_MERGE_MIN = RGC_KW_MERGE_MIN;  // a batch with more qualifying candidates than this is merged by a sorting network
 
 __device__ __forceinline__ unsigned long long shfl64(unsigned long long v, int src) {
   return ((unsigned long long)__shfl_sync(0xffffffffu, (unsigned)(v >> 32), src) << 32) | __shfl_sync(0xffffffffu, (unsigned)v, src);
+}
+__device__ __forceinline__ unsigned long long shfl64_xor(unsigned long long v, int m) {
+  return ((unsigned long long)__shfl_xor_sync(0xffffffffu, (unsigned)(v >> 32), m) << 32) | __shfl_xor_sync(0xffffffffu, (unsigned)v, m);
 }
 __device__ __forceinline__ unsigned long long shfl64_up1(unsigned long long v) {
   return ((unsigned long long)__shfl_up_sync(0xffffffffu, (unsigned)(v >> 32), 1) << 32) | __shfl_up_sync(0xffffffffu, (unsigned)v, 1);
@@ -927,6 +937,30 @@ __global__ void __launch_bounds__(KW_WARPS * 32, RGC_KW_MINB) k_knn_warp(GridVie
     auto offer = [&](unsigned long long ck, bool valid) {
       unsigned long long wk = shfl64(mine, k - 1);
       unsigned acc = __ballot_sync(0xffffffffu, valid && ck < wk && ck <= capk);
+      if (__popc(acc) > KW_MERGE_MIN) {
+        // many of the 32 candidates qualify (the seeds of every query; whole batches in sparse regions, whose queries
+        // were the tail of the launch: ~150 dependent cycles per one-at-a-time insertion): sort the batch with a
+        // bitonic network, keep the 32 smallest of (list, batch) — min(list[i], batch[31 - i]) is a bitonic sequence
+        // of exactly those — and merge: 20 compare-exchange steps whatever the number of insertions
+        unsigned long long b = ((acc >> lane) & 1u) ? ck : ~0ull;
+#pragma unroll
+        for (int size = 2; size <= 32; size <<= 1)
+#pragma unroll
+          for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const unsigned long long o = shfl64_xor(b, stride);
+            const bool keep_min = ((lane & stride) == 0) == ((lane & size) == 0);
+            b = keep_min ? (o < b ? o : b) : (o > b ? o : b);
+          }
+        const unsigned long long r = shfl64(b, 31 - lane);
+        unsigned long long m = r < mine ? r : mine;
+#pragma unroll
+        for (int stride = 16; stride > 0; stride >>= 1) {
+          const unsigned long long o = shfl64_xor(m, stride);
+          m = ((lane & stride) == 0) ? (o < m ? o : m) : (o > m ? o : m);
+        }
+        mine = m;
+        return;
+      }
       while (acc) {
         const int src = __ffs(acc) - 1;
         const unsigned long long nk = shfl64(ck, src);
