@@ -590,6 +590,9 @@ static int pre_filter(rgc_ctx* c, const void* points, size_t n_sz, size_t stride
 // hold k <= 32; above that the tile kernel alone does the self-kNN (its per-lane heaps live in shared memory:
 // 36 KB per warp at k = 128), the covariances come from the generic kernel and the target's are computed eagerly.
 constexpr int kMaxK = 128;
+#ifndef RGC_KNN_ALLWARP_MAX  // largest single cloud whose self-kNN runs entirely in the warp-per-query kernel (0: never)
+#define RGC_KNN_ALLWARP_MAX 48000
+#endif
 
 template <bool SELF>
 static int launch_knn(rgc_ctx* c, const GridView& v, const float4* queries, int m, int k, int* idx, float* d2) {
@@ -626,6 +629,16 @@ static int launch_knn_self(rgc_ctx* c, const GridView& v, int n, int k, int* nbr
   const int want_defer = c->knn_defer < 0 ? auto_defer : c->knn_defer;
   const int defer = (want_defer > 0 && n_cloud < 2000000 && k <= 32) ? want_defer : INT_MAX;  // k_knn_warp keeps the k best in one warp's registers
   const int ntiles = tiles ? n_tiles : div_up(n, 32);
+  // a single sweep-sized cloud skips the tile kernel: one warp per query for every point.  With the four-node walk and
+  // the batch merge of round 2 the warp kernel does the 22k-point sweep in 0.077 ms; the tile kernel + the warp
+  // kernel for its deferred tiles took 0.165 ms (a sweep's sparse rings make most tiles gather far more candidates
+  // than 32 queries can share).  Dense maps keep the tile kernel (2.6x fewer instructions per query there).
+  // (an explicit deferral threshold — rgc_debug_set_knn_defer / RGC_KNN_DEFER, the tests' way of forcing either kernel — keeps the tile path)
+  if (!tiles && k <= 32 && n <= RGC_KNN_ALLWARP_MAX && c->knn_defer < 0) {
+    k_knn_warp<<<std::min(div_up(n, KW_WARPS), 148 * RGC_KW_MINB), KW_WARPS * 32, 0, c->stream>>>(v, n, k, nullptr, nullptr, nullptr, 0, nbr, nullptr, nullptr, 0);
+    CKL(c);
+    return RGC_OK;
+  }
   Scratch tmp(c);
   int* dq = (int*)tmp.get(sizeof(int) * (size_t)(ntiles + 1));  // [0] = count, [1..] = tile ids
   if (!dq) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (knn defer list)");

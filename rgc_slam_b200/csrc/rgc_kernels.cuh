@@ -904,7 +904,7 @@ __global__ void __launch_bounds__(KW_WARPS * 32, RGC_KW_MINB) k_knn_warp(GridVie
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   TileNode* stack = stacks[warp];
   const float4* pts4 = reinterpret_cast<const float4*>(g.pts);
-  const int nq = qlist ? *defer_count : *defer_count * 32;
+  const int nq = qlist ? *defer_count : (defer_count ? *defer_count * 32 : n);  // no list at all: every point of the cloud
   for (int w = blockIdx.x * KW_WARPS + warp; w < nq; w += gridDim.x * KW_WARPS) {
     int t, lo = 0, hi = n;
     uint64_t prefix = 0ull;
@@ -926,8 +926,10 @@ __global__ void __launch_bounds__(KW_WARPS * 32, RGC_KW_MINB) k_knn_warp(GridVie
       lo = td.lo;
       hi = td.hi;
       prefix = td.prefix;
-    } else {
+    } else if (defer_tiles) {
       t = defer_tiles[w >> 5] * 32 + (w & 31);
+    } else {
+      t = w;
     }
     if (t >= hi) continue;
     const float4 q = pts4[t];

@@ -56,11 +56,12 @@ def knn_defer(rgc):
     set_(-1)  # back to the size-dependent default
 
 
-@pytest.mark.parametrize("defer", [600, 1, 40, 0])
+@pytest.mark.parametrize("defer", [600, 1, 40, 0, -1])
 @pytest.mark.parametrize("k", [1, 7, 20, 32])
 def test_knn_self_tile_kernel_bitexact(rgc, orc, scan_pair, k, defer, knn_defer):
     """the production self-kNN (warp-cooperative tile kernel used by calculate_covariances);
-    defer=1 sends nearly every tile through the warp-per-query kernel, 0 none"""
+    defer=1 sends nearly every tile through the warp-per-query kernel, 0 none; -1 is the size-dependent default
+    (sweep-sized clouds: the warp-per-query kernel for every point, no tile kernel at all)"""
     knn_defer(defer)
     src, tgt, _ = scan_pair
     for cloud in (tgt, src[:1000], src[:33], src[:5]):
