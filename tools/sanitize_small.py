@@ -33,3 +33,10 @@ print("vgicp", v.last_result)
 scans = [synth.lidar_scan(scene, traj[f], n_azimuth=400, seed=50 + f) for f in range(3)]
 r, ms = extract_features(scans)
 print("features", [x["cloud_size"] for x in r], [len(x["corner_sharp"]) for x in r])
+# batched registration (multi-cloud grids, per-pair reductions, on-demand covariances over a list)
+from rgc_slam_b200 import batch
+pp = [dict(src=src[: 2000 + 300 * i], tgt=tgt, guess=np.eye(4, dtype=np.float32)) for i in range(3)]
+prm = batch.default_params()
+prm.max_iterations, prm.max_correspondence_distance = 16, 2.0
+res = batch.align_batch(pp, params=prm, want_fitness=True)
+print("batch", [(r["iterations"], r["converged"], round(float(r["fitness"]), 4)) for r in res])
