@@ -316,6 +316,7 @@ def run_c5(torch, dist, rgc, local, rank, world):
     ctx.synchronize()
     t_warm = time.perf_counter() - t0
     n_ar = gs.n_allreduce - n0
+    main_iters, main_conv = gs.last_result["iterations"], gs.hasConverged()
     Tg = case["guess"].astype(np.float64)
     lin = []
     for _ in range(5):
@@ -335,7 +336,7 @@ def run_c5(torch, dist, rgc, local, rank, world):
            "n_target": int(len(case["tgt"])), "n_source": int(len(case["src"])), "local_target_max": int(stats[4].item()),
            "set_target_s_max": float(stats[0].item()), "set_target": "full map from pinned host memory, slab + halo selected on the device, voxel hash built",
            "align_cold_ms_max": 1e3 * float(stats[1].item()), "align_warm_ms_max": 1e3 * float(stats[2].item()),
-           "linearize_ms_max": 1e3 * float(stats[3].item()), "iterations": gs.last_result["iterations"], "converged": gs.hasConverged(),
+           "linearize_ms_max": 1e3 * float(stats[3].item()), "iterations": main_iters, "converged": main_conv,
            "allreduces_per_align": n_ar, "allreduce": gs.allreduce_kind, "allreduce_us": ar_us, "with_default_trans_eps_5e-4": default_eps}
     if rank == 0:  # unsharded on rank 0's GPU: H, b and the final pose must agree
         gu = rgc.FastGICP(ctx)
@@ -355,7 +356,7 @@ def run_c5(torch, dist, rgc, local, rank, world):
         out["unsharded_align_warm_ms"] = 1e3 * (time.perf_counter() - t0)
         eu, Hu, bu = gu.linearize(Tg)
         out.update(H_rel_vs_unsharded=float(np.abs(H - Hu).max() / np.abs(Hu).max()), b_rel_vs_unsharded=float(np.abs(b - bu).max() / np.abs(bu).max()),
-                   pose_dt_vs_unsharded=float(np.abs(T[:3, 3] - Tu[:3, 3]).max()), iterations_equal=gs.last_result["iterations"] == gu.last_result["iterations"])
+                   pose_dt_vs_unsharded=float(np.abs(T[:3, 3] - Tu[:3, 3]).max()), iterations_equal=main_iters == gu.last_result["iterations"])
         gu = None
     gs.close()
     gs = None
@@ -583,7 +584,7 @@ def run_ours(args, rank, world):
 
     # ---------------- the other configurations
     if not args.no_extra:
-        legs = [("c3", lambda: leg_c3(torch, rgc, local)), ("c4", lambda: run_c4(torch, dist, rgc, local, rank, world, args.c4_pairs or 256))] if world == 1 else \
+        legs = [("c3", lambda: leg_c3(torch, rgc, local)), ("c4", lambda: run_c4(torch, dist, rgc, local, rank, world, args.c4_pairs or 4096))] if world == 1 else \
                [("c4", lambda: run_c4(torch, dist, rgc, local, rank, world, args.c4_pairs or 4096)), ("c5", lambda: run_c5(torch, dist, rgc, local, rank, world))]
         for name, fn in legs:
             try:
@@ -718,7 +719,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-large", action="store_true", help="skip the 8 M / 2 M HBM-kernel leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the C3 / C4 / C5 legs")
-    ap.add_argument("--c4-pairs", type=int, default=0, help="pairs of the C4 leg (default 256 at N=1, 4096 at N>1)")
+    ap.add_argument("--c4-pairs", type=int, default=0, help="pairs of the C4 leg (default 4096 at every N: one strong-scaling series)")
     ap.add_argument("--concurrent", type=int, default=4, help="host threads of the concurrent-throughput leg (0/1 = skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))

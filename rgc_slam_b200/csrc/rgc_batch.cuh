@@ -144,31 +144,53 @@ __global__ void __launch_bounds__(kThreads) k_bcompute_error(const float4* __res
 // for small clouds included) replayed per pair, so the sums come out bit-identical
 // final_Tf: 16 floats per pair — the final transformation (12) and, as int bits, the buffer set holding the
 // pair's last correspondences (hints, see k_fitness) or -1
-__global__ void __launch_bounds__(kThreads, RGC_CORR_MINB) k_bfitness(GridView tgt, const float4* __restrict__ src, const BPairInfo* __restrict__ info,
-                                                                     const int* __restrict__ fblk_pair, const float* __restrict__ final_Tf, double max_range,
-                                                                     const int* __restrict__ corr0, const int* __restrict__ corr1,
-                                                                     double* __restrict__ partials, unsigned int* __restrict__ tickets, double* __restrict__ results) {
-  const int pair = fblk_pair[blockIdx.x];
+// getFitnessScore, search half: the exact nearest target point of every source point at the pair's final pose, one lane
+// per query over the linearize-shaped grid (the batch has no idle lanes to give a query), hinted by the pair's last
+// correspondences.  d2 (or -1: no target point at all) goes to the sqd buffer of the set the pair is NOT using.
+__global__ void __launch_bounds__(kThreads, RGC_CORR_MINB) k_bfitness_search(GridView tgt, const float4* __restrict__ src, const BPairInfo* __restrict__ info,
+                                                                            const int* __restrict__ blk_pair, const float* __restrict__ final_Tf,
+                                                                            const int* __restrict__ corr0, const int* __restrict__ corr1, float* __restrict__ sqd0,
+                                                                            float* __restrict__ sqd1) {
+  const int pair = blk_pair[blockIdx.x];
   const BPairInfo pi = info[pair];
-  const int vb = blockIdx.x - pi.fblk0;
+  const int vb = blockIdx.x - pi.blk0;
   float Tf[12];
 #pragma unroll
   for (int j = 0; j < 12; j++) Tf[j] = final_Tf[pair * 16 + j];
   const int hsel = __float_as_int(final_Tf[pair * 16 + 12]);
   const int* hint = hsel < 0 ? nullptr : (hsel ? corr1 : corr0);
-  double acc[2] = {0.0, 0.0};
-  const int gt = vb * kThreads + threadIdx.x;
-  const int il = gt / pi.spread;
-  if ((gt & (pi.spread - 1)) == 0 && il < pi.src_hi - pi.src_lo) {
-    const float4 p = __ldg(&src[pi.src_lo + il]);
+  float* out = hsel == 1 ? sqd0 : sqd1;
+  const CloudRange cr{pi.tgt_lo, pi.tgt_hi, pi.tgt_prefix};
+  const int n_src = pi.src_hi - pi.src_lo;
+  for (int il = vb * kThreads + threadIdx.x; il < n_src; il += pi.nblk * kThreads) {
+    const int i = pi.src_lo + il;
+    const float4 p = __ldg(&src[i]);
     float qx, qy, qz;
     transform_f(Tf, p.x, p.y, p.z, qx, qy, qz);
     Best1 top;
     top.reset(1, INFINITY);
-    const CloudRange cr{pi.tgt_lo, pi.tgt_hi, pi.tgt_prefix};
-    knn_search(tgt, qx, qy, qz, 1, INFINITY, hint ? __ldg(&hint[pi.src_lo + il]) : -1, top, nullptr, &cr);
-    if (top.id0 >= 0 && (double)top.d0 <= max_range) {
-      acc[0] = (double)top.d0;
+    knn_search(tgt, qx, qy, qz, 1, INFINITY, hint ? __ldg(&hint[i]) : -1, top, nullptr, &cr);
+    out[i] = top.id0 >= 0 ? top.d0 : -1.0f;
+  }
+}
+
+// getFitnessScore, reduction half: [sum d2, count] over d2 <= max_range in the thread layout and summation order of the
+// single registration's k_fitness (a query's value sits on the first of its `spread` lanes), hence the same bits
+__global__ void __launch_bounds__(kThreads) k_bfitness(const BPairInfo* __restrict__ info, const int* __restrict__ fblk_pair, const float* __restrict__ final_Tf,
+                                                      double max_range, const float* __restrict__ sqd0, const float* __restrict__ sqd1,
+                                                      double* __restrict__ partials, unsigned int* __restrict__ tickets, double* __restrict__ results) {
+  const int pair = fblk_pair[blockIdx.x];
+  const BPairInfo pi = info[pair];
+  const int vb = blockIdx.x - pi.fblk0;
+  const int hsel = __float_as_int(final_Tf[pair * 16 + 12]);
+  const float* d2 = hsel == 1 ? sqd0 : sqd1;
+  double acc[2] = {0.0, 0.0};
+  const int gt = vb * kThreads + threadIdx.x;
+  const int il = gt / pi.spread;
+  if ((gt & (pi.spread - 1)) == 0 && il < pi.src_hi - pi.src_lo) {
+    const float d0 = d2[pi.src_lo + il];
+    if (d0 >= 0.f && (double)d0 <= max_range) {
+      acc[0] = (double)d0;
       acc[1] = 1.0;
     }
   }

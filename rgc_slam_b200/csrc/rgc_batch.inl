@@ -396,8 +396,9 @@ static int batch_chunk(rgc_ctx* c, const rgc_params& prm, const rgc_pair* pairs,
   }
   if (want_fitness) {
     CK(c, cudaMemcpyAsync(d_final, h_final, sizeof(float) * 16 * (size_t)B, cudaMemcpyHostToDevice, st));
-    k_bfitness<<<nfblk, kThreads, 0, st>>>(tgts.view, srcs.sorted, d_info, d_fblk_pair, d_final, max_range, corr[0], corr[1], fit_partials, tickets + 2 * B,
-                                           d_fit_res);
+    k_bfitness_search<<<nblk, kThreads, 0, st>>>(tgts.view, srcs.sorted, d_info, d_blk_pair, d_final, corr[0], corr[1], sqd[0], sqd[1]);
+    CKL(c);
+    k_bfitness<<<nfblk, kThreads, 0, st>>>(d_info, d_fblk_pair, d_final, max_range, sqd[0], sqd[1], fit_partials, tickets + 2 * B, d_fit_res);
     CKL(c);
     CK(c, cudaMemcpyAsync(h_res + 33 * (size_t)B, d_fit_res, sizeof(double) * 2 * (size_t)B, cudaMemcpyDeviceToHost, st));
   }

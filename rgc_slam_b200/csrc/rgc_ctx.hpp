@@ -58,7 +58,15 @@ struct rgc_ctx {
     int nbits = 0;
     float s0 = 0.f, cell = 0.f;
     int cloud_bits = 0;
+    // per-level table sizes of that cloud: the next build on the lane allocates, clears and FILLS its level
+    // tables with them right behind the sort, while the per-level cell counts that used to size the tables
+    // travel to the host beside it (build_phase3 checks them against these sizes)
+    bool have_slots = false;
+    uint32_t slots[20] = {};
   } geom_hint[2];
+  bool spec_tables = std::getenv("RGC_NO_SPEC_TABLES") == nullptr;
+  uint64_t spec_table_builds = 0, spec_table_misses = 0;
+  cudaStream_t aux[2] = {nullptr, nullptr};  // per lane: the work a build forks off its lane (table clear, cell counts)
   bool spec_build = std::getenv("RGC_NO_SPEC_BUILD") == nullptr;
   uint64_t spec_builds = 0, spec_misses = 0;  // set_source / set_target return before the build's host waits
   // pinned, device-mapped result area the reduction kernels write straight into

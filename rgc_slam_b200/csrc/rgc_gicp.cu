@@ -71,6 +71,11 @@ struct BuildJob {
   float* h_slot = nullptr;     // pinned + mapped: 6 x kBboxBlocks floats, then kMaxLevels counters and the sort's error word
   float* d_slot = nullptr;     // device alias of h_slot: the kernels write those numbers straight into it
   cudaEvent_t ready = nullptr;  // the host copy the next phase waits for has landed
+  // speculative level tables (sizes of the previous cloud of the lane): cleared on the lane's aux stream during the
+  // sort, filled right behind it; the cell counts are taken on the aux stream meanwhile
+  bool spec_tables = false;
+  size_t spec_slots[kMaxLevels] = {};
+  cudaEvent_t cleared = nullptr;
   explicit BuildJob(rgc_ctx* c) : tmp(c) {}
 };
 
@@ -104,7 +109,8 @@ struct Cloud {
   int n_tiles = 0;
   // stage timing: build begin / end, kNN begin, kNN end (= covariance begin), covariance end.
   // Read back lazily (cloud_times) so that nothing here makes the host wait for the device.
-  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  // ev[5]: the sorted points are final (recorded behind the radix sort's gather pass)
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool build_timed = false, cov_timed = false;
 };
 
@@ -143,18 +149,25 @@ static int join_side(rgc_ctx* c) {
   return RGC_OK;
 }
 
-// The main stream may read a cloud prepared on lane 1 as soon as its BUILD is done (cl.ev[1]); the covariances
-// that lane 1 is still computing are only needed by the first kernel that reads them, which calls join_side()
-// itself.  side_pending stays set.
+// The main stream may read the POINTS of a source cloud prepared on lane 1 as soon as they are sorted (cl.ev[5], or
+// the end of the build, cl.ev[1], with RGC_JOIN_TABLES=1): the correspondence search, the on-demand target
+// covariances and the fitness score read the source's sorted points only — its level tables serve its own k-NN,
+// on lane 1, and the covariances that lane is still computing are only needed by the first kernel that reads them
+// (k_linearize), which calls join_side() itself.  side_pending stays set.  The host has already run the build's
+// last phase (reg_drain), so a sort redone after a grid-geometry miss is the one the event stands for.
 static int join_side_build(rgc_ctx* c, const Cloud& cl) {
-  if (c->side_pending && cl.valid && cl.lane_built == 1 && cl.ev[1]) CK(c, cudaStreamWaitEvent(c->stream, cl.ev[1], 0));
+  static const bool tables = std::getenv("RGC_JOIN_TABLES") != nullptr;
+  cudaEvent_t ev = (!tables && cl.ev[5]) ? cl.ev[5] : cl.ev[1];
+  if (c->side_pending && cl.valid && cl.lane_built == 1 && ev) CK(c, cudaStreamWaitEvent(c->stream, ev, 0));
   return RGC_OK;
 }
 
 static void cloud_release(rgc_ctx* c, Cloud& cl) {
   if (cl.job) {  // a build in flight: its scratch goes back to the pool (stream-ordered reuse), the rest below
+    if (cl.job->spec_tables) cudaStreamSynchronize(c->aux[cl.job->lane]);  // (error paths only) the forked count must not outlive its scratch
     c->put_hslot(cl.job->h_slot);
     c->put_event(cl.job->ready);
+    c->put_event(cl.job->cleared);
     cl.job.reset();
   }
   c->put(cl.sorted);
@@ -164,7 +177,7 @@ static void cloud_release(rgc_ctx* c, Cloud& cl) {
   c->put(cl.cov_state);
   c->put(cl.d_off);
   c->put(cl.d_tiles);
-  for (int i = 0; i < 5; i++) c->put_event(cl.ev[i]);
+  for (int i = 0; i < 6; i++) c->put_event(cl.ev[i]);
   cl = Cloud();
 }
 
@@ -215,6 +228,36 @@ static int radix_sort_pairs(rgc_ctx* c, uint64_t* keys_a, uint64_t* keys_b, uint
 
 static int build_keys(rgc_ctx* c, Cloud& cl, const unsigned char* raw, size_t stride);
 static int build_passes(rgc_ctx* c, Cloud& cl);
+static int build_tables_spec(rgc_ctx* c, Cloud& cl);
+
+// level tables of `slots[l]` entries each, laid out one after the other in cl.tables
+static void table_layout(Cloud& cl, const size_t* slots, TableSet& ts) {
+  GridView& v = cl.view;
+  ts.nlevels = v.nlevels;
+  size_t off = 0;
+  for (int l = 0; l < kMaxLevels; l++) {
+    if (l < v.nlevels) {
+      ts.table[l] = cl.tables + off;
+      ts.mask[l] = (uint32_t)(slots[l] - 1);
+      int lg = 0;
+      while (((size_t)1 << lg) < slots[l]) lg++;
+      ts.shift[l] = (uint32_t)(64 - lg);
+      off += slots[l];
+    } else {
+      ts.table[l] = nullptr;
+      ts.mask[l] = 0;
+      ts.shift[l] = 63;
+    }
+    v.table[l] = ts.table[l];
+    v.mask[l] = ts.mask[l];
+    v.shift[l] = ts.shift[l];
+  }
+}
+static size_t table_slots_for(uint32_t cells) {
+  size_t s = 8;
+  while (s < 2 * (size_t)cells) s <<= 1;
+  return s;
+}
 
 // upload (or adopt a device pointer), Morton-sort, build the level tables — in three phases separated by
 // the two host waits (see BuildJob).  All phases of a cloud run on the lane that was current in phase 1.
@@ -228,7 +271,7 @@ static int build_phase1(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, 
   if (stride < 12 || stride % 4) FAIL(c, RGC_ERR_INVALID, "point stride must be a multiple of 4 and >= 12 bytes");
   const int n = (int)n_sz;
   cudaStream_t st = c->stream;
-  for (int i = 0; i < 5; i++)
+  for (int i = 0; i < 6; i++)
     if (!(cl.ev[i] = c->get_event())) FAIL(c, RGC_ERR_CUDA, "cudaEventCreate failed");
   CK(c, cudaEventRecord(cl.ev[0], st));
   c->mark("build: begin");
@@ -283,6 +326,20 @@ static int build_phase1(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, 
     c->spec_builds++;
     grid_set(cl.view, h.nbits, h.s0);
     cl.view.n = n;
+    if (c->spec_tables && h.have_slots) {
+      // level tables of the previous cloud's sizes, cleared on the aux stream while the keys are made and sorted
+      size_t total = 0;
+      for (int l = 0; l < cl.view.nlevels; l++) total += (j.spec_slots[l] = h.slots[l]);
+      cl.tables = (GridSlot*)c->get(total * sizeof(GridSlot));
+      j.cleared = c->get_event();
+      if (!cl.tables || !j.cleared) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (tables)");
+      cudaStream_t aux = c->aux[c->lane];
+      CK(c, cudaStreamWaitEvent(aux, cl.ev[0], 0));  // the pool block's previous users are ordered before ev[0] on this lane
+      CK(c, cudaMemsetAsync(cl.tables, 0xff, total * sizeof(GridSlot), aux));
+      CK(c, cudaEventRecord(j.cleared, aux));
+      j.spec_tables = true;
+      c->spec_table_builds++;
+    }
     TRY(build_keys(c, cl, d_raw, stride));
     // main-lane (target) clouds of a deferred build stop here: their sort passes are issued by the drain AFTER the
     // side lane's (the source's whole chain is short but the host needs ~40 us to issue a sort: issued first, the
@@ -342,17 +399,40 @@ static int build_passes(rgc_ctx* c, Cloud& cl) {
   j.vin = j.vals_a;
   const SortGather gather{j.orig, cl.sorted, cl.inv};
   TRY(radix_sort_pairs(c, j.keys_a, j.keys_b, j.vals_a, j.vals_b, j.hist, n, 3 * v.nbits + j.cloud_bits, &j.kin, &j.vin, true, &gather));
+  CK(c, cudaEventRecord(cl.ev[5], st));
   c->mark("build: radix sort + gather");
   // level counts, then the sort's error word (a look-back that gave up: cannot happen, but must not pass silently),
   // written into the mapped slot by the kernel's last block
-  CK(c, cudaMemsetAsync(j.d_counts, 0, 4 * (kMaxLevels + 1), st));
-  k_count_cells<<<div_up(n, 256), 256, 0, st>>>(j.kin, n, v.nlevels, j.d_counts, j.hist + 8, reinterpret_cast<uint32_t*>(j.d_slot + 6 * kBboxBlocks));
+  cudaStream_t cst = st;
+  if (j.spec_tables) {
+    // the tables are filled right away, with the sizes of the lane's previous cloud; the counts that say whether those
+    // sizes hold are taken beside it on the aux stream (build_phase3 reads them)
+    TRY(build_tables_spec(c, cl));
+    cst = c->aux[j.lane];
+    CK(c, cudaStreamWaitEvent(cst, cl.ev[5], 0));
+  }
+  CK(c, cudaMemsetAsync(j.d_counts, 0, 4 * (kMaxLevels + 1), cst));
+  k_count_cells<<<div_up(n, 256), 256, 0, cst>>>(j.kin, n, v.nlevels, j.d_counts, j.hist + 8, reinterpret_cast<uint32_t*>(j.d_slot + 6 * kBboxBlocks));
   CKL(c);
-  CK(c, cudaEventRecord(j.ready, st));
-  c->mark("build: cell counts");
+  CK(c, cudaEventRecord(j.ready, cst));
+  if (!j.spec_tables) c->mark("build: cell counts");
   j.stage = 2;
   return RGC_OK;
 }
+// fill the level tables with the sizes of the lane's previous cloud, right behind the sort (BuildJob::spec_tables)
+static int build_tables_spec(rgc_ctx* c, Cloud& cl) {
+  BuildJob& j = *cl.job;
+  cudaStream_t st = c->stream;
+  TableSet ts;
+  table_layout(cl, j.spec_slots, ts);
+  CK(c, cudaStreamWaitEvent(st, j.cleared, 0));
+  k_build_tables<<<dim3(div_up(j.n, 256), cl.view.nlevels), 256, 0, st>>>(j.kin, j.n, ts);
+  CKL(c);
+  CK(c, cudaEventRecord(cl.ev[1], st));
+  c->mark("build: tables (speculative sizes)");
+  return RGC_OK;
+}
+
 static int build_sort(rgc_ctx* c, Cloud& cl, const unsigned char* raw, size_t stride) {
   TRY(build_keys(c, cl, raw, stride));
   return build_passes(c, cl);
@@ -396,6 +476,11 @@ static int build_phase3(rgc_ctx* c, Cloud& cl) {
     rgc_ctx::GeomHint& h = c->geom_hint[j.lane];
     if (s0 != v.s0 || nbits > v.nbits) {  // it does not: sort again with the right geometry (j.orig is intact)
       c->spec_misses++;
+      if (j.spec_tables) {  // the tables filled from those keys go too (stream-ordered reuse of the block on this lane)
+        c->put(cl.tables);
+        cl.tables = nullptr;
+        j.spec_tables = false;
+      }
       grid_geometry(mn, mx, j.cell, v, j.max_bits);
       v.n = n;
       j.spec = false;
@@ -415,48 +500,48 @@ static int build_phase3(rgc_ctx* c, Cloud& cl) {
   size_t total_slots = 0;
   size_t slots[kMaxLevels];
   for (int l = 0; l < v.nlevels; l++) {
-    size_t s = 8;
-    while (s < 2 * (size_t)h_counts[l]) s <<= 1;
-    slots[l] = s;
-    total_slots += s;
+    slots[l] = table_slots_for(h_counts[l]);
+    total_slots += slots[l];
   }
-  cl.tables = (GridSlot*)c->get(total_slots * sizeof(GridSlot));
-  if (!cl.tables) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (tables)");
-  CK(c, cudaMemsetAsync(cl.tables, 0xff, total_slots * sizeof(GridSlot), st));
-  TableSet ts;
-  ts.nlevels = v.nlevels;
-  size_t off = 0;
-  for (int l = 0; l < kMaxLevels; l++) {
-    if (l < v.nlevels) {
-      ts.table[l] = cl.tables + off;
-      ts.mask[l] = (uint32_t)(slots[l] - 1);
-      int lg = 0;
-      while (((size_t)1 << lg) < slots[l]) lg++;
-      ts.shift[l] = (uint32_t)(64 - lg);
-      off += slots[l];
-    } else {
-      ts.table[l] = nullptr;
-      ts.mask[l] = 0;
-      ts.shift[l] = 63;
+  {  // what the next cloud of this lane will try
+    rgc_ctx::GeomHint& h = c->geom_hint[j.lane];
+    h.have_slots = h.valid && h.nbits == v.nbits && v.nlevels <= 20;
+    for (int l = 0; h.have_slots && l < v.nlevels; l++) h.slots[l] = (uint32_t)slots[l];
+  }
+  bool tables_done = false;
+  if (j.spec_tables) {
+    // tables already filled (build_passes) with the previous cloud's sizes: they stand if every level stayed under
+    // 70 % load (sized from its own counts a table is 25 - 50 % full); the search results do not depend on the sizes
+    tables_done = true;
+    for (int l = 0; l < v.nlevels; l++) tables_done = tables_done && 10 * (size_t)h_counts[l] <= 7 * j.spec_slots[l];
+    if (!tables_done) {
+      c->spec_table_misses++;
+      c->put(cl.tables);
+      cl.tables = nullptr;
     }
-    v.table[l] = ts.table[l];
-    v.mask[l] = ts.mask[l];
-    v.shift[l] = ts.shift[l];
   }
-  c->mark("build: host wait over, tables cleared");
-  k_build_tables<<<dim3(div_up(n, 256), v.nlevels), 256, 0, st>>>(j.kin, n, ts);
-  CKL(c);
-  c->mark("build: tables");
+  if (!tables_done) {
+    cl.tables = (GridSlot*)c->get(total_slots * sizeof(GridSlot));
+    if (!cl.tables) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (tables)");
+    CK(c, cudaMemsetAsync(cl.tables, 0xff, total_slots * sizeof(GridSlot), st));
+    TableSet ts;
+    table_layout(cl, slots, ts);
+    c->mark("build: host wait over, tables cleared");
+    k_build_tables<<<dim3(div_up(n, 256), v.nlevels), 256, 0, st>>>(j.kin, n, ts);
+    CKL(c);
+    c->mark("build: tables");
+    CK(c, cudaEventRecord(cl.ev[1], st));
+  }
   v.pts = reinterpret_cast<const F4*>(cl.sorted);
   v.inv = cl.inv;
   cl.n = n;
   cl.key = j.key;
   cl.valid = true;
   cl.lane_built = c->lane;
-  CK(c, cudaEventRecord(cl.ev[1], st));
   cl.build_timed = true;
   c->put_hslot(j.h_slot);
   c->put_event(j.ready);
+  c->put_event(j.cleared);
   cl.job.reset();  // scratch back to the pool (the kernels above are ordered before any reuse on this lane)
   return RGC_OK;
 }
@@ -1362,7 +1447,9 @@ int rgc_ctx_create(int device, rgc_ctx** out) {
        cudaStreamCreateWithPriority(&c->parked.stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
        cudaHostAlloc((void**)&c->parked.h_bbox, sizeof(float) * 6 * kBboxBlocks, cudaHostAllocDefault) == cudaSuccess &&
        cudaHostAlloc((void**)&c->parked.h_counts, sizeof(uint32_t) * kMaxLevels, cudaHostAllocDefault) == cudaSuccess &&
-       cudaEventCreateWithFlags(&c->join_ev, cudaEventDisableTiming) == cudaSuccess;
+       cudaEventCreateWithFlags(&c->join_ev, cudaEventDisableTiming) == cudaSuccess &&
+       cudaStreamCreateWithPriority(&c->aux[0], cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
+       cudaStreamCreateWithPriority(&c->aux[1], cudaStreamNonBlocking, prio_hi) == cudaSuccess;
   for (int i = 0; ok && i < 8; i++) ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
   for (int i = 0; ok && i < 4; i++) ok = cudaEventCreate(&c->evk[i]) == cudaSuccess;
   c->profile = std::getenv("RGC_PROFILE") != nullptr;
@@ -1380,6 +1467,11 @@ int rgc_ctx_destroy(rgc_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   cudaStreamSynchronize(c->parked.stream);
+  for (cudaStream_t a : c->aux)
+    if (a) {
+      cudaStreamSynchronize(a);
+      cudaStreamDestroy(a);
+    }
   for (auto& kv : c->block_info) cudaFree(kv.first);
   cudaFreeHost(c->h_result);
   cudaFreeHost(c->h_seq);
@@ -1403,6 +1495,7 @@ const char* rgc_last_error(const rgc_ctx* c) { return c ? c->err.c_str() : "null
 int rgc_ctx_synchronize(rgc_ctx* c) {
   CK(c, cudaStreamSynchronize(c->parked.stream));
   CK(c, cudaStreamSynchronize(c->stream));
+  for (cudaStream_t a : c->aux) CK(c, cudaStreamSynchronize(a));
   return RGC_OK;
 }
 void* rgc_ctx_stream(rgc_ctx* c) { return (void*)c->stream; }
@@ -1775,6 +1868,13 @@ int rgc_debug_build_stats(rgc_ctx* c, unsigned long long* spec_builds, unsigned 
   if (!c) return RGC_ERR_INVALID;
   if (spec_builds) *spec_builds = c->spec_builds;
   if (spec_misses) *spec_misses = c->spec_misses;
+  return RGC_OK;
+}
+// builds whose level tables were filled with the previous cloud's sizes / how many of those had to be redone
+int rgc_debug_table_stats(rgc_ctx* c, unsigned long long* spec_tables, unsigned long long* spec_table_misses) {
+  if (!c) return RGC_ERR_INVALID;
+  if (spec_tables) *spec_tables = c->spec_table_builds;
+  if (spec_table_misses) *spec_table_misses = c->spec_table_misses;
   return RGC_OK;
 }
 int rgc_debug_set_knn_defer(rgc_ctx* c, int cands) {

@@ -116,7 +116,10 @@ __global__ void __launch_bounds__(256) k_morton(const float4* __restrict__ pts, 
 // LSD radix sort, 8-bit digits.  Tile = 256 threads x RS_ITEMS keys; inside a tile the key order
 // is (warp, round, lane) == ascending index, so ranks computed per (warp, round) with match_any
 // are stable.  hist is digit-major [256][nblk] so one exclusive scan yields every block's base.
-constexpr int RS_ITEMS = 8;
+#ifndef RGC_RS_ITEMS
+#define RGC_RS_ITEMS 8
+#endif
+constexpr int RS_ITEMS = RGC_RS_ITEMS;
 constexpr int RS_TILE = 256 * RS_ITEMS;
 
 __global__ void __launch_bounds__(256) k_rs_hist(const uint64_t* __restrict__ keys, int n, int shift, uint32_t* __restrict__ hist, int nblk) {
@@ -494,14 +497,17 @@ struct TableSet {
   int nlevels;
 };
 
+// nullptr: the table is full.  Only a table sized SPECULATIVELY (from the previous cloud's cell counts, before
+// this cloud's are known) can be: the host sees the real counts a moment later and rebuilds it (build_phase3).
 __device__ __forceinline__ GridSlot* slot_insert_or_find(GridSlot* tab, uint32_t mask, uint32_t shift, uint64_t key) {
   uint32_t h = slot_of(key, shift);
-  for (;;) {
+  for (uint32_t probes = 0; probes <= mask; probes++) {
     unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long*>(&tab[h].key), (unsigned long long)kEmptyKey, (unsigned long long)key);
     // the top byte of a live key word collects the occupied-children bits while the table is being built
     if (prev == kEmptyKey || (prev & kKeyMask) == key) return &tab[h];
     h = (h + 1) & mask;
   }
+  return nullptr;
 }
 
 // blockIdx.y = level: one (point, level) pair per thread, so no thread walks all the levels
@@ -522,15 +528,19 @@ __global__ void __launch_bounds__(256) k_build_tables(const uint64_t* __restrict
   }
   if (opens) {
     const uint64_t ck = key >> (3 * l);
-    slot_insert_or_find(ts.table[l], ts.mask[l], ts.shift[l], ck)->start = (uint32_t)i;
-    if (i > 0) slot_insert_or_find(ts.table[l], ts.mask[l], ts.shift[l], prev >> (3 * l))->end = (uint32_t)i;
+    GridSlot* s = slot_insert_or_find(ts.table[l], ts.mask[l], ts.shift[l], ck);
+    if (s) s->start = (uint32_t)i;
+    if (i > 0 && (s = slot_insert_or_find(ts.table[l], ts.mask[l], ts.shift[l], prev >> (3 * l)))) s->end = (uint32_t)i;
     if (l + 1 < ts.nlevels) {
       GridSlot* ps = slot_insert_or_find(ts.table[l + 1], ts.mask[l + 1], ts.shift[l + 1], ck >> 3);
       // the mask lives in the top byte of the 64-bit key word = top byte of its high 32-bit half
-      atomicOr(reinterpret_cast<unsigned int*>(&ps->key) + 1, 1u << (24 + (int)(ck & 7)));
+      if (ps) atomicOr(reinterpret_cast<unsigned int*>(&ps->key) + 1, 1u << (24 + (int)(ck & 7)));
     }
   }
-  if (i == n - 1) slot_insert_or_find(ts.table[l], ts.mask[l], ts.shift[l], key >> (3 * l))->end = (uint32_t)n;
+  if (i == n - 1) {
+    GridSlot* s = slot_insert_or_find(ts.table[l], ts.mask[l], ts.shift[l], key >> (3 * l));
+    if (s) s->end = (uint32_t)n;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

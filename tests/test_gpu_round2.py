@@ -405,6 +405,50 @@ def test_speculative_grid_geometry_hits_and_misses(rgc, orc):
 
 
 @pytest.mark.gpu
+def test_speculative_table_sizes_hits_and_misses(rgc, orc):
+    """The level tables of a cloud are allocated, cleared and filled with the table sizes of the previous cloud of the
+    lane, before this cloud's own cell counts reach the host (rgc_gicp.cu: build_passes / build_phase3).  Similar
+    clouds must keep those tables, a cloud with many more cells must get them rebuilt, and the neighbour lists are
+    the oracle's either way (they do not depend on table sizes)."""
+    import ctypes as C
+    L = rgc.lib()
+    L.rgc_debug_table_stats.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
+    from rgc_slam_b200 import api
+    ctx = api.default_context(0)
+
+    def stats():
+        a, b = C.c_ulonglong(), C.c_ulonglong()
+        ctx.check(L.rgc_debug_table_stats(ctx._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    rng = np.random.default_rng(11)
+
+    def cloud(n):
+        P = np.ones((n, 4), np.float32)
+        P[:, :3] = rng.uniform(-20, 20, (n, 3))
+        return P
+
+    def check(P):
+        idx, d2 = rgc.knn(P, P[:400], 20)
+        oi, od = orc.knn(P, P[:400], 20, brute=True)
+        assert np.array_equal(idx, oi) and np.array_equal(d2, od)
+
+    check(cloud(3000))
+    check(cloud(3000))   # (the first one may still shrink the hinted grid left by earlier tests: the sizes are kept from the second on)
+    s0 = stats()
+    check(cloud(3100))   # same extent, same density: the previous sizes hold
+    check(cloud(2900))
+    s1 = stats()
+    assert s1[0] >= s0[0] + 2, "tables are not being filled speculatively"
+    assert s1[1] == s0[1], "similar clouds must keep the speculative tables"
+    check(cloud(40000))  # > 10x the cells: far over the 70 % load the check tolerates (some levels overflow outright)
+    s2 = stats()
+    assert s2[1] >= s1[1] + 1, "an overfull speculative table was not detected"
+    check(cloud(3000))   # oversized tables are fine; the hint follows the latest cloud
+    check(cloud(3000))
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("k", [33, 64, 128])
 def test_k_above_32(rgc, orc, small_pair, k):
     """setCorrespondenceRandomness accepts any k in the reference (fast_gicp_impl.hpp:38-40); above 32 the tile kernel

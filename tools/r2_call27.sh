@@ -1,0 +1,20 @@
+# round 2, GPU call 27: speculative table sizes (tables filled right behind the sort, counts on an aux stream) and the
+# one-launch cooperative build of sweep-sized clouds (k_small_build)
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/r2c27_pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/r2c27_pytest.log
+tail -5 gpurun_out/r2c27_pytest.log
+run() { timeout 300 python bench.py --steps 60 --warmup 8 --no-cpu --no-large --no-extra --concurrent 0 2>/dev/null | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$1', round(d['ms_per_step'],3), 'p50', round(d['p50_ms'],3), 'e2e ms', round(1e3/d['e2e']['value'],3), 'warm', round(d['warm_ms_per_align'],3), {k: round(v,3) for k,v in d['stage_ms'].items()})"; }
+for r in 1 2; do
+  RGC_NO_SPEC_TABLES=1 RGC_NO_SMALL_BUILD=1 run old
+  RGC_NO_SMALL_BUILD=1 run spec_tables
+  RGC_NO_SPEC_TABLES=1 run small_build
+  run both
+done 2>&1 | tee gpurun_out/r2c27_ab.txt
+RGC_TIMELINE=1 timeout 300 python tools/prof_step.py 6 > gpurun_out/r2c27_timeline.log 2> gpurun_out/r2c27_timeline.err
+python - <<'PY'
+lines = open("gpurun_out/r2c27_timeline.err").read().split("\n")
+starts = [i for i, l in enumerate(lines) if "marks (us since" in l]
+print("\n".join(lines[starts[-1]:starts[-1]+24]))
+PY
+timeout 600 compute-sanitizer --tool memcheck python tools/sanitize_small.py > gpurun_out/r2c27_memcheck.log 2>&1; tail -2 gpurun_out/r2c27_memcheck.log
+timeout 600 compute-sanitizer --tool racecheck python tools/sanitize_small.py > gpurun_out/r2c27_racecheck.log 2>&1; tail -2 gpurun_out/r2c27_racecheck.log
