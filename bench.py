@@ -45,6 +45,14 @@ METRIC = "scan-to-map GICP aligns/sec (VLP-16 vs 500k-pt map)"
 DTYPE = "f64 (H/b, covariances) + f32 (points, kNN distances)"
 
 
+_T0 = time.perf_counter()
+
+
+def log(msg: str):
+    """progress on stderr (stdout carries the one JSON line)"""
+    print(f"[bench +{time.perf_counter() - _T0:6.1f}s rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
+
+
 def build_workload(rank: int, n_submap: int, n_pairs: int = N_PAIRS):
     """config C2 stream (rgc_slam_b200/workloads.py): sweeps along a trajectory vs the accumulated submap"""
     return workloads.build_c2_pairs(rank, n_submap, n_pairs)
@@ -451,7 +459,98 @@ def run_ours(args, rank, world):
     h2d = 16 * (n_src + n_tgt)
     d2h = 64 + (res["n_linearize"] * 29 + res["n_compute_error"]) * 8 + 296 * 24 * 2 + 22 * 4 * 2
 
+    log(f"headline legs done: {value:.1f} aligns/s device, {e2e_value:.1f} e2e")
+    # ---------------- per-kernel numbers of one C2 sweep (CUDA events recorded by the library around each launch)
+    peak, peak_src = peak_hbm()
+    gw = new_reg(rgc, ctx)
+    gw.setInputTarget(dev[0]["tgt"])
+    gw.setInputSource(dev[0]["src"])
+    Tg = pairs[0]["guess"].astype(np.float64)
+    gw.linearize(Tg)
+    ctx.set_profiling(True)
+    km = []
+    for _ in range(7):
+        gw.linearize(Tg)
+        gw.compute_error(Tg)
+        km.append(ctx.last_kernel_ms())
+    ctx.set_profiling(False)
+    kc = {kk: float(np.median([x[kk] for x in km])) for kk in km[0]}
+    gw = None
+    st = cold["stage"]
+    it_mean = float(np.mean(cold["iters"]))
+    # share of a cold step: one un-hinted (~2x) + it_mean hinted correspondence searches vs everything else
+    corr_step_ms = kc["k_correspond"] * (it_mean + 2.0)
+    corr_bytes = n_src * (16 + 4 + 4 + 16)  # p in, corr + d2 out, the neighbour found
+    kernels = {
+        "k_correspond (1-NN, hinted, 1 sweep; 4 lanes per query)": {"ms": kc["k_correspond"], "queries": n_src, "Mqueries_per_s": n_src / kc["k_correspond"] / 1e3, "bound": "sm"},
+        "k_knn_tile + k_knn_warp k=20 (source sweep)": {"ms": st["src_knn"], "queries": n_src, "Mqueries_per_s": n_src / max(st["src_knn"], 1e-9) / 1e3, "bound": "sm"},
+        "k_linearize (1 sweep)": {"ms": kc["k_linearize"], "bound": "latency at one sweep (4 MB); hbm at batch scale: see hbm_kernels"},
+        "k_compute_error (1 sweep)": {"ms": kc["k_compute_error"], "bound": "latency at one sweep"},
+        "target build (sort + voxel hash, 500k)": {"ms": st["tgt_build"], "bound": "latency: 9 dependent kernels (keys + histograms, 5 one-launch radix passes, cell counts, tables) and one host wait"},
+    }
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    tinfo = json.load(open(tpath)).get("k_correspond", {}) if os.path.exists(tpath) else {}
+    roofline = {"bound": "sm", "kernel": "k_correspond", "achieved": corr_bytes / (kc["k_correspond"] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": corr_bytes / (kc["k_correspond"] * 1e-3) / 1e9 / peak, "traffic": tinfo.get("bytes"), "peak_source": peak_src,
+                "share_of_step": corr_step_ms / (dev_ms_max / args.steps),
+                "sm": {kk: tinfo[kk] for kk in tinfo if kk != "bytes"},
+                "note": "with on-demand target covariances the largest share of a cold step is the exact 1-NN correspondence search (one launch per "
+                        "linearize), a divergent tree walk over an L2-resident voxel hash: SM-issue bound, reported as queries/s and ncu SM throughput "
+                        "(profiles/); `achieved` is its algorithmic bytes over its time for completeness.  The HBM-bound kernels of the path "
+                        "(covariance, linearize, compute_error) are measured at 8 M / 2 M points under hbm_kernels.",
+                "kernels": kernels}
+    # ---------------- CPU baseline (oracle port), rank 0, N=1 only, bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline(pairs, n_aligns=3)
+        log("cpu_baseline done")
+
+    # ---------------- the line, as far as the required legs go.  The optional legs below add their keys to it; a
+    # watchdog prints it without them if they overrun their budget (a leg stuck inside a library call must not cost
+    # the round its headline number)
+    Tt = pairs[(args.steps - 1) % len(pairs)]["truth"]
+    tt = cold["times"]
+    out = {
+        "metric": METRIC, "value": value, "unit": "aligns/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "p50_ms": float(np.percentile(tt, 50)),
+        "p99_ms": float(np.percentile(tt, 99)), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic", "config": config_dict(n_src, n_tgt, len(pairs), world),
+        "e2e": {"value": e2e_value, "unit": "aligns/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "p50_ms": 1e3 * float(np.percentile(e2e["times"], 50)),
+                "p99_ms": 1e3 * float(np.percentile(e2e["times"], 99)),
+                "timing": "wall clock around new object + setInputTarget + setInputSource + align with pinned host clouds"},
+        "gpu_launches": int(cold["launches"]),
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "stage_ms": st,
+        "stage_ms_note": "per-stage CUDA-event times on each stage's own stream; the source stages run on a second "
+                         "stream concurrently with the target stages, so the stages do not add up to ms_per_step",
+        "lm_iterations_mean": it_mean,
+        "wall_s_timed_region": wall,
+        "pose_err_vs_truth_m": float(np.abs(T[:3, 3] - Tt[:3, 3]).max()),
+    }
     extra = {}
+    emitted = threading.Lock()
+
+    def emit(note=None):
+        if not emitted.acquire(blocking=False):
+            return
+        if rank == 0:
+            line = dict(out)
+            line.update(extra)
+            if note:
+                line["optional_legs"] = note
+            print(json.dumps(line), flush=True)
+
+    def overrun():
+        log(f"optional legs overran {args.leg_budget:.0f} s: printing the line without the unfinished ones")
+        emit(f"stopped after {args.leg_budget:.0f} s; finished: {sorted(extra)}")
+        os._exit(0)
+
+    dog = threading.Timer(args.leg_budget, overrun)
+    dog.daemon = True
+    dog.start()
+
     if world == 1:
         nshort = max(10, min(args.steps, 40))
         # ---------------- the reference's covariance schedule: all 500k target covariances every frame
@@ -534,45 +633,7 @@ def run_ours(args, rank, world):
             for cx in ctxs:
                 cx.close()
 
-    # ---------------- per-kernel numbers of one C2 sweep (CUDA events recorded by the library around each launch)
-    peak, peak_src = peak_hbm()
-    gw = new_reg(rgc, ctx)
-    gw.setInputTarget(dev[0]["tgt"])
-    gw.setInputSource(dev[0]["src"])
-    Tg = pairs[0]["guess"].astype(np.float64)
-    gw.linearize(Tg)
-    ctx.set_profiling(True)
-    km = []
-    for _ in range(7):
-        gw.linearize(Tg)
-        gw.compute_error(Tg)
-        km.append(ctx.last_kernel_ms())
-    ctx.set_profiling(False)
-    kc = {kk: float(np.median([x[kk] for x in km])) for kk in km[0]}
-    gw = None
-    st = cold["stage"]
-    it_mean = float(np.mean(cold["iters"]))
-    # share of a cold step: one un-hinted (~2x) + it_mean hinted correspondence searches vs everything else
-    corr_step_ms = kc["k_correspond"] * (it_mean + 2.0)
-    corr_bytes = n_src * (16 + 4 + 4 + 16)  # p in, corr + d2 out, the neighbour found
-    kernels = {
-        "k_correspond (1-NN, hinted, 1 sweep; 4 lanes per query)": {"ms": kc["k_correspond"], "queries": n_src, "Mqueries_per_s": n_src / kc["k_correspond"] / 1e3, "bound": "sm"},
-        "k_knn_tile + k_knn_warp k=20 (source sweep)": {"ms": st["src_knn"], "queries": n_src, "Mqueries_per_s": n_src / max(st["src_knn"], 1e-9) / 1e3, "bound": "sm"},
-        "k_linearize (1 sweep)": {"ms": kc["k_linearize"], "bound": "latency at one sweep (4 MB); hbm at batch scale: see hbm_kernels"},
-        "k_compute_error (1 sweep)": {"ms": kc["k_compute_error"], "bound": "latency at one sweep"},
-        "target build (sort + voxel hash, 500k)": {"ms": st["tgt_build"], "bound": "latency: 9 dependent kernels (keys + histograms, 5 one-launch radix passes, cell counts, tables) and one host wait"},
-    }
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    tinfo = json.load(open(tpath)).get("k_correspond", {}) if os.path.exists(tpath) else {}
-    roofline = {"bound": "sm", "kernel": "k_correspond", "achieved": corr_bytes / (kc["k_correspond"] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": corr_bytes / (kc["k_correspond"] * 1e-3) / 1e9 / peak, "traffic": tinfo.get("bytes"), "peak_source": peak_src,
-                "share_of_step": corr_step_ms / (dev_ms_max / args.steps),
-                "sm": {kk: tinfo[kk] for kk in tinfo if kk != "bytes"},
-                "note": "with on-demand target covariances the largest share of a cold step is the exact 1-NN correspondence search (one launch per "
-                        "linearize), a divergent tree walk over an L2-resident voxel hash: SM-issue bound, reported as queries/s and ncu SM throughput "
-                        "(profiles/); `achieved` is its algorithmic bytes over its time for completeness.  The HBM-bound kernels of the path "
-                        "(covariance, linearize, compute_error) are measured at 8 M / 2 M points under hbm_kernels.",
-                "kernels": kernels}
+        log("eager / warm / vgicp / concurrent legs done")
     ctx.close()
     del dev, flush
     torch.cuda.empty_cache()
@@ -581,6 +642,8 @@ def run_ours(args, rank, world):
             roofline["hbm_kernels"] = leg_roofline_large(torch, rgc, local)
         except Exception as e:  # noqa: BLE001 — the headline must still be printed
             roofline["hbm_kernels"] = {"error": f"{type(e).__name__}: {e}"}
+
+        log("hbm_kernels leg done")
 
     # ---------------- the other configurations
     if not args.no_extra:
@@ -594,36 +657,9 @@ def run_ours(args, rank, world):
                     raise  # a collective leg that fails on one rank would hang the others
                 extra[name] = {"error": f"{type(e).__name__}: {e}"}
 
-    # ---------------- CPU baseline (oracle port), rank 0, N=1 only, bounded sample
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_baseline(pairs, n_aligns=3)
-
-    if rank == 0:
-        Tt = pairs[(args.steps - 1) % len(pairs)]["truth"]
-        tt = cold["times"]
-        cfg = config_dict(n_src, n_tgt, len(pairs), world)
-        out = {
-            "metric": METRIC, "value": value, "unit": "aligns/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "p50_ms": float(np.percentile(tt, 50)),
-            "p99_ms": float(np.percentile(tt, 99)), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic", "config": cfg,
-            "e2e": {"value": e2e_value, "unit": "aligns/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "p50_ms": 1e3 * float(np.percentile(e2e["times"], 50)),
-                    "p99_ms": 1e3 * float(np.percentile(e2e["times"], 99)),
-                    "timing": "wall clock around new object + setInputTarget + setInputSource + align with pinned host clouds"},
-            "gpu_launches": int(cold["launches"]),
-            "clocks": clocks,
-            "roofline": roofline,
-            "cpu_baseline": cpu,
-            "stage_ms": st,
-            "stage_ms_note": "per-stage CUDA-event times on each stage's own stream; the source stages run on a second "
-                             "stream concurrently with the target stages, so the stages do not add up to ms_per_step",
-            "lm_iterations_mean": it_mean,
-            "wall_s_timed_region": wall,
-            "pose_err_vs_truth_m": float(np.abs(T[:3, 3] - Tt[:3, 3]).max()),
-        }
-        out.update(extra)
-        print(json.dumps(out))
+            log(f"{name} leg done")
+    dog.cancel()
+    emit()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -720,6 +756,8 @@ def main():
     ap.add_argument("--no-large", action="store_true", help="skip the 8 M / 2 M HBM-kernel leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the C3 / C4 / C5 legs")
     ap.add_argument("--c4-pairs", type=int, default=0, help="pairs of the C4 leg (default 4096 at every N: one strong-scaling series)")
+    ap.add_argument("--leg-budget", type=float, default=420.0, help="seconds the optional legs (everything after the headline, per-kernel and "
+                    "cpu_baseline numbers) may take before the line is printed without the unfinished ones")
     ap.add_argument("--concurrent", type=int, default=4, help="host threads of the concurrent-throughput leg (0/1 = skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))

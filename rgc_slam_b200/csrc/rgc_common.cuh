@@ -126,6 +126,24 @@ RGC_HD void transform_f(const float* T, float x, float y, float z, float& ox, fl
   oz = fadd(fadd(fadd(fmul(T[8], x), fmul(T[9], y)), fmul(T[10], z)), T[11]);
 }
 
+#if defined(__CUDACC__)
+// Programmatic dependent launch (sm_90+ `griddepcontrol`).  The hot chains of this library are strings of short
+// dependent kernels (a cloud build: keys -> five sort passes -> tables; an LM step: correspondences -> on-demand
+// k-NN -> covariances -> linearize), each boundary costing a drain + launch gap of a few microseconds.  A kernel
+// launched with cudaLaunchAttributeProgrammaticStreamSerialization (launch_pdl, rgc_gicp.cu) may be scheduled
+// while its predecessor is still running; pdl_enter() is therefore the FIRST statement of every kernel on those
+// chains, before any early return: `wait` blocks until the predecessor grid has completed and its writes are
+// visible (so the kernel body sees exactly what it would see in plain stream order), `launch_dependents` lets the
+// successor's blocks become resident behind this grid's last wave.  Without the launch attribute both
+// instructions are no-ops, so the same kernels can be launched with <<<>>> elsewhere.
+__device__ __forceinline__ void pdl_enter() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+#endif
+
 enum RegMethod { REG_NONE = 0, REG_MIN_EIG = 1, REG_NORMALIZED_MIN_EIG = 2, REG_PLANE = 3, REG_FROBENIUS = 4 };
 
 }  // namespace rgc

@@ -63,8 +63,11 @@ struct rgc_ctx {
     // travel to the host beside it (build_phase3 checks them against these sizes)
     bool have_slots = false;
     uint32_t slots[20] = {};
+    int slots_n = 0;  // points of the cloud those sizes were made for: a much larger cloud does not try them
   } geom_hint[2];
   bool spec_tables = std::getenv("RGC_NO_SPEC_TABLES") == nullptr;
+  // programmatic dependent launch on the build / LM kernel chains (rgc_common.cuh: pdl_enter; rgc_gicp.cu: launch_pdl)
+  bool pdl = std::getenv("RGC_NO_PDL") == nullptr;
   uint64_t spec_table_builds = 0, spec_table_misses = 0;
   cudaStream_t aux[2] = {nullptr, nullptr};  // per lane: the work a build forks off its lane (table clear, cell counts)
   bool spec_build = std::getenv("RGC_NO_SPEC_BUILD") == nullptr;

@@ -33,6 +33,24 @@ using namespace rgc;
 
 #include "rgc_comm.inl"
 
+// Launch `kern` so that it may be scheduled while the kernel before it on `st` is still draining (programmatic
+// dependent launch).  Only for kernels that start with pdl_enter() (rgc_common.cuh); with c->pdl off (RGC_NO_PDL=1)
+// this is a plain launch.  Arguments are converted to the kernel's parameter types by cudaLaunchKernelEx.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(const rgc_ctx* c, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = c->pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 // RGC_TRACE=1: wall-clock trace of the host side of the build pipeline (debug aid)
 static bool trace_on() {
   static int v = -1;
@@ -214,9 +232,9 @@ static int radix_sort_pairs(rgc_ctx* c, uint64_t* keys_a, uint64_t* keys_b, uint
   uint32_t *vin = vals_a, *vo = vals_b;
   for (int p = 0; p < passes; p++) {
     if (gather && p == passes - 1)
-      k_rs_onesweep<true><<<nblk, 256, 0, c->stream>>>(kin, vin, ko, vo, scratch, p, n, nblk, gather->pts, gather->sorted, gather->inv);
+      launch_pdl(c, k_rs_onesweep<true>, dim3(nblk), dim3(256), 0, c->stream, kin, vin, ko, vo, scratch, p, n, nblk, gather->pts, gather->sorted, gather->inv);
     else
-      k_rs_onesweep<false><<<nblk, 256, 0, c->stream>>>(kin, vin, ko, vo, scratch, p, n, nblk, nullptr, nullptr, nullptr);
+      launch_pdl(c, k_rs_onesweep<false>, dim3(nblk), dim3(256), 0, c->stream, kin, vin, ko, vo, scratch, p, n, nblk, nullptr, nullptr, nullptr);
     CKL(c);
     std::swap(kin, ko);
     std::swap(vin, vo);
@@ -326,7 +344,10 @@ static int build_phase1(rgc_ctx* c, Cloud& cl, const void* points, size_t n_sz, 
     c->spec_builds++;
     grid_set(cl.view, h.nbits, h.s0);
     cl.view.n = n;
-    if (c->spec_tables && h.have_slots) {
+    // (only for a cloud of about the previous one's size: its tables were sized for 25 - 50 % load, and a table that
+    // runs full makes every further insert probe all of it — a 19.6 M-point multi-cloud target grid filled into the
+    // tables of the 4.4 M-point source grid built just before it on the same lane did not finish in minutes)
+    if (c->spec_tables && h.have_slots && (long long)n * 4 <= (long long)h.slots_n * 5) {
       // level tables of the previous cloud's sizes, cleared on the aux stream while the keys are made and sorted
       size_t total = 0;
       for (int l = 0; l < cl.view.nlevels; l++) total += (j.spec_slots[l] = h.slots[l]);
@@ -381,9 +402,9 @@ static int build_keys(rgc_ctx* c, Cloud& cl, const unsigned char* raw, size_t st
   const GridGeom geom{v.inv_s0, v.bias, v.nbits};
   CK(c, cudaMemsetAsync(j.hist, 0, sizeof(uint32_t) * rs_scratch_words(n, passes), st));
   if (raw)
-    k_keys_hist<true><<<kBboxBlocks, 256, 0, st>>>(raw, stride, n, j.orig, j.d_slot, geom, cl.d_off, j.n_clouds, passes, j.keys_a, j.vals_a, j.hist);
+    launch_pdl(c, k_keys_hist<true>, dim3(kBboxBlocks), dim3(256), 0, st, raw, stride, n, j.orig, j.d_slot, geom, cl.d_off, j.n_clouds, passes, j.keys_a, j.vals_a, j.hist);
   else
-    k_keys_hist<false><<<kBboxBlocks, 256, 0, st>>>(nullptr, 0, n, j.orig, nullptr, geom, cl.d_off, j.n_clouds, passes, j.keys_a, j.vals_a, j.hist);
+    launch_pdl(c, k_keys_hist<false>, dim3(kBboxBlocks), dim3(256), 0, st, nullptr, 0, n, j.orig, nullptr, geom, cl.d_off, j.n_clouds, passes, j.keys_a, j.vals_a, j.hist);
   CKL(c);
   c->mark("build: keys + histograms");
   j.stage = 3;
@@ -412,7 +433,7 @@ static int build_passes(rgc_ctx* c, Cloud& cl) {
     CK(c, cudaStreamWaitEvent(cst, cl.ev[5], 0));
   }
   CK(c, cudaMemsetAsync(j.d_counts, 0, 4 * (kMaxLevels + 1), cst));
-  k_count_cells<<<div_up(n, 256), 256, 0, cst>>>(j.kin, n, v.nlevels, j.d_counts, j.hist + 8, reinterpret_cast<uint32_t*>(j.d_slot + 6 * kBboxBlocks));
+  launch_pdl(c, k_count_cells, dim3(div_up(n, 256)), dim3(256), 0, cst, j.kin, n, v.nlevels, j.d_counts, j.hist + 8, reinterpret_cast<uint32_t*>(j.d_slot + 6 * kBboxBlocks));
   CKL(c);
   CK(c, cudaEventRecord(j.ready, cst));
   if (!j.spec_tables) c->mark("build: cell counts");
@@ -426,7 +447,7 @@ static int build_tables_spec(rgc_ctx* c, Cloud& cl) {
   TableSet ts;
   table_layout(cl, j.spec_slots, ts);
   CK(c, cudaStreamWaitEvent(st, j.cleared, 0));
-  k_build_tables<<<dim3(div_up(j.n, 256), cl.view.nlevels), 256, 0, st>>>(j.kin, j.n, ts);
+  launch_pdl(c, k_build_tables, dim3(div_up(j.n, 256), cl.view.nlevels), dim3(256), 0, st, j.kin, j.n, ts);
   CKL(c);
   CK(c, cudaEventRecord(cl.ev[1], st));
   c->mark("build: tables (speculative sizes)");
@@ -507,6 +528,7 @@ static int build_phase3(rgc_ctx* c, Cloud& cl) {
     rgc_ctx::GeomHint& h = c->geom_hint[j.lane];
     h.have_slots = h.valid && h.nbits == v.nbits && v.nlevels <= 20;
     for (int l = 0; h.have_slots && l < v.nlevels; l++) h.slots[l] = (uint32_t)slots[l];
+    h.slots_n = n;
   }
   bool tables_done = false;
   if (j.spec_tables) {
@@ -527,7 +549,7 @@ static int build_phase3(rgc_ctx* c, Cloud& cl) {
     TableSet ts;
     table_layout(cl, slots, ts);
     c->mark("build: host wait over, tables cleared");
-    k_build_tables<<<dim3(div_up(n, 256), v.nlevels), 256, 0, st>>>(j.kin, n, ts);
+    launch_pdl(c, k_build_tables, dim3(div_up(n, 256), v.nlevels), dim3(256), 0, st, j.kin, n, ts);
     CKL(c);
     c->mark("build: tables");
     CK(c, cudaEventRecord(cl.ev[1], st));
@@ -720,7 +742,7 @@ static int launch_knn_self(rgc_ctx* c, const GridView& v, int n, int k, int* nbr
   // than 32 queries can share).  Dense maps keep the tile kernel (2.6x fewer instructions per query there).
   // (an explicit deferral threshold — rgc_debug_set_knn_defer / RGC_KNN_DEFER, the tests' way of forcing either kernel — keeps the tile path)
   if (!tiles && k <= 32 && n <= RGC_KNN_ALLWARP_MAX && c->knn_defer < 0) {
-    k_knn_warp<<<std::min(div_up(n, KW_WARPS), 148 * RGC_KW_MINB), KW_WARPS * 32, 0, c->stream>>>(v, n, k, nullptr, nullptr, nullptr, 0, nbr, nullptr, nullptr, 0);
+    launch_pdl(c, k_knn_warp, dim3(std::min(div_up(n, KW_WARPS), 148 * RGC_KW_MINB)), dim3(KW_WARPS * 32), 0, c->stream, v, n, k, nullptr, nullptr, nullptr, 0, nbr, nullptr, nullptr, 0);
     CKL(c);
     return RGC_OK;
   }
@@ -728,10 +750,10 @@ static int launch_knn_self(rgc_ctx* c, const GridView& v, int n, int k, int* nbr
   int* dq = (int*)tmp.get(sizeof(int) * (size_t)(ntiles + 1));  // [0] = count, [1..] = tile ids
   if (!dq) FAIL(c, RGC_ERR_NOMEM, "device allocation failed (knn defer list)");
   CK(c, cudaMemsetAsync(dq, 0, sizeof(int), c->stream));
-  k_knn_tile<<<div_up(ntiles, KT_WARPS), KT_WARPS * 32, smem, c->stream>>>(v, n, k, n_seeds, defer, dq, dq + 1, nbr, tiles, ntiles);
+  launch_pdl(c, k_knn_tile, dim3(div_up(ntiles, KT_WARPS)), dim3(KT_WARPS * 32), smem, c->stream, v, n, k, n_seeds, defer, dq, dq + 1, nbr, tiles, ntiles);
   CKL(c);
   if (defer != INT_MAX) {
-    k_knn_warp<<<std::min(div_up(n, KW_WARPS), 148 * RGC_KW_MINB), KW_WARPS * 32, 0, c->stream>>>(v, n, k, dq, dq + 1, nullptr, 0, nbr, tiles, nullptr, 0);
+    launch_pdl(c, k_knn_warp, dim3(std::min(div_up(n, KW_WARPS), 148 * RGC_KW_MINB)), dim3(KW_WARPS * 32), 0, c->stream, v, n, k, dq, dq + 1, nullptr, 0, nbr, tiles, nullptr, 0);
     CKL(c);
   }
   return RGC_OK;
@@ -774,11 +796,11 @@ static int launch_covariance(rgc_ctx* c, cudaStream_t st, const float4* pts, con
   if (k > 32)
     k_covariance_any<<<grid, kThreads, 0, st>>>(pts, nbr, n_stride, grid_threads, k, method, cov);
   else if (k == 20 && full)
-    k_covariance<20, true><<<grid, kThreads, smem20, st>>>(pts, nbr, n_stride, k, method, cov, qlist, qcount);
+    launch_pdl(c, k_covariance<20, true>, dim3(grid), dim3(kThreads), smem20, st, pts, nbr, n_stride, k, method, cov, qlist, qcount);
   else if (k <= 20)
-    k_covariance<20, false><<<grid, kThreads, smem20, st>>>(pts, nbr, n_stride, k, method, cov, qlist, qcount);
+    launch_pdl(c, k_covariance<20, false>, dim3(grid), dim3(kThreads), smem20, st, pts, nbr, n_stride, k, method, cov, qlist, qcount);
   else
-    k_covariance<32, false><<<grid, kThreads, smem32, st>>>(pts, nbr, n_stride, k, method, cov, qlist, qcount);
+    launch_pdl(c, k_covariance<32, false>, dim3(grid), dim3(kThreads), smem32, st, pts, nbr, n_stride, k, method, cov, qlist, qcount);
   CKL(c);
   return RGC_OK;
 }
@@ -1133,11 +1155,11 @@ static int gicp_linearize_launch(rgc_reg* r, const double* T, int want, const in
   const int corr_blocks = div_up(r->src.n * spread, kThreads);
   if (ce.on) {
     const int ce_blocks = reduce_grid(r->src.n);
-    k_trial_step<<<ce_blocks + corr_blocks, kThreads, 0, c->stream>>>(r->tgt.view, r->src.sorted, r->src.n, spread, Tf, thr2, r->slab, hint, corr, sqd,
+    launch_pdl(c, k_trial_step, dim3(ce_blocks + corr_blocks), dim3(kThreads), 0, c->stream, r->tgt.view, r->src.sorted, r->src.n, spread, Tf, thr2, r->slab, hint, corr, sqd,
                                                                       lazy ? r->tgt.cov_state : nullptr, r->need_list, r->need_count, ce_blocks, Td, r->maha,
                                                                       r->partials, c->d_ticket, ce.result, ce.done);
   } else {
-    k_correspond<<<corr_blocks, kThreads, 0, c->stream>>>(r->tgt.view, r->src.sorted, r->src.n, spread, Tf, thr2, r->slab, hint, corr, sqd,
+    launch_pdl(c, k_correspond, dim3(corr_blocks), dim3(kThreads), 0, c->stream, r->tgt.view, r->src.sorted, r->src.n, spread, Tf, thr2, r->slab, hint, corr, sqd,
                                                           lazy ? r->tgt.cov_state : nullptr, r->need_list, r->need_count);
   }
   CKL(c);
@@ -1149,7 +1171,7 @@ static int gicp_linearize_launch(rgc_reg* r, const double* T, int want, const in
     // (every source point a new target point) and read the real count from the device: nothing here
     // makes the host wait.  After the first linearize of an align the list is nearly empty.
     const int k = r->tgt.cov_k, method = r->tgt.cov_method, cap = r->cap_src, n_t = r->tgt.n;
-    k_knn_warp<<<std::min(div_up(r->src.n, KW_WARPS), 148 * RGC_KW_MINB), KW_WARPS * 32, 0, c->stream>>>(r->tgt.view, n_t, k, r->need_count, nullptr, r->need_list, cap, r->need_nbr, nullptr, nullptr, 0);
+    launch_pdl(c, k_knn_warp, dim3(std::min(div_up(r->src.n, KW_WARPS), 148 * RGC_KW_MINB)), dim3(KW_WARPS * 32), 0, c->stream, r->tgt.view, n_t, k, r->need_count, nullptr, r->need_list, cap, r->need_nbr, nullptr, nullptr, 0);
     CKL(c);
     c->mark("lm: on-demand k_knn_warp");
     TRY(launch_covariance(c, c->stream, r->tgt.sorted, r->need_nbr, cap, r->src.n, k, n_t >= k, method, r->tgt.cov, r->need_list, r->need_count));
@@ -1157,7 +1179,7 @@ static int gicp_linearize_launch(rgc_reg* r, const double* T, int want, const in
     if (c->profile) CK(c, cudaEventRecord(c->evk[3], c->stream));
   }
   TRY(join_side(c));  // the source covariances (lane 1) are first read here: reg_ready joined the source's build only
-  k_linearize<<<reduce_grid(r->src.n), kThreads, 0, c->stream>>>(r->tgt.sorted, r->src.sorted, r->src.cov, r->tgt.cov, r->src.n, Td, want, corr, maha, r->partials,
+  launch_pdl(c, k_linearize, dim3(reduce_grid(r->src.n)), dim3(kThreads), 0, c->stream, r->tgt.sorted, r->src.sorted, r->src.cov, r->tgt.cov, r->src.n, Td, want, corr, maha, r->partials,
                                                                      c->d_ticket, result, reg_next_done(r), lazy ? r->need_count : nullptr);
   CKL(c);
   c->mark("lm: k_linearize");
@@ -1224,7 +1246,7 @@ static int reg_compute_error(rgc_reg* r, const double* T, double* err, bool ahea
     ce.done = reg_next_done(r);
     TRY(gicp_linearize_launch(r, T, 1, r->corr, r->corr2, r->sqd2, r->maha2, reg_spec_ptr(r), ce));
   } else {
-    k_compute_error<<<reduce_grid(r->src.n), kThreads, 0, c->stream>>>(r->tgt.sorted, r->src.sorted, r->src.n, Td, r->corr, r->maha, r->partials,
+    launch_pdl(c, k_compute_error, dim3(reduce_grid(r->src.n)), dim3(kThreads), 0, c->stream, r->tgt.sorted, r->src.sorted, r->src.n, Td, r->corr, r->maha, r->partials,
                                                                            c->d_ticket, reg_result_ptr(r), reg_next_done(r));
     CKL(c);
     if (c->profile) CK(c, cudaEventRecord(c->evk[1], c->stream));

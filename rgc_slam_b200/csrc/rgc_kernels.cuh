@@ -274,6 +274,7 @@ template <bool INGEST>
 __global__ void __launch_bounds__(256) k_keys_hist(const unsigned char* __restrict__ raw, size_t stride, int n, float4* pts, float* __restrict__ bbox_partials,
                                                    GridGeom g, const int* __restrict__ cloud_off, int n_clouds, int passes, uint64_t* __restrict__ keys,
                                                    uint32_t* __restrict__ vals, uint32_t* __restrict__ scratch) {
+  pdl_enter();
   __shared__ uint32_t h[RS_MAX_PASSES * 256];
   for (int i = threadIdx.x; i < passes * 256; i += 256) h[i] = 0;
   __syncthreads();
@@ -322,6 +323,7 @@ template <bool LAST_GATHER>
 __global__ void __launch_bounds__(256) k_rs_onesweep(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint64_t* __restrict__ keys_out,
                                                      uint32_t* __restrict__ vals_out, uint32_t* scratch, int pass, int n, int nblk,
                                                      const float4* __restrict__ pts, float4* __restrict__ sorted, int* __restrict__ inv) {
+  pdl_enter();
   __shared__ uint32_t cnt[8][256];
   __shared__ uint32_t digit_base[256];
   __shared__ uint32_t s_tile;
@@ -461,6 +463,7 @@ __global__ void __launch_bounds__(256) k_gather_sorted(const float4* __restrict_
 // finish publishes the counters, followed by the radix sort's error word, in mapped pinned host memory.
 __global__ void __launch_bounds__(256) k_count_cells(const uint64_t* __restrict__ keys, int n, int nlevels, uint32_t* __restrict__ counts,
                                                      const uint32_t* __restrict__ sort_err, uint32_t* __restrict__ host_out) {
+  pdl_enter();
   __shared__ uint32_t c[kMaxLevels];
   __shared__ bool is_last;
   if (threadIdx.x < kMaxLevels) c[threadIdx.x] = 0;
@@ -501,7 +504,12 @@ struct TableSet {
 // this cloud's are known) can be: the host sees the real counts a moment later and rebuilds it (build_phase3).
 __device__ __forceinline__ GridSlot* slot_insert_or_find(GridSlot* tab, uint32_t mask, uint32_t shift, uint64_t key) {
   uint32_t h = slot_of(key, shift);
-  for (uint32_t probes = 0; probes <= mask; probes++) {
+  // bounded walk: tables are sized for <= 50 % load (<= 70 % when filled with the previous cloud's sizes, checked by
+  // build_phase3 against the real cell counts), where a linear-probing cluster of 2048 slots does not occur
+  // (P ~ exp(-0.057 L)); the bound only keeps a speculative fill of a table that turns out too small — which
+  // build_phase3 then throws away — from probing the whole table once per insert
+  const uint32_t max_probes = mask < 2047u ? mask : 2047u;
+  for (uint32_t probes = 0; probes <= max_probes; probes++) {
     unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long*>(&tab[h].key), (unsigned long long)kEmptyKey, (unsigned long long)key);
     // the top byte of a live key word collects the occupied-children bits while the table is being built
     if (prev == kEmptyKey || (prev & kKeyMask) == key) return &tab[h];
@@ -516,6 +524,7 @@ __device__ __forceinline__ GridSlot* slot_insert_or_find(GridSlot* tab, uint32_t
 // its parent's occupied-children mask (insert-or-find: whoever comes first creates the parent's slot) —
 // this used to be a second kernel over the finished tables (k_child_masks, 13 us on the 500k-point submap).
 __global__ void __launch_bounds__(256) k_build_tables(const uint64_t* __restrict__ keys, int n, TableSet ts) {
+  pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int l = blockIdx.y;
   if (i >= n) return;
@@ -634,6 +643,7 @@ __device__ __forceinline__ float warp_min(float v) {
 
 __global__ void __launch_bounds__(KT_WARPS * 32) k_knn_tile(GridView g, int n, int k, int n_seeds, int defer_cands, int* __restrict__ defer_count, int* __restrict__ defer_tiles,
                                                            int* __restrict__ out_idx, const TileDesc* __restrict__ tiles, int ntiles) {
+  pdl_enter();
   extern __shared__ __align__(16) unsigned char tile_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long dbg_t0 = clock64();
@@ -910,6 +920,7 @@ __device__ __forceinline__ unsigned long long shfl64_up1(unsigned long long v) {
 __global__ void __launch_bounds__(KW_WARPS * 32, RGC_KW_MINB) k_knn_warp(GridView g, int n, int k, const int* __restrict__ defer_count, const int* __restrict__ defer_tiles,
                                                            const int* __restrict__ qlist, int out_stride, int* __restrict__ out_idx,
                                                            const TileDesc* __restrict__ tiles, const int* __restrict__ cloud_off, int n_clouds) {
+  pdl_enter();
   __shared__ TileNode stacks[KW_WARPS][KW_STACK];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   TileNode* stack = stacks[warp];
@@ -1180,6 +1191,7 @@ __global__ void __launch_bounds__(KW_WARPS * 32, RGC_KW_MINB) k_knn_warp(GridVie
 template <int KCAP, bool FULL>
 __global__ void __launch_bounds__(kThreads, RGC_COV_MINB) k_covariance(const float4* __restrict__ pts, const int* __restrict__ nbr, int n, int k, int method,
                                                             double* __restrict__ cov, const int* __restrict__ qlist, const int* __restrict__ qcount) {
+  pdl_enter();
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (qlist ? *qcount : n)) return;
   // all k index loads first (coalesced, k-major), then the point gathers in batches of kBatch:
@@ -1513,6 +1525,7 @@ __device__ __forceinline__ void correspond_query(const GridView& tgt, const floa
 __global__ void __launch_bounds__(kThreads, RGC_CORR_MINB) k_correspond(GridView tgt, const float4* __restrict__ src, int n_src, int spread, RtF Tf, float thr2, Slab slab,
                                                             const int* hint, int* corr, float* __restrict__ sqd, int* __restrict__ need_state,
                                                             int* __restrict__ need_list, int* __restrict__ need_count) {
+  pdl_enter();
   correspond_query(tgt, src, n_src, spread, Tf, thr2, slab, hint, corr, sqd, need_state, need_list, need_count, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
@@ -1630,6 +1643,7 @@ __global__ void __launch_bounds__(kThreads, RGC_LIN_MINB) k_linearize(const floa
                                                            const double* __restrict__ tgt_cov, int n_src, Rt Td, int want_hb, const int* __restrict__ corr,
                                                            double* __restrict__ maha, double* __restrict__ partials, unsigned int* __restrict__ ticket,
                                                            double* __restrict__ result, DoneFlag done, int* __restrict__ zero_me) {
+  pdl_enter();
   double acc[kLinN];
 #pragma unroll
   for (int j = 0; j < kLinN; j++) acc[j] = 0.0;
@@ -1706,6 +1720,7 @@ __global__ void __launch_bounds__(kThreads) k_compute_error(const float4* __rest
                                                             const int* __restrict__ corr, const double* __restrict__ maha,
                                                             double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ result,
                                                             DoneFlag done) {
+  pdl_enter();
   double acc[1] = {0.0};
   compute_error_points(tgt_pts, src, corr, maha, Td, 0, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, n_src, acc);
   grid_reduce<1>(acc, partials, ticket, result, done);
@@ -1722,6 +1737,7 @@ __global__ void __launch_bounds__(kThreads, RGC_CORR_MINB) k_trial_step(GridView
                                                             int* __restrict__ need_list, int* __restrict__ need_count, int ce_blocks, Rt Td,
                                                             const double* __restrict__ ce_maha, double* __restrict__ partials, unsigned int* __restrict__ ticket,
                                                             double* __restrict__ ce_result, DoneFlag ce_done) {
+  pdl_enter();
   if ((int)blockIdx.x < ce_blocks) {
     double acc[1] = {0.0};
     compute_error_points(reinterpret_cast<const float4*>(tgt.pts), src, hint, ce_maha, Td, 0, blockIdx.x * blockDim.x + threadIdx.x, ce_blocks * blockDim.x, n_src, acc);

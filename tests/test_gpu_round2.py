@@ -441,10 +441,23 @@ def test_speculative_table_sizes_hits_and_misses(rgc, orc):
     s1 = stats()
     assert s1[0] >= s0[0] + 2, "tables are not being filled speculatively"
     assert s1[1] == s0[1], "similar clouds must keep the speculative tables"
-    check(cloud(40000))  # > 10x the cells: far over the 70 % load the check tolerates (some levels overflow outright)
-    s2 = stats()
-    assert s2[1] >= s1[1] + 1, "an overfull speculative table was not detected"
-    check(cloud(3000))   # oversized tables are fine; the hint follows the latest cloud
+    check(cloud(40000))  # far more points than the cloud the sizes were made for: they are not even tried (a table that
+    s2 = stats()         # runs full makes every further insert probe all of it)
+    assert s2 == s1, "a much larger cloud must not be filled into the previous cloud's tables"
+
+    def clustered(n):    # same extent (eight corner points), but nearly all points in a handful of cells
+        P = np.ones((n, 4), np.float32)
+        P[:, :3] = rng.normal(0, 0.003, (n, 3))
+        P[:8, :3] = np.array([[sx, sy, sz] for sx in (-20, 20) for sy in (-20, 20) for sz in (-20, 20)], np.float32)
+        return P
+
+    check(clustered(3000))  # oversized tables are fine; the hint follows the latest cloud
+    check(clustered(3000))
+    s3 = stats()
+    check(cloud(3000))   # as many points, > 10x the cells: far over the 70 % load the check tolerates (levels overflow outright)
+    s4 = stats()
+    assert s4[0] >= s3[0] + 1 and s4[1] >= s3[1] + 1, "an overfull speculative table was not detected"
+    check(cloud(3000))
     check(cloud(3000))
 
 
