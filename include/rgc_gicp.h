@@ -207,9 +207,13 @@ int rgc_reg_set_target_slab(rgc_reg* reg, const void* points, size_t n, size_t s
 
 /* Cross-rank sum of the partial (err, H, b).  Preferred: a communicator owned by the library — the partial sums
  * of linearize (29 doubles), compute_error (1), the two together when the LM loop issues them back to back (30) and
- * fitness (2) are summed by ONE ncclAllReduce on the context's stream, moved to the host result area by a
- * one-block kernel and picked up by the host's poll: no host code runs between the reduction kernels and the
- * totals, and every rank takes identical LM steps.  rank 0 calls rgc_comm_unique_id and hands the 128 bytes to the
+ * fitness (2) are summed by ONE launch on the context's stream and picked up by the host's poll: no host code runs
+ * between the reduction kernels and the totals, and every rank takes identical LM steps.  Transport: each rank's
+ * 1-block kernel stores its partials into a mailbox on EVERY rank (device memory mapped through CUDA IPC, plain
+ * stores over NVLink, the call's sequence number packed into every word), polls its own mailbox for the other
+ * ranks' words, adds the partials in rank order (bit-identical totals everywhere) and writes them to the host result area (rgc_comm_transport() == 1).  If
+ * the mailboxes cannot be mapped on every rank (no peer access, world > 16, RGC_NO_P2P=1) the same sums are one
+ * ncclAllReduce + a publishing kernel (rgc_comm_transport() == 0).  rank 0 calls rgc_comm_unique_id and hands the 128 bytes to the
  * other ranks by any side channel (torch.distributed, MPI, a file); every rank then calls rgc_comm_create
  * (collective).  libnccl.so.2 is opened at run time (RGC_NCCL_LIB overrides the name).                       */
 typedef struct rgc_comm rgc_comm;
@@ -217,6 +221,7 @@ int rgc_comm_unique_id(char* id128);
 int rgc_comm_create(rgc_ctx* ctx, const char* id128, int rank, int world, rgc_comm** out);
 int rgc_comm_destroy(rgc_comm* comm);
 int rgc_comm_info(const rgc_comm* comm, int* rank, int* world, uint64_t* n_allreduce, int* nccl_version);
+int rgc_comm_transport(const rgc_comm* comm); /* 1 = peer-memory mailboxes (k_peer_allreduce), 0 = ncclAllReduce */
 int rgc_reg_set_comm(rgc_reg* reg, rgc_comm* comm); /* NULL switches it off */
 /* mean latency (us, CUDA events) of `reps` back-to-back all-reduces of n doubles on the context's stream; collective */
 int rgc_comm_allreduce_us(rgc_comm* comm, int n_doubles, int reps, float* us);

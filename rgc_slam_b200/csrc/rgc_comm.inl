@@ -11,6 +11,7 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   ncclResult_t (*GetVersion)(int*) = nullptr;
@@ -36,6 +37,7 @@ static NcclApi* nccl_api() {
   api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
   api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
   api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+  api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
   api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
   api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
   api.GetVersion = (decltype(api.GetVersion))sym("ncclGetVersion");
@@ -51,15 +53,103 @@ struct rgc_comm {
   int rank = 0, world = 1;
   double* d_buf = nullptr;  // 64 doubles: where the reduction kernels put a rank's partial sums
   uint64_t n_allreduce = 0;
+  // all-reduce over peer memory (k_peer_allreduce): this rank's mailbox, every rank's mailbox as seen from here
+  bool p2p = false;
+  unsigned char* mailbox = nullptr;
+  void* opened[kPeerMax] = {};
+  PeerSet peers = {};
+  unsigned long long p2p_seq = 0;
 };
+constexpr size_t kMailboxBytes = sizeof(unsigned long long) * 2 * kPeerMax * 2 * kPeerSlot;  // mail[2][kPeerMax][2 * kPeerSlot]
 
-// partial sums -> sum over ranks (in place, on the context's stream)
-static int comm_allreduce(rgc_comm* m, int n_doubles) {
+static void comm_p2p_release(rgc_comm* m) {
+  for (int r = 0; r < kPeerMax; r++)
+    if (m->opened[r]) {
+      cudaIpcCloseMemHandle(m->opened[r]);
+      m->opened[r] = nullptr;
+    }
+  if (m->mailbox) cudaFree(m->mailbox);
+  m->mailbox = nullptr;
+  m->p2p = false;
+  cudaGetLastError();
+}
+
+// Map every rank's mailbox into this process (CUDA IPC; the handles travel through one ncclAllGather) — a collective,
+// part of rgc_comm_create.  The ranks then agree (all-reduce of a success word) on whether ALL of them got there:
+// the peer-memory all-reduce is used by everybody or by nobody (NCCL stays the transport otherwise, e.g. ranks on
+// GPUs without peer access, or RGC_NO_P2P=1).
+static int comm_p2p_setup(rgc_comm* m) {
   rgc_ctx* c = m->ctx;
+  NcclApi* api = nccl_api();
+  if (m->world < 2 || m->world > kPeerMax || !api->AllGather || std::getenv("RGC_NO_P2P")) return RGC_OK;
+  bool ok = true;
+  cudaIpcMemHandle_t mine;
+  std::memset(&mine, 0, sizeof(mine));
+  unsigned char* d_handles = nullptr;
+  ok = ok && cudaMalloc((void**)&m->mailbox, kMailboxBytes) == cudaSuccess;
+  ok = ok && cudaMemsetAsync(m->mailbox, 0, kMailboxBytes, c->stream) == cudaSuccess;  // ordered before the collectives below: every rank's
+                                                                                        // mailbox is clear before any peer can write into it
+  ok = ok && cudaIpcGetMemHandle(&mine, m->mailbox) == cudaSuccess;
+  const size_t hb = sizeof(cudaIpcMemHandle_t);
+  // the collectives below are entered by every rank whatever happened above
+  if (cudaMalloc((void**)&d_handles, hb * (size_t)m->world) != cudaSuccess) {
+    cudaGetLastError();
+    FAIL(c, RGC_ERR_NOMEM, "device allocation failed (IPC handles)");
+  }
+  CK(c, cudaMemcpyAsync(d_handles + hb * (size_t)m->rank, &mine, hb, cudaMemcpyHostToDevice, c->stream));
+  if (api->AllGather(d_handles + hb * (size_t)m->rank, d_handles, hb, ncclChar, m->comm, c->stream) != ncclSuccess) {
+    cudaFree(d_handles);
+    FAIL(c, RGC_ERR_CUDA, "ncclAllGather (IPC handles) failed");
+  }
+  std::vector<cudaIpcMemHandle_t> all((size_t)m->world);
+  CK(c, cudaMemcpyAsync(all.data(), d_handles, hb * (size_t)m->world, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  cudaFree(d_handles);
+  for (int r = 0; ok && r < m->world; r++) {
+    void* p = m->mailbox;
+    if (r != m->rank) {
+      ok = cudaIpcOpenMemHandle(&p, all[(size_t)r], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+      if (ok) m->opened[r] = p;
+    }
+    if (ok) m->peers.mail[r] = reinterpret_cast<unsigned long long*>(p);
+  }
+  cudaGetLastError();
+  // everybody or nobody (this all-reduce is also the barrier behind every rank's cleared mailbox)
+  const double mine_ok = ok ? 1.0 : 0.0;
+  double all_ok = 0.0;
+  CK(c, cudaMemcpyAsync(m->d_buf, &mine_ok, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (api->AllReduce(m->d_buf, m->d_buf, 1, ncclDouble, ncclMin, m->comm, c->stream) != ncclSuccess) FAIL(c, RGC_ERR_CUDA, "ncclAllReduce (IPC agreement) failed");
+  CK(c, cudaMemcpyAsync(&all_ok, m->d_buf, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  CK(c, cudaMemsetAsync(m->d_buf, 0, sizeof(double) * 64, c->stream));
+  if (all_ok == 1.0)
+    m->p2p = true;
+  else
+    comm_p2p_release(m);
+  return RGC_OK;
+}
+
+// partial sums -> sum over ranks (in place, on the context's stream); with `publish`, the first n_a totals also go to
+// dst_a, the next n_b to dst_b (the mapped host result area), followed by the completion word.  Over peer memory
+// this is ONE launch; over NCCL the caller publishes with k_publish.
+static int comm_allreduce(rgc_comm* m, int n_doubles, bool publish = false, int n_a = 0, double* dst_a = nullptr, int n_b = 0, double* dst_b = nullptr,
+                          DoneFlag done = DoneFlag{nullptr, 0ull}) {
+  rgc_ctx* c = m->ctx;
+  if (m->p2p) {
+    launch_pdl(c, k_peer_allreduce, dim3(1), dim3(64), 0, c->stream, m->d_buf, n_doubles, m->peers, m->rank, m->world, ++m->p2p_seq, publish ? n_a : 0,
+               publish ? dst_a : nullptr, publish ? n_b : 0, publish ? dst_b : nullptr, done);
+    CKL(c);
+    m->n_allreduce++;
+    return RGC_OK;
+  }
   NcclApi* api = nccl_api();
   const ncclResult_t rc = api->AllReduce(m->d_buf, m->d_buf, (size_t)n_doubles, ncclDouble, ncclSum, m->comm, c->stream);
   if (rc != ncclSuccess) FAIL(c, RGC_ERR_CUDA, std::string("ncclAllReduce: ") + (api->GetErrorString ? api->GetErrorString(rc) : "error"));
   m->n_allreduce++;
+  if (publish) {
+    k_publish<<<1, 64, 0, c->stream>>>(m->d_buf, n_a, dst_a, n_b, dst_b, done);
+    CKL(c);
+  }
   return RGC_OK;
 }
 
@@ -114,6 +204,16 @@ int rgc_comm_create(rgc_ctx* c, const char* id128, int rank, int world, rgc_comm
     }
   }
   CK(c, cudaStreamSynchronize(c->stream));
+  {
+    const int rc = comm_p2p_setup(m);
+    if (rc != RGC_OK) {
+      comm_p2p_release(m);
+      api->CommDestroy(m->comm);
+      cudaFree(m->d_buf);
+      delete m;
+      return rc;
+    }
+  }
   *out = m;
   return RGC_OK;
 }
@@ -122,6 +222,7 @@ int rgc_comm_destroy(rgc_comm* m) {
   if (!m) return RGC_OK;
   cudaSetDevice(m->ctx->device);
   cudaStreamSynchronize(m->ctx->stream);
+  comm_p2p_release(m);
   if (m->comm) nccl_api()->CommDestroy(m->comm);
   cudaFree(m->d_buf);
   delete m;
@@ -147,6 +248,8 @@ int rgc_comm_allreduce_us(rgc_comm* m, int n_doubles, int reps, float* us) {
   CK(c, cudaMemsetAsync(m->d_buf, 0, sizeof(double) * 64, c->stream));
   return RGC_OK;
 }
+
+int rgc_comm_transport(const rgc_comm* m) { return m ? (m->p2p ? 1 : 0) : RGC_ERR_INVALID; }
 
 int rgc_comm_info(const rgc_comm* m, int* rank, int* world, uint64_t* n_allreduce, int* nccl_version) {
   if (!m) return RGC_ERR_INVALID;

@@ -31,8 +31,6 @@
 
 using namespace rgc;
 
-#include "rgc_comm.inl"
-
 // Launch `kern` so that it may be scheduled while the kernel before it on `st` is still draining (programmatic
 // dependent launch).  Only for kernels that start with pdl_enter() (rgc_common.cuh); with c->pdl off (RGC_NO_PDL=1)
 // this is a plain launch.  Arguments are converted to the kernel's parameter types by cudaLaunchKernelEx.
@@ -50,6 +48,8 @@ static inline cudaError_t launch_pdl(const rgc_ctx* c, void (*kern)(KArgs...), d
   cfg.numAttrs = c->pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
+
+#include "rgc_comm.inl"
 
 // RGC_TRACE=1: wall-clock trace of the host side of the build pipeline (debug aid)
 static bool trace_on() {
@@ -926,12 +926,11 @@ static int reg_spin(rgc_ctx* c) {
 static int reg_finish_reduce(rgc_reg* r, int n_a, int n_b = 0) {
   rgc_ctx* c = r->ctx;
   if (r->comm) {
-    // one all-reduce of the n_a + n_b partial sums over NVLink, then a one-block kernel moves the totals into
-    // the mapped host result area and stores the completion word: no host involvement in between
-    TRY(comm_allreduce(r->comm, n_a + n_b));
+    // one all-reduce of the n_a + n_b partial sums over NVLink that also moves the totals into the mapped host result
+    // area and stores the completion word (k_peer_allreduce: one launch over peer memory; ncclAllReduce + k_publish
+    // where the ranks' mailboxes could not be mapped): no host involvement in between
     const DoneFlag done = c->spin_wait ? DoneFlag{c->d_seq, ++c->seq} : DoneFlag{nullptr, 0ull};
-    k_publish<<<1, 64, 0, c->stream>>>(r->comm->d_buf, n_a, c->d_result, n_b, c->d_result + kSpecSlot, done);
-    CKL(c);
+    TRY(comm_allreduce(r->comm, n_a + n_b, true, n_a, c->d_result, n_b, c->d_result + kSpecSlot, done));
     if (c->spin_wait) return reg_spin(c);
   } else if (r->reduce_fn) {
     if (n_b) FAIL(c, RGC_ERR_STATE, "look-ahead is not available with an all-reduce callback");

@@ -1837,6 +1837,70 @@ __global__ void __launch_bounds__(64) k_publish(const double* __restrict__ src, 
   __threadfence_system();
 }
 
+// ---- all-reduce + publish over NVLink peer memory (config C5), one launch per LM step.
+// Every rank owns a mailbox (device memory, mapped into the other ranks' address spaces through CUDA IPC):
+//   mail[parity][sender][2 * 64] 64-bit words, each = (sequence number << 32) | one 32-bit half of a double.
+// Flag-in-data, as in NCCL's low-latency protocol: an aligned 8-byte store is indivisible, so a word whose upper half
+// shows this call's sequence number carries this call's data — no fence between data and flag, one NVLink trip.
+// The block (a) stores the two halves of each of this rank's partial sums into slot [parity][rank] of EVERY rank's
+// mailbox (plain stores over NVLink), (b) polls its OWN mailbox until every sender's words show the sequence number,
+// (c) adds the world's partials in rank order — the same order on every rank, so all ranks get bit-identical totals
+// and take identical LM steps — and (d) writes the totals back in place and, when asked, into the mapped host result
+// area followed by the completion word the host polls.  (A first version — data, __threadfence_system(), flag
+// word, fence — took 13.1 us per call on two GPUs against ncclAllReduce's 9.6 us.)
+// Two parities: a rank can be one call ahead of a peer (it starts call s + 1 once it has everybody's call-s
+// data, while a peer may still be reading its own copy of call s), never two.  A peer that never arrives turns
+// the totals into NaN after ~2 s instead of hanging the stream.
+constexpr int kPeerMax = 16;
+constexpr int kPeerSlot = 64;
+struct PeerSet {
+  unsigned long long* mail[kPeerMax];
+};
+__global__ void __launch_bounds__(64) k_peer_allreduce(double* __restrict__ buf, int n, PeerSet ps, int rank, int world, unsigned long long seq, int n_a,
+                                                       double* __restrict__ dst_a, int n_b, double* __restrict__ dst_b, DoneFlag done) {
+  pdl_enter();
+  const int t = threadIdx.x;
+  const size_t par_off = (size_t)(seq & 1ull) * kPeerMax * 2 * kPeerSlot;
+  const unsigned long long tag = (seq & 0xffffffffull) << 32;
+  if (t < n) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(buf[t]);
+    const unsigned long long w0 = tag | (bits & 0xffffffffull), w1 = tag | (bits >> 32);
+    const size_t at = par_off + (size_t)rank * 2 * kPeerSlot + 2 * t;
+    for (int r = 0; r < world; r++) {
+      volatile unsigned long long* m = ps.mail[r] + at;
+      m[0] = w0;
+      m[1] = w1;
+    }
+    const volatile unsigned long long* mine = ps.mail[rank] + par_off + 2 * t;
+    unsigned long long t0 = 0, now = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    double sum = 0.0;
+    bool ok = true;
+    for (int r = 0; r < world; r++) {
+      unsigned long long a, b;
+      for (;;) {
+        a = mine[(size_t)r * 2 * kPeerSlot];
+        b = mine[(size_t)r * 2 * kPeerSlot + 1];
+        if ((a & 0xffffffff00000000ull) == tag && (b & 0xffffffff00000000ull) == tag) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (now - t0 > 2000000000ull) {
+          ok = false;
+          break;
+        }
+      }
+      sum = dadd(sum, __longlong_as_double((long long)((a & 0xffffffffull) | (b << 32))));
+    }
+    if (!ok) sum = __longlong_as_double(0x7ff8000000000000ll);
+    buf[t] = sum;
+    if (dst_a && t < n_a) dst_a[t] = sum;
+    if (dst_b && t >= n_a && t < n_a + n_b) dst_b[t - n_a] = sum;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (t == 0 && done.flag) *reinterpret_cast<volatile unsigned long long*>(done.flag) = done.value;
+  __threadfence_system();
+}
+
 // config C5: the points of a raw cloud whose `axis` coordinate lies in [lo, hi) (a rank's slab + halo), kept in
 // input order: per-block counts -> k_vg_scan_blocks -> ordered scatter (+ the index of each kept point)
 constexpr int kSlabItems = 8;

@@ -111,8 +111,14 @@ class ShardedFastGICP(api.FastGICP):
             ver = C.c_int(0)
             L.rgc_comm_info(self._comm, None, None, None, C.byref(ver))
             v = ver.value
-            self.allreduce_kind = (f"ncclAllReduce (NCCL {v // 10000}.{(v // 100) % 100}.{v % 100}) issued by the library on its stream, "
-                                   "one per LM step (compute_error + look-ahead linearize summed together)")
+            L.rgc_comm_transport.argtypes = [C.c_void_p]
+            if L.rgc_comm_transport(self._comm) == 1:
+                self.allreduce_kind = ("k_peer_allreduce: one 1-block launch per LM step over NVLink peer memory (CUDA-IPC mailboxes on every rank; "
+                                       "store partials + sequence tag to all ranks, poll, sum in rank order, publish to the host) — compute_error + "
+                                       "look-ahead linearize summed together")
+            else:
+                self.allreduce_kind = (f"ncclAllReduce (NCCL {v // 10000}.{(v // 100) % 100}.{v % 100}) issued by the library on its stream, "
+                                       "one per LM step (compute_error + look-ahead linearize summed together)")
         elif self.world > 1:
             self._buf = torch.zeros(32, dtype=torch.float64, device=f"cuda:{self.ctx.device}")
             self._ext = torch.cuda.ExternalStream(self.ctx.stream, device=self.ctx.device)
