@@ -489,3 +489,32 @@ def test_k_above_32(rgc, orc, small_pair, k):
         o.setInputTarget(tgt)
         To = o.align()
         _same_run(g, o, T, To)
+
+
+def test_programmatic_dependent_launch_changes_nothing(rgc, scan_pair):
+    """The kernels of the build and LM chains start with `griddepcontrol.wait` (pdl_enter, rgc_common.cuh) and are
+    launched with programmatic stream serialization (launch_pdl, rgc_gicp.cu): a grid's blocks may become resident
+    while its predecessor drains, but run only once it has completed.  RGC_NO_PDL=1 (read when a context is created)
+    launches the same kernels plainly; pose, Hessian, iteration counts and neighbour lists must not differ by a bit."""
+    src, tgt, _ = scan_pair
+
+    def run(ctx):
+        g = rgc.FastGICP(ctx)
+        g.setInputTarget(tgt)
+        g.setInputSource(src)
+        T = g.align(np.eye(4, dtype=np.float32))
+        r = g.last_result
+        out = (T.copy(), g.getFinalHessian().copy(), (r["iterations"], r["n_linearize"], r["n_compute_error"]), g.getFitnessScore())
+        g = None
+        return out
+
+    ctx_pdl = rgc.Context(0)
+    os.environ["RGC_NO_PDL"] = "1"
+    try:
+        ctx_plain = rgc.Context(0)
+    finally:
+        del os.environ["RGC_NO_PDL"]
+    a, b = run(ctx_pdl), run(ctx_plain)
+    ctx_pdl.close()
+    ctx_plain.close()
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2] and a[3] == b[3]
