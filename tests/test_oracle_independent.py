@@ -563,3 +563,80 @@ def test_feature_path_equals_the_python_restatement(scene, traj, beams, az, fram
     assert np.allclose(a[:3], b[:3], atol=1e-9) and np.allclose(a[9:], b[9:], atol=1e-9)
     for o_ in (3, 6):                                                             # eigenvectors 1, 2: defined up to sign
         assert min(np.abs(a[o_:o_ + 3] - b[o_:o_ + 3]).max(), np.abs(a[o_:o_ + 3] + b[o_:o_ + 3]).max()) < 1e-7
+
+
+def rings_restated(scan, n_scans, min_range=0.5, max_range=80.0, scan_period=0.1):
+    """scanRegistration.cpp:110-230 + :732-763: NaN removal, range gate, ring id from the elevation, relative time from the
+    azimuth (startOri / endOri / halfPassed), ring buckets concatenated in ring order.  Returns (src_index, ring, relTime)."""
+    P = scan.astype(F32)
+    keep = []
+    th1, th2 = F32(min_range), F32(max_range)
+    for i, (x, y, z, _) in enumerate(P):                                           # removeClosedPointCloud (:732-763)
+        if not (np.isfinite(x) and np.isfinite(y) and np.isfinite(z)):
+            continue                                                              # pcl::removeNaNFromPointCloud (:112)
+        dis = (x * x + y * y) + z * z
+        if dis < th1 * th1 or dis > th2 * th2:
+            continue
+        if x < 0 and abs(float(y)) < 0.5:
+            continue
+        keep.append(i)
+    Q = P[keep]
+    n = len(Q)
+    pi = np.pi
+    start = F32(-np.arctan2(Q[0, 1], Q[0, 0]))                                    # :117-118 (float)
+    end = F32(np.float64(F32(-np.arctan2(Q[n - 1, 1], Q[n - 1, 0]))) + 2 * pi)
+    if float(end - start) > 3 * pi:                                               # :120-127
+        end = F32(float(end) - 2 * pi)
+    elif float(end - start) < pi:
+        end = F32(float(end) + 2 * pi)
+    half = False
+    buckets = [[] for _ in range(n_scans)]
+    for k in range(n):
+        x, y, z = Q[k, 0], Q[k, 1], Q[k, 2]
+        va = F32(float(np.arctan(z / np.sqrt(x * x + y * y))) * 180 / pi)          # :141
+        if n_scans == 16:                                                         # :144-178
+            sid = int(float(va + F32(15)) / 2 + 0.5)
+        elif n_scans == 32:
+            sid = int((float(va) + 92.0 / 3.0) * 3.0 / 4.0)
+        else:
+            sid = int((2 - float(va)) * 3.0 + 0.5) if float(va) >= -8.83 else n_scans // 2 + int((-8.83 - float(va)) * 2.0 + 0.5)
+            if float(va) > 2 or float(va) < -24.33 or sid > 50:
+                continue
+        if sid > n_scans - 1 or sid < 0:
+            continue
+        ori = float(F32(-np.arctan2(y, x)))                                       # :186
+        s, e = float(start), float(end)
+        if not half:                                                              # :187-205 (float ori, double pi terms)
+            if ori < s - pi / 2:
+                ori = float(F32(ori + 2 * pi))
+            elif ori > s + pi * 3 / 2:
+                ori = float(F32(ori - 2 * pi))
+            if float(F32(ori) - start) > pi:
+                half = True
+        else:
+            ori = float(F32(ori + 2 * pi))
+            if ori < e - pi * 3 / 2:
+                ori = float(F32(ori + 2 * pi))
+            elif ori > e + pi / 2:
+                ori = float(F32(ori - 2 * pi))
+        rel = F32(F32(ori) - start) / (end - start)                               # :208, float
+        buckets[sid].append((keep[k], sid, float(rel)))
+    flat = [t for b in buckets for t in b]
+    return np.array([t[0] for t in flat]), np.array([t[1] for t in flat]), np.array([t[2] for t in flat]), scan_period
+
+
+@pytest.mark.parametrize("beams,az", [(16, 1800), (32, 900)])
+def test_ring_assignment_equals_the_python_restatement(scene, traj, beams, az):
+    """which points survive, their ring and their order are integers and must be equal; the relative time goes through
+    atan2 in float (libm there, numpy here) and is compared to 2e-6"""
+    scan = synth.lidar_scan(scene, traj[25], n_beams=beams, n_azimuth=az, seed=77)
+    scan[::997, 0] = np.nan                                                       # a few invalid returns
+    f = orc.extract_features(scan, n_scans=beams)
+    src_index, ring, rel, period = rings_restated(scan, beams)
+    assert np.array_equal(f["src_index"], src_index)
+    inten = f["cloud"][:, 3].astype(np.float64)
+    assert np.abs(inten - (ring + period * rel)).max() < 2e-6
+    assert rel.min() > -0.5 and rel.max() < 1.5
+    sizes = np.bincount(ring, minlength=beams)
+    ends = np.cumsum(sizes)
+    assert np.array_equal(f["scan_start"], ends - sizes + 5) and np.array_equal(f["scan_end"], ends - 5)   # :221-228
