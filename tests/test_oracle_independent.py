@@ -640,3 +640,21 @@ def test_ring_assignment_equals_the_python_restatement(scene, traj, beams, az):
     sizes = np.bincount(ring, minlength=beams)
     ends = np.cumsum(sizes)
     assert np.array_equal(f["scan_start"], ends - sizes + 5) and np.array_equal(f["scan_end"], ends - 5)   # :221-228
+
+
+@pytest.mark.parametrize("max_range", [np.finfo(np.float64).max, 0.05])
+def test_fitness_score_equals_numpy(tiny_pair, max_range):
+    """pcl::Registration::getFitnessScore(max_range): the source transformed by the final transformation (float),
+    1-NN squared distance to the target, mean over the distances <= max_range (callers RGC_odometer.cpp:1010,
+    RGC_mapping.cpp:2070)."""
+    src, tgt = tiny_pair
+    o = orc.FastGICP(max_iterations=5)
+    o.setInputTarget(tgt)
+    o.setInputSource(src)
+    T = o.align()
+    q = (src.astype(F32) @ T.astype(F32).T)[:, :3]
+    d, _ = cKDTree(tgt[:, :3].astype(np.float64)).query(q.astype(np.float64), k=1)
+    d2 = d * d
+    sel = d2 <= max_range
+    assert sel.any() and (max_range > 1 or not sel.all())
+    assert abs(o.getFitnessScore(max_range) - d2[sel].mean()) <= 1e-5 * d2[sel].mean()   # float d2 there, double here
