@@ -249,6 +249,64 @@ int rgc_comm_allreduce_us(rgc_comm* m, int n_doubles, int reps, float* us) {
   return RGC_OK;
 }
 
+// Test hook: k_peer_allreduce with `world` ranks played by `world` streams of ONE device (every "rank" has its own mailbox
+// and buffer in the same address space, so no IPC is needed): `reps` back-to-back all-reduces of n doubles per rank.
+// in / out: [reps][world][n] host doubles; `published` (nullable): [reps][world][n], what each launch wrote through its
+// dst_a (first n_a values) / dst_b (the rest) pointers.  The kernels of one repetition wait for each other, so all of a
+// repetition's launches are issued before anything on the host blocks.
+int rgc_debug_peer_allreduce_selftest(rgc_ctx* c, int world, int n, int n_a, int reps, const double* in, double* out, double* published) {
+  if (!c || !in || !out || world < 1 || world > kPeerMax || n < 1 || n > kPeerSlot || n_a < 0 || n_a > n || reps < 1) return RGC_ERR_INVALID;
+  CK(c, cudaSetDevice(c->device));
+  const size_t per = (size_t)reps * world * kPeerSlot;
+  unsigned char* boxes = nullptr;
+  double *bufs = nullptr, *pub = nullptr;
+  std::vector<cudaStream_t> st((size_t)world, nullptr);
+  std::vector<double> h(per, 0.0);
+  auto cleanup = [&]() {
+    for (cudaStream_t s : st)
+      if (s) cudaStreamDestroy(s);
+    cudaFree(boxes);
+    cudaFree(bufs);
+    cudaFree(pub);
+    cudaGetLastError();
+  };
+  bool ok = cudaMalloc((void**)&boxes, kMailboxBytes * (size_t)world) == cudaSuccess && cudaMalloc((void**)&bufs, sizeof(double) * per) == cudaSuccess &&
+            cudaMalloc((void**)&pub, sizeof(double) * per) == cudaSuccess;
+  for (int r = 0; ok && r < world; r++) ok = cudaStreamCreateWithFlags(&st[(size_t)r], cudaStreamNonBlocking) == cudaSuccess;
+  if (!ok) {
+    cleanup();
+    FAIL(c, RGC_ERR_NOMEM, "allocation failed (peer all-reduce self-test)");
+  }
+  for (int rep = 0; rep < reps; rep++)
+    for (int r = 0; r < world; r++)
+      for (int t = 0; t < n; t++) h[((size_t)rep * world + r) * kPeerSlot + t] = in[((size_t)rep * world + r) * n + t];
+  cudaMemset(boxes, 0, kMailboxBytes * (size_t)world);
+  cudaMemset(pub, 0, sizeof(double) * per);
+  cudaMemcpy(bufs, h.data(), sizeof(double) * per, cudaMemcpyHostToDevice);
+  cudaDeviceSynchronize();
+  PeerSet ps = {};
+  for (int r = 0; r < world; r++) ps.mail[r] = reinterpret_cast<unsigned long long*>(boxes + kMailboxBytes * (size_t)r);
+  for (int rep = 0; rep < reps; rep++)
+    for (int r = 0; r < world; r++) {
+      double* b = bufs + ((size_t)rep * world + r) * kPeerSlot;
+      double* d = pub + ((size_t)rep * world + r) * kPeerSlot;
+      k_peer_allreduce<<<1, 64, 0, st[(size_t)r]>>>(b, n, ps, r, world, (unsigned long long)(rep + 1), n_a, d, n - n_a, d + n_a, DoneFlag{nullptr, 0ull});
+    }
+  cudaError_t e = cudaGetLastError();
+  for (int r = 0; r < world && e == cudaSuccess; r++) e = cudaStreamSynchronize(st[(size_t)r]);
+  auto fetch = [&](const double* dev, double* host) {
+    if (e == cudaSuccess) e = cudaMemcpy(h.data(), dev, sizeof(double) * per, cudaMemcpyDeviceToHost);
+    for (int rep = 0; rep < reps; rep++)
+      for (int r = 0; r < world; r++)
+        for (int t = 0; t < n; t++) host[((size_t)rep * world + r) * n + t] = h[((size_t)rep * world + r) * kPeerSlot + t];
+  };
+  fetch(bufs, out);
+  if (published) fetch(pub, published);
+  cleanup();
+  CK(c, e);
+  return RGC_OK;
+}
+
 int rgc_comm_transport(const rgc_comm* m) { return m ? (m->p2p ? 1 : 0) : RGC_ERR_INVALID; }
 
 int rgc_comm_info(const rgc_comm* m, int* rank, int* world, uint64_t* n_allreduce, int* nccl_version) {
