@@ -111,38 +111,8 @@ def test_linearize_and_compute_error_equal_the_4x4_numpy_restatement(tiny_pair, 
     assert abs(o.compute_error(T2) - n.compute_error(T2)) <= 1e-10 * abs(n.compute_error(T2))
 
 
-def far_guess(trial: int) -> np.ndarray:
-    """the same draws as tests/test_gpu_round2.py::far_guess (rotation U(20, 180) deg, translation U(+-5 m)^3)"""
-    rng = np.random.default_rng(0)
-    for _ in range(trial + 1):
-        ang = rng.uniform(20, 180)
-        axis = rng.normal(size=3)
-        axis /= np.linalg.norm(axis)
-        g = np.eye(4, dtype=np.float32)
-        g[:3, :3] = Rotation.from_rotvec(np.deg2rad(ang) * axis).as_matrix()
-        g[:3, 3] = rng.uniform(-5, 5, 3)
-    return g
-
-
-@pytest.mark.parametrize("case", ["near", "far"])
-def test_lm_steps_equal_the_numpy_restatement(tiny_pair, case):
-    """lsq_registration_impl.hpp:53-172 driven by the numpy linearize / compute_error above: the same number of
-    linearize / compute_error calls (i.e. the same accepted and REJECTED steps: the far guess is one of the cases the
-    GPU suite uses for the rho < 0 branch), iteration count, final pose and final Hessian as the oracle's align()."""
-    src, tgt = tiny_pair
-    if case == "near":
-        max_it, corr_dist = 8, np.finfo(np.float32).max
-        guess = np.eye(4, dtype=np.float32)
-        guess[:3, 3] = [0.2, 0.1, 0.0]
-    else:
-        max_it, corr_dist, guess = 30, 1.0, far_guess(3)
-    o = orc.FastGICP(max_iterations=max_it, corr_dist=corr_dist)
-    o.setInputTarget(tgt)
-    o.setInputSource(src)
-    o.linearize(np.eye(4), want_Hb=False)
-    n = NumpyGICP(src, tgt, o.getSourceCovariances(), o.getTargetCovariances(), corr_dist)
-    To = o.align(guess)
-
+def numpy_lm(n, guess, max_it):
+    """LsqRegistration::computeTransformation + step_lm + is_converged (lsq_registration_impl.hpp:53-172) over a NumpyGICP"""
     x0 = guess.astype(np.float64)                                              # :54
     lam, lam_factor, max_inner = -1.0, 1e-9, 10                                # :17-19, :56
     rot_eps, trans_eps = 2e-3, 5e-4                                            # :12-13
@@ -182,6 +152,42 @@ def test_lm_steps_equal_the_numpy_restatement(tiny_pair, case):
         if is_converged(delta):                                                # :74
             converged = True
             break
+    return x0, iters, converged, final_H, n_lin, n_ce
+
+
+def far_guess(trial: int) -> np.ndarray:
+    """the same draws as tests/test_gpu_round2.py::far_guess (rotation U(20, 180) deg, translation U(+-5 m)^3)"""
+    rng = np.random.default_rng(0)
+    for _ in range(trial + 1):
+        ang = rng.uniform(20, 180)
+        axis = rng.normal(size=3)
+        axis /= np.linalg.norm(axis)
+        g = np.eye(4, dtype=np.float32)
+        g[:3, :3] = Rotation.from_rotvec(np.deg2rad(ang) * axis).as_matrix()
+        g[:3, 3] = rng.uniform(-5, 5, 3)
+    return g
+
+
+@pytest.mark.parametrize("case", ["near", "far"])
+def test_lm_steps_equal_the_numpy_restatement(tiny_pair, case):
+    """lsq_registration_impl.hpp:53-172 driven by the numpy linearize / compute_error above: the same number of
+    linearize / compute_error calls (i.e. the same accepted and REJECTED steps: the far guess is one of the cases the
+    GPU suite uses for the rho < 0 branch), iteration count, final pose and final Hessian as the oracle's align()."""
+    src, tgt = tiny_pair
+    if case == "near":
+        max_it, corr_dist = 8, np.finfo(np.float32).max
+        guess = np.eye(4, dtype=np.float32)
+        guess[:3, 3] = [0.2, 0.1, 0.0]
+    else:
+        max_it, corr_dist, guess = 30, 1.0, far_guess(3)
+    o = orc.FastGICP(max_iterations=max_it, corr_dist=corr_dist)
+    o.setInputTarget(tgt)
+    o.setInputSource(src)
+    o.linearize(np.eye(4), want_Hb=False)
+    n = NumpyGICP(src, tgt, o.getSourceCovariances(), o.getTargetCovariances(), corr_dist)
+    To = o.align(guess)
+
+    x0, iters, converged, final_H, n_lin, n_ce = numpy_lm(n, guess, max_it)
     assert (n_lin, n_ce) == (o.last["n_linearize"], o.last["n_compute_error"])
     if case == "far":
         assert n_ce > n_lin, "this case is here for its rejected steps"
@@ -658,3 +664,57 @@ def test_fitness_score_equals_numpy(tiny_pair, max_range):
     sel = d2 <= max_range
     assert sel.any() and (max_range > 1 or not sel.all())
     assert abs(o.getFitnessScore(max_range) - d2[sel].mean()) <= 1e-5 * d2[sel].mean()   # float d2 there, double here
+
+
+@pytest.mark.parametrize("beams", [16, 32])
+def test_golden_feature_vectors_equal_the_python_chain(beams):
+    """tests/golden/features_small.npz (what the GPU suite is checked against) from the raw scan through the two Python
+    restatements above — ring assignment, then the feature pass — with no oracle code in between."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "features_small.npz"))
+    scan = z[f"scan{beams}"]
+    src_index, ring, rel, period = rings_restated(scan, beams)
+    assert np.array_equal(src_index, z[f"src_index{beams}"])
+    cloud = np.zeros((len(src_index), 4), F32)
+    cloud[:, :3] = scan[src_index, :3]
+    cloud[:, 3] = (ring + period * rel).astype(F32)
+    sizes = np.bincount(ring, minlength=beams)
+    ends = np.cumsum(sizes)
+    g = features_restated(cloud, scan[src_index, 3], ends - sizes + 5, ends - 5, beams)
+    for k in ("label", "inten_label", "neighbor_picked", "inten_neighbor_picked", "ground_marked", "curvature", "inten_curvature", "curvature2",
+              "corner_sharp", "surf_flat", "inten_sharp", "corner_less_sharp"):
+        assert np.array_equal(g[k], z[f"{k}{beams}"]), k
+    a, b = z[f"groundparam{beams}"], g["groundparam"]
+    assert np.allclose(a[:3], b[:3], atol=1e-9) and np.allclose(a[9:], b[9:], atol=1e-9)
+
+
+def test_golden_gicp_vectors_equal_the_numpy_chain():
+    """tests/golden/gicp_small.npz (what the GPU suite is checked against): covariances from the golden neighbour lists
+    with numpy's SVD (fast_gicp_impl.hpp:256-293, PLANE), then linearize and the LM loop of the numpy restatement."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "gicp_small.npz"))
+    src, tgt = z["src"], z["tgt"]
+
+    def plane_covs(P, idx):
+        out = np.zeros((len(P), 4, 4))
+        for i, nb in enumerate(idx):
+            X = P[nb].astype(np.float64)                                          # 4 x k matrix of neighbours, w = 1 (:256-259)
+            X = X - X.mean(axis=0)
+            C = X.T @ X / len(nb)                                                 # :262
+            U, _, Vt = np.linalg.svd(C[:3, :3])                                   # :273
+            out[i, :3, :3] = U @ np.diag([1.0, 1.0, 1e-3]) @ Vt                   # :274-276, :288-293
+        return out
+
+    idx_t, _ = orc.knn(tgt, tgt, 20)
+    assert np.array_equal(idx_t, z["knn_idx"])
+    idx_s, _ = orc.knn(src, src, 20)
+    ks = cKDTree(src[:, :3].astype(np.float64)).query(src[:, :3].astype(np.float64), k=20)[1]
+    assert (np.sort(ks, 1) == np.sort(idx_s, 1)).mean() > 0.999                   # the neighbour SETS, independently (ties aside)
+    n = NumpyGICP(src, tgt, plane_covs(src, idx_s), plane_covs(tgt, idx_t))
+    e, H, b = n.linearize(z["T_lin"].astype(np.float64))
+    assert np.array_equal(n.corr, z["corr"])
+    assert abs(e - z["lin_err"]) <= 1e-7 * abs(e)
+    assert np.abs(H - z["lin_H"]).max() <= 1e-7 * np.abs(H).max() and np.abs(b - z["lin_b"]).max() <= 1e-7 * np.abs(b).max()
+    x0, iters, converged, _, _, _ = numpy_lm(n, np.eye(4, dtype=np.float32), 64)
+    assert iters == int(z["iterations"]) and converged
+    assert np.abs(x0 - z["T_final"].astype(np.float64)).max() < 1e-6
