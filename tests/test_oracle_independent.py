@@ -695,22 +695,12 @@ def test_golden_gicp_vectors_equal_the_numpy_chain():
     z = np.load(os.path.join(os.path.dirname(__file__), "golden", "gicp_small.npz"))
     src, tgt = z["src"], z["tgt"]
 
-    def plane_covs(P, idx):
-        out = np.zeros((len(P), 4, 4))
-        for i, nb in enumerate(idx):
-            X = P[nb].astype(np.float64)                                          # 4 x k matrix of neighbours, w = 1 (:256-259)
-            X = X - X.mean(axis=0)
-            C = X.T @ X / len(nb)                                                 # :262
-            U, _, Vt = np.linalg.svd(C[:3, :3])                                   # :273
-            out[i, :3, :3] = U @ np.diag([1.0, 1.0, 1e-3]) @ Vt                   # :274-276, :288-293
-        return out
-
     idx_t, _ = orc.knn(tgt, tgt, 20)
     assert np.array_equal(idx_t, z["knn_idx"])
     idx_s, _ = orc.knn(src, src, 20)
     ks = cKDTree(src[:, :3].astype(np.float64)).query(src[:, :3].astype(np.float64), k=20)[1]
     assert (np.sort(ks, 1) == np.sort(idx_s, 1)).mean() > 0.999                   # the neighbour SETS, independently (ties aside)
-    n = NumpyGICP(src, tgt, plane_covs(src, idx_s), plane_covs(tgt, idx_t))
+    n = NumpyGICP(src, tgt, plane_covs_numpy(src, idx_s), plane_covs_numpy(tgt, idx_t))
     e, H, b = n.linearize(z["T_lin"].astype(np.float64))
     assert np.array_equal(n.corr, z["corr"])
     assert abs(e - z["lin_err"]) <= 1e-7 * abs(e)
@@ -718,3 +708,56 @@ def test_golden_gicp_vectors_equal_the_numpy_chain():
     x0, iters, converged, _, _, _ = numpy_lm(n, np.eye(4, dtype=np.float32), 64)
     assert iters == int(z["iterations"]) and converged
     assert np.abs(x0 - z["T_final"].astype(np.float64)).max() < 1e-6
+
+
+def plane_covs_numpy(P, idx):
+    """fast_gicp_impl.hpp:256-293 (PLANE) with numpy's SVD, from given neighbour lists"""
+    out = np.zeros((len(P), 4, 4))
+    for i, nb in enumerate(idx):
+        X = P[nb].astype(np.float64)
+        X = X - X.mean(axis=0)
+        U, _, Vt = np.linalg.svd((X.T @ X / len(nb))[:3, :3])
+        out[i, :3, :3] = U @ np.diag([1.0, 1.0, 1e-3]) @ Vt
+    return out
+
+
+class NumpyVGICP:
+    """FastVGICP's linearize / compute_error (fast_vgicp_impl.hpp:73-204) with the interface numpy_lm drives"""
+
+    def __init__(self, src, cov_src, vox, resolution, method):
+        self.src, self.cov_src, self.vox, self.res, self.method = src, cov_src, vox, resolution, method
+        self.T_lin = None
+
+    def linearize(self, T):
+        self.T_lin = T.copy()
+        e, H, b, self.ncorr = numpy_vgicp_linearize(self.src, self.cov_src, self.vox, self.res, self.method, T)
+        return e, H, b
+
+    def compute_error(self, T):
+        return numpy_vgicp_linearize(self.src, self.cov_src, self.vox, self.res, self.method, self.T_lin, T_err=T)[0]
+
+
+def test_golden_vgicp_vectors_equal_the_numpy_chain():
+    """tests/golden/vgicp_small.npz: voxel map, DIRECT1 / DIRECT7 linearize and the aligned pose from the numpy chain alone"""
+    import os
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    z, v = np.load(os.path.join(gold, "gicp_small.npz")), np.load(os.path.join(gold, "vgicp_small.npz"))
+    tgt = z["tgt"]
+    cov_t = plane_covs_numpy(tgt, z["knn_idx"])
+    vox = numpy_voxelmap(tgt, cov_t, 1.0, False)
+    keys = sorted(vox)
+    assert np.array_equal(np.array(keys), v["vox_coords"]) and np.array_equal([vox[k]["n"] for k in keys], v["vox_num"])
+    assert np.allclose([vox[k]["mean"][:3] for k in keys], v["vox_mean"], rtol=0, atol=1e-9)
+    got_cov = np.array([[vox[k]["cov"][0, 0], vox[k]["cov"][0, 1], vox[k]["cov"][0, 2], vox[k]["cov"][1, 1], vox[k]["cov"][1, 2], vox[k]["cov"][2, 2]] for k in keys])
+    assert np.allclose(got_cov, v["vox_cov"], rtol=0, atol=1e-9)
+    full_src = z["src"]
+    cov_s = plane_covs_numpy(full_src, orc.knn(full_src, full_src, 20)[0])
+    T = z["T_lin"].astype(np.float64)
+    for name, method in (("d1", orc.DIRECT1), ("d7", orc.DIRECT7)):
+        e, H, b, ncorr = numpy_vgicp_linearize(full_src, cov_s, vox, 1.0, method, T)
+        assert ncorr == int(v[f"{name}_ncorr"])
+        assert abs(e - v[f"{name}_err"]) <= 1e-7 * abs(e)
+        assert np.abs(H - v[f"{name}_H"]).max() <= 1e-7 * np.abs(H).max() and np.abs(b - v[f"{name}_b"]).max() <= 1e-7 * np.abs(b).max()
+    x0, iters, converged, _, _, _ = numpy_lm(NumpyVGICP(full_src, cov_s, vox, 1.0, orc.DIRECT1), np.eye(4, dtype=np.float32), 64)
+    assert converged and iters == int(v["d1_iterations"])
+    assert np.abs(x0 - v["d1_T"].astype(np.float64)).max() < 1e-6
